@@ -1,0 +1,267 @@
+/*
+ * spg_capi.h — C ABI of the B200-native node-removal path (libspg_b200.so).
+ *
+ * This is the drop-in boundary for the hot path that the reference enters through
+ *   GraphWrapperG2O::marginalizeNoOptimize()  (reference src/graph_wrapper_g2o.cpp:398-453)
+ *     -> VertexRemover::remove(removeList)    (reference src/vertex_remover.cpp:83-140).
+ *
+ * Two levels are exported:
+ *   1. Blanket level  (spg_remove_round*)  — one wavefront round of non-interfering Markov
+ *      blankets, packed into fp64/int32 records, processed by the sm_100a kernels. This is what a
+ *      VertexRemover adapter inside the reference would call once per round.
+ *   2. Graph level    (spg_graph_*)        — a g2o-free pose-graph container with the reference's
+ *      removal semantics (VertexRemover / TopologyProvider / SparsityOptions / decimation),
+ *      implemented in C++ on top of level 1. It replaces GraphWrapper::marginalize for callers
+ *      that do not bring g2o.
+ *
+ * Plain pointers and sizes only; no C++ / torch types. All matrices are fp64.
+ * Every function returns spg_status; per-blanket numerical conditions are reported in the
+ * blanket's output record (never by assert()/exit() as the reference does,
+ * src/optimizer.cpp:75-77, src/topology_provider_glc.cpp:85-89).
+ */
+#ifndef SPG_CAPI_H_
+#define SPG_CAPI_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------ */
+/* Enumerations                                                                               */
+/* ------------------------------------------------------------------------------------------ */
+
+typedef enum {
+    SPG_OK = 0,
+    SPG_ERR_INVALID = 1,      /* bad argument / malformed record                          */
+    SPG_ERR_CUDA = 2,         /* CUDA runtime error (message via spg_last_error)          */
+    SPG_ERR_NO_DEVICE = 3,    /* no sm_100 device: the product path has NO CPU fallback   */
+    SPG_ERR_UNSUPPORTED = 4,  /* option combination the reference asserts against         */
+    SPG_ERR_IO = 5
+} spg_status;
+
+/* reference src/sparsity_options.h:12-14 (same numeric values) */
+typedef enum {
+    SPG_TOPO_TREE = 0,
+    SPG_TOPO_SUBGRAPH = 1,
+    SPG_TOPO_CLIQUEY_SUBGRAPH = 2,
+    SPG_TOPO_DENSE = 3,
+    SPG_TOPO_CLIQUEY_DENSE = 4
+} spg_topology;
+
+/* reference src/sparsity_options.h:16-18 */
+typedef enum { SPG_LIN_LOCAL = 0, SPG_LIN_GLOBAL = 1 } spg_lin_point;
+
+/* which TopologyProvider family is registered, reference src/graph_wrapper_g2o.cpp:431-439 */
+typedef enum { SPG_ALG_NFR = 0, SPG_ALG_GLC = 1 } spg_algorithm;
+
+/* reference src/sparsity_options.h:11-30; defaults: Tree, 1.0, Local, true */
+typedef struct {
+    int32_t topology;             /* spg_topology  */
+    int32_t lin_point;            /* spg_lin_point */
+    double  chord_ratio;
+    int32_t include_intra_clique;
+    int32_t reserved;
+} spg_sparsity_options;
+
+/* edge kinds inside a blanket record */
+typedef enum {
+    SPG_EDGE_POSE = 0,   /* EdgeSE2ISAM (src/se2_compatibility.h:21-52) or EdgeSE3ISAM == g2o::EdgeSE3 */
+    SPG_EDGE_GLC = 1,    /* GLCEdge (src/glc_edge.h:15-70), error W * r(x (-) meas), Omega = I    */
+    SPG_EDGE_MULTI = 2   /* MultiEdgeCorrelated<E> (src/multi_edge_correlated.h:16-127)           */
+} spg_edge_kind;
+
+/* per-blanket status word in the output record */
+typedef enum {
+    SPG_BLANKET_OK = 0,
+    SPG_BLANKET_NOT_PD_MARGINAL = 1,  /* LLT(Lambda_mm) failed, vertex_remover.cpp:444            */
+    SPG_BLANKET_NOT_PD_CHOWLIU = 2,   /* LLT(Lambda_t + I) failed, pseudo_chow_liu.cpp:189        */
+    SPG_BLANKET_EIG_NOCONV = 3,       /* eigen-solver did not converge                            */
+    SPG_BLANKET_NOT_PD_CLOSED = 4,    /* LLT(J Sigma J^T) failed, logdet_function.cpp:273         */
+    SPG_BLANKET_TOO_LARGE = 5,        /* blanket exceeds the compiled on-chip capacity            */
+    SPG_BLANKET_LINESEARCH_FAIL = 6,  /* pqn/line_search.cpp:24-26 returned -1 (ignored by ref.)  */
+    SPG_BLANKET_KLD_INF = 7,          /* optimizer.cpp:75-77 (reference calls exit(0))            */
+    SPG_BLANKET_UNSUPPORTED = 8,      /* edge kind / option not handled on device                 */
+    SPG_BLANKET_NOT_PD_JOINT = 9      /* LLT in PseudoChowLiu::marginal failed (GLC tree)         */
+} spg_blanket_status;
+
+/* ------------------------------------------------------------------------------------------ */
+/* Packed blanket records (one round).  Unit: 8-byte words.                                   */
+/* ------------------------------------------------------------------------------------------ */
+/*
+ * INPUT record of one blanket (contiguous, 16-byte aligned start; all offsets in words):
+ *   w0  : int32 n_vert      | int32 n_removed      vertices: removed first, then kept in
+ *   w1  : int32 n_edges     | int32 dim (3|6)       ascending original id (vertex_remover.cpp:349-356)
+ *   w2  : int32 rec_words   | int32 flags
+ *   w3  : int32 tag         | int32 reserved        tag = caller cookie (index in the removal list)
+ *   then int32 vert_id[n_vert]        (padded to a whole word)   original ids
+ *   then double pose[n_vert][P]       P = 3 (SE2: x y theta) or 7 (SE3: tx ty tz qx qy qz qw)
+ *   then int32 edge_off[n_edges]      (padded)   word offset of each edge from the record start
+ *   then edges, each:
+ *        e0 : int32 kind | int32 nv                 nv = #vertices of the edge
+ *        e1 : int32 rows | int32 reserved           rows = error dimension (d for POSE)
+ *        int32 vidx[nv] (padded)                    local vertex indices into this blanket
+ *        POSE : double meas[P], double info[d*d]    (column-major, full)
+ *        GLC  : double meas[d*nv], double W[rows][d*nv]   (row-major: one constraint per row)
+ *   Edge order inside the record is the summation order of H = sum J^T Omega J.
+ *
+ * OUTPUT record of one blanket:
+ *   w0 : int32 status | int32 n_new_edges
+ *   w1 : int32 newton_iters | int32 flags
+ *   w2 : double kld        (value of the projected KLD at the solution, NFR only)
+ *   w3 : double reserved
+ *   then n_new_edges slots, slot size fixed per (algorithm, dim, topology):
+ *     NFR slot:  int32 a | int32 b   (indices into the blanket's KEPT list, a<b),
+ *                double meas[P]      (Z = Xa^-1 Xb, setMeasurementFromState)
+ *                double info[d*d]    (X_e, column-major; reference vertex_remover.cpp:531-533)
+ *     GLC slot:  int32 nv | int32 rank
+ *                int32 vidx[nvcap] (padded)   kept-list indices
+ *                double meas[d*nvcap]
+ *                double W[d*nvcap][d*nvcap]   row-major, rows >= rank are zero, Omega = I_rank
+ *       nvcap = 2 for Tree, n_kept for Dense.
+ */
+
+#define SPG_REC_HEADER_WORDS 4
+#define SPG_OUT_HEADER_WORDS 4
+
+typedef struct {
+    int32_t dim;                 /* 3 | 6                                                   */
+    int32_t algorithm;           /* spg_algorithm                                           */
+    spg_sparsity_options opts;
+    int32_t n_blankets;
+    int32_t reserved;
+    const int64_t *rec_off;      /* [n_blankets+1] word offsets into records                */
+    const uint64_t *records;     /* packed input records                                    */
+    const int64_t *out_off;      /* [n_blankets+1] word offsets into out                    */
+} spg_round_in;
+
+typedef struct {
+    uint64_t *out;               /* packed output records, out_off[n_blankets] words        */
+    double *dbg_target;          /* optional: Lambda_t of every blanket, k*k each, packed   */
+    const int64_t *dbg_target_off; /* [n_blankets+1] offsets (doubles) into dbg_target, or NULL */
+    double *dbg_weights;         /* optional: Chow-Liu MI weights, pairs in (i<j) lexicographic order */
+    const int64_t *dbg_weights_off;
+} spg_round_out;
+
+typedef struct {
+    int32_t device;              /* CUDA device ordinal                                      */
+    int32_t reserved;
+    int64_t max_record_words;    /* initial device buffer sizes (grown on demand)            */
+    int64_t max_out_words;
+} spg_config;
+
+typedef struct spg_ctx spg_ctx;
+
+/* library / context */
+const char *spg_version(void);
+const char *spg_last_error(void);
+spg_status spg_create(spg_ctx **ctx, const spg_config *cfg);
+void spg_destroy(spg_ctx *ctx);
+/* number of kernels launched by this context so far (bench.py's gpu_launches) */
+int64_t spg_launch_count(const spg_ctx *ctx);
+/* device time (ms, CUDA events on the context stream) of the kernels of the last round */
+double spg_last_kernel_ms(const spg_ctx *ctx);
+
+/* record sizing + packing helpers (pure host code, usable without a GPU) */
+int64_t spg_pose_words(int32_t dim);                       /* 3 or 7 */
+int64_t spg_record_words(int32_t dim, int32_t n_vert, int32_t n_edges,
+                         const int32_t *edge_kind, const int32_t *edge_nv,
+                         const int32_t *edge_rows);
+int64_t spg_out_record_words(int32_t dim, int32_t algorithm, const spg_sparsity_options *opts,
+                             int32_t n_kept);
+int32_t spg_out_edge_count(int32_t algorithm, const spg_sparsity_options *opts, int32_t n_kept);
+int64_t spg_out_slot_words(int32_t dim, int32_t algorithm, const spg_sparsity_options *opts,
+                           int32_t n_kept);
+
+/*
+ * One wavefront round through the GPU, host buffers in and out.
+ * Replaces, for every blanket of the round, the body of the loop in
+ * VertexRemover::remove (src/vertex_remover.cpp:89-139): computeTargetInformation (:394-450),
+ * tp->topology (:111), buildJacobianMapping + optimizeInformation (:123-126).
+ * Synchronous: H2D copy, kernels, D2H copy, stream sync.
+ */
+spg_status spg_remove_round(spg_ctx *ctx, const spg_round_in *in, spg_round_out *out);
+
+/*
+ * Same, but every pointer inside in/out is a DEVICE pointer already resident in HBM
+ * (rec_off/out_off too). Asynchronous on the context stream; call spg_sync().
+ */
+spg_status spg_remove_round_device(spg_ctx *ctx, const spg_round_in *in_dev, spg_round_out *out_dev,
+                                   int32_t max_n_vert, int32_t max_n_edges);
+spg_status spg_sync(spg_ctx *ctx);
+void *spg_stream(spg_ctx *ctx); /* cudaStream_t of the context */
+
+/* ------------------------------------------------------------------------------------------ */
+/* Graph level: g2o-free container with the reference's removal semantics.                    */
+/* Mirrors GraphWrapper (src/graph_wrapper.h:17-81) for the calls on the removal path.        */
+/* ------------------------------------------------------------------------------------------ */
+
+typedef struct spg_graph spg_graph;
+
+spg_status spg_graph_create(spg_graph **g, int32_t dim);
+void spg_graph_destroy(spg_graph *g);
+/* reads VERTEX_SE2/EDGE_SE2/VERTEX_SE3:QUAT/EDGE_SE3:QUAT (src/graph_wrapper_g2o.cpp:107-147) */
+spg_status spg_graph_load_g2o(spg_graph **g, const char *path);
+spg_status spg_graph_add_vertex(spg_graph *g, int32_t id, const double *pose);
+spg_status spg_graph_add_edge(spg_graph *g, int32_t from, int32_t to, const double *meas,
+                              const double *info /* d*d column-major */);
+int32_t spg_graph_dim(const spg_graph *g);
+int32_t spg_graph_num_vertices(const spg_graph *g);
+int32_t spg_graph_num_edges(const spg_graph *g);
+int32_t spg_graph_max_vertex_id(const spg_graph *g);
+
+/* removal schedules, reference src/decimation.cpp:11-49. Returns count; ids written to out (cap). */
+int32_t spg_decimate_global(int32_t last, int32_t endvert, int32_t sparsity, int32_t *out, int32_t cap);
+int32_t spg_decimate_online(int32_t last, int32_t endvert, int32_t sparsity, int32_t *out, int32_t cap);
+int32_t spg_decimate_cluster(int32_t last, int32_t endvert, int32_t sparsity, int32_t cluster_size,
+                             int32_t *out, int32_t cap);
+
+/*
+ * GraphWrapperG2O::marginalizeNoOptimize(which, options) (src/graph_wrapper_g2o.cpp:398-453):
+ * removes the vertices `which` (in this order) and splices the substitute edges in. The result is
+ * identical to the reference's one-at-a-time loop; internally removals are grouped into
+ * wavefront rounds of non-interfering blankets, each round is one spg_remove_round().
+ */
+spg_status spg_graph_marginalize(spg_graph *g, spg_ctx *ctx, const int32_t *which, int32_t n_which,
+                                 const spg_sparsity_options *opts, int32_t algorithm);
+
+typedef struct {
+    int32_t n_rounds;
+    int32_t n_blankets;
+    int32_t max_round_width;
+    int32_t max_blanket_vertices;
+    int32_t n_failed;            /* blankets whose status != OK */
+    int32_t n_dropped_edges;     /* GLC rank-0 edges (reference returns NULL, :85-89) */
+    double pack_ms, gpu_ms, splice_ms;
+} spg_marginalize_stats;
+spg_status spg_graph_last_stats(const spg_graph *g, spg_marginalize_stats *stats);
+
+/* read-back of the current edge list (for parity tests / writers). Edge index order is the
+ * canonical creation order. */
+typedef struct {
+    int32_t kind;      /* spg_edge_kind */
+    int32_t nv;
+    int32_t rows;
+    int32_t uid_major; /* -1 for file edges, else index in the removal list that created it */
+    int32_t uid_minor; /* file order / provider order */
+} spg_edge_desc;
+spg_status spg_graph_edge_desc(const spg_graph *g, int32_t idx, spg_edge_desc *desc);
+/* vertex ids (nv), measurement (P or d*nv doubles), info-or-W (d*d col-major, or rows*d*nv row-major) */
+spg_status spg_graph_edge_data(const spg_graph *g, int32_t idx, int32_t *vert_ids, double *meas,
+                               double *info_or_w);
+spg_status spg_graph_vertex_ids(const spg_graph *g, int32_t *ids /* num_vertices */);
+spg_status spg_graph_vertex_pose(const spg_graph *g, int32_t id, double *pose);
+
+/*
+ * computeSubstituteEdge (src/compute_substitute_edge.cpp:13-96) on this container.
+ * marginalized: sorted ids. from/to are in-out. meas: P doubles, info: d*d column-major.
+ */
+spg_status spg_compute_substitute_edge(const spg_graph *g, const int32_t *marginalized,
+                                       int32_t n_marginalized, int32_t maxid, int32_t *from,
+                                       int32_t *to, double *meas, double *info);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPG_CAPI_H_ */
