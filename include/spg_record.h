@@ -9,15 +9,21 @@
 #include <stdint.h>
 #include "spg_capi.h"
 
+#ifdef __CUDACC__
+#define SPGR_FN static __host__ __device__ inline
+#else
+#define SPGR_FN static inline
+#endif
+
 #ifdef __cplusplus
 extern "C" {
 #endif
 
-static inline int64_t spgr_pad2(int64_t n_int32) { return (n_int32 + 1) / 2; }
-static inline int64_t spgr_pose_words(int32_t dim) { return dim == 3 ? 3 : 7; }
+SPGR_FN int64_t spgr_pad2(int64_t n_int32) { return (n_int32 + 1) / 2; }
+SPGR_FN int64_t spgr_pose_words(int32_t dim) { return dim == 3 ? 3 : 7; }
 
 /* words of one edge inside an input record */
-static inline int64_t spgr_edge_words(int32_t dim, int32_t kind, int32_t nv, int32_t rows) {
+SPGR_FN int64_t spgr_edge_words(int32_t dim, int32_t kind, int32_t nv, int32_t rows) {
     int64_t w = 2 + spgr_pad2(nv);
     if(kind == SPG_EDGE_POSE) {
         w += spgr_pose_words(dim) + (int64_t) dim * dim;
@@ -31,19 +37,19 @@ static inline int64_t spgr_edge_words(int32_t dim, int32_t kind, int32_t nv, int
 }
 
 /* words of the fixed part of an input record (header, ids, poses, edge offset table) */
-static inline int64_t spgr_record_fixed_words(int32_t dim, int32_t n_vert, int32_t n_edges) {
+SPGR_FN int64_t spgr_record_fixed_words(int32_t dim, int32_t n_vert, int32_t n_edges) {
     return SPG_REC_HEADER_WORDS + spgr_pad2(n_vert) + (int64_t) n_vert * spgr_pose_words(dim) +
            spgr_pad2(n_edges);
 }
-static inline int64_t spgr_ids_off(void) { return SPG_REC_HEADER_WORDS; }
-static inline int64_t spgr_poses_off(int32_t n_vert) { return SPG_REC_HEADER_WORDS + spgr_pad2(n_vert); }
-static inline int64_t spgr_edgetab_off(int32_t dim, int32_t n_vert) {
+SPGR_FN int64_t spgr_ids_off(void) { return SPG_REC_HEADER_WORDS; }
+SPGR_FN int64_t spgr_poses_off(int32_t n_vert) { return SPG_REC_HEADER_WORDS + spgr_pad2(n_vert); }
+SPGR_FN int64_t spgr_edgetab_off(int32_t dim, int32_t n_vert) {
     return spgr_poses_off(n_vert) + (int64_t) n_vert * spgr_pose_words(dim);
 }
 
 /* number of edges the chosen provider emits for n_kept kept vertices (upper bound for GLC, where
  * rank-0 edges are dropped). Follows pseudo_chow_liu.cpp:41-86 and topology_provider_glc.cpp:113-183. */
-static inline int32_t spgr_out_edge_count(int32_t algorithm, int32_t topology, double chord_ratio,
+SPGR_FN int32_t spgr_out_edge_count(int32_t algorithm, int32_t topology, double chord_ratio,
                                           int32_t n_kept) {
     int32_t n = n_kept;
     if(algorithm == SPG_ALG_GLC) {
@@ -65,7 +71,7 @@ static inline int32_t spgr_out_edge_count(int32_t algorithm, int32_t topology, d
 }
 
 /* words of one output slot */
-static inline int64_t spgr_out_slot_words(int32_t dim, int32_t algorithm, int32_t topology, int32_t n_kept) {
+SPGR_FN int64_t spgr_out_slot_words(int32_t dim, int32_t algorithm, int32_t topology, int32_t n_kept) {
     int64_t P = spgr_pose_words(dim);
     if(algorithm == SPG_ALG_GLC) {
         int64_t nvcap = (topology == SPG_TOPO_DENSE || n_kept == 1) ? n_kept : 2;
@@ -81,7 +87,7 @@ static inline int64_t spgr_out_slot_words(int32_t dim, int32_t algorithm, int32_
     return 1 + P + (int64_t) dim * dim;
 }
 
-static inline int64_t spgr_out_record_words(int32_t dim, int32_t algorithm, int32_t topology,
+SPGR_FN int64_t spgr_out_record_words(int32_t dim, int32_t algorithm, int32_t topology,
                                             double chord_ratio, int32_t n_kept) {
     int64_t w = SPG_OUT_HEADER_WORDS +
                 (int64_t) spgr_out_edge_count(algorithm, topology, chord_ratio, n_kept) *

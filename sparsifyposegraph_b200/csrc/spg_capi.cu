@@ -1,0 +1,366 @@
+// spg_capi.cu — C ABI of libspg_b200.so, blanket level (include/spg_capi.h).
+// Host side of one wavefront round: bucket the blankets of the round by size, copy the packed
+// records to HBM, launch one fused kernel per bucket (shared memory and CTA width sized to the
+// bucket), copy the substitute-edge records back. No CPU fallback: without an sm_100 device every
+// entry point that computes returns SPG_ERR_NO_DEVICE.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "spg_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+void set_err(const std::string &s) { g_err = s; }
+
+#define SPG_CUDA(call)                                                                            \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if(e_ != cudaSuccess) {                                                                   \
+            set_err(std::string(#call) + ": " + cudaGetErrorString(e_));                          \
+            return SPG_ERR_CUDA;                                                                  \
+        }                                                                                         \
+    } while(0)
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if(bytes <= cap) return cudaSuccess;
+        if(p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if(e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if(p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct Bucket {
+    std::vector<int32_t> list;
+    int max_nv = 0, max_e = 0, max_rec = 0;
+};
+
+} // namespace
+
+struct spg_ctx {
+    int device = 0;
+    int sm_count = 148;
+    size_t smem_optin = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int64_t launches = 0;
+    double last_ms = 0;
+    DevBuf d_rec, d_recoff, d_outoff, d_out, d_list, d_tgt, d_tgtoff, d_wts, d_wtsoff;
+};
+
+namespace {
+
+template <int D, int NT>
+spg_status launch_bucket(spg_ctx *ctx, spg::KernelParams &kp) {
+    static std::mutex mu;
+    static size_t configured = 0;
+    const size_t smem = (size_t) kp.total_doubles * sizeof(double);
+    if(smem > ctx->smem_optin) {
+        set_err("bucket needs more shared memory than the device offers");
+        return SPG_ERR_INVALID;
+    }
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        if(smem > configured) {
+            SPG_CUDA(cudaFuncSetAttribute(spg::blanket_kernel<D, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int) ctx->smem_optin));
+            configured = ctx->smem_optin;
+        }
+    }
+    int per_sm = 0;
+    SPG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, spg::blanket_kernel<D, NT>, NT, smem));
+    if(per_sm < 1) per_sm = 1;
+    int grid = std::min<int64_t>(kp.n_list, (int64_t) per_sm * ctx->sm_count);
+    if(grid < 1) return SPG_OK;
+    spg::blanket_kernel<D, NT><<<grid, NT, smem, ctx->stream>>>(kp);
+    SPG_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return SPG_OK;
+}
+
+template <int D>
+spg_status launch_dim(spg_ctx *ctx, spg::KernelParams &kp) {
+    spg::plan_smem<D>(kp);
+    const int kmax = D * (kp.max_nv - 1);
+    if(kmax <= 12) return launch_bucket<D, 32>(ctx, kp);
+    if(kmax <= 30) return launch_bucket<D, 64>(ctx, kp);
+    if(kmax <= 54) return launch_bucket<D, 128>(ctx, kp);
+    return launch_bucket<D, 256>(ctx, kp);
+}
+
+// largest vertex count whose bucket still fits in shared memory
+template <int D>
+int max_fit_nv(const spg_ctx *ctx, int max_e_hint, int max_rec_hint) {
+    int best = 0;
+    for(int nv = 2; nv <= 400; nv++) {
+        spg::KernelParams kp{};
+        kp.max_nv = nv;
+        kp.max_e = max_e_hint;
+        kp.max_rec_words = max_rec_hint;
+        spg::plan_smem<D>(kp);
+        if((size_t) kp.total_doubles * 8 <= ctx->smem_optin) best = nv;
+        else break;
+    }
+    return best;
+}
+
+spg_status check_device(spg_ctx *ctx) {
+    if(!ctx) {
+        set_err("null context");
+        return SPG_ERR_INVALID;
+    }
+    return SPG_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+const char *spg_version(void) { return "sparsifyposegraph_b200 0.1 (sm_100a)"; }
+const char *spg_last_error(void) { return g_err.c_str(); }
+
+spg_status spg_create(spg_ctx **out, const spg_config *cfg) {
+    if(!out) return SPG_ERR_INVALID;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if(e != cudaSuccess || count == 0) {
+        set_err("no CUDA device: the node-removal path has no CPU fallback");
+        return SPG_ERR_NO_DEVICE;
+    }
+    int dev = cfg ? cfg->device : 0;
+    if(dev < 0 || dev >= count) {
+        set_err("bad device ordinal");
+        return SPG_ERR_INVALID;
+    }
+    cudaDeviceProp prop;
+    SPG_CUDA(cudaGetDeviceProperties(&prop, dev));
+    if(prop.major < 10) {
+        set_err(std::string("device is sm_") + std::to_string(prop.major) + std::to_string(prop.minor) +
+                ", this library is built for sm_100a only");
+        return SPG_ERR_NO_DEVICE;
+    }
+    SPG_CUDA(cudaSetDevice(dev));
+    spg_ctx *ctx = new spg_ctx;
+    ctx->device = dev;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    SPG_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    SPG_CUDA(cudaEventCreate(&ctx->ev0));
+    SPG_CUDA(cudaEventCreate(&ctx->ev1));
+    if(cfg && cfg->max_record_words > 0) SPG_CUDA(ctx->d_rec.reserve((size_t) cfg->max_record_words * 8));
+    if(cfg && cfg->max_out_words > 0) SPG_CUDA(ctx->d_out.reserve((size_t) cfg->max_out_words * 8));
+    *out = ctx;
+    return SPG_OK;
+}
+
+void spg_destroy(spg_ctx *ctx) {
+    if(!ctx) return;
+    cudaSetDevice(ctx->device);
+    for(DevBuf *b : {&ctx->d_rec, &ctx->d_recoff, &ctx->d_outoff, &ctx->d_out, &ctx->d_list, &ctx->d_tgt,
+                     &ctx->d_tgtoff, &ctx->d_wts, &ctx->d_wtsoff})
+        b->release();
+    if(ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if(ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if(ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int64_t spg_launch_count(const spg_ctx *ctx) { return ctx ? ctx->launches : 0; }
+double spg_last_kernel_ms(const spg_ctx *ctx) { return ctx ? ctx->last_ms : 0.0; }
+void *spg_stream(spg_ctx *ctx) { return ctx ? (void *) ctx->stream : nullptr; }
+
+int64_t spg_pose_words(int32_t dim) { return spgr_pose_words(dim); }
+int64_t spg_record_words(int32_t dim, int32_t n_vert, int32_t n_edges, const int32_t *edge_kind,
+                         const int32_t *edge_nv, const int32_t *edge_rows) {
+    int64_t w = spgr_record_fixed_words(dim, n_vert, n_edges);
+    for(int e = 0; e < n_edges; e++) w += spgr_edge_words(dim, edge_kind[e], edge_nv[e], edge_rows[e]);
+    return (w + 1) & ~(int64_t) 1;
+}
+int64_t spg_out_record_words(int32_t dim, int32_t algorithm, const spg_sparsity_options *o, int32_t n_kept) {
+    return spgr_out_record_words(dim, algorithm, o->topology, o->chord_ratio, n_kept);
+}
+int32_t spg_out_edge_count(int32_t algorithm, const spg_sparsity_options *o, int32_t n_kept) {
+    return spgr_out_edge_count(algorithm, o->topology, o->chord_ratio, n_kept);
+}
+int64_t spg_out_slot_words(int32_t dim, int32_t algorithm, const spg_sparsity_options *o, int32_t n_kept) {
+    return spgr_out_slot_words(dim, algorithm, o->topology, n_kept);
+}
+
+spg_status spg_sync(spg_ctx *ctx) {
+    if(check_device(ctx) != SPG_OK) return SPG_ERR_INVALID;
+    SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    if(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->last_ms = ms;
+    else (void) cudaGetLastError();
+    return SPG_OK;
+}
+
+spg_status spg_remove_round_device(spg_ctx *ctx, const spg_round_in *in, spg_round_out *out, int32_t max_n_vert,
+                                   int32_t max_n_edges) {
+    if(check_device(ctx) != SPG_OK) return SPG_ERR_INVALID;
+    if(!in || !out || (in->dim != 3 && in->dim != 6)) {
+        set_err("bad round descriptor");
+        return SPG_ERR_INVALID;
+    }
+    SPG_CUDA(cudaSetDevice(ctx->device));
+    spg::KernelParams kp{};
+    kp.algorithm = in->algorithm;
+    kp.topology = in->opts.topology;
+    kp.chord_ratio = in->opts.chord_ratio;
+    kp.n_list = in->n_blankets;
+    kp.list = nullptr;
+    kp.rec_off = in->rec_off;
+    kp.records = in->records;
+    kp.out_off = in->out_off;
+    kp.out = out->out;
+    kp.dbg_target = out->dbg_target;
+    kp.dbg_target_off = out->dbg_target_off;
+    kp.dbg_weights = out->dbg_weights;
+    kp.dbg_weights_off = out->dbg_weights_off;
+    kp.max_nv = max_n_vert;
+    kp.max_e = max_n_edges;
+    // all-POSE upper bound of the record size for this (nv, ne)
+    kp.max_rec_words = (int32_t) ((spgr_record_fixed_words(in->dim, max_n_vert, max_n_edges) +
+                                   (int64_t) max_n_edges * spgr_edge_words(in->dim, SPG_EDGE_POSE, 2, in->dim) + 1) & ~1LL);
+    SPG_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    spg_status st = (in->dim == 6) ? launch_dim<6>(ctx, kp) : launch_dim<3>(ctx, kp);
+    if(st != SPG_OK) return st;
+    SPG_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+    return SPG_OK;
+}
+
+spg_status spg_remove_round(spg_ctx *ctx, const spg_round_in *in, spg_round_out *out) {
+    if(check_device(ctx) != SPG_OK) return SPG_ERR_INVALID;
+    if(!in || !out || !out->out || (in->dim != 3 && in->dim != 6) || in->n_blankets < 0) {
+        set_err("bad round descriptor");
+        return SPG_ERR_INVALID;
+    }
+    const int nb = in->n_blankets;
+    if(nb == 0) return SPG_OK;
+    SPG_CUDA(cudaSetDevice(ctx->device));
+    const int dim = in->dim;
+    const int64_t rec_words = in->rec_off[nb];
+    const int64_t out_words = in->out_off[nb];
+
+    // ---- bucket by blanket size -------------------------------------------------------------
+    static const int bounds6[] = {3, 4, 5, 6, 7, 8, 10, 12, 14, 16, 20, 24, 32, 48, 64, 128, 1 << 30};
+    std::vector<Bucket> buckets(sizeof(bounds6) / sizeof(int));
+    for(int b = 0; b < nb; b++) {
+        const int32_t *h = reinterpret_cast<const int32_t *>(in->records + in->rec_off[b]);
+        const int nv = h[0], ne = h[2];
+        const int rw = (int) (in->rec_off[b + 1] - in->rec_off[b]);
+        if(h[3] != dim || h[4] > rw || nv < 1) {
+            set_err("malformed blanket record " + std::to_string(b));
+            return SPG_ERR_INVALID;
+        }
+        int bi = 0;
+        while(nv > bounds6[bi]) bi++;
+        Bucket &B = buckets[bi];
+        B.list.push_back(b);
+        B.max_nv = std::max(B.max_nv, nv);
+        B.max_e = std::max(B.max_e, ne);
+        B.max_rec = std::max(B.max_rec, (int) h[4]);
+    }
+
+    // ---- H2D ---------------------------------------------------------------------------------
+    SPG_CUDA(ctx->d_rec.reserve((size_t) rec_words * 8));
+    SPG_CUDA(ctx->d_recoff.reserve((size_t) (nb + 1) * 8));
+    SPG_CUDA(ctx->d_outoff.reserve((size_t) (nb + 1) * 8));
+    SPG_CUDA(ctx->d_out.reserve((size_t) out_words * 8));
+    SPG_CUDA(ctx->d_list.reserve((size_t) nb * 4));
+    SPG_CUDA(cudaMemcpyAsync(ctx->d_rec.p, in->records, (size_t) rec_words * 8, cudaMemcpyHostToDevice, ctx->stream));
+    SPG_CUDA(cudaMemcpyAsync(ctx->d_recoff.p, in->rec_off, (size_t) (nb + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    SPG_CUDA(cudaMemcpyAsync(ctx->d_outoff.p, in->out_off, (size_t) (nb + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    std::vector<int32_t> flat;
+    flat.reserve(nb);
+    for(auto &B : buckets) flat.insert(flat.end(), B.list.begin(), B.list.end());
+    SPG_CUDA(cudaMemcpyAsync(ctx->d_list.p, flat.data(), (size_t) nb * 4, cudaMemcpyHostToDevice, ctx->stream));
+    int64_t tgt_n = 0, wts_n = 0;
+    if(out->dbg_target && out->dbg_target_off) {
+        tgt_n = out->dbg_target_off[nb];
+        SPG_CUDA(ctx->d_tgt.reserve((size_t) tgt_n * 8 + 8));
+        SPG_CUDA(ctx->d_tgtoff.reserve((size_t) (nb + 1) * 8));
+        SPG_CUDA(cudaMemcpyAsync(ctx->d_tgtoff.p, out->dbg_target_off, (size_t) (nb + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+        SPG_CUDA(cudaMemsetAsync(ctx->d_tgt.p, 0, (size_t) tgt_n * 8 + 8, ctx->stream));
+    }
+    if(out->dbg_weights && out->dbg_weights_off) {
+        wts_n = out->dbg_weights_off[nb];
+        SPG_CUDA(ctx->d_wts.reserve((size_t) wts_n * 8 + 8));
+        SPG_CUDA(ctx->d_wtsoff.reserve((size_t) (nb + 1) * 8));
+        SPG_CUDA(cudaMemcpyAsync(ctx->d_wtsoff.p, out->dbg_weights_off, (size_t) (nb + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+        SPG_CUDA(cudaMemsetAsync(ctx->d_wts.p, 0, (size_t) wts_n * 8 + 8, ctx->stream));
+    }
+
+    // ---- kernels -----------------------------------------------------------------------------
+    SPG_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    size_t list_pos = 0;
+    const int fit = (dim == 6) ? max_fit_nv<6>(ctx, 64, 4096) : max_fit_nv<3>(ctx, 64, 4096);
+    (void) fit;
+    for(auto &B : buckets) {
+        if(B.list.empty()) continue;
+        spg::KernelParams kp{};
+        kp.algorithm = in->algorithm;
+        kp.topology = in->opts.topology;
+        kp.chord_ratio = in->opts.chord_ratio;
+        kp.n_list = (int32_t) B.list.size();
+        kp.list = reinterpret_cast<const int32_t *>(ctx->d_list.p) + list_pos;
+        list_pos += B.list.size();
+        kp.rec_off = reinterpret_cast<const int64_t *>(ctx->d_recoff.p);
+        kp.records = reinterpret_cast<const uint64_t *>(ctx->d_rec.p);
+        kp.out_off = reinterpret_cast<const int64_t *>(ctx->d_outoff.p);
+        kp.out = reinterpret_cast<uint64_t *>(ctx->d_out.p);
+        kp.dbg_target = tgt_n ? reinterpret_cast<double *>(ctx->d_tgt.p) : nullptr;
+        kp.dbg_target_off = tgt_n ? reinterpret_cast<const int64_t *>(ctx->d_tgtoff.p) : nullptr;
+        kp.dbg_weights = wts_n ? reinterpret_cast<double *>(ctx->d_wts.p) : nullptr;
+        kp.dbg_weights_off = wts_n ? reinterpret_cast<const int64_t *>(ctx->d_wtsoff.p) : nullptr;
+        kp.max_nv = B.max_nv;
+        kp.max_e = B.max_e;
+        kp.max_rec_words = (B.max_rec + 1) & ~1;
+        // a bucket that does not fit on chip is shrunk to the largest size that does: the kernel
+        // flags its over-sized blankets SPG_BLANKET_TOO_LARGE (global-memory variant: DESIGN.md)
+        {
+            spg::KernelParams probe = kp;
+            if(dim == 6) spg::plan_smem<6>(probe); else spg::plan_smem<3>(probe);
+            while((size_t) probe.total_doubles * 8 > ctx->smem_optin && probe.max_nv > 2) {
+                probe.max_nv--;
+                probe.max_rec_words = std::min(probe.max_rec_words, 6000);
+                if(dim == 6) spg::plan_smem<6>(probe); else spg::plan_smem<3>(probe);
+            }
+            kp.max_nv = probe.max_nv;
+            kp.max_rec_words = probe.max_rec_words;
+        }
+        spg_status st = (dim == 6) ? launch_dim<6>(ctx, kp) : launch_dim<3>(ctx, kp);
+        if(st != SPG_OK) return st;
+    }
+    SPG_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+
+    // ---- D2H ---------------------------------------------------------------------------------
+    SPG_CUDA(cudaMemcpyAsync(out->out, ctx->d_out.p, (size_t) out_words * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if(tgt_n) SPG_CUDA(cudaMemcpyAsync(out->dbg_target, ctx->d_tgt.p, (size_t) tgt_n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if(wts_n) SPG_CUDA(cudaMemcpyAsync(out->dbg_weights, ctx->d_wts.p, (size_t) wts_n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    SPG_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ctx->last_ms = ms;
+    return SPG_OK;
+}
+
+} // extern "C"

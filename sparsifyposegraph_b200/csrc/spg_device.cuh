@@ -1,0 +1,364 @@
+// spg_device.cuh — device-side building blocks of the blanket kernels (sm_100a).
+//
+// Everything here is "group cooperative": one CTA of NT threads owns one Markov blanket, the
+// matrices live in shared memory (column-major, odd leading dimension so that both column and
+// row walks are bank-conflict free for fp64), and every routine is called by all NT threads.
+// FP64 vector pipe only — the matrices are 6x6 ... ~100x100, far below a DMMA tile economy.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+namespace spg {
+
+template <int NT>
+__device__ __forceinline__ void gsync() {
+    if constexpr(NT <= 32) __syncwarp();
+    else __syncthreads();
+}
+
+__host__ __device__ __forceinline__ int odd_ld(int n) { return n | 1; }
+
+// ------------------------------------------------------------------------------------------
+// poses
+// ------------------------------------------------------------------------------------------
+// SE3 pose in shared memory: R (row-major 3x3) then t  -> 12 doubles.
+// SE2 pose: x y theta cos sin -> padded to 6 doubles.
+template <int D> struct PoseStride { static constexpr int value = (D == 6) ? 12 : 6; };
+
+__device__ __forceinline__ double normalize_theta(double theta) {
+    if(theta >= -M_PI && theta < M_PI) return theta;
+    double multiplier = floor(theta / (2 * M_PI));
+    theta = theta - multiplier * 2 * M_PI;
+    if(theta >= M_PI) theta -= 2 * M_PI;
+    if(theta < -M_PI) theta += 2 * M_PI;
+    return theta;
+}
+
+__device__ __forceinline__ void quat_to_R(const double q[4], double R[9]) {
+    const double x = q[0], y = q[1], z = q[2], w = q[3];
+    const double tx = 2 * x, ty = 2 * y, tz = 2 * z;
+    const double twx = tx * w, twy = ty * w, twz = tz * w;
+    const double txx = tx * x, txy = ty * x, txz = tz * x;
+    const double tyy = ty * y, tyz = tz * y, tzz = tz * z;
+    R[0] = 1 - (tyy + tzz); R[1] = txy - twz;       R[2] = txz + twy;
+    R[3] = txy + twz;       R[4] = 1 - (txx + tzz); R[5] = tyz - twx;
+    R[6] = txz - twy;       R[7] = tyz + twx;       R[8] = 1 - (txx + tyy);
+}
+
+// Eigen::Quaterniond(Matrix3d) followed by g2o normalize (unit, w >= 0)
+__device__ __forceinline__ void R_to_quat(const double R[9], double q[4]) {
+    double t = R[0] + R[4] + R[8];
+    if(t > 0) {
+        t = sqrt(t + 1.0);
+        q[3] = 0.5 * t;
+        t = 0.5 / t;
+        q[0] = (R[7] - R[5]) * t;
+        q[1] = (R[2] - R[6]) * t;
+        q[2] = (R[3] - R[1]) * t;
+    } else {
+        int i = 0;
+        if(R[4] > R[0]) i = 1;
+        if(R[8] > R[3 * i + i]) i = 2;
+        int j = (i + 1) % 3, k = (j + 1) % 3;
+        t = sqrt(R[3 * i + i] - R[3 * j + j] - R[3 * k + k] + 1.0);
+        double qq[4];
+        qq[i] = 0.5 * t;
+        t = 0.5 / t;
+        qq[3] = (R[3 * k + j] - R[3 * j + k]) * t;
+        qq[j] = (R[3 * j + i] + R[3 * i + j]) * t;
+        qq[k] = (R[3 * k + i] + R[3 * i + k]) * t;
+        q[0] = qq[0]; q[1] = qq[1]; q[2] = qq[2]; q[3] = qq[3];
+    }
+    double n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    double s = (q[3] < 0) ? -1.0 / n : 1.0 / n;
+    q[0] *= s; q[1] *= s; q[2] *= s; q[3] *= s;
+}
+
+// flat (t, qx qy qz qw) -> (R, t), quaternion normalised like g2o::internal::fromVectorQT
+__device__ __forceinline__ void se3_from_flat(const double *v, double *p) {
+    double q[4] = {v[3], v[4], v[5], v[6]};
+    double n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    double s = (q[3] < 0) ? -1.0 / n : 1.0 / n;
+    q[0] *= s; q[1] *= s; q[2] *= s; q[3] *= s;
+    quat_to_R(q, p);
+    p[9] = v[0]; p[10] = v[1]; p[11] = v[2];
+}
+__device__ __forceinline__ void se3_to_flat(const double *p, double *v) {
+    double q[4];
+    R_to_quat(p, q);
+    v[0] = p[9]; v[1] = p[10]; v[2] = p[11];
+    v[3] = q[0]; v[4] = q[1]; v[5] = q[2]; v[6] = q[3];
+}
+__device__ __forceinline__ void se3_compose(const double *a, const double *b, double *r) {
+#pragma unroll
+    for(int i = 0; i < 3; i++) {
+#pragma unroll
+        for(int j = 0; j < 3; j++) r[3 * i + j] = a[3 * i] * b[j] + a[3 * i + 1] * b[3 + j] + a[3 * i + 2] * b[6 + j];
+        r[9 + i] = a[3 * i] * b[9] + a[3 * i + 1] * b[10] + a[3 * i + 2] * b[11] + a[9 + i];
+    }
+}
+__device__ __forceinline__ void se3_inverse(const double *a, double *r) {
+#pragma unroll
+    for(int i = 0; i < 3; i++)
+#pragma unroll
+        for(int j = 0; j < 3; j++) r[3 * i + j] = a[3 * j + i];
+#pragma unroll
+    for(int i = 0; i < 3; i++) r[9 + i] = -(r[3 * i] * a[9] + r[3 * i + 1] * a[10] + r[3 * i + 2] * a[11]);
+}
+// g2o::internal::fromVectorMQT
+__device__ __forceinline__ void se3_from_mqt(const double *v, double *p) {
+    double w = 1 - (v[3] * v[3] + v[4] * v[4] + v[5] * v[5]);
+    if(w < 0) {
+        p[0] = 1; p[1] = 0; p[2] = 0; p[3] = 0; p[4] = 1; p[5] = 0; p[6] = 0; p[7] = 0; p[8] = 1;
+    } else {
+        double q[4] = {v[3], v[4], v[5], sqrt(w)};
+        quat_to_R(q, p);
+    }
+    p[9] = v[0]; p[10] = v[1]; p[11] = v[2];
+}
+// g2o::internal::toVectorMQT
+__device__ __forceinline__ void se3_to_mqt(const double *p, double *v) {
+    double q[4];
+    R_to_quat(p, q);
+    v[0] = p[9]; v[1] = p[10]; v[2] = p[11];
+    v[3] = q[0]; v[4] = q[1]; v[5] = q[2];
+}
+
+__device__ __forceinline__ void se2_from_flat(const double *v, double *p) {
+    p[0] = v[0]; p[1] = v[1];
+    p[2] = normalize_theta(v[2]);
+    p[3] = cos(p[2]); p[4] = sin(p[2]); p[5] = 0;
+}
+__device__ __forceinline__ void se2_compose(const double *a, const double *b, double *r) {
+    r[0] = a[0] + a[3] * b[0] - a[4] * b[1];
+    r[1] = a[1] + a[4] * b[0] + a[3] * b[1];
+    r[2] = normalize_theta(a[2] + b[2]);
+    r[3] = cos(r[2]); r[4] = sin(r[2]); r[5] = 0;
+}
+__device__ __forceinline__ void se2_inverse(const double *a, double *r) {
+    r[2] = normalize_theta(-a[2]);
+    r[3] = cos(r[2]); r[4] = sin(r[2]); r[5] = 0;
+    r[0] = r[3] * (-a[0]) - r[4] * (-a[1]);
+    r[1] = r[4] * (-a[0]) + r[3] * (-a[1]);
+}
+
+// d err / d delta_i | d err / d delta_j for one relative-pose edge; J is d x 2d column-major
+// (ld = D): columns [0,D) = Ji, [D,2D) = Jj.
+//   SE2: EdgeSE2ISAM::linearizeOplus, reference src/se2_compatibility.h:35-51
+//   SE3: analytic derivative of toVectorMQT(Z^-1 (Xi (+) di)^-1 (Xj (+) dj)) — the quantity
+//        g2o::internal::computeEdgeSE3Gradient evaluates (call site src/se3_compatibility.h:25-29);
+//        closed form derived in DESIGN.md §Jacobians.
+template <int D>
+__device__ __forceinline__ void edge_jacobians(const double *Z, const double *Xi, const double *Xj, double *J) {
+    if constexpr(D == 3) {
+        const double dtx = Xj[0] - Xi[0], dty = Xj[1] - Xi[1];
+        const double ci = Xi[3], si = Xi[4];
+        // Ji
+        J[0] = -ci; J[3] = -si; J[6] = -si * dtx + ci * dty;
+        J[1] = si;  J[4] = -ci; J[7] = -ci * dtx - si * dty;
+        J[2] = 0;   J[5] = 0;   J[8] = -1;
+        // Jj
+        J[9] = ci;   J[12] = si; J[15] = 0;
+        J[10] = -si; J[13] = ci; J[16] = 0;
+        J[11] = 0;   J[14] = 0;  J[17] = 1;
+    } else {
+        double A[12], B[12], T[12], E[12];
+        se3_inverse(Z, A);
+        se3_inverse(Xi, T);
+        se3_compose(T, Xj, B);
+        se3_compose(A, B, E);
+        double qA[4], qB[4];
+        R_to_quat(A, qA);
+        R_to_quat(B, qB);
+        const double wA = qA[3], wB = qB[3];
+        double wE = wA * wB - (qA[0] * qB[0] + qA[1] * qB[1] + qA[2] * qB[2]);
+        double vE[3] = {wA * qB[0] + wB * qA[0] + (qA[1] * qB[2] - qA[2] * qB[1]),
+                        wA * qB[1] + wB * qA[1] + (qA[2] * qB[0] - qA[0] * qB[2]),
+                        wA * qB[2] + wB * qA[2] + (qA[0] * qB[1] - qA[1] * qB[0])};
+        const double nE = sqrt(wE * wE + vE[0] * vE[0] + vE[1] * vE[1] + vE[2] * vE[2]);
+        const double sigma = (wE < 0) ? -1.0 : 1.0;
+        wE = sigma * wE / nE;
+        vE[0] = sigma * vE[0] / nE; vE[1] = sigma * vE[1] / nE; vE[2] = sigma * vE[2] / nE;
+        // skew matrices (row-major)
+        const double SA[9] = {0, -qA[2], qA[1], qA[2], 0, -qA[0], -qA[1], qA[0], 0};
+        const double SB[9] = {0, -qB[2], qB[1], qB[2], 0, -qB[0], -qB[1], qB[0], 0};
+        const double SE[9] = {0, -vE[2], vE[1], vE[2], 0, -vE[0], -vE[1], vE[0], 0};
+        const double St[9] = {0, -B[11], B[10], B[11], 0, -B[9], -B[10], B[9], 0};
+#pragma unroll
+        for(int i = 0; i < 72; i++) J[i] = 0;
+#pragma unroll
+        for(int r = 0; r < 3; r++)
+#pragma unroll
+            for(int c = 0; c < 3; c++) {
+                J[r + 6 * c] = -A[3 * r + c];
+                J[r + 6 * (3 + c)] = 2 * (A[3 * r] * St[c] + A[3 * r + 1] * St[3 + c] + A[3 * r + 2] * St[6 + c]);
+                J[36 + r + 6 * c] = E[3 * r + c];
+                const double sbsa = SB[3 * r] * SA[c] + SB[3 * r + 1] * SA[3 + c] + SB[3 * r + 2] * SA[6 + c];
+                const double M = (r == c ? wA * wB : 0.0) + wB * SA[3 * r + c] - wA * SB[3 * r + c] - sbsa - qB[r] * qA[c];
+                J[(3 + r) + 6 * (3 + c)] = -sigma * M;
+                J[36 + (3 + r) + 6 * (3 + c)] = (r == c ? wE : 0.0) + SE[3 * r + c];
+            }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// cooperative dense linear algebra on shared-memory matrices (column-major)
+// ------------------------------------------------------------------------------------------
+
+// In-place lower Cholesky A = L L^T of the leading n x n block (reads the lower triangle).
+// Returns false (uniformly) if a pivot is not > 0. Right-looking, thread per row.
+template <int NT>
+__device__ bool chol_lower(double *A, int n, int ld) {
+    const int tid = threadIdx.x;
+    for(int j = 0; j < n; j++) {
+        const double ajj = A[j + j * ld];
+        if(!(ajj > 0)) return false; // uniform: every thread reads the same value
+        const double inv = 1.0 / sqrt(ajj);
+        for(int i = j + 1 + tid; i < n; i += NT) A[i + j * ld] *= inv;
+        gsync<NT>();
+        for(int i = j + 1 + tid; i < n; i += NT) {
+            const double lij = A[i + j * ld];
+            for(int l = j + 1; l <= i; l++) A[i + l * ld] -= lij * A[l + j * ld];
+        }
+        if(tid == 0) A[j + j * ld] = sqrt(ajj);
+        gsync<NT>();
+    }
+    return true;
+}
+
+// X = (L L^T)^-1 written to X (n x n, ldx) from the Cholesky factor L (lower, ld). Thread per
+// column: forward then backward substitution on its own column of X. No syncs inside.
+template <int NT>
+__device__ void chol_inverse(const double *L, int n, int ld, double *X, int ldx) {
+    for(int c = threadIdx.x; c < n; c += NT) {
+        double *x = X + (size_t) c * ldx;
+        for(int i = 0; i < c; i++) x[i] = 0;
+        // forward: L y = e_c
+        for(int i = c; i < n; i++) {
+            double s = (i == c) ? 1.0 : 0.0;
+            for(int p = c; p < i; p++) s -= L[i + p * ld] * x[p];
+            x[i] = s / L[i + i * ld];
+        }
+        // backward: L^T z = y
+        for(int i = n - 1; i >= 0; i--) {
+            double s = x[i];
+            for(int p = i + 1; p < n; p++) s -= L[p + i * ld] * x[p];
+            x[i] = s / L[i + i * ld];
+        }
+    }
+}
+
+// Parallel-order two-sided Jacobi eigen-decomposition of the symmetric n x n matrix A (ld),
+// destroying A (eigenvalues end on its diagonal) and accumulating eigenvectors in the columns
+// of V (ldv). cs: scratch of 2*((n+1)/2) doubles; red: one double of scratch.
+// Round-robin tournament ordering: (n_even - 1) rounds of n_even/2 disjoint rotations; each round
+// applies J^T A J as independent 2x2 blocks (Brent-Luk), then V J.
+// Returns the number of sweeps used, or -1 if not converged.
+template <int NT>
+__device__ int jacobi_eig(double *A, int n, int ld, double *V, int ldv, double *cs, double *red) {
+    const int tid = threadIdx.x;
+    for(int t = tid; t < n * n; t += NT) {
+        int i = t % n, j = t / n;
+        V[i + j * ldv] = (i == j) ? 1.0 : 0.0;
+    }
+    if(n < 2) {
+        gsync<NT>();
+        return 0;
+    }
+    const int ne = (n + 1) & ~1, np = ne / 2;
+    // scale = max |diag| (>= every |a_ij| for PSD input, a good size proxy otherwise)
+    if(tid == 0) {
+        double m = 0;
+        for(int i = 0; i < n; i++) m = fmax(m, fabs(A[i + i * ld]));
+        for(int j = 0; j < n; j++)
+            for(int i = 0; i < n; i++) m = fmax(m, fabs(A[i + j * ld]));
+        red[0] = m;
+    }
+    gsync<NT>();
+    const double scale = red[0];
+    const double tol = 4.0 * 2.220446049250313e-16 * scale;
+    gsync<NT>();
+    const int max_sweeps = 30;
+    for(int sweep = 0; sweep < max_sweeps; sweep++) {
+        double mymax = 0;
+        for(int r = 0; r < ne - 1; r++) {
+            // phase 1: rotation parameters of the np pairs of this round
+            for(int i = tid; i < np; i += NT) {
+                int p, q;
+                if(i == 0) { p = ne - 1; q = r; }
+                else { p = (r + i) % (ne - 1); q = (r - i + ne - 1) % (ne - 1); }
+                if(p > q) { int tmp = p; p = q; q = tmp; }
+                double c = 1.0, s = 0.0;
+                if(q < n) {
+                    const double apq = A[p + q * ld];
+                    mymax = fmax(mymax, fabs(apq));
+                    if(fabs(apq) > 1e-300) {
+                        const double app = A[p + p * ld], aqq = A[q + q * ld];
+                        const double tau = (aqq - app) / (2.0 * apq);
+                        const double t = (tau >= 0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+                        c = 1.0 / sqrt(1.0 + t * t);
+                        s = t * c;
+                    }
+                }
+                cs[2 * i] = c;
+                cs[2 * i + 1] = s;
+            }
+            gsync<NT>();
+            // phase 2: A <- J^T A J on (pair, pair) blocks; V <- V J on (row, pair)
+            const int nblk = np * np;
+            for(int t = tid; t < nblk + n * np; t += NT) {
+                if(t < nblk) {
+                    const int i1 = t % np, i2 = t / np;
+                    int p1, q1, p2, q2;
+                    if(i1 == 0) { p1 = ne - 1; q1 = r; } else { p1 = (r + i1) % (ne - 1); q1 = (r - i1 + ne - 1) % (ne - 1); }
+                    if(i2 == 0) { p2 = ne - 1; q2 = r; } else { p2 = (r + i2) % (ne - 1); q2 = (r - i2 + ne - 1) % (ne - 1); }
+                    if(p1 > q1) { int tmp = p1; p1 = q1; q1 = tmp; }
+                    if(p2 > q2) { int tmp = p2; p2 = q2; q2 = tmp; }
+                    const bool v1 = q1 < n, v2 = q2 < n; // a pair with the padding index is a no-op
+                    const double c1 = cs[2 * i1], s1 = cs[2 * i1 + 1], c2 = cs[2 * i2], s2 = cs[2 * i2 + 1];
+                    // rows p1,q1 ; cols p2,q2 (q may be the padding index -> skip those entries)
+                    double b00 = A[p1 + p2 * ld];
+                    double b01 = v2 ? A[p1 + q2 * ld] : 0.0;
+                    double b10 = v1 ? A[q1 + p2 * ld] : 0.0;
+                    double b11 = (v1 && v2) ? A[q1 + q2 * ld] : 0.0;
+                    // left: rows <- R1^T rows  (row p = c*rp - s*rq ; row q = s*rp + c*rq)
+                    const double r00 = c1 * b00 - s1 * b10, r01 = c1 * b01 - s1 * b11;
+                    const double r10 = s1 * b00 + c1 * b10, r11 = s1 * b01 + c1 * b11;
+                    // right: cols <- cols R2  (col p = c*cp - s*cq ; col q = s*cp + c*cq)
+                    b00 = c2 * r00 - s2 * r01; b01 = s2 * r00 + c2 * r01;
+                    b10 = c2 * r10 - s2 * r11; b11 = s2 * r10 + c2 * r11;
+                    if(i1 == i2) { // diagonal block: off-diagonal is annihilated exactly
+                        if(v1) { b01 = 0.0; b10 = 0.0; }
+                    }
+                    A[p1 + p2 * ld] = b00;
+                    if(v2) A[p1 + q2 * ld] = b01;
+                    if(v1) A[q1 + p2 * ld] = b10;
+                    if(v1 && v2) A[q1 + q2 * ld] = b11;
+                } else {
+                    const int u = t - nblk;
+                    const int row = u % n, i2 = u / n;
+                    int p2, q2;
+                    if(i2 == 0) { p2 = ne - 1; q2 = r; } else { p2 = (r + i2) % (ne - 1); q2 = (r - i2 + ne - 1) % (ne - 1); }
+                    if(p2 > q2) { int tmp = p2; p2 = q2; q2 = tmp; }
+                    if(q2 < n) {
+                        const double c2 = cs[2 * i2], s2 = cs[2 * i2 + 1];
+                        const double vp = V[row + p2 * ldv], vq = V[row + q2 * ldv];
+                        V[row + p2 * ldv] = c2 * vp - s2 * vq;
+                        V[row + q2 * ldv] = s2 * vp + c2 * vq;
+                    }
+                }
+            }
+            gsync<NT>();
+        }
+        // converged when every off-diagonal entry seen in this sweep was below tol
+        unsigned conv = (mymax <= tol);
+        int all;
+        if constexpr(NT <= 32) all = __all_sync(0xffffffffu, conv);
+        else all = __syncthreads_and((int) conv);
+        if(all) return sweep + 1;
+    }
+    return -1;
+}
+
+} // namespace spg

@@ -1,0 +1,645 @@
+// spg_kernels.cuh — the fused blanket kernel (sm_100a): one CTA per Markov blanket runs the whole
+// per-vertex body of VertexRemover::remove (reference src/vertex_remover.cpp:89-139) on chip:
+//   R3  assembly  H = sum_e J^T Omega J                (g2o buildSystem, vertex_remover.cpp:397-409)
+//   R4  Schur     Lambda_t = H_kk - H_mk^T H_mm^-1 H_mk (vertex_remover.cpp:443-449)
+//   R5  Chow-Liu  C = (Lambda_t + I)^-1, MI weights, max-heap Kruskal (pseudo_chow_liu.cpp)
+//   R7  Jacobians of the new edges at zero error       (vertex_remover.cpp:466-498)
+//   R8  NFR closed form: eig(Lambda_t), Sigma blocks, X_e = (J Sigma J^T)^-1 (logdet_function.cpp:14-64,236-279)
+// H, Lambda_t, C and the eigenvectors never leave shared memory; HBM sees the packed record in and
+// the substitute-edge record out (SURVEY.md §8d "compulsory traffic").
+#pragma once
+#include "../../include/spg_capi.h"
+#include "../../include/spg_record.h"
+#include "spg_device.cuh"
+
+namespace spg {
+
+struct KernelParams {
+    int32_t algorithm, topology;
+    double chord_ratio;
+    int32_t n_list;              // blankets handled by this launch
+    const int32_t *list;         // their indices (NULL: identity)
+    const int64_t *rec_off;
+    const uint64_t *records;
+    const int64_t *out_off;
+    uint64_t *out;
+    double *dbg_target;
+    const int64_t *dbg_target_off;
+    double *dbg_weights;
+    const int64_t *dbg_weights_off;
+    // shared-memory carve-up of this bucket (all in doubles)
+    int32_t max_nv, max_e, max_rec_words;
+    int32_t off_pose, off_buf0, off_buf1, off_buf2, off_small, total_doubles;
+    int32_t buf0_doubles, buf1_doubles, buf2_doubles;
+};
+
+constexpr int ASM_CHUNK = 8; // edges linearised per pre-pass
+
+// Host-side: shared-memory layout for a bucket with at most max_nv vertices (n_removed >= 1),
+// max_e edges and max_rec_words record words.
+template <int D>
+inline void plan_smem(KernelParams &p) {
+    const int PS = PoseStride<D>::value;
+    const int N = D * p.max_nv;
+    const int kmax = D * (p.max_nv - 1);
+    const int nk = p.max_nv - 1;
+    const int pairs = nk * (nk - 1) / 2;
+    int o = p.max_rec_words;             // record copy
+    p.off_pose = o;  o += p.max_nv * PS;
+    p.off_buf0 = o;
+    p.buf0_doubles = N * odd_ld(N);
+    o += p.buf0_doubles;
+    p.off_buf1 = o;
+    int b1 = kmax * odd_ld(kmax > 0 ? kmax : 1);
+    int asm_scratch = ASM_CHUNK * 2 * (D * 2 * D);
+    p.buf1_doubles = b1 > asm_scratch ? b1 : asm_scratch;
+    o += p.buf1_doubles;
+    p.off_buf2 = o;
+    p.buf2_doubles = (nk >= 3) ? b1 : 0; // pseudo-covariance C; only blankets with >= 3 kept vertices run Chow-Liu
+    o += p.buf2_doubles;
+    p.off_small = o;
+    // small: w[kmax] order[kmax](int) cs[kmax+2] red[8] weights[pairs] heapw[pairs] heapab[pairs] (int2)
+    //        tree[2*max(pairs,1)] (int) uf[nk] (int) Lfac[nk*D*D] logd[nk] misc[16]
+    o += kmax + (kmax + 1) / 2 + (kmax + 2) + 8 + pairs + pairs + pairs + (pairs > 0 ? pairs : 1) + (nk + 1) / 2 + 1 +
+         nk * D * D + nk + 16;
+    p.total_doubles = o;
+}
+
+// std::priority_queue<WeightedEdge> emulation (libstdc++ __push_heap / __adjust_heap), compared on
+// weight only (pseudo_chow_liu.h:49-53) so that equal weights pop in the reference's order.
+struct HeapView {
+    double *w;
+    int *ab; // packed a | b << 16
+    int len;
+    __device__ void push(double vw, int vab) {
+        int hole = len++;
+        int parent = (hole - 1) / 2;
+        while(hole > 0 && w[parent] < vw) {
+            w[hole] = w[parent]; ab[hole] = ab[parent];
+            hole = parent;
+            parent = (hole - 1) / 2;
+        }
+        w[hole] = vw; ab[hole] = vab;
+    }
+    __device__ void pop(double &tw, int &tab) {
+        tw = w[0]; tab = ab[0];
+        if(len > 1) {
+            const int n = len - 1;
+            const double vw = w[n];
+            const int vab = ab[n];
+            w[n] = w[0]; ab[n] = ab[0];
+            int hole = 0, second = 0;
+            while(second < (n - 1) / 2) {
+                second = 2 * (second + 1);
+                if(w[second] < w[second - 1]) second--;
+                w[hole] = w[second]; ab[hole] = ab[second];
+                hole = second;
+            }
+            if((n & 1) == 0 && second == (n - 2) / 2) {
+                second = 2 * (second + 1);
+                w[hole] = w[second - 1]; ab[hole] = ab[second - 1];
+                hole = second - 1;
+            }
+            int parent = (hole - 1) / 2;
+            while(hole > 0 && w[parent] < vw) {
+                w[hole] = w[parent]; ab[hole] = ab[parent];
+                hole = parent;
+                parent = (hole - 1) / 2;
+            }
+            w[hole] = vw; ab[hole] = vab;
+        }
+        len--;
+    }
+};
+
+// log-determinant pieces of the Chow-Liu weight (pseudo_chow_liu.cpp:169-183), all in registers.
+// Lj: Cholesky factor of C_jj is not needed; we use
+//   logdet C_{ij,ij} = logdet C_ii + logdet (C_jj - C_ji C_ii^-1 C_ij)
+// with Li = chol(C_ii) from shared memory (column-major D x D, lower).
+template <int D>
+__device__ __forceinline__ double schur_logdet(const double *C, int ld, int i, int j, const double *Li) {
+    double Y[D][D]; // Y = Li^-1 * C_ji^T   (C_ji = rows of j, cols of i: the lower-triangle block)
+#pragma unroll
+    for(int c = 0; c < D; c++) {
+#pragma unroll
+        for(int r = 0; r < D; r++) {
+            double s = C[(j * D + c) + (i * D + r) * ld];
+#pragma unroll
+            for(int p = 0; p < r; p++) s -= Li[r + p * D] * Y[p][c];
+            Y[r][c] = s / Li[r + r * D];
+        }
+    }
+    double S[D][D];
+#pragma unroll
+    for(int c = 0; c < D; c++)
+#pragma unroll
+        for(int r = c; r < D; r++) {
+            double s = C[(j * D + r) + (j * D + c) * ld];
+#pragma unroll
+            for(int p = 0; p < D; p++) s -= Y[p][r] * Y[p][c];
+            S[r][c] = s;
+        }
+    // LDL^T without pivoting; logdet = sum log d
+    double ld_sum = 0;
+    double dinv[D];
+#pragma unroll
+    for(int c = 0; c < D; c++) {
+        double d = S[c][c];
+#pragma unroll
+        for(int p = 0; p < c; p++) d -= S[c][p] * S[c][p] * dinv[p]; // l_cp^2 d_p, with S[c][p] = l_cp * d_p
+        ld_sum += log(d);
+        dinv[c] = 1.0 / d;
+#pragma unroll
+        for(int r = c + 1; r < D; r++) {
+            double s = S[r][c];
+#pragma unroll
+            for(int p = 0; p < c; p++) s -= S[r][p] * S[c][p] * dinv[p];
+            S[r][c] = s; // = l_rc * d_c
+        }
+    }
+    return ld_sum;
+}
+
+// D x D Cholesky in registers -> Lout (column-major), returns logdet. ok=false if not PD.
+template <int D>
+__device__ __forceinline__ double chol_small(const double *A, int ld, double *Lout, bool &ok) {
+    double L[D][D];
+    double lds = 0;
+    ok = true;
+#pragma unroll
+    for(int c = 0; c < D; c++) {
+        double d = A[c + c * ld];
+#pragma unroll
+        for(int p = 0; p < c; p++) d -= L[c][p] * L[c][p];
+        if(!(d > 0)) { ok = false; d = 1.0; }
+        const double l = sqrt(d);
+        L[c][c] = l;
+        lds += log(d);
+#pragma unroll
+        for(int r = c + 1; r < D; r++) {
+            double s = A[r + c * ld];
+#pragma unroll
+            for(int p = 0; p < c; p++) s -= L[r][p] * L[c][p];
+            L[r][c] = s / l;
+        }
+    }
+#pragma unroll
+    for(int c = 0; c < D; c++)
+#pragma unroll
+        for(int r = 0; r < D; r++) Lout[r + c * D] = (r >= c) ? L[r][c] : 0.0;
+    return lds;
+}
+
+// X = A^-1 for a symmetric PD D x D matrix (reads the lower triangle, column-major ld=D), via LLT
+// like Eigen's chol.solve(Identity) (logdet_function.cpp:273-274). Xout column-major.
+template <int D>
+__device__ __forceinline__ bool spd_inverse_small(const double *A, double *Xout) {
+    double L[D * D];
+    bool ok;
+    chol_small<D>(A, D, L, ok);
+    if(!ok) return false;
+#pragma unroll
+    for(int c = 0; c < D; c++) {
+        double x[D];
+#pragma unroll
+        for(int i = 0; i < D; i++) {
+            double s = (i == c) ? 1.0 : 0.0;
+#pragma unroll
+            for(int p = 0; p < i; p++) s -= L[i + p * D] * x[p];
+            x[i] = s / L[i + i * D];
+        }
+#pragma unroll
+        for(int i = D - 1; i >= 0; i--) {
+            double s = x[i];
+#pragma unroll
+            for(int p = i + 1; p < D; p++) s -= L[p + i * D] * x[p];
+            x[i] = s / L[i + i * D];
+        }
+#pragma unroll
+        for(int i = 0; i < D; i++) Xout[i + c * D] = x[i];
+    }
+    return true;
+}
+
+
+// pair index (a | b << 16) helpers
+__device__ __forceinline__ int pk(int a, int b) { return a | (b << 16); }
+__device__ __forceinline__ int pk_a(int v) { return v & 0xffff; }
+__device__ __forceinline__ int pk_b(int v) { return v >> 16; }
+
+template <int D, int NT>
+__global__ void __launch_bounds__(NT) blanket_kernel(const KernelParams P) {
+    extern __shared__ double smem[];
+    constexpr int PS = PoseStride<D>::value;
+    constexpr int PW = (D == 6) ? 7 : 3; // pose words in records
+    constexpr int JW = D * 2 * D;        // doubles of one edge Jacobian [Ji Jj]
+    constexpr int SW = 4 * D * D;        // doubles of one 2D x 2D block
+    const int tid = threadIdx.x;
+
+    uint64_t *s_rec = reinterpret_cast<uint64_t *>(smem);
+    double *s_pose = smem + P.off_pose;
+    double *buf0 = smem + P.off_buf0;
+    double *buf1 = smem + P.off_buf1;
+    double *buf2 = smem + P.off_buf2;
+    double *s_small = smem + P.off_small;
+    const int kmax = D * (P.max_nv - 1);
+    const int nkmax = P.max_nv - 1;
+    const int pairs_max = nkmax * (nkmax - 1) / 2;
+    // carve the small region (sizes must match plan_smem)
+    double *s_w = s_small;
+    int *s_order = reinterpret_cast<int *>(s_w + kmax);
+    double *s_cs = s_w + kmax + (kmax + 1) / 2;
+    double *s_red = s_cs + (kmax + 2);
+    double *s_wt = s_red + 8;
+    double *s_heapw = s_wt + pairs_max;
+    int *s_heapab = reinterpret_cast<int *>(s_heapw + pairs_max);
+    int *s_tree = reinterpret_cast<int *>(s_heapw + 2 * pairs_max);
+    int *s_uf = reinterpret_cast<int *>(s_heapw + 2 * pairs_max + (pairs_max > 0 ? pairs_max : 1));
+    double *s_Lfac = s_heapw + 2 * pairs_max + (pairs_max > 0 ? pairs_max : 1) + (nkmax + 1) / 2 + 1;
+    double *s_logd = s_Lfac + nkmax * D * D;
+    int *s_misc = reinterpret_cast<int *>(s_logd + nkmax);
+
+    for(int li = blockIdx.x; li < P.n_list; li += gridDim.x) {
+        const int b = P.list ? P.list[li] : li;
+        const uint64_t *grec = P.records + P.rec_off[b];
+        uint64_t *gout = P.out + P.out_off[b];
+        const int out_words = (int) (P.out_off[b + 1] - P.out_off[b]);
+        const int32_t *gh = reinterpret_cast<const int32_t *>(grec);
+        const int nv = gh[0], nrem = gh[1], ne = gh[2], rdim = gh[3], rec_words = gh[4];
+        const int nk = nv - nrem;
+        const int N = D * nv, m = D * nrem, k = D * nk;
+        const int ldH = odd_ld(N);
+        const int ldk = odd_ld(k > 0 ? k : 1);
+
+        int status = SPG_BLANKET_OK;
+        if(rdim != D || nv > P.max_nv || ne > P.max_e || rec_words > P.max_rec_words || nrem < 1 || nk < 0)
+            status = SPG_BLANKET_TOO_LARGE;
+
+        // zero the output record (unused slots must read as zeros)
+        for(int t = tid; t < out_words; t += NT) gout[t] = 0;
+        gsync<NT>(); // also protects the shared buffers of the previous blanket
+
+        if(status != SPG_BLANKET_OK) {
+            if(tid == 0) reinterpret_cast<int32_t *>(gout)[0] = status;
+            continue;
+        }
+
+        // ---- S0: stage the record in shared memory, expand poses ---------------------------------
+        for(int t = tid; t < rec_words; t += NT) s_rec[t] = grec[t];
+        if(tid == 0) { s_misc[0] = SPG_BLANKET_OK; s_misc[1] = 0; }
+        gsync<NT>();
+        const double *r_pose = reinterpret_cast<const double *>(s_rec + spgr_poses_off(nv));
+        const int32_t *r_etab = reinterpret_cast<const int32_t *>(s_rec + spgr_edgetab_off(D, nv));
+        for(int v = tid; v < nv; v += NT) {
+            if constexpr(D == 6) se3_from_flat(r_pose + PW * v, s_pose + PS * v);
+            else se2_from_flat(r_pose + PW * v, s_pose + PS * v);
+        }
+        for(int t = tid; t < N * ldH; t += NT) buf0[t] = 0.0;
+        gsync<NT>();
+
+        // ---- S1: assembly H = sum_e J^T Omega J (edge order = record order) -------------------------
+        double *H = buf0;
+        for(int e0 = 0; e0 < ne; e0 += ASM_CHUNK) {
+            const int ce = min(ASM_CHUNK, ne - e0);
+            for(int e = tid; e < ce; e += NT) { // linearise: one thread per edge
+                const uint64_t *ew = s_rec + r_etab[e0 + e];
+                const int32_t *eh = reinterpret_cast<const int32_t *>(ew);
+                double *J = buf1 + (size_t) e * 2 * JW;
+                if(eh[0] == SPG_EDGE_POSE && eh[1] == 2) {
+                    const int32_t *vi = reinterpret_cast<const int32_t *>(ew + 2);
+                    const double *pl = reinterpret_cast<const double *>(ew + 3);
+                    double Z[PS];
+                    if constexpr(D == 6) se3_from_flat(pl, Z);
+                    else se2_from_flat(pl, Z);
+                    edge_jacobians<D>(Z, s_pose + PS * vi[0], s_pose + PS * vi[1], J);
+                } else {
+                    s_misc[0] = SPG_BLANKET_UNSUPPORTED;
+                    for(int q = 0; q < JW; q++) J[q] = 0;
+                }
+            }
+            gsync<NT>();
+            for(int t = tid; t < ce * JW; t += NT) { // M = Omega * J  (D x 2D per edge)
+                const int e = t / JW, q = t % JW, r = q % D, c = q / D;
+                const uint64_t *ew = s_rec + r_etab[e0 + e];
+                const double *Om = reinterpret_cast<const double *>(ew + 3) + PW; // column-major D x D
+                const double *J = buf1 + (size_t) e * 2 * JW;
+                double s = 0;
+#pragma unroll
+                for(int p = 0; p < D; p++) s += Om[r + p * D] * J[p + c * D];
+                buf1[(size_t) e * 2 * JW + JW + q] = s;
+            }
+            gsync<NT>();
+            for(int e = 0; e < ce; e++) { // sequential over edges: fixed summation order
+                const uint64_t *ew = s_rec + r_etab[e0 + e];
+                const int32_t *vi = reinterpret_cast<const int32_t *>(ew + 2);
+                const int va = vi[0], vb = vi[1];
+                const double *J = buf1 + (size_t) e * 2 * JW;
+                const double *M = J + JW;
+                for(int t = tid; t < SW; t += NT) {
+                    const int r = t % (2 * D), c = t / (2 * D);
+                    double s = 0;
+#pragma unroll
+                    for(int p = 0; p < D; p++) s += J[p + r * D] * M[p + c * D];
+                    const int gr = (r < D ? va * D + r : vb * D + r - D);
+                    const int gc = (c < D ? va * D + c : vb * D + c - D);
+                    H[gr + gc * ldH] += s;
+                }
+                gsync<NT>();
+            }
+        }
+        if(s_misc[0] != SPG_BLANKET_OK) status = s_misc[0];
+
+        // ---- S2: Schur complement onto the kept variables ----------------------------------------
+        if(status == SPG_BLANKET_OK) {
+            if(!chol_lower<NT>(H, m, ldH)) status = SPG_BLANKET_NOT_PD_MARGINAL;
+        }
+        double *T = H + m + (size_t) m * ldH; // Lambda_t in place, leading dimension ldH
+        if(status == SPG_BLANKET_OK && k > 0) {
+            for(int c = m + tid; c < N; c += NT) { // Y = L^-1 H_mk : thread per kept column
+                double *y = H + (size_t) c * ldH;
+                for(int i = 0; i < m; i++) {
+                    double s = y[i];
+                    for(int p = 0; p < i; p++) s -= H[i + p * ldH] * y[p];
+                    y[i] = s / H[i + i * ldH];
+                }
+            }
+            gsync<NT>();
+            // Lambda_t = H_kk - Y^T Y; upper triangle mirrored to the lower (vertex_remover.cpp:447-449)
+            for(int t = tid; t < k * k; t += NT) {
+                const int i = t % k, j = t / k;
+                if(i <= j) {
+                    const double *yi = H + (size_t) (m + i) * ldH, *yj = H + (size_t) (m + j) * ldH;
+                    double s = 0;
+                    for(int p = 0; p < m; p++) s += yi[p] * yj[p];
+                    const double v = T[i + (size_t) j * ldH] - s;
+                    T[i + (size_t) j * ldH] = v;
+                    if(i != j) T[j + (size_t) i * ldH] = v;
+                }
+            }
+            gsync<NT>();
+            if(P.dbg_target) {
+                double *g = P.dbg_target + P.dbg_target_off[b];
+                if(P.dbg_target_off[b + 1] - P.dbg_target_off[b] >= (int64_t) k * k)
+                    for(int t = tid; t < k * k; t += NT) g[t] = T[(t % k) + (size_t) (t / k) * ldH];
+            }
+        }
+
+        // ---- S3: sparsity pattern (PseudoChowLiu::computeSparsityPattern, pseudo_chow_liu.cpp:33-87) ---
+        int n_out = 0;
+        if(status == SPG_BLANKET_OK && P.algorithm == SPG_ALG_NFR && nk >= 2) {
+            const int mch = (int) ((1 + P.chord_ratio) * (nk - 1));
+            const int all = nk * (nk - 1) / 2;
+            const bool full = mch >= all;
+            const bool cliquey = (P.topology == SPG_TOPO_CLIQUEY_DENSE || P.topology == SPG_TOPO_CLIQUEY_SUBGRAPH);
+            if(nk == 2) {
+                n_out = 1;
+                if(tid == 0) s_tree[0] = pk(0, 1);
+            } else if(cliquey) {
+                status = SPG_BLANKET_UNSUPPORTED; // correlated (MultiEdgeCorrelated) outputs: host path, see DESIGN.md
+            } else if(P.topology == SPG_TOPO_DENSE || (P.topology == SPG_TOPO_SUBGRAPH && full)) {
+                n_out = all;
+                for(int t = tid; t < all; t += NT) {
+                    int i = 0, rem = t;
+                    while(rem >= nk - 1 - i) { rem -= nk - 1 - i; i++; }
+                    s_tree[t] = pk(i, i + 1 + rem);
+                }
+            } else {
+                n_out = (P.topology == SPG_TOPO_TREE) ? nk - 1 : mch;
+                // C = (Lambda_t + 1 I)^-1  (fillEdges, pseudo_chow_liu.cpp:185-190)
+                double *Lc = buf1, *C = buf2;
+                for(int t = tid; t < k * k; t += NT) {
+                    const int i = t % k, j = t / k;
+                    Lc[i + j * ldk] = T[i + (size_t) j * ldH] + (i == j ? 1.0 : 0.0);
+                }
+                gsync<NT>();
+                if(!chol_lower<NT>(Lc, k, ldk)) status = SPG_BLANKET_NOT_PD_CHOWLIU;
+                if(status == SPG_BLANKET_OK) {
+                    chol_inverse<NT>(Lc, k, ldk, C, ldk);
+                    gsync<NT>();
+                    // per-vertex Cholesky of the diagonal blocks + their log-determinants
+                    for(int v = tid; v < nk; v += NT) {
+                        bool ok;
+                        s_logd[v] = chol_small<D>(C + (size_t) v * D + (size_t) v * D * ldk, ldk, s_Lfac + v * D * D, ok);
+                        if(!ok) s_misc[0] = SPG_BLANKET_NOT_PD_CHOWLIU;
+                    }
+                    gsync<NT>();
+                    // weight(i,j) = logdet C_ii + logdet C_jj - logdet C_{ij,ij}   (:169-183)
+                    //             = logdet C_jj - logdet (C_jj - C_ji C_ii^-1 C_ij)
+                    for(int t = tid; t < all; t += NT) {
+                        int i = 0, rem = t;
+                        while(rem >= nk - 1 - i) { rem -= nk - 1 - i; i++; }
+                        const int j = i + 1 + rem;
+                        s_wt[t] = s_logd[j] - schur_logdet<D>(C, ldk, i, j, s_Lfac + i * D * D);
+                    }
+                    gsync<NT>();
+                    if(s_misc[0] != SPG_BLANKET_OK) status = s_misc[0];
+                    if(P.dbg_weights) {
+                        double *g = P.dbg_weights + P.dbg_weights_off[b];
+                        const int cap = (int) (P.dbg_weights_off[b + 1] - P.dbg_weights_off[b]);
+                        for(int t = tid; t < cap; t += NT) g[t] = t < all ? s_wt[t] : 0.0;
+                    }
+                    // doKruskal (:253-289): max-heap pops, accepted edges first then rejected
+                    if(tid == 0) {
+                        HeapView hp{s_heapw, s_heapab, 0};
+                        int t = 0;
+                        for(int i = 0; i < nk - 1; i++)
+                            for(int j = i + 1; j < nk; j++, t++) hp.push(s_wt[t], pk(i, j));
+                        for(int v = 0; v < nk; v++) s_uf[v] = v;
+                        int nacc = 0, nrej = 0;
+                        // rejected edges are staged at the tail of s_tree in reverse, then appended
+                        while(hp.len > 0) {
+                            double w; int ab;
+                            hp.pop(w, ab);
+                            int ra = pk_a(ab), rb = pk_b(ab);
+                            while(s_uf[ra] != ra) ra = s_uf[ra];
+                            while(s_uf[rb] != rb) rb = s_uf[rb];
+                            if(ra != rb) {
+                                s_uf[rb] = ra;
+                                s_tree[nacc++] = ab;
+                            } else {
+                                // heap storage behind the live heap is free: hp.len slots are in use
+                                s_heapab[all - 1 - nrej] = ab;
+                                nrej++;
+                            }
+                        }
+                        for(int q = 0; q < nrej; q++) s_tree[nacc + q] = s_heapab[all - 1 - q];
+                    }
+                    gsync<NT>();
+                }
+            }
+        }
+
+        // ---- S4: NFR information fit (optimizeInformation, optimizer.cpp:16-81) ------------------------
+        if(status == SPG_BLANKET_OK && P.algorithm == SPG_ALG_NFR && n_out > 0) {
+            gsync<NT>(); // s_tree visible
+            const int r = k - D;
+            const bool closed = (n_out * D == r); // hasClosedFormSolution, logdet_function.cpp:83-86
+            // eig(Lambda_t): A = T in place (destroyed), V in buf1
+            double *V = buf1;
+            const int sweeps = jacobi_eig<NT>(T, k, ldH, V, ldk, s_cs, s_red);
+            if(sweeps < 0) status = SPG_BLANKET_EIG_NOCONV;
+            for(int i = tid; i < k; i += NT) s_w[i] = T[i + (size_t) i * ldH];
+            gsync<NT>();
+            // ascending order (SelfAdjointEigenSolver sorts increasingly); ties by index
+            int mysmall = 0;
+            for(int i = tid; i < k; i += NT) {
+                const double wi = s_w[i];
+                int rank = 0;
+                for(int j = 0; j < k; j++) {
+                    const double wj = s_w[j];
+                    rank += (wj < wi) || (wj == wi && j < i);
+                }
+                s_order[rank] = i;
+                if(wi < 1e-5) mysmall++;
+            }
+            if(mysmall) atomicAdd(&s_misc[1], mysmall);
+            gsync<NT>();
+            const int smalleigs = s_misc[1];
+            // new-edge Jacobians at the linearisation point with measurement == state (:466-498),
+            // measurements written straight to the output record
+            double *Jn = buf0;                       // n_out * JW   (buf0 is free: eigenvalues are saved)
+            double *Sg = buf0 + (size_t) n_out * JW; // n_out * SW
+            double *Bk = Sg + (size_t) n_out * SW;   // n_out * D*D
+            const int slot = 1 + PW + D * D;
+            for(int e = tid; e < n_out; e += NT) {
+                const int a = pk_a(s_tree[e]), bb = pk_b(s_tree[e]);
+                const double *Xa = s_pose + PS * (nrem + a), *Xb = s_pose + PS * (nrem + bb);
+                double Z[PS], Ti[PS];
+                if constexpr(D == 6) { se3_inverse(Xa, Ti); se3_compose(Ti, Xb, Z); }
+                else { se2_inverse(Xa, Ti); se2_compose(Ti, Xb, Z); }
+                edge_jacobians<D>(Z, Xa, Xb, Jn + (size_t) e * JW);
+                uint64_t *sl = gout + SPG_OUT_HEADER_WORDS + (size_t) e * slot;
+                int32_t *si = reinterpret_cast<int32_t *>(sl);
+                si[0] = a; si[1] = bb;
+                double *sm = reinterpret_cast<double *>(sl + 1);
+                if constexpr(D == 6) se3_to_flat(Z, sm);
+                else { sm[0] = Z[0]; sm[1] = Z[1]; sm[2] = Z[2]; }
+            }
+            // S (inverse eigenvalues) and the kept eigen-directions, logdet_function.cpp:33-61
+            double *s_S = s_cs; // r values (cs is free after the eigen-solver)
+            int ooff = 0; // kept direction l is eigen-column s_order[ooff + l]
+            if(smalleigs <= D) {
+                ooff = D;
+                for(int l = tid; l < r; l += NT) s_S[l] = 1.0 / s_w[s_order[D + l]];
+                gsync<NT>();
+            } else {
+                // chooseDimensions (:66-81): among the `smalleigs` smallest directions drop the D with
+                // the smallest || J u ||  (sparseJacobian drops |J| < eps entries, :335)
+                gsync<NT>(); // Jn complete
+                double *cn = Bk; // || J u_c || per candidate (Bk is not in use yet)
+                for(int c = tid; c < smalleigs; c += NT) {
+                    const double *u = V + (size_t) s_order[c] * ldk;
+                    double acc = 0;
+                    for(int e = 0; e < n_out; e++) {
+                        const int a = pk_a(s_tree[e]), bb = pk_b(s_tree[e]);
+                        const double *J = Jn + (size_t) e * JW;
+                        for(int row = 0; row < D; row++) {
+                            double s = 0;
+                            for(int q = 0; q < D; q++) {
+                                const double ja = J[row + q * D], jb = J[row + (D + q) * D];
+                                if(fabs(ja) >= 2.220446049250313e-16) s += ja * u[a * D + q];
+                                if(fabs(jb) >= 2.220446049250313e-16) s += jb * u[bb * D + q];
+                            }
+                            acc += s * s;
+                        }
+                    }
+                    cn[c] = sqrt(acc);
+                }
+                gsync<NT>();
+                if(tid == 0) {
+                    // std::sort of (norm, index) pairs ascending; the first D are dropped
+                    const double wmax = s_w[s_order[k - 1]];
+                    int *drop = s_misc + 4;
+                    int nd = 0;
+                    for(int d0 = 0; d0 < D; d0++) {
+                        int best = -1;
+                        for(int c = 0; c < smalleigs; c++) {
+                            bool used = false;
+                            for(int q = 0; q < nd; q++) used |= (drop[q] == c);
+                            if(used) continue;
+                            if(best < 0 || cn[c] < cn[best]) best = c;
+                        }
+                        drop[nd++] = best;
+                    }
+                    int jj = 0;
+                    for(int i = 0; i < k; i++) { // in-place compaction (jj <= i)
+                        bool dropped = false;
+                        for(int q = 0; q < nd; q++) dropped |= (drop[q] == i);
+                        if(!dropped) {
+                            const int col = s_order[i];
+                            s_S[jj] = fmin(fabs(1.0 / s_w[col]), 1e6 / wmax);
+                            s_order[jj] = col;
+                            jj++;
+                        }
+                    }
+                }
+                gsync<NT>();
+            }
+            if(status == SPG_BLANKET_OK && !closed) status = SPG_BLANKET_UNSUPPORTED; // Newton/barrier loop: separate kernel
+            if(status == SPG_BLANKET_OK) {
+                // Sigma blocks: Sg_e = U[ab,:] S U[ab,:]^T, lower triangle mirrored up (:239-240)
+                for(int t = tid; t < n_out * SW; t += NT) {
+                    const int e = t / SW, q = t % SW, i = q % (2 * D), j = q / (2 * D);
+                    if(i >= j) {
+                        const int a = pk_a(s_tree[e]), bb = pk_b(s_tree[e]);
+                        const int ri = (i < D ? a * D + i : bb * D + i - D);
+                        const int rj = (j < D ? a * D + j : bb * D + j - D);
+                        double s = 0;
+                        for(int l = 0; l < r; l++) {
+                            const double *u = V + (size_t) s_order[ooff + l] * ldk;
+                            s += u[ri] * s_S[l] * u[rj];
+                        }
+                        Sg[(size_t) e * SW + i + j * 2 * D] = s;
+                        Sg[(size_t) e * SW + j + i * 2 * D] = s;
+                    }
+                }
+                gsync<NT>();
+                // block_e = J Sg_e J^T, symmetrised (:249-270)
+                for(int t = tid; t < n_out * D * D; t += NT) {
+                    const int e = t / (D * D), q = t % (D * D), rr = q % D, cc = q / D;
+                    if(rr >= cc) {
+                        const double *J = Jn + (size_t) e * JW;
+                        const double *S2 = Sg + (size_t) e * SW;
+                        double s1 = 0, s2 = 0;
+                        for(int j = 0; j < 2 * D; j++) {
+                            double tr = 0, tc = 0;
+#pragma unroll
+                            for(int i = 0; i < 2 * D; i++) {
+                                tr += J[rr + i * D] * S2[i + j * 2 * D];
+                                tc += J[cc + i * D] * S2[i + j * 2 * D];
+                            }
+                            s1 += tr * J[cc + j * D];
+                            s2 += tc * J[rr + j * D];
+                        }
+                        const double v = 0.5 * (s1 + s2);
+                        Bk[(size_t) e * D * D + rr + cc * D] = v;
+                        Bk[(size_t) e * D * D + cc + rr * D] = v;
+                    }
+                }
+                gsync<NT>();
+                // X_e = block_e^-1 through LLT (:273-274), straight to the output record
+                for(int e = tid; e < n_out; e += NT) {
+                    double X[D * D];
+                    const bool ok = spd_inverse_small<D>(Bk + (size_t) e * D * D, X);
+                    if(!ok) s_misc[0] = SPG_BLANKET_NOT_PD_CLOSED;
+                    double *sx = reinterpret_cast<double *>(gout + SPG_OUT_HEADER_WORDS + (size_t) e * slot + 1 + PW);
+#pragma unroll
+                    for(int q = 0; q < D * D; q++) sx[q] = ok ? X[q] : 0.0;
+                }
+                gsync<NT>();
+                if(s_misc[0] != SPG_BLANKET_OK) status = s_misc[0];
+            }
+        }
+
+        gsync<NT>();
+        if(tid == 0) {
+            int32_t *oh = reinterpret_cast<int32_t *>(gout);
+            oh[0] = status;
+            oh[1] = (status == SPG_BLANKET_OK) ? n_out : 0;
+            oh[2] = 0;
+            oh[3] = 0;
+        }
+    }
+}
+
+} // namespace spg

@@ -1,0 +1,93 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path through the C ABI
+(libspg_b200.so, spg_remove_round) against the CPU oracle on the same packed records.
+Tolerances are BASELINE.json's: topology bit-exact, information matrices <= 1e-9 relative
+Frobenius."""
+import numpy as np
+import pytest
+
+from sparsifyposegraph_b200 import records as R
+from sparsifyposegraph_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+REL_FRO = 1e-9
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from sparsifyposegraph_b200 import capi
+    c = capi.Context(0)
+    yield c
+    c.close()
+
+
+def run_both(ctx, oracle, blk, algorithm, topology, chord_ratio=1.0):
+    from sparsifyposegraph_b200 import capi
+    dim, n, B = blk["dim"], blk["n"], blk["B"]
+    nk = R.n_kept_of(blk["records"], blk["rec_off"])
+    out_off = R.out_offsets(dim, algorithm, topology, chord_ratio, nk)
+    k = dim * (n - 1)
+    toff = np.arange(B + 1, dtype=np.int64) * k * k
+    woff = np.arange(B + 1, dtype=np.int64) * ((n - 1) * (n - 2) // 2)
+    o_opts = oracle.make_opts(topology, R.LIN_GLOBAL, chord_ratio)
+    g_opts = capi.make_opts(topology, R.LIN_GLOBAL, chord_ratio)
+    ref = oracle.remove_round(dim, algorithm, o_opts, blk["records"], blk["rec_off"], out_off, 0, toff, woff)
+    got = ctx.remove_round(dim, algorithm, g_opts, blk["records"], blk["rec_off"], out_off, None, toff, woff)
+    return out_off, ref, got
+
+
+def rel(a, b):
+    nb = np.linalg.norm(b)
+    return np.linalg.norm(a - b) / (nb if nb > 0 else 1.0)
+
+
+@pytest.mark.parametrize("dim,n,variant,B", [
+    (6, 2, "star", 64), (6, 3, "star", 64), (6, 3, "ring", 64), (6, 4, "ring", 128), (6, 5, "star", 256),
+    (6, 5, "ring", 512), (6, 6, "ring", 128), (6, 8, "ring", 64), (6, 12, "star", 32), (6, 16, "ring", 16),
+    (3, 3, "star", 64), (3, 5, "ring", 256), (3, 8, "ring", 64), (3, 14, "star", 32), (3, 24, "ring", 8),
+])
+def test_nfr_tree_parity(ctx, oracle, dim, n, variant, B):
+    blk = synth.make_blankets(n, B, dim=dim, variant=variant, seed=1000 + 10 * n + dim)
+    out_off, (ro, _, rt, rw), (go, gt, gw) = run_both(ctx, oracle, blk, R.ALG_NFR, R.TOPO_TREE)
+    k = dim * (n - 1)
+    worst_t = worst_x = 0.0
+    for b in range(B):
+        r = R.parse_out(ro, out_off, b, dim, R.ALG_NFR, R.TOPO_TREE, n - 1)
+        g = R.parse_out(go, out_off, b, dim, R.ALG_NFR, R.TOPO_TREE, n - 1)
+        assert g["status"] == r["status"] == 0, (b, g["status"], r["status"])
+        assert g["n_edges"] == r["n_edges"]
+        if n >= 3:
+            Tr = rt[b * k * k:(b + 1) * k * k]
+            Tg = gt[b * k * k:(b + 1) * k * k]
+            worst_t = max(worst_t, rel(Tg, Tr))
+        assert [e["v"] for e in g["edges"]] == [e["v"] for e in r["edges"]], b   # Chow-Liu topology bit-exact
+        for eg, er in zip(g["edges"], r["edges"]):
+            assert np.allclose(eg["meas"], er["meas"], atol=1e-12)
+            worst_x = max(worst_x, rel(eg["info"], er["info"]))
+    if n >= 4:
+        assert np.allclose(gw, rw, rtol=1e-9, atol=1e-10)
+    assert worst_t <= REL_FRO, worst_t
+    assert worst_x <= REL_FRO, worst_x
+
+
+def test_mixed_sizes_one_round(ctx, oracle):
+    """Blankets of different sizes in one round exercise the size buckets."""
+    from sparsifyposegraph_b200 import capi
+    recs, nks = [], []
+    for n in (2, 3, 5, 4, 9, 5, 16, 3, 7):
+        blk = synth.make_blankets(n, 3, dim=6, variant="ring", seed=50 + n)
+        W = blk["rec_off"][1]
+        for b in range(3):
+            recs.append(blk["records"][b * W:(b + 1) * W])
+            nks.append(n - 1)
+    records, rec_off = R.concat_records(recs)
+    out_off = R.out_offsets(6, R.ALG_NFR, R.TOPO_TREE, 1.0, nks)
+    ro, _, _, _ = oracle.remove_round(6, R.ALG_NFR, oracle.make_opts(0, 1), records, rec_off, out_off, 0)
+    go, _, _ = ctx.remove_round(6, R.ALG_NFR, capi.make_opts(0, 1), records, rec_off, out_off)
+    for b, nk in enumerate(nks):
+        r = R.parse_out(ro, out_off, b, 6, R.ALG_NFR, R.TOPO_TREE, nk)
+        g = R.parse_out(go, out_off, b, 6, R.ALG_NFR, R.TOPO_TREE, nk)
+        assert g["status"] == r["status"] == 0
+        assert [e["v"] for e in g["edges"]] == [e["v"] for e in r["edges"]]
+        for eg, er in zip(g["edges"], r["edges"]):
+            assert rel(eg["info"], er["info"]) <= REL_FRO
