@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py — vertices marginalised per second (SE3, fp64, NFR) on B200.
+
+Workload (BASELINE.json configs[3], the configuration the metric is quoted on that fits one GPU):
+the batched Markov-blanket sweep — synthetic SE3 blankets with n in {2,3,4,5,6,8,12,16} vertices
+(H 12x12 ... 96x96 fp64), `--blankets` (default 1e5) blankets per size, star+ring edge pattern,
+NFR with Chow-Liu Tree topology. One "step" = one pass of the node-removal hot path (assembly,
+Schur complement, Chow-Liu MI + spanning tree, NFR closed-form information fit) over the whole
+sweep. Every rank of a multi-GPU run owns its own sweep (weak scaling, no data-path collective).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--blankets B] [--impl reference]
+
+`value`  : device-resident inputs, CUDA events on the library's stream, max over ranks.
+`e2e`    : the same sweep through the host-buffer C-ABI call spg_remove_round (pinned host
+           records in, H2D + kernels + D2H inside the timed region).
+`--impl reference` times the CPU restatement of the reference path (oracle/) on all host threads
+over a bounded sample of the same sweep (the reference itself cannot be built offline).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from sparsifyposegraph_b200 import records as R  # noqa: E402
+from sparsifyposegraph_b200 import synth  # noqa: E402
+
+SIZES = (2, 3, 4, 5, 6, 8, 12, 16)
+VARIANT = "ring"
+METRIC = "vertices marginalized/sec (SE3 fp64, NFR)"
+UNIT = "vertices/s"
+
+
+def workload_config(blankets, n_gpus):
+    return {"workload": f"C4 batched Markov-blanket sweep: SE3, n in {list(SIZES)}, {blankets} blankets per size per GPU, "
+                        f"star+ring edges, NFR Chow-Liu tree (closed-form fit)",
+            "blankets_per_size": blankets, "sizes": list(SIZES), "topology": "tree", "algorithm": "nfr",
+            "lin_point": "global", "l2": "inputs larger than L2 (126 MB) at the default size; each blanket is read once",
+            "parallelism": f"blankets sharded over {n_gpus} GPU(s), no data-path collective"}
+
+
+def make_sweep(blankets, rank):
+    sweep = []
+    for n in SIZES:
+        blk = synth.make_blankets(n, blankets, dim=6, variant=VARIANT, seed=synth.SEED + n + 1000 * rank)
+        nk = np.full(blankets, n - 1, dtype=np.int64)
+        blk["out_off"] = R.out_offsets(6, R.ALG_NFR, R.TOPO_TREE, 1.0, nk)
+        sweep.append(blk)
+    return sweep
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                o = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                   capture_output=True, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.samples.append([x.strip() for x in o.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def start(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=6)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                mx.append(float(s[1]))
+            except Exception:
+                continue
+            for nme, v in zip(names, s[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_reference(args, rank, world):
+    """CPU arm: the oracle (restatement of the reference's CPU path) on all host threads."""
+    if rank != 0:
+        return
+    from oracle import pyoracle
+    pyoracle.build()
+    cores = os.cpu_count() or 1
+    S = args.ref_sample
+    sweep = []
+    for n in SIZES:
+        blk = synth.make_blankets(n, S, dim=6, variant=VARIANT, seed=synth.SEED + n)
+        blk["out_off"] = R.out_offsets(6, R.ALG_NFR, R.TOPO_TREE, 1.0, np.full(S, n - 1))
+        sweep.append(blk)
+    opts = pyoracle.make_opts(R.TOPO_TREE, R.LIN_GLOBAL, 1.0)
+
+    def step():
+        t = 0.0
+        for blk in sweep:
+            _, secs, _, _ = pyoracle.remove_round(6, R.ALG_NFR, opts, blk["records"], blk["rec_off"], blk["out_off"], cores)
+            t += secs
+        return t
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    total = len(SIZES) * S * args.steps
+    val = total / dt
+    sample = f"first {S} blankets of each of the {len(SIZES)} sizes per step (same generator and mix as the GPU arm)"
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args.blankets, args.gpus),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                             "note": "CPU restatement of the reference path (oracle/); the reference itself needs "
+                                     "Eigen/g2o/iSAM/CHOLMOD and cannot be built offline"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--blankets", type=int, default=100000, help="blankets per size per GPU")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--ref-sample", type=int, default=256, help="blankets per size per step for the CPU arms")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sizes", default=None, help="comma list overriding the size sweep (debug)")
+    args = ap.parse_args()
+    global SIZES
+    if args.sizes:
+        SIZES = tuple(int(x) for x in args.sizes.split(","))
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from sparsifyposegraph_b200 import capi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the node-removal path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = capi.Context(local_rank)
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local_rank))
+    opts = capi.make_opts(R.TOPO_TREE, R.LIN_GLOBAL, 1.0)
+
+    # ---- data: per-size device-resident records + one mixed host round for the e2e path -------------
+    sweep = make_sweep(args.blankets, rank)
+    dev = []
+    for blk in sweep:
+        d = {"n": blk["n"], "E": blk["E"], "B": blk["B"],
+             "rec": torch.from_numpy(blk["records"].view(np.int64)).cuda(),
+             "rec_off": torch.from_numpy(blk["rec_off"]).cuda(),
+             "out_off": torch.from_numpy(blk["out_off"]).cuda(),
+             "out": torch.zeros(int(blk["out_off"][-1]), dtype=torch.int64, device="cuda")}
+        dev.append(d)
+    total_blankets = sum(b["B"] for b in sweep)
+    # mixed host round (all sizes in one spg_remove_round call), pinned
+    rec_words = sum(len(b["records"]) for b in sweep)
+    out_words = sum(int(b["out_off"][-1]) for b in sweep)
+    h_rec = torch.empty(rec_words, dtype=torch.int64).pin_memory()
+    h_out = torch.empty(out_words, dtype=torch.int64).pin_memory()
+    h_rec_np = h_rec.numpy().view(np.uint64)
+    h_out_np = h_out.numpy().view(np.uint64)
+    rec_off_all = np.zeros(total_blankets + 1, dtype=np.int64)
+    out_off_all = np.zeros(total_blankets + 1, dtype=np.int64)
+    pr = po = pb = 0
+    for b in sweep:
+        n_r, n_o, nb = len(b["records"]), int(b["out_off"][-1]), b["B"]
+        h_rec_np[pr:pr + n_r] = b["records"]
+        rec_off_all[pb:pb + nb + 1] = b["rec_off"] + pr
+        out_off_all[pb:pb + nb + 1] = b["out_off"] + po
+        pr += n_r
+        po += n_o
+        pb += nb
+    h2d_bytes = rec_words * 8 + 2 * (total_blankets + 1) * 8 + total_blankets * 4
+    d2h_bytes = out_words * 8
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def device_step():
+        for d in dev:
+            ctx.remove_round_device(6, R.ALG_NFR, opts, d["B"], d["rec"].data_ptr(), d["rec_off"].data_ptr(),
+                                    d["out_off"].data_ptr(), d["out"].data_ptr(), d["n"], d["E"])
+
+    # ---- FP64 peak (roofline denominator; MEASURED_PEAKS.json has no FP64 figure) --------------------
+    fp64_peak = ctx.fp64_peak_tflops(5)
+
+    # ---- warm-up ------------------------------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        device_step()
+    ctx.sync()
+    barrier()
+
+    # ---- timed: device-resident ---------------------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = ctx.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    with torch.cuda.stream(stream):
+        ev0.record()
+        for _ in range(args.steps):
+            device_step()
+        ev1.record()
+    ctx.sync()
+    barrier()
+    dev_ms = ev0.elapsed_time(ev1)
+    launches = ctx.launches - launches0
+
+    # per-size kernel time (dominant kernel + roofline), one extra pass, events on the same stream
+    per_size = []
+    for d in dev:
+        with torch.cuda.stream(stream):
+            a, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            ctx.remove_round_device(6, R.ALG_NFR, opts, d["B"], d["rec"].data_ptr(), d["rec_off"].data_ptr(),
+                                    d["out_off"].data_ptr(), d["out"].data_ptr(), d["n"], d["E"])
+            b2.record()
+        ctx.sync()
+        ms = a.elapsed_time(b2)
+        alg = synth.algorithmic_bytes_flops(d["n"], d["E"], 6, "nfr")
+        per_size.append({"n": d["n"], "E": d["E"], "ms": ms, "vertices_per_s": d["B"] / (ms * 1e-3),
+                         "gflops": alg["flops"] * d["B"] / (ms * 1e-3) / 1e9,
+                         "gbs": alg["bytes"] * d["B"] / (ms * 1e-3) / 1e9})
+    clocks = sampler.stop()
+
+    # ---- timed: end to end through the host-buffer C ABI ----------------------------------------------
+    e2e_steps = max(1, min(args.steps, 3))
+    ctx.remove_round(6, R.ALG_NFR, opts, h_rec_np, rec_off_all, out_off_all, out=h_out_np)  # warm-up (allocations)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ctx.remove_round(6, R.ALG_NFR, opts, h_rec_np, rec_off_all, out_off_all, out=h_out_np)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    n_ok = int((h_out_np[out_off_all[:-1]].view(np.int32)[0::2] == 0).sum())
+
+    # ---- reduce over ranks ----------------------------------------------------------------------------
+    if world > 1:
+        t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_s = float(t[0]), float(t[1])
+        # the only collective of the multi-GPU path: gather the substitute-edge records (NCCL over
+        # NVLink); timed separately, outside the throughput region
+        small = dev[3]["out"][: min(len(dev[3]["out"]), 1 << 22)]
+        gathered = torch.empty(world * small.numel(), dtype=small.dtype, device="cuda")
+        torch.cuda.synchronize()
+        g0 = time.perf_counter()
+        dist.all_gather_into_tensor(gathered, small)
+        torch.cuda.synchronize()
+        gather_ms = 1e3 * (time.perf_counter() - g0)
+    else:
+        gather_ms = None
+
+    if rank == 0:
+        value = world * total_blankets * args.steps / (dev_ms * 1e-3)
+        e2e_value = world * total_blankets * e2e_steps / e2e_s
+        dom = max(per_size, key=lambda p: p["ms"])
+        alg = synth.algorithmic_bytes_flops(dom["n"], dom["E"], 6, "nfr")
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        roofline = {"bound": "fp64", "kernel": f"blanket_kernel<6,256> (n={dom['n']} bucket)",
+                    "achieved": dom["gflops"] / 1e3, "peak": fp64_peak, "unit": "TFLOP/s",
+                    "frac": dom["gflops"] / 1e3 / fp64_peak if fp64_peak else None,
+                    "peak_source": "measured here: register-resident DFMA loop on all SMs (spg_fp64_peak_probe); "
+                                   "MEASURED_PEAKS.json has no FP64 figure",
+                    "algorithmic_flops_per_blanket": alg["flops"], "algorithmic_bytes_per_blanket": alg["bytes"],
+                    "hbm": {"achieved": dom["gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": dom["gbs"] / hbm_peak,
+                            "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"},
+                    "traffic": None, "share_of_step": dom["ms"] / sum(p["ms"] for p in per_size)}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": workload_config(args.blankets, world),
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                        "steps": e2e_steps, "blankets_ok": n_ok, "blankets": total_blankets},
+                "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "per_size": per_size,
+                "fp64_peak_tflops_measured": fp64_peak, "gather_ms": gather_ms}
+        if not args.no_cpu_baseline:
+            from oracle import pyoracle
+            pyoracle.build()
+            cores = os.cpu_count() or 1
+            S = args.ref_sample
+            o_opts = pyoracle.make_opts(R.TOPO_TREE, R.LIN_GLOBAL, 1.0)
+            secs = 0.0
+            for blk in sweep:
+                W = int(blk["rec_off"][1])
+                nb = min(S, blk["B"])
+                _, s, _, _ = pyoracle.remove_round(6, R.ALG_NFR, o_opts, blk["records"][: nb * W], blk["rec_off"][: nb + 1],
+                                                   blk["out_off"][: nb + 1], cores)
+                secs += s
+            nb_total = sum(min(S, blk["B"]) for blk in sweep)
+            line["cpu_baseline"] = {"value": nb_total / secs, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"first {S} blankets of each size of this run's sweep, one blanket per thread"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()

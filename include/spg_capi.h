@@ -62,8 +62,10 @@ typedef struct {
     int32_t lin_point;            /* spg_lin_point */
     double  chord_ratio;
     int32_t include_intra_clique;
-    int32_t reserved;
+    int32_t flags;                /* library extension, 0 = default. SPG_OPT_FORCE_EIGEN: always run the
+                                     eigen-decomposition NFR path (disable the gauge shortcut) */
 } spg_sparsity_options;
+#define SPG_OPT_FORCE_EIGEN 1
 
 /* edge kinds inside a blanket record */
 typedef enum {
@@ -191,6 +193,13 @@ spg_status spg_remove_round_device(spg_ctx *ctx, const spg_round_in *in_dev, spg
                                    int32_t max_n_vert, int32_t max_n_edges);
 spg_status spg_sync(spg_ctx *ctx);
 void *spg_stream(spg_ctx *ctx); /* cudaStream_t of the context */
+
+/*
+ * Roofline denominator: register-resident DFMA loop on every SM (no memory traffic), timed with
+ * CUDA events. MEASURED_PEAKS.json carries no FP64 figure, so bench.py measures it with this.
+ * Returns the best of `repeats` in TFLOP/s (2 flops per DFMA).
+ */
+spg_status spg_fp64_peak_probe(spg_ctx *ctx, int32_t repeats, double *tflops);
 
 /* ------------------------------------------------------------------------------------------ */
 /* Graph level: g2o-free container with the reference's removal semantics.                    */

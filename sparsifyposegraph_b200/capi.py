@@ -77,12 +77,13 @@ def lib():
         L.spg_stream.argtypes = [C.c_void_p]
         L.spg_out_record_words.restype = C.c_int64
         L.spg_out_record_words.argtypes = [C.c_int32, C.c_int32, C.POINTER(SparsityOptions), C.c_int32]
+        L.spg_fp64_peak_probe.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_double)]
         _lib = L
     return _lib
 
 
-def make_opts(topology=0, lin_point=1, chord_ratio=1.0, include_intra_clique=True):
-    return SparsityOptions(int(topology), int(lin_point), float(chord_ratio), int(bool(include_intra_clique)), 0)
+def make_opts(topology=0, lin_point=1, chord_ratio=1.0, include_intra_clique=True, flags=0):
+    return SparsityOptions(int(topology), int(lin_point), float(chord_ratio), int(bool(include_intra_clique)), int(flags))
 
 
 def _check(rc):
@@ -153,3 +154,9 @@ class Context:
 
     def sync(self):
         _check(lib().spg_sync(self.h))
+
+    def fp64_peak_tflops(self, repeats=5):
+        """Measured DFMA peak of this device (roofline denominator for the FP64-bound kernels)."""
+        v = C.c_double()
+        _check(lib().spg_fp64_peak_probe(self.h, int(repeats), C.byref(v)))
+        return float(v.value)

@@ -67,6 +67,21 @@ struct spg_ctx {
 
 namespace {
 
+// FP64 pipe peak probe: 8 independent DFMA chains per thread, no memory traffic.
+__global__ void __launch_bounds__(256) dfma_probe_kernel(double *sink, int iters, double seed) {
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0000001, c = 1e-9;
+    for(int i = 0; i < iters; i++) {
+#pragma unroll
+        for(int u = 0; u < 8; u++) {
+            a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+            a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+        }
+    }
+    const double r = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if(r == 12345.678) sink[0] = r; // never true: keeps the chains alive
+}
+
 template <int D, int NT>
 spg_status launch_bucket(spg_ctx *ctx, spg::KernelParams &kp) {
     static std::mutex mu;
@@ -204,6 +219,28 @@ int64_t spg_out_slot_words(int32_t dim, int32_t algorithm, const spg_sparsity_op
     return spgr_out_slot_words(dim, algorithm, o->topology, n_kept);
 }
 
+spg_status spg_fp64_peak_probe(spg_ctx *ctx, int32_t repeats, double *tflops) {
+    if(check_device(ctx) != SPG_OK || !tflops) return SPG_ERR_INVALID;
+    SPG_CUDA(cudaSetDevice(ctx->device));
+    SPG_CUDA(ctx->d_list.reserve(64));
+    const int iters = 4096, blocks = ctx->sm_count * 8, threads = 256;
+    double best = 0;
+    for(int r = 0; r < repeats + 1; r++) {
+        SPG_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+        dfma_probe_kernel<<<blocks, threads, 0, ctx->stream>>>(reinterpret_cast<double *>(ctx->d_list.p), iters, 1.0 + r);
+        SPG_CUDA(cudaGetLastError());
+        SPG_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+        SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+        ctx->launches++;
+        float ms = 0;
+        SPG_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        const double flops = 2.0 * 64.0 * iters * (double) blocks * threads;
+        if(r > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    *tflops = best;
+    return SPG_OK;
+}
+
 spg_status spg_sync(spg_ctx *ctx) {
     if(check_device(ctx) != SPG_OK) return SPG_ERR_INVALID;
     SPG_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -225,6 +262,7 @@ spg_status spg_remove_round_device(spg_ctx *ctx, const spg_round_in *in, spg_rou
     kp.algorithm = in->algorithm;
     kp.topology = in->opts.topology;
     kp.chord_ratio = in->opts.chord_ratio;
+    kp.flags = in->opts.flags;
     kp.n_list = in->n_blankets;
     kp.list = nullptr;
     kp.rec_off = in->rec_off;
@@ -320,6 +358,7 @@ spg_status spg_remove_round(spg_ctx *ctx, const spg_round_in *in, spg_round_out 
         kp.algorithm = in->algorithm;
         kp.topology = in->opts.topology;
         kp.chord_ratio = in->opts.chord_ratio;
+        kp.flags = in->opts.flags;
         kp.n_list = (int32_t) B.list.size();
         kp.list = reinterpret_cast<const int32_t *>(ctx->d_list.p) + list_pos;
         list_pos += B.list.size();

@@ -228,66 +228,79 @@ __device__ bool chol_lower(double *A, int n, int ld) {
 }
 
 // X = (L L^T)^-1 written to X (n x n, ldx) from the Cholesky factor L (lower, ld). Thread per
-// column: forward then backward substitution on its own column of X. No syncs inside.
+// column: forward then backward substitution on its own column of X (no syncs inside); the dot
+// products run on two independent accumulators to halve the DFMA dependency chain.
 template <int NT>
 __device__ void chol_inverse(const double *L, int n, int ld, double *X, int ldx) {
     for(int c = threadIdx.x; c < n; c += NT) {
         double *x = X + (size_t) c * ldx;
         for(int i = 0; i < c; i++) x[i] = 0;
-        // forward: L y = e_c
-        for(int i = c; i < n; i++) {
-            double s = (i == c) ? 1.0 : 0.0;
-            for(int p = c; p < i; p++) s -= L[i + p * ld] * x[p];
-            x[i] = s / L[i + i * ld];
+        for(int i = c; i < n; i++) { // forward: L y = e_c
+            double s0 = (i == c) ? 1.0 : 0.0, s1 = 0.0;
+            int p = c;
+            for(; p + 1 < i; p += 2) {
+                s0 -= L[i + p * ld] * x[p];
+                s1 -= L[i + (p + 1) * ld] * x[p + 1];
+            }
+            if(p < i) s0 -= L[i + p * ld] * x[p];
+            x[i] = (s0 + s1) / L[i + i * ld];
         }
-        // backward: L^T z = y
-        for(int i = n - 1; i >= 0; i--) {
-            double s = x[i];
-            for(int p = i + 1; p < n; p++) s -= L[p + i * ld] * x[p];
-            x[i] = s / L[i + i * ld];
+        for(int i = n - 1; i >= 0; i--) { // backward: L^T z = y
+            double s0 = x[i], s1 = 0.0;
+            int p = i + 1;
+            for(; p + 1 < n; p += 2) {
+                s0 -= L[p + i * ld] * x[p];
+                s1 -= L[p + 1 + i * ld] * x[p + 1];
+            }
+            if(p < n) s0 -= L[p + i * ld] * x[p];
+            x[i] = (s0 + s1) / L[i + i * ld];
         }
     }
 }
 
 // Parallel-order two-sided Jacobi eigen-decomposition of the symmetric n x n matrix A (ld),
 // destroying A (eigenvalues end on its diagonal) and accumulating eigenvectors in the columns
-// of V (ldv). cs: scratch of 2*((n+1)/2) doubles; red: one double of scratch.
+// of V (ldv). cs: scratch of 3*((n+1)/2) doubles (c, s and the packed pair); red: one double.
 // Round-robin tournament ordering: (n_even - 1) rounds of n_even/2 disjoint rotations; each round
-// applies J^T A J as independent 2x2 blocks (Brent-Luk), then V J.
+// applies J^T A J as independent 2x2 blocks (Brent-Luk) and V J, indexed through a per-round pair
+// table so the inner loops carry no integer division.
 // Returns the number of sweeps used, or -1 if not converged.
 template <int NT>
 __device__ int jacobi_eig(double *A, int n, int ld, double *V, int ldv, double *cs, double *red) {
+    constexpr int TX = (NT >= 128) ? 16 : 8;
+    constexpr int TY = NT / TX;
     const int tid = threadIdx.x;
-    for(int t = tid; t < n * n; t += NT) {
-        int i = t % n, j = t / n;
-        V[i + j * ldv] = (i == j) ? 1.0 : 0.0;
-    }
+    const int tx = tid % TX, ty = tid / TX;
+    for(int j = ty; j < n; j += TY)
+        for(int i = tx; i < n; i += TX) V[i + j * ldv] = (i == j) ? 1.0 : 0.0;
     if(n < 2) {
         gsync<NT>();
         return 0;
     }
     const int ne = (n + 1) & ~1, np = ne / 2;
-    // scale = max |diag| (>= every |a_ij| for PSD input, a good size proxy otherwise)
+    int *pq = reinterpret_cast<int *>(cs + 2 * np);
     if(tid == 0) {
         double m = 0;
-        for(int i = 0; i < n; i++) m = fmax(m, fabs(A[i + i * ld]));
         for(int j = 0; j < n; j++)
             for(int i = 0; i < n; i++) m = fmax(m, fabs(A[i + j * ld]));
         red[0] = m;
     }
     gsync<NT>();
     const double scale = red[0];
-    const double tol = 4.0 * 2.220446049250313e-16 * scale;
+    const double tol = 8.0 * 2.220446049250313e-16 * scale;
     gsync<NT>();
     const int max_sweeps = 30;
     for(int sweep = 0; sweep < max_sweeps; sweep++) {
         double mymax = 0;
         for(int r = 0; r < ne - 1; r++) {
-            // phase 1: rotation parameters of the np pairs of this round
+            // phase 1: pair table + rotation parameters of this round
             for(int i = tid; i < np; i += NT) {
                 int p, q;
                 if(i == 0) { p = ne - 1; q = r; }
-                else { p = (r + i) % (ne - 1); q = (r - i + ne - 1) % (ne - 1); }
+                else {
+                    p = r + i; if(p >= ne - 1) p -= ne - 1;
+                    q = r - i; if(q < 0) q += ne - 1;
+                }
                 if(p > q) { int tmp = p; p = q; q = tmp; }
                 double c = 1.0, s = 0.0;
                 if(q < n) {
@@ -300,58 +313,51 @@ __device__ int jacobi_eig(double *A, int n, int ld, double *V, int ldv, double *
                         c = 1.0 / sqrt(1.0 + t * t);
                         s = t * c;
                     }
+                    pq[i] = p | (q << 16);
+                } else {
+                    pq[i] = p | (p << 16) | 0x40000000; // padding partner: identity on a single index
                 }
                 cs[2 * i] = c;
                 cs[2 * i + 1] = s;
             }
             gsync<NT>();
-            // phase 2: A <- J^T A J on (pair, pair) blocks; V <- V J on (row, pair)
-            const int nblk = np * np;
-            for(int t = tid; t < nblk + n * np; t += NT) {
-                if(t < nblk) {
-                    const int i1 = t % np, i2 = t / np;
-                    int p1, q1, p2, q2;
-                    if(i1 == 0) { p1 = ne - 1; q1 = r; } else { p1 = (r + i1) % (ne - 1); q1 = (r - i1 + ne - 1) % (ne - 1); }
-                    if(i2 == 0) { p2 = ne - 1; q2 = r; } else { p2 = (r + i2) % (ne - 1); q2 = (r - i2 + ne - 1) % (ne - 1); }
-                    if(p1 > q1) { int tmp = p1; p1 = q1; q1 = tmp; }
-                    if(p2 > q2) { int tmp = p2; p2 = q2; q2 = tmp; }
-                    const bool v1 = q1 < n, v2 = q2 < n; // a pair with the padding index is a no-op
-                    const double c1 = cs[2 * i1], s1 = cs[2 * i1 + 1], c2 = cs[2 * i2], s2 = cs[2 * i2 + 1];
-                    // rows p1,q1 ; cols p2,q2 (q may be the padding index -> skip those entries)
+            // phase 2a: A <- J^T A J on (pair, pair) blocks
+            for(int i2 = ty; i2 < np; i2 += TY) {
+                const int w2 = pq[i2];
+                const int p2 = w2 & 0x7fff, q2 = (w2 >> 16) & 0x3fff;
+                const bool v2 = !(w2 & 0x40000000);
+                const double c2 = cs[2 * i2], s2 = cs[2 * i2 + 1];
+                for(int i1 = tx; i1 < np; i1 += TX) {
+                    const int w1 = pq[i1];
+                    const int p1 = w1 & 0x7fff, q1 = (w1 >> 16) & 0x3fff;
+                    const bool v1 = !(w1 & 0x40000000);
+                    const double c1 = cs[2 * i1], s1 = cs[2 * i1 + 1];
                     double b00 = A[p1 + p2 * ld];
                     double b01 = v2 ? A[p1 + q2 * ld] : 0.0;
                     double b10 = v1 ? A[q1 + p2 * ld] : 0.0;
                     double b11 = (v1 && v2) ? A[q1 + q2 * ld] : 0.0;
-                    // left: rows <- R1^T rows  (row p = c*rp - s*rq ; row q = s*rp + c*rq)
                     const double r00 = c1 * b00 - s1 * b10, r01 = c1 * b01 - s1 * b11;
                     const double r10 = s1 * b00 + c1 * b10, r11 = s1 * b01 + c1 * b11;
-                    // right: cols <- cols R2  (col p = c*cp - s*cq ; col q = s*cp + c*cq)
                     b00 = c2 * r00 - s2 * r01; b01 = s2 * r00 + c2 * r01;
                     b10 = c2 * r10 - s2 * r11; b11 = s2 * r10 + c2 * r11;
-                    if(i1 == i2) { // diagonal block: off-diagonal is annihilated exactly
-                        if(v1) { b01 = 0.0; b10 = 0.0; }
-                    }
+                    if(i1 == i2 && v1) { b01 = 0.0; b10 = 0.0; } // annihilated exactly
                     A[p1 + p2 * ld] = b00;
                     if(v2) A[p1 + q2 * ld] = b01;
                     if(v1) A[q1 + p2 * ld] = b10;
                     if(v1 && v2) A[q1 + q2 * ld] = b11;
-                } else {
-                    const int u = t - nblk;
-                    const int row = u % n, i2 = u / n;
-                    int p2, q2;
-                    if(i2 == 0) { p2 = ne - 1; q2 = r; } else { p2 = (r + i2) % (ne - 1); q2 = (r - i2 + ne - 1) % (ne - 1); }
-                    if(p2 > q2) { int tmp = p2; p2 = q2; q2 = tmp; }
-                    if(q2 < n) {
-                        const double c2 = cs[2 * i2], s2 = cs[2 * i2 + 1];
-                        const double vp = V[row + p2 * ldv], vq = V[row + q2 * ldv];
-                        V[row + p2 * ldv] = c2 * vp - s2 * vq;
-                        V[row + q2 * ldv] = s2 * vp + c2 * vq;
+                }
+                // phase 2b: V <- V J on (row, pair); rows walk a column: conflict free
+                if(v2) {
+                    double *vp = V + (size_t) p2 * ldv, *vq = V + (size_t) q2 * ldv;
+                    for(int row = tx; row < n; row += TX) {
+                        const double a = vp[row], b = vq[row];
+                        vp[row] = c2 * a - s2 * b;
+                        vq[row] = s2 * a + c2 * b;
                     }
                 }
             }
             gsync<NT>();
         }
-        // converged when every off-diagonal entry seen in this sweep was below tol
         unsigned conv = (mymax <= tol);
         int all;
         if constexpr(NT <= 32) all = __all_sync(0xffffffffu, conv);

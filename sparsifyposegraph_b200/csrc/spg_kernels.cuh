@@ -17,6 +17,8 @@ namespace spg {
 struct KernelParams {
     int32_t algorithm, topology;
     double chord_ratio;
+    int32_t flags;               // bit 0: force the general (eigen-decomposition) NFR path
+    int32_t pad0;
     int32_t n_list;              // blankets handled by this launch
     const int32_t *list;         // their indices (NULL: identity)
     const int64_t *rec_off;
@@ -55,12 +57,12 @@ inline void plan_smem(KernelParams &p) {
     p.buf1_doubles = b1 > asm_scratch ? b1 : asm_scratch;
     o += p.buf1_doubles;
     p.off_buf2 = o;
-    p.buf2_doubles = (nk >= 3) ? b1 : 0; // pseudo-covariance C; only blankets with >= 3 kept vertices run Chow-Liu
+    p.buf2_doubles = (nk >= 2) ? b1 : 0; // pseudo-covariance C, then the gauge-anchored inverse G
     o += p.buf2_doubles;
     p.off_small = o;
     // small: w[kmax] order[kmax](int) cs[kmax+2] red[8] weights[pairs] heapw[pairs] heapab[pairs] (int2)
     //        tree[2*max(pairs,1)] (int) uf[nk] (int) Lfac[nk*D*D] logd[nk] misc[16]
-    o += kmax + (kmax + 1) / 2 + (kmax + 2) + 8 + pairs + pairs + pairs + (pairs > 0 ? pairs : 1) + (nk + 1) / 2 + 1 +
+    o += kmax + (kmax + 1) / 2 + (kmax + kmax / 2 + 4) + 8 + pairs + pairs + pairs + (pairs > 0 ? pairs : 1) + (nk + 1) / 2 + 1 +
          nk * D * D + nk + 16;
     p.total_doubles = o;
 }
@@ -249,7 +251,7 @@ __global__ void __launch_bounds__(NT) blanket_kernel(const KernelParams P) {
     double *s_w = s_small;
     int *s_order = reinterpret_cast<int *>(s_w + kmax);
     double *s_cs = s_w + kmax + (kmax + 1) / 2;
-    double *s_red = s_cs + (kmax + 2);
+    double *s_red = s_cs + (kmax + kmax / 2 + 4);
     double *s_wt = s_red + 8;
     double *s_heapw = s_wt + pairs_max;
     int *s_heapab = reinterpret_cast<int *>(s_heapw + pairs_max);
@@ -474,27 +476,66 @@ __global__ void __launch_bounds__(NT) blanket_kernel(const KernelParams P) {
             gsync<NT>(); // s_tree visible
             const int r = k - D;
             const bool closed = (n_out * D == r); // hasClosedFormSolution, logdet_function.cpp:83-86
-            // eig(Lambda_t): A = T in place (destroyed), V in buf1
             double *V = buf1;
-            const int sweeps = jacobi_eig<NT>(T, k, ldH, V, ldk, s_cs, s_red);
-            if(sweeps < 0) status = SPG_BLANKET_EIG_NOCONV;
-            for(int i = tid; i < k; i += NT) s_w[i] = T[i + (size_t) i * ldH];
-            gsync<NT>();
-            // ascending order (SelfAdjointEigenSolver sorts increasingly); ties by index
-            int mysmall = 0;
-            for(int i = tid; i < k; i += NT) {
-                const double wi = s_w[i];
-                int rank = 0;
-                for(int j = 0; j < k; j++) {
-                    const double wj = s_w[j];
-                    rank += (wj < wi) || (wj == wi && j < i);
+            int smalleigs = 0;
+            // -- gauge shortcut ---------------------------------------------------------------------------
+            // A blanket made only of relative-pose edges is gauge free: Lambda_t has a d-dimensional null
+            // space N and every new-edge Jacobian satisfies J N = 0. The reference's
+            // Sigma = U S U^T (d smallest eigen-directions dropped, logdet_function.cpp:33-41) is then the
+            // pseudo-inverse, and J Sigma J^T = J G J^T for ANY generalised inverse G of Lambda_t. We take
+            // G = [[Lambda_rr^-1, 0], [0, 0]] (last kept vertex anchored): one Cholesky instead of an
+            // eigen-decomposition. The shortcut is taken only when the reference would be in the same
+            // branch: (i) trace(G) <= 1e5 => smallest eigenvalue of Lambda_rr >= 1e-5 => by interlacing
+            // lambda_{d+1} >= cutoff, i.e. smalleigs <= d; (ii) max diag < 1e8 so the null eigenvalues
+            // (~ k eps ||Lambda||) stay below the cutoff, i.e. smalleigs >= d. Otherwise: general path.
+            bool fast = false;
+            const int kk = k - D, ldg = odd_ld(kk > 0 ? kk : 1);
+            double *G = buf2;
+            if(closed && !(P.flags & 1)) {
+                for(int t = tid; t < kk * kk; t += NT) {
+                    const int i = t % kk, j = t / kk;
+                    buf1[i + j * ldg] = T[i + (size_t) j * ldH];
                 }
-                s_order[rank] = i;
-                if(wi < 1e-5) mysmall++;
+                if(tid == 0) {
+                    double md = 0;
+                    for(int i = 0; i < k; i++) md = fmax(md, fabs(T[i + (size_t) i * ldH]));
+                    s_red[1] = md;
+                }
+                gsync<NT>();
+                if(chol_lower<NT>(buf1, kk, ldg)) {
+                    chol_inverse<NT>(buf1, kk, ldg, G, ldg);
+                    gsync<NT>();
+                    if(tid == 0) {
+                        double tr = 0;
+                        for(int i = 0; i < kk; i++) tr += G[i + i * ldg];
+                        s_red[2] = tr;
+                    }
+                    gsync<NT>();
+                    fast = (s_red[2] <= 1e5) && (s_red[1] < 1e8); // false for NaN too
+                }
             }
-            if(mysmall) atomicAdd(&s_misc[1], mysmall);
-            gsync<NT>();
-            const int smalleigs = s_misc[1];
+            if(!fast) {
+                // eig(Lambda_t): A = T in place (destroyed), V in buf1
+                const int sweeps = jacobi_eig<NT>(T, k, ldH, V, ldk, s_cs, s_red);
+                if(sweeps < 0) status = SPG_BLANKET_EIG_NOCONV;
+                for(int i = tid; i < k; i += NT) s_w[i] = T[i + (size_t) i * ldH];
+                gsync<NT>();
+                // ascending order (SelfAdjointEigenSolver sorts increasingly); ties by index
+                int mysmall = 0;
+                for(int i = tid; i < k; i += NT) {
+                    const double wi = s_w[i];
+                    int rank = 0;
+                    for(int j = 0; j < k; j++) {
+                        const double wj = s_w[j];
+                        rank += (wj < wi) || (wj == wi && j < i);
+                    }
+                    s_order[rank] = i;
+                    if(wi < 1e-5) mysmall++;
+                }
+                if(mysmall) atomicAdd(&s_misc[1], mysmall);
+                gsync<NT>();
+                smalleigs = s_misc[1];
+            }
             // new-edge Jacobians at the linearisation point with measurement == state (:466-498),
             // measurements written straight to the output record
             double *Jn = buf0;                       // n_out * JW   (buf0 is free: eigenvalues are saved)
@@ -518,7 +559,9 @@ __global__ void __launch_bounds__(NT) blanket_kernel(const KernelParams P) {
             // S (inverse eigenvalues) and the kept eigen-directions, logdet_function.cpp:33-61
             double *s_S = s_cs; // r values (cs is free after the eigen-solver)
             int ooff = 0; // kept direction l is eigen-column s_order[ooff + l]
-            if(smalleigs <= D) {
+            if(fast) {
+                gsync<NT>();
+            } else if(smalleigs <= D) {
                 ooff = D;
                 for(int l = tid; l < r; l += NT) s_S[l] = 1.0 / s_w[s_order[D + l]];
                 gsync<NT>();
@@ -585,9 +628,13 @@ __global__ void __launch_bounds__(NT) blanket_kernel(const KernelParams P) {
                         const int ri = (i < D ? a * D + i : bb * D + i - D);
                         const int rj = (j < D ? a * D + j : bb * D + j - D);
                         double s = 0;
-                        for(int l = 0; l < r; l++) {
-                            const double *u = V + (size_t) s_order[ooff + l] * ldk;
-                            s += u[ri] * s_S[l] * u[rj];
+                        if(fast) {
+                            if(ri < kk) s = G[ri + rj * ldg]; // rj <= ri: lower triangle of G
+                        } else {
+                            for(int l = 0; l < r; l++) {
+                                const double *u = V + (size_t) s_order[ooff + l] * ldk;
+                                s += u[ri] * s_S[l] * u[rj];
+                            }
                         }
                         Sg[(size_t) e * SW + i + j * 2 * D] = s;
                         Sg[(size_t) e * SW + j + i * 2 * D] = s;

@@ -21,7 +21,7 @@ def ctx():
     c.close()
 
 
-def run_both(ctx, oracle, blk, algorithm, topology, chord_ratio=1.0):
+def run_both(ctx, oracle, blk, algorithm, topology, chord_ratio=1.0, flags=0):
     from sparsifyposegraph_b200 import capi
     dim, n, B = blk["dim"], blk["n"], blk["B"]
     nk = R.n_kept_of(blk["records"], blk["rec_off"])
@@ -30,7 +30,7 @@ def run_both(ctx, oracle, blk, algorithm, topology, chord_ratio=1.0):
     toff = np.arange(B + 1, dtype=np.int64) * k * k
     woff = np.arange(B + 1, dtype=np.int64) * ((n - 1) * (n - 2) // 2)
     o_opts = oracle.make_opts(topology, R.LIN_GLOBAL, chord_ratio)
-    g_opts = capi.make_opts(topology, R.LIN_GLOBAL, chord_ratio)
+    g_opts = capi.make_opts(topology, R.LIN_GLOBAL, chord_ratio, flags=flags)
     ref = oracle.remove_round(dim, algorithm, o_opts, blk["records"], blk["rec_off"], out_off, 0, toff, woff)
     got = ctx.remove_round(dim, algorithm, g_opts, blk["records"], blk["rec_off"], out_off, None, toff, woff)
     return out_off, ref, got
@@ -46,9 +46,12 @@ def rel(a, b):
     (6, 5, "ring", 512), (6, 6, "ring", 128), (6, 8, "ring", 64), (6, 12, "star", 32), (6, 16, "ring", 16),
     (3, 3, "star", 64), (3, 5, "ring", 256), (3, 8, "ring", 64), (3, 14, "star", 32), (3, 24, "ring", 8),
 ])
-def test_nfr_tree_parity(ctx, oracle, dim, n, variant, B):
+@pytest.mark.parametrize("flags", [0, 1], ids=["gauge-shortcut", "force-eigen"])
+def test_nfr_tree_parity(ctx, oracle, dim, n, variant, B, flags):
+    """flags=0: default path (gauge shortcut where valid); flags=1 (SPG_OPT_FORCE_EIGEN): the general
+    eigen-decomposition path that follows logdet_function.cpp:14-64 literally."""
     blk = synth.make_blankets(n, B, dim=dim, variant=variant, seed=1000 + 10 * n + dim)
-    out_off, (ro, _, rt, rw), (go, gt, gw) = run_both(ctx, oracle, blk, R.ALG_NFR, R.TOPO_TREE)
+    out_off, (ro, _, rt, rw), (go, gt, gw) = run_both(ctx, oracle, blk, R.ALG_NFR, R.TOPO_TREE, flags=flags)
     k = dim * (n - 1)
     worst_t = worst_x = 0.0
     for b in range(B):
