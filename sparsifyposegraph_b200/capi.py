@@ -160,3 +160,146 @@ class Context:
         v = C.c_double()
         _check(lib().spg_fp64_peak_probe(self.h, int(repeats), C.byref(v)))
         return float(v.value)
+
+
+def _graph_protos(L):
+    if getattr(L, "_graph_protos_done", False):
+        return
+    L.spg_graph_create.argtypes = [C.POINTER(C.c_void_p), C.c_int32]
+    L.spg_graph_destroy.argtypes = [C.c_void_p]
+    L.spg_graph_load_g2o.argtypes = [C.POINTER(C.c_void_p), C.c_char_p]
+    L.spg_graph_add_vertex.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+    L.spg_graph_add_edge.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+    for f in ("spg_graph_dim", "spg_graph_num_vertices", "spg_graph_num_edges", "spg_graph_max_vertex_id"):
+        getattr(L, f).argtypes = [C.c_void_p]
+    for f in ("spg_decimate_global", "spg_decimate_online"):
+        getattr(L, f).argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32]
+    L.spg_decimate_cluster.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32]
+    L.spg_graph_marginalize.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(SparsityOptions), C.c_int32]
+    L.spg_graph_last_stats.argtypes = [C.c_void_p, C.POINTER(MarginalizeStats)]
+    L.spg_graph_edge_desc.argtypes = [C.c_void_p, C.c_int32, C.POINTER(EdgeDesc)]
+    L.spg_graph_edge_data.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.spg_graph_vertex_ids.argtypes = [C.c_void_p, C.c_void_p]
+    L.spg_graph_vertex_pose.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+    L.spg_compute_substitute_edge.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_int32),
+                                              C.POINTER(C.c_int32), C.c_void_p, C.c_void_p]
+    L._graph_protos_done = True
+
+
+class Graph:
+    """spg_graph: g2o-free pose graph with the reference's removal semantics
+    (GraphWrapper::marginalize, src/graph_wrapper.h:17-81 / graph_wrapper_g2o.cpp:398-453)."""
+
+    def __init__(self, path=None, dim=None):
+        L = lib()
+        _graph_protos(L)
+        self.h = C.c_void_p()
+        if path is not None:
+            _check(L.spg_graph_load_g2o(C.byref(self.h), os.fsencode(path)))
+        else:
+            _check(L.spg_graph_create(C.byref(self.h), int(dim)))
+        self.dim = L.spg_graph_dim(self.h)
+        self.P = 3 if self.dim == 3 else 7
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().spg_graph_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def add_vertex(self, vid, pose):
+        p = np.ascontiguousarray(pose, dtype=np.float64)
+        _check(lib().spg_graph_add_vertex(self.h, int(vid), _p(p)))
+
+    def add_edge(self, a, b, meas, info):
+        m = np.ascontiguousarray(meas, dtype=np.float64)
+        i = np.ascontiguousarray(np.asarray(info, dtype=np.float64).T)
+        _check(lib().spg_graph_add_edge(self.h, int(a), int(b), _p(m), _p(i)))
+
+    @property
+    def num_vertices(self):
+        return lib().spg_graph_num_vertices(self.h)
+
+    @property
+    def num_edges(self):
+        return lib().spg_graph_num_edges(self.h)
+
+    @property
+    def max_vertex_id(self):
+        return lib().spg_graph_max_vertex_id(self.h)
+
+    def vertex_ids(self):
+        ids = np.zeros(self.num_vertices, dtype=np.int32)
+        _check(lib().spg_graph_vertex_ids(self.h, _p(ids)))
+        return ids
+
+    def vertex_pose(self, vid):
+        p = np.zeros(self.P)
+        _check(lib().spg_graph_vertex_pose(self.h, int(vid), _p(p)))
+        return p
+
+    def marginalize(self, ctx, which, opts, algorithm):
+        """VertexRemover::remove(which) through the GPU; returns the marginalize stats."""
+        w = np.ascontiguousarray(which, dtype=np.int32)
+        _check(lib().spg_graph_marginalize(self.h, ctx.h, _p(w), len(w), C.byref(opts), int(algorithm)))
+        return self.stats()
+
+    def stats(self):
+        s = MarginalizeStats()
+        _check(lib().spg_graph_last_stats(self.h, C.byref(s)))
+        return {f: getattr(s, f) for f, _ in MarginalizeStats._fields_}
+
+    def edges(self):
+        L = lib()
+        res = []
+        d = EdgeDesc()
+        for i in range(self.num_edges):
+            _check(L.spg_graph_edge_desc(self.h, i, C.byref(d)))
+            ids = np.zeros(d.nv, dtype=np.int32)
+            if d.kind == 0:
+                meas, info = np.zeros(self.P), np.zeros(self.dim * self.dim)
+            elif d.kind == 1:
+                meas, info = np.zeros(self.dim * d.nv), np.zeros(d.rows * self.dim * d.nv)
+            else:
+                meas, info = np.zeros((d.rows // self.dim) * self.P), np.zeros(d.rows * d.rows)
+            _check(L.spg_graph_edge_data(self.h, i, _p(ids), _p(meas), _p(info)))
+            if d.kind == 0:
+                info = info.reshape(self.dim, self.dim).T
+            elif d.kind == 1:
+                info = info.reshape(d.rows, self.dim * d.nv)
+            else:
+                info = info.reshape(d.rows, d.rows).T
+            res.append({"kind": d.kind, "v": ids, "rows": d.rows, "uid": (d.uid_major, d.uid_minor), "meas": meas,
+                        "info": info})
+        return res
+
+    def compute_substitute_edge(self, marginalized, maxid, frm, to):
+        """computeSubstituteEdge (src/compute_substitute_edge.cpp:13-96) -> (from, to, meas, info)."""
+        m = np.ascontiguousarray(sorted(marginalized), dtype=np.int32)
+        f, t = C.c_int32(int(frm)), C.c_int32(int(to))
+        meas, info = np.zeros(self.P), np.zeros(self.dim * self.dim)
+        _check(lib().spg_compute_substitute_edge(self.h, _p(m), len(m), int(maxid), C.byref(f), C.byref(t), _p(meas), _p(info)))
+        return f.value, t.value, meas, info.reshape(self.dim, self.dim).T
+
+
+def decimate_global(last, endvert, sparsity):
+    _graph_protos(lib())
+    out = np.zeros(max(endvert + 1, 1), dtype=np.int32)
+    n = lib().spg_decimate_global(last, endvert, sparsity, _p(out), len(out))
+    return out[:n]
+
+
+def decimate_online(last, endvert, sparsity):
+    _graph_protos(lib())
+    out = np.zeros(4, dtype=np.int32)
+    n = lib().spg_decimate_online(last, endvert, sparsity, _p(out), len(out))
+    return out[:n]
+
+
+def decimate_cluster(last, endvert, sparsity, cluster):
+    _graph_protos(lib())
+    out = np.zeros(max(endvert + 1, 1), dtype=np.int32)
+    n = lib().spg_decimate_cluster(last, endvert, sparsity, cluster, _p(out), len(out))
+    return out[:n]

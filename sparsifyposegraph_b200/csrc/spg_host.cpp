@@ -1,0 +1,904 @@
+// spg_host.cpp — host side of the node-removal path: pose-graph container, g2o text reader,
+// decimation schedules, wavefront round scheduler + packer (VertexRemover) and
+// computeSubstituteEdge. See spg_host.h for the reference files each piece mirrors.
+// All numerical work of a removal happens on the GPU through spg_remove_round(); this file only
+// moves integers, copies doubles and composes a few poses (Local linearisation point, R2).
+#include "spg_host.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <deque>
+#include <fstream>
+#include <limits>
+#include <sstream>
+
+#include "../../include/spg_record.h"
+
+namespace spg {
+
+// ---- small pose helpers -----------------------------------------------------------------------
+static double normalizeTheta(double theta) {
+    if(theta >= -M_PI && theta < M_PI) return theta;
+    double multiplier = std::floor(theta / (2 * M_PI));
+    theta = theta - multiplier * 2 * M_PI;
+    if(theta >= M_PI) theta -= 2 * M_PI;
+    if(theta < -M_PI) theta += 2 * M_PI;
+    return theta;
+}
+static void qmul(const double *a, const double *b, double *o) { // x y z w
+    o[0] = a[3] * b[0] + a[0] * b[3] + a[1] * b[2] - a[2] * b[1];
+    o[1] = a[3] * b[1] - a[0] * b[2] + a[1] * b[3] + a[2] * b[0];
+    o[2] = a[3] * b[2] + a[0] * b[1] - a[1] * b[0] + a[2] * b[3];
+    o[3] = a[3] * b[3] - a[0] * b[0] - a[1] * b[1] - a[2] * b[2];
+}
+static void qrot(const double *q, const double *v, double *o) {
+    // o = R(q) v
+    const double x = q[0], y = q[1], z = q[2], w = q[3];
+    const double tx = 2 * (y * v[2] - z * v[1]), ty = 2 * (z * v[0] - x * v[2]), tz = 2 * (x * v[1] - y * v[0]);
+    o[0] = v[0] + w * tx + (y * tz - z * ty);
+    o[1] = v[1] + w * ty + (z * tx - x * tz);
+    o[2] = v[2] + w * tz + (x * ty - y * tx);
+}
+static void qnorm(double *q) {
+    double n = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    double s = (q[3] < 0 ? -1.0 : 1.0) / n;
+    for(int i = 0; i < 4; i++) q[i] *= s;
+}
+void poseCompose(int dim, const double *a, const double *b, double *out) {
+    if(dim == 3) {
+        const double c = std::cos(a[2]), s = std::sin(a[2]);
+        double x = a[0] + c * b[0] - s * b[1], y = a[1] + s * b[0] + c * b[1];
+        out[0] = x; out[1] = y; out[2] = normalizeTheta(a[2] + b[2]);
+    } else {
+        double qa[4] = {a[3], a[4], a[5], a[6]}, qb[4] = {b[3], b[4], b[5], b[6]};
+        qnorm(qa); qnorm(qb);
+        double t[3], q[4];
+        qrot(qa, b, t);
+        qmul(qa, qb, q);
+        qnorm(q);
+        out[0] = a[0] + t[0]; out[1] = a[1] + t[1]; out[2] = a[2] + t[2];
+        out[3] = q[0]; out[4] = q[1]; out[5] = q[2]; out[6] = q[3];
+    }
+}
+void poseInverse(int dim, const double *a, double *out) {
+    if(dim == 3) {
+        const double th = normalizeTheta(-a[2]);
+        const double c = std::cos(th), s = std::sin(th);
+        double x = c * (-a[0]) - s * (-a[1]), y = s * (-a[0]) + c * (-a[1]);
+        out[0] = x; out[1] = y; out[2] = th;
+    } else {
+        double q[4] = {-a[3], -a[4], -a[5], a[6]};
+        qnorm(q);
+        double mt[3] = {-a[0], -a[1], -a[2]}, t[3];
+        qrot(q, mt, t);
+        out[0] = t[0]; out[1] = t[1]; out[2] = t[2];
+        out[3] = q[0]; out[4] = q[1]; out[5] = q[2]; out[6] = q[3];
+    }
+}
+static void poseIdentity(int dim, double *out) {
+    for(int i = 0; i < 7; i++) out[i] = 0;
+    if(dim == 6) out[6] = 1;
+}
+
+// ---- decimation (src/decimation.cpp:11-49) ---------------------------------------------------------
+std::vector<int> clusterDecimate(int last, int endvert, const DecimateOptions &opts) {
+    if(((last - 4) % opts.clusterSize == 0 && last > 4) || last == endvert) {
+        std::vector<int> ret;
+        for(int i = int(std::ceil((last - 5) / (double) opts.clusterSize) - 1) * opts.clusterSize + 5; i <= last; i++)
+            if(i % opts.sparsity > 0) ret.push_back(i);
+        return ret;
+    }
+    return std::vector<int>();
+}
+std::vector<int> onlineDecimate(int last, int, const DecimateOptions &opts) {
+    if(last % opts.sparsity == 0) return std::vector<int>();
+    return std::vector<int>({last});
+}
+std::vector<int> globalDecimate(int last, int endvert, const DecimateOptions &opts) {
+    if(last == endvert) {
+        std::vector<int> which;
+        for(int i = 4; i <= endvert; i++)
+            if(i % opts.sparsity != 0) which.push_back(i);
+        return which;
+    }
+    return std::vector<int>();
+}
+
+// ---- Graph -------------------------------------------------------------------------------------------
+bool Graph::hasVertex(int id) const {
+    auto it = index.find(id);
+    return it != index.end() && verts[it->second].alive;
+}
+GraphVertex *Graph::vertex(int id) {
+    auto it = index.find(id);
+    if(it == index.end() || !verts[it->second].alive) return nullptr;
+    return &verts[it->second];
+}
+const GraphVertex *Graph::vertex(int id) const {
+    auto it = index.find(id);
+    if(it == index.end() || !verts[it->second].alive) return nullptr;
+    return &verts[it->second];
+}
+bool Graph::addVertex(int id, const double *pose) {
+    if(hasVertex(id)) return false;
+    GraphVertex v;
+    v.id = id;
+    std::memcpy(v.pose, pose, sizeof(double) * poseWords());
+    if(dim == 3) v.pose[2] = normalizeTheta(v.pose[2]);
+    else qnorm(v.pose + 3);
+    index[id] = (int) verts.size();
+    verts.push_back(v);
+    aliveVertices++;
+    return true;
+}
+int Graph::addEdge(const GraphEdge &e) {
+    int ei = (int) edges.size();
+    edges.push_back(e);
+    edges.back().alive = true;
+    for(int id : e.v) verts[index[id]].edges.push_back(ei);
+    aliveEdges++;
+    return ei;
+}
+int Graph::addPoseEdge(int from, int to, const double *meas, const double *info) {
+    if(!hasVertex(from) || !hasVertex(to)) return -1;
+    GraphEdge e;
+    e.kind = SPG_EDGE_POSE;
+    e.v = {from, to};
+    e.rows = dim;
+    e.meas.assign(meas, meas + poseWords());
+    if(dim == 3) e.meas[2] = normalizeTheta(e.meas[2]);
+    else qnorm(e.meas.data() + 3);
+    e.info.assign(info, info + dim * dim);
+    e.uidMajor = -1;
+    e.uidMinor = fileEdges++;
+    return addEdge(e);
+}
+void Graph::removeEdge(int ei) {
+    GraphEdge &e = edges[ei];
+    if(!e.alive) return;
+    e.alive = false;
+    for(int id : e.v) {
+        std::vector<int> &ve = verts[index[id]].edges;
+        auto it = std::find(ve.begin(), ve.end(), ei);
+        if(it != ve.end()) { *it = ve.back(); ve.pop_back(); }
+    }
+    std::vector<double>().swap(e.info);
+    aliveEdges--;
+}
+void Graph::removeVertex(int id) {
+    GraphVertex *v = vertex(id);
+    if(!v) return;
+    v->alive = false;
+    aliveVertices--;
+}
+int Graph::maxVertexId() const {
+    int m = -1;
+    for(const GraphVertex &v : verts)
+        if(v.alive) m = std::max(m, v.id);
+    return m;
+}
+std::vector<int> Graph::vertexIds() const {
+    std::vector<int> ids;
+    for(const GraphVertex &v : verts)
+        if(v.alive) ids.push_back(v.id);
+    std::sort(ids.begin(), ids.end());
+    return ids;
+}
+std::vector<int> Graph::edgeOrder() const {
+    std::vector<int> o;
+    for(size_t i = 0; i < edges.size(); i++)
+        if(edges[i].alive) o.push_back((int) i);
+    std::sort(o.begin(), o.end(), [&](int a, int b) {
+        if(edges[a].uidMajor != edges[b].uidMajor) return edges[a].uidMajor < edges[b].uidMajor;
+        return edges[a].uidMinor < edges[b].uidMinor;
+    });
+    return o;
+}
+
+// g2o text reader for the four tags the reference's datasets use (graph_wrapper_g2o.cpp:107-147).
+Graph *Graph::loadG2o(const std::string &path, std::string *err) {
+    std::ifstream f(path);
+    if(!f) {
+        if(err) *err = "cannot open " + path;
+        return nullptr;
+    }
+    Graph *g = nullptr;
+    struct Pend { int a, b; double z[7]; double info[36]; };
+    std::vector<Pend> pend;
+    std::string line;
+    while(std::getline(f, line)) {
+        std::istringstream is(line);
+        std::string tag;
+        if(!(is >> tag)) continue;
+        if(tag == "VERTEX_SE2" || tag == "VERTEX_SE3:QUAT") {
+            int d = tag == "VERTEX_SE2" ? 3 : 6;
+            if(!g) g = new Graph(d);
+            int id;
+            double p[7] = {0, 0, 0, 0, 0, 0, 1};
+            is >> id;
+            for(int i = 0; i < g->poseWords(); i++) is >> p[i];
+            g->addVertex(id, p);
+        } else if(tag == "EDGE_SE2" || tag == "EDGE_SE3:QUAT") {
+            int d = tag == "EDGE_SE2" ? 3 : 6, P = d == 3 ? 3 : 7;
+            Pend pe;
+            is >> pe.a >> pe.b;
+            for(int i = 0; i < P; i++) is >> pe.z[i];
+            for(int i = 0; i < d; i++)
+                for(int j = i; j < d; j++) {
+                    double v;
+                    is >> v;
+                    pe.info[i + j * d] = v;
+                    pe.info[j + i * d] = v;
+                }
+            pend.push_back(pe);
+        }
+    }
+    if(!g) {
+        if(err) *err = "no vertices in " + path;
+        return nullptr;
+    }
+    for(const Pend &pe : pend) g->addPoseEdge(pe.a, pe.b, pe.z, pe.info);
+    return g;
+}
+
+// ---- VertexRemover --------------------------------------------------------------------------------
+VertexRemover::VertexRemover() {}
+VertexRemover::~VertexRemover() {
+    for(TopologyProvider *t : _topologies) delete t;
+}
+void VertexRemover::setSparsityOptions(const SparsityOptions &opts) {
+    _opts = opts;
+    for(TopologyProvider *t : _topologies) t->setSparsityOptions(opts);
+}
+
+// src/vertex_remover.cpp:197-215
+std::vector<int> VertexRemover::markovBlanketVertices(int root) const {
+    std::set<int> vset;
+    vset.insert(root);
+    const GraphVertex *v = _graph->vertex(root);
+    if(v)
+        for(int ei : v->edges)
+            for(int id : _graph->edges[ei].v) vset.insert(id);
+    return std::vector<int>(vset.begin(), vset.end());
+}
+// :142-195 (live branch :185-191): the id-ordered set grows while it is being iterated, so the closure
+// is transitive only towards larger ids
+std::vector<int> VertexRemover::extendedMarkovBlanketVertices(int root, const std::set<int> &pickBin,
+                                                               std::vector<int> &picked) const {
+    std::set<int> pk, ret;
+    for(int id : markovBlanketVertices(root)) ret.insert(id);
+    pk.insert(root);
+    for(auto it = ret.begin(); it != ret.end(); ++it) {
+        int v = *it;
+        if(pickBin.count(v) > 0 && pk.count(v) == 0) {
+            pk.insert(v);
+            for(int id : markovBlanketVertices(v)) ret.insert(id);
+        }
+    }
+    picked.assign(pk.begin(), pk.end());
+    return std::vector<int>(ret.begin(), ret.end());
+}
+// :225-251
+std::vector<int> VertexRemover::markovBlanketEdges(const std::vector<int> &mb, const std::vector<int> &hubs) const {
+    std::set<int> inb(mb.begin(), mb.end()), hub(hubs.begin(), hubs.end());
+    std::set<int> es;
+    for(int id : mb) {
+        const GraphVertex *v = _graph->vertex(id);
+        if(!v) continue;
+        for(int ei : v->edges) {
+            const GraphEdge &e = _graph->edges[ei];
+            bool is_markov = true, found_hub = false;
+            for(int x : e.v) {
+                if(inb.count(x) == 0) { is_markov = false; break; }
+                if(hub.count(x) > 0) found_hub = true;
+            }
+            if(is_markov && (_opts.includeIntraClique || found_hub)) es.insert(ei);
+        }
+    }
+    std::vector<int> out(es.begin(), es.end());
+    std::sort(out.begin(), out.end(), [&](int a, int b) {
+        const GraphEdge &x = _graph->edges[a], &y = _graph->edges[b];
+        if(x.uidMajor != y.uidMajor) return x.uidMajor < y.uidMajor;
+        return x.uidMinor < y.uidMinor;
+    });
+    return out;
+}
+
+bool VertexRemover::buildUnit(int root, int listIndex, const std::set<int> &toRemoveSet, RemovalUnit &u) const {
+    u = RemovalUnit();
+    u.listIndex = listIndex;
+    std::vector<int> vmarkov;
+    if(_opts.topology == SparsityOptions::Dense || _opts.topology == SparsityOptions::CliqueyDense) {
+        vmarkov = extendedMarkovBlanketVertices(root, toRemoveSet, u.removed);
+    } else {
+        vmarkov = markovBlanketVertices(root);
+        u.removed.push_back(root);
+    }
+    std::set<int> rem(u.removed.begin(), u.removed.end());
+    for(int id : vmarkov)
+        if(!rem.count(id)) u.kept.push_back(id);
+    u.edges = markovBlanketEdges(vmarkov, u.removed);
+    return !u.edges.empty();
+}
+
+// src/vertex_remover.cpp:452-463: first registered provider that is applicable
+TopologyProvider *VertexRemover::chooseTopologyProvider(const RemovalUnit &u) const {
+    std::set<int> kinds;
+    for(int ei : u.edges) kinds.insert(_graph->edges[ei].kind);
+    for(TopologyProvider *tp : _topologies)
+        if(tp->applicable(_graph->dim, kinds)) return tp;
+    return nullptr;
+}
+
+// buildSubgraph (src/vertex_remover.cpp:285-392) + record packing. Returns false when the blanket
+// needs the Local non-star linearisation point (g2o LM on the subgraph; not part of this path).
+bool VertexRemover::packUnit(const RemovalUnit &u, std::vector<uint64_t> &rec) const {
+    const int dim = _graph->dim, P = _graph->poseWords();
+    const int nrem = (int) u.removed.size(), nv = nrem + (int) u.kept.size(), ne = (int) u.edges.size();
+    std::unordered_map<int, int> local;
+    std::vector<int> ids;
+    for(int id : u.removed) { local[id] = (int) ids.size(); ids.push_back(id); }
+    for(int id : u.kept) { local[id] = (int) ids.size(); ids.push_back(id); }
+    std::vector<double> poses((size_t) nv * P);
+    for(int i = 0; i < nv; i++) std::memcpy(&poses[(size_t) i * P], _graph->vertex(ids[i])->pose, sizeof(double) * P);
+
+    if(_opts.linPoint == SparsityOptions::Local) {
+        // closed-form estimate only for star-shaped blankets (:304-342)
+        bool closedForm = true;
+        std::vector<int> nconn(nv, 0);
+        for(int ei : u.edges) {
+            const GraphEdge &e = _graph->edges[ei];
+            for(int id : e.v) {
+                int li = local[id];
+                if(li != 0) {
+                    nconn[li]++;
+                    closedForm = closedForm && (e.kind != SPG_EDGE_GLC); // GLCEdge::initialEstimatePossible == -1
+                }
+            }
+        }
+        for(int i = 1; i < nv; i++)
+            if(nconn[i] > 1) { closedForm = false; break; }
+        if(!closedForm) return false;
+        // :363-381 — removed vertex at the origin, each neighbour from its measurement
+        poseIdentity(dim, &poses[0]);
+        double tmp[7], inv[7];
+        auto apply = [&](int vi, int vj, const double *z) {
+            if(vi == 0) {
+                poseCompose(dim, &poses[(size_t) vi * P], z, tmp);
+                std::memcpy(&poses[(size_t) vj * P], tmp, sizeof(double) * P);
+            } else {
+                poseInverse(dim, z, inv);
+                poseCompose(dim, &poses[(size_t) vj * P], inv, tmp);
+                std::memcpy(&poses[(size_t) vi * P], tmp, sizeof(double) * P);
+            }
+        };
+        for(int ei : u.edges) {
+            const GraphEdge &e = _graph->edges[ei];
+            if(e.kind == SPG_EDGE_POSE) {
+                apply(local[e.v[0]], local[e.v[1]], e.meas.data());
+            } else if(e.kind == SPG_EDGE_MULTI) {
+                for(size_t vi = 0; vi < e.v.size(); vi++)
+                    for(size_t m = 0; m < e.pairs.size() / 2; m++)
+                        if(e.pairs[2 * m] == (int) vi || e.pairs[2 * m + 1] == (int) vi)
+                            apply(local[e.v[e.pairs[2 * m]]], local[e.v[e.pairs[2 * m + 1]]], &e.meas[m * P]);
+            }
+        }
+    }
+
+    int64_t words = spgr_record_fixed_words(dim, nv, ne);
+    std::vector<int64_t> eoff(ne);
+    for(int i = 0; i < ne; i++) {
+        const GraphEdge &e = _graph->edges[u.edges[i]];
+        eoff[i] = words;
+        words += spgr_edge_words(dim, e.kind, (int) e.v.size(), e.rows);
+    }
+    words = (words + 1) & ~(int64_t) 1;
+    rec.assign((size_t) words, 0);
+    int32_t *h = reinterpret_cast<int32_t *>(rec.data());
+    h[0] = nv; h[1] = nrem; h[2] = ne; h[3] = dim; h[4] = (int32_t) words; h[5] = 0; h[6] = u.listIndex; h[7] = 0;
+    int32_t *rid = reinterpret_cast<int32_t *>(rec.data() + spgr_ids_off());
+    for(int i = 0; i < nv; i++) rid[i] = ids[i];
+    std::memcpy(rec.data() + spgr_poses_off(nv), poses.data(), sizeof(double) * nv * P);
+    int32_t *etab = reinterpret_cast<int32_t *>(rec.data() + spgr_edgetab_off(dim, nv));
+    for(int i = 0; i < ne; i++) {
+        const GraphEdge &e = _graph->edges[u.edges[i]];
+        etab[i] = (int32_t) eoff[i];
+        uint64_t *ew = rec.data() + eoff[i];
+        int32_t *eh = reinterpret_cast<int32_t *>(ew);
+        const int nve = (int) e.v.size();
+        eh[0] = e.kind; eh[1] = nve; eh[2] = e.rows; eh[3] = 0;
+        int32_t *vi = reinterpret_cast<int32_t *>(ew + 2);
+        for(int q = 0; q < nve; q++) vi[q] = local[e.v[q]];
+        double *pl = reinterpret_cast<double *>(ew + 2 + spgr_pad2(nve));
+        if(e.kind == SPG_EDGE_POSE) {
+            std::memcpy(pl, e.meas.data(), sizeof(double) * P);
+            std::memcpy(pl + P, e.info.data(), sizeof(double) * dim * dim);
+        } else if(e.kind == SPG_EDGE_GLC) {
+            std::memcpy(pl, e.meas.data(), sizeof(double) * dim * nve);
+            std::memcpy(pl + dim * nve, e.info.data(), sizeof(double) * e.rows * dim * nve);
+        } else {
+            const int nm = e.rows / dim;
+            int32_t *pr = reinterpret_cast<int32_t *>(ew + 2 + spgr_pad2(nve));
+            for(int q = 0; q < 2 * nm; q++) pr[q] = e.pairs[q];
+            double *pm = reinterpret_cast<double *>(ew + 2 + spgr_pad2(nve) + spgr_pad2(2 * nm));
+            std::memcpy(pm, e.meas.data(), sizeof(double) * nm * P);
+            std::memcpy(pm + (size_t) nm * P, e.info.data(), sizeof(double) * e.rows * e.rows);
+        }
+    }
+    return true;
+}
+
+std::vector<int> VertexRemover::remove(int toRemove, spg_status *status) {
+    return remove(std::vector<int>(1, toRemove), status);
+}
+
+// src/vertex_remover.cpp:83-140, regrouped into wavefront rounds.
+//
+// Two removal units U (earlier in the list) and V commute — removing them in either order, hence
+// also both from one snapshot, gives the same graph — iff V's blanket is untouched by U:
+//   removed(V) ∩ blanket(U) = ∅,  kept(V) ∩ removed(U) = ∅  and  |kept(U) ∩ kept(V)| <= 1
+// (U deletes / creates edges only among vertices of blanket(U); with includeIntraClique an edge
+// inside kept(U) ∩ kept(V) would belong to both blankets).
+// A round is built by scanning the pending list in order. A unit is selected when it commutes with
+// every unit already selected AND with every earlier unit that had to be deferred, using for the
+// deferred ones a conservative region: their blanket plus the blankets of all units they were
+// deferred behind (their neighbourhood can only grow through those). Selected units are then
+// processed from the same snapshot, and spliced in list order.
+std::vector<int> VertexRemover::remove(const std::vector<int> &toRemove, spg_status *status) {
+    using clk = std::chrono::steady_clock;
+    std::vector<int> added;
+    if(status) *status = SPG_OK;
+    stats = spg_marginalize_stats{};
+    const int dim = _graph->dim;
+    std::set<int> toRemoveSet(toRemove.begin(), toRemove.end());
+    std::vector<char> done(toRemove.size(), 0);
+    size_t remaining = toRemove.size();
+
+    struct Region { std::vector<int> removed, region; }; // region: every vertex of the (conservative) blanket
+    while(remaining > 0) {
+        auto t0 = clk::now();
+        // ---- select a round -------------------------------------------------------------------
+        std::vector<RemovalUnit> units;
+        std::vector<Region> regions;            // selected first, then deferred ones
+        std::unordered_map<int, std::vector<int>> touch; // vertex -> regions containing it
+        std::unordered_map<int, int> removedBy;          // vertex -> region removing it
+        std::vector<char> regionSelected;
+        for(size_t i = 0; i < toRemove.size(); i++) {
+            if(done[i]) continue;
+            if(!_graph->hasVertex(toRemove[i])) { // merged into an earlier extended blanket (:91)
+                done[i] = 1;
+                remaining--;
+                continue;
+            }
+            RemovalUnit u;
+            if(!buildUnit(toRemove[i], (int) i, toRemoveSet, u)) {
+                // isolated vertex: the reference asserts blanketEdges.size() > 0
+                error = "vertex " + std::to_string(toRemove[i]) + " has no edges";
+                if(status) *status = SPG_ERR_INVALID;
+                return added;
+            }
+            // conflicts with earlier regions?
+            std::vector<int> hit; // regions this unit interferes with
+            {
+                std::unordered_map<int, int> shared;
+                auto note = [&](int rg) { if(std::find(hit.begin(), hit.end(), rg) == hit.end()) hit.push_back(rg); };
+                for(int x : u.removed) {
+                    auto it = touch.find(x);
+                    if(it != touch.end()) for(int rg : it->second) note(rg);
+                }
+                for(int x : u.kept) {
+                    auto rb = removedBy.find(x);
+                    if(rb != removedBy.end()) note(rb->second);
+                    auto it = touch.find(x);
+                    if(it != touch.end())
+                        for(int rg : it->second)
+                            if(++shared[rg] >= 2) note(rg);
+                }
+            }
+            Region rg;
+            rg.removed = u.removed;
+            rg.region = u.removed;
+            rg.region.insert(rg.region.end(), u.kept.begin(), u.kept.end());
+            const bool select = hit.empty();
+            if(!select) {
+                // deferred: widen its region by everything it waits for (transitively, because the
+                // regions it hit already carry their own closure)
+                std::set<int> wide(rg.region.begin(), rg.region.end());
+                for(int h : hit) wide.insert(regions[h].region.begin(), regions[h].region.end());
+                rg.region.assign(wide.begin(), wide.end());
+            }
+            const int rid = (int) regions.size();
+            for(int x : rg.region) touch[x].push_back(rid);
+            for(int x : rg.removed) removedBy[x] = rid;
+            regions.push_back(std::move(rg));
+            regionSelected.push_back(select);
+            if(select) units.push_back(std::move(u));
+        }
+        if(units.empty()) break;
+
+        // ---- pack ----------------------------------------------------------------------------
+        TopologyProvider *tp = nullptr;
+        std::vector<uint64_t> records;
+        std::vector<int64_t> recOff(1, 0), outOff(1, 0);
+        std::vector<uint64_t> rec;
+        for(const RemovalUnit &u : units) {
+            TopologyProvider *t = chooseTopologyProvider(u);
+            if(!t) {
+                error = "No valid topology provider for Markov blanket";
+                if(status) *status = SPG_ERR_UNSUPPORTED;
+                return added;
+            }
+            if(tp && t->algorithm() != tp->algorithm()) {
+                error = "mixed providers within one round";
+                if(status) *status = SPG_ERR_UNSUPPORTED;
+                return added;
+            }
+            tp = t;
+            if(!packUnit(u, rec)) {
+                error = "Local linearisation point on a non-star blanket needs the subgraph optimiser (not on this path)";
+                if(status) *status = SPG_ERR_UNSUPPORTED;
+                return added;
+            }
+            records.insert(records.end(), rec.begin(), rec.end());
+            recOff.push_back((int64_t) records.size());
+            outOff.push_back(outOff.back() + spgr_out_record_words(dim, tp->algorithm(), _opts.topology, _opts.chordRatio,
+                                                                   (int) u.kept.size()));
+            stats.max_blanket_vertices = std::max<int>(stats.max_blanket_vertices, (int) (u.removed.size() + u.kept.size()));
+        }
+        const int algorithm = tp->algorithm();
+        if(algorithm == SPG_ALG_GLC) {
+            // asserts of TopologyProviderGLC::topology (src/topology_provider_glc.cpp:107-111)
+            if(!(_opts.topology == SparsityOptions::Dense || _opts.topology == SparsityOptions::Tree) ||
+               _opts.linPoint != SparsityOptions::Global) {
+                error = "GLC needs Dense|Tree topology and the Global linearisation point";
+                if(status) *status = SPG_ERR_UNSUPPORTED;
+                return added;
+            }
+        }
+        std::vector<uint64_t> out((size_t) outOff.back(), 0);
+        auto t1 = clk::now();
+
+        // ---- GPU -----------------------------------------------------------------------------
+        spg_round_in rin{};
+        rin.dim = dim;
+        rin.algorithm = algorithm;
+        rin.opts.topology = _opts.topology;
+        rin.opts.lin_point = _opts.linPoint;
+        rin.opts.chord_ratio = _opts.chordRatio;
+        rin.opts.include_intra_clique = _opts.includeIntraClique;
+        rin.opts.flags = _opts.flags;
+        rin.n_blankets = (int32_t) units.size();
+        rin.rec_off = recOff.data();
+        rin.records = records.data();
+        rin.out_off = outOff.data();
+        spg_round_out rout{};
+        rout.out = out.data();
+        spg_status st = spg_remove_round(_ctx, &rin, &rout);
+        if(st != SPG_OK) {
+            error = spg_last_error();
+            if(status) *status = st;
+            return added;
+        }
+        auto t2 = clk::now();
+
+        // ---- splice, in list order (updateInputGraph, src/vertex_remover.cpp:500-546) ---------------
+        const int P = _graph->poseWords();
+        for(size_t ui = 0; ui < units.size(); ui++) {
+            const RemovalUnit &u = units[ui];
+            const uint64_t *o = out.data() + outOff[ui];
+            const int32_t *oh = reinterpret_cast<const int32_t *>(o);
+            const int bstatus = oh[0], nnew = oh[1];
+            if(bstatus != SPG_BLANKET_OK) stats.n_failed++;
+            for(int ei : u.edges) _graph->removeEdge(ei);
+            for(int id : u.removed) _graph->removeVertex(id);
+            const int nk = (int) u.kept.size();
+            const int64_t slot = spgr_out_slot_words(dim, algorithm, _opts.topology, nk);
+            int minor = 0;
+            for(int e = 0; e < nnew; e++) {
+                const uint64_t *sl = o + SPG_OUT_HEADER_WORDS + (int64_t) e * slot;
+                const int32_t *si = reinterpret_cast<const int32_t *>(sl);
+                GraphEdge ge;
+                ge.uidMajor = u.listIndex;
+                if(algorithm == SPG_ALG_NFR) {
+                    ge.kind = SPG_EDGE_POSE;
+                    ge.v = {u.kept[si[0]], u.kept[si[1]]};
+                    ge.rows = dim;
+                    const double *pm = reinterpret_cast<const double *>(sl + 1);
+                    ge.meas.assign(pm, pm + P);
+                    ge.info.assign(pm + P, pm + P + dim * dim);
+                } else {
+                    const int nvcap = (_opts.topology == SparsityOptions::Dense || nk == 1) ? nk : 2;
+                    const int c = dim * nvcap, nve = si[0], rank = si[1];
+                    if(rank == 0) { // getEdge returned NULL (src/topology_provider_glc.cpp:85-89)
+                        stats.n_dropped_edges++;
+                        continue;
+                    }
+                    ge.kind = SPG_EDGE_GLC;
+                    const int32_t *vi = reinterpret_cast<const int32_t *>(sl + 1);
+                    for(int q = 0; q < nve; q++) ge.v.push_back(u.kept[vi[q]]);
+                    ge.rows = rank;
+                    const double *pm = reinterpret_cast<const double *>(sl + 1 + spgr_pad2(nvcap));
+                    ge.meas.assign(pm, pm + dim * nve);
+                    const double *W = pm + c;
+                    ge.info.resize((size_t) rank * dim * nve);
+                    for(int r = 0; r < rank; r++)
+                        for(int q = 0; q < dim * nve; q++) ge.info[(size_t) r * dim * nve + q] = W[(size_t) r * c + q];
+                }
+                ge.uidMinor = minor++;
+                added.push_back(_graph->addEdge(ge));
+            }
+            done[u.listIndex] = 1;
+            remaining--;
+            stats.n_blankets++;
+        }
+        auto t3 = clk::now();
+        stats.n_rounds++;
+        stats.max_round_width = std::max<int>(stats.max_round_width, (int) units.size());
+        stats.pack_ms += std::chrono::duration<double, std::milli>(t1 - t0).count();
+        stats.gpu_ms += std::chrono::duration<double, std::milli>(t2 - t1).count();
+        stats.splice_ms += std::chrono::duration<double, std::milli>(t3 - t2).count();
+    }
+    return added;
+}
+
+// ---- computeSubstituteEdge (src/compute_substitute_edge.cpp:13-96) ---------------------------------
+static void invertSmall(int n, const double *A, double *X) { // Eigen MatrixXd::inverse(): partial-pivot LU
+    std::vector<double> LU(A, A + n * n);
+    std::vector<int> piv(n);
+    for(int k = 0; k < n; k++) {
+        int p = k;
+        double big = std::fabs(LU[k + k * n]);
+        for(int i = k + 1; i < n; i++)
+            if(std::fabs(LU[i + k * n]) > big) { big = std::fabs(LU[i + k * n]); p = i; }
+        piv[k] = p;
+        if(p != k)
+            for(int j = 0; j < n; j++) std::swap(LU[k + j * n], LU[p + j * n]);
+        for(int i = k + 1; i < n; i++) {
+            LU[i + k * n] /= LU[k + k * n];
+            for(int j = k + 1; j < n; j++) LU[i + j * n] -= LU[i + k * n] * LU[k + j * n];
+        }
+    }
+    for(int c = 0; c < n; c++) {
+        std::vector<double> x(n, 0.0);
+        x[c] = 1;
+        for(int k = 0; k < n; k++)
+            if(piv[k] != k) std::swap(x[k], x[piv[k]]);
+        for(int i = 0; i < n; i++)
+            for(int k = 0; k < i; k++) x[i] -= LU[i + k * n] * x[k];
+        for(int i = n - 1; i >= 0; i--) {
+            for(int k = i + 1; k < n; k++) x[i] -= LU[i + k * n] * x[k];
+            x[i] /= LU[i + i * n];
+        }
+        for(int i = 0; i < n; i++) X[i + c * n] = x[i];
+    }
+}
+
+void computeSubstituteEdge(const Graph *gw, const std::set<int> &marginalized, int maxid, int &from, int &to,
+                           double *edgemeas, double *edgeinfo) {
+    std::set<int> visited;
+    std::deque<std::set<int>> frontiers;
+    std::set<int> newFrontier;
+    int minid = std::numeric_limits<int>::max();
+    const int toConnect = std::max(from, to), toReplace = std::min(from, to);
+    newFrontier.insert(toReplace);
+    visited.insert(toConnect);
+    visited.insert(toReplace);
+    auto sortedEdges = [&](int id) {
+        std::vector<int> es = gw->vertex(id)->edges;
+        std::sort(es.begin(), es.end(), [&](int a, int b) {
+            const GraphEdge &x = gw->edges[a], &y = gw->edges[b];
+            if(x.uidMajor != y.uidMajor) return x.uidMajor < y.uidMajor;
+            return x.uidMinor < y.uidMinor;
+        });
+        return es;
+    };
+    do {
+        frontiers.push_back(newFrontier);
+        newFrontier.clear();
+        for(int r : frontiers.back()) {
+            if(marginalized.count(r) == 0 && r != from && r != to) {
+                minid = std::min(minid, r);
+            } else {
+                visited.insert(r);
+                for(int ei : gw->vertex(r)->edges) {
+                    const GraphEdge &e = gw->edges[ei];
+                    if(e.v.size() == 2) {
+                        int idother = e.v[0] == r ? e.v[1] : e.v[0];
+                        if(visited.count(idother) == 0 && idother <= maxid && idother != 0) newFrontier.insert(idother);
+                    }
+                }
+            }
+        }
+    } while(minid == std::numeric_limits<int>::max());
+    visited.clear();
+    visited.insert(toConnect);
+    frontiers.push_front(visited);
+    frontiers.pop_back();
+
+    const int dim = gw->dim, P = gw->poseWords();
+    std::vector<double> covsum(dim * dim, 0.0), inv(dim * dim);
+    double meas[7], tmp[7], zi[7];
+    poseIdentity(dim, meas);
+    int reach = minid;
+    while(!frontiers.empty()) {
+        std::set<int> lastFrontier = frontiers.back();
+        frontiers.pop_back();
+        for(int ei : sortedEdges(reach)) {
+            const GraphEdge &e = gw->edges[ei];
+            if(e.v.size() != 2 || e.kind != SPG_EDGE_POSE) continue;
+            if(lastFrontier.count(e.v[0]) || lastFrontier.count(e.v[1])) {
+                invertSmall(dim, e.info.data(), inv.data());
+                for(int q = 0; q < dim * dim; q++) covsum[q] += inv[q];
+                poseInverse(dim, e.meas.data(), zi);
+                if(from == toConnect) {
+                    if(e.v[1] == reach) poseCompose(dim, e.meas.data(), meas, tmp);
+                    else poseCompose(dim, zi, meas, tmp);
+                } else {
+                    if(e.v[1] == reach) poseCompose(dim, meas, zi, tmp);
+                    else poseCompose(dim, meas, e.meas.data(), tmp);
+                }
+                std::memcpy(meas, tmp, sizeof(double) * P);
+                reach = e.v[1] == reach ? e.v[0] : e.v[1];
+                break;
+            }
+        }
+    }
+    invertSmall(dim, covsum.data(), inv.data());
+    for(int i = 0; i < dim; i++)
+        for(int j = 0; j < dim; j++) edgeinfo[i + j * dim] = 0.5 * (inv[i + j * dim] + inv[j + i * dim]);
+    std::memcpy(edgemeas, meas, sizeof(double) * P);
+    if(from == toConnect) to = minid;
+    else from = minid;
+}
+
+} // namespace spg
+
+// ---- C ABI, graph level ------------------------------------------------------------------------------
+extern "C" {
+
+spg_status spg_graph_create(spg_graph **g, int32_t dim) {
+    if(!g || (dim != 3 && dim != 6)) return SPG_ERR_INVALID;
+    *g = new spg_graph;
+    (*g)->g = new spg::Graph(dim);
+    return SPG_OK;
+}
+void spg_graph_destroy(spg_graph *g) {
+    if(!g) return;
+    delete g->g;
+    delete g;
+}
+spg_status spg_graph_load_g2o(spg_graph **g, const char *path) {
+    if(!g || !path) return SPG_ERR_INVALID;
+    std::string err;
+    spg::Graph *gr = spg::Graph::loadG2o(path, &err);
+    if(!gr) return SPG_ERR_IO;
+    *g = new spg_graph;
+    (*g)->g = gr;
+    return SPG_OK;
+}
+spg_status spg_graph_add_vertex(spg_graph *g, int32_t id, const double *pose) {
+    if(!g || !pose) return SPG_ERR_INVALID;
+    return g->g->addVertex(id, pose) ? SPG_OK : SPG_ERR_INVALID;
+}
+spg_status spg_graph_add_edge(spg_graph *g, int32_t from, int32_t to, const double *meas, const double *info) {
+    if(!g || !meas || !info) return SPG_ERR_INVALID;
+    return g->g->addPoseEdge(from, to, meas, info) >= 0 ? SPG_OK : SPG_ERR_INVALID;
+}
+int32_t spg_graph_dim(const spg_graph *g) { return g ? g->g->dim : 0; }
+int32_t spg_graph_num_vertices(const spg_graph *g) { return g ? g->g->aliveVertices : 0; }
+int32_t spg_graph_num_edges(const spg_graph *g) { return g ? g->g->aliveEdges : 0; }
+int32_t spg_graph_max_vertex_id(const spg_graph *g) { return g ? g->g->maxVertexId() : -1; }
+
+static int32_t copyOut(const std::vector<int> &r, int32_t *out, int32_t cap) {
+    for(size_t i = 0; i < r.size() && (int32_t) i < cap; i++) out[i] = r[i];
+    return (int32_t) r.size();
+}
+int32_t spg_decimate_global(int32_t last, int32_t endvert, int32_t sparsity, int32_t *out, int32_t cap) {
+    return copyOut(spg::globalDecimate(last, endvert, spg::DecimateOptions{sparsity, 0}), out, cap);
+}
+int32_t spg_decimate_online(int32_t last, int32_t endvert, int32_t sparsity, int32_t *out, int32_t cap) {
+    return copyOut(spg::onlineDecimate(last, endvert, spg::DecimateOptions{sparsity, 0}), out, cap);
+}
+int32_t spg_decimate_cluster(int32_t last, int32_t endvert, int32_t sparsity, int32_t cluster_size, int32_t *out,
+                             int32_t cap) {
+    return copyOut(spg::clusterDecimate(last, endvert, spg::DecimateOptions{sparsity, cluster_size}), out, cap);
+}
+
+// GraphWrapperG2O::marginalizeNoOptimize (src/graph_wrapper_g2o.cpp:398-453): provider registration
+// order as :431-439, then VertexRemover::remove.
+spg_status spg_graph_marginalize(spg_graph *g, spg_ctx *ctx, const int32_t *which, int32_t n_which,
+                                 const spg_sparsity_options *opts, int32_t algorithm) {
+    if(!g || !ctx || !which || !opts || n_which < 0) return SPG_ERR_INVALID;
+    for(int i = 0; i < n_which; i++)
+        if(!g->g->hasVertex(which[i])) return SPG_ERR_INVALID; // "vertex needs to exist in order to be marginalized" (:406-407)
+    spg::VertexRemover vr;
+    if(algorithm == SPG_ALG_GLC) {
+        vr.registerTopologyProvider(new spg::TopologyProviderGLC);
+    } else {
+        vr.registerTopologyProvider(new spg::TopologyProviderSE2);
+        vr.registerTopologyProvider(new spg::TopologyProviderSE2ISAM);
+        vr.registerTopologyProvider(new spg::TopologyProviderSE3);
+        vr.registerTopologyProvider(new spg::TopologyProviderSE3ISAM);
+    }
+    vr.setGraph(g->g);
+    vr.setContext(ctx);
+    spg::SparsityOptions o;
+    o.topology = (spg::SparsityOptions::SparsityTopology) opts->topology;
+    o.chordRatio = opts->chord_ratio;
+    o.linPoint = (spg::SparsityOptions::LinearizationPoint) opts->lin_point;
+    o.includeIntraClique = opts->include_intra_clique != 0;
+    o.flags = opts->flags;
+    vr.setSparsityOptions(o);
+    spg_status st = SPG_OK;
+    vr.remove(std::vector<int>(which, which + n_which), &st);
+    g->stats = vr.stats;
+    return st;
+}
+spg_status spg_graph_last_stats(const spg_graph *g, spg_marginalize_stats *stats) {
+    if(!g || !stats) return SPG_ERR_INVALID;
+    *stats = g->stats;
+    return SPG_OK;
+}
+
+// edge read-back in canonical order (idx is a position in that order; O(E log E) per call batch: the
+// order is cached per query run by callers that iterate 0..E-1)
+static thread_local std::vector<int> t_order;
+static thread_local const spg::Graph *t_order_of = nullptr;
+static thread_local size_t t_order_edges = 0;
+static const spg::GraphEdge *edgeAt(const spg_graph *g, int idx) {
+    if(t_order_of != g->g || t_order_edges != g->g->edges.size() || (int) t_order.size() != g->g->aliveEdges) {
+        t_order = g->g->edgeOrder();
+        t_order_of = g->g;
+        t_order_edges = g->g->edges.size();
+    }
+    if(idx < 0 || idx >= (int) t_order.size()) return nullptr;
+    return &g->g->edges[t_order[idx]];
+}
+spg_status spg_graph_edge_desc(const spg_graph *g, int32_t idx, spg_edge_desc *d) {
+    if(!g || !d) return SPG_ERR_INVALID;
+    const spg::GraphEdge *e = edgeAt(g, idx);
+    if(!e) return SPG_ERR_INVALID;
+    d->kind = e->kind;
+    d->nv = (int32_t) e->v.size();
+    d->rows = e->rows;
+    d->uid_major = e->uidMajor;
+    d->uid_minor = e->uidMinor;
+    return SPG_OK;
+}
+spg_status spg_graph_edge_data(const spg_graph *g, int32_t idx, int32_t *vert_ids, double *meas, double *info_or_w) {
+    if(!g) return SPG_ERR_INVALID;
+    const spg::GraphEdge *e = edgeAt(g, idx);
+    if(!e) return SPG_ERR_INVALID;
+    if(vert_ids) for(size_t i = 0; i < e->v.size(); i++) vert_ids[i] = e->v[i];
+    if(meas) std::memcpy(meas, e->meas.data(), sizeof(double) * e->meas.size());
+    if(info_or_w) std::memcpy(info_or_w, e->info.data(), sizeof(double) * e->info.size());
+    return SPG_OK;
+}
+spg_status spg_graph_vertex_ids(const spg_graph *g, int32_t *ids) {
+    if(!g || !ids) return SPG_ERR_INVALID;
+    std::vector<int> v = g->g->vertexIds();
+    for(size_t i = 0; i < v.size(); i++) ids[i] = v[i];
+    return SPG_OK;
+}
+spg_status spg_graph_vertex_pose(const spg_graph *g, int32_t id, double *pose) {
+    if(!g || !pose) return SPG_ERR_INVALID;
+    const spg::GraphVertex *v = g->g->vertex(id);
+    if(!v) return SPG_ERR_INVALID;
+    std::memcpy(pose, v->pose, sizeof(double) * g->g->poseWords());
+    return SPG_OK;
+}
+spg_status spg_compute_substitute_edge(const spg_graph *g, const int32_t *marginalized, int32_t n_marginalized,
+                                       int32_t maxid, int32_t *from, int32_t *to, double *meas, double *info) {
+    if(!g || !from || !to || !meas || !info) return SPG_ERR_INVALID;
+    std::set<int> m(marginalized, marginalized + n_marginalized);
+    int f = *from, t = *to;
+    if(!g->g->hasVertex(f) || !g->g->hasVertex(t)) return SPG_ERR_INVALID;
+    spg::computeSubstituteEdge(g->g, m, maxid, f, t, meas, info);
+    *from = f;
+    *to = t;
+    return SPG_OK;
+}
+
+} // extern "C"

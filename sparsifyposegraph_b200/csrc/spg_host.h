@@ -1,0 +1,176 @@
+// spg_host.h — host-side mirror of the reference's plugin surface for the node-removal path,
+// over a g2o-free pose-graph container. Names follow the reference so the adapters read like it:
+//   SparsityOptions        reference src/sparsity_options.h:11-30
+//   DecimateOptions / *Decimate   src/decimation.{h,cpp}
+//   TopologyProvider{,GLC,SE2,SE3}  src/topology_provider*.h — here a provider is a *descriptor*: it
+//        decides applicability per blanket on the host and selects the device code path
+//        (algorithm + dimension); the numerical body of topology()/optimizeInformation() runs in the
+//        fused CUDA kernel (spg_kernels.cuh).
+//   VertexRemover          src/vertex_remover.{h,cpp} — same public calls; remove() groups the
+//        removal list into wavefront rounds of non-interfering blankets (result identical to the
+//        reference's one-at-a-time loop) and sends each round through spg_remove_round().
+//   computeSubstituteEdge  src/compute_substitute_edge.cpp:13-96
+#pragma once
+#include <cstdint>
+#include <list>
+#include <map>
+#include <set>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/spg_capi.h"
+
+namespace spg {
+
+struct SparsityOptions {
+    enum SparsityTopology { Tree, Subgraph, CliqueySubgraph, Dense, CliqueyDense };
+    enum LinearizationPoint { Local, Global };
+    SparsityTopology topology = Tree;
+    double chordRatio = 1;
+    LinearizationPoint linPoint = Local;
+    bool includeIntraClique = true;
+    int flags = 0;
+};
+
+struct DecimateOptions {
+    int sparsity;
+    int clusterSize;
+};
+std::vector<int> clusterDecimate(int last, int endvert, const DecimateOptions &opts);
+std::vector<int> onlineDecimate(int last, int endvert, const DecimateOptions &opts);
+std::vector<int> globalDecimate(int lastid, int endvert, const DecimateOptions &opts);
+typedef std::vector<int> (*DecimateFunction)(int last, int endvert, const DecimateOptions &opts);
+
+// ---- pose-graph container ----------------------------------------------------------------------
+struct GraphEdge {
+    int kind = SPG_EDGE_POSE;
+    std::vector<int> v;          // vertex ids, in the edge's own order (from, to, ...)
+    int rows = 0;                // error dimension
+    std::vector<double> meas;    // POSE: P; GLC: d*nv; MULTI: nmeas*P
+    std::vector<double> info;    // POSE/MULTI: rows*rows column-major; GLC: W rows x d*nv row-major
+    std::vector<int> pairs;      // MULTI: 2*nmeas indices into v
+    int uidMajor = -1, uidMinor = 0; // canonical order: file edges (-1, file index); new edges (list index, k)
+    bool alive = true;
+};
+struct GraphVertex {
+    int id = 0;
+    double pose[7] = {0, 0, 0, 0, 0, 0, 1};
+    std::vector<int> edges;      // indices into Graph::edges (alive ones only)
+    bool alive = true;
+};
+
+class Graph {
+public:
+    explicit Graph(int dim_) : dim(dim_) {}
+    int dim;
+    int poseWords() const { return dim == 3 ? 3 : 7; }
+    std::vector<GraphVertex> verts;
+    std::vector<GraphEdge> edges;
+    std::unordered_map<int, int> index; // id -> verts index
+    int fileEdges = 0;
+    int aliveVertices = 0, aliveEdges = 0;
+
+    static Graph *loadG2o(const std::string &path, std::string *err);
+    bool hasVertex(int id) const;
+    GraphVertex *vertex(int id);
+    const GraphVertex *vertex(int id) const;
+    bool addVertex(int id, const double *pose);
+    int addPoseEdge(int from, int to, const double *meas, const double *info);
+    int addEdge(const GraphEdge &e); // generic (uid must be set)
+    void removeEdge(int ei);
+    void removeVertex(int id);
+    int maxVertexId() const;
+    std::vector<int> vertexIds() const;          // ascending
+    std::vector<int> edgeOrder() const;          // alive edges in canonical order
+};
+
+// ---- topology providers (descriptors) --------------------------------------------------------------
+class TopologyProvider {
+public:
+    virtual ~TopologyProvider() {}
+    // src/topology_provider_base.h:20-24 — every vertex/edge kind of the blanket must be supported
+    virtual bool applicable(int dim, const std::set<int> &edgeKinds) const = 0;
+    virtual int algorithm() const = 0;                 // SPG_ALG_*
+    virtual bool requiresOptimization() const = 0;     // NFR: true, GLC: false
+    virtual void setSparsityOptions(const SparsityOptions &o) { _opts = o; }
+protected:
+    SparsityOptions _opts;
+};
+class TopologyProviderGLC : public TopologyProvider { // src/topology_provider_glc.{h,cpp}
+public:
+    bool applicable(int dim, const std::set<int> &) const override { return dim == 3 || dim == 6; } // checks vertices only (:26-30)
+    int algorithm() const override { return SPG_ALG_GLC; }
+    bool requiresOptimization() const override { return false; }
+};
+template <int DIM>
+class TopologyProviderBinary : public TopologyProvider { // src/topology_provider_binary.{h,hpp}
+public:
+    bool applicable(int dim, const std::set<int> &kinds) const override {
+        if(dim != DIM) return false;
+        for(int k : kinds)
+            if(k != SPG_EDGE_POSE && k != SPG_EDGE_MULTI) return false; // E and MultiEdgeCorrelated<E> (:15-19)
+        return true;
+    }
+    int algorithm() const override { return SPG_ALG_NFR; }
+    bool requiresOptimization() const override { return true; }
+};
+typedef TopologyProviderBinary<3> TopologyProviderSE2ISAM; // the graphs built here carry the *ISAM edge types
+typedef TopologyProviderBinary<6> TopologyProviderSE3ISAM; // (graph_wrapper_g2o.cpp:120-146)
+typedef TopologyProviderBinary<3> TopologyProviderSE2;
+typedef TopologyProviderBinary<6> TopologyProviderSE3;
+
+// ---- VertexRemover ---------------------------------------------------------------------------------
+struct RemovalUnit {
+    int listIndex = 0;               // index of the root in the removal list
+    std::vector<int> removed;        // ascending id (toRemoveNow)
+    std::vector<int> kept;           // ascending id
+    std::vector<int> edges;          // blanket edges, canonical order
+};
+
+class VertexRemover {
+public:
+    VertexRemover();
+    ~VertexRemover();
+    void setSparsityOptions(const SparsityOptions &opts);
+    void setGraph(Graph *graph) { _graph = graph; }
+    void setContext(spg_ctx *ctx) { _ctx = ctx; }
+    void registerTopologyProvider(TopologyProvider *topology) { _topologies.push_back(topology); } // takes ownership
+
+    // Returns the indices (into Graph::edges) of the edges added, in removal order then provider order.
+    // status: SPG_OK or the first error (graph is left consistent up to the failing round).
+    std::vector<int> remove(int toRemove, spg_status *status = nullptr);
+    std::vector<int> remove(const std::vector<int> &toRemove, spg_status *status = nullptr);
+
+    std::vector<int> markovBlanketVertices(int root) const;
+    std::vector<int> extendedMarkovBlanketVertices(int root, const std::set<int> &pickBin, std::vector<int> &picked) const;
+    std::vector<int> markovBlanketEdges(const std::vector<int> &mbVertices, const std::vector<int> &hubs) const;
+
+    spg_marginalize_stats stats{};
+    std::string error;
+
+private:
+    bool buildUnit(int root, int listIndex, const std::set<int> &toRemoveSet, RemovalUnit &u) const;
+    TopologyProvider *chooseTopologyProvider(const RemovalUnit &u) const;
+    bool packUnit(const RemovalUnit &u, std::vector<uint64_t> &rec) const;
+
+    SparsityOptions _opts;
+    Graph *_graph = nullptr;
+    spg_ctx *_ctx = nullptr;
+    std::list<TopologyProvider *> _topologies;
+};
+
+// src/compute_substitute_edge.cpp:13-96 (meas: P doubles, info: d*d column-major)
+void computeSubstituteEdge(const Graph *gw, const std::set<int> &marginalized, int maxid, int &from, int &to,
+                           double *edgemeas, double *edgeinfo);
+
+// small pose helpers shared by the host code (packer / substitute edge); not the hot path
+void poseCompose(int dim, const double *a, const double *b, double *out);
+void poseInverse(int dim, const double *a, double *out);
+
+} // namespace spg
+
+struct spg_graph {
+    spg::Graph *g = nullptr;
+    spg_marginalize_stats stats{};
+};

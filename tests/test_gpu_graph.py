@@ -1,0 +1,86 @@
+"""GPU graph-level parity (run with -m gpu): spg_graph_marginalize (wavefront rounds through the CUDA
+kernels) against the oracle's sequential VertexRemover::remove on the reference's datasets
+(BASELINE.json configs 1-3). Removal sets / topology bit-exact, information matrices <= 1e-9 relative
+Frobenius."""
+import numpy as np
+import pytest
+
+import datasets
+from sparsifyposegraph_b200 import records as R
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from sparsifyposegraph_b200 import capi
+    c = capi.Context(0)
+    yield c
+    c.close()
+
+
+def compare_graphs(g, o, tol=1e-9):
+    assert np.array_equal(g.vertex_ids(), o.vertex_ids())
+    ge, oe = g.edges(), o.edges()
+    assert len(ge) == len(oe)
+    worst = 0.0
+    for a, b in zip(ge, oe):
+        assert a["uid"] == b["uid"], (a["uid"], b["uid"])
+        assert a["kind"] == b["kind"] and list(a["v"]) == list(b["v"]), (a["uid"], a["v"], b["v"])
+        assert np.allclose(a["meas"], b["meas"], atol=1e-11)
+        if a["kind"] == 1:   # GLC: compare W^T W (eigenvector signs are free)
+            assert a["rows"] == b["rows"]
+            A, B = a["info"].T @ a["info"], b["info"].T @ b["info"]
+        else:
+            A, B = a["info"], b["info"]
+        worst = max(worst, np.linalg.norm(A - B) / max(np.linalg.norm(B), 1e-300))
+    assert worst <= tol, worst
+    return worst
+
+
+@pytest.mark.parametrize("name,alg,topo,sparsity", [
+    ("sphere", R.ALG_NFR, R.TOPO_TREE, 2),
+    ("intel", R.ALG_NFR, R.TOPO_TREE, 2),
+    ("manhattan", R.ALG_NFR, R.TOPO_TREE, 2),
+    ("intel", R.ALG_NFR, R.TOPO_TREE, 3),
+    ("sphere", R.ALG_NFR, R.TOPO_TREE, 4),
+])
+def test_global_decimation_matches_sequential_oracle(ctx, oracle, name, alg, topo, sparsity):
+    from sparsifyposegraph_b200 import capi
+    g = capi.Graph(datasets.path(name))
+    o = oracle.Graph(datasets.path(name))
+    last = g.max_vertex_id
+    which = capi.decimate_global(last, last, sparsity)
+    assert np.array_equal(which, oracle.decimate_global(last, last, sparsity))
+    st = g.marginalize(ctx, which, capi.make_opts(topo, R.LIN_GLOBAL), alg)
+    bad = o.marginalize(which, oracle.make_opts(topo, R.LIN_GLOBAL), alg)
+    assert bad == 0 and st["n_failed"] == 0
+    assert st["n_blankets"] == len(which)
+    assert st["n_rounds"] < len(which) / 4          # the wavefront really batches
+    worst = compare_graphs(g, o)
+    print(f"{name}: {st['n_blankets']} blankets in {st['n_rounds']} rounds (max width {st['max_round_width']}), "
+          f"worst rel. Frobenius {worst:.2e}")
+
+
+def test_local_linearisation_star_blankets(ctx, oracle):
+    """Local lin. point with the closed-form (star) estimate, vertex_remover.cpp:304-381: removing a
+    chain's interior vertices one by one keeps every blanket star-shaped."""
+    from sparsifyposegraph_b200 import capi, synth
+    rng = np.random.default_rng(4)
+    n = 12
+    poses = synth.random_poses(rng, (n,), 6)
+    g = capi.Graph(dim=6)
+    o = oracle.Graph(dim=6)
+    for i in range(n):
+        g.add_vertex(i, poses[i])
+        o.add_vertex(i, poses[i])
+    for i in range(n - 1):
+        z = synth.se3_compose(synth.se3_compose(synth.se3_inverse(poses[i]), poses[i + 1]),
+                              synth.se3_exp_small(rng, (), 0.05, 0.02))
+        info = synth.random_info(rng, (), 6)
+        g.add_edge(i, i + 1, z, info)
+        o.add_edge(i, i + 1, z, info)
+    which = [5, 7, 9]
+    g.marginalize(ctx, which, capi.make_opts(R.TOPO_TREE, R.LIN_LOCAL), R.ALG_NFR)
+    assert o.marginalize(which, oracle.make_opts(R.TOPO_TREE, R.LIN_LOCAL), R.ALG_NFR) == 0
+    compare_graphs(g, o)

@@ -1,0 +1,98 @@
+"""CPU tests of the product's host side (no GPU, no compute calls into CUDA): the C ABI exports every
+symbol of include/spg_capi.h, the g2o reader / decimation / computeSubstituteEdge agree with the
+oracle, and the no-device path fails loudly."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import datasets
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from sparsifyposegraph_b200 import capi
+    L = capi.lib()
+    hdr = open(os.path.join(ROOT, "include", "spg_capi.h")).read()
+    names = set(re.findall(r"\b(spg_[a-z0-9_]+)\s*\(", hdr))
+    assert len(names) > 25
+    for n in sorted(names):
+        assert hasattr(L, n), n
+    assert b"sm_100a" in L.spg_version()
+
+
+def test_no_device_fails_loudly():
+    import torch
+    from sparsifyposegraph_b200 import capi
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(capi.SpgError):
+        capi.Context(0)
+
+
+def test_record_sizes_match_python_mirror():
+    from sparsifyposegraph_b200 import capi, records as R
+    L = capi.lib()
+    for dim in (3, 6):
+        for alg in (0, 1):
+            for topo in (0, 1, 3):
+                for nk in (1, 2, 3, 5, 9):
+                    o = capi.make_opts(topo, 1, 1.0)
+                    assert L.spg_out_record_words(dim, alg, ctypes.byref(o), nk) == R.out_record_words(dim, alg, topo, 1.0, nk)
+
+
+@pytest.mark.parametrize("name", ["intel", "sphere"])
+def test_graph_load_matches_oracle(oracle, name):
+    from sparsifyposegraph_b200 import capi
+    g = capi.Graph(datasets.path(name))
+    o = oracle.Graph(datasets.path(name))
+    assert (g.num_vertices, g.num_edges, g.dim, g.max_vertex_id) == (o.num_vertices, o.num_edges, o.dim, o.max_vertex_id)
+    assert np.array_equal(g.vertex_ids(), o.vertex_ids())
+    ge, oe = g.edges(), o.edges()
+    for a, b in list(zip(ge, oe))[::97]:
+        assert a["uid"] == b["uid"] and list(a["v"]) == list(b["v"])
+        assert np.allclose(a["meas"], b["meas"], atol=1e-15) and np.allclose(a["info"], b["info"], atol=0)
+
+
+def test_decimation_matches_reference_rules(oracle):
+    from sparsifyposegraph_b200 import capi
+    for last, end, s in [(942, 942, 2), (941, 942, 2), (20, 20, 3), (2499, 2499, 5)]:
+        assert np.array_equal(capi.decimate_global(last, end, s), oracle.decimate_global(last, end, s))
+    for last in range(3, 40):
+        assert np.array_equal(capi.decimate_online(last, 100, 3), oracle.decimate_online(last, 100, 3))
+        assert np.array_equal(capi.decimate_cluster(last, 37, 2, 10), oracle.decimate_cluster(last, 37, 2, 10))
+
+
+@pytest.mark.parametrize("name", ["intel", "sphere"])
+def test_compute_substitute_edge_matches_oracle(oracle, name):
+    """Online profile situation (evaluate.cpp:103-123): a new vertex links to an already marginalised one."""
+    import ctypes as C
+    from sparsifyposegraph_b200 import capi
+    g = capi.Graph(datasets.path(name))
+    o = oracle.Graph(datasets.path(name))
+    L = oracle.lib()
+    edges = g.edges()
+    rng = np.random.default_rng(0)
+    checked = 0
+    for e in edges:
+        a, b = int(e["v"][0]), int(e["v"][1])
+        hi, lo = max(a, b), min(a, b)
+        if hi - lo < 2 or lo < 4 or lo % 2 == 0:
+            continue
+        marg = [i for i in range(4, hi) if i % 2 != 0]   # odd ids below the new vertex are gone
+        f1, t1, m1, i1 = g.compute_substitute_edge(marg, hi - 1, a, b)
+        mm = np.asarray(sorted(marg), dtype=np.int32)
+        f, t = C.c_int(a), C.c_int(b)
+        m2, i2 = np.zeros(g.P), np.zeros(g.dim * g.dim)
+        L.orc_compute_substitute_edge(o.h, mm.ctypes.data_as(C.c_void_p), len(mm), hi - 1, C.byref(f), C.byref(t),
+                                      m2.ctypes.data_as(C.c_void_p), i2.ctypes.data_as(C.c_void_p))
+        assert (f1, t1) == (f.value, t.value)
+        assert np.allclose(m1, m2, atol=1e-12)
+        assert np.allclose(i1, i2.reshape(g.dim, g.dim).T, rtol=1e-10, atol=1e-9)
+        checked += 1
+        if checked >= 25:
+            break
+    assert checked >= 5
