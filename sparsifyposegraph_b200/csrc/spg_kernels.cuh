@@ -11,6 +11,7 @@
 #include "../../include/spg_capi.h"
 #include "../../include/spg_record.h"
 #include "spg_device.cuh"
+#include "spg_glc.cuh"
 
 namespace spg {
 
@@ -33,6 +34,7 @@ struct KernelParams {
     int32_t max_nv, max_e, max_rec_words;
     int32_t off_pose, off_buf0, off_buf1, off_buf2, off_small, total_doubles;
     int32_t buf0_doubles, buf1_doubles, buf2_doubles;
+    int32_t off_glc, glc_doubles; // GLC scratch (only for algorithm == SPG_ALG_GLC launches)
 };
 
 constexpr int ASM_CHUNK = 8; // edges linearised per pre-pass
@@ -64,6 +66,17 @@ inline void plan_smem(KernelParams &p) {
     //        tree[2*max(pairs,1)] (int) uf[nk] (int) Lfac[nk*D*D] logd[nk] misc[16]
     o += kmax + (kmax + 1) / 2 + (kmax + kmax / 2 + 4) + 8 + pairs + pairs + pairs + (pairs > 0 ? pairs : 1) + (nk + 1) / 2 + 1 +
          nk * D * D + nk + 16;
+    p.off_glc = o;
+    p.glc_doubles = 0;
+    if(p.algorithm == SPG_ALG_GLC) {
+        // tree: joint (4D^2) + target (4D^2) + pinv out (D^2) + pinv scratch + getEdge scratch (c = 2D);
+        // dense: meas k + blocks 2 nk D^2 + Jacobi scratch + order
+        const int c = 2 * D;
+        const int tree = 4 * D * D + 4 * D * D + D * D + (2 * D * (D | 1) + 2 * D + 16) + (8 * c * c + 8 * c + 64);
+        const int dense = kmax + 2 * nk * D * D + (kmax + kmax / 2 + 8) + 8 + kmax / 2 + 2;
+        p.glc_doubles = (tree > dense ? tree : dense) + 8;
+        o += p.glc_doubles;
+    }
     p.total_doubles = o;
 }
 
@@ -229,6 +242,44 @@ __device__ __forceinline__ int pk(int a, int b) { return a | (b << 16); }
 __device__ __forceinline__ int pk_a(int v) { return v & 0xffff; }
 __device__ __forceinline__ int pk_b(int v) { return v >> 16; }
 
+// H += J^T J for one GLC edge, J = W * J_reparam (Omega = I). Returns false (uniformly) when the
+// scratch does not fit.
+template <int D, int NT>
+__device__ bool assemble_glc_edge(const uint64_t *ew, const double *s_pose, double *H, int ldH, double *scratch, int cap) {
+    constexpr int PS = PoseStride<D>::value;
+    const int tid = threadIdx.x;
+    const int32_t *eh = reinterpret_cast<const int32_t *>(ew);
+    const int nv = eh[1], r = eh[2], c = D * nv;
+    const int32_t *vi = reinterpret_cast<const int32_t *>(ew + 2);
+    const double *meas = reinterpret_cast<const double *>(ew + 2 + spgr_pad2(nv));
+    const double *W = meas + c; // r x c row-major
+    double *JA = scratch, *JB = scratch + nv * D * D, *Jf = scratch + 2 * nv * D * D; // Jf: r x c column-major (ld r)
+    if(2 * nv * D * D + r * c > cap) return false;
+    for(int i = tid; i < nv; i += NT)
+        glc_reparam_blocks<D>(i, meas, s_pose + PS * vi[0], s_pose + PS * vi[i], JA + i * D * D, JB + i * D * D);
+    gsync<NT>();
+    for(int t = tid; t < r * c; t += NT) {
+        const int row = t % r, col = t / r, bi = col / D, j = col % D;
+        double s = 0;
+        if(bi == 0) {
+            for(int i = 0; i < nv; i++)
+                for(int q = 0; q < D; q++) s += W[(size_t) row * c + i * D + q] * JA[i * D * D + q + j * D];
+        } else {
+            for(int q = 0; q < D; q++) s += W[(size_t) row * c + bi * D + q] * JB[bi * D * D + q + j * D];
+        }
+        Jf[row + (size_t) col * r] = s;
+    }
+    gsync<NT>();
+    for(int t = tid; t < c * c; t += NT) {
+        const int a = t % c, b = t / c;
+        double s = 0;
+        for(int row = 0; row < r; row++) s += Jf[row + (size_t) a * r] * Jf[row + (size_t) b * r];
+        H[(vi[a / D] * D + a % D) + (size_t) (vi[b / D] * D + b % D) * ldH] += s;
+    }
+    gsync<NT>();
+    return true;
+}
+
 template <int D, int NT>
 __global__ void __launch_bounds__(NT) blanket_kernel(const KernelParams P) {
     extern __shared__ double smem[];
@@ -301,8 +352,22 @@ __global__ void __launch_bounds__(NT) blanket_kernel(const KernelParams P) {
 
         // ---- S1: assembly H = sum_e J^T Omega J (edge order = record order) -------------------------
         double *H = buf0;
-        for(int e0 = 0; e0 < ne; e0 += ASM_CHUNK) {
-            const int ce = min(ASM_CHUNK, ne - e0);
+        int e0 = 0;
+        while(e0 < ne) {
+            const int kind0 = reinterpret_cast<const int32_t *>(s_rec + r_etab[e0])[0];
+            if(kind0 != SPG_EDGE_POSE) {
+                // GLCEdge (J = W * J_reparam, Omega = I; glc_edge.cpp:40-49) — one edge at a time, whole CTA.
+                // Scratch: buf1 and buf2 are contiguous and both free during assembly.
+                bool okg = false;
+                if(kind0 == SPG_EDGE_GLC)
+                    okg = assemble_glc_edge<D, NT>(s_rec + r_etab[e0], s_pose, H, ldH, buf1, P.buf1_doubles + P.buf2_doubles);
+                if(!okg) status = SPG_BLANKET_UNSUPPORTED; // uniform
+                e0++;
+                continue;
+            }
+            int ce = 1;
+            while(ce < ASM_CHUNK && e0 + ce < ne &&
+                  reinterpret_cast<const int32_t *>(s_rec + r_etab[e0 + ce])[0] == SPG_EDGE_POSE) ce++;
             for(int e = tid; e < ce; e += NT) { // linearise: one thread per edge
                 const uint64_t *ew = s_rec + r_etab[e0 + e];
                 const int32_t *eh = reinterpret_cast<const int32_t *>(ew);
@@ -348,6 +413,7 @@ __global__ void __launch_bounds__(NT) blanket_kernel(const KernelParams P) {
                 }
                 gsync<NT>();
             }
+            e0 += ce;
         }
         if(s_misc[0] != SPG_BLANKET_OK) status = s_misc[0];
 
@@ -388,7 +454,8 @@ __global__ void __launch_bounds__(NT) blanket_kernel(const KernelParams P) {
 
         // ---- S3: sparsity pattern (PseudoChowLiu::computeSparsityPattern, pseudo_chow_liu.cpp:33-87) ---
         int n_out = 0;
-        if(status == SPG_BLANKET_OK && P.algorithm == SPG_ALG_NFR && nk >= 2) {
+        const bool glc_tree = (P.algorithm == SPG_ALG_GLC && P.topology == SPG_TOPO_TREE);
+        if(status == SPG_BLANKET_OK && (P.algorithm == SPG_ALG_NFR || glc_tree) && nk >= 2) {
             const int mch = (int) ((1 + P.chord_ratio) * (nk - 1));
             const int all = nk * (nk - 1) / 2;
             const bool full = mch >= all;
@@ -676,6 +743,66 @@ __global__ void __launch_bounds__(NT) blanket_kernel(const KernelParams P) {
                 gsync<NT>();
                 if(s_misc[0] != SPG_BLANKET_OK) status = s_misc[0];
             }
+        }
+
+        // ---- S5: GLC substitute factors (TopologyProviderGLC::topology, topology_provider_glc.cpp:100-185) ----
+        if(status == SPG_BLANKET_OK && P.algorithm == SPG_ALG_GLC && nk >= 1) {
+            gsync<NT>();
+            double *gsc = smem + P.off_glc;
+            const double *kept_pose = s_pose + PS * nrem;
+            const bool dense = (P.topology == SPG_TOPO_DENSE) || nk == 1;
+            const int nvcap = dense ? nk : 2, cslot = D * nvcap;
+            const int64_t slotw = 1 + spgr_pad2(nvcap) + cslot + (int64_t) cslot * cslot;
+            int emitted = 0;
+            if(dense) {
+                const int rank = glc_get_edge_dense<D, NT>(T, k, ldH, nk, kept_pose, buf1, buf2, ldk, gsc, gout + SPG_OUT_HEADER_WORDS);
+                if(rank < 0) status = SPG_BLANKET_EIG_NOCONV;
+                else if(rank > 0) emitted = 1;
+            } else {
+                double *Sj = gsc, *tgt = Sj + 4 * D * D, *pin = tgt + 4 * D * D, *psc = pin + D * D;
+                double *esc = psc + (2 * D * (D | 1) + 2 * D + 16);
+                int *kv = s_misc + 12;
+                // root unary factor from the marginal of the root vertex (:134-140)
+                const int root = pk_a(s_tree[0]);
+                if(!glc_marginal<D, NT>(T, k, ldH, root, 0, 1, Sj, buf1, buf2)) status = SPG_BLANKET_NOT_PD_JOINT;
+                if(status == SPG_BLANKET_OK) {
+                    if(tid == 0) kv[0] = root;
+                    gsync<NT>();
+                    const int rank = glc_get_edge_small<D, NT>(Sj, 1, kv, kept_pose, esc, gout + SPG_OUT_HEADER_WORDS + emitted * slotw, cslot, nvcap);
+                    if(rank < 0) status = SPG_BLANKET_EIG_NOCONV;
+                    else if(rank > 0) emitted++;
+                }
+                for(int e = 0; e < n_out && status == SPG_BLANKET_OK; e++) {
+                    const int a = pk_a(s_tree[e]), bb = pk_b(s_tree[e]);
+                    if(!glc_marginal<D, NT>(T, k, ldH, a, bb, 2, Sj, buf1, buf2)) { status = SPG_BLANKET_NOT_PD_JOINT; break; }
+                    // target = [Jaa Jab; Jba Jba pinv(Jaa) Jab], then selfadjointView<Upper> (:146-176)
+                    glc_posdef_pinv<D, NT>(Sj, 2 * D, pin, psc);
+                    for(int t = tid; t < 4 * D * D; t += NT) {
+                        const int i = t % (2 * D), j = t / (2 * D);
+                        if(i <= j) {
+                            double v;
+                            if(i >= D) { // lower-right block: Jba * pinv * Jab
+                                v = 0;
+                                for(int p = 0; p < D; p++) {
+                                    double u = 0;
+                                    for(int q = 0; q < D; q++) u += Sj[i + q * 2 * D] * pin[q + p * D];
+                                    v += u * Sj[p + j * 2 * D];
+                                }
+                            } else {
+                                v = Sj[i + j * 2 * D];
+                            }
+                            tgt[i + j * 2 * D] = v;
+                            tgt[j + i * 2 * D] = v;
+                        }
+                    }
+                    if(tid == 0) { kv[0] = a; kv[1] = bb; }
+                    gsync<NT>();
+                    const int rank = glc_get_edge_small<D, NT>(tgt, 2, kv, kept_pose, esc, gout + SPG_OUT_HEADER_WORDS + emitted * slotw, cslot, nvcap);
+                    if(rank < 0) status = SPG_BLANKET_EIG_NOCONV;
+                    else if(rank > 0) emitted++;
+                }
+            }
+            n_out = emitted;
         }
 
         gsync<NT>();

@@ -44,6 +44,9 @@ def compare_graphs(g, o, tol=1e-9):
     ("manhattan", R.ALG_NFR, R.TOPO_TREE, 2),
     ("intel", R.ALG_NFR, R.TOPO_TREE, 3),
     ("sphere", R.ALG_NFR, R.TOPO_TREE, 4),
+    ("intel", R.ALG_GLC, R.TOPO_TREE, 2),       # BASELINE.json configs[0]
+    ("sphere", R.ALG_GLC, R.TOPO_TREE, 2),      # configs[2], GLC half
+    ("manhattan", R.ALG_GLC, R.TOPO_TREE, 3),
 ])
 def test_global_decimation_matches_sequential_oracle(ctx, oracle, name, alg, topo, sparsity):
     from sparsifyposegraph_b200 import capi
@@ -84,3 +87,17 @@ def test_local_linearisation_star_blankets(ctx, oracle):
     g.marginalize(ctx, which, capi.make_opts(R.TOPO_TREE, R.LIN_LOCAL), R.ALG_NFR)
     assert o.marginalize(which, oracle.make_opts(R.TOPO_TREE, R.LIN_LOCAL), R.ALG_NFR) == 0
     compare_graphs(g, o)
+
+
+def test_glc_dense_isolated_removals(ctx, oracle):
+    """GLC Dense (one n-ary factor per blanket) on removals that are never adjacent, so the blankets
+    stay small; later blankets contain the n-ary GLC factors created earlier (GLC-edge assembly)."""
+    from sparsifyposegraph_b200 import capi
+    g = capi.Graph(datasets.path("intel"))
+    o = oracle.Graph(datasets.path("intel"))
+    which = [i for i in range(5, 900, 3)]
+    st = g.marginalize(ctx, which, capi.make_opts(R.TOPO_DENSE, R.LIN_GLOBAL), R.ALG_GLC)
+    assert o.marginalize(which, oracle.make_opts(R.TOPO_DENSE, R.LIN_GLOBAL), R.ALG_GLC) == 0
+    assert st["n_failed"] == 0
+    worst = compare_graphs(g, o, tol=1e-8)
+    print(f"intel GLC dense: {st['n_blankets']} blankets, {st['n_rounds']} rounds, max blanket {st['max_blanket_vertices']}, worst {worst:.2e}")

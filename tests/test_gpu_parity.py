@@ -94,3 +94,25 @@ def test_mixed_sizes_one_round(ctx, oracle):
         assert [e["v"] for e in g["edges"]] == [e["v"] for e in r["edges"]]
         for eg, er in zip(g["edges"], r["edges"]):
             assert rel(eg["info"], er["info"]) <= REL_FRO
+
+
+@pytest.mark.parametrize("dim,n,topology,B", [
+    (6, 2, R.TOPO_TREE, 16), (6, 3, R.TOPO_TREE, 32), (6, 5, R.TOPO_TREE, 64), (6, 9, R.TOPO_TREE, 16),
+    (3, 4, R.TOPO_TREE, 32), (3, 7, R.TOPO_TREE, 32), (3, 16, R.TOPO_TREE, 8),
+    (6, 3, R.TOPO_DENSE, 16), (6, 5, R.TOPO_DENSE, 32), (6, 8, R.TOPO_DENSE, 8), (3, 6, R.TOPO_DENSE, 32), (3, 12, R.TOPO_DENSE, 8),
+])
+def test_glc_parity(ctx, oracle, dim, n, topology, B):
+    """R6: GLC tree / dense factors. W is compared through W^T W (eigenvector signs / order are free)."""
+    blk = synth.make_blankets(n, B, dim=dim, variant="ring", seed=3000 + 10 * n + dim)
+    out_off, (ro, _, rt, rw), (go, gt, gw) = run_both(ctx, oracle, blk, R.ALG_GLC, topology)
+    worst = 0.0
+    for b in range(B):
+        r = R.parse_out(ro, out_off, b, dim, R.ALG_GLC, topology, n - 1)
+        g = R.parse_out(go, out_off, b, dim, R.ALG_GLC, topology, n - 1)
+        assert g["status"] == r["status"] == 0, (b, g["status"], r["status"])
+        assert g["n_edges"] == r["n_edges"], (b, g["n_edges"], r["n_edges"])
+        for eg, er in zip(g["edges"], r["edges"]):
+            assert eg["v"] == er["v"] and eg["rank"] == er["rank"]
+            assert np.allclose(eg["meas"], er["meas"], atol=1e-12)
+            worst = max(worst, rel(eg["W"].T @ eg["W"], er["W"].T @ er["W"]))
+    assert worst <= REL_FRO, worst
