@@ -312,7 +312,6 @@ static inline void nfrTopology(const SparsityOptions &opts, int dim, const Mat &
     for(BEdge &e : res.edges) e.info = *it++;
     if(res.status == ST_OK) {
         if(res.nfr.kldInf) res.status = ST_KLD_INF;
-        else if(res.nfr.lineSearchFailed) res.status = ST_LINESEARCH_FAIL;
         else if(res.nfr.notPd && res.nfr.closedForm) res.status = ST_NOT_PD_CLOSED;
     }
 }

@@ -88,7 +88,7 @@ void writeOut(const Blanket &b, const BlanketResult &res, int algorithm, const S
     h[0] = res.status;
     h[1] = (int32_t) res.edges.size();
     h[2] = res.nfr.newtonIters;
-    h[3] = 0;
+    h[3] = (res.nfr.lineSearchFailed ? 1 : 0);
     f64(out)[2] = res.nfr.kld;
     int64_t slot = spgr_out_slot_words(dim, algorithm, opts.topology, nk);
     uint64_t *w = out + SPG_OUT_HEADER_WORDS;

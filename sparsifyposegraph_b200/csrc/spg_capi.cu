@@ -62,7 +62,7 @@ struct spg_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int64_t launches = 0;
     double last_ms = 0;
-    DevBuf d_rec, d_recoff, d_outoff, d_out, d_list, d_tgt, d_tgtoff, d_wts, d_wtsoff;
+    DevBuf d_rec, d_recoff, d_outoff, d_out, d_list, d_tgt, d_tgtoff, d_wts, d_wtsoff, d_ws;
 };
 
 namespace {
@@ -104,6 +104,23 @@ spg_status launch_bucket(spg_ctx *ctx, spg::KernelParams &kp) {
     if(per_sm < 1) per_sm = 1;
     int grid = std::min<int64_t>(kp.n_list, (int64_t) per_sm * ctx->sm_count);
     if(grid < 1) return SPG_OK;
+    // iterative NFR (Subgraph / Dense, >= 3 kept vertices): per-CTA global workspace
+    kp.nfr_ws = nullptr;
+    kp.nfr_ws_stride = 0;
+    const int nkmax = kp.max_nv - 1;
+    if(kp.algorithm == SPG_ALG_NFR && nkmax >= 3 && (kp.topology == SPG_TOPO_SUBGRAPH || kp.topology == SPG_TOPO_DENSE)) {
+        const int ne = spgr_out_edge_count(SPG_ALG_NFR, kp.topology, kp.chord_ratio, nkmax);
+        if(ne > nkmax - 1) {
+            const int64_t stride = (spg::nfr_work_doubles(ne, D, D * (nkmax - 1)) + 1) & ~(int64_t) 1;
+            const int64_t budget = (int64_t) 6 << 27; // 6 GiB of doubles workspace at most
+            if(stride <= budget) {
+                if((int64_t) grid * stride > budget) grid = (int) std::max<int64_t>(1, budget / stride);
+                SPG_CUDA(ctx->d_ws.reserve((size_t) grid * stride * sizeof(double)));
+                kp.nfr_ws = reinterpret_cast<double *>(ctx->d_ws.p);
+                kp.nfr_ws_stride = stride;
+            }
+        }
+    }
     spg::blanket_kernel<D, NT><<<grid, NT, smem, ctx->stream>>>(kp);
     SPG_CUDA(cudaGetLastError());
     ctx->launches++;
@@ -190,7 +207,7 @@ void spg_destroy(spg_ctx *ctx) {
     if(!ctx) return;
     cudaSetDevice(ctx->device);
     for(DevBuf *b : {&ctx->d_rec, &ctx->d_recoff, &ctx->d_outoff, &ctx->d_out, &ctx->d_list, &ctx->d_tgt,
-                     &ctx->d_tgtoff, &ctx->d_wts, &ctx->d_wtsoff})
+                     &ctx->d_tgtoff, &ctx->d_wts, &ctx->d_wtsoff, &ctx->d_ws})
         b->release();
     if(ctx->ev0) cudaEventDestroy(ctx->ev0);
     if(ctx->ev1) cudaEventDestroy(ctx->ev1);

@@ -35,6 +35,8 @@ struct KernelParams {
     int32_t off_pose, off_buf0, off_buf1, off_buf2, off_small, total_doubles;
     int32_t buf0_doubles, buf1_doubles, buf2_doubles;
     int32_t off_glc, glc_doubles; // GLC scratch (only for algorithm == SPG_ALG_GLC launches)
+    double *nfr_ws;               // per-CTA workspace of the iterative NFR fit (global memory)
+    int64_t nfr_ws_stride;        // doubles per CTA
 };
 
 constexpr int ASM_CHUNK = 8; // edges linearised per pre-pass
@@ -237,6 +239,10 @@ __device__ __forceinline__ bool spd_inverse_small(const double *A, double *Xout)
 }
 
 
+} // namespace spg
+#include "spg_nfr.cuh"
+namespace spg {
+
 // pair index (a | b << 16) helpers
 __device__ __forceinline__ int pk(int a, int b) { return a | (b << 16); }
 __device__ __forceinline__ int pk_a(int v) { return v & 0xffff; }
@@ -325,6 +331,8 @@ __global__ void __launch_bounds__(NT) blanket_kernel(const KernelParams P) {
         const int ldk = odd_ld(k > 0 ? k : 1);
 
         int status = SPG_BLANKET_OK;
+        int newton_iters = 0, out_flags = 0;
+        double out_kld = 0;
         if(rdim != D || nv > P.max_nv || ne > P.max_e || rec_words > P.max_rec_words || nrem < 1 || nk < 0)
             status = SPG_BLANKET_TOO_LARGE;
 
@@ -685,8 +693,29 @@ __global__ void __launch_bounds__(NT) blanket_kernel(const KernelParams P) {
                 }
                 gsync<NT>();
             }
-            if(status == SPG_BLANKET_OK && !closed) status = SPG_BLANKET_UNSUPPORTED; // Newton/barrier loop: separate kernel
-            if(status == SPG_BLANKET_OK) {
+            if(status == SPG_BLANKET_OK && !closed) {
+                // ---- R9: interior-point / Newton loop (Subgraph, Dense with >= 3 kept vertices) --------
+                gsync<NT>(); // Jn, S, order complete
+                if(P.nfr_ws == nullptr || nfr_work_doubles(n_out, D, r) > P.nfr_ws_stride) {
+                    status = SPG_BLANKET_TOO_LARGE;
+                } else {
+                    double *ws = P.nfr_ws + (size_t) blockIdx.x * P.nfr_ws_stride;
+                    int fl = 0;
+                    double kld = 0;
+                    nfr_iterative<D, NT>(ws, n_out, k, r, V, ldk, s_order + ooff, s_S, Jn, s_tree, s_red, s_misc + 2, newton_iters, fl, kld);
+                    out_flags = fl;
+                    out_kld = kld;
+                    if(fl & 2) status = SPG_BLANKET_KLD_INF;
+                    const NfrWork w = nfr_carve(ws, n_out, D, r);
+                    for(int t = tid; t < n_out * D * D; t += NT) { // decondense: selfadjointView<Lower> (:88-99)
+                        const int e = t / (D * D), qq = t % (D * D), i = qq % D, j = qq / D;
+                        const double *xe = w.x + (size_t) e * D * D;
+                        double *sx = reinterpret_cast<double *>(gout + SPG_OUT_HEADER_WORDS + (size_t) e * slot + 1 + PW);
+                        sx[qq] = (i >= j) ? xe[i + j * D] : xe[j + i * D];
+                    }
+                    gsync<NT>();
+                }
+            } else if(status == SPG_BLANKET_OK) {
                 // Sigma blocks: Sg_e = U[ab,:] S U[ab,:]^T, lower triangle mirrored up (:239-240)
                 for(int t = tid; t < n_out * SW; t += NT) {
                     const int e = t / SW, q = t % SW, i = q % (2 * D), j = q / (2 * D);
@@ -810,8 +839,9 @@ __global__ void __launch_bounds__(NT) blanket_kernel(const KernelParams P) {
             int32_t *oh = reinterpret_cast<int32_t *>(gout);
             oh[0] = status;
             oh[1] = (status == SPG_BLANKET_OK) ? n_out : 0;
-            oh[2] = 0;
-            oh[3] = 0;
+            oh[2] = newton_iters;
+            oh[3] = out_flags;
+            reinterpret_cast<double *>(gout)[2] = out_kld;
         }
     }
 }

@@ -116,3 +116,46 @@ def test_glc_parity(ctx, oracle, dim, n, topology, B):
             assert np.allclose(eg["meas"], er["meas"], atol=1e-12)
             worst = max(worst, rel(eg["W"].T @ eg["W"], er["W"].T @ er["W"]))
     assert worst <= REL_FRO, worst
+
+
+@pytest.mark.parametrize("dim,n,topology,B", [
+    (3, 4, R.TOPO_DENSE, 16), (3, 5, R.TOPO_DENSE, 16), (3, 6, R.TOPO_SUBGRAPH, 16), (3, 7, R.TOPO_SUBGRAPH, 8),
+    (6, 4, R.TOPO_DENSE, 8), (6, 5, R.TOPO_SUBGRAPH, 8), (6, 6, R.TOPO_SUBGRAPH, 4),
+])
+def test_nfr_iterative_parity(ctx, oracle, dim, n, topology, B):
+    """R9: Subgraph / Dense topologies run the interior-point Newton loop (optimizer.cpp:38-79).
+    KLD within 1e-6 relative (BASELINE.json); X within 1e-9 relative Frobenius where the iterate
+    sequences coincide — X is ill-conditioned at the final barrier weight, so the
+    X residual is additionally reported through J^T X J."""
+    blk = synth.make_blankets(n, B, dim=dim, variant="ring", seed=5000 + 10 * n + dim)
+    out_off, (ro, _, rt, rw), (go, gt, gw) = run_both(ctx, oracle, blk, R.ALG_NFR, topology)
+    k = dim * (n - 1)
+    worst_x = worst_kld = worst_jxj = 0.0
+    iters_o = iters_g = 0
+    for b in range(B):
+        r = R.parse_out(ro, out_off, b, dim, R.ALG_NFR, topology, n - 1)
+        g = R.parse_out(go, out_off, b, dim, R.ALG_NFR, topology, n - 1)
+        assert g["status"] == r["status"] == 0, (b, g["status"], r["status"])
+        assert [e["v"] for e in g["edges"]] == [e["v"] for e in r["edges"]]
+        assert r["newton_iters"] > 0 and g["newton_iters"] > 0
+        iters_o += r["newton_iters"]
+        iters_g += g["newton_iters"]
+        worst_kld = max(worst_kld, abs(g["kld"] - r["kld"]) / max(abs(r["kld"]), 1e-3))
+        kept = blk["poses"][b][1:]
+        JXJ_g = np.zeros((k, k))
+        JXJ_r = np.zeros((k, k))
+        for eg, er in zip(g["edges"], r["edges"]):
+            worst_x = max(worst_x, rel(eg["info"], er["info"]))
+            a, bb = eg["v"]
+            Ji, Jj = oracle.edge_jacobians(dim, er["meas"], kept[a], kept[bb])
+            J = np.zeros((dim, k))
+            J[:, dim * a:dim * a + dim] = Ji
+            J[:, dim * bb:dim * bb + dim] = Jj
+            JXJ_g += J.T @ eg["info"] @ J
+            JXJ_r += J.T @ er["info"] @ J
+        worst_jxj = max(worst_jxj, rel(JXJ_g, JXJ_r))
+    print(f"dim {dim} n {n} topo {topology}: newton iters oracle {iters_o} gpu {iters_g}; worst rel X {worst_x:.2e}, "
+          f"J^T X J {worst_jxj:.2e}, KLD {worst_kld:.2e}")
+    assert worst_kld <= 1e-6
+    assert worst_jxj <= 1e-6
+    assert worst_x <= 1e-5
