@@ -200,6 +200,8 @@ void *spg_stream(spg_ctx *ctx); /* cudaStream_t of the context */
  * Returns the best of `repeats` in TFLOP/s (2 flops per DFMA).
  */
 spg_status spg_fp64_peak_probe(spg_ctx *ctx, int32_t repeats, double *tflops);
+/* developer aid: per-stage clock64() accumulators of the fused kernel (16 values), see tools/stage_profile.py */
+spg_status spg_stage_profile(spg_ctx *ctx, int32_t enable, uint64_t *cycles);
 
 /* ------------------------------------------------------------------------------------------ */
 /* Graph level: g2o-free container with the reference's removal semantics.                    */

@@ -10,42 +10,12 @@
 #include <string>
 #include <vector>
 
-#include "spg_kernels.cuh"
+#include "spg_ctx.h"
+#include "spg_plan.h"
 
 namespace {
 
 thread_local std::string g_err;
-
-void set_err(const std::string &s) { g_err = s; }
-
-#define SPG_CUDA(call)                                                                            \
-    do {                                                                                          \
-        cudaError_t e_ = (call);                                                                  \
-        if(e_ != cudaSuccess) {                                                                   \
-            set_err(std::string(#call) + ": " + cudaGetErrorString(e_));                          \
-            return SPG_ERR_CUDA;                                                                  \
-        }                                                                                         \
-    } while(0)
-
-struct DevBuf {
-    void *p = nullptr;
-    size_t cap = 0;
-    cudaError_t reserve(size_t bytes) {
-        if(bytes <= cap) return cudaSuccess;
-        if(p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-        size_t want = bytes + bytes / 4 + 256;
-        cudaError_t e = cudaMalloc(&p, want);
-        if(e == cudaSuccess) cap = want;
-        return e;
-    }
-    void release() {
-        if(p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-    }
-};
 
 struct Bucket {
     std::vector<int32_t> list;
@@ -54,16 +24,8 @@ struct Bucket {
 
 } // namespace
 
-struct spg_ctx {
-    int device = 0;
-    int sm_count = 148;
-    size_t smem_optin = 0;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    int64_t launches = 0;
-    double last_ms = 0;
-    DevBuf d_rec, d_recoff, d_outoff, d_out, d_list, d_tgt, d_tgtoff, d_wts, d_wtsoff, d_ws;
-};
+void spg_set_err(const std::string &s) { g_err = s; }
+#define set_err spg_set_err
 
 namespace {
 
@@ -82,59 +44,22 @@ __global__ void __launch_bounds__(256) dfma_probe_kernel(double *sink, int iters
     if(r == 12345.678) sink[0] = r; // never true: keeps the chains alive
 }
 
-template <int D, int NT>
-spg_status launch_bucket(spg_ctx *ctx, spg::KernelParams &kp) {
-    static std::mutex mu;
-    static size_t configured = 0;
-    const size_t smem = (size_t) kp.total_doubles * sizeof(double);
-    if(smem > ctx->smem_optin) {
-        set_err("bucket needs more shared memory than the device offers");
-        return SPG_ERR_INVALID;
-    }
-    {
-        std::lock_guard<std::mutex> lk(mu);
-        if(smem > configured) {
-            SPG_CUDA(cudaFuncSetAttribute(spg::blanket_kernel<D, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int) ctx->smem_optin));
-            configured = ctx->smem_optin;
-        }
-    }
-    int per_sm = 0;
-    SPG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, spg::blanket_kernel<D, NT>, NT, smem));
-    if(per_sm < 1) per_sm = 1;
-    int grid = std::min<int64_t>(kp.n_list, (int64_t) per_sm * ctx->sm_count);
-    if(grid < 1) return SPG_OK;
-    // iterative NFR (Subgraph / Dense, >= 3 kept vertices): per-CTA global workspace
-    kp.nfr_ws = nullptr;
-    kp.nfr_ws_stride = 0;
-    const int nkmax = kp.max_nv - 1;
-    if(kp.algorithm == SPG_ALG_NFR && nkmax >= 3 && (kp.topology == SPG_TOPO_SUBGRAPH || kp.topology == SPG_TOPO_DENSE)) {
-        const int ne = spgr_out_edge_count(SPG_ALG_NFR, kp.topology, kp.chord_ratio, nkmax);
-        if(ne > nkmax - 1) {
-            const int64_t stride = (spg::nfr_work_doubles(ne, D, D * (nkmax - 1)) + 1) & ~(int64_t) 1;
-            const int64_t budget = (int64_t) 6 << 27; // 6 GiB of doubles workspace at most
-            if(stride <= budget) {
-                if((int64_t) grid * stride > budget) grid = (int) std::max<int64_t>(1, budget / stride);
-                SPG_CUDA(ctx->d_ws.reserve((size_t) grid * stride * sizeof(double)));
-                kp.nfr_ws = reinterpret_cast<double *>(ctx->d_ws.p);
-                kp.nfr_ws_stride = stride;
-            }
-        }
-    }
-    spg::blanket_kernel<D, NT><<<grid, NT, smem, ctx->stream>>>(kp);
-    SPG_CUDA(cudaGetLastError());
-    ctx->launches++;
-    return SPG_OK;
-}
-
 template <int D>
 spg_status launch_dim(spg_ctx *ctx, spg::KernelParams &kp) {
     spg::plan_smem<D>(kp);
-    const int kmax = D * (kp.max_nv - 1);
-    if(kmax <= 12) return launch_bucket<D, 32>(ctx, kp);
-    if(kmax <= 30) return launch_bucket<D, 64>(ctx, kp);
-    if(kmax <= 54) return launch_bucket<D, 128>(ctx, kp);
-    return launch_bucket<D, 256>(ctx, kp);
+    // CTA width by the size of H (N = D * vertices): the register-tiled sweeps cover
+    // N <= 12 / 32 / 56 / 96 for 32 / 64 / 128 / 256 threads (SweepGrid in spg_device.cuh)
+    const int N = D * kp.max_nv;
+    if(D == 6) {
+        if(N <= 12) return spg_launch_6_32(ctx, kp);
+        if(N <= 32) return spg_launch_6_64(ctx, kp);
+        if(N <= 56) return spg_launch_6_128(ctx, kp);
+        return spg_launch_6_256(ctx, kp);
+    }
+    if(N <= 12) return spg_launch_3_32(ctx, kp);
+    if(N <= 32) return spg_launch_3_64(ctx, kp);
+    if(N <= 56) return spg_launch_3_128(ctx, kp);
+    return spg_launch_3_256(ctx, kp);
 }
 
 // largest vertex count whose bucket still fits in shared memory
@@ -207,7 +132,7 @@ void spg_destroy(spg_ctx *ctx) {
     if(!ctx) return;
     cudaSetDevice(ctx->device);
     for(DevBuf *b : {&ctx->d_rec, &ctx->d_recoff, &ctx->d_outoff, &ctx->d_out, &ctx->d_list, &ctx->d_tgt,
-                     &ctx->d_tgtoff, &ctx->d_wts, &ctx->d_wtsoff, &ctx->d_ws})
+                     &ctx->d_tgtoff, &ctx->d_wts, &ctx->d_wtsoff, &ctx->d_ws, &ctx->d_prof})
         b->release();
     if(ctx->ev0) cudaEventDestroy(ctx->ev0);
     if(ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -255,6 +180,19 @@ spg_status spg_fp64_peak_probe(spg_ctx *ctx, int32_t repeats, double *tflops) {
         if(r > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
     }
     *tflops = best;
+    return SPG_OK;
+}
+
+// Developer aid: per-stage cycle accumulators of blanket_kernel (thread 0 of every CTA, clock64).
+// enable != 0 zeroes and enables them; cycles (16 values) may be NULL. Not part of the product path.
+spg_status spg_stage_profile(spg_ctx *ctx, int32_t enable, uint64_t *cycles) {
+    if(check_device(ctx) != SPG_OK) return SPG_ERR_INVALID;
+    SPG_CUDA(cudaSetDevice(ctx->device));
+    SPG_CUDA(ctx->d_prof.reserve(16 * 8));
+    SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+    if(cycles) SPG_CUDA(cudaMemcpy(cycles, ctx->d_prof.p, 16 * 8, cudaMemcpyDeviceToHost));
+    if(enable) SPG_CUDA(cudaMemset(ctx->d_prof.p, 0, 16 * 8));
+    ctx->profiling = enable != 0;
     return SPG_OK;
 }
 

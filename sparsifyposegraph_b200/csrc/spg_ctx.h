@@ -1,0 +1,64 @@
+// spg_ctx.h — internal: context object and launch plumbing shared by the translation units of
+// libspg_b200.so (one .cu per kernel instantiation so they compile in parallel).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/spg_capi.h"
+
+void spg_set_err(const std::string &s);
+
+#define SPG_CUDA(call)                                                                            \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if(e_ != cudaSuccess) {                                                                   \
+            spg_set_err(std::string(#call) + ": " + cudaGetErrorString(e_));                      \
+            return SPG_ERR_CUDA;                                                                  \
+        }                                                                                         \
+    } while(0)
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if(bytes <= cap) return cudaSuccess;
+        if(p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if(e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if(p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct spg_ctx {
+    int device = 0;
+    int sm_count = 148;
+    size_t smem_optin = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int64_t launches = 0;
+    double last_ms = 0;
+    DevBuf d_rec, d_recoff, d_outoff, d_out, d_list, d_tgt, d_tgtoff, d_wts, d_wtsoff, d_ws, d_prof;
+    bool profiling = false;
+};
+
+namespace spg { struct KernelParams; }
+// one per kernel instantiation (spg_inst_<D>_<NT>.cu)
+spg_status spg_launch_3_32(spg_ctx *, spg::KernelParams &);
+spg_status spg_launch_3_64(spg_ctx *, spg::KernelParams &);
+spg_status spg_launch_3_128(spg_ctx *, spg::KernelParams &);
+spg_status spg_launch_3_256(spg_ctx *, spg::KernelParams &);
+spg_status spg_launch_6_32(spg_ctx *, spg::KernelParams &);
+spg_status spg_launch_6_64(spg_ctx *, spg::KernelParams &);
+spg_status spg_launch_6_128(spg_ctx *, spg::KernelParams &);
+spg_status spg_launch_6_256(spg_ctx *, spg::KernelParams &);

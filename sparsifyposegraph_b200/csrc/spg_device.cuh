@@ -150,7 +150,7 @@ __device__ __forceinline__ void se2_inverse(const double *a, double *r) {
 //        g2o::internal::computeEdgeSE3Gradient evaluates (call site src/se3_compatibility.h:25-29);
 //        closed form derived in DESIGN.md §Jacobians.
 template <int D>
-__device__ __forceinline__ void edge_jacobians(const double *Z, const double *Xi, const double *Xj, double *J) {
+__device__ __noinline__ void edge_jacobians(const double *Z, const double *Xi, const double *Xj, double *J) {
     if constexpr(D == 3) {
         const double dtx = Xj[0] - Xi[0], dty = Xj[1] - Xi[1];
         const double ci = Xi[3], si = Xi[4];
@@ -206,25 +206,251 @@ __device__ __forceinline__ void edge_jacobians(const double *Z, const double *Xi
 // cooperative dense linear algebra on shared-memory matrices (column-major)
 // ------------------------------------------------------------------------------------------
 
+template <int NT>
+__device__ __forceinline__ int gsync_or(int pred) {
+    if constexpr(NT <= 32) return __any_sync(0xffffffffu, pred);
+    else return __syncthreads_or(pred);
+}
+
 // In-place lower Cholesky A = L L^T of the leading n x n block (reads the lower triangle).
-// Returns false (uniformly) if a pivot is not > 0. Right-looking, thread per row.
+// Returns false (uniformly) if a pivot is not > 0.
+// Blocked right-looking, panel width CHOL_NB: (1) the NB x NB diagonal block is factored by one
+// thread, (2) the panel below it by one thread per row (triangular solve against the block),
+// (3) the trailing matrix is updated by ALL threads on a 2-D (row, column) grid with NB-long dot
+// products. 3 barriers per panel instead of 2 per column.
+constexpr int CHOL_NB = 8;
 template <int NT>
 __device__ bool chol_lower(double *A, int n, int ld) {
-    const int tid = threadIdx.x;
-    for(int j = 0; j < n; j++) {
-        const double ajj = A[j + j * ld];
-        if(!(ajj > 0)) return false; // uniform: every thread reads the same value
-        const double inv = 1.0 / sqrt(ajj);
-        for(int i = j + 1 + tid; i < n; i += NT) A[i + j * ld] *= inv;
-        gsync<NT>();
-        for(int i = j + 1 + tid; i < n; i += NT) {
-            const double lij = A[i + j * ld];
-            for(int l = j + 1; l <= i; l++) A[i + l * ld] -= lij * A[l + j * ld];
+    constexpr int TX = (NT >= 128) ? 16 : 8;
+    constexpr int TY = NT / TX;
+    const int tid = threadIdx.x, tx = tid % TX, ty = tid / TX;
+    for(int j0 = 0; j0 < n; j0 += CHOL_NB) {
+        const int jb = min(CHOL_NB, n - j0);
+        int bad = 0;
+        if(tid == 0) {
+            for(int c = 0; c < jb; c++) {
+                const int jc = j0 + c;
+                double d = A[jc + jc * ld];
+                for(int p = 0; p < c; p++) d -= A[jc + (j0 + p) * ld] * A[jc + (j0 + p) * ld];
+                if(!(d > 0)) { bad = 1; break; }
+                const double l = sqrt(d), inv = 1.0 / l;
+                A[jc + jc * ld] = l;
+                for(int r = c + 1; r < jb; r++) {
+                    double s = A[j0 + r + jc * ld];
+                    for(int p = 0; p < c; p++) s -= A[j0 + r + (j0 + p) * ld] * A[jc + (j0 + p) * ld];
+                    A[j0 + r + jc * ld] = s * inv;
+                }
+            }
         }
-        if(tid == 0) A[j + j * ld] = sqrt(ajj);
+        if(gsync_or<NT>(bad)) return false;
+        const int i0 = j0 + jb;
+        for(int i = i0 + tid; i < n; i += NT) { // panel: row i against the diagonal block
+            for(int c = 0; c < jb; c++) {
+                double s = A[i + (j0 + c) * ld];
+                for(int p = 0; p < c; p++) s -= A[i + (j0 + p) * ld] * A[j0 + c + (j0 + p) * ld];
+                A[i + (j0 + c) * ld] = s / A[j0 + c + (j0 + c) * ld];
+            }
+        }
+        gsync<NT>();
+        for(int l = i0 + ty; l < n; l += TY) // trailing update, lower triangle
+            for(int i = l + tx; i < n; i += TX) {
+                double s = 0;
+                for(int p = 0; p < jb; p++) s += A[i + (j0 + p) * ld] * A[l + (j0 + p) * ld];
+                A[i + l * ld] -= s;
+            }
         gsync<NT>();
     }
     return true;
+}
+
+// X = (L L^T)^-1 for the Cholesky factor L (n x n lower, ld). The result (full symmetric matrix)
+// OVERWRITES L; Y (n x ld) is scratch. Two fully parallel phases:
+//   A) Y = L^-1 by blocked forward substitution (GEMM update of a row panel by all threads, then one
+//      thread per column solves against the NB x NB diagonal block),
+//   B) X = Y^T Y on a 2-D grid.
+template <int NT>
+__device__ void chol_inverse_inplace(double *L, int n, int ld, double *Y) {
+    constexpr int TX = (NT >= 128) ? 16 : 8;
+    constexpr int TY = NT / TX;
+    const int tid = threadIdx.x, tx = tid % TX, ty = tid / TX;
+    for(int j0 = 0; j0 < n; j0 += CHOL_NB) {
+        const int jb = min(CHOL_NB, n - j0);
+        // rhs of panel rows: -L[panel, <j0] * Y[<j0, c] for c < j0 ; identity for c in the panel
+        for(int c = ty; c < j0 + jb; c += TY)
+            for(int r = tx; r < jb; r += TX) {
+                double s = (c == j0 + r) ? 1.0 : 0.0;
+                for(int q = c; q < j0; q++) s -= L[j0 + r + q * ld] * Y[q + c * ld];
+                Y[j0 + r + c * ld] = s;
+            }
+        gsync<NT>();
+        for(int c = tid; c < j0 + jb; c += NT) { // triangular solve with the diagonal block
+            double *y = Y + j0 + (size_t) c * ld;
+            for(int r = 0; r < jb; r++) {
+                double s = y[r];
+                for(int q = 0; q < r; q++) s -= L[j0 + r + (j0 + q) * ld] * y[q];
+                y[r] = s / L[j0 + r + (j0 + r) * ld];
+            }
+        }
+        gsync<NT>();
+    }
+    // X = Y^T Y : X[i][j] = sum_{p >= max(i,j)} Y[p][i] Y[p][j]; written over L (L is dead)
+    for(int j = ty; j < n; j += TY)
+        for(int i = j + tx; i < n; i += TX) {
+            double s0 = 0, s1 = 0;
+            int p = i;
+            for(; p + 1 < n; p += 2) {
+                s0 += Y[p + i * ld] * Y[p + j * ld];
+                s1 += Y[p + 1 + i * ld] * Y[p + 1 + j * ld];
+            }
+            if(p < n) s0 += Y[p + i * ld] * Y[p + j * ld];
+            L[i + j * ld] = s0 + s1;
+            L[j + i * ld] = s0 + s1;
+        }
+    gsync<NT>();
+}
+
+// Register-tiled symmetric sweep (Gauss-Jordan on an SPD matrix, no pivoting): sweeps the first
+// `nsweep` pivots of the n x n matrix A (shared memory, ld) in place.
+//   nsweep == n : A <- A^-1
+//   nsweep == m : the trailing block A[m:,m:] <- A_kk - A_km A_mm^-1 A_mk (Schur complement); the
+//                 first m rows/columns hold sweep by-products and must be ignored.
+// Every thread of a T x T grid keeps a TS x TS cyclic tile of A in registers for the whole sweep;
+// per step only the pivot column travels through shared memory (double-buffered in `colbuf`,
+// 2*n doubles) and one barrier is needed. Pivots are the Schur-complement diagonals (= squared
+// Cholesky pivots), so "pivot > 0" is the same positive-definiteness test as LLT's.
+// Requires T*T <= NT and n <= T*TS. Returns false (uniformly) on a non-positive pivot.
+template <int NT, int T, int TS>
+__device__ __noinline__ bool sweep_spd(double *A, int n, int ld, int nsweep, double *colbuf) {
+    static_assert(T * T <= NT, "thread grid larger than the CTA");
+    const int tid = threadIdx.x;
+    const bool active = tid < T * T;
+    const int tx = tid % T, ty = (tid / T) % T;
+    // colbuf: two slots of (n + 2) doubles: the pivot column, then the pivot d and 1/d
+    const int cstride = n + 2;
+    double a[TS][TS];
+#pragma unroll
+    for(int c = 0; c < TS; c++)
+#pragma unroll
+        for(int r = 0; r < TS; r++) {
+            const int i = tx + T * r, l = ty + T * c;
+            a[r][c] = (active && i < n && l < n) ? A[i + l * ld] : 0.0;
+        }
+    // publish column 0
+    if(active && ty == 0) {
+#pragma unroll
+        for(int r = 0; r < TS; r++) {
+            const int i = tx + T * r;
+            if(i < n) colbuf[i] = a[r][0];
+        }
+        if(tx == 0) { colbuf[n] = a[0][0]; colbuf[n + 1] = 1.0 / a[0][0]; }
+    }
+    gsync<NT>();
+    bool ok = true;
+    // Step j = jj + T*c0 sweeps pivot j. The register index of row/column j (c0) is a compile-time
+    // constant inside the unrolled c0 loop, so the tile never leaves the register file. Look-ahead:
+    // the next pivot column (and 1/pivot) is updated first and published before the bulk of the
+    // tile update, so the store -> barrier -> load latency and the division hide behind the FMAs.
+#pragma unroll
+    for(int c0 = 0; c0 < TS; c0++) {
+        const int jjmax = min(T, nsweep - T * c0); // uniform; <= 0: nothing left in this block
+#pragma unroll 1 // keep the step body at TS copies: a fully unrolled sweep (T*TS steps) thrashes the I-cache
+        for(int jj = 0; jj < jjmax; jj++) {
+            const int j = jj + T * c0;
+            const double *col = colbuf + (j & 1) * cstride;
+            double *ncol = colbuf + ((j + 1) & 1) * cstride;
+            const double d = col[n], inv = col[n + 1];
+            if(!(d > 0)) ok = false; // uniform: every thread reads the same pivot
+            if(ok && active) {
+                double ci[TS], cl[TS];
+#pragma unroll
+                for(int r = 0; r < TS; r++) {
+                    const int i = tx + T * r, l = ty + T * r;
+                    ci[r] = (i < n) ? col[i] : 0.0;
+                    cl[r] = (l < n) ? col[l] * inv : 0.0;
+                }
+                const bool rowj = (tx == jj), colj = (ty == jj);
+                const bool wrap = (jj + 1 == T);
+                const bool more = (j + 1 < nsweep);
+                // ---- look-ahead column: register column c0 (same block) or c0 + 1 (wrap) ----
+                if(!wrap) {
+#pragma unroll
+                    for(int r = 0; r < TS; r++) a[r][c0] -= ci[r] * cl[c0];
+                    if(rowj) a[c0][c0] = cl[c0];
+                    if(colj) { // this thread's register column c0 is matrix column j itself
+#pragma unroll
+                        for(int r = 0; r < TS; r++) a[r][c0] = ci[r] * inv;
+                        if(rowj) a[c0][c0] = -inv;
+                    }
+                    if(more && ty == jj + 1) {
+#pragma unroll
+                        for(int r = 0; r < TS; r++) {
+                            const int i = tx + T * r;
+                            if(i < n) ncol[i] = a[r][c0];
+                        }
+                        if(tx == jj + 1) { ncol[n] = a[c0][c0]; ncol[n + 1] = 1.0 / a[c0][c0]; }
+                    }
+                } else if(c0 + 1 < TS) {
+                    constexpr int dummy = 0; (void) dummy;
+#pragma unroll
+                    for(int r = 0; r < TS; r++) a[r][(c0 + 1) % TS] -= ci[r] * cl[(c0 + 1) % TS];
+                    if(rowj) a[c0][(c0 + 1) % TS] = cl[(c0 + 1) % TS];
+                    if(more && ty == 0) {
+#pragma unroll
+                        for(int r = 0; r < TS; r++) {
+                            const int i = tx + T * r;
+                            if(i < n) ncol[i] = a[r][(c0 + 1) % TS];
+                        }
+                        if(tx == 0) { ncol[n] = a[(c0 + 1) % TS][(c0 + 1) % TS]; ncol[n + 1] = 1.0 / a[(c0 + 1) % TS][(c0 + 1) % TS]; }
+                    }
+                }
+                // ---- bulk of the tile ----
+#pragma unroll
+                for(int c = 0; c < TS; c++) {
+                    const bool done_ahead = (!wrap && c == c0) || (wrap && c == c0 + 1);
+                    if(!done_ahead) {
+#pragma unroll
+                        for(int r = 0; r < TS; r++) a[r][c] -= ci[r] * cl[c];
+                        if(rowj) a[c0][c] = cl[c];
+                    }
+                }
+                if(wrap && colj) { // column j lives in register column c0 and was updated in the bulk
+#pragma unroll
+                    for(int r = 0; r < TS; r++) a[r][c0] = ci[r] * inv;
+                    if(rowj) a[c0][c0] = -inv;
+                }
+            }
+            gsync<NT>();
+        }
+    }
+    if(!ok) return false;
+    // full sweep leaves -A^-1; a partial sweep leaves the Schur complement in the trailing block
+    const double sgn = (nsweep >= n) ? -1.0 : 1.0;
+#pragma unroll
+    for(int c = 0; c < TS; c++)
+#pragma unroll
+        for(int r = 0; r < TS; r++) {
+            const int i = tx + T * r, l = ty + T * c;
+            if(active && i < n && l < n) A[i + l * ld] = sgn * a[r][c];
+        }
+    gsync<NT>();
+    return true;
+}
+
+// One tile shape per CTA width: the largest n it covers is T * TS.
+template <int NT> struct SweepGrid;
+template <> struct SweepGrid<32>  { static constexpr int T = 4,  TS = 3; };   // n <= 12
+template <> struct SweepGrid<64>  { static constexpr int T = 8,  TS = 4; };   // n <= 32
+template <> struct SweepGrid<128> { static constexpr int T = 8,  TS = 7; };   // n <= 56
+template <> struct SweepGrid<256> { static constexpr int T = 16, TS = 6; };   // n <= 96
+
+// returns 1 ok, 0 not positive definite, -1 n too large for the register tiles. scratch: 2 * (n + 2) doubles.
+// (A per-vertex blocked variant — rank-6 updates, 2 barriers per vertex — was measured slower on
+// B200: 186k vs 100k cycles for k = 90; the tile plus panel operands spill. See DESIGN.md §3.)
+template <int D, int NT>
+__device__ __forceinline__ int sweep_spd_auto(double *A, int n, int ld, int nsweep, double *scratch) {
+    using G = SweepGrid<NT>;
+    if(n <= G::T * G::TS) return sweep_spd<NT, G::T, G::TS>(A, n, ld, nsweep, scratch) ? 1 : 0;
+    return -1;
 }
 
 // X = (L L^T)^-1 written to X (n x n, ldx) from the Cholesky factor L (lower, ld). Thread per

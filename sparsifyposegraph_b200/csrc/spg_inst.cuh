@@ -1,0 +1,58 @@
+// spg_inst.cuh — launch wrapper of one blanket_kernel<D, NT> instantiation.
+#pragma once
+#include <algorithm>
+#include <mutex>
+
+#include "spg_ctx.h"
+#include "spg_kernels.cuh"
+
+namespace {
+#define set_err spg_set_err
+template <int D, int NT>
+spg_status launch_bucket(spg_ctx *ctx, spg::KernelParams &kp) {
+    static std::mutex mu;
+    static size_t configured = 0;
+    const size_t smem = (size_t) kp.total_doubles * sizeof(double);
+    if(smem > ctx->smem_optin) {
+        set_err("bucket needs more shared memory than the device offers");
+        return SPG_ERR_INVALID;
+    }
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        if(smem > configured) {
+            SPG_CUDA(cudaFuncSetAttribute(spg::blanket_kernel<D, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int) ctx->smem_optin));
+            configured = ctx->smem_optin;
+        }
+    }
+    int per_sm = 0;
+    SPG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, spg::blanket_kernel<D, NT>, NT, smem));
+    if(per_sm < 1) per_sm = 1;
+    int grid = std::min<int64_t>(kp.n_list, (int64_t) per_sm * ctx->sm_count);
+    if(grid < 1) return SPG_OK;
+    kp.prof = ctx->profiling ? reinterpret_cast<unsigned long long *>(ctx->d_prof.p) : nullptr;
+    // iterative NFR (Subgraph / Dense, >= 3 kept vertices): per-CTA global workspace
+    kp.nfr_ws = nullptr;
+    kp.nfr_ws_stride = 0;
+    const int nkmax = kp.max_nv - 1;
+    if(kp.algorithm == SPG_ALG_NFR && nkmax >= 3 && (kp.topology == SPG_TOPO_SUBGRAPH || kp.topology == SPG_TOPO_DENSE)) {
+        const int ne = spgr_out_edge_count(SPG_ALG_NFR, kp.topology, kp.chord_ratio, nkmax);
+        if(ne > nkmax - 1) {
+            const int64_t stride = (spg::nfr_work_doubles(ne, D, D * (nkmax - 1)) + 1) & ~(int64_t) 1;
+            const int64_t budget = (int64_t) 6 << 27; // 6 GiB of doubles workspace at most
+            if(stride <= budget) {
+                if((int64_t) grid * stride > budget) grid = (int) std::max<int64_t>(1, budget / stride);
+                SPG_CUDA(ctx->d_ws.reserve((size_t) grid * stride * sizeof(double)));
+                kp.nfr_ws = reinterpret_cast<double *>(ctx->d_ws.p);
+                kp.nfr_ws_stride = stride;
+            }
+        }
+    }
+    spg::blanket_kernel<D, NT><<<grid, NT, smem, ctx->stream>>>(kp);
+    SPG_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return SPG_OK;
+}
+
+#undef set_err
+} // namespace

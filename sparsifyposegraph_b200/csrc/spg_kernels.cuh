@@ -11,76 +11,10 @@
 #include "../../include/spg_capi.h"
 #include "../../include/spg_record.h"
 #include "spg_device.cuh"
+#include "spg_plan.h"
 #include "spg_glc.cuh"
 
 namespace spg {
-
-struct KernelParams {
-    int32_t algorithm, topology;
-    double chord_ratio;
-    int32_t flags;               // bit 0: force the general (eigen-decomposition) NFR path
-    int32_t pad0;
-    int32_t n_list;              // blankets handled by this launch
-    const int32_t *list;         // their indices (NULL: identity)
-    const int64_t *rec_off;
-    const uint64_t *records;
-    const int64_t *out_off;
-    uint64_t *out;
-    double *dbg_target;
-    const int64_t *dbg_target_off;
-    double *dbg_weights;
-    const int64_t *dbg_weights_off;
-    // shared-memory carve-up of this bucket (all in doubles)
-    int32_t max_nv, max_e, max_rec_words;
-    int32_t off_pose, off_buf0, off_buf1, off_buf2, off_small, total_doubles;
-    int32_t buf0_doubles, buf1_doubles, buf2_doubles;
-    int32_t off_glc, glc_doubles; // GLC scratch (only for algorithm == SPG_ALG_GLC launches)
-    double *nfr_ws;               // per-CTA workspace of the iterative NFR fit (global memory)
-    int64_t nfr_ws_stride;        // doubles per CTA
-};
-
-constexpr int ASM_CHUNK = 8; // edges linearised per pre-pass
-
-// Host-side: shared-memory layout for a bucket with at most max_nv vertices (n_removed >= 1),
-// max_e edges and max_rec_words record words.
-template <int D>
-inline void plan_smem(KernelParams &p) {
-    const int PS = PoseStride<D>::value;
-    const int N = D * p.max_nv;
-    const int kmax = D * (p.max_nv - 1);
-    const int nk = p.max_nv - 1;
-    const int pairs = nk * (nk - 1) / 2;
-    int o = p.max_rec_words;             // record copy
-    p.off_pose = o;  o += p.max_nv * PS;
-    p.off_buf0 = o;
-    p.buf0_doubles = N * odd_ld(N);
-    o += p.buf0_doubles;
-    p.off_buf1 = o;
-    int b1 = kmax * odd_ld(kmax > 0 ? kmax : 1);
-    int asm_scratch = ASM_CHUNK * 2 * (D * 2 * D);
-    p.buf1_doubles = b1 > asm_scratch ? b1 : asm_scratch;
-    o += p.buf1_doubles;
-    p.off_buf2 = o;
-    p.buf2_doubles = (nk >= 2) ? b1 : 0; // pseudo-covariance C, then the gauge-anchored inverse G
-    o += p.buf2_doubles;
-    p.off_small = o;
-    // small: w[kmax] order[kmax](int) cs[kmax+2] red[8] weights[pairs] heapw[pairs] heapab[pairs] (int2)
-    //        tree[2*max(pairs,1)] (int) uf[nk] (int) Lfac[nk*D*D] logd[nk] misc[16]
-    o += kmax + (kmax + 1) / 2 + (kmax + kmax / 2 + 4) + 8 + pairs + pairs + pairs + (pairs > 0 ? pairs : 1) + (nk + 1) / 2 + 1 +
-         nk * D * D + nk + 16;
-    p.off_glc = o;
-    p.glc_doubles = 0;
-    if(p.algorithm == SPG_ALG_GLC) {
-        // tree: joint (4D^2) + target (4D^2) + pinv out (D^2) + pinv scratch + getEdge scratch (c = 2D);
-        // dense: meas k + blocks 2 nk D^2 + Jacobi scratch + order
-        const int c = 2 * D;
-        const int tree = 4 * D * D + 4 * D * D + D * D + (2 * D * (D | 1) + 2 * D + 16) + (8 * c * c + 8 * c + 64);
-        const int dense = kmax + 2 * nk * D * D + (kmax + kmax / 2 + 8) + 8 + kmax / 2 + 2;
-        p.glc_doubles = (tree > dense ? tree : dense) + 8;
-        o += p.glc_doubles;
-    }
-    p.total_doubles = o;
-}
 
 // std::priority_queue<WeightedEdge> emulation (libstdc++ __push_heap / __adjust_heap), compared on
 // weight only (pseudo_chow_liu.h:49-53) so that equal weights pop in the reference's order.
@@ -286,8 +220,17 @@ __device__ bool assemble_glc_edge(const uint64_t *ew, const double *s_pose, doub
     return true;
 }
 
+#define SPG_T(i)                                                                                     \
+    do {                                                                                             \
+        if(P.prof && tid == 0) {                                                                     \
+            const long long t_now = clock64();                                                       \
+            atomicAdd(&P.prof[i], (unsigned long long) (t_now - t_last));                            \
+            t_last = t_now;                                                                          \
+        }                                                                                            \
+    } while(0)
+
 template <int D, int NT>
-__global__ void __launch_bounds__(NT) blanket_kernel(const KernelParams P) {
+__global__ void __launch_bounds__(NT, (NT >= 256) ? 1 : (NT == 128 ? 3 : 512 / NT)) blanket_kernel(const KernelParams P) {
     extern __shared__ double smem[];
     constexpr int PS = PoseStride<D>::value;
     constexpr int PW = (D == 6) ? 7 : 3; // pose words in records
@@ -345,6 +288,7 @@ __global__ void __launch_bounds__(NT) blanket_kernel(const KernelParams P) {
             continue;
         }
 
+        long long t_last = clock64();
         // ---- S0: stage the record in shared memory, expand poses ---------------------------------
         for(int t = tid; t < rec_words; t += NT) s_rec[t] = grec[t];
         if(tid == 0) { s_misc[0] = SPG_BLANKET_OK; s_misc[1] = 0; }
@@ -358,8 +302,10 @@ __global__ void __launch_bounds__(NT) blanket_kernel(const KernelParams P) {
         for(int t = tid; t < N * ldH; t += NT) buf0[t] = 0.0;
         gsync<NT>();
 
+        SPG_T(0);
         // ---- S1: assembly H = sum_e J^T Omega J (edge order = record order) -------------------------
         double *H = buf0;
+        const int asm_chunk = max(1, min(32, P.buf1_doubles / (2 * JW))); // edges linearised per pass
         int e0 = 0;
         while(e0 < ne) {
             const int kind0 = reinterpret_cast<const int32_t *>(s_rec + r_etab[e0])[0];
@@ -374,7 +320,7 @@ __global__ void __launch_bounds__(NT) blanket_kernel(const KernelParams P) {
                 continue;
             }
             int ce = 1;
-            while(ce < ASM_CHUNK && e0 + ce < ne &&
+            while(ce < asm_chunk && e0 + ce < ne &&
                   reinterpret_cast<const int32_t *>(s_rec + r_etab[e0 + ce])[0] == SPG_EDGE_POSE) ce++;
             for(int e = tid; e < ce; e += NT) { // linearise: one thread per edge
                 const uint64_t *ew = s_rec + r_etab[e0 + e];
@@ -425,34 +371,48 @@ __global__ void __launch_bounds__(NT) blanket_kernel(const KernelParams P) {
         }
         if(s_misc[0] != SPG_BLANKET_OK) status = s_misc[0];
 
+        SPG_T(1);
         // ---- S2: Schur complement onto the kept variables ----------------------------------------
-        if(status == SPG_BLANKET_OK) {
-            if(!chol_lower<NT>(H, m, ldH)) status = SPG_BLANKET_NOT_PD_MARGINAL;
-        }
         double *T = H + m + (size_t) m * ldH; // Lambda_t in place, leading dimension ldH
+        if(status == SPG_BLANKET_OK) {
+            // register-tiled partial sweep of the m removed pivots: H_kk <- H_kk - H_km H_mm^-1 H_mk
+            const int sw = sweep_spd_auto<D, NT>(H, N, ldH, m, buf1);
+            if(sw == 0) status = SPG_BLANKET_NOT_PD_MARGINAL;
+            if(sw > 0) {
+                // upper triangle mirrored to the lower (vertex_remover.cpp:447-449)
+                for(int t = tid; t < k * k; t += NT) {
+                    const int i = t % k, j = t / k;
+                    if(i > j) T[i + (size_t) j * ldH] = T[j + (size_t) i * ldH];
+                }
+                gsync<NT>();
+            } else if(sw < 0) { // blanket larger than the register tiles: LLT route
+                if(!chol_lower<NT>(H, m, ldH)) status = SPG_BLANKET_NOT_PD_MARGINAL;
+                if(status == SPG_BLANKET_OK && k > 0) {
+                    for(int c = m + tid; c < N; c += NT) { // Y = L^-1 H_mk : thread per kept column
+                        double *y = H + (size_t) c * ldH;
+                        for(int i = 0; i < m; i++) {
+                            double s = y[i];
+                            for(int p = 0; p < i; p++) s -= H[i + p * ldH] * y[p];
+                            y[i] = s / H[i + i * ldH];
+                        }
+                    }
+                    gsync<NT>();
+                    for(int t = tid; t < k * k; t += NT) {
+                        const int i = t % k, j = t / k;
+                        if(i <= j) {
+                            const double *yi = H + (size_t) (m + i) * ldH, *yj = H + (size_t) (m + j) * ldH;
+                            double s = 0;
+                            for(int p = 0; p < m; p++) s += yi[p] * yj[p];
+                            const double v = T[i + (size_t) j * ldH] - s;
+                            T[i + (size_t) j * ldH] = v;
+                            if(i != j) T[j + (size_t) i * ldH] = v;
+                        }
+                    }
+                    gsync<NT>();
+                }
+            }
+        }
         if(status == SPG_BLANKET_OK && k > 0) {
-            for(int c = m + tid; c < N; c += NT) { // Y = L^-1 H_mk : thread per kept column
-                double *y = H + (size_t) c * ldH;
-                for(int i = 0; i < m; i++) {
-                    double s = y[i];
-                    for(int p = 0; p < i; p++) s -= H[i + p * ldH] * y[p];
-                    y[i] = s / H[i + i * ldH];
-                }
-            }
-            gsync<NT>();
-            // Lambda_t = H_kk - Y^T Y; upper triangle mirrored to the lower (vertex_remover.cpp:447-449)
-            for(int t = tid; t < k * k; t += NT) {
-                const int i = t % k, j = t / k;
-                if(i <= j) {
-                    const double *yi = H + (size_t) (m + i) * ldH, *yj = H + (size_t) (m + j) * ldH;
-                    double s = 0;
-                    for(int p = 0; p < m; p++) s += yi[p] * yj[p];
-                    const double v = T[i + (size_t) j * ldH] - s;
-                    T[i + (size_t) j * ldH] = v;
-                    if(i != j) T[j + (size_t) i * ldH] = v;
-                }
-            }
-            gsync<NT>();
             if(P.dbg_target) {
                 double *g = P.dbg_target + P.dbg_target_off[b];
                 if(P.dbg_target_off[b + 1] - P.dbg_target_off[b] >= (int64_t) k * k)
@@ -460,6 +420,7 @@ __global__ void __launch_bounds__(NT) blanket_kernel(const KernelParams P) {
             }
         }
 
+        SPG_T(2);
         // ---- S3: sparsity pattern (PseudoChowLiu::computeSparsityPattern, pseudo_chow_liu.cpp:33-87) ---
         int n_out = 0;
         const bool glc_tree = (P.algorithm == SPG_ALG_GLC && P.topology == SPG_TOPO_TREE);
@@ -483,16 +444,23 @@ __global__ void __launch_bounds__(NT) blanket_kernel(const KernelParams P) {
             } else {
                 n_out = (P.topology == SPG_TOPO_TREE) ? nk - 1 : mch;
                 // C = (Lambda_t + 1 I)^-1  (fillEdges, pseudo_chow_liu.cpp:185-190)
-                double *Lc = buf1, *C = buf2;
+                double *Lc = buf1, *C = buf1; // the inverse overwrites the factor; buf2 is its scratch
                 for(int t = tid; t < k * k; t += NT) {
                     const int i = t % k, j = t / k;
                     Lc[i + j * ldk] = T[i + (size_t) j * ldH] + (i == j ? 1.0 : 0.0);
                 }
                 gsync<NT>();
-                if(!chol_lower<NT>(Lc, k, ldk)) status = SPG_BLANKET_NOT_PD_CHOWLIU;
+                {
+                    const int sw = sweep_spd_auto<D, NT>(Lc, k, ldk, k, buf2);
+                    if(sw == 0) status = SPG_BLANKET_NOT_PD_CHOWLIU;
+                    if(sw < 0) {
+                        if(!chol_lower<NT>(Lc, k, ldk)) status = SPG_BLANKET_NOT_PD_CHOWLIU;
+                        else chol_inverse_inplace<NT>(Lc, k, ldk, buf2);
+                    }
+                }
                 if(status == SPG_BLANKET_OK) {
-                    chol_inverse<NT>(Lc, k, ldk, C, ldk);
-                    gsync<NT>();
+                    SPG_T(3);
+                    SPG_T(4);
                     // per-vertex Cholesky of the diagonal blocks + their log-determinants
                     for(int v = tid; v < nk; v += NT) {
                         bool ok;
@@ -500,6 +468,7 @@ __global__ void __launch_bounds__(NT) blanket_kernel(const KernelParams P) {
                         if(!ok) s_misc[0] = SPG_BLANKET_NOT_PD_CHOWLIU;
                     }
                     gsync<NT>();
+                    SPG_T(5);
                     // weight(i,j) = logdet C_ii + logdet C_jj - logdet C_{ij,ij}   (:169-183)
                     //             = logdet C_jj - logdet (C_jj - C_ji C_ii^-1 C_ij)
                     for(int t = tid; t < all; t += NT) {
@@ -515,37 +484,79 @@ __global__ void __launch_bounds__(NT) blanket_kernel(const KernelParams P) {
                         const int cap = (int) (P.dbg_weights_off[b + 1] - P.dbg_weights_off[b]);
                         for(int t = tid; t < cap; t += NT) g[t] = t < all ? s_wt[t] : 0.0;
                     }
-                    // doKruskal (:253-289): max-heap pops, accepted edges first then rejected
+                    SPG_T(6);
+                    // doKruskal (:253-289): pops of a max-heap keyed on the weight only, accepted edges first
+                    // then rejected. Without exactly equal (or NaN) weights the pop order is simply the
+                    // descending order, which all threads establish by ranking; otherwise one thread
+                    // replays libstdc++'s heap so ties break as in the reference.
+                    int *s_sorted = s_tree + all; // second half of the tree scratch
+                    if(tid == 0) s_misc[3] = 0;
+                    gsync<NT>();
+                    for(int t = tid; t < all; t += NT) {
+                        const double wt = s_wt[t];
+                        int rank = 0, tie = (wt != wt);
+                        for(int u = 0; u < all; u++) {
+                            const double wu = s_wt[u];
+                            rank += (wu > wt);
+                            tie |= (u != t) && (wu == wt);
+                        }
+                        if(tie) s_misc[3] = 1;
+                        else {
+                            int i = 0, rem = t;
+                            while(rem >= nk - 1 - i) { rem -= nk - 1 - i; i++; }
+                            s_sorted[rank] = pk(i, i + 1 + rem);
+                        }
+                    }
+                    gsync<NT>();
                     if(tid == 0) {
-                        HeapView hp{s_heapw, s_heapab, 0};
-                        int t = 0;
-                        for(int i = 0; i < nk - 1; i++)
-                            for(int j = i + 1; j < nk; j++, t++) hp.push(s_wt[t], pk(i, j));
                         for(int v = 0; v < nk; v++) s_uf[v] = v;
                         int nacc = 0, nrej = 0;
-                        // rejected edges are staged at the tail of s_tree in reverse, then appended
-                        while(hp.len > 0) {
-                            double w; int ab;
-                            hp.pop(w, ab);
-                            int ra = pk_a(ab), rb = pk_b(ab);
-                            while(s_uf[ra] != ra) ra = s_uf[ra];
-                            while(s_uf[rb] != rb) rb = s_uf[rb];
-                            if(ra != rb) {
-                                s_uf[rb] = ra;
-                                s_tree[nacc++] = ab;
-                            } else {
-                                // heap storage behind the live heap is free: hp.len slots are in use
-                                s_heapab[all - 1 - nrej] = ab;
-                                nrej++;
+                        if(!s_misc[3]) {
+                            const bool tree_only = (n_out == nk - 1);
+                            for(int q = 0; q < all; q++) {
+                                const int ab = s_sorted[q];
+                                int ra = pk_a(ab), rb = pk_b(ab);
+                                while(s_uf[ra] != ra) ra = s_uf[ra];
+                                while(s_uf[rb] != rb) rb = s_uf[rb];
+                                if(ra != rb) {
+                                    s_uf[rb] = ra;
+                                    s_tree[nacc++] = ab;
+                                    if(tree_only && nacc == nk - 1) break; // only the spanning tree is used
+                                } else {
+                                    s_heapab[nrej++] = ab;
+                                }
                             }
+                            if(!tree_only)
+                                for(int q = 0; q < nrej && nacc + q < n_out; q++) s_tree[nacc + q] = s_heapab[q];
+                        } else {
+                            HeapView hp{s_heapw, s_heapab, 0};
+                            int t = 0;
+                            for(int i = 0; i < nk - 1; i++)
+                                for(int j = i + 1; j < nk; j++, t++) hp.push(s_wt[t], pk(i, j));
+                            // rejected edges are staged at the tail of the heap storage, then appended
+                            while(hp.len > 0) {
+                                double w; int ab;
+                                hp.pop(w, ab);
+                                int ra = pk_a(ab), rb = pk_b(ab);
+                                while(s_uf[ra] != ra) ra = s_uf[ra];
+                                while(s_uf[rb] != rb) rb = s_uf[rb];
+                                if(ra != rb) {
+                                    s_uf[rb] = ra;
+                                    s_tree[nacc++] = ab;
+                                } else {
+                                    s_heapab[all - 1 - nrej] = ab; // behind the live heap: free slots
+                                    nrej++;
+                                }
+                            }
+                            for(int q = 0; q < nrej && nacc + q < all; q++) s_tree[nacc + q] = s_heapab[all - 1 - q];
                         }
-                        for(int q = 0; q < nrej; q++) s_tree[nacc + q] = s_heapab[all - 1 - q];
                     }
                     gsync<NT>();
                 }
             }
         }
 
+        SPG_T(7);
         // ---- S4: NFR information fit (optimizeInformation, optimizer.cpp:16-81) ------------------------
         if(status == SPG_BLANKET_OK && P.algorithm == SPG_ALG_NFR && n_out > 0) {
             gsync<NT>(); // s_tree visible
@@ -565,7 +576,7 @@ __global__ void __launch_bounds__(NT) blanket_kernel(const KernelParams P) {
             // (~ k eps ||Lambda||) stay below the cutoff, i.e. smalleigs >= d. Otherwise: general path.
             bool fast = false;
             const int kk = k - D, ldg = odd_ld(kk > 0 ? kk : 1);
-            double *G = buf2;
+            double *G = buf1; // the inverse overwrites the Cholesky factor; buf2 is its scratch
             if(closed && !(P.flags & 1)) {
                 for(int t = tid; t < kk * kk; t += NT) {
                     const int i = t % kk, j = t / kk;
@@ -577,9 +588,13 @@ __global__ void __launch_bounds__(NT) blanket_kernel(const KernelParams P) {
                     s_red[1] = md;
                 }
                 gsync<NT>();
-                if(chol_lower<NT>(buf1, kk, ldg)) {
-                    chol_inverse<NT>(buf1, kk, ldg, G, ldg);
-                    gsync<NT>();
+                int swg = sweep_spd_auto<D, NT>(buf1, kk, ldg, kk, buf2);
+                if(swg < 0) {
+                    swg = chol_lower<NT>(buf1, kk, ldg) ? 1 : 0;
+                    if(swg) chol_inverse_inplace<NT>(buf1, kk, ldg, buf2);
+                }
+                if(swg > 0) {
+                    SPG_T(8);
                     if(tid == 0) {
                         double tr = 0;
                         for(int i = 0; i < kk; i++) tr += G[i + i * ldg];
@@ -611,6 +626,7 @@ __global__ void __launch_bounds__(NT) blanket_kernel(const KernelParams P) {
                 gsync<NT>();
                 smalleigs = s_misc[1];
             }
+            SPG_T(9);
             // new-edge Jacobians at the linearisation point with measurement == state (:466-498),
             // measurements written straight to the output record
             double *Jn = buf0;                       // n_out * JW   (buf0 is free: eigenvalues are saved)
@@ -716,6 +732,7 @@ __global__ void __launch_bounds__(NT) blanket_kernel(const KernelParams P) {
                     gsync<NT>();
                 }
             } else if(status == SPG_BLANKET_OK) {
+                SPG_T(10);
                 // Sigma blocks: Sg_e = U[ab,:] S U[ab,:]^T, lower triangle mirrored up (:239-240)
                 for(int t = tid; t < n_out * SW; t += NT) {
                     const int e = t / SW, q = t % SW, i = q % (2 * D), j = q / (2 * D);
@@ -760,6 +777,7 @@ __global__ void __launch_bounds__(NT) blanket_kernel(const KernelParams P) {
                     }
                 }
                 gsync<NT>();
+                SPG_T(11);
                 // X_e = block_e^-1 through LLT (:273-274), straight to the output record
                 for(int e = tid; e < n_out; e += NT) {
                     double X[D * D];
@@ -774,6 +792,7 @@ __global__ void __launch_bounds__(NT) blanket_kernel(const KernelParams P) {
             }
         }
 
+        SPG_T(12);
         // ---- S5: GLC substitute factors (TopologyProviderGLC::topology, topology_provider_glc.cpp:100-185) ----
         if(status == SPG_BLANKET_OK && P.algorithm == SPG_ALG_GLC && nk >= 1) {
             gsync<NT>();
@@ -834,6 +853,7 @@ __global__ void __launch_bounds__(NT) blanket_kernel(const KernelParams P) {
             n_out = emitted;
         }
 
+        SPG_T(13);
         gsync<NT>();
         if(tid == 0) {
             int32_t *oh = reinterpret_cast<int32_t *>(gout);

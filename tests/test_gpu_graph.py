@@ -47,6 +47,7 @@ def compare_graphs(g, o, tol=1e-9):
     ("intel", R.ALG_GLC, R.TOPO_TREE, 2),       # BASELINE.json configs[0]
     ("sphere", R.ALG_GLC, R.TOPO_TREE, 2),      # configs[2], GLC half
     ("manhattan", R.ALG_GLC, R.TOPO_TREE, 3),
+    ("manhattan", R.ALG_NFR, R.TOPO_SUBGRAPH, 2),   # configs[1]: Chow-Liu topology + KLD Newton fit
 ])
 def test_global_decimation_matches_sequential_oracle(ctx, oracle, name, alg, topo, sparsity):
     from sparsifyposegraph_b200 import capi
