@@ -237,6 +237,20 @@ int32_t spg_decimate_cluster(int32_t last, int32_t endvert, int32_t sparsity, in
 spg_status spg_graph_marginalize(spg_graph *g, spg_ctx *ctx, const int32_t *which, int32_t n_which,
                                  const spg_sparsity_options *opts, int32_t algorithm);
 
+/*
+ * The same removal, one wavefront round at a time, for callers that run the blankets of a round
+ * themselves (sharded over ranks / GPUs):
+ *   spg_graph_rounds_begin(g, which, n, opts, alg);
+ *   for (;;) { spg_graph_round_next(g, &round); if (round.n_blankets == 0) break;
+ *              ... fill `out` (round.out_off[n_blankets] words) with spg_remove_round on any split ...
+ *              spg_graph_round_apply(g, out); }
+ * The pointers inside `round` stay valid until the next spg_graph_round_* call.
+ */
+spg_status spg_graph_rounds_begin(spg_graph *g, const int32_t *which, int32_t n_which,
+                                  const spg_sparsity_options *opts, int32_t algorithm);
+spg_status spg_graph_round_next(spg_graph *g, spg_round_in *round);
+spg_status spg_graph_round_apply(spg_graph *g, const uint64_t *out);
+
 typedef struct {
     int32_t n_rounds;
     int32_t n_blankets;

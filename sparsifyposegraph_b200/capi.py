@@ -303,3 +303,45 @@ def decimate_cluster(last, endvert, sparsity, cluster):
     out = np.zeros(max(endvert + 1, 1), dtype=np.int32)
     n = lib().spg_decimate_cluster(last, endvert, sparsity, cluster, _p(out), len(out))
     return out[:n]
+
+
+# ---- round-by-round removal (sharding a round over ranks / GPUs) ------------------------------------
+
+def _round_protos(L):
+    if getattr(L, "_round_protos_done", False):
+        return
+    _graph_protos(L)
+    L.spg_graph_rounds_begin.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(SparsityOptions), C.c_int32]
+    L.spg_graph_round_next.argtypes = [C.c_void_p, C.POINTER(RoundIn)]
+    L.spg_graph_round_apply.argtypes = [C.c_void_p, C.c_void_p]
+    L._round_protos_done = True
+
+
+def rounds_begin(graph, which, opts, algorithm):
+    L = lib()
+    _round_protos(L)
+    w = np.ascontiguousarray(which, dtype=np.int32)
+    _check(L.spg_graph_rounds_begin(graph.h, _p(w), len(w), C.byref(opts), int(algorithm)))
+
+
+def round_next(graph):
+    """Next wavefront round as numpy copies: dict(dim, algorithm, opts, n, records, rec_off, out_off) or None."""
+    L = lib()
+    _round_protos(L)
+    r = RoundIn()
+    _check(L.spg_graph_round_next(graph.h, C.byref(r)))
+    n = r.n_blankets
+    if n == 0:
+        return None
+    rec_off = np.ctypeslib.as_array(C.cast(r.rec_off, C.POINTER(C.c_int64)), shape=(n + 1,)).copy()
+    out_off = np.ctypeslib.as_array(C.cast(r.out_off, C.POINTER(C.c_int64)), shape=(n + 1,)).copy()
+    records = np.ctypeslib.as_array(C.cast(r.records, C.POINTER(C.c_uint64)), shape=(int(rec_off[-1]),)).copy()
+    return {"dim": r.dim, "algorithm": r.algorithm, "opts": r.opts, "n": n, "records": records, "rec_off": rec_off,
+            "out_off": out_off}
+
+
+def round_apply(graph, out):
+    L = lib()
+    _round_protos(L)
+    out = np.ascontiguousarray(out, dtype=np.uint64)
+    _check(L.spg_graph_round_apply(graph.h, _p(out)))

@@ -448,36 +448,85 @@ std::vector<int> VertexRemover::remove(int toRemove, spg_status *status) {
 // processed from the same snapshot, and spliced in list order.
 std::vector<int> VertexRemover::remove(const std::vector<int> &toRemove, spg_status *status) {
     using clk = std::chrono::steady_clock;
-    std::vector<int> added;
     if(status) *status = SPG_OK;
-    stats = spg_marginalize_stats{};
-    const int dim = _graph->dim;
-    std::set<int> toRemoveSet(toRemove.begin(), toRemove.end());
-    std::vector<char> done(toRemove.size(), 0);
-    size_t remaining = toRemove.size();
-
-    struct Region { std::vector<int> removed, region; }; // region: every vertex of the (conservative) blanket
-    while(remaining > 0) {
+    spg_status st = beginRemoval(toRemove);
+    while(st == SPG_OK) {
         auto t0 = clk::now();
+        st = planRound();
+        if(st != SPG_OK || _round.units.empty()) break;
+        auto t1 = clk::now();
+        std::vector<uint64_t> out((size_t) _round.outOff.back(), 0);
+        spg_round_in rin = roundDescriptor();
+        spg_round_out rout{};
+        rout.out = out.data();
+        st = spg_remove_round(_ctx, &rin, &rout);
+        if(st != SPG_OK) {
+            error = spg_last_error();
+            break;
+        }
+        auto t2 = clk::now();
+        applyRound(out.data());
+        auto t3 = clk::now();
+        stats.pack_ms += std::chrono::duration<double, std::milli>(t1 - t0).count();
+        stats.gpu_ms += std::chrono::duration<double, std::milli>(t2 - t1).count();
+        stats.splice_ms += std::chrono::duration<double, std::milli>(t3 - t2).count();
+    }
+    if(status) *status = st;
+    return _added;
+}
+
+spg_status VertexRemover::beginRemoval(const std::vector<int> &toRemove) {
+    stats = spg_marginalize_stats{};
+    _added.clear();
+    _pending = toRemove;
+    _toRemoveSet = std::set<int>(toRemove.begin(), toRemove.end());
+    _done.assign(toRemove.size(), 0);
+    _remaining = toRemove.size();
+    _round = Round();
+    return SPG_OK;
+}
+
+spg_round_in VertexRemover::roundDescriptor() const {
+    spg_round_in rin{};
+    rin.dim = _graph->dim;
+    rin.algorithm = _round.algorithm;
+    rin.opts.topology = _opts.topology;
+    rin.opts.lin_point = _opts.linPoint;
+    rin.opts.chord_ratio = _opts.chordRatio;
+    rin.opts.include_intra_clique = _opts.includeIntraClique;
+    rin.opts.flags = _opts.flags;
+    rin.n_blankets = (int32_t) _round.units.size();
+    rin.rec_off = _round.recOff.data();
+    rin.records = _round.records.data();
+    rin.out_off = _round.outOff.data();
+    return rin;
+}
+
+// Select and pack the next wavefront round (empty round: nothing left).
+spg_status VertexRemover::planRound() {
+    _round = Round();
+    if(_remaining == 0) return SPG_OK;
+    const int dim = _graph->dim;
+    const std::vector<int> &toRemove = _pending;
+    struct Region { std::vector<int> removed, region; }; // region: every vertex of the (conservative) blanket
+    {
         // ---- select a round -------------------------------------------------------------------
-        std::vector<RemovalUnit> units;
-        std::vector<Region> regions;            // selected first, then deferred ones
+        std::vector<RemovalUnit> &units = _round.units;
+        std::vector<Region> regions;            // selected and deferred ones, in list order
         std::unordered_map<int, std::vector<int>> touch; // vertex -> regions containing it
         std::unordered_map<int, int> removedBy;          // vertex -> region removing it
-        std::vector<char> regionSelected;
         for(size_t i = 0; i < toRemove.size(); i++) {
-            if(done[i]) continue;
+            if(_done[i]) continue;
             if(!_graph->hasVertex(toRemove[i])) { // merged into an earlier extended blanket (:91)
-                done[i] = 1;
-                remaining--;
+                _done[i] = 1;
+                _remaining--;
                 continue;
             }
             RemovalUnit u;
-            if(!buildUnit(toRemove[i], (int) i, toRemoveSet, u)) {
+            if(!buildUnit(toRemove[i], (int) i, _toRemoveSet, u)) {
                 // isolated vertex: the reference asserts blanketEdges.size() > 0
                 error = "vertex " + std::to_string(toRemove[i]) + " has no edges";
-                if(status) *status = SPG_ERR_INVALID;
-                return added;
+                return SPG_ERR_INVALID;
             }
             // conflicts with earlier regions?
             std::vector<int> hit; // regions this unit interferes with
@@ -513,134 +562,103 @@ std::vector<int> VertexRemover::remove(const std::vector<int> &toRemove, spg_sta
             for(int x : rg.region) touch[x].push_back(rid);
             for(int x : rg.removed) removedBy[x] = rid;
             regions.push_back(std::move(rg));
-            regionSelected.push_back(select);
             if(select) units.push_back(std::move(u));
         }
-        if(units.empty()) break;
-
-        // ---- pack ----------------------------------------------------------------------------
-        TopologyProvider *tp = nullptr;
-        std::vector<uint64_t> records;
-        std::vector<int64_t> recOff(1, 0), outOff(1, 0);
-        std::vector<uint64_t> rec;
-        for(const RemovalUnit &u : units) {
-            TopologyProvider *t = chooseTopologyProvider(u);
-            if(!t) {
-                error = "No valid topology provider for Markov blanket";
-                if(status) *status = SPG_ERR_UNSUPPORTED;
-                return added;
-            }
-            if(tp && t->algorithm() != tp->algorithm()) {
-                error = "mixed providers within one round";
-                if(status) *status = SPG_ERR_UNSUPPORTED;
-                return added;
-            }
-            tp = t;
-            if(!packUnit(u, rec)) {
-                error = "Local linearisation point on a non-star blanket needs the subgraph optimiser (not on this path)";
-                if(status) *status = SPG_ERR_UNSUPPORTED;
-                return added;
-            }
-            records.insert(records.end(), rec.begin(), rec.end());
-            recOff.push_back((int64_t) records.size());
-            outOff.push_back(outOff.back() + spgr_out_record_words(dim, tp->algorithm(), _opts.topology, _opts.chordRatio,
-                                                                   (int) u.kept.size()));
-            stats.max_blanket_vertices = std::max<int>(stats.max_blanket_vertices, (int) (u.removed.size() + u.kept.size()));
-        }
-        const int algorithm = tp->algorithm();
-        if(algorithm == SPG_ALG_GLC) {
-            // asserts of TopologyProviderGLC::topology (src/topology_provider_glc.cpp:107-111)
-            if(!(_opts.topology == SparsityOptions::Dense || _opts.topology == SparsityOptions::Tree) ||
-               _opts.linPoint != SparsityOptions::Global) {
-                error = "GLC needs Dense|Tree topology and the Global linearisation point";
-                if(status) *status = SPG_ERR_UNSUPPORTED;
-                return added;
-            }
-        }
-        std::vector<uint64_t> out((size_t) outOff.back(), 0);
-        auto t1 = clk::now();
-
-        // ---- GPU -----------------------------------------------------------------------------
-        spg_round_in rin{};
-        rin.dim = dim;
-        rin.algorithm = algorithm;
-        rin.opts.topology = _opts.topology;
-        rin.opts.lin_point = _opts.linPoint;
-        rin.opts.chord_ratio = _opts.chordRatio;
-        rin.opts.include_intra_clique = _opts.includeIntraClique;
-        rin.opts.flags = _opts.flags;
-        rin.n_blankets = (int32_t) units.size();
-        rin.rec_off = recOff.data();
-        rin.records = records.data();
-        rin.out_off = outOff.data();
-        spg_round_out rout{};
-        rout.out = out.data();
-        spg_status st = spg_remove_round(_ctx, &rin, &rout);
-        if(st != SPG_OK) {
-            error = spg_last_error();
-            if(status) *status = st;
-            return added;
-        }
-        auto t2 = clk::now();
-
-        // ---- splice, in list order (updateInputGraph, src/vertex_remover.cpp:500-546) ---------------
-        const int P = _graph->poseWords();
-        for(size_t ui = 0; ui < units.size(); ui++) {
-            const RemovalUnit &u = units[ui];
-            const uint64_t *o = out.data() + outOff[ui];
-            const int32_t *oh = reinterpret_cast<const int32_t *>(o);
-            const int bstatus = oh[0], nnew = oh[1];
-            if(bstatus != SPG_BLANKET_OK) stats.n_failed++;
-            for(int ei : u.edges) _graph->removeEdge(ei);
-            for(int id : u.removed) _graph->removeVertex(id);
-            const int nk = (int) u.kept.size();
-            const int64_t slot = spgr_out_slot_words(dim, algorithm, _opts.topology, nk);
-            int minor = 0;
-            for(int e = 0; e < nnew; e++) {
-                const uint64_t *sl = o + SPG_OUT_HEADER_WORDS + (int64_t) e * slot;
-                const int32_t *si = reinterpret_cast<const int32_t *>(sl);
-                GraphEdge ge;
-                ge.uidMajor = u.listIndex;
-                if(algorithm == SPG_ALG_NFR) {
-                    ge.kind = SPG_EDGE_POSE;
-                    ge.v = {u.kept[si[0]], u.kept[si[1]]};
-                    ge.rows = dim;
-                    const double *pm = reinterpret_cast<const double *>(sl + 1);
-                    ge.meas.assign(pm, pm + P);
-                    ge.info.assign(pm + P, pm + P + dim * dim);
-                } else {
-                    const int nvcap = (_opts.topology == SparsityOptions::Dense || nk == 1) ? nk : 2;
-                    const int c = dim * nvcap, nve = si[0], rank = si[1];
-                    if(rank == 0) { // getEdge returned NULL (src/topology_provider_glc.cpp:85-89)
-                        stats.n_dropped_edges++;
-                        continue;
-                    }
-                    ge.kind = SPG_EDGE_GLC;
-                    const int32_t *vi = reinterpret_cast<const int32_t *>(sl + 1);
-                    for(int q = 0; q < nve; q++) ge.v.push_back(u.kept[vi[q]]);
-                    ge.rows = rank;
-                    const double *pm = reinterpret_cast<const double *>(sl + 1 + spgr_pad2(nvcap));
-                    ge.meas.assign(pm, pm + dim * nve);
-                    const double *W = pm + c;
-                    ge.info.resize((size_t) rank * dim * nve);
-                    for(int r = 0; r < rank; r++)
-                        for(int q = 0; q < dim * nve; q++) ge.info[(size_t) r * dim * nve + q] = W[(size_t) r * c + q];
-                }
-                ge.uidMinor = minor++;
-                added.push_back(_graph->addEdge(ge));
-            }
-            done[u.listIndex] = 1;
-            remaining--;
-            stats.n_blankets++;
-        }
-        auto t3 = clk::now();
-        stats.n_rounds++;
-        stats.max_round_width = std::max<int>(stats.max_round_width, (int) units.size());
-        stats.pack_ms += std::chrono::duration<double, std::milli>(t1 - t0).count();
-        stats.gpu_ms += std::chrono::duration<double, std::milli>(t2 - t1).count();
-        stats.splice_ms += std::chrono::duration<double, std::milli>(t3 - t2).count();
+        if(units.empty()) return SPG_OK;
     }
-    return added;
+    // ---- pack ----------------------------------------------------------------------------
+    TopologyProvider *tp = nullptr;
+    _round.recOff.assign(1, 0);
+    _round.outOff.assign(1, 0);
+    std::vector<uint64_t> rec;
+    for(const RemovalUnit &u : _round.units) {
+        TopologyProvider *t = chooseTopologyProvider(u);
+        if(!t) {
+            error = "No valid topology provider for Markov blanket";
+            return SPG_ERR_UNSUPPORTED;
+        }
+        if(tp && t->algorithm() != tp->algorithm()) {
+            error = "mixed providers within one round";
+            return SPG_ERR_UNSUPPORTED;
+        }
+        tp = t;
+        if(!packUnit(u, rec)) {
+            error = "Local linearisation point on a non-star blanket needs the subgraph optimiser (not on this path)";
+            return SPG_ERR_UNSUPPORTED;
+        }
+        _round.records.insert(_round.records.end(), rec.begin(), rec.end());
+        _round.recOff.push_back((int64_t) _round.records.size());
+        _round.outOff.push_back(_round.outOff.back() + spgr_out_record_words(dim, tp->algorithm(), _opts.topology, _opts.chordRatio,
+                                                                             (int) u.kept.size()));
+        stats.max_blanket_vertices = std::max<int>(stats.max_blanket_vertices, (int) (u.removed.size() + u.kept.size()));
+    }
+    _round.algorithm = tp->algorithm();
+    if(_round.algorithm == SPG_ALG_GLC) {
+        // asserts of TopologyProviderGLC::topology (src/topology_provider_glc.cpp:107-111)
+        if(!(_opts.topology == SparsityOptions::Dense || _opts.topology == SparsityOptions::Tree) ||
+           _opts.linPoint != SparsityOptions::Global) {
+            error = "GLC needs Dense|Tree topology and the Global linearisation point";
+            return SPG_ERR_UNSUPPORTED;
+        }
+    }
+    return SPG_OK;
+}
+
+// Splice the output records of the planned round, in list order (updateInputGraph,
+// src/vertex_remover.cpp:500-546).
+void VertexRemover::applyRound(const uint64_t *out) {
+    const int dim = _graph->dim, P = _graph->poseWords(), algorithm = _round.algorithm;
+    for(size_t ui = 0; ui < _round.units.size(); ui++) {
+        const RemovalUnit &u = _round.units[ui];
+        const uint64_t *o = out + _round.outOff[ui];
+        const int32_t *oh = reinterpret_cast<const int32_t *>(o);
+        const int bstatus = oh[0], nnew = oh[1];
+        if(bstatus != SPG_BLANKET_OK) stats.n_failed++;
+        for(int ei : u.edges) _graph->removeEdge(ei);
+        for(int id : u.removed) _graph->removeVertex(id);
+        const int nk = (int) u.kept.size();
+        const int64_t slot = spgr_out_slot_words(dim, algorithm, _opts.topology, nk);
+        int minor = 0;
+        for(int e = 0; e < nnew; e++) {
+            const uint64_t *sl = o + SPG_OUT_HEADER_WORDS + (int64_t) e * slot;
+            const int32_t *si = reinterpret_cast<const int32_t *>(sl);
+            GraphEdge ge;
+            ge.uidMajor = u.listIndex;
+            if(algorithm == SPG_ALG_NFR) {
+                ge.kind = SPG_EDGE_POSE;
+                ge.v = {u.kept[si[0]], u.kept[si[1]]};
+                ge.rows = dim;
+                const double *pm = reinterpret_cast<const double *>(sl + 1);
+                ge.meas.assign(pm, pm + P);
+                ge.info.assign(pm + P, pm + P + dim * dim);
+            } else {
+                const int nvcap = (_opts.topology == SparsityOptions::Dense || nk == 1) ? nk : 2;
+                const int c = dim * nvcap, nve = si[0], rank = si[1];
+                if(rank == 0) { // getEdge returned NULL (src/topology_provider_glc.cpp:85-89)
+                    stats.n_dropped_edges++;
+                    continue;
+                }
+                ge.kind = SPG_EDGE_GLC;
+                const int32_t *vi = reinterpret_cast<const int32_t *>(sl + 1);
+                for(int q = 0; q < nve; q++) ge.v.push_back(u.kept[vi[q]]);
+                ge.rows = rank;
+                const double *pm = reinterpret_cast<const double *>(sl + 1 + spgr_pad2(nvcap));
+                ge.meas.assign(pm, pm + dim * nve);
+                const double *W = pm + c;
+                ge.info.resize((size_t) rank * dim * nve);
+                for(int r = 0; r < rank; r++)
+                    for(int q = 0; q < dim * nve; q++) ge.info[(size_t) r * dim * nve + q] = W[(size_t) r * c + q];
+            }
+            ge.uidMinor = minor++;
+            _added.push_back(_graph->addEdge(ge));
+        }
+        _done[u.listIndex] = 1;
+        _remaining--;
+        stats.n_blankets++;
+    }
+    stats.n_rounds++;
+    stats.max_round_width = std::max<int>(stats.max_round_width, (int) _round.units.size());
+    _round.units.clear();
 }
 
 // ---- computeSubstituteEdge (src/compute_substitute_edge.cpp:13-96) ---------------------------------
@@ -766,6 +784,7 @@ spg_status spg_graph_create(spg_graph **g, int32_t dim) {
 }
 void spg_graph_destroy(spg_graph *g) {
     if(!g) return;
+    delete g->session;
     delete g->g;
     delete g;
 }
@@ -836,6 +855,51 @@ spg_status spg_graph_marginalize(spg_graph *g, spg_ctx *ctx, const int32_t *whic
     g->stats = vr.stats;
     return st;
 }
+// Round-by-round variant of spg_graph_marginalize, for callers that run the blankets of a round
+// themselves (e.g. sharded over several GPUs / ranks): begin -> { next -> compute -> apply }*.
+static spg::VertexRemover *makeRemover(spg_graph *g, const spg_sparsity_options *opts, int32_t algorithm) {
+    spg::VertexRemover *vr = new spg::VertexRemover;
+    if(algorithm == SPG_ALG_GLC) {
+        vr->registerTopologyProvider(new spg::TopologyProviderGLC);
+    } else {
+        vr->registerTopologyProvider(new spg::TopologyProviderSE2);
+        vr->registerTopologyProvider(new spg::TopologyProviderSE2ISAM);
+        vr->registerTopologyProvider(new spg::TopologyProviderSE3);
+        vr->registerTopologyProvider(new spg::TopologyProviderSE3ISAM);
+    }
+    vr->setGraph(g->g);
+    spg::SparsityOptions o;
+    o.topology = (spg::SparsityOptions::SparsityTopology) opts->topology;
+    o.chordRatio = opts->chord_ratio;
+    o.linPoint = (spg::SparsityOptions::LinearizationPoint) opts->lin_point;
+    o.includeIntraClique = opts->include_intra_clique != 0;
+    o.flags = opts->flags;
+    vr->setSparsityOptions(o);
+    return vr;
+}
+spg_status spg_graph_rounds_begin(spg_graph *g, const int32_t *which, int32_t n_which, const spg_sparsity_options *opts,
+                                  int32_t algorithm) {
+    if(!g || !which || !opts || n_which < 0) return SPG_ERR_INVALID;
+    for(int i = 0; i < n_which; i++)
+        if(!g->g->hasVertex(which[i])) return SPG_ERR_INVALID;
+    delete g->session;
+    g->session = makeRemover(g, opts, algorithm);
+    return g->session->beginRemoval(std::vector<int>(which, which + n_which));
+}
+spg_status spg_graph_round_next(spg_graph *g, spg_round_in *round) {
+    if(!g || !g->session || !round) return SPG_ERR_INVALID;
+    spg_status st = g->session->planRound();
+    *round = g->session->roundDescriptor();
+    if(st != SPG_OK || round->n_blankets == 0) g->stats = g->session->stats;
+    return st;
+}
+spg_status spg_graph_round_apply(spg_graph *g, const uint64_t *out) {
+    if(!g || !g->session || !out) return SPG_ERR_INVALID;
+    g->session->applyRound(out);
+    g->stats = g->session->stats;
+    return SPG_OK;
+}
+
 spg_status spg_graph_last_stats(const spg_graph *g, spg_marginalize_stats *stats) {
     if(!g || !stats) return SPG_ERR_INVALID;
     *stats = g->stats;

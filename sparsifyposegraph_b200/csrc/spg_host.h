@@ -146,6 +146,19 @@ public:
     std::vector<int> extendedMarkovBlanketVertices(int root, const std::set<int> &pickBin, std::vector<int> &picked) const;
     std::vector<int> markovBlanketEdges(const std::vector<int> &mbVertices, const std::vector<int> &hubs) const;
 
+    // round-by-round interface (what remove() loops over): beginRemoval, then planRound /
+    // roundDescriptor / applyRound until planRound leaves an empty round
+    struct Round {
+        std::vector<RemovalUnit> units;
+        std::vector<uint64_t> records;
+        std::vector<int64_t> recOff, outOff;
+        int algorithm = SPG_ALG_NFR;
+    };
+    spg_status beginRemoval(const std::vector<int> &toRemove);
+    spg_status planRound();
+    spg_round_in roundDescriptor() const;
+    void applyRound(const uint64_t *out);
+
     spg_marginalize_stats stats{};
     std::string error;
 
@@ -154,6 +167,11 @@ private:
     TopologyProvider *chooseTopologyProvider(const RemovalUnit &u) const;
     bool packUnit(const RemovalUnit &u, std::vector<uint64_t> &rec) const;
 
+    Round _round;
+    std::vector<int> _pending, _added;
+    std::set<int> _toRemoveSet;
+    std::vector<char> _done;
+    size_t _remaining = 0;
     SparsityOptions _opts;
     Graph *_graph = nullptr;
     spg_ctx *_ctx = nullptr;
@@ -172,5 +190,6 @@ void poseInverse(int dim, const double *a, double *out);
 
 struct spg_graph {
     spg::Graph *g = nullptr;
+    spg::VertexRemover *session = nullptr; // round-by-round removal in progress
     spg_marginalize_stats stats{};
 };
