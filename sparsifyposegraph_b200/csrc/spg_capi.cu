@@ -48,17 +48,17 @@ template <int D>
 spg_status launch_dim(spg_ctx *ctx, spg::KernelParams &kp) {
     spg::plan_smem<D>(kp);
     // CTA width by the size of H (N = D * vertices): the register-tiled sweeps cover
-    // N <= 12 / 32 / 56 / 96 for 32 / 64 / 128 / 256 threads (SweepGrid in spg_device.cuh)
+    // N <= 12 / 32 / 48 / 96 for 32 / 64 / 128 / 256 threads (SweepGrid in spg_device.cuh)
     const int N = D * kp.max_nv;
     if(D == 6) {
         if(N <= 12) return spg_launch_6_32(ctx, kp);
         if(N <= 32) return spg_launch_6_64(ctx, kp);
-        if(N <= 56) return spg_launch_6_128(ctx, kp);
+        if(N <= 48) return spg_launch_6_128(ctx, kp);
         return spg_launch_6_256(ctx, kp);
     }
     if(N <= 12) return spg_launch_3_32(ctx, kp);
     if(N <= 32) return spg_launch_3_64(ctx, kp);
-    if(N <= 56) return spg_launch_3_128(ctx, kp);
+    if(N <= 48) return spg_launch_3_128(ctx, kp);
     return spg_launch_3_256(ctx, kp);
 }
 

@@ -326,7 +326,9 @@ __device__ __noinline__ bool sweep_spd(double *A, int n, int ld, int nsweep, dou
     const bool active = tid < T * T;
     const int tx = tid % T, ty = (tid / T) % T;
     // colbuf: two slots of (n + 2) doubles: the pivot column, then the pivot d and 1/d
-    const int cstride = n + 2;
+    constexpr int NP = T * TS;      // padded length: loads / stores of the pivot column need no bounds checks
+    const int cstride = NP + 2;
+    for(int t = n + tid; t < NP; t += NT) { colbuf[t] = 0.0; colbuf[cstride + t] = 0.0; }
     double a[TS][TS];
 #pragma unroll
     for(int c = 0; c < TS; c++)
@@ -338,11 +340,8 @@ __device__ __noinline__ bool sweep_spd(double *A, int n, int ld, int nsweep, dou
     // publish column 0
     if(active && ty == 0) {
 #pragma unroll
-        for(int r = 0; r < TS; r++) {
-            const int i = tx + T * r;
-            if(i < n) colbuf[i] = a[r][0];
-        }
-        if(tx == 0) { colbuf[n] = a[0][0]; colbuf[n + 1] = 1.0 / a[0][0]; }
+        for(int r = 0; r < TS; r++) colbuf[tx + T * r] = a[r][0];
+        if(tx == 0) { colbuf[NP] = a[0][0]; colbuf[NP + 1] = 1.0 / a[0][0]; }
     }
     gsync<NT>();
     bool ok = true;
@@ -358,15 +357,14 @@ __device__ __noinline__ bool sweep_spd(double *A, int n, int ld, int nsweep, dou
             const int j = jj + T * c0;
             const double *col = colbuf + (j & 1) * cstride;
             double *ncol = colbuf + ((j + 1) & 1) * cstride;
-            const double d = col[n], inv = col[n + 1];
+            const double d = col[NP], inv = col[NP + 1];
             if(!(d > 0)) ok = false; // uniform: every thread reads the same pivot
             if(ok && active) {
                 double ci[TS], cl[TS];
 #pragma unroll
                 for(int r = 0; r < TS; r++) {
-                    const int i = tx + T * r, l = ty + T * r;
-                    ci[r] = (i < n) ? col[i] : 0.0;
-                    cl[r] = (l < n) ? col[l] * inv : 0.0;
+                    ci[r] = col[tx + T * r];
+                    cl[r] = col[ty + T * r] * inv;
                 }
                 const bool rowj = (tx == jj), colj = (ty == jj);
                 const bool wrap = (jj + 1 == T);
@@ -383,11 +381,8 @@ __device__ __noinline__ bool sweep_spd(double *A, int n, int ld, int nsweep, dou
                     }
                     if(more && ty == jj + 1) {
 #pragma unroll
-                        for(int r = 0; r < TS; r++) {
-                            const int i = tx + T * r;
-                            if(i < n) ncol[i] = a[r][c0];
-                        }
-                        if(tx == jj + 1) { ncol[n] = a[c0][c0]; ncol[n + 1] = 1.0 / a[c0][c0]; }
+                        for(int r = 0; r < TS; r++) ncol[tx + T * r] = a[r][c0];
+                        if(tx == jj + 1) { ncol[NP] = a[c0][c0]; ncol[NP + 1] = 1.0 / a[c0][c0]; }
                     }
                 } else if(c0 + 1 < TS) {
                     constexpr int dummy = 0; (void) dummy;
@@ -396,11 +391,8 @@ __device__ __noinline__ bool sweep_spd(double *A, int n, int ld, int nsweep, dou
                     if(rowj) a[c0][(c0 + 1) % TS] = cl[(c0 + 1) % TS];
                     if(more && ty == 0) {
 #pragma unroll
-                        for(int r = 0; r < TS; r++) {
-                            const int i = tx + T * r;
-                            if(i < n) ncol[i] = a[r][(c0 + 1) % TS];
-                        }
-                        if(tx == 0) { ncol[n] = a[(c0 + 1) % TS][(c0 + 1) % TS]; ncol[n + 1] = 1.0 / a[(c0 + 1) % TS][(c0 + 1) % TS]; }
+                        for(int r = 0; r < TS; r++) ncol[tx + T * r] = a[r][(c0 + 1) % TS];
+                        if(tx == 0) { ncol[NP] = a[(c0 + 1) % TS][(c0 + 1) % TS]; ncol[NP + 1] = 1.0 / a[(c0 + 1) % TS][(c0 + 1) % TS]; }
                     }
                 }
                 // ---- bulk of the tile ----
@@ -440,10 +432,10 @@ __device__ __noinline__ bool sweep_spd(double *A, int n, int ld, int nsweep, dou
 template <int NT> struct SweepGrid;
 template <> struct SweepGrid<32>  { static constexpr int T = 4,  TS = 3; };   // n <= 12
 template <> struct SweepGrid<64>  { static constexpr int T = 8,  TS = 4; };   // n <= 32
-template <> struct SweepGrid<128> { static constexpr int T = 8,  TS = 7; };   // n <= 56
+template <> struct SweepGrid<128> { static constexpr int T = 8,  TS = 6; };   // n <= 48 (a 7 x 7 tile spills)
 template <> struct SweepGrid<256> { static constexpr int T = 16, TS = 6; };   // n <= 96
 
-// returns 1 ok, 0 not positive definite, -1 n too large for the register tiles. scratch: 2 * (n + 2) doubles.
+// returns 1 ok, 0 not positive definite, -1 n too large for the register tiles. scratch: 2 * (T*TS + 2) doubles.
 // (A per-vertex blocked variant — rank-6 updates, 2 barriers per vertex — was measured slower on
 // B200: 186k vs 100k cycles for k = 90; the tile plus panel operands spill. See DESIGN.md §3.)
 template <int D, int NT>
