@@ -428,20 +428,22 @@ __device__ __noinline__ bool sweep_spd(double *A, int n, int ld, int nsweep, dou
     return true;
 }
 
-// One tile shape per CTA width: the largest n it covers is T * TS.
+// Two tile shapes per CTA width: the largest n each covers is T * TS.
 template <int NT> struct SweepGrid;
-template <> struct SweepGrid<32>  { static constexpr int T = 4,  TS = 3; };   // n <= 12
-template <> struct SweepGrid<64>  { static constexpr int T = 8,  TS = 4; };   // n <= 32
-template <> struct SweepGrid<128> { static constexpr int T = 8,  TS = 6; };   // n <= 48 (a 7 x 7 tile spills)
-template <> struct SweepGrid<256> { static constexpr int T = 16, TS = 6; };   // n <= 96
+template <> struct SweepGrid<32>  { static constexpr int T = 4,  TS0 = 2, TS1 = 3; };   // n <= 8 / 12
+template <> struct SweepGrid<64>  { static constexpr int T = 8,  TS0 = 3, TS1 = 4; };   // n <= 24 / 32
+template <> struct SweepGrid<128> { static constexpr int T = 8,  TS0 = 5, TS1 = 6; };   // n <= 40 / 48 (7 x 7 spills)
+template <> struct SweepGrid<256> { static constexpr int T = 16, TS0 = 5, TS1 = 6; };   // n <= 80 / 96
 
 // returns 1 ok, 0 not positive definite, -1 n too large for the register tiles. scratch: 2 * (T*TS + 2) doubles.
-// (A per-vertex blocked variant — rank-6 updates, 2 barriers per vertex — was measured slower on
-// B200: 186k vs 100k cycles for k = 90; the tile plus panel operands spill. See DESIGN.md §3.)
+// (Blocked variants were measured and dropped: a per-vertex rank-6 sweep took 186k vs 100k cycles at
+// k = 90 and a rank-2 sweep 79k vs 78k — the extra panel operands spill next to the 6 x 6 tile, and the
+// kernel is issue-latency bound at 8 warps per SM rather than barrier bound. See DESIGN.md §3.)
 template <int D, int NT>
 __device__ __forceinline__ int sweep_spd_auto(double *A, int n, int ld, int nsweep, double *scratch) {
     using G = SweepGrid<NT>;
-    if(n <= G::T * G::TS) return sweep_spd<NT, G::T, G::TS>(A, n, ld, nsweep, scratch) ? 1 : 0;
+    if(n <= G::T * G::TS0) return sweep_spd<NT, G::T, G::TS0>(A, n, ld, nsweep, scratch) ? 1 : 0;
+    if(n <= G::T * G::TS1) return sweep_spd<NT, G::T, G::TS1>(A, n, ld, nsweep, scratch) ? 1 : 0;
     return -1;
 }
 

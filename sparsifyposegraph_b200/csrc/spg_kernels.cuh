@@ -571,7 +571,7 @@ __global__ void __launch_bounds__(NT, (NT >= 256) ? 1 : (NT == 128 ? 3 : 512 / N
             // pseudo-inverse, and J Sigma J^T = J G J^T for ANY generalised inverse G of Lambda_t. We take
             // G = [[Lambda_rr^-1, 0], [0, 0]] (last kept vertex anchored): one Cholesky instead of an
             // eigen-decomposition. The shortcut is taken only when the reference would be in the same
-            // branch: (i) trace(G) <= 1e5 => smallest eigenvalue of Lambda_rr >= 1e-5 => by interlacing
+            // branch: (i) diag(G) <= 1e5/(k-d) => trace(G) <= 1e5 => smallest eigenvalue of Lambda_rr >= 1e-5 => by interlacing
             // lambda_{d+1} >= cutoff, i.e. smalleigs <= d; (ii) max diag < 1e8 so the null eigenvalues
             // (~ k eps ||Lambda||) stay below the cutoff, i.e. smalleigs >= d. Otherwise: general path.
             bool fast = false;
@@ -582,12 +582,10 @@ __global__ void __launch_bounds__(NT, (NT >= 256) ? 1 : (NT == 128 ? 3 : 512 / N
                     const int i = t % kk, j = t / kk;
                     buf1[i + j * ldg] = T[i + (size_t) j * ldH];
                 }
-                if(tid == 0) {
-                    double md = 0;
-                    for(int i = 0; i < k; i++) md = fmax(md, fabs(T[i + (size_t) i * ldH]));
-                    s_red[1] = md;
-                }
-                gsync<NT>();
+                // guard (ii): every diagonal entry of Lambda_t below 1e8 (checked by all threads, OR-reduced)
+                int bigdiag = 0;
+                for(int i = tid; i < k; i += NT) bigdiag |= !(fabs(T[i + (size_t) i * ldH]) < 1e8);
+                bigdiag = gsync_or<NT>(bigdiag);
                 int swg = sweep_spd_auto<D, NT>(buf1, kk, ldg, kk, buf2);
                 if(swg < 0) {
                     swg = chol_lower<NT>(buf1, kk, ldg) ? 1 : 0;
@@ -595,13 +593,12 @@ __global__ void __launch_bounds__(NT, (NT >= 256) ? 1 : (NT == 128 ? 3 : 512 / N
                 }
                 if(swg > 0) {
                     SPG_T(8);
-                    if(tid == 0) {
-                        double tr = 0;
-                        for(int i = 0; i < kk; i++) tr += G[i + i * ldg];
-                        s_red[2] = tr;
-                    }
-                    gsync<NT>();
-                    fast = (s_red[2] <= 1e5) && (s_red[1] < 1e8); // false for NaN too
+                    // guard (i): every diagonal entry of G at most 1e5 / (k - d)  =>  trace(G) <= 1e5
+                    int bigg = 0;
+                    const double glim = 1e5 / (double) (kk > 0 ? kk : 1);
+                    for(int i = tid; i < kk; i += NT) bigg |= !(G[i + i * ldg] <= glim); // true for NaN too
+                    bigg = gsync_or<NT>(bigg);
+                    fast = !bigg && !bigdiag;
                 }
             }
             if(!fast) {
@@ -778,14 +775,30 @@ __global__ void __launch_bounds__(NT, (NT >= 256) ? 1 : (NT == 128 ? 3 : 512 / N
                 }
                 gsync<NT>();
                 SPG_T(11);
-                // X_e = block_e^-1 through LLT (:273-274), straight to the output record
-                for(int e = tid; e < n_out; e += NT) {
-                    double X[D * D];
-                    const bool ok = spd_inverse_small<D>(Bk + (size_t) e * D * D, X);
-                    if(!ok) s_misc[0] = SPG_BLANKET_NOT_PD_CLOSED;
+                // X_e = block_e^-1 (:273-274; the reference goes through LLT, here all D x D blocks are inverted
+                // together by D symmetric Gauss-Jordan sweeps, one thread per entry; a pivot <= 0 is the same
+                // "not positive definite" condition), straight to the output record
+                double *src = Bk, *dst = Sg; // Sg is free again: ping-pong between the two
+                for(int s0 = 0; s0 < D; s0++) {
+                    for(int t = tid; t < n_out * D * D; t += NT) {
+                        const int e = t / (D * D), q = t % (D * D), i = q % D, j = q / D;
+                        const double *B = src + (size_t) e * D * D;
+                        const double d = B[s0 + s0 * D];
+                        if(!(d > 0)) s_misc[0] = SPG_BLANKET_NOT_PD_CLOSED;
+                        const double inv = 1.0 / d, bis = B[i + s0 * D], bsj = B[s0 + j * D];
+                        double v = B[i + j * D] - bis * bsj * inv;
+                        if(j == s0) v = bis * inv;
+                        if(i == s0) v = bsj * inv;
+                        if(i == s0 && j == s0) v = -inv;
+                        dst[t] = v;
+                    }
+                    gsync<NT>();
+                    double *tmp = src; src = dst; dst = tmp;
+                }
+                for(int t = tid; t < n_out * D * D; t += NT) {
+                    const int e = t / (D * D), q = t % (D * D);
                     double *sx = reinterpret_cast<double *>(gout + SPG_OUT_HEADER_WORDS + (size_t) e * slot + 1 + PW);
-#pragma unroll
-                    for(int q = 0; q < D * D; q++) sx[q] = ok ? X[q] : 0.0;
+                    sx[q] = (s_misc[0] == SPG_BLANKET_OK) ? -src[t] : 0.0;
                 }
                 gsync<NT>();
                 if(s_misc[0] != SPG_BLANKET_OK) status = s_misc[0];

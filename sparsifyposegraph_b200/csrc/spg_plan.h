@@ -52,7 +52,7 @@ inline void plan_smem(KernelParams &p) {
     p.off_buf1 = o;
     int b1 = kmax * odd_ld(kmax > 0 ? kmax : 1);
     int asm_scratch = ASM_CHUNK * 2 * (D * 2 * D);
-    const int sweep_scratch = 208; // two padded pivot-column buffers of the register-tiled sweeps (2 * (96 + 2), buf1 or buf2)
+    const int sweep_scratch = 392; // pivot-column buffers of the register-tiled sweeps (2 parities x 2 columns x 96 + pad; buf1 or buf2)
     p.buf1_doubles = b1 > asm_scratch ? b1 : asm_scratch;
     if(p.buf1_doubles < sweep_scratch) p.buf1_doubles = sweep_scratch;
     o += p.buf1_doubles;
