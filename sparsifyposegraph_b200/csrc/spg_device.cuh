@@ -202,6 +202,34 @@ __device__ __noinline__ void edge_jacobians(const double *Z, const double *Xi, c
     }
 }
 
+// Jacobians of a NEW substitute edge, whose measurement was just set from the state
+// (setMeasurementFromState, topology_provider_binary.hpp:43-47), i.e. at zero error E = I.
+// SE3: with Z = Xa^-1 Xb = (R, p) the general formulas collapse to
+//   Jj = I,   Ji = [[-R^T, 2 R^T [p]x], [0, -R^T]]     (FD-checked in tests/test_oracle.py)
+// SE2: the ISAM-style Jacobians do not depend on the measurement at all.
+template <int D>
+__device__ __forceinline__ void edge_jacobians_zero_error(const double *Z, const double *Xi, const double *Xj, double *J) {
+    if constexpr(D == 3) {
+        edge_jacobians<D>(Z, Xi, Xj, J);
+    } else {
+#pragma unroll
+        for(int i = 0; i < 72; i++) J[i] = 0;
+        const double px = Z[9], py = Z[10], pz = Z[11];
+        const double S[9] = {0, -pz, py, pz, 0, -px, -py, px, 0}; // [p]x row-major
+#pragma unroll
+        for(int r = 0; r < 3; r++)
+#pragma unroll
+            for(int c = 0; c < 3; c++) {
+                const double rt = Z[3 * c + r]; // R^T[r][c]
+                J[r + 6 * c] = -rt;
+                J[(3 + r) + 6 * (3 + c)] = -rt;
+                J[r + 6 * (3 + c)] = 2 * (Z[r] * S[c] + Z[3 + r] * S[3 + c] + Z[6 + r] * S[6 + c]); // 2 (R^T [p]x)[r][c]
+            }
+#pragma unroll
+        for(int d = 0; d < 6; d++) J[36 + d + 6 * d] = 1.0;
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // cooperative dense linear algebra on shared-memory matrices (column-major)
 // ------------------------------------------------------------------------------------------

@@ -636,7 +636,7 @@ __global__ void __launch_bounds__(NT, (NT >= 256) ? 1 : (NT == 128 ? 3 : 512 / N
                 double Z[PS], Ti[PS];
                 if constexpr(D == 6) { se3_inverse(Xa, Ti); se3_compose(Ti, Xb, Z); }
                 else { se2_inverse(Xa, Ti); se2_compose(Ti, Xb, Z); }
-                edge_jacobians<D>(Z, Xa, Xb, Jn + (size_t) e * JW);
+                edge_jacobians_zero_error<D>(Z, Xa, Xb, Jn + (size_t) e * JW);
                 uint64_t *sl = gout + SPG_OUT_HEADER_WORDS + (size_t) e * slot;
                 int32_t *si = reinterpret_cast<int32_t *>(sl);
                 si[0] = a; si[1] = bb;
@@ -751,22 +751,28 @@ __global__ void __launch_bounds__(NT, (NT >= 256) ? 1 : (NT == 128 ? 3 : 512 / N
                     }
                 }
                 gsync<NT>();
-                // block_e = J Sg_e J^T, symmetrised (:249-270)
+                // block_e = J Sg_e J^T, symmetrised (:249-270), in two stages: Tm = J Sg_e (D x 2D), then Tm J^T
+                double *Tm = buf2; // n_out * JW doubles; buf2 is free here
+                for(int t = tid; t < n_out * JW; t += NT) {
+                    const int e = t / JW, q = t % JW, rr = q % D, j = q / D;
+                    const double *J = Jn + (size_t) e * JW;
+                    const double *S2 = Sg + (size_t) e * SW;
+                    double acc = 0;
+#pragma unroll
+                    for(int i = 0; i < 2 * D; i++) acc += J[rr + i * D] * S2[i + j * 2 * D];
+                    Tm[t] = acc;
+                }
+                gsync<NT>();
                 for(int t = tid; t < n_out * D * D; t += NT) {
                     const int e = t / (D * D), q = t % (D * D), rr = q % D, cc = q / D;
                     if(rr >= cc) {
                         const double *J = Jn + (size_t) e * JW;
-                        const double *S2 = Sg + (size_t) e * SW;
+                        const double *Te = Tm + (size_t) e * JW;
                         double s1 = 0, s2 = 0;
-                        for(int j = 0; j < 2 * D; j++) {
-                            double tr = 0, tc = 0;
 #pragma unroll
-                            for(int i = 0; i < 2 * D; i++) {
-                                tr += J[rr + i * D] * S2[i + j * 2 * D];
-                                tc += J[cc + i * D] * S2[i + j * 2 * D];
-                            }
-                            s1 += tr * J[cc + j * D];
-                            s2 += tc * J[rr + j * D];
+                        for(int j = 0; j < 2 * D; j++) {
+                            s1 += Te[rr + j * D] * J[cc + j * D];
+                            s2 += Te[cc + j * D] * J[rr + j * D];
                         }
                         const double v = 0.5 * (s1 + s2);
                         Bk[(size_t) e * D * D + rr + cc * D] = v;
