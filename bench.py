@@ -173,6 +173,8 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the node-removal path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    # keep stdout to the single JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION/INFO
+    os.environ["NCCL_DEBUG"] = os.environ.get("SPG_NCCL_DEBUG", "WARN")
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = capi.Context(local_rank)
@@ -311,6 +313,13 @@ def main():
                     "hbm": {"achieved": dom["gbs"], "peak": hbm_peak, "unit": "GB/s", "frac": dom["gbs"] / hbm_peak,
                             "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"},
                     "traffic": None, "share_of_step": dom["ms"] / sum(p["ms"] for p in per_size)}
+        try:  # DRAM bytes per blanket of this kernel from the committed ncu --set full capture
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+            if tr.get("n") == dom["n"]:
+                roofline["traffic"] = tr["dram_bytes_per_blanket"] * args.blankets
+                roofline["traffic_source"] = tr["source"]
+        except Exception:
+            pass
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": workload_config(args.blankets, world),
