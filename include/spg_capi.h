@@ -81,7 +81,7 @@ typedef enum {
     SPG_BLANKET_NOT_PD_CHOWLIU = 2,   /* LLT(Lambda_t + I) failed, pseudo_chow_liu.cpp:189        */
     SPG_BLANKET_EIG_NOCONV = 3,       /* eigen-solver did not converge                            */
     SPG_BLANKET_NOT_PD_CLOSED = 4,    /* LLT(J Sigma J^T) failed, logdet_function.cpp:273         */
-    SPG_BLANKET_TOO_LARGE = 5,        /* blanket exceeds the compiled on-chip capacity            */
+    SPG_BLANKET_TOO_LARGE = 5,        /* iterative-fit workspace of the blanket exceeds its budget */
     SPG_BLANKET_LINESEARCH_FAIL = 6,  /* pqn/line_search.cpp:24-26 returned -1 (ignored by ref.)  */
     SPG_BLANKET_KLD_INF = 7,          /* optimizer.cpp:75-77 (reference calls exit(0))            */
     SPG_BLANKET_UNSUPPORTED = 8,      /* edge kind / option not handled on device                 */

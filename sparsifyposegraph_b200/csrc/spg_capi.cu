@@ -50,6 +50,9 @@ spg_status launch_dim(spg_ctx *ctx, spg::KernelParams &kp) {
     // CTA width by the size of H (N = D * vertices): the register-tiled sweeps cover
     // N <= 12 / 32 / 48 / 96 for 32 / 64 / 128 / 256 threads (SweepGrid in spg_device.cuh)
     const int N = D * kp.max_nv;
+    // working set beyond shared memory (SE3 > 19, SE2 > 39 vertices): same kernel over a global workspace
+    if((size_t) kp.total_doubles * sizeof(double) > ctx->smem_optin)
+        return D == 6 ? spg_launch_6_spill(ctx, kp) : spg_launch_3_spill(ctx, kp);
     if(D == 6) {
         if(N <= 12) return spg_launch_6_32(ctx, kp);
         if(N <= 32) return spg_launch_6_64(ctx, kp);
@@ -60,22 +63,6 @@ spg_status launch_dim(spg_ctx *ctx, spg::KernelParams &kp) {
     if(N <= 32) return spg_launch_3_64(ctx, kp);
     if(N <= 48) return spg_launch_3_128(ctx, kp);
     return spg_launch_3_256(ctx, kp);
-}
-
-// largest vertex count whose bucket still fits in shared memory
-template <int D>
-int max_fit_nv(const spg_ctx *ctx, int max_e_hint, int max_rec_hint) {
-    int best = 0;
-    for(int nv = 2; nv <= 400; nv++) {
-        spg::KernelParams kp{};
-        kp.max_nv = nv;
-        kp.max_e = max_e_hint;
-        kp.max_rec_words = max_rec_hint;
-        spg::plan_smem<D>(kp);
-        if((size_t) kp.total_doubles * 8 <= ctx->smem_optin) best = nv;
-        else break;
-    }
-    return best;
 }
 
 spg_status check_device(spg_ctx *ctx) {
@@ -132,7 +119,7 @@ void spg_destroy(spg_ctx *ctx) {
     if(!ctx) return;
     cudaSetDevice(ctx->device);
     for(DevBuf *b : {&ctx->d_rec, &ctx->d_recoff, &ctx->d_outoff, &ctx->d_out, &ctx->d_list, &ctx->d_tgt,
-                     &ctx->d_tgtoff, &ctx->d_wts, &ctx->d_wtsoff, &ctx->d_ws, &ctx->d_prof})
+                     &ctx->d_tgtoff, &ctx->d_wts, &ctx->d_wtsoff, &ctx->d_ws, &ctx->d_gws, &ctx->d_prof})
         b->release();
     if(ctx->ev0) cudaEventDestroy(ctx->ev0);
     if(ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -305,8 +292,6 @@ spg_status spg_remove_round(spg_ctx *ctx, const spg_round_in *in, spg_round_out 
     // ---- kernels -----------------------------------------------------------------------------
     SPG_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
     size_t list_pos = 0;
-    const int fit = (dim == 6) ? max_fit_nv<6>(ctx, 64, 4096) : max_fit_nv<3>(ctx, 64, 4096);
-    (void) fit;
     for(auto &B : buckets) {
         if(B.list.empty()) continue;
         spg::KernelParams kp{};
@@ -328,19 +313,6 @@ spg_status spg_remove_round(spg_ctx *ctx, const spg_round_in *in, spg_round_out 
         kp.max_nv = B.max_nv;
         kp.max_e = B.max_e;
         kp.max_rec_words = (B.max_rec + 1) & ~1;
-        // a bucket that does not fit on chip is shrunk to the largest size that does: the kernel
-        // flags its over-sized blankets SPG_BLANKET_TOO_LARGE (global-memory variant: DESIGN.md)
-        {
-            spg::KernelParams probe = kp;
-            if(dim == 6) spg::plan_smem<6>(probe); else spg::plan_smem<3>(probe);
-            while((size_t) probe.total_doubles * 8 > ctx->smem_optin && probe.max_nv > 2) {
-                probe.max_nv--;
-                probe.max_rec_words = std::min(probe.max_rec_words, 6000);
-                if(dim == 6) spg::plan_smem<6>(probe); else spg::plan_smem<3>(probe);
-            }
-            kp.max_nv = probe.max_nv;
-            kp.max_rec_words = probe.max_rec_words;
-        }
         spg_status st = (dim == 6) ? launch_dim<6>(ctx, kp) : launch_dim<3>(ctx, kp);
         if(st != SPG_OK) return st;
     }

@@ -48,7 +48,7 @@ struct spg_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int64_t launches = 0;
     double last_ms = 0;
-    DevBuf d_rec, d_recoff, d_outoff, d_out, d_list, d_tgt, d_tgtoff, d_wts, d_wtsoff, d_ws, d_prof;
+    DevBuf d_rec, d_recoff, d_outoff, d_out, d_list, d_tgt, d_tgtoff, d_wts, d_wtsoff, d_ws, d_gws, d_prof;
     bool profiling = false;
 };
 
@@ -62,3 +62,5 @@ spg_status spg_launch_6_32(spg_ctx *, spg::KernelParams &);
 spg_status spg_launch_6_64(spg_ctx *, spg::KernelParams &);
 spg_status spg_launch_6_128(spg_ctx *, spg::KernelParams &);
 spg_status spg_launch_6_256(spg_ctx *, spg::KernelParams &);
+spg_status spg_launch_3_spill(spg_ctx *, spg::KernelParams &); // 256 threads, buffers in global memory
+spg_status spg_launch_6_spill(spg_ctx *, spg::KernelParams &);

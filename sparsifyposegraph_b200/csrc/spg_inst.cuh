@@ -8,28 +8,43 @@
 
 namespace {
 #define set_err spg_set_err
-template <int D, int NT>
+template <int D, int NT, bool SPILL = false>
 spg_status launch_bucket(spg_ctx *ctx, spg::KernelParams &kp) {
     static std::mutex mu;
     static size_t configured = 0;
-    const size_t smem = (size_t) kp.total_doubles * sizeof(double);
+    size_t smem = (size_t) kp.total_doubles * sizeof(double);
+    if(SPILL) smem = 0;
     if(smem > ctx->smem_optin) {
         set_err("bucket needs more shared memory than the device offers");
         return SPG_ERR_INVALID;
     }
-    {
+    if(!SPILL) {
         std::lock_guard<std::mutex> lk(mu);
         if(smem > configured) {
-            SPG_CUDA(cudaFuncSetAttribute(spg::blanket_kernel<D, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            SPG_CUDA(cudaFuncSetAttribute(spg::blanket_kernel<D, NT, SPILL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int) ctx->smem_optin));
             configured = ctx->smem_optin;
         }
     }
     int per_sm = 0;
-    SPG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, spg::blanket_kernel<D, NT>, NT, smem));
+    SPG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, spg::blanket_kernel<D, NT, SPILL>, NT, smem));
     if(per_sm < 1) per_sm = 1;
     int grid = std::min<int64_t>(kp.n_list, (int64_t) per_sm * ctx->sm_count);
     if(grid < 1) return SPG_OK;
+    kp.gws = nullptr;
+    kp.gws_stride = 0;
+    if(SPILL) {
+        const int64_t stride = ((int64_t) kp.total_doubles + 15) & ~(int64_t) 15;
+        const int64_t budget = (int64_t) 8 << 27; // 8 GiB of doubles at most
+        if(stride > budget) {
+            set_err("blanket too large for the spill workspace");
+            return SPG_ERR_INVALID;
+        }
+        if((int64_t) grid * stride > budget) grid = (int) std::max<int64_t>(1, budget / stride);
+        SPG_CUDA(ctx->d_gws.reserve((size_t) grid * stride * sizeof(double)));
+        kp.gws = reinterpret_cast<double *>(ctx->d_gws.p);
+        kp.gws_stride = stride;
+    }
     kp.prof = ctx->profiling ? reinterpret_cast<unsigned long long *>(ctx->d_prof.p) : nullptr;
     // iterative NFR (Subgraph / Dense, >= 3 kept vertices): per-CTA global workspace
     kp.nfr_ws = nullptr;
@@ -48,7 +63,7 @@ spg_status launch_bucket(spg_ctx *ctx, spg::KernelParams &kp) {
             }
         }
     }
-    spg::blanket_kernel<D, NT><<<grid, NT, smem, ctx->stream>>>(kp);
+    spg::blanket_kernel<D, NT, SPILL><<<grid, NT, smem, ctx->stream>>>(kp);
     SPG_CUDA(cudaGetLastError());
     ctx->launches++;
     return SPG_OK;

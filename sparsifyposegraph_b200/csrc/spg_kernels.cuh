@@ -229,16 +229,21 @@ __device__ bool assemble_glc_edge(const uint64_t *ew, const double *s_pose, doub
         }                                                                                            \
     } while(0)
 
-template <int D, int NT>
+// SPILL = true: the variant for blankets whose working set exceeds shared memory. Same code; the record is
+// read in place and every buffer of the shared-memory plan lives in a per-CTA slice of a global workspace
+// (served by L1/L2). A separate instantiation so that the on-chip variant keeps LDS/STS addressing.
+template <int D, int NT, bool SPILL = false>
 __global__ void __launch_bounds__(NT, (NT >= 256) ? 1 : (NT == 128 ? 3 : 512 / NT)) blanket_kernel(const KernelParams P) {
-    extern __shared__ double smem[];
+    extern __shared__ double smem_dyn[];
+    double *smem = smem_dyn;
+    if constexpr(SPILL) smem = P.gws + (size_t) blockIdx.x * (size_t) P.gws_stride;
     constexpr int PS = PoseStride<D>::value;
     constexpr int PW = (D == 6) ? 7 : 3; // pose words in records
     constexpr int JW = D * 2 * D;        // doubles of one edge Jacobian [Ji Jj]
     constexpr int SW = 4 * D * D;        // doubles of one 2D x 2D block
     const int tid = threadIdx.x;
 
-    uint64_t *s_rec = reinterpret_cast<uint64_t *>(smem);
+    uint64_t *s_rec_buf = reinterpret_cast<uint64_t *>(smem);
     double *s_pose = smem + P.off_pose;
     double *buf0 = smem + P.off_buf0;
     double *buf1 = smem + P.off_buf1;
@@ -290,7 +295,9 @@ __global__ void __launch_bounds__(NT, (NT >= 256) ? 1 : (NT == 128 ? 3 : 512 / N
 
         long long t_last = clock64();
         // ---- S0: stage the record in shared memory, expand poses ---------------------------------
-        for(int t = tid; t < rec_words; t += NT) s_rec[t] = grec[t];
+        const uint64_t *s_rec = SPILL ? grec : s_rec_buf;
+        if constexpr(!SPILL)
+            for(int t = tid; t < rec_words; t += NT) s_rec_buf[t] = grec[t];
         if(tid == 0) { s_misc[0] = SPG_BLANKET_OK; s_misc[1] = 0; }
         gsync<NT>();
         const double *r_pose = reinterpret_cast<const double *>(s_rec + spgr_poses_off(nv));

@@ -30,6 +30,8 @@ struct KernelParams {
     int32_t off_glc, glc_doubles; // GLC scratch (only for algorithm == SPG_ALG_GLC launches)
     double *nfr_ws;               // per-CTA workspace of the iterative NFR fit (global memory)
     int64_t nfr_ws_stride;        // doubles per CTA
+    double *gws;                  // spill variant: per-CTA slice holding the whole buffer plan (global memory)
+    int64_t gws_stride;           // doubles per CTA
     unsigned long long *prof;     // optional: 16 per-stage cycle accumulators (thread 0 of every CTA)
 };
 

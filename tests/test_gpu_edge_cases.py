@@ -1,0 +1,159 @@
+"""GPU edge cases (-m gpu): the situations the reference's data and code paths contain beyond the
+regular sweep — empty rounds, parallel (duplicate) edges, several removed vertices in one blanket
+(Dense / CliqueyDense extended blankets), weakly
+constrained blankets (chooseDimensions branch of logdet_function.cpp:42-60) and non-PD marginals."""
+import numpy as np
+import pytest
+
+from sparsifyposegraph_b200 import records as R
+from sparsifyposegraph_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from sparsifyposegraph_b200 import capi
+    c = capi.Context(0)
+    yield c
+    c.close()
+
+
+def rel(a, b):
+    nb = np.linalg.norm(b)
+    return np.linalg.norm(a - b) / (nb if nb > 0 else 1.0)
+
+
+def both(ctx, oracle, dim, recs, nks, algorithm, topology, flags=0):
+    from sparsifyposegraph_b200 import capi
+    records, rec_off = R.concat_records(recs)
+    out_off = R.out_offsets(dim, algorithm, topology, 1.0, nks)
+    ro = oracle.remove_round(dim, algorithm, oracle.make_opts(topology, 1), records, rec_off, out_off, 0)[0]
+    go = ctx.remove_round(dim, algorithm, capi.make_opts(topology, 1, flags=flags), records, rec_off, out_off)[0]
+    res = []
+    for b, nk in enumerate(nks):
+        res.append((R.parse_out(go, out_off, b, dim, algorithm, topology, nk),
+                    R.parse_out(ro, out_off, b, dim, algorithm, topology, nk)))
+    return res
+
+
+def se3_edge(rng, poses, i, j, info=None, noise=(0.05, 0.02)):
+    z = synth.se3_compose(synth.se3_compose(synth.se3_inverse(poses[i]), poses[j]),
+                          synth.se3_exp_small(rng, (), noise[0], noise[1]))
+    return {"kind": 0, "v": [i, j], "meas": z, "info": synth.random_info(rng, (), 6) if info is None else info}
+
+
+def test_empty_round(ctx):
+    from sparsifyposegraph_b200 import capi
+    out, _, _ = ctx.remove_round(6, R.ALG_NFR, capi.make_opts(0, 1), np.zeros(0, np.uint64), np.zeros(1, np.int64),
+                                 np.zeros(1, np.int64))
+    assert len(out) == 0
+
+
+def test_parallel_duplicate_edges(ctx, oracle):
+    """manhattan / intel contain duplicated vertex pairs: H simply sums them."""
+    rng = np.random.default_rng(1)
+    recs = []
+    for _ in range(8):
+        poses = synth.random_poses(rng, (5,), 6)
+        edges = [se3_edge(rng, poses, 0, i) for i in range(1, 5)]
+        edges += [se3_edge(rng, poses, 0, 2), se3_edge(rng, poses, 0, 2), se3_edge(rng, poses, 1, 3), se3_edge(rng, poses, 1, 3)]
+        recs.append(R.pack_blanket(6, [7, 2, 4, 9, 11], poses, edges))
+    for g, r in both(ctx, oracle, 6, recs, [4] * 8, R.ALG_NFR, R.TOPO_TREE):
+        assert g["status"] == r["status"] == 0
+        assert [e["v"] for e in g["edges"]] == [e["v"] for e in r["edges"]]
+        for eg, er in zip(g["edges"], r["edges"]):
+            assert rel(eg["info"], er["info"]) <= 1e-9
+
+
+@pytest.mark.parametrize("algorithm,topology", [(R.ALG_NFR, R.TOPO_TREE), (R.ALG_GLC, R.TOPO_DENSE), (R.ALG_GLC, R.TOPO_TREE)])
+def test_several_removed_vertices(ctx, oracle, algorithm, topology):
+    """Extended blankets (vertex_remover.cpp:93-95,142-195): m = d * #removed."""
+    rng = np.random.default_rng(2)
+    recs, nks = [], []
+    for nrem in (2, 3):
+        for _ in range(4):
+            nk = 4
+            n = nrem + nk
+            poses = synth.random_poses(rng, (n,), 6)
+            edges = [se3_edge(rng, poses, i, i + 1) for i in range(nrem - 1)]          # chain of removed vertices
+            edges += [se3_edge(rng, poses, rng.integers(0, nrem), nrem + j) for j in range(nk)]
+            edges += [se3_edge(rng, poses, nrem + j, nrem + (j + 1) % nk) for j in range(nk)]
+            edges += [se3_edge(rng, poses, 0, nrem + 1)]
+            recs.append(R.pack_blanket(6, list(range(100, 100 + n)), poses, edges, n_removed=nrem))
+            nks.append(nk)
+    for g, r in both(ctx, oracle, 6, recs, nks, algorithm, topology):
+        assert g["status"] == r["status"] == 0
+        assert g["n_edges"] == r["n_edges"]
+        for eg, er in zip(g["edges"], r["edges"]):
+            assert eg["v"] == er["v"]
+            if algorithm == R.ALG_NFR:
+                assert rel(eg["info"], er["info"]) <= 1e-9
+            else:
+                assert eg["rank"] == er["rank"]
+                assert rel(eg["W"].T @ eg["W"], er["W"].T @ er["W"]) <= 1e-9
+
+
+def test_weak_blanket_takes_choose_dimensions_branch(ctx, oracle):
+    """More than d eigenvalues below the 1e-5 cutoff (an almost unconstrained kept vertex): the reference
+    switches to chooseDimensions (logdet_function.cpp:42-60). The gauge shortcut must refuse the blanket
+    and the eigen path must reproduce the oracle."""
+    rng = np.random.default_rng(4)
+    recs = []
+    for _ in range(6):
+        poses = synth.random_poses(rng, (5,), 6)
+        edges = [se3_edge(rng, poses, 0, i) for i in range(1, 4)]
+        edges.append(se3_edge(rng, poses, 0, 4, info=3e-6 * np.eye(6)))     # vertex 4 hangs on a 3e-6 thread
+        edges.append(se3_edge(rng, poses, 1, 2))
+        recs.append(R.pack_blanket(6, [9, 2, 4, 6, 8], poses, edges))
+    for flags in (0, 1):
+        for g, r in both(ctx, oracle, 6, recs, [4] * 6, R.ALG_NFR, R.TOPO_TREE, flags=flags):
+            assert g["status"] == r["status"] == 0
+            assert [e["v"] for e in g["edges"]] == [e["v"] for e in r["edges"]]
+            for eg, er in zip(g["edges"], r["edges"]):
+                assert rel(eg["info"], er["info"]) <= 1e-6, rel(eg["info"], er["info"])
+
+
+def test_not_positive_definite_marginal_is_reported(ctx, oracle):
+    """A removed vertex without information: LLT(Lambda_mm) fails in the reference (garbage follows); here
+    the blanket is flagged and produces no edges instead of asserting."""
+    rng = np.random.default_rng(5)
+    poses = synth.random_poses(rng, (4,), 6)
+    edges = [se3_edge(rng, poses, 0, i, info=np.zeros((6, 6))) for i in range(1, 4)]
+    edges.append(se3_edge(rng, poses, 1, 2))
+    recs = [R.pack_blanket(6, [5, 1, 2, 3], poses, edges)]
+    (g, r), = both(ctx, oracle, 6, recs, [3], R.ALG_NFR, R.TOPO_TREE)
+    assert g["status"] == R.__dict__.get("ST_NOT_PD", 1) == r["status"]
+    assert g["n_edges"] == 0
+
+
+def test_se2_large_blanket(ctx, oracle):
+    """intel-sized SE2 blankets (up to 14 vertices in the first round)."""
+    blk = synth.make_blankets(14, 16, dim=3, variant="ring", seed=77)
+    nk = R.n_kept_of(blk["records"], blk["rec_off"])
+    recs = [blk["records"][blk["rec_off"][b]:blk["rec_off"][b + 1]] for b in range(16)]
+    for alg, topo in ((R.ALG_NFR, R.TOPO_TREE), (R.ALG_GLC, R.TOPO_TREE)):
+        for g, r in both(ctx, oracle, 3, recs, list(nk), alg, topo):
+            assert g["status"] == r["status"] == 0
+            assert [e["v"] for e in g["edges"]] == [e["v"] for e in r["edges"]]
+
+
+@pytest.mark.parametrize("dim,n", [(6, 24), (6, 40), (3, 48), (3, 100)])
+@pytest.mark.parametrize("algorithm,topology", [(R.ALG_NFR, R.TOPO_TREE), (R.ALG_GLC, R.TOPO_TREE), (R.ALG_GLC, R.TOPO_DENSE)])
+def test_blankets_beyond_shared_memory(ctx, oracle, dim, n, algorithm, topology):
+    """Blankets whose working set exceeds the 227 KB of shared memory (SE3 > 19, SE2 > 39 vertices; the hubs
+    of intel / sphere under Dense topologies) run the same kernel over a global-memory workspace."""
+    nb = 3
+    blk = synth.make_blankets(n, nb, dim=dim, variant="ring", seed=n)
+    nk = R.n_kept_of(blk["records"], blk["rec_off"])
+    recs = [blk["records"][blk["rec_off"][b]:blk["rec_off"][b + 1]] for b in range(nb)]
+    for g, r in both(ctx, oracle, dim, recs, list(nk), algorithm, topology):
+        assert g["status"] == r["status"] == 0
+        assert g["n_edges"] == r["n_edges"]
+        for eg, er in zip(g["edges"], r["edges"]):
+            assert eg["v"] == er["v"]
+            if algorithm == R.ALG_NFR:
+                assert rel(eg["info"], er["info"]) <= 1e-9
+            else:
+                assert eg["rank"] == er["rank"]
+                assert rel(eg["W"].T @ eg["W"], er["W"].T @ er["W"]) <= 1e-9

@@ -102,3 +102,19 @@ def test_glc_dense_isolated_removals(ctx, oracle):
     assert st["n_failed"] == 0
     worst = compare_graphs(g, o, tol=1e-8)
     print(f"intel GLC dense: {st['n_blankets']} blankets, {st['n_rounds']} rounds, max blanket {st['max_blanket_vertices']}, worst {worst:.2e}")
+
+
+@pytest.mark.parametrize("name", ["intel", "manhattan"])
+def test_glc_dense_global_decimation(ctx, oracle, name):
+    """GLC Dense with every 2nd vertex removed: n-ary factors of up to 43 (intel) / 29 (manhattan) vertices;
+    the largest blankets exceed shared memory and take the global-workspace variant of the kernel."""
+    from sparsifyposegraph_b200 import capi
+    g = capi.Graph(datasets.path(name))
+    o = oracle.Graph(datasets.path(name))
+    last = g.max_vertex_id
+    which = capi.decimate_global(last, last, 2)
+    st = g.marginalize(ctx, which, capi.make_opts(R.TOPO_DENSE, R.LIN_GLOBAL), R.ALG_GLC)
+    assert o.marginalize(which, oracle.make_opts(R.TOPO_DENSE, R.LIN_GLOBAL), R.ALG_GLC) == 0
+    assert st["n_failed"] == 0
+    worst = compare_graphs(g, o, tol=1e-7)
+    print(f"{name} GLC dense: {st['n_blankets']} blankets, {st['n_rounds']} rounds, max blanket {st['max_blanket_vertices']}, worst {worst:.2e}")
