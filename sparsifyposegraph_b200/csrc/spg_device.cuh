@@ -337,6 +337,95 @@ __device__ void chol_inverse_inplace(double *L, int n, int ld, double *Y) {
     gsync<NT>();
 }
 
+// 1/x for a normal, positive x: MUFU.RCP64H seed + two Newton steps (<= 1 ulp). The IEEE division of
+// CUDA costs ~140 cycles on the critical path of a pivot step, this one ~70.
+__device__ __forceinline__ double fast_rcp(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
+
+// One pivot step of the register-tiled sweep (see sweep_spd). C0 = register row/column of the pivot.
+template <int T, int TS, int C0>
+__device__ __forceinline__ void sweep_step(double (&a)[TS][TS], double *colbuf, int jj, int nsweep, int tx, int ty, bool &bad) {
+    constexpr int NP = T * TS;
+    constexpr int cstride = NP + 2;
+    const int j = jj + T * C0;
+    const double *col = colbuf + (j & 1) * cstride;
+    double *ncol = colbuf + ((j + 1) & 1) * cstride;
+    const double d = col[NP], inv = col[NP + 1];
+    bad |= !(d > 0);
+    double ci[TS], cl[TS];
+#pragma unroll
+    for(int r = 0; r < TS; r++) {
+        ci[r] = col[tx + T * r];
+        cl[r] = col[ty + T * r] * inv;
+    }
+    const bool rowj = (tx == jj), colj = (ty == jj);
+    const bool wrap = (jj + 1 == T);
+    const bool more = (j + 1 < nsweep);
+    constexpr int CN = (C0 + 1) % TS;
+    // look-ahead: the next pivot column (register column C0, or C0 + 1 at the end of a block) is updated
+    // and published first, so that the store -> barrier -> load latency hides behind the bulk of the tile
+    if(!wrap) {
+#pragma unroll
+        for(int r = 0; r < TS; r++) a[r][C0] -= ci[r] * cl[C0];
+        if(rowj) a[C0][C0] = cl[C0];
+        if(colj) { // this thread's register column C0 is matrix column j itself
+#pragma unroll
+            for(int r = 0; r < TS; r++) a[r][C0] = ci[r] * inv;
+            if(rowj) a[C0][C0] = -inv;
+        }
+        if(more && ty == jj + 1) {
+#pragma unroll
+            for(int r = 0; r < TS; r++) ncol[tx + T * r] = a[r][C0];
+            if(tx == jj + 1) { ncol[NP] = a[C0][C0]; ncol[NP + 1] = fast_rcp(a[C0][C0]); }
+        }
+    } else if(C0 + 1 < TS) {
+#pragma unroll
+        for(int r = 0; r < TS; r++) a[r][CN] -= ci[r] * cl[CN];
+        if(rowj) a[C0][CN] = cl[CN];
+        if(more && ty == 0) {
+#pragma unroll
+            for(int r = 0; r < TS; r++) ncol[tx + T * r] = a[r][CN];
+            if(tx == 0) { ncol[NP] = a[CN][CN]; ncol[NP + 1] = fast_rcp(a[CN][CN]); }
+        }
+    }
+#pragma unroll
+    for(int c = 0; c < TS; c++) {
+        const bool done_ahead = (!wrap && c == C0) || (wrap && c == C0 + 1);
+        if(!done_ahead) {
+#pragma unroll
+            for(int r = 0; r < TS; r++) a[r][c] -= ci[r] * cl[c];
+            if(rowj) a[C0][c] = cl[c];
+        }
+    }
+    if(wrap && colj) { // column j lives in register column C0 and was updated in the bulk
+#pragma unroll
+        for(int r = 0; r < TS; r++) a[r][C0] = ci[r] * inv;
+        if(rowj) a[C0][C0] = -inv;
+    }
+}
+
+// Blocks C0, C0 + 1, ... of T pivots each: the register index of the pivot row/column is a template
+// constant, so the tile never leaves the register file; the jj loop is not unrolled (a fully unrolled
+// sweep of T*TS steps thrashes the instruction cache).
+template <int NT, int T, int TS, int C0>
+__device__ __forceinline__ void sweep_blocks(double (&a)[TS][TS], double *colbuf, int nsweep, int tx, int ty, bool active, bool &bad) {
+    if constexpr(C0 < TS) {
+        const int jjmax = min(T, nsweep - T * C0); // uniform; <= 0: nothing left
+#pragma unroll 1
+        for(int jj = 0; jj < jjmax; jj++) {
+            if(active) sweep_step<T, TS, C0>(a, colbuf, jj, nsweep, tx, ty, bad);
+            gsync<NT>();
+        }
+        sweep_blocks<NT, T, TS, C0 + 1>(a, colbuf, nsweep, tx, ty, active, bad);
+    }
+}
+
 // Register-tiled symmetric sweep (Gauss-Jordan on an SPD matrix, no pivoting): sweeps the first
 // `nsweep` pivots of the n x n matrix A (shared memory, ld) in place.
 //   nsweep == n : A <- A^-1
@@ -344,18 +433,22 @@ __device__ void chol_inverse_inplace(double *L, int n, int ld, double *Y) {
 //                 first m rows/columns hold sweep by-products and must be ignored.
 // Every thread of a T x T grid keeps a TS x TS cyclic tile of A in registers for the whole sweep;
 // per step only the pivot column travels through shared memory (double-buffered in `colbuf`,
-// 2*n doubles) and one barrier is needed. Pivots are the Schur-complement diagonals (= squared
-// Cholesky pivots), so "pivot > 0" is the same positive-definiteness test as LLT's.
+// 2 * (T*TS + 2) doubles) and one barrier is needed. Pivots are the Schur-complement diagonals
+// (= squared Cholesky pivots), so "pivot > 0" is the same positive-definiteness test as LLT's; a
+// non-positive pivot is remembered and reported at the end (the arithmetic in between is discarded).
 // Requires T*T <= NT and n <= T*TS. Returns false (uniformly) on a non-positive pivot.
+// Measured (tools/sweep_bench.cu, B200): ~700 cycles per pivot step at every tile shape: operand
+// delivery through shared memory (24 wavefronts per warp and step) plus the FP64 issue slots, not latency —
+// sharing the barriers between two independent sweeps gains 4 %, deferring the rank-T update into the
+// next block's bubbles or handing the pivot columns to a dedicated warp is slower. See DESIGN.md.
 template <int NT, int T, int TS>
 __device__ __noinline__ bool sweep_spd(double *A, int n, int ld, int nsweep, double *colbuf) {
     static_assert(T * T <= NT, "thread grid larger than the CTA");
     const int tid = threadIdx.x;
     const bool active = tid < T * T;
     const int tx = tid % T, ty = (tid / T) % T;
-    // colbuf: two slots of (n + 2) doubles: the pivot column, then the pivot d and 1/d
     constexpr int NP = T * TS;      // padded length: loads / stores of the pivot column need no bounds checks
-    const int cstride = NP + 2;
+    constexpr int cstride = NP + 2; // the pivot column, then the pivot d and 1/d
     for(int t = n + tid; t < NP; t += NT) { colbuf[t] = 0.0; colbuf[cstride + t] = 0.0; }
     double a[TS][TS];
 #pragma unroll
@@ -369,80 +462,12 @@ __device__ __noinline__ bool sweep_spd(double *A, int n, int ld, int nsweep, dou
     if(active && ty == 0) {
 #pragma unroll
         for(int r = 0; r < TS; r++) colbuf[tx + T * r] = a[r][0];
-        if(tx == 0) { colbuf[NP] = a[0][0]; colbuf[NP + 1] = 1.0 / a[0][0]; }
+        if(tx == 0) { colbuf[NP] = a[0][0]; colbuf[NP + 1] = fast_rcp(a[0][0]); }
     }
     gsync<NT>();
-    bool ok = true;
-    // Step j = jj + T*c0 sweeps pivot j. The register index of row/column j (c0) is a compile-time
-    // constant inside the unrolled c0 loop, so the tile never leaves the register file. Look-ahead:
-    // the next pivot column (and 1/pivot) is updated first and published before the bulk of the
-    // tile update, so the store -> barrier -> load latency and the division hide behind the FMAs.
-#pragma unroll
-    for(int c0 = 0; c0 < TS; c0++) {
-        const int jjmax = min(T, nsweep - T * c0); // uniform; <= 0: nothing left in this block
-#pragma unroll 1 // keep the step body at TS copies: a fully unrolled sweep (T*TS steps) thrashes the I-cache
-        for(int jj = 0; jj < jjmax; jj++) {
-            const int j = jj + T * c0;
-            const double *col = colbuf + (j & 1) * cstride;
-            double *ncol = colbuf + ((j + 1) & 1) * cstride;
-            const double d = col[NP], inv = col[NP + 1];
-            if(!(d > 0)) ok = false; // uniform: every thread reads the same pivot
-            if(ok && active) {
-                double ci[TS], cl[TS];
-#pragma unroll
-                for(int r = 0; r < TS; r++) {
-                    ci[r] = col[tx + T * r];
-                    cl[r] = col[ty + T * r] * inv;
-                }
-                const bool rowj = (tx == jj), colj = (ty == jj);
-                const bool wrap = (jj + 1 == T);
-                const bool more = (j + 1 < nsweep);
-                // ---- look-ahead column: register column c0 (same block) or c0 + 1 (wrap) ----
-                if(!wrap) {
-#pragma unroll
-                    for(int r = 0; r < TS; r++) a[r][c0] -= ci[r] * cl[c0];
-                    if(rowj) a[c0][c0] = cl[c0];
-                    if(colj) { // this thread's register column c0 is matrix column j itself
-#pragma unroll
-                        for(int r = 0; r < TS; r++) a[r][c0] = ci[r] * inv;
-                        if(rowj) a[c0][c0] = -inv;
-                    }
-                    if(more && ty == jj + 1) {
-#pragma unroll
-                        for(int r = 0; r < TS; r++) ncol[tx + T * r] = a[r][c0];
-                        if(tx == jj + 1) { ncol[NP] = a[c0][c0]; ncol[NP + 1] = 1.0 / a[c0][c0]; }
-                    }
-                } else if(c0 + 1 < TS) {
-                    constexpr int dummy = 0; (void) dummy;
-#pragma unroll
-                    for(int r = 0; r < TS; r++) a[r][(c0 + 1) % TS] -= ci[r] * cl[(c0 + 1) % TS];
-                    if(rowj) a[c0][(c0 + 1) % TS] = cl[(c0 + 1) % TS];
-                    if(more && ty == 0) {
-#pragma unroll
-                        for(int r = 0; r < TS; r++) ncol[tx + T * r] = a[r][(c0 + 1) % TS];
-                        if(tx == 0) { ncol[NP] = a[(c0 + 1) % TS][(c0 + 1) % TS]; ncol[NP + 1] = 1.0 / a[(c0 + 1) % TS][(c0 + 1) % TS]; }
-                    }
-                }
-                // ---- bulk of the tile ----
-#pragma unroll
-                for(int c = 0; c < TS; c++) {
-                    const bool done_ahead = (!wrap && c == c0) || (wrap && c == c0 + 1);
-                    if(!done_ahead) {
-#pragma unroll
-                        for(int r = 0; r < TS; r++) a[r][c] -= ci[r] * cl[c];
-                        if(rowj) a[c0][c] = cl[c];
-                    }
-                }
-                if(wrap && colj) { // column j lives in register column c0 and was updated in the bulk
-#pragma unroll
-                    for(int r = 0; r < TS; r++) a[r][c0] = ci[r] * inv;
-                    if(rowj) a[c0][c0] = -inv;
-                }
-            }
-            gsync<NT>();
-        }
-    }
-    if(!ok) return false;
+    bool bad = false;
+    sweep_blocks<NT, T, TS, 0>(a, colbuf, nsweep, tx, ty, active, bad);
+    if(gsync_or<NT>(bad)) return false;
     // full sweep leaves -A^-1; a partial sweep leaves the Schur complement in the trailing block
     const double sgn = (nsweep >= n) ? -1.0 : 1.0;
 #pragma unroll

@@ -1,0 +1,945 @@
+// sweep_bench.cu — micro-benchmark of the register-tiled symmetric sweep (spg_device.cuh: sweep_spd) and of
+// diagnostic variants that knock out one cost at a time (division, barrier, pivot row/column fix-ups, FMAs).
+// Variants > 0 produce wrong numbers on purpose; they only answer "what does a pivot step pay for".
+//   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -o tools/build/sweep_bench tools/sweep_bench.cu
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "../sparsifyposegraph_b200/csrc/spg_device.cuh"
+
+using namespace spg;
+
+template <int NT, int T, int TS, int VAR>
+__device__ __noinline__ bool sweep_var(double *A, int n, int ld, int nsweep, double *colbuf) {
+    const int tid = threadIdx.x;
+    const bool active = tid < T * T;
+    const int tx = tid % T, ty = (tid / T) % T;
+    constexpr int NP = T * TS;
+    const int cstride = NP + 2;
+    for(int t = n + tid; t < NP; t += NT) { colbuf[t] = 0.0; colbuf[cstride + t] = 0.0; }
+    double a[TS][TS];
+#pragma unroll
+    for(int c = 0; c < TS; c++)
+#pragma unroll
+        for(int r = 0; r < TS; r++) {
+            const int i = tx + T * r, l = ty + T * c;
+            a[r][c] = (active && i < n && l < n) ? A[i + l * ld] : 0.0;
+        }
+    if(active && ty == 0) {
+#pragma unroll
+        for(int r = 0; r < TS; r++) colbuf[tx + T * r] = a[r][0];
+        if(tx == 0) { colbuf[NP] = a[0][0]; colbuf[NP + 1] = 1.0 / a[0][0]; }
+    }
+    gsync<NT>();
+    bool ok = true;
+#pragma unroll
+    for(int c0 = 0; c0 < TS; c0++) {
+        const int jjmax = min(T, nsweep - T * c0);
+#pragma unroll 1
+        for(int jj = 0; jj < jjmax; jj++) {
+            const int j = jj + T * c0;
+            const double *col = colbuf + (j & 1) * cstride;
+            double *ncol = colbuf + ((j + 1) & 1) * cstride;
+            const double d = col[NP], inv = col[NP + 1];
+            if(VAR != 5 && !(d > 0)) ok = false;
+            if(ok && active) {
+                double ci[TS], cl[TS];
+#pragma unroll
+                for(int r = 0; r < TS; r++) {
+                    ci[r] = col[tx + T * r];
+                    cl[r] = col[ty + T * r] * inv;
+                }
+                const bool rowj = (VAR == 3) ? false : (tx == jj), colj = (VAR == 3) ? false : (ty == jj);
+                const bool wrap = (jj + 1 == T);
+                const bool more = (j + 1 < nsweep);
+                if(!wrap) {
+#pragma unroll
+                    for(int r = 0; r < TS; r++) a[r][c0] -= ci[r] * cl[c0];
+                    if(rowj) a[c0][c0] = cl[c0];
+                    if(colj) {
+#pragma unroll
+                        for(int r = 0; r < TS; r++) a[r][c0] = ci[r] * inv;
+                        if(rowj) a[c0][c0] = -inv;
+                    }
+                    if(more && ty == jj + 1) {
+#pragma unroll
+                        for(int r = 0; r < TS; r++) ncol[tx + T * r] = a[r][c0];
+                        if(tx == jj + 1) { ncol[NP] = a[c0][c0]; ncol[NP + 1] = (VAR == 1) ? 1e-3 : 1.0 / a[c0][c0]; }
+                    }
+                } else if(c0 + 1 < TS) {
+#pragma unroll
+                    for(int r = 0; r < TS; r++) a[r][(c0 + 1) % TS] -= ci[r] * cl[(c0 + 1) % TS];
+                    if(rowj) a[c0][(c0 + 1) % TS] = cl[(c0 + 1) % TS];
+                    if(more && ty == 0) {
+#pragma unroll
+                        for(int r = 0; r < TS; r++) ncol[tx + T * r] = a[r][(c0 + 1) % TS];
+                        if(tx == 0) { ncol[NP] = a[(c0 + 1) % TS][(c0 + 1) % TS]; ncol[NP + 1] = (VAR == 1) ? 1e-3 : 1.0 / a[(c0 + 1) % TS][(c0 + 1) % TS]; }
+                    }
+                }
+                if(VAR != 4) {
+#pragma unroll
+                    for(int c = 0; c < TS; c++) {
+                        const bool done_ahead = (!wrap && c == c0) || (wrap && c == c0 + 1);
+                        if(!done_ahead) {
+#pragma unroll
+                            for(int r = 0; r < TS; r++) a[r][c] -= ci[r] * cl[c];
+                            if(rowj) a[c0][c] = cl[c];
+                        }
+                    }
+                }
+                if(wrap && colj) {
+#pragma unroll
+                    for(int r = 0; r < TS; r++) a[r][c0] = ci[r] * inv;
+                    if(rowj) a[c0][c0] = -inv;
+                }
+            }
+            if(VAR != 2) gsync<NT>();
+        }
+    }
+    if(!ok) return false;
+    const double sgn = (nsweep >= n) ? -1.0 : 1.0;
+#pragma unroll
+    for(int c = 0; c < TS; c++)
+#pragma unroll
+        for(int r = 0; r < TS; r++) {
+            const int i = tx + T * r, l = ty + T * c;
+            if(active && i < n && l < n) A[i + l * ld] = sgn * a[r][c];
+        }
+    gsync<NT>();
+    return true;
+}
+
+
+// ---- two-phase (panel + deferred trailing update) sweep -------------------------------------------------
+__device__ long long g_prof[8];
+template <int NT, int T, int TS, int VAR = 10>
+__device__ __noinline__ bool sweep_spd2(double *A, int n, int ld, int nsweep, double *panel) {
+    long long tp0 = clock64(), tp1;
+#define PROF(i) do { if(threadIdx.x == 0 && blockIdx.x == 0) { tp1 = clock64(); g_prof[i] += tp1 - tp0; tp0 = tp1; } } while(0)
+    const int tid = threadIdx.x;
+    const bool active = tid < T * T;
+    const int tx = tid % T, ty = (tid / T) % T;
+    constexpr int NP = T * TS, CS = NP + 2;
+    if(n < NP)
+        for(int t = tid; t < 2 * T * (NP - n); t += NT) panel[(t / (NP - n)) * CS + n + t % (NP - n)] = 0.0;
+    double a[TS][TS];
+#pragma unroll
+    for(int c = 0; c < TS; c++)
+#pragma unroll
+        for(int r = 0; r < TS; r++) {
+            const int i = tx + T * r, l = ty + T * c;
+            a[r][c] = (active && i < n && l < n) ? A[i + l * ld] : 0.0;
+        }
+    bool ok = true;
+    PROF(0);
+#pragma unroll
+    for(int c0 = 0; c0 < TS; c0++) {
+        const int jjmax = min(T, nsweep - T * c0); // uniform
+        if(jjmax > 0) {
+            double *pan = panel + (c0 & 1) * (T * CS);
+            if(active && ty == 0) {
+#pragma unroll
+                for(int r = 0; r < TS; r++) pan[tx + T * r] = a[r][c0];
+                if(tx == 0) { pan[NP] = a[c0][c0]; pan[NP + 1] = 1.0 / a[c0][c0]; }
+            }
+            gsync<NT>();
+            // phase 1: the T pivot columns of this block (register column c0 of every thread)
+#pragma unroll 1
+            for(int jj = 0; jj < jjmax; jj++) {
+                const double *col = pan + jj * CS;
+                const double d = col[NP], inv = col[NP + 1];
+                if(VAR < 13 && !(d > 0)) ok = false;
+                if(VAR != 15 && ok && active) {
+                    const double clc = col[ty + T * c0] * inv;
+                    double ci[TS];
+#pragma unroll
+                    for(int r = 0; r < TS; r++) ci[r] = col[tx + T * r];
+                    const bool rowj = (tx == jj), colj = (ty == jj);
+#pragma unroll
+                    for(int r = 0; r < TS; r++) a[r][c0] -= ci[r] * clc;
+                    if(rowj) a[c0][c0] = clc;
+                    if(colj) {
+#pragma unroll
+                        for(int r = 0; r < TS; r++) a[r][c0] = ci[r] * inv;
+                        if(rowj) a[c0][c0] = -inv;
+                    }
+                    if(VAR != 14 && jj + 1 < jjmax && ty == jj + 1) {
+                        double *ncol = pan + (jj + 1) * CS;
+#pragma unroll
+                        for(int r = 0; r < TS; r++) ncol[tx + T * r] = a[r][c0];
+                        if(tx == jj + 1) { ncol[NP] = a[c0][c0]; ncol[NP + 1] = (VAR == 13) ? 1e-2 : 1.0 / a[c0][c0]; }
+                    }
+                }
+                if(VAR != 12 && jj + 1 < jjmax) gsync<NT>();
+            }
+            PROF(1);
+            // phase 2: deferred update of the other register columns, no barriers
+            if(VAR != 11 && ok && active) {
+#pragma unroll 1
+                for(int jj = 0; jj < jjmax; jj++) {
+                    const double *col = pan + jj * CS;
+                    const double inv = col[NP + 1];
+                    double ci[TS];
+#pragma unroll
+                    for(int r = 0; r < TS; r++) ci[r] = col[tx + T * r];
+                    const bool rowj = (tx == jj);
+#pragma unroll
+                    for(int c = 0; c < TS; c++) {
+                        if(c != c0) {
+                            const double clc = col[ty + T * c] * inv;
+#pragma unroll
+                            for(int r = 0; r < TS; r++) a[r][c] -= ci[r] * clc;
+                            if(rowj) a[c0][c] = clc;
+                        }
+                    }
+                }
+            }
+            PROF(2);
+        }
+    }
+    if(!ok) return false; // uniform
+    const double sgn = (nsweep >= n) ? -1.0 : 1.0;
+#pragma unroll
+    for(int c = 0; c < TS; c++)
+#pragma unroll
+        for(int r = 0; r < TS; r++) {
+            const int i = tx + T * r, l = ty + T * c;
+            if(active && i < n && l < n) A[i + l * ld] = sgn * a[r][c];
+        }
+    gsync<NT>();
+    PROF(3);
+    return true;
+}
+
+// ---- v3: two-phase, branch-free panel, fast reciprocal, packed panel columns (128-bit smem accesses) ------
+__device__ __forceinline__ double fast_rcp(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
+
+template <int NT, int T, int TS, int VAR = 20>
+__device__ __noinline__ bool sweep_spd3(double *A, int n, int ld, int nsweep, double *panel) {
+    long long tp0 = clock64(), tp1;
+    const int tid = threadIdx.x;
+    constexpr bool ALL = (NT == T * T);
+    const bool active = ALL || tid < T * T;
+    const int tx = tid % T, ty = (tid / T) % T;
+    constexpr int TSP = (TS + 1) & ~1;          // packed column: row i = tx + T r lives at tx * TSP + r
+    constexpr int NP = T * TSP, CS = NP + 2;    // + pivot d and 1/d
+    for(int t = tid; t < 2 * T * CS; t += NT) panel[t] = 0.0;
+    double a[TS][TS];
+#pragma unroll
+    for(int c = 0; c < TS; c++)
+#pragma unroll
+        for(int r = 0; r < TS; r++) {
+            const int i = tx + T * r, l = ty + T * c;
+            a[r][c] = (active && i < n && l < n) ? A[i + l * ld] : 0.0;
+        }
+    bool bad = false;
+    gsync<NT>();
+    PROF(0);
+    const double *my_ci = panel + tx * TSP, *my_cl = panel + ty * TSP;
+#pragma unroll
+    for(int c0 = 0; c0 < TS; c0++) {
+        const int jjmax = min(T, nsweep - T * c0); // uniform
+        if(jjmax > 0) {
+            const int poff = (c0 & 1) * (T * CS);
+            if(active && ty == 0) {
+                double *pc = panel + poff + tx * TSP;
+#pragma unroll
+                for(int r = 0; r < TS; r++) pc[r] = a[r][c0];
+                if(tx == 0) { panel[poff + NP] = a[c0][c0]; panel[poff + NP + 1] = fast_rcp(a[c0][c0]); }
+            }
+            gsync<NT>();
+            // phase 1
+#pragma unroll 1
+            for(int jj = 0; jj < jjmax; jj++) {
+                const int coff = poff + jj * CS;
+                const double d = panel[coff + NP], inv = panel[coff + NP + 1];
+                bad |= !(d > 0);
+                const double clc = my_cl[coff + c0] * inv;
+                double ci[TS];
+#pragma unroll
+                for(int r = 0; r < TS; r++) ci[r] = my_ci[coff + r];
+                const bool rowj = (tx == jj), colj = (ty == jj);
+#pragma unroll
+                for(int r = 0; r < TS; r++) {
+                    const double upd = fma(-ci[r], clc, a[r][c0]);
+                    a[r][c0] = colj ? ci[r] * inv : upd;
+                }
+                a[c0][c0] = rowj ? (colj ? -inv : clc) : a[c0][c0];
+                if(active && jj + 1 < jjmax && ty == jj + 1) {
+                    double *pc = panel + coff + CS + tx * TSP;
+#pragma unroll
+                    for(int r = 0; r < TS; r++) pc[r] = a[r][c0];
+                    if(tx == jj + 1) { panel[coff + CS + NP] = a[c0][c0]; panel[coff + CS + NP + 1] = fast_rcp(a[c0][c0]); }
+                }
+                if(jj + 1 < jjmax) gsync<NT>();
+            }
+            PROF(1);
+            // phase 2
+            if(VAR != 21) {
+                double ci[TS], cl[TS], inv;
+                {
+                    const int coff = poff;
+                    inv = panel[coff + NP + 1];
+#pragma unroll
+                    for(int r = 0; r < TS; r++) { ci[r] = my_ci[coff + r]; cl[r] = my_cl[coff + r]; }
+                }
+#pragma unroll 1
+                for(int jj = 0; jj < jjmax; jj++) {
+                    // prefetch the next step's operands (the slot after the last column is never written: zeros)
+                    const int noff = poff + (jj + 1 < jjmax ? jj + 1 : jj) * CS;
+                    double nci[TS], ncl[TS];
+                    const double ninv = panel[noff + NP + 1];
+#pragma unroll
+                    for(int r = 0; r < TS; r++) { nci[r] = my_ci[noff + r]; ncl[r] = my_cl[noff + r]; }
+                    const bool rowj = (tx == jj);
+#pragma unroll
+                    for(int c = 0; c < TS; c++) {
+                        if(c != c0) {
+                            const double clc = cl[c] * inv;
+#pragma unroll
+                            for(int r = 0; r < TS; r++) a[r][c] = fma(-ci[r], clc, a[r][c]);
+                            a[c0][c] = rowj ? clc : a[c0][c];
+                        }
+                    }
+                    inv = ninv;
+#pragma unroll
+                    for(int r = 0; r < TS; r++) { ci[r] = nci[r]; cl[r] = ncl[r]; }
+                }
+            }
+            PROF(2);
+        }
+    }
+    if(__syncthreads_or(bad)) return false;
+    const double sgn = (nsweep >= n) ? -1.0 : 1.0;
+#pragma unroll
+    for(int c = 0; c < TS; c++)
+#pragma unroll
+        for(int r = 0; r < TS; r++) {
+            const int i = tx + T * r, l = ty + T * c;
+            if(active && i < n && l < n) A[i + l * ld] = sgn * a[r][c];
+        }
+    gsync<NT>();
+    PROF(3);
+    return true;
+}
+
+// ---- v4: warp-specialised sweep. T*T tile threads keep the matrix in registers; one extra warp factors each
+// block of T pivot columns on its own (registers + shuffles, no block barriers) while the tile threads apply
+// the previous block's rank-T update. Hand-offs through two named barriers per block.
+__device__ __forceinline__ void nbar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void nbar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+template <int T, int TS>
+struct PW {
+    static constexpr int NT = T * T + 32;
+    static constexpr int NP = T * TS;                 // padded matrix dimension
+    static constexpr int TSP = (TS + 1) & ~1;         // packed column: row i = tx + T r at tx * TSP + r
+    static constexpr int NPK = T * TSP;
+    static constexpr int CS = NPK + 2;                // + pivot, 1/pivot
+    static constexpr int PS = ((NP + 15) & ~15) + 8;  // exchange buffer column stride
+    static constexpr int NSLOT = (NP + 31) / 32;
+    static constexpr int SCRATCH = T * PS + 2 * T * CS;
+};
+
+template <int T, int TS>
+__device__ __forceinline__ bool pw_panel(double *P, double *S, int c0, int jjmax, int lane) {
+    using K = PW<T, TS>;
+    double p[K::NSLOT][T];
+    int row[K::NSLOT], pk[K::NSLOT];
+    bool valid[K::NSLOT];
+#pragma unroll
+    for(int s = 0; s < K::NSLOT; s++) {
+        const int rp = lane + 32 * s; // rotated row: the block's pivot rows are rp = 0 .. T-1 (slot 0, lanes 0 .. T-1)
+        valid[s] = rp < K::NP;
+        int rr = rp + T * c0;
+        if(rr >= K::NP) rr -= K::NP;
+        row[s] = valid[s] ? rr : 0;
+        pk[s] = (row[s] % T) * K::TSP + row[s] / T;
+#pragma unroll
+        for(int l = 0; l < T; l++) p[s][l] = valid[s] ? P[l * K::PS + row[s]] : 0.0;
+    }
+    bool bad = false;
+#pragma unroll
+    for(int jj = 0; jj < T; jj++) {
+        if(jj < jjmax) { // uniform
+            double *Sj = S + jj * K::CS;
+#pragma unroll
+            for(int s = 0; s < K::NSLOT; s++)
+                if(valid[s]) Sj[pk[s]] = p[s][jj]; // column jj as it is when pivot jj is applied
+            const double d = __shfl_sync(0xffffffffu, p[0][jj], jj);
+            const double inv = fast_rcp(d);
+            bad |= !(d > 0);
+            if(lane == 0) { Sj[K::NPK] = d; Sj[K::NPK + 1] = inv; }
+            double ci[K::NSLOT];
+#pragma unroll
+            for(int s = 0; s < K::NSLOT; s++) ci[s] = p[s][jj];
+            const bool prow = (lane == jj);
+#pragma unroll
+            for(int l = 0; l < T; l++) {
+                const double clv = __shfl_sync(0xffffffffu, ci[0], l) * inv; // column entry of block row l, scaled
+#pragma unroll
+                for(int s = 0; s < K::NSLOT; s++) p[s][l] = (l == jj) ? ci[s] * inv : fma(-ci[s], clv, p[s][l]);
+                if(prow) p[0][l] = (l == jj) ? -inv : clv;
+            }
+        }
+    }
+#pragma unroll
+    for(int s = 0; s < K::NSLOT; s++)
+#pragma unroll
+        for(int l = 0; l < T; l++)
+            if(valid[s]) P[l * K::PS + row[s]] = p[s][l];
+    return bad;
+}
+
+
+template <int T, int TS, int C0, int VAR>
+__device__ __forceinline__ void pw_tile_blocks(double (&a)[TS][TS], const double *S0, double *myP, int nblk, int nsweep, int tx, int ty) {
+    using K = PW<T, TS>;
+    constexpr int NT = K::NT;
+    if constexpr(C0 < TS) {
+        if(C0 < nblk) { // uniform
+            const int jjmax = min(T, nsweep - T * C0);
+            const double *S = S0 + (C0 & 1) * (T * K::CS);
+            const double *sci = S + tx * K::TSP, *scl = S + ty * K::TSP;
+            long long w0 = clock64(), w1;
+            nbar_sync(2, NT);
+            if(threadIdx.x == 0 && blockIdx.x == 0) { w1 = clock64(); g_prof[1] += w1 - w0; w0 = w1; }
+#pragma unroll
+            for(int r = 0; r < TS; r++) a[r][C0] = myP[T * r];
+            constexpr int CN = (C0 + 1 < TS) ? C0 + 1 : C0;
+            const bool next = (C0 + 1 < TS) && (C0 + 1 < nblk);
+            if(next) {
+                // urgent: the next panel column
+#pragma unroll 2
+                for(int jj = 0; jj < jjmax; jj++) {
+                    const int off = jj * K::CS;
+                    const double clc = scl[off + CN] * S[off + K::NPK + 1];
+#pragma unroll
+                    for(int r = 0; r < TS; r++) a[r][CN] = fma(-sci[off + r], clc, a[r][CN]);
+                    a[C0][CN] = (tx == jj) ? clc : a[C0][CN];
+                }
+#pragma unroll
+                for(int r = 0; r < TS; r++) myP[T * r] = a[r][CN];
+                nbar_arrive(1, NT);
+            }
+            if(threadIdx.x == 0 && blockIdx.x == 0) { w1 = clock64(); g_prof[2] += w1 - w0; w0 = w1; }
+            // lazy: every other register column
+            if(VAR != 31) {
+#pragma unroll 1
+                for(int jj = 0; jj < jjmax; jj++) {
+                    const int off = jj * K::CS;
+                    const double inv = S[off + K::NPK + 1];
+                    double ci[TS];
+#pragma unroll
+                    for(int r = 0; r < TS; r++) ci[r] = sci[off + r];
+                    const bool rowj = (tx == jj);
+#pragma unroll
+                    for(int c = 0; c < TS; c++) {
+                        if(c != C0 && c != C0 + 1) {
+                            const double clc = scl[off + c] * inv;
+#pragma unroll
+                            for(int r = 0; r < TS; r++) a[r][c] = fma(-ci[r], clc, a[r][c]);
+                            a[C0][c] = rowj ? clc : a[C0][c];
+                        }
+                    }
+                    if(C0 + 1 < TS && !next) { // partial sweep ending here: column C0 + 1 is an ordinary trailing column
+                        const double clc = scl[off + CN] * inv;
+#pragma unroll
+                        for(int r = 0; r < TS; r++) a[r][CN] = fma(-ci[r], clc, a[r][CN]);
+                        a[C0][CN] = rowj ? clc : a[C0][CN];
+                    }
+                }
+            }
+            if(threadIdx.x == 0 && blockIdx.x == 0) { w1 = clock64(); g_prof[3] += w1 - w0; w0 = w1; }
+        }
+        pw_tile_blocks<T, TS, C0 + 1, VAR>(a, S0, myP, nblk, nsweep, tx, ty);
+    }
+}
+
+template <int T, int TS, int VAR = 30>
+__device__ __forceinline__ bool sweep_pw(double *A, int n, int ld, int nsweep, double *scratch) {
+    using K = PW<T, TS>;
+    constexpr int NT = K::NT;
+    long long tp0 = clock64(), tp1;
+    const int tid = threadIdx.x;
+    const bool tile = tid < T * T;
+    const int tx = tid % T, ty = (tid / T) % T;
+    double *P = scratch, *S0 = scratch + T * K::PS;
+    __shared__ int s_bad;
+    for(int t = tid; t < K::SCRATCH; t += NT) scratch[t] = 0.0;
+    if(tid == 0) s_bad = 0;
+    double a[TS][TS];
+    if(tile) {
+#pragma unroll
+        for(int c = 0; c < TS; c++)
+#pragma unroll
+            for(int r = 0; r < TS; r++) {
+                const int i = tx + T * r, l = ty + T * c;
+                a[r][c] = (i < n && l < n) ? A[i + l * ld] : 0.0;
+            }
+    }
+    __syncthreads();
+    PROF(0);
+    const int nblk = (nsweep + T - 1) / T;
+    if(!tile) {
+        // ---------------- panel warp ----------------
+        const int lane = tid - T * T;
+        bool bad = false;
+        long long q0 = clock64(), q1;
+        for(int c0 = 0; c0 < nblk; c0++) {
+            nbar_sync(1, NT);
+            if(lane == 0 && blockIdx.x == 0) { q1 = clock64(); g_prof[5] += q1 - q0; q0 = q1; }
+            bad |= pw_panel<T, TS>(P, S0 + (c0 & 1) * (T * K::CS), c0, min(T, nsweep - T * c0), lane);
+            __syncwarp();
+            nbar_arrive(2, NT);
+            if(lane == 0 && blockIdx.x == 0) { q1 = clock64(); g_prof[6] += q1 - q0; q0 = q1; }
+        }
+        if(bad && lane == 0) s_bad = 1;
+    } else {
+        // ---------------- tile threads ----------------
+        double *myP = P + ty * K::PS + tx;
+#pragma unroll
+        for(int r = 0; r < TS; r++) myP[T * r] = a[r][0];
+        nbar_arrive(1, NT);
+        pw_tile_blocks<T, TS, 0, VAR>(a, S0, myP, nblk, nsweep, tx, ty);
+    }
+    __syncthreads();
+    if(s_bad) return false;
+    const double sgn = (nsweep >= n) ? -1.0 : 1.0;
+    if(tile) {
+#pragma unroll
+        for(int c = 0; c < TS; c++)
+#pragma unroll
+            for(int r = 0; r < TS; r++) {
+                const int i = tx + T * r, l = ty + T * c;
+                if(i < n && l < n) A[i + l * ld] = sgn * a[r][c];
+            }
+    }
+    __syncthreads();
+    PROF(4);
+    return true;
+}
+
+// ---- v5: two-phase with the rank-T trailing update of block B deferred into the panel steps of block B+1 ----
+template <int T, int TS>
+struct V5 {
+    static constexpr int TSP = (TS + 1) & ~1;
+    static constexpr int NP = T * TSP;
+    static constexpr int CS = NP + 2;
+    static constexpr int SCRATCH = 2 * T * CS;
+};
+
+// one pivot's update of the register columns outside [B, B + SKIP] with the recorded column jj of block B
+template <int T, int TS, int B, int SKIP>
+__device__ __forceinline__ void v5_trail_step(double (&a)[TS][TS], const double *S, int jj, int tx, const double *sci, const double *scl) {
+    using K = V5<T, TS>;
+    const int off = jj * K::CS;
+    const double inv = S[off + K::NP + 1];
+    double ci[TS];
+#pragma unroll
+    for(int r = 0; r < TS; r++) ci[r] = sci[off + r];
+    const bool rowj = (tx == jj);
+#pragma unroll
+    for(int c = 0; c < TS; c++) {
+        if(c < B || c > B + SKIP) {
+            const double clc = scl[off + c] * inv;
+#pragma unroll
+            for(int r = 0; r < TS; r++) a[r][c] = fma(-ci[r], clc, a[r][c]);
+            a[B][c] = rowj ? clc : a[B][c];
+        }
+    }
+}
+
+template <int NT, int T, int TS, int C0>
+__device__ __forceinline__ void v5_blocks(double (&a)[TS][TS], double *panel, int nsweep, int tx, int ty, bool &bad) {
+    using K = V5<T, TS>;
+    if constexpr(C0 < TS) {
+        const int jjmax = min(T, nsweep - T * C0); // uniform
+        if(jjmax > 0) {
+            double *S = panel + (C0 & 1) * (T * K::CS);
+            const double *Sprev = panel + ((C0 + 1) & 1) * (T * K::CS);
+            const double *sci = S + tx * K::TSP, *scl = S + ty * K::TSP;
+            const double *pci = Sprev + tx * K::TSP, *pcl = Sprev + ty * K::TSP;
+            const int warp = threadIdx.x >> 5;
+            if(C0 > 0) gsync<NT>(); // every warp is done reading the buffer this block records into
+            if(ty == 0) {
+                double *pc = S + tx * K::TSP;
+#pragma unroll
+                for(int r = 0; r < TS; r++) pc[r] = a[r][C0];
+                if(tx == 0) { S[K::NP] = a[C0][C0]; S[K::NP + 1] = fast_rcp(a[C0][C0]); }
+            }
+            gsync<NT>();
+            int lz = 0;
+            const int lzmax = (C0 > 0) ? T : 0;
+#pragma unroll 1
+            for(int jj = 0; jj < jjmax; jj++) {
+                const int coff = jj * K::CS;
+                const double d = S[coff + K::NP], inv = S[coff + K::NP + 1];
+                bad |= !(d > 0);
+                const double clc = scl[coff + C0] * inv;
+                double ci[TS];
+#pragma unroll
+                for(int r = 0; r < TS; r++) ci[r] = sci[coff + r];
+                const bool rowj = (tx == jj), colj = (ty == jj);
+#pragma unroll
+                for(int r = 0; r < TS; r++) {
+                    const double upd = fma(-ci[r], clc, a[r][C0]);
+                    a[r][C0] = colj ? ci[r] * inv : upd;
+                }
+                a[C0][C0] = rowj ? (colj ? -inv : clc) : a[C0][C0];
+                const bool more = jj + 1 < jjmax;
+                if(more && ty == jj + 1) {
+                    double *pc = S + coff + K::CS + tx * K::TSP;
+#pragma unroll
+                    for(int r = 0; r < TS; r++) pc[r] = a[r][C0];
+                    if(tx == jj + 1) { S[coff + K::CS + K::NP] = a[C0][C0]; S[coff + K::CS + K::NP + 1] = fast_rcp(a[C0][C0]); }
+                }
+                if constexpr(C0 > 0) {
+                    // deferred trailing update of the previous block; the warp on the critical path (it publishes) skips its turn
+                    const bool pubwarp = more && (((jj + 1) * T) >> 5) == warp;
+                    if(!pubwarp) {
+#pragma unroll 1
+                        for(int q = 0; q < 2 && lz < lzmax; q++, lz++) v5_trail_step<T, TS, C0 - 1, 1>(a, Sprev, lz, tx, pci, pcl);
+                    }
+                }
+                if(more) gsync<NT>();
+            }
+            if constexpr(C0 > 0) {
+#pragma unroll 1
+                for(; lz < lzmax; lz++) v5_trail_step<T, TS, C0 - 1, 1>(a, Sprev, lz, tx, pci, pcl);
+            }
+            const bool next = (C0 + 1 < TS) && (nsweep > T * (C0 + 1));
+            if(next) {
+                if constexpr(C0 + 1 < TS) {
+                    // the next block's own register column has to be current before its panel starts
+#pragma unroll 2
+                    for(int jj = 0; jj < jjmax; jj++) {
+                        const int off = jj * K::CS;
+                        const double clc = scl[off + C0 + 1] * S[off + K::NP + 1];
+#pragma unroll
+                        for(int r = 0; r < TS; r++) a[r][C0 + 1] = fma(-sci[off + r], clc, a[r][C0 + 1]);
+                        a[C0][C0 + 1] = (tx == jj) ? clc : a[C0][C0 + 1];
+                    }
+                }
+            } else {
+#pragma unroll 1
+                for(int jj = 0; jj < jjmax; jj++) v5_trail_step<T, TS, C0, 0>(a, S, jj, tx, sci, scl);
+            }
+        }
+        v5_blocks<NT, T, TS, C0 + 1>(a, panel, nsweep, tx, ty, bad);
+    }
+}
+
+template <int NT, int T, int TS>
+__device__ __forceinline__ bool sweep_spd5(double *A, int n, int ld, int nsweep, double *panel) {
+    static_assert(NT == T * T, "one thread per tile");
+    using K = V5<T, TS>;
+    const int tid = threadIdx.x;
+    const int tx = tid % T, ty = tid / T;
+    for(int t = tid; t < K::SCRATCH; t += NT) panel[t] = 0.0;
+    double a[TS][TS];
+#pragma unroll
+    for(int c = 0; c < TS; c++)
+#pragma unroll
+        for(int r = 0; r < TS; r++) {
+            const int i = tx + T * r, l = ty + T * c;
+            a[r][c] = (i < n && l < n) ? A[i + l * ld] : 0.0;
+        }
+    bool bad = false;
+    gsync<NT>();
+    v5_blocks<NT, T, TS, 0>(a, panel, nsweep, tx, ty, bad);
+    if(__syncthreads_or(bad)) return false;
+    const double sgn = (nsweep >= n) ? -1.0 : 1.0;
+#pragma unroll
+    for(int c = 0; c < TS; c++)
+#pragma unroll
+        for(int r = 0; r < TS; r++) {
+            const int i = tx + T * r, l = ty + T * c;
+            if(i < n && l < n) A[i + l * ld] = sgn * a[r][c];
+        }
+    gsync<NT>();
+    return true;
+}
+
+// ---- v6: the baseline step as a function, so that two independent matrices can share the barriers ------------
+template <int T, int TS, int C0>
+__device__ __forceinline__ void v6_step(double (&a)[TS][TS], double *colbuf, int jj, int nsweep, int tx, int ty, bool &bad) {
+    constexpr int NP = T * TS;
+    constexpr int cstride = NP + 2;
+    const int j = jj + T * C0;
+    if(j >= nsweep) return; // uniform
+    const double *col = colbuf + (j & 1) * cstride;
+    double *ncol = colbuf + ((j + 1) & 1) * cstride;
+    const double d = col[NP], inv = col[NP + 1];
+    bad |= !(d > 0);
+    double ci[TS], cl[TS];
+#pragma unroll
+    for(int r = 0; r < TS; r++) {
+        ci[r] = col[tx + T * r];
+        cl[r] = col[ty + T * r] * inv;
+    }
+    const bool rowj = (tx == jj), colj = (ty == jj);
+    const bool wrap = (jj + 1 == T);
+    const bool more = (j + 1 < nsweep);
+    constexpr int CN = (C0 + 1) % TS;
+    if(!wrap) {
+#pragma unroll
+        for(int r = 0; r < TS; r++) a[r][C0] -= ci[r] * cl[C0];
+        if(rowj) a[C0][C0] = cl[C0];
+        if(colj) {
+#pragma unroll
+            for(int r = 0; r < TS; r++) a[r][C0] = ci[r] * inv;
+            if(rowj) a[C0][C0] = -inv;
+        }
+        if(more && ty == jj + 1) {
+#pragma unroll
+            for(int r = 0; r < TS; r++) ncol[tx + T * r] = a[r][C0];
+            if(tx == jj + 1) { ncol[NP] = a[C0][C0]; ncol[NP + 1] = fast_rcp(a[C0][C0]); }
+        }
+    } else if(C0 + 1 < TS) {
+#pragma unroll
+        for(int r = 0; r < TS; r++) a[r][CN] -= ci[r] * cl[CN];
+        if(rowj) a[C0][CN] = cl[CN];
+        if(more && ty == 0) {
+#pragma unroll
+            for(int r = 0; r < TS; r++) ncol[tx + T * r] = a[r][CN];
+            if(tx == 0) { ncol[NP] = a[CN][CN]; ncol[NP + 1] = fast_rcp(a[CN][CN]); }
+        }
+    }
+#pragma unroll
+    for(int c = 0; c < TS; c++) {
+        const bool done_ahead = (!wrap && c == C0) || (wrap && c == C0 + 1);
+        if(!done_ahead) {
+#pragma unroll
+            for(int r = 0; r < TS; r++) a[r][c] -= ci[r] * cl[c];
+            if(rowj) a[C0][c] = cl[c];
+        }
+    }
+    if(wrap && colj) {
+#pragma unroll
+        for(int r = 0; r < TS; r++) a[r][C0] = ci[r] * inv;
+        if(rowj) a[C0][C0] = -inv;
+    }
+}
+
+template <int NT, int T, int TS, int C0, bool DUAL>
+__device__ __forceinline__ void v6_blocks(double (&a)[TS][TS], double (&b)[TS][TS], double *cba, double *cbb, int nsa, int nsb, int tx, int ty, bool &bad) {
+    if constexpr(C0 < TS) {
+        const int jjmax = min(T, max(nsa, DUAL ? nsb : 0) - T * C0);
+#pragma unroll 1
+        for(int jj = 0; jj < jjmax; jj++) {
+            v6_step<T, TS, C0>(a, cba, jj, nsa, tx, ty, bad);
+            if constexpr(DUAL) v6_step<T, TS, C0>(b, cbb, jj, nsb, tx, ty, bad);
+            gsync<NT>();
+        }
+        v6_blocks<NT, T, TS, C0 + 1, DUAL>(a, b, cba, cbb, nsa, nsb, tx, ty, bad);
+    }
+}
+
+// sweeps A (na x na, all pivots) and, when DUAL, B (nb x nb, all pivots) together
+template <int NT, int T, int TS, bool DUAL>
+__device__ __forceinline__ bool sweep_v6(double *A, int na, int lda, double *B, int nb, int ldb, double *colbuf) {
+    static_assert(NT == T * T, "");
+    constexpr int NP = T * TS, cstride = NP + 2;
+    const int tid = threadIdx.x, tx = tid % T, ty = tid / T;
+    double *cba = colbuf, *cbb = colbuf + 2 * cstride;
+    for(int t = tid; t < 4 * cstride; t += NT) colbuf[t] = 0.0;
+    double a[TS][TS], b[TS][TS];
+#pragma unroll
+    for(int c = 0; c < TS; c++)
+#pragma unroll
+        for(int r = 0; r < TS; r++) {
+            const int i = tx + T * r, l = ty + T * c;
+            a[r][c] = (i < na && l < na) ? A[i + l * lda] : 0.0;
+            if(DUAL) b[r][c] = (i < nb && l < nb) ? B[i + l * ldb] : 0.0;
+        }
+    gsync<NT>();
+    if(ty == 0) {
+#pragma unroll
+        for(int r = 0; r < TS; r++) { cba[tx + T * r] = a[r][0]; if(DUAL) cbb[tx + T * r] = b[r][0]; }
+        if(tx == 0) {
+            cba[NP] = a[0][0]; cba[NP + 1] = fast_rcp(a[0][0]);
+            if(DUAL) { cbb[NP] = b[0][0]; cbb[NP + 1] = fast_rcp(b[0][0]); }
+        }
+    }
+    gsync<NT>();
+    bool bad = false;
+    v6_blocks<NT, T, TS, 0, DUAL>(a, b, cba, cbb, na, nb, tx, ty, bad);
+    if(__syncthreads_or(bad)) return false;
+#pragma unroll
+    for(int c = 0; c < TS; c++)
+#pragma unroll
+        for(int r = 0; r < TS; r++) {
+            const int i = tx + T * r, l = ty + T * c;
+            if(i < na && l < na) A[i + l * lda] = -a[r][c];
+            if(DUAL && i < nb && l < nb) B[i + l * ldb] = -b[r][c];
+        }
+    gsync<NT>();
+    return true;
+}
+
+template <int NT, int T, int TS, int VAR>
+__global__ void __launch_bounds__(NT) __maxnreg__(NT == 288 ? 168 : (NT <= 64 ? 128 : (NT <= 128 ? 168 : 255))) bench_kernel(const double *src, int n, int nsweep, int reps, long long *cycles, double *sink, double *result) {
+    extern __shared__ double sm[];
+    const int ld = odd_ld(n);
+    double *A = sm, *colbuf = sm + n * ld;
+    double *B2 = colbuf + 4 * (T * TS + 2) + 16; // second matrix of the dual variants (leading block of the same input)
+    long long total = 0;
+    double acc = 0;
+    for(int rep = 0; rep < reps; rep++) {
+        for(int t = threadIdx.x; t < n * n; t += NT) A[(t % n) + (t / n) * ld] = src[t];
+        if(VAR == 51) for(int t = threadIdx.x; t < n * n; t += NT) B2[(t % n) + (t / n) * ld] = src[t];
+        __syncthreads();
+        const long long t0 = clock64();
+        bool ok;
+        if constexpr(VAR == 0) ok = sweep_spd<NT, T, TS>(A, n, ld, nsweep, colbuf);
+        else if constexpr(VAR == 50) ok = sweep_v6<NT, T, TS, false>(A, n, ld, A, n, ld, colbuf);
+        else if constexpr(VAR == 51) ok = sweep_v6<NT, T, TS, true>(A, n, ld, B2, n - 6, ld, colbuf);
+        else if constexpr(VAR >= 40) ok = sweep_spd5<NT, T, TS>(A, n, ld, nsweep, colbuf);
+        else if constexpr(VAR >= 30) ok = sweep_pw<T, TS, VAR>(A, n, ld, nsweep, colbuf);
+        else if constexpr(VAR >= 20) ok = sweep_spd3<NT, T, TS, VAR>(A, n, ld, nsweep, colbuf);
+        else if constexpr(VAR >= 10) ok = sweep_spd2<NT, T, TS, VAR>(A, n, ld, nsweep, colbuf);
+        else ok = sweep_var<NT, T, TS, VAR>(A, n, ld, nsweep, colbuf);
+        const long long t1 = clock64();
+        total += t1 - t0;
+        acc += ok ? A[threadIdx.x % n] : 1.0;
+        if(rep == reps - 1 && blockIdx.x == 0 && result)
+            for(int t = threadIdx.x; t < n * n; t += NT) result[t] = A[(t % n) + (t / n) * ld];
+        __syncthreads();
+    }
+    if(threadIdx.x == 0) cycles[blockIdx.x] = total / reps;
+    if(acc == 1.2345) sink[0] = acc;
+}
+
+static const char *ok_note(const std::vector<double> &r) { for(double v : r) if(v != v) return "(NaN in result)"; return ""; }
+static std::vector<double> ref;
+template <int NT, int T, int TS, int VAR>
+void run(const char *name, const double *dsrc, int n, int nsweep, size_t smem_force, int ctas_per_sm) {
+    long long *dc;
+    double *dsink;
+    const int grid = 148 * ctas_per_sm;
+    cudaMalloc(&dc, grid * sizeof(long long));
+    cudaMalloc(&dsink, 8);
+    cudaFuncSetAttribute(bench_kernel<NT, T, TS, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_force);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const int reps = 20;
+    double *dres;
+    cudaMalloc(&dres, n * n * 8);
+    bench_kernel<NT, T, TS, VAR><<<grid, NT, smem_force>>>(dsrc, n, nsweep, 2, dc, dsink, dres);
+    cudaEventRecord(e0);
+    bench_kernel<NT, T, TS, VAR><<<grid, NT, smem_force>>>(dsrc, n, nsweep, reps, dc, dsink, dres);
+    cudaEventRecord(e1);
+    cudaError_t err = cudaDeviceSynchronize();
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    std::vector<long long> hc(grid);
+    cudaMemcpy(hc.data(), dc, grid * sizeof(long long), cudaMemcpyDeviceToHost);
+    std::vector<double> res(n * n);
+    cudaMemcpy(res.data(), dres, n * n * 8, cudaMemcpyDeviceToHost);
+    cudaFree(dres);
+    double diff = 0, nrm = 0;
+    if(VAR == 0) ref = res;
+    else if(ref.size() == res.size()) for(size_t i = 0; i < res.size(); i++) { diff += (res[i] - ref[i]) * (res[i] - ref[i]); nrm += ref[i] * ref[i]; }
+    double mean = 0;
+    for(long long c : hc) mean += (double) c / grid;
+    printf("%-34s NT=%3d T=%2d TS=%d n=%3d nsweep=%3d ctas/sm=%d: %9.0f cycles/sweep  %7.1f cycles/step  (%.3f ms, %s) rel.diff vs baseline %.1e\n", name, NT, T, TS, n,
+           nsweep, ctas_per_sm, mean, mean / nsweep, ms, cudaGetErrorString(err), nrm > 0 ? sqrt(diff / nrm) : -1.0);
+    if(VAR >= 10 && VAR < 40) {
+        long long hp[8];
+        cudaMemcpyFromSymbol(hp, g_prof, sizeof(hp));
+        if(VAR >= 30)
+            printf("      CTA 0, per sweep: load %lld  tile: wait-for-panel %lld  reload+urgent %lld  lazy %lld  store %lld | panel warp: wait %lld  factor %lld  %s\n", hp[0] / (reps + 2),
+                   hp[1] / (reps + 2), hp[2] / (reps + 2), hp[3] / (reps + 2), hp[4] / (reps + 2), hp[5] / (reps + 2), hp[6] / (reps + 2), ok_note(res));
+        else
+        printf("      CTA 0 thread 0, per sweep: load %lld  panel %lld  trailing %lld  store %lld  %s\n", hp[0] / (reps + 2), hp[1] / (reps + 2),
+               hp[2] / (reps + 2), hp[3] / (reps + 2), ok_note(res));
+        long long z[8] = {0};
+        cudaMemcpyToSymbol(g_prof, z, sizeof(z));
+    }
+    cudaFree(dc); cudaFree(dsink);
+}
+
+int main() {
+    const int nmax = 96;
+    std::vector<double> h(nmax * nmax);
+    // SPD: diagonally dominant
+    for(int n : {90, 42, 24}) {
+        srand(1);
+        for(int i = 0; i < n; i++)
+            for(int j = 0; j <= i; j++) {
+                double v = (i == j) ? n + 1.0 : (rand() / (double) RAND_MAX - 0.5);
+                h[i + j * n] = h[j + i * n] = v;
+            }
+        double *d;
+        cudaMalloc(&d, n * n * 8);
+        cudaMemcpy(d, h.data(), n * n * 8, cudaMemcpyHostToDevice);
+        if(n == 90 || n == 66) {
+            const size_t big = 200 * 1024;
+            run<256, 16, 6, 0>("baseline", d, n, n, big, 1);
+            run<256, 16, 6, 10>("two-phase", d, n, n, big, 1);
+            run<256, 16, 6, 50>("v6 single (function form)", d, n, n, big, 1);
+            run<256, 16, 6, 51>("v6 dual: n and n-6 together", d, n, n, big, 1);
+            run<256, 16, 6, 40>("v5 deferred trailing", d, n, n, big, 1);
+            run<256, 16, 6, 40>("v5 n=84", d, 84, 84, big, 1);
+            run<256, 16, 6, 0>("baseline n=84", d, 84, 84, big, 1);
+            run<256, 16, 6, 40>("v5 partial m=6", d, n, 6, big, 1);
+            run<256, 16, 5, 40>("v5 TS=5 n=66", d, 66, 66, big, 1);
+            run<256, 16, 5, 0>("baseline TS=5 n=66", d, 66, 66, big, 1);
+            run<256, 16, 6, 0>("baseline", d, n, n, big, 1);
+            run<288, 16, 6, 30>("v4 panel warp", d, n, n, big, 1);
+            run<288, 16, 6, 31>("v4 panel warp, no lazy", d, n, n, big, 1);
+            run<288, 16, 6, 30>("v4 partial m=6", d, n, 6, big, 1);
+            run<256, 16, 6, 0>("baseline partial m=6", d, n, 6, big, 1);
+            run<256, 16, 6, 0>("baseline", d, n, n, big, 1);
+            run<256, 16, 6, 20>("v3", d, n, n, big, 1);
+            run<256, 16, 6, 21>("v3, no trailing", d, n, n, big, 1);
+            run<256, 16, 6, 20>("v3 partial m=6", d, n, 6, big, 1);
+            run<256, 16, 6, 11>("two-phase, no trailing", d, n, n, big, 1);
+            run<256, 16, 6, 12>("two-phase, no panel barriers", d, n, n, big, 1);
+            run<256, 16, 6, 13>("two-phase, panel w/o division", d, n, n, big, 1);
+            run<256, 16, 6, 14>("two-phase, panel w/o publish", d, n, n, big, 1);
+            run<256, 16, 6, 15>("two-phase, null panel (LDS+BAR)", d, n, n, big, 1);
+            run<256, 16, 6, 10>("two-phase partial m=6", d, n, 6, big, 1);
+            run<256, 16, 6, 0>("baseline partial m=6", d, n, 6, big, 1);
+            run<256, 16, 6, 0>("baseline", d, n, n, big, 1);
+            run<256, 16, 6, 1>("no division", d, n, n, big, 1);
+            run<256, 16, 6, 2>("no barrier", d, n, n, big, 1);
+            run<256, 16, 6, 3>("no pivot row/col fix-ups", d, n, n, big, 1);
+            run<256, 16, 6, 4>("no bulk FMAs", d, n, n, big, 1);
+            run<256, 16, 6, 5>("no pd check", d, n, n, big, 1);
+            run<256, 16, 6, 0>("baseline, 2 CTAs/SM", d, n, n, 100 * 1024, 2);
+            if(n == 66) run<256, 16, 5, 0>("baseline TS=5", d, n, n, big, 1);
+        } else if(n == 42) {
+            run<128, 8, 6, 0>("baseline", d, n, n, 70 * 1024, 3);
+            run<128, 8, 6, 10>("two-phase", d, n, n, 70 * 1024, 3);
+            run<128, 8, 6, 20>("v3", d, n, n, 70 * 1024, 3);
+            run<96, 8, 6, 30>("v4 panel warp", d, n, n, 70 * 1024, 3);
+            run<64, 8, 6, 40>("v5 64 threads TS=6", d, n, n, 70 * 1024, 3);
+            run<64, 8, 6, 50>("v6 single 64 threads TS=6", d, n, n, 70 * 1024, 3);
+            run<128, 8, 5, 20>("v3 TS=5 (n=40)", d, 40, 40, 70 * 1024, 3);
+            run<128, 8, 6, 2>("no barrier", d, n, n, 70 * 1024, 3);
+            run<128, 8, 6, 4>("no bulk FMAs", d, n, n, 70 * 1024, 3);
+            run<256, 16, 3, 0>("256 threads TS=3, 3/SM", d, n, n, 70 * 1024, 3);
+        } else {
+            run<64, 8, 3, 0>("baseline", d, n, n, 27 * 1024, 8);
+            run<64, 8, 3, 10>("two-phase", d, n, n, 27 * 1024, 8);
+            run<64, 8, 3, 20>("v3", d, n, n, 27 * 1024, 8);
+            run<96, 8, 3, 30>("v4 panel warp", d, n, n, 27 * 1024, 8);
+            run<64, 8, 3, 40>("v5", d, n, n, 27 * 1024, 8);
+            run<64, 8, 4, 20>("v3 TS=4", d, n, n, 27 * 1024, 8);
+            run<64, 8, 3, 2>("no barrier", d, n, n, 27 * 1024, 8);
+            run<64, 8, 3, 4>("no bulk FMAs", d, n, n, 27 * 1024, 8);
+        }
+        cudaFree(d);
+    }
+    return 0;
+}
