@@ -57,11 +57,13 @@ spg_status launch_dim(spg_ctx *ctx, spg::KernelParams &kp) {
         if(N <= 12) return spg_launch_6_32(ctx, kp);
         if(N <= 32) return spg_launch_6_64(ctx, kp);
         if(N <= 48) return spg_launch_6_128(ctx, kp);
+        if(N <= 80) return spg_launch_6_512(ctx, kp); // 5 x 5 tiles fit the 128 registers of a 512-thread CTA
         return spg_launch_6_256(ctx, kp);
     }
     if(N <= 12) return spg_launch_3_32(ctx, kp);
     if(N <= 32) return spg_launch_3_64(ctx, kp);
     if(N <= 48) return spg_launch_3_128(ctx, kp);
+    if(N <= 80) return spg_launch_3_512(ctx, kp);
     return spg_launch_3_256(ctx, kp);
 }
 

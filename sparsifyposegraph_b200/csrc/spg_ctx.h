@@ -58,9 +58,11 @@ spg_status spg_launch_3_32(spg_ctx *, spg::KernelParams &);
 spg_status spg_launch_3_64(spg_ctx *, spg::KernelParams &);
 spg_status spg_launch_3_128(spg_ctx *, spg::KernelParams &);
 spg_status spg_launch_3_256(spg_ctx *, spg::KernelParams &);
+spg_status spg_launch_3_512(spg_ctx *, spg::KernelParams &); // two sweep groups of 256, 128 registers: N <= 80
 spg_status spg_launch_6_32(spg_ctx *, spg::KernelParams &);
 spg_status spg_launch_6_64(spg_ctx *, spg::KernelParams &);
 spg_status spg_launch_6_128(spg_ctx *, spg::KernelParams &);
 spg_status spg_launch_6_256(spg_ctx *, spg::KernelParams &);
+spg_status spg_launch_6_512(spg_ctx *, spg::KernelParams &);
 spg_status spg_launch_3_spill(spg_ctx *, spg::KernelParams &); // 256 threads, buffers in global memory
 spg_status spg_launch_6_spill(spg_ctx *, spg::KernelParams &);

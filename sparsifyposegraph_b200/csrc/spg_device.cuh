@@ -240,6 +240,24 @@ __device__ __forceinline__ int gsync_or(int pred) {
     else return __syncthreads_or(pred);
 }
 
+// Barrier / OR-reduction over either the whole CTA (BAR == 0) or a group of GS threads on named barrier BAR
+// (GS a multiple of 32; every thread of the group must call it).
+template <int NT, int BAR, int GS>
+__device__ __forceinline__ void group_sync() {
+    if constexpr(BAR == 0) gsync<NT>();
+    else asm volatile("bar.sync %0, %1;" ::"n"(BAR), "n"(GS) : "memory");
+}
+template <int NT, int BAR, int GS>
+__device__ __forceinline__ int group_or(int pred) {
+    if constexpr(BAR == 0) return gsync_or<NT>(pred);
+    else {
+        int r;
+        asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.s32 p, %1, 0;\n\tbar.red.or.pred q, %2, %3, p;\n\tselp.s32 %0, 1, 0, q;\n\t}"
+                     : "=r"(r) : "r"(pred), "n"(BAR), "n"(GS) : "memory");
+        return r;
+    }
+}
+
 // In-place lower Cholesky A = L L^T of the leading n x n block (reads the lower triangle).
 // Returns false (uniformly) if a pivot is not > 0.
 // Blocked right-looking, panel width CHOL_NB: (1) the NB x NB diagonal block is factored by one
@@ -413,16 +431,16 @@ __device__ __forceinline__ void sweep_step(double (&a)[TS][TS], double *colbuf, 
 // Blocks C0, C0 + 1, ... of T pivots each: the register index of the pivot row/column is a template
 // constant, so the tile never leaves the register file; the jj loop is not unrolled (a fully unrolled
 // sweep of T*TS steps thrashes the instruction cache).
-template <int NT, int T, int TS, int C0>
+template <int NT, int T, int TS, int C0, int BAR>
 __device__ __forceinline__ void sweep_blocks(double (&a)[TS][TS], double *colbuf, int nsweep, int tx, int ty, bool active, bool &bad) {
     if constexpr(C0 < TS) {
         const int jjmax = min(T, nsweep - T * C0); // uniform; <= 0: nothing left
 #pragma unroll 1
         for(int jj = 0; jj < jjmax; jj++) {
             if(active) sweep_step<T, TS, C0>(a, colbuf, jj, nsweep, tx, ty, bad);
-            gsync<NT>();
+            group_sync<NT, BAR, T * T>();
         }
-        sweep_blocks<NT, T, TS, C0 + 1>(a, colbuf, nsweep, tx, ty, active, bad);
+        sweep_blocks<NT, T, TS, C0 + 1, BAR>(a, colbuf, nsweep, tx, ty, active, bad);
     }
 }
 
@@ -441,15 +459,17 @@ __device__ __forceinline__ void sweep_blocks(double (&a)[TS][TS], double *colbuf
 // delivery through shared memory (24 wavefronts per warp and step) plus the FP64 issue slots, not latency —
 // sharing the barriers between two independent sweeps gains 4 %, deferring the rank-T update into the
 // next block's bubbles or handing the pivot columns to a dedicated warp is slower. See DESIGN.md.
-template <int NT, int T, int TS>
-__device__ __noinline__ bool sweep_spd(double *A, int n, int ld, int nsweep, double *colbuf) {
+// BAR > 0: the sweep is run by a group of exactly T*T threads (group-local index `tid`) that synchronises on
+// named barrier BAR, so that two groups of one CTA can sweep two matrices at the same time.
+template <int NT, int T, int TS, int BAR = 0>
+__device__ __forceinline__ bool sweep_spd_inl(double *A, int n, int ld, int nsweep, double *colbuf, int tid) {
     static_assert(T * T <= NT, "thread grid larger than the CTA");
-    const int tid = threadIdx.x;
+    constexpr int NTG = (BAR == 0) ? NT : T * T; // threads taking part
     const bool active = tid < T * T;
     const int tx = tid % T, ty = (tid / T) % T;
     constexpr int NP = T * TS;      // padded length: loads / stores of the pivot column need no bounds checks
     constexpr int cstride = NP + 2; // the pivot column, then the pivot d and 1/d
-    for(int t = n + tid; t < NP; t += NT) { colbuf[t] = 0.0; colbuf[cstride + t] = 0.0; }
+    for(int t = n + tid; t < NP; t += NTG) { colbuf[t] = 0.0; colbuf[cstride + t] = 0.0; }
     double a[TS][TS];
 #pragma unroll
     for(int c = 0; c < TS; c++)
@@ -464,10 +484,10 @@ __device__ __noinline__ bool sweep_spd(double *A, int n, int ld, int nsweep, dou
         for(int r = 0; r < TS; r++) colbuf[tx + T * r] = a[r][0];
         if(tx == 0) { colbuf[NP] = a[0][0]; colbuf[NP + 1] = fast_rcp(a[0][0]); }
     }
-    gsync<NT>();
+    group_sync<NT, BAR, T * T>();
     bool bad = false;
-    sweep_blocks<NT, T, TS, 0>(a, colbuf, nsweep, tx, ty, active, bad);
-    if(gsync_or<NT>(bad)) return false;
+    sweep_blocks<NT, T, TS, 0, BAR>(a, colbuf, nsweep, tx, ty, active, bad);
+    if(group_or<NT, BAR, T * T>(bad)) return false;
     // full sweep leaves -A^-1; a partial sweep leaves the Schur complement in the trailing block
     const double sgn = (nsweep >= n) ? -1.0 : 1.0;
 #pragma unroll
@@ -477,8 +497,13 @@ __device__ __noinline__ bool sweep_spd(double *A, int n, int ld, int nsweep, dou
             const int i = tx + T * r, l = ty + T * c;
             if(active && i < n && l < n) A[i + l * ld] = sgn * a[r][c];
         }
-    gsync<NT>();
+    group_sync<NT, BAR, T * T>();
     return true;
+}
+
+template <int NT, int T, int TS, int BAR = 0>
+__device__ __noinline__ bool sweep_spd(double *A, int n, int ld, int nsweep, double *colbuf, int tid = threadIdx.x) {
+    return sweep_spd_inl<NT, T, TS, BAR>(A, n, ld, nsweep, colbuf, tid);
 }
 
 // Two tile shapes per CTA width: the largest n each covers is T * TS.
@@ -487,6 +512,7 @@ template <> struct SweepGrid<32>  { static constexpr int T = 4,  TS0 = 2, TS1 = 
 template <> struct SweepGrid<64>  { static constexpr int T = 8,  TS0 = 3, TS1 = 4; };   // n <= 24 / 32
 template <> struct SweepGrid<128> { static constexpr int T = 8,  TS0 = 5, TS1 = 6; };   // n <= 40 / 48 (7 x 7 spills)
 template <> struct SweepGrid<256> { static constexpr int T = 16, TS0 = 5, TS1 = 6; };   // n <= 80 / 96
+template <> struct SweepGrid<512> { static constexpr int T = 16, TS0 = 4, TS1 = 5; };   // n <= 64 / 80: two groups of 256, 128 registers each (6 x 6 spills)
 
 // returns 1 ok, 0 not positive definite, -1 n too large for the register tiles. scratch: 2 * (T*TS + 2) doubles.
 // (Blocked variants were measured and dropped: a per-vertex rank-6 sweep took 186k vs 100k cycles at
@@ -497,6 +523,17 @@ __device__ __forceinline__ int sweep_spd_auto(double *A, int n, int ld, int nswe
     using G = SweepGrid<NT>;
     if(n <= G::T * G::TS0) return sweep_spd<NT, G::T, G::TS0>(A, n, ld, nsweep, scratch) ? 1 : 0;
     if(n <= G::T * G::TS1) return sweep_spd<NT, G::T, G::TS1>(A, n, ld, nsweep, scratch) ? 1 : 0;
+    return -1;
+}
+
+// CTAs at least twice as wide as the tile grid can sweep two matrices at once, one per group of T*T threads.
+template <int NT> struct SweepDual { static constexpr bool value = (SweepGrid<NT>::T >= 8) && (NT >= 2 * SweepGrid<NT>::T * SweepGrid<NT>::T); };
+// group g (0 or 1) = threads [g*T*T, (g+1)*T*T); same return convention as sweep_spd_auto. scratch: 2 * (T*TS + 2) doubles per group.
+template <int D, int NT, int BAR>
+__device__ __forceinline__ int sweep_spd_group(double *A, int n, int ld, int nsweep, double *scratch, int gtid) {
+    using G = SweepGrid<NT>;
+    if(n <= G::T * G::TS0) return sweep_spd<NT, G::T, G::TS0, BAR>(A, n, ld, nsweep, scratch, gtid) ? 1 : 0;
+    if(n <= G::T * G::TS1) return sweep_spd<NT, G::T, G::TS1, BAR>(A, n, ld, nsweep, scratch, gtid) ? 1 : 0;
     return -1;
 }
 

@@ -430,6 +430,7 @@ __global__ void __launch_bounds__(NT, (NT >= 256) ? 1 : (NT == 128 ? 3 : 512 / N
         SPG_T(2);
         // ---- S3: sparsity pattern (PseudoChowLiu::computeSparsityPattern, pseudo_chow_liu.cpp:33-87) ---
         int n_out = 0;
+        bool g_ready = false; // Lambda_rr^-1 already sits in buf2 (computed next to the Chow-Liu inverse)
         const bool glc_tree = (P.algorithm == SPG_ALG_GLC && P.topology == SPG_TOPO_TREE);
         if(status == SPG_BLANKET_OK && (P.algorithm == SPG_ALG_NFR || glc_tree) && nk >= 2) {
             const int mch = (int) ((1 + P.chord_ratio) * (nk - 1));
@@ -456,8 +457,38 @@ __global__ void __launch_bounds__(NT, (NT >= 256) ? 1 : (NT == 128 ? 3 : 512 / N
                     const int i = t % k, j = t / k;
                     Lc[i + j * ldk] = T[i + (size_t) j * ldH] + (i == j ? 1.0 : 0.0);
                 }
+                // CTAs twice as wide as the sweep's thread grid invert the anchored block Lambda_rr of the NFR
+                // gauge shortcut (S4) at the same time, on their second group of threads: two independent
+                // pivot chains per SM instead of one.
+                if constexpr(SweepDual<NT>::value && !SPILL) {
+                    using SG = SweepGrid<NT>;
+                    const int kk = k - D, ldg = odd_ld(kk > 0 ? kk : 1);
+                    if(P.algorithm == SPG_ALG_NFR && n_out * D == kk && !(P.flags & 1) && k <= SG::T * SG::TS1) {
+                        g_ready = true; // uniform
+                        for(int t = tid; t < kk * kk; t += NT) {
+                            const int i = t % kk, j = t / kk;
+                            buf2[i + j * ldg] = T[i + (size_t) j * ldH];
+                        }
+                    }
+                }
                 gsync<NT>();
-                {
+                if(g_ready) {
+                    if constexpr(SweepDual<NT>::value && !SPILL) {
+                        using SG = SweepGrid<NT>;
+                        constexpr int GS = SG::T * SG::T;
+                        const int kk = k - D, ldg = odd_ld(kk > 0 ? kk : 1);
+                        double *cb = reinterpret_cast<double *>(s_rec_buf); // the record copy is dead after the assembly
+                        if(tid < GS) {
+                            const int sw = sweep_spd_group<D, NT, 1>(Lc, k, ldk, k, cb, tid);
+                            if(tid == 0) s_misc[8] = sw;
+                        } else if(tid < 2 * GS) {
+                            const int sw = sweep_spd_group<D, NT, 2>(buf2, kk, ldg, kk, cb + 2 * (SG::T * SG::TS1 + 2), tid - GS);
+                            if(tid == GS) s_misc[9] = sw;
+                        }
+                        gsync<NT>();
+                        if(s_misc[8] == 0) status = SPG_BLANKET_NOT_PD_CHOWLIU;
+                    }
+                } else {
                     const int sw = sweep_spd_auto<D, NT>(Lc, k, ldk, k, buf2);
                     if(sw == 0) status = SPG_BLANKET_NOT_PD_CHOWLIU;
                     if(sw < 0) {
@@ -583,20 +614,25 @@ __global__ void __launch_bounds__(NT, (NT >= 256) ? 1 : (NT == 128 ? 3 : 512 / N
             // (~ k eps ||Lambda||) stay below the cutoff, i.e. smalleigs >= d. Otherwise: general path.
             bool fast = false;
             const int kk = k - D, ldg = odd_ld(kk > 0 ? kk : 1);
-            double *G = buf1; // the inverse overwrites the Cholesky factor; buf2 is its scratch
+            double *G = g_ready ? buf2 : buf1; // the inverse overwrites the Cholesky factor; buf2 is its scratch
             if(closed && !(P.flags & 1)) {
-                for(int t = tid; t < kk * kk; t += NT) {
-                    const int i = t % kk, j = t / kk;
-                    buf1[i + j * ldg] = T[i + (size_t) j * ldH];
-                }
+                if(!g_ready)
+                    for(int t = tid; t < kk * kk; t += NT) {
+                        const int i = t % kk, j = t / kk;
+                        buf1[i + j * ldg] = T[i + (size_t) j * ldH];
+                    }
                 // guard (ii): every diagonal entry of Lambda_t below 1e8 (checked by all threads, OR-reduced)
                 int bigdiag = 0;
                 for(int i = tid; i < k; i += NT) bigdiag |= !(fabs(T[i + (size_t) i * ldH]) < 1e8);
                 bigdiag = gsync_or<NT>(bigdiag);
-                int swg = sweep_spd_auto<D, NT>(buf1, kk, ldg, kk, buf2);
-                if(swg < 0) {
-                    swg = chol_lower<NT>(buf1, kk, ldg) ? 1 : 0;
-                    if(swg) chol_inverse_inplace<NT>(buf1, kk, ldg, buf2);
+                int swg;
+                if(g_ready) swg = s_misc[9];
+                else {
+                    swg = sweep_spd_auto<D, NT>(buf1, kk, ldg, kk, buf2);
+                    if(swg < 0) {
+                        swg = chol_lower<NT>(buf1, kk, ldg) ? 1 : 0;
+                        if(swg) chol_inverse_inplace<NT>(buf1, kk, ldg, buf2);
+                    }
                 }
                 if(swg > 0) {
                     SPG_T(8);

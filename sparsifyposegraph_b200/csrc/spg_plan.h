@@ -46,7 +46,7 @@ inline void plan_smem(KernelParams &p) {
     const int kmax = D * (p.max_nv - 1);
     const int nk = p.max_nv - 1;
     const int pairs = nk * (nk - 1) / 2;
-    int o = p.max_rec_words;             // record copy
+    int o = p.max_rec_words > 400 ? p.max_rec_words : 400; // record copy; after the assembly: pivot columns of two concurrent sweeps
     p.off_pose = o;  o += p.max_nv * PS;
     p.off_buf0 = o;
     p.buf0_doubles = N * odd_ld(N);

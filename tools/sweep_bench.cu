@@ -213,14 +213,6 @@ __device__ __noinline__ bool sweep_spd2(double *A, int n, int ld, int nsweep, do
 }
 
 // ---- v3: two-phase, branch-free panel, fast reciprocal, packed panel columns (128-bit smem accesses) ------
-__device__ __forceinline__ double fast_rcp(double x) {
-    double y;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    double e = fma(-x, y, 1.0);
-    y = fma(y, e, y);
-    e = fma(-x, y, 1.0);
-    return fma(y, e, y);
-}
 
 template <int NT, int T, int TS, int VAR = 20>
 __device__ __noinline__ bool sweep_spd3(double *A, int n, int ld, int nsweep, double *panel) {
@@ -786,6 +778,205 @@ __device__ __forceinline__ bool sweep_v6(double *A, int na, int lda, double *B, 
     return true;
 }
 
+// ---- v7: block Gauss-Jordan on FP64 tensor cores. 16 pivots per block: D = A[B,B] is inverted by one warp
+// (registers + shuffles), W = A[:,B] D^-1 and the rank-16 update A -= W A[:,B]^T are DMMA GEMMs on a tile
+// that stays in mma C-fragments for the whole sweep. 3 barriers per 16 pivots instead of 16.
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+struct V7 {
+    static constexpr int NT = 256, NMAX = 96, FR = 3, FC = 6, NB = 6; // 4 x 2 warps, cyclic 8 x 8 fragments
+    static constexpr int YS = 20;                                      // row stride of Y / W / Dinv: conflict-free fragment loads
+    static constexpr int YSZ = NMAX * YS;
+    static constexpr int SCRATCH = 3 * YSZ + 16 * YS + 8 + 40;        // Y (double-buffered), W, Dinv, flag, pivot columns of the small sweep
+    static constexpr bool INV_BY_WARP = false;
+};
+
+// -(D^-1) by Gauss-Jordan on the p x p leading block; lane = (row i, half h), 8 columns per lane
+__device__ __forceinline__ void v7_inv16(const double *Yb, double *Di, int p, int lane, bool &bad) {
+    const int i = lane & 15, h = lane >> 4;
+    double v[8];
+#pragma unroll
+    for(int q = 0; q < 8; q++) {
+        const int l = 8 * h + q;
+        v[q] = (i < p && l < p) ? Yb[i * V7::YS + l] : (i == l ? 1.0 : 0.0);
+    }
+#pragma unroll
+    for(int j = 0; j < 16; j++) {
+        if(j < p) { // uniform
+            constexpr int dummy = 0; (void) dummy;
+            const int hj = j >> 3, qj = j & 7;
+            const double aij = __shfl_sync(0xffffffffu, v[qj], i + 16 * hj);
+            const double d = __shfl_sync(0xffffffffu, v[qj], j + 16 * hj);
+            const double inv = fast_rcp(d);
+            bad |= !(d > 0);
+            const double s = aij * inv;
+#pragma unroll
+            for(int q = 0; q < 8; q++) {
+                const double ajl = __shfl_sync(0xffffffffu, v[q], j + 16 * h);
+                const double nv = fma(-s, ajl, v[q]);
+                v[q] = (i == j) ? ajl * inv : nv;
+            }
+            if(h == hj) v[qj] = (i == j) ? -inv : s;
+        }
+    }
+#pragma unroll
+    for(int q = 0; q < 8; q++) {
+        const int l = 8 * h + q;
+        Di[i * V7::YS + l] = (i < p && l < p) ? -v[q] : 0.0;
+    }
+}
+
+template <int B>
+__device__ __forceinline__ void v7_blocks(double (&a)[V7::FR][V7::FC][2], double *scr, int n, int nsweep, int lane, int wr, int wc, int warp) {
+    using K = V7;
+    if constexpr(B < K::NB) {
+        const int p = min(16, nsweep - 16 * B); // uniform
+        if(p > 0) {
+            double *Yc = scr + (B & 1) * K::YSZ, *W = scr + 2 * K::YSZ, *Di = scr + 3 * K::YSZ;
+            int *flag = reinterpret_cast<int *>(Di + 16 * K::YS);
+            const int lr = lane >> 2, lc = lane & 3;
+            long long tp0 = clock64(), tp1;
+            // (0) the warps holding the block's 16 columns copy them out (columns >= p of a partial block read as zero)
+#pragma unroll
+            for(int fr = 0; fr < K::FR; fr++) {
+                const int R = 8 * (wr + 4 * fr) + lr, cidx = 8 * wc + 2 * lc;
+                double2 val = make_double2(cidx < p ? a[fr][B][0] : 0.0, cidx + 1 < p ? a[fr][B][1] : 0.0);
+                *reinterpret_cast<double2 *>(&Yc[R * K::YS + cidx]) = val;
+            }
+            __syncthreads();
+            PROF(0);
+            // (1) D^-1
+            if(K::INV_BY_WARP) {
+                if(warp == 0) {
+                    bool bad = false;
+                    v7_inv16(Yc + 16 * B * K::YS, Di, p, lane, bad);
+                    if(bad) *flag = 1;
+                }
+                PROF(1);
+                __syncthreads();
+            } else {
+                // all 256 threads: one element each, scalar register sweep of the 16 x 16 block
+                const int i = threadIdx.x & 15, l = threadIdx.x >> 4;
+                Di[i * K::YS + l] = (i < p && l < p) ? Yc[(16 * B + i) * K::YS + l] : 0.0;
+                __syncthreads();
+                if(!sweep_spd<256, 16, 1>(Di, p, K::YS, p, Di + 16 * K::YS + 8)) *flag = 1;
+                PROF(1);
+            }
+            // (2) W = Y D^-1: every warp computes the three fragments it owns of the block's columns
+            double wf[K::FR][2];
+#pragma unroll
+            for(int fr = 0; fr < K::FR; fr++) wf[fr][0] = wf[fr][1] = 0.0;
+#pragma unroll
+            for(int ks = 0; ks < 4; ks++) {
+                const double bop = Di[(4 * ks + lc) * K::YS + 8 * wc + lr];
+#pragma unroll
+                for(int fr = 0; fr < K::FR; fr++) {
+                    const double aop = Yc[(8 * (wr + 4 * fr) + lr) * K::YS + 4 * ks + lc];
+                    dmma884(wf[fr][0], wf[fr][1], aop, bop);
+                }
+            }
+#pragma unroll
+            for(int fr = 0; fr < K::FR; fr++)
+                *reinterpret_cast<double2 *>(&W[(8 * (wr + 4 * fr) + lr) * K::YS + 8 * wc + 2 * lc]) = make_double2(wf[fr][0], wf[fr][1]);
+            __syncthreads();
+            PROF(2);
+            // (3) A -= W Y^T on every fragment inside the matrix (pivot rows / columns are overwritten below)
+#pragma unroll
+            for(int ks = 0; ks < 4; ks++) {
+                double an[K::FR];
+#pragma unroll
+                for(int fr = 0; fr < K::FR; fr++) an[fr] = -W[(8 * (wr + 4 * fr) + lr) * K::YS + 4 * ks + lc];
+#pragma unroll
+                for(int fc = 0; fc < K::FC; fc++) {
+                    if(8 * (wc + 2 * fc) < n && !(fc == B && p == 16)) {
+                        const double bop = Yc[(8 * (wc + 2 * fc) + lr) * K::YS + 4 * ks + lc];
+#pragma unroll
+                        for(int fr = 0; fr < K::FR; fr++)
+                            if(8 * (wr + 4 * fr) < n) dmma884(a[fr][fc][0], a[fr][fc][1], an[fr], bop);
+                    }
+                }
+            }
+            PROF(3);
+            // (4a) the block's own columns
+#pragma unroll
+            for(int fr = 0; fr < K::FR; fr++) {
+                const int R = 8 * (wr + 4 * fr) + lr;
+                const bool pr = (R >= 16 * B) && (R < 16 * B + p);
+#pragma unroll
+                for(int e = 0; e < 2; e++) {
+                    const int cidx = 8 * wc + 2 * lc + e;
+                    const bool pc = cidx < p;
+                    double val = a[fr][B][e];
+                    if(pc) val = pr ? -Di[(R - 16 * B) * K::YS + cidx] : wf[fr][e];
+                    else if(pr) val = W[(16 * B + cidx) * K::YS + (R - 16 * B)];
+                    a[fr][B][e] = val;
+                }
+            }
+            // (4b) the block's rows in the other fragment columns: A[B, l] = W[l, B]^T
+#pragma unroll
+            for(int t = 0; t < 2; t++) {
+                constexpr int dummy = 0; (void) dummy;
+                const int g = 2 * B + t;
+                if(wr == (g & 3)) { // uniform
+                    const int R = 8 * g + lr;
+                    if(R < 16 * B + p) {
+#pragma unroll
+                        for(int fc = 0; fc < K::FC; fc++) {
+                            if(fc != B) {
+#pragma unroll
+                                for(int e = 0; e < 2; e++) {
+                                    const int Cc = 8 * (wc + 2 * fc) + 2 * lc + e;
+                                    const double val = W[Cc * K::YS + (R - 16 * B)];
+                                    if(t == 0) a[(2 * B) / 4][fc][e] = val; else a[(2 * B + 1) / 4][fc][e] = val;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            PROF(4);
+        }
+        v7_blocks<B + 1>(a, scr, n, nsweep, lane, wr, wc, warp);
+    }
+}
+
+__device__ __forceinline__ bool sweep_v7(double *A, int n, int ld, int nsweep, double *scr) {
+    using K = V7;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wr = warp & 3, wc = warp >> 2;
+    const int lr = lane >> 2, lc = lane & 3;
+    for(int t = tid; t < K::SCRATCH; t += K::NT) scr[t] = 0.0;
+    double a[K::FR][K::FC][2];
+#pragma unroll
+    for(int fr = 0; fr < K::FR; fr++)
+#pragma unroll
+        for(int fc = 0; fc < K::FC; fc++)
+#pragma unroll
+            for(int e = 0; e < 2; e++) {
+                const int R = 8 * (wr + 4 * fr) + lr, Cc = 8 * (wc + 2 * fc) + 2 * lc + e;
+                a[fr][fc][e] = (R < n && Cc < n) ? A[R + Cc * ld] : 0.0;
+            }
+    __syncthreads();
+    v7_blocks<0>(a, scr, n, nsweep, lane, wr, wc, warp);
+    __syncthreads();
+    const int bad = *reinterpret_cast<int *>(scr + 3 * K::YSZ + 16 * K::YS);
+    if(bad) return false;
+    const double sgn = (nsweep >= n) ? -1.0 : 1.0;
+#pragma unroll
+    for(int fr = 0; fr < K::FR; fr++)
+#pragma unroll
+        for(int fc = 0; fc < K::FC; fc++)
+#pragma unroll
+            for(int e = 0; e < 2; e++) {
+                const int R = 8 * (wr + 4 * fr) + lr, Cc = 8 * (wc + 2 * fc) + 2 * lc + e;
+                if(R < n && Cc < n) A[R + Cc * ld] = sgn * a[fr][fc][e];
+            }
+    __syncthreads();
+    return true;
+}
+
 template <int NT, int T, int TS, int VAR>
 __global__ void __launch_bounds__(NT) __maxnreg__(NT == 288 ? 168 : (NT <= 64 ? 128 : (NT <= 128 ? 168 : 255))) bench_kernel(const double *src, int n, int nsweep, int reps, long long *cycles, double *sink, double *result) {
     extern __shared__ double sm[];
@@ -801,6 +992,7 @@ __global__ void __launch_bounds__(NT) __maxnreg__(NT == 288 ? 168 : (NT <= 64 ? 
         const long long t0 = clock64();
         bool ok;
         if constexpr(VAR == 0) ok = sweep_spd<NT, T, TS>(A, n, ld, nsweep, colbuf);
+        else if constexpr(VAR == 60) ok = sweep_v7(A, n, ld, nsweep, colbuf);
         else if constexpr(VAR == 50) ok = sweep_v6<NT, T, TS, false>(A, n, ld, A, n, ld, colbuf);
         else if constexpr(VAR == 51) ok = sweep_v6<NT, T, TS, true>(A, n, ld, B2, n - 6, ld, colbuf);
         else if constexpr(VAR >= 40) ok = sweep_spd5<NT, T, TS>(A, n, ld, nsweep, colbuf);
@@ -848,11 +1040,22 @@ void run(const char *name, const double *dsrc, int n, int nsweep, size_t smem_fo
     cudaFree(dres);
     double diff = 0, nrm = 0;
     if(VAR == 0) ref = res;
+    if(nsweep < n) { // partial sweep: only the trailing block is defined
+        for(int j = 0; j < n; j++) for(int i = 0; i < n; i++) if(i < nsweep || j < nsweep) { res[i + j * n] = 0; if(ref.size() == res.size() && VAR == 0) ref[i + j * n] = 0; }
+    }
     else if(ref.size() == res.size()) for(size_t i = 0; i < res.size(); i++) { diff += (res[i] - ref[i]) * (res[i] - ref[i]); nrm += ref[i] * ref[i]; }
     double mean = 0;
     for(long long c : hc) mean += (double) c / grid;
     printf("%-34s NT=%3d T=%2d TS=%d n=%3d nsweep=%3d ctas/sm=%d: %9.0f cycles/sweep  %7.1f cycles/step  (%.3f ms, %s) rel.diff vs baseline %.1e\n", name, NT, T, TS, n,
            nsweep, ctas_per_sm, mean, mean / nsweep, ms, cudaGetErrorString(err), nrm > 0 ? sqrt(diff / nrm) : -1.0);
+    if(VAR == 60) {
+        long long hp[8];
+        cudaMemcpyFromSymbol(hp, g_prof, sizeof(hp));
+        printf("      CTA 0 thread 0, per sweep: extract+bar %lld  dinv %lld  bar+wgemm+bar %lld  trailing %lld  overwrite %lld\n", hp[0] / (reps + 2), hp[1] / (reps + 2),
+               hp[2] / (reps + 2), hp[3] / (reps + 2), hp[4] / (reps + 2));
+        long long z[8] = {0};
+        cudaMemcpyToSymbol(g_prof, z, sizeof(z));
+    }
     if(VAR >= 10 && VAR < 40) {
         long long hp[8];
         cudaMemcpyFromSymbol(hp, g_prof, sizeof(hp));
@@ -886,6 +1089,12 @@ int main() {
             const size_t big = 200 * 1024;
             run<256, 16, 6, 0>("baseline", d, n, n, big, 1);
             run<256, 16, 6, 10>("two-phase", d, n, n, big, 1);
+            run<256, 16, 6, 60>("v7 block GJ on DMMA", d, n, n, big, 1);
+            run<256, 16, 6, 60>("v7 partial m=6", d, n, 6, big, 1);
+            run<256, 16, 6, 0>("baseline partial m=6", d, n, 6, big, 1);
+            run<256, 16, 6, 60>("v7 partial m=40", d, n, 40, big, 1);
+            run<256, 16, 6, 0>("baseline partial m=40", d, n, 40, big, 1);
+            run<256, 16, 6, 0>("baseline", d, n, n, big, 1);
             run<256, 16, 6, 50>("v6 single (function form)", d, n, n, big, 1);
             run<256, 16, 6, 51>("v6 dual: n and n-6 together", d, n, n, big, 1);
             run<256, 16, 6, 40>("v5 deferred trailing", d, n, n, big, 1);
