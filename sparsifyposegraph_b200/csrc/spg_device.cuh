@@ -526,9 +526,16 @@ __device__ __forceinline__ int sweep_spd_auto(double *A, int n, int ld, int nswe
     return -1;
 }
 
-// CTAs at least twice as wide as the tile grid can sweep two matrices at once, one per group of T*T threads.
-template <int NT> struct SweepDual { static constexpr bool value = (SweepGrid<NT>::T >= 8) && (NT >= 2 * SweepGrid<NT>::T * SweepGrid<NT>::T); };
-// group g (0 or 1) = threads [g*T*T, (g+1)*T*T); same return convention as sweep_spd_auto. scratch: 2 * (T*TS + 2) doubles per group.
+// CTAs wide enough sweep two matrices at once, one per group of GS threads (group g = threads [g*GS, (g+1)*GS)):
+//   128 threads: two 8 x 8 grids, tiles up to 6 x 6 (n <= 48)
+//   512 threads: two 16 x 16 grids, tiles 4 x 4 / 5 x 5 (n <= 64 / 80), 128 registers (6 x 6 spills)
+// CB = doubles of pivot-column scratch per group. (A 256-thread CTA with two 16 x 8 groups and 6 x 12 tiles
+// covers n <= 96 but measured no faster than two 16 x 16 sweeps one after the other: tools/sweep_bench.cu.)
+template <int NT> struct SweepDual { static constexpr bool value = false; static constexpr int GS = NT, NMAX = 0, CB = 0; };
+template <> struct SweepDual<128> { static constexpr bool value = true; static constexpr int GS = 64, NMAX = 48, CB = 100; };
+template <> struct SweepDual<512> { static constexpr bool value = true; static constexpr int GS = 256, NMAX = 80, CB = 164; };
+
+// same return convention as sweep_spd_auto
 template <int D, int NT, int BAR>
 __device__ __forceinline__ int sweep_spd_group(double *A, int n, int ld, int nsweep, double *scratch, int gtid) {
     using G = SweepGrid<NT>;

@@ -483,6 +483,12 @@ spg_status VertexRemover::beginRemoval(const std::vector<int> &toRemove) {
     _done.assign(toRemove.size(), 0);
     _remaining = toRemove.size();
     _round = Round();
+    _unitCache.assign(toRemove.size(), RemovalUnit());
+    _unitBuilt.assign(toRemove.size(), 0);
+    _stamp.assign(_graph->verts.size(), 0);
+    _touchHead.assign(_graph->verts.size(), -1);
+    _removedBy.assign(_graph->verts.size(), -1);
+    _planNo = 0;
     return SPG_OK;
 }
 
@@ -508,13 +514,26 @@ spg_status VertexRemover::planRound() {
     if(_remaining == 0) return SPG_OK;
     const int dim = _graph->dim;
     const std::vector<int> &toRemove = _pending;
-    struct Region { std::vector<int> removed, region; }; // region: every vertex of the (conservative) blanket
     {
         // ---- select a round -------------------------------------------------------------------
+        // A unit U may run in this round iff it commutes with every earlier pending unit V (selected or
+        // deferred): removed(U) misses V's blanket, kept(U) misses removed(V) and U shares at most one kept
+        // vertex with V. A deferred unit waits for the units it hit; its blanket after they ran lies inside
+        // the union of their blankets and its own, so the two are merged into one component (union-find over
+        // region ids) and later units are tested against whole components. Linear in the blanket sizes;
+        // blankets are re-extracted only when a vertex of theirs was touched by an applied round.
         std::vector<RemovalUnit> &units = _round.units;
-        std::vector<Region> regions;            // selected and deferred ones, in list order
-        std::unordered_map<int, std::vector<int>> touch; // vertex -> regions containing it
-        std::unordered_map<int, int> removedBy;          // vertex -> region removing it
+        const int Vn = (int) _graph->verts.size();
+        _planNo++;
+        if((int) _stamp.size() < Vn) _stamp.resize(Vn, 0);
+        if((int) _touchHead.size() < Vn) { _touchHead.resize(Vn, -1); _removedBy.resize(Vn, -1); }
+        _touchNext.clear();
+        _touchRegion.clear();
+        std::vector<int> touched;   // vertex indices whose per-round lists must be reset
+        std::vector<int> parent;    // union-find over region ids
+        auto find = [&](int x) { while(parent[x] != x) { parent[x] = parent[parent[x]]; x = parent[x]; } return x; };
+        std::vector<int> hit, comps;
+        std::vector<std::pair<int, int>> shared;
         for(size_t i = 0; i < toRemove.size(); i++) {
             if(_done[i]) continue;
             if(!_graph->hasVertex(toRemove[i])) { // merged into an earlier extended blanket (:91)
@@ -522,48 +541,58 @@ spg_status VertexRemover::planRound() {
                 _remaining--;
                 continue;
             }
-            RemovalUnit u;
-            if(!buildUnit(toRemove[i], (int) i, _toRemoveSet, u)) {
-                // isolated vertex: the reference asserts blanketEdges.size() > 0
-                error = "vertex " + std::to_string(toRemove[i]) + " has no edges";
-                return SPG_ERR_INVALID;
+            RemovalUnit &u = _unitCache[i];
+            bool stale = !_unitBuilt[i];
+            if(!stale) {
+                for(int x : u.removed) if(_stamp[_graph->index.at(x)] >= _unitBuilt[i]) { stale = true; break; }
+                if(!stale) for(int x : u.kept) if(_stamp[_graph->index.at(x)] >= _unitBuilt[i]) { stale = true; break; }
             }
-            // conflicts with earlier regions?
-            std::vector<int> hit; // regions this unit interferes with
-            {
-                std::unordered_map<int, int> shared;
-                auto note = [&](int rg) { if(std::find(hit.begin(), hit.end(), rg) == hit.end()) hit.push_back(rg); };
-                for(int x : u.removed) {
-                    auto it = touch.find(x);
-                    if(it != touch.end()) for(int rg : it->second) note(rg);
+            if(stale) {
+                if(!buildUnit(toRemove[i], (int) i, _toRemoveSet, u)) {
+                    // isolated vertex: the reference asserts blanketEdges.size() > 0
+                    error = "vertex " + std::to_string(toRemove[i]) + " has no edges";
+                    return SPG_ERR_INVALID;
                 }
-                for(int x : u.kept) {
-                    auto rb = removedBy.find(x);
-                    if(rb != removedBy.end()) note(rb->second);
-                    auto it = touch.find(x);
-                    if(it != touch.end())
-                        for(int rg : it->second)
-                            if(++shared[rg] >= 2) note(rg);
+                _unitBuilt[i] = _planNo;
+            }
+            hit.clear();
+            shared.clear();
+            auto note = [&](int c) { if(std::find(hit.begin(), hit.end(), c) == hit.end()) hit.push_back(c); };
+            for(int x : u.removed) {
+                const int xi = _graph->index.at(x);
+                for(int t = _touchHead[xi]; t >= 0; t = _touchNext[t]) note(find(_touchRegion[t]));
+            }
+            for(int x : u.kept) {
+                const int xi = _graph->index.at(x);
+                if(_removedBy[xi] >= 0) note(find(_removedBy[xi]));
+                comps.clear();
+                for(int t = _touchHead[xi]; t >= 0; t = _touchNext[t]) {
+                    const int c = find(_touchRegion[t]);
+                    if(std::find(comps.begin(), comps.end(), c) == comps.end()) comps.push_back(c);
+                }
+                for(int c : comps) {
+                    auto it = std::find_if(shared.begin(), shared.end(), [&](const std::pair<int, int> &pr) { return pr.first == c; });
+                    if(it == shared.end()) shared.emplace_back(c, 1);
+                    else if(++it->second >= 2) note(c);
                 }
             }
-            Region rg;
-            rg.removed = u.removed;
-            rg.region = u.removed;
-            rg.region.insert(rg.region.end(), u.kept.begin(), u.kept.end());
+            const int rid = (int) parent.size();
+            parent.push_back(rid);
             const bool select = hit.empty();
-            if(!select) {
-                // deferred: widen its region by everything it waits for (transitively, because the
-                // regions it hit already carry their own closure)
-                std::set<int> wide(rg.region.begin(), rg.region.end());
-                for(int h : hit) wide.insert(regions[h].region.begin(), regions[h].region.end());
-                rg.region.assign(wide.begin(), wide.end());
-            }
-            const int rid = (int) regions.size();
-            for(int x : rg.region) touch[x].push_back(rid);
-            for(int x : rg.removed) removedBy[x] = rid;
-            regions.push_back(std::move(rg));
-            if(select) units.push_back(std::move(u));
+            for(int c : hit) parent[find(c)] = rid;
+            auto reg = [&](int x, bool removed) {
+                const int xi = _graph->index.at(x);
+                if(_touchHead[xi] < 0 && _removedBy[xi] < 0) touched.push_back(xi);
+                _touchNext.push_back(_touchHead[xi]);
+                _touchRegion.push_back(rid);
+                _touchHead[xi] = (int) _touchNext.size() - 1;
+                if(removed) _removedBy[xi] = rid;
+            };
+            for(int x : u.removed) reg(x, true);
+            for(int x : u.kept) reg(x, false);
+            if(select) units.push_back(u);
         }
+        for(int xi : touched) { _touchHead[xi] = -1; _removedBy[xi] = -1; }
         if(units.empty()) return SPG_OK;
     }
     // ---- pack ----------------------------------------------------------------------------
@@ -614,6 +643,8 @@ void VertexRemover::applyRound(const uint64_t *out) {
         const int32_t *oh = reinterpret_cast<const int32_t *>(o);
         const int bstatus = oh[0], nnew = oh[1];
         if(bstatus != SPG_BLANKET_OK) stats.n_failed++;
+        for(int id : u.removed) _stamp[_graph->index.at(id)] = _planNo; // cached blankets containing these are stale
+        for(int id : u.kept) _stamp[_graph->index.at(id)] = _planNo;
         for(int ei : u.edges) _graph->removeEdge(ei);
         for(int id : u.removed) _graph->removeVertex(id);
         const int nk = (int) u.kept.size();

@@ -172,6 +172,12 @@ private:
     std::set<int> _toRemoveSet;
     std::vector<char> _done;
     size_t _remaining = 0;
+    // scheduler state: cached blankets of the pending vertices (re-extracted when stale) and per-round scratch
+    std::vector<RemovalUnit> _unitCache;
+    std::vector<int> _unitBuilt;            // planning pass that extracted the cached blanket (0: never)
+    std::vector<int> _stamp;                // per vertex index: last planning pass whose round touched it
+    std::vector<int> _touchHead, _touchNext, _touchRegion, _removedBy;
+    int _planNo = 0;
     SparsityOptions _opts;
     Graph *_graph = nullptr;
     spg_ctx *_ctx = nullptr;

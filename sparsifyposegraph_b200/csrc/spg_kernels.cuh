@@ -461,9 +461,8 @@ __global__ void __launch_bounds__(NT, (NT >= 256) ? 1 : (NT == 128 ? 3 : 512 / N
                 // gauge shortcut (S4) at the same time, on their second group of threads: two independent
                 // pivot chains per SM instead of one.
                 if constexpr(SweepDual<NT>::value && !SPILL) {
-                    using SG = SweepGrid<NT>;
                     const int kk = k - D, ldg = odd_ld(kk > 0 ? kk : 1);
-                    if(P.algorithm == SPG_ALG_NFR && n_out * D == kk && !(P.flags & 1) && k <= SG::T * SG::TS1) {
+                    if(P.algorithm == SPG_ALG_NFR && n_out * D == kk && !(P.flags & 1) && k <= SweepDual<NT>::NMAX) {
                         g_ready = true; // uniform
                         for(int t = tid; t < kk * kk; t += NT) {
                             const int i = t % kk, j = t / kk;
@@ -474,15 +473,14 @@ __global__ void __launch_bounds__(NT, (NT >= 256) ? 1 : (NT == 128 ? 3 : 512 / N
                 gsync<NT>();
                 if(g_ready) {
                     if constexpr(SweepDual<NT>::value && !SPILL) {
-                        using SG = SweepGrid<NT>;
-                        constexpr int GS = SG::T * SG::T;
+                        constexpr int GS = SweepDual<NT>::GS;
                         const int kk = k - D, ldg = odd_ld(kk > 0 ? kk : 1);
                         double *cb = reinterpret_cast<double *>(s_rec_buf); // the record copy is dead after the assembly
                         if(tid < GS) {
                             const int sw = sweep_spd_group<D, NT, 1>(Lc, k, ldk, k, cb, tid);
                             if(tid == 0) s_misc[8] = sw;
                         } else if(tid < 2 * GS) {
-                            const int sw = sweep_spd_group<D, NT, 2>(buf2, kk, ldg, kk, cb + 2 * (SG::T * SG::TS1 + 2), tid - GS);
+                            const int sw = sweep_spd_group<D, NT, 2>(buf2, kk, ldg, kk, cb + SweepDual<NT>::CB, tid - GS);
                             if(tid == GS) s_misc[9] = sw;
                         }
                         gsync<NT>();

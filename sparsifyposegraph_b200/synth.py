@@ -193,3 +193,27 @@ def make_grid_graph(rows, cols, dim=6, seed=SEED, sigma_t=0.05, sigma_r=0.02):
         meas = se2_compose(se2_compose(se2_inverse(Xi), Xj), noise)
     info = random_info(rng, (E,), dim)
     return poses, edges, meas, info
+
+
+def grid_removal_order(rows, cols, sparsity=10, colour_mod=4):
+    """Removal list of BASELINE.json configs[4] (synthetic grid, 90 % removal at sparsity 10): the ids
+    globalDecimate selects (decimation.cpp:36-49: i in [4, V-1] with i % sparsity != 0), ordered by colour class
+    (r % m, c % m) and then by id. The reference removes in list order; in raster order the wavefront rounds are
+    a handful of blankets wide, in colour order thousands. colour_mod = 0: raster order."""
+    V = rows * cols
+    ids = np.arange(4, V, dtype=np.int32)
+    ids = ids[ids % sparsity != 0]
+    if colour_mod:
+        r, c = np.divmod(ids, cols)
+        colour = (r % colour_mod) * colour_mod + (c % colour_mod)
+        ids = ids[np.lexsort((ids, colour))]
+    return np.ascontiguousarray(ids, dtype=np.int32)
+
+
+def fill_graph(graph, poses, edges, meas, info):
+    """add_vertex / add_edge of a generated graph into a product or oracle Graph (same call surface)."""
+    for i in range(len(poses)):
+        graph.add_vertex(i, poses[i])
+    for e in range(len(edges)):
+        graph.add_edge(int(edges[e, 0]), int(edges[e, 1]), meas[e], info[e])
+    return graph

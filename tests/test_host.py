@@ -96,3 +96,33 @@ def test_compute_substitute_edge_matches_oracle(oracle, name):
         if checked >= 25:
             break
     assert checked >= 5
+
+
+@pytest.mark.parametrize("colour_mod", [0, 4])
+def test_round_scheduler_equals_sequential_removal_on_grid(oracle, colour_mod):
+    """BASELINE.json configs[4] at small scale: the wavefront rounds (product scheduler; blankets computed by the
+    oracle here, no GPU) must leave exactly the graph of the one-at-a-time loop of VertexRemover::remove
+    (vertex_remover.cpp:83-140), in raster order (narrow rounds) and in colour order (wide rounds)."""
+    from sparsifyposegraph_b200 import capi, synth, records as R
+    from test_gpu_graph import compare_graphs
+    rows, cols = 24, 28
+    data = synth.make_grid_graph(rows, cols, dim=6)
+    g = synth.fill_graph(capi.Graph(dim=6), *data)
+    o = synth.fill_graph(oracle.Graph(dim=6), *data)
+    which = synth.grid_removal_order(rows, cols, 10, colour_mod)
+    opts = capi.make_opts(R.TOPO_TREE, R.LIN_GLOBAL)
+    capi.rounds_begin(g, which, opts, R.ALG_NFR)
+    widths = []
+    while True:
+        rd = capi.round_next(g)
+        if rd is None:
+            break
+        widths.append(rd["n"])
+        out = oracle.remove_round(rd["dim"], rd["algorithm"], oracle.make_opts(R.TOPO_TREE, R.LIN_GLOBAL), rd["records"],
+                                  rd["rec_off"], rd["out_off"], 0)[0]
+        capi.round_apply(g, out)
+    assert sum(widths) == len(which)
+    assert o.marginalize(which, oracle.make_opts(R.TOPO_TREE, R.LIN_GLOBAL), R.ALG_NFR) == 0
+    compare_graphs(g, o, tol=1e-9)
+    if colour_mod:
+        assert max(widths) >= 25 and len(widths) < len(which) / 8

@@ -17,7 +17,7 @@ ctx = capi.Context(0)
 L = capi.lib()
 L.spg_stage_profile.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
 for n in sizes:
-    B = 4000
+    B = 4000 if n <= 19 else 8
     blk = synth.make_blankets(n, B, dim=6, variant="ring", seed=n)
     out_off = R.out_offsets(6, 0, 0, 1.0, np.full(B, n - 1))
     ctx.remove_round(6, 0, capi.make_opts(0, 1), blk["records"], blk["rec_off"], out_off)

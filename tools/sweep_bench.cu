@@ -10,6 +10,126 @@
 
 using namespace spg;
 
+namespace spg {
+// ---- rectangular variant: TX x TY thread grid (TX a multiple of TY), TSR x TSC register tile ---------------
+// rows i = tx + TX r, columns l = ty + TY c, TX*TSR == TY*TSC. Same arithmetic per entry as sweep_step, so the
+// results are bit-identical; it exists so that 128 threads (16 x 8, 6 x 12 tile) can carry a 96 x 96 matrix and
+// a 256-thread CTA can run two sweeps side by side. C0 = block of TY pivots.
+template <int TX, int TY, int TSR, int TSC, int C0>
+__device__ __forceinline__ void rsweep_step(double (&a)[TSR][TSC], double *colbuf, int jj, int nsweep, int tx, int ty, bool &bad) {
+    static_assert(TX % TY == 0 && TX * TSR == TY * TSC, "rectangular sweep shape");
+    constexpr int NP = TX * TSR;
+    constexpr int cstride = NP + 2;
+    constexpr int R0 = (TY * C0) / TX;                  // register row of this block's pivot rows
+    constexpr int TXO = (TY * C0) % TX;                 // tx of its first pivot row
+    constexpr int CN = (C0 + 1) % TSC;
+    constexpr int R0N = (TY * CN) / TX, TXN = (TY * CN) % TX; // the same for the first pivot of the next block
+    const int j = jj + TY * C0;
+    const double *col = colbuf + (j & 1) * cstride;
+    double *ncol = colbuf + ((j + 1) & 1) * cstride;
+    const double d = col[NP], inv = col[NP + 1];
+    bad |= !(d > 0);
+    double ci[TSR];
+#pragma unroll
+    for(int r = 0; r < TSR; r++) ci[r] = col[tx + TX * r];
+    const double *clp = col + ty; // the scaled pivot-row entries are fetched column by column: 12 more live doubles would spill
+    const bool rowj = (tx == jj + TXO), colj = (ty == jj);
+    const bool wrap = (jj + 1 == TY);
+    const bool more = (j + 1 < nsweep);
+    if(!wrap) {
+        const double cl0 = clp[TY * C0] * inv;
+#pragma unroll
+        for(int r = 0; r < TSR; r++) a[r][C0] -= ci[r] * cl0;
+        if(rowj) a[R0][C0] = cl0;
+        if(colj) {
+#pragma unroll
+            for(int r = 0; r < TSR; r++) a[r][C0] = ci[r] * inv;
+            if(rowj) a[R0][C0] = -inv;
+        }
+        if(more && ty == jj + 1) {
+#pragma unroll
+            for(int r = 0; r < TSR; r++) ncol[tx + TX * r] = a[r][C0];
+            if(tx == jj + 1 + TXO) { ncol[NP] = a[R0][C0]; ncol[NP + 1] = fast_rcp(a[R0][C0]); }
+        }
+    } else if(C0 + 1 < TSC) {
+        const double cln = clp[TY * CN] * inv;
+#pragma unroll
+        for(int r = 0; r < TSR; r++) a[r][CN] -= ci[r] * cln;
+        if(rowj) a[R0][CN] = cln;
+        if(more && ty == 0) {
+#pragma unroll
+            for(int r = 0; r < TSR; r++) ncol[tx + TX * r] = a[r][CN];
+            if(tx == TXN) { ncol[NP] = a[R0N][CN]; ncol[NP + 1] = fast_rcp(a[R0N][CN]); }
+        }
+    }
+#pragma unroll
+    for(int c = 0; c < TSC; c++) {
+        const bool done_ahead = (!wrap && c == C0) || (wrap && c == C0 + 1);
+        if(!done_ahead) {
+            const double clc = clp[TY * c] * inv;
+#pragma unroll
+            for(int r = 0; r < TSR; r++) a[r][c] -= ci[r] * clc;
+            if(rowj) a[R0][c] = clc;
+        }
+    }
+    if(wrap && colj) {
+#pragma unroll
+        for(int r = 0; r < TSR; r++) a[r][C0] = ci[r] * inv;
+        if(rowj) a[R0][C0] = -inv;
+    }
+}
+
+template <int NT, int TX, int TY, int TSR, int TSC, int C0, int BAR>
+__device__ __forceinline__ void rsweep_blocks(double (&a)[TSR][TSC], double *colbuf, int nsweep, int tx, int ty, bool &bad) {
+    if constexpr(C0 < TSC) {
+        const int jjmax = min(TY, nsweep - TY * C0); // uniform
+#pragma unroll 1
+        for(int jj = 0; jj < jjmax; jj++) {
+            rsweep_step<TX, TY, TSR, TSC, C0>(a, colbuf, jj, nsweep, tx, ty, bad);
+            group_sync<NT, BAR, TX * TY>();
+        }
+        rsweep_blocks<NT, TX, TY, TSR, TSC, C0 + 1, BAR>(a, colbuf, nsweep, tx, ty, bad);
+    }
+}
+
+// run by a group of exactly TX*TY threads (group-local index gtid) on named barrier BAR > 0
+template <int NT, int TX, int TY, int TSR, int TSC, int BAR>
+__device__ __noinline__ bool rsweep_spd(double *A, int n, int ld, int nsweep, double *colbuf, int gtid) {
+    static_assert(BAR > 0, "group sweep");
+    constexpr int GS = TX * TY, NP = TX * TSR, cstride = NP + 2;
+    const int tx = gtid % TX, ty = gtid / TX;
+    for(int t = n + gtid; t < NP; t += GS) { colbuf[t] = 0.0; colbuf[cstride + t] = 0.0; }
+    double a[TSR][TSC];
+#pragma unroll
+    for(int c = 0; c < TSC; c++)
+#pragma unroll
+        for(int r = 0; r < TSR; r++) {
+            const int i = tx + TX * r, l = ty + TY * c;
+            a[r][c] = (i < n && l < n) ? A[i + l * ld] : 0.0;
+        }
+    if(ty == 0) {
+#pragma unroll
+        for(int r = 0; r < TSR; r++) colbuf[tx + TX * r] = a[r][0];
+        if(tx == 0) { colbuf[NP] = a[0][0]; colbuf[NP + 1] = fast_rcp(a[0][0]); }
+    }
+    group_sync<NT, BAR, GS>();
+    bool bad = false;
+    rsweep_blocks<NT, TX, TY, TSR, TSC, 0, BAR>(a, colbuf, nsweep, tx, ty, bad);
+    if(group_or<NT, BAR, GS>(bad)) return false;
+    const double sgn = (nsweep >= n) ? -1.0 : 1.0;
+#pragma unroll
+    for(int c = 0; c < TSC; c++)
+#pragma unroll
+        for(int r = 0; r < TSR; r++) {
+            const int i = tx + TX * r, l = ty + TY * c;
+            if(i < n && l < n) A[i + l * ld] = sgn * a[r][c];
+        }
+    group_sync<NT, BAR, GS>();
+    return true;
+}
+
+} // namespace spg
+
 template <int NT, int T, int TS, int VAR>
 __device__ __noinline__ bool sweep_var(double *A, int n, int ld, int nsweep, double *colbuf) {
     const int tid = threadIdx.x;
@@ -978,7 +1098,7 @@ __device__ __forceinline__ bool sweep_v7(double *A, int n, int ld, int nsweep, d
 }
 
 template <int NT, int T, int TS, int VAR>
-__global__ void __launch_bounds__(NT) __maxnreg__(NT == 288 ? 168 : (NT <= 64 ? 128 : (NT <= 128 ? 168 : 255))) bench_kernel(const double *src, int n, int nsweep, int reps, long long *cycles, double *sink, double *result) {
+__global__ void __launch_bounds__(NT) __maxnreg__(NT == 288 ? 168 : (NT == 1024 ? 64 : (NT == 512 ? 128 : (NT <= 64 ? 128 : (NT <= 128 ? 255 : 255))))) bench_kernel(const double *src, int n, int nsweep, int reps, long long *cycles, double *sink, double *result) {
     extern __shared__ double sm[];
     const int ld = odd_ld(n);
     double *A = sm, *colbuf = sm + n * ld;
@@ -993,6 +1113,9 @@ __global__ void __launch_bounds__(NT) __maxnreg__(NT == 288 ? 168 : (NT <= 64 ? 
         bool ok;
         if constexpr(VAR == 0) ok = sweep_spd<NT, T, TS>(A, n, ld, nsweep, colbuf);
         else if constexpr(VAR == 60) ok = sweep_v7(A, n, ld, nsweep, colbuf);
+        else if constexpr(VAR == 70) ok = rsweep_spd<NT, 32, 16, 3, 6, 1>(A, n, ld, nsweep, colbuf, threadIdx.x);
+        else if constexpr(VAR == 71) ok = rsweep_spd<NT, 16, 8, 6, 12, 1>(A, n, ld, nsweep, colbuf, threadIdx.x);
+        else if constexpr(VAR == 72) ok = rsweep_spd<NT, 32, 32, 3, 3, 1>(A, n, ld, nsweep, colbuf, threadIdx.x);
         else if constexpr(VAR == 50) ok = sweep_v6<NT, T, TS, false>(A, n, ld, A, n, ld, colbuf);
         else if constexpr(VAR == 51) ok = sweep_v6<NT, T, TS, true>(A, n, ld, B2, n - 6, ld, colbuf);
         else if constexpr(VAR >= 40) ok = sweep_spd5<NT, T, TS>(A, n, ld, nsweep, colbuf);
@@ -1089,6 +1212,9 @@ int main() {
             const size_t big = 200 * 1024;
             run<256, 16, 6, 0>("baseline", d, n, n, big, 1);
             run<256, 16, 6, 10>("two-phase", d, n, n, big, 1);
+            run<512, 16, 6, 70>("512 threads, 32x16 grid, 3x6 tiles", d, n, n, big, 1);
+            run<128, 16, 6, 71>("128 threads, 16x8 grid, 6x12 tiles", d, n, n, big, 1);
+            run<1024, 16, 6, 72>("1024 threads, 32x32 grid, 3x3 tiles", d, n, n, big, 1);
             run<256, 16, 6, 60>("v7 block GJ on DMMA", d, n, n, big, 1);
             run<256, 16, 6, 60>("v7 partial m=6", d, n, 6, big, 1);
             run<256, 16, 6, 0>("baseline partial m=6", d, n, 6, big, 1);
