@@ -110,7 +110,9 @@ typedef enum {
  *
  * OUTPUT record of one blanket:
  *   w0 : int32 status | int32 n_new_edges
- *   w1 : int32 newton_iters | int32 flags
+ *   w1 : int32 newton_iters | int32 flags   (bit 0: a line search of the iterative fit failed, bit 1: KLD infinite;
+ *                                           diagnostics: bit 4: gauge shortcut refused, eigen path taken,
+ *                                           bit 5: anchored block not positive definite, bit 6: |diag| >= 1e8)
  *   w2 : double kld        (value of the projected KLD at the solution, NFR only)
  *   w3 : double reserved
  *   then n_new_edges slots, slot size fixed per (algorithm, dim, topology):

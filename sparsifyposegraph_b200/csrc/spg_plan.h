@@ -62,9 +62,9 @@ inline void plan_smem(KernelParams &p) {
     p.buf2_doubles = (nk >= 2) ? (b1 > sweep_scratch ? b1 : sweep_scratch) : 0; // eigenvectors / sweep scratch
     o += p.buf2_doubles;
     p.off_small = o;
-    // small: w[kmax] order[kmax](int) cs[kmax+2] red[8] weights[pairs] heapw[pairs] heapab[pairs] (int2)
+    // small: w[kmax] order[kmax](int) cs[kmax+2] red[34] weights[pairs] heapw[pairs] heapab[pairs] (int2)
     //        tree[2*max(pairs,1)] (int) uf[nk] (int) Lfac[nk*D*D] logd[nk] misc[16]
-    o += kmax + (kmax + 1) / 2 + (kmax + kmax / 2 + 4) + 8 + pairs + pairs + pairs + (pairs > 0 ? pairs : 1) + (nk + 1) / 2 + 1 +
+    o += kmax + (kmax + 1) / 2 + (kmax + kmax / 2 + 4) + 34 + pairs + pairs + pairs + (pairs > 0 ? pairs : 1) + (nk + 1) / 2 + 1 +
          nk * D * D + nk + 16;
     p.off_glc = o;
     p.glc_doubles = 0;

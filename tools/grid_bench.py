@@ -76,7 +76,7 @@ def main():
         prof = False
         if os.environ.get("SPG_GRID_LOG") and b1 > b0:
             nvs_ = rd["records"][ro[:-1]].view(np.int32).reshape(-1, 2)[:, 0]
-            prof = int(nvs_.max()) >= 38 and not getattr(main, "profiled", False)
+            prof = int(nvs_.max()) >= 30
             if prof:
                 import ctypes as C
                 L = capi.lib()
@@ -95,7 +95,11 @@ def main():
                      "new_jac", "sigma", "x_inv", "write", "-", "-"]
             print("stage cycles of a round with a", int(nvs_.max()), "vertex blanket:", {n: int(c) for n, c in zip(names, cyc) if c}, file=sys.stderr)
             st = np.asarray(local).view(np.int32)
-            print("   statuses:", [int(np.asarray(local)[oo[b] - oo[b0]:oo[b] - oo[b0] + 1].view(np.int32)[0]) for b in range(b0, b1)][:20], file=sys.stderr)
+            for b in range(b0, b1):
+                hdr = np.asarray(local)[oo[b] - oo[b0]:oo[b] - oo[b0] + 2]
+                i32 = hdr.view(np.int32)
+                if i32[3]:
+                    print(f"   blanket with {int(nvs_[b])} vertices: status {int(i32[0])} flags {int(i32[3])} kld-slot {hdr[1:2].view(np.float64)[0]:.4g}", file=sys.stderr)
         if world > 1:
             out = distributed.gather_outputs(np.ascontiguousarray(local, dtype=np.uint64),
                                              [int(oo[bounds[r + 1]] - oo[bounds[r]]) for r in range(world)], None,
