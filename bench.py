@@ -140,10 +140,30 @@ def run_reference(args, rank, world):
                                      "Eigen/g2o/iSAM/CHOLMOD and cannot be built offline"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    _emit(line)
+
+
+_JSON_OUT = None
+
+
+def _claim_stdout():
+    """The driver reads ONE JSON line from stdout. Libraries write there too (NCCL prints its version banner at
+    NCCL_DEBUG >= VERSION): keep a private copy of fd 1 for the JSON line and point fd 1 at stderr for everyone else."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    _claim_stdout()
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
 
 
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -173,7 +193,6 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the node-removal path has no CPU fallback")
     torch.cuda.set_device(local_rank)
-    # keep stdout to the single JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION/INFO
     os.environ["NCCL_DEBUG"] = os.environ.get("SPG_NCCL_DEBUG", "WARN")
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -343,7 +362,7 @@ def main():
             nb_total = sum(min(S, blk["B"]) for blk in sweep)
             line["cpu_baseline"] = {"value": nb_total / secs, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"first {S} blankets of each size of this run's sweep, one blanket per thread"}
-        print(json.dumps(line))
+        _emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

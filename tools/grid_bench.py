@@ -21,6 +21,9 @@ from sparsifyposegraph_b200 import capi, distributed, records as R, synth  # noq
 
 
 def main():
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")   # fd 1 goes to stderr for everything else (NCCL banner)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--rows", type=int, default=300)
     ap.add_argument("--cols", type=int, default=300)
@@ -128,7 +131,7 @@ def main():
         hist = np.bincount([l[2] for l in log])
         print("rounds by largest blanket:", {int(i): int(c) for i, c in enumerate(hist) if c}, file=sys.stderr)
     if rank == 0:
-        print(json.dumps({
+        json_out.write(json.dumps({
             "metric": "vertices marginalized/sec, graph level (plan + pack + H2D + kernels + D2H + gather + splice)",
             "value": len(which) / total, "unit": "vertices/s", "n_gpus": world, "higher_is_better": True,
             "config": {"workload": f"C5 synthetic SE3 grid {args.rows}x{args.cols} = {args.rows * args.cols} poses, {len(which)} removed "
@@ -137,7 +140,8 @@ def main():
             "remaining_edges": g.num_edges if hasattr(g, "num_edges") else None,
             "split_s": {"plan_pack": t_plan, "gpu_incl_copies_gather": t_gpu, "splice": t_apply},
             "host_share": (t_plan + t_apply) / max(total, 1e-9), "graph_build_s": t_build, "data": "synthetic",
-        }))
+        }) + "\n")
+        json_out.flush()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
