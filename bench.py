@@ -198,7 +198,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = capi.Context(local_rank)
     stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local_rank))
-    opts = capi.make_opts(R.TOPO_TREE, R.LIN_GLOBAL, 1.0)
+    opts = capi.make_opts(R.TOPO_TREE, R.LIN_GLOBAL, 1.0, flags=2)  # SPG_OPT_POSE_EDGES_ONLY: the sweep has POSE edges only
 
     # ---- data: per-size device-resident records + one mixed host round for the e2e path -------------
     sweep = make_sweep(args.blankets, rank)

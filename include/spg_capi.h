@@ -66,6 +66,10 @@ typedef struct {
                                      eigen-decomposition NFR path (disable the gauge shortcut) */
 } spg_sparsity_options;
 #define SPG_OPT_FORCE_EIGEN 1
+/* The caller guarantees that every blanket edge of the round is a POSE edge (no GLC / MULTI factors): NFR rounds
+ * of mid-sized blankets then run a leaner kernel, two blankets per SM. A record that breaks the promise is
+ * answered with SPG_BLANKET_UNSUPPORTED, never with wrong numbers. VertexRemover sets it per round. */
+#define SPG_OPT_POSE_EDGES_ONLY 2
 
 /* edge kinds inside a blanket record */
 typedef enum {

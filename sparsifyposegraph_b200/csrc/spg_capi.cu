@@ -50,6 +50,15 @@ spg_status launch_dim(spg_ctx *ctx, spg::KernelParams &kp) {
     // CTA width by the size of H (N = D * vertices): the register-tiled sweeps cover
     // N <= 12 / 32 / 48 / 96 for 32 / 64 / 128 / 256 threads (SweepGrid in spg_device.cuh)
     const int N = D * kp.max_nv;
+    // NFR rounds of POSE edges, 48 < N <= 80: lean variant, two CTAs per SM (falls through when it does not fit twice)
+    if(kp.algorithm == SPG_ALG_NFR && (kp.flags & SPG_OPT_POSE_EDGES_ONLY) && N > 48 && N <= 80) {
+        kp.lean = 1;
+        spg::plan_smem<D>(kp);
+        const spg_status st = (D == 6) ? spg_launch_6_256l(ctx, kp) : spg_launch_3_256l(ctx, kp);
+        if(st != SPG_ERR_UNSUPPORTED) return st;
+        kp.lean = 0;
+        spg::plan_smem<D>(kp);
+    }
     // working set beyond shared memory (SE3 > 19, SE2 > 39 vertices): same kernel over a global workspace
     if((size_t) kp.total_doubles * sizeof(double) > ctx->smem_optin)
         return D == 6 ? spg_launch_6_spill(ctx, kp) : spg_launch_3_spill(ctx, kp);

@@ -64,5 +64,7 @@ spg_status spg_launch_6_64(spg_ctx *, spg::KernelParams &);
 spg_status spg_launch_6_128(spg_ctx *, spg::KernelParams &);
 spg_status spg_launch_6_256(spg_ctx *, spg::KernelParams &);
 spg_status spg_launch_6_512(spg_ctx *, spg::KernelParams &);
+spg_status spg_launch_3_256l(spg_ctx *, spg::KernelParams &);  // lean: 256 threads, 128 registers, two CTAs per SM
+spg_status spg_launch_6_256l(spg_ctx *, spg::KernelParams &);
 spg_status spg_launch_3_spill(spg_ctx *, spg::KernelParams &); // 256 threads, buffers in global memory
 spg_status spg_launch_6_spill(spg_ctx *, spg::KernelParams &);

@@ -518,9 +518,10 @@ template <> struct SweepGrid<512> { static constexpr int T = 16, TS0 = 4, TS1 = 
 // (Blocked variants were measured and dropped: a per-vertex rank-6 sweep took 186k vs 100k cycles at
 // k = 90 and a rank-2 sweep 79k vs 78k — the extra panel operands spill next to the 6 x 6 tile, and the
 // kernel is issue-latency bound at 8 warps per SM rather than barrier bound. See DESIGN.md §3.)
-template <int D, int NT>
+// LEAN: the 256-thread CTA built for two residents per SM (128 registers): the tile shapes of the 512-thread grid.
+template <int D, int NT, bool LEAN = false>
 __device__ __forceinline__ int sweep_spd_auto(double *A, int n, int ld, int nsweep, double *scratch) {
-    using G = SweepGrid<NT>;
+    using G = SweepGrid<LEAN ? 512 : NT>;
     if(n <= G::T * G::TS0) return sweep_spd<NT, G::T, G::TS0>(A, n, ld, nsweep, scratch) ? 1 : 0;
     if(n <= G::T * G::TS1) return sweep_spd<NT, G::T, G::TS1>(A, n, ld, nsweep, scratch) ? 1 : 0;
     return -1;

@@ -500,7 +500,7 @@ spg_round_in VertexRemover::roundDescriptor() const {
     rin.opts.lin_point = _opts.linPoint;
     rin.opts.chord_ratio = _opts.chordRatio;
     rin.opts.include_intra_clique = _opts.includeIntraClique;
-    rin.opts.flags = _opts.flags;
+    rin.opts.flags = _opts.flags | (_round.poseOnly ? SPG_OPT_POSE_EDGES_ONLY : 0);
     rin.n_blankets = (int32_t) _round.units.size();
     rin.rec_off = _round.recOff.data();
     rin.records = _round.records.data();
@@ -600,6 +600,7 @@ spg_status VertexRemover::planRound() {
     _round.recOff.assign(1, 0);
     _round.outOff.assign(1, 0);
     std::vector<uint64_t> rec;
+    bool poseOnly = true;
     for(const RemovalUnit &u : _round.units) {
         TopologyProvider *t = chooseTopologyProvider(u);
         if(!t) {
@@ -611,6 +612,7 @@ spg_status VertexRemover::planRound() {
             return SPG_ERR_UNSUPPORTED;
         }
         tp = t;
+        for(int ei : u.edges) poseOnly = poseOnly && (_graph->edges[ei].kind == SPG_EDGE_POSE);
         if(!packUnit(u, rec)) {
             error = "Local linearisation point on a non-star blanket needs the subgraph optimiser (not on this path)";
             return SPG_ERR_UNSUPPORTED;
@@ -622,6 +624,7 @@ spg_status VertexRemover::planRound() {
         stats.max_blanket_vertices = std::max<int>(stats.max_blanket_vertices, (int) (u.removed.size() + u.kept.size()));
     }
     _round.algorithm = tp->algorithm();
+    _round.poseOnly = poseOnly;
     if(_round.algorithm == SPG_ALG_GLC) {
         // asserts of TopologyProviderGLC::topology (src/topology_provider_glc.cpp:107-111)
         if(!(_opts.topology == SparsityOptions::Dense || _opts.topology == SparsityOptions::Tree) ||

@@ -153,6 +153,7 @@ public:
         std::vector<uint64_t> records;
         std::vector<int64_t> recOff, outOff;
         int algorithm = SPG_ALG_NFR;
+        bool poseOnly = false;       // every blanket edge of the round is a POSE edge (SPG_OPT_POSE_EDGES_ONLY)
     };
     spg_status beginRemoval(const std::vector<int> &toRemove);
     spg_status planRound();

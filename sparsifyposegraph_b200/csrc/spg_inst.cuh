@@ -8,7 +8,7 @@
 
 namespace {
 #define set_err spg_set_err
-template <int D, int NT, bool SPILL = false>
+template <int D, int NT, bool SPILL = false, bool LEAN = false>
 spg_status launch_bucket(spg_ctx *ctx, spg::KernelParams &kp) {
     static std::mutex mu;
     static size_t configured = 0;
@@ -21,13 +21,14 @@ spg_status launch_bucket(spg_ctx *ctx, spg::KernelParams &kp) {
     if(!SPILL) {
         std::lock_guard<std::mutex> lk(mu);
         if(smem > configured) {
-            SPG_CUDA(cudaFuncSetAttribute(spg::blanket_kernel<D, NT, SPILL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            SPG_CUDA(cudaFuncSetAttribute(spg::blanket_kernel<D, NT, SPILL, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int) ctx->smem_optin));
             configured = ctx->smem_optin;
         }
     }
     int per_sm = 0;
-    SPG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, spg::blanket_kernel<D, NT, SPILL>, NT, smem));
+    SPG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, spg::blanket_kernel<D, NT, SPILL, LEAN>, NT, smem));
+    if(LEAN && per_sm < 2) return SPG_ERR_UNSUPPORTED; // the caller falls back to the one-CTA-per-SM variant
     if(per_sm < 1) per_sm = 1;
     int grid = std::min<int64_t>(kp.n_list, (int64_t) per_sm * ctx->sm_count);
     if(grid < 1) return SPG_OK;
@@ -63,7 +64,7 @@ spg_status launch_bucket(spg_ctx *ctx, spg::KernelParams &kp) {
             }
         }
     }
-    spg::blanket_kernel<D, NT, SPILL><<<grid, NT, smem, ctx->stream>>>(kp);
+    spg::blanket_kernel<D, NT, SPILL, LEAN><<<grid, NT, smem, ctx->stream>>>(kp);
     SPG_CUDA(cudaGetLastError());
     ctx->launches++;
     return SPG_OK;

@@ -232,8 +232,10 @@ __device__ bool assemble_glc_edge(const uint64_t *ew, const double *s_pose, doub
 // SPILL = true: the variant for blankets whose working set exceeds shared memory. Same code; the record is
 // read in place and every buffer of the shared-memory plan lives in a per-CTA slice of a global workspace
 // (served by L1/L2). A separate instantiation so that the on-chip variant keeps LDS/STS addressing.
-template <int D, int NT, bool SPILL = false>
-__global__ void __launch_bounds__(NT, (NT >= 256) ? 1 : (NT == 128 ? 3 : 512 / NT)) blanket_kernel(const KernelParams P) {
+// LEAN = true: 256 threads at 128 registers with a small buf2, two CTAs per SM, for NFR rounds made of POSE edges
+// only (N <= 80): two independent pivot chains per SM.
+template <int D, int NT, bool SPILL = false, bool LEAN = false>
+__global__ void __launch_bounds__(NT, LEAN ? 2 : ((NT >= 256) ? 1 : (NT == 128 ? 3 : 512 / NT))) blanket_kernel(const KernelParams P) {
     extern __shared__ double smem_dyn[];
     double *smem = smem_dyn;
     if constexpr(SPILL) smem = P.gws + (size_t) blockIdx.x * (size_t) P.gws_stride;
@@ -383,7 +385,7 @@ __global__ void __launch_bounds__(NT, (NT >= 256) ? 1 : (NT == 128 ? 3 : 512 / N
         double *T = H + m + (size_t) m * ldH; // Lambda_t in place, leading dimension ldH
         if(status == SPG_BLANKET_OK) {
             // register-tiled partial sweep of the m removed pivots: H_kk <- H_kk - H_km H_mm^-1 H_mk
-            const int sw = sweep_spd_auto<D, NT>(H, N, ldH, m, buf1);
+            const int sw = sweep_spd_auto<D, NT, LEAN>(H, N, ldH, m, buf1);
             if(sw == 0) status = SPG_BLANKET_NOT_PD_MARGINAL;
             if(sw > 0) {
                 // upper triangle mirrored to the lower (vertex_remover.cpp:447-449)
@@ -487,7 +489,7 @@ __global__ void __launch_bounds__(NT, (NT >= 256) ? 1 : (NT == 128 ? 3 : 512 / N
                         if(s_misc[8] == 0) status = SPG_BLANKET_NOT_PD_CHOWLIU;
                     }
                 } else {
-                    const int sw = sweep_spd_auto<D, NT>(Lc, k, ldk, k, buf2);
+                    const int sw = sweep_spd_auto<D, NT, LEAN>(Lc, k, ldk, k, buf2);
                     if(sw == 0) status = SPG_BLANKET_NOT_PD_CHOWLIU;
                     if(sw < 0) {
                         if(!chol_lower<NT>(Lc, k, ldk)) status = SPG_BLANKET_NOT_PD_CHOWLIU;
@@ -626,7 +628,7 @@ __global__ void __launch_bounds__(NT, (NT >= 256) ? 1 : (NT == 128 ? 3 : 512 / N
                 int swg;
                 if(g_ready) swg = s_misc[9];
                 else {
-                    swg = sweep_spd_auto<D, NT>(buf1, kk, ldg, kk, buf2);
+                    swg = sweep_spd_auto<D, NT, LEAN>(buf1, kk, ldg, kk, buf2);
                     if(swg < 0) {
                         swg = chol_lower<NT>(buf1, kk, ldg) ? 1 : 0;
                         if(swg) chol_inverse_inplace<NT>(buf1, kk, ldg, buf2);

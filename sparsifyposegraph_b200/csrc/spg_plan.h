@@ -12,7 +12,7 @@ struct KernelParams {
     int32_t algorithm, topology;
     double chord_ratio;
     int32_t flags;               // bit 0: force the general (eigen-decomposition) NFR path
-    int32_t pad0;
+    int32_t lean;                // buf2 holds sweep / J Sigma scratch only (NFR rounds of POSE edges): two CTAs per SM
     int32_t n_list;              // blankets handled by this launch
     const int32_t *list;         // their indices (NULL: identity)
     const int64_t *rec_off;
@@ -60,6 +60,10 @@ inline void plan_smem(KernelParams &p) {
     o += p.buf1_doubles;
     p.off_buf2 = o;
     p.buf2_doubles = (nk >= 2) ? (b1 > sweep_scratch ? b1 : sweep_scratch) : 0; // eigenvectors / sweep scratch
+    if(p.lean) { // pivot columns of a sweep (392) or Tm = J Sigma of the closed form (one D x 2D block per tree edge)
+        const int tm = nk * D * 2 * D;
+        p.buf2_doubles = tm > 400 ? tm : 400;
+    }
     o += p.buf2_doubles;
     p.off_small = o;
     // small: w[kmax] order[kmax](int) cs[kmax+2] red[34] weights[pairs] heapw[pairs] heapab[pairs] (int2)

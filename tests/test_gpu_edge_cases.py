@@ -157,3 +157,22 @@ def test_blankets_beyond_shared_memory(ctx, oracle, dim, n, algorithm, topology)
             else:
                 assert eg["rank"] == er["rank"]
                 assert rel(eg["W"].T @ eg["W"], er["W"].T @ er["W"]) <= 1e-9
+
+
+@pytest.mark.parametrize("n", [9, 10, 12, 13])
+@pytest.mark.parametrize("topology", [R.TOPO_TREE, R.TOPO_SUBGRAPH])
+def test_pose_only_promise_runs_the_lean_kernel(ctx, oracle, n, topology):
+    """SPG_OPT_POSE_EDGES_ONLY (flags = 2): NFR rounds with 48 < 6 n <= 80 take the 256-thread / two-CTAs-per-SM
+    variant with a small third buffer. Same results as the oracle, on the shortcut and on the forced eigen path."""
+    nb = 6
+    blk = synth.make_blankets(n, nb, dim=6, variant="ring", seed=100 + n)
+    nk = R.n_kept_of(blk["records"], blk["rec_off"])
+    recs = [blk["records"][blk["rec_off"][b]:blk["rec_off"][b + 1]] for b in range(nb)]
+    for flags in (2, 3):
+        if topology == R.TOPO_SUBGRAPH and flags == 3:
+            continue
+        for g, r in both(ctx, oracle, 6, recs, list(nk), R.ALG_NFR, topology, flags=flags):
+            assert g["status"] == r["status"] == 0
+            assert [e["v"] for e in g["edges"]] == [e["v"] for e in r["edges"]]
+            for eg, er in zip(g["edges"], r["edges"]):
+                assert rel(eg["info"], er["info"]) <= 1e-9
