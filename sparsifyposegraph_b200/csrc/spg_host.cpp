@@ -307,19 +307,56 @@ std::vector<int> VertexRemover::markovBlanketEdges(const std::vector<int> &mb, c
 }
 
 bool VertexRemover::buildUnit(int root, int listIndex, const std::set<int> &toRemoveSet, RemovalUnit &u) const {
-    u = RemovalUnit();
+    u.removed.clear(); u.kept.clear(); u.edges.clear(); u.ridx.clear(); u.kidx.clear(); // keep the capacity
     u.listIndex = listIndex;
     std::vector<int> vmarkov;
     if(_opts.topology == SparsityOptions::Dense || _opts.topology == SparsityOptions::CliqueyDense) {
         vmarkov = extendedMarkovBlanketVertices(root, toRemoveSet, u.removed);
     } else {
-        vmarkov = markovBlanketVertices(root);
+        // single removal (Tree / Subgraph / CliqueySubgraph): the same sets as markovBlanketVertices / -Edges with
+        // sorted vectors instead of node-based sets — this runs once per pending vertex and round
+        const GraphVertex *rv = _graph->vertex(root);
+        std::vector<int> &mb = vmarkov;
+        mb.push_back(root);
+        if(rv)
+            for(int ei : rv->edges)
+                for(int id : _graph->edges[ei].v) mb.push_back(id);
+        std::sort(mb.begin(), mb.end());
+        mb.erase(std::unique(mb.begin(), mb.end()), mb.end());
         u.removed.push_back(root);
+        for(int id : mb)
+            if(id != root) u.kept.push_back(id);
+        std::vector<int> &es = u.edges;
+        for(int id : mb) {
+            const GraphVertex *v = _graph->vertex(id);
+            if(!v) continue;
+            for(int ei : v->edges) {
+                const GraphEdge &e = _graph->edges[ei];
+                bool is_markov = true, found_hub = false;
+                for(int x : e.v) {
+                    if(!std::binary_search(mb.begin(), mb.end(), x)) { is_markov = false; break; }
+                    if(x == root) found_hub = true;
+                }
+                if(is_markov && (_opts.includeIntraClique || found_hub)) es.push_back(ei);
+            }
+        }
+        std::sort(es.begin(), es.end(), [&](int a, int b) {
+            const GraphEdge &x = _graph->edges[a], &y = _graph->edges[b];
+            if(x.uidMajor != y.uidMajor) return x.uidMajor < y.uidMajor;
+            if(x.uidMinor != y.uidMinor) return x.uidMinor < y.uidMinor;
+            return a < b;
+        });
+        es.erase(std::unique(es.begin(), es.end()), es.end());
+        for(int id : u.removed) u.ridx.push_back(_graph->index.at(id));
+        for(int id : u.kept) u.kidx.push_back(_graph->index.at(id));
+        return !es.empty();
     }
     std::set<int> rem(u.removed.begin(), u.removed.end());
     for(int id : vmarkov)
         if(!rem.count(id)) u.kept.push_back(id);
     u.edges = markovBlanketEdges(vmarkov, u.removed);
+    for(int id : u.removed) u.ridx.push_back(_graph->index.at(id));
+    for(int id : u.kept) u.kidx.push_back(_graph->index.at(id));
     return !u.edges.empty();
 }
 
@@ -485,6 +522,11 @@ spg_status VertexRemover::beginRemoval(const std::vector<int> &toRemove) {
     _round = Round();
     _unitCache.assign(toRemove.size(), RemovalUnit());
     _unitBuilt.assign(toRemove.size(), 0);
+    _rootIdx.assign(toRemove.size(), -1);
+    for(size_t i = 0; i < toRemove.size(); i++) {
+        auto it = _graph->index.find(toRemove[i]);
+        if(it != _graph->index.end()) _rootIdx[i] = it->second;
+    }
     _stamp.assign(_graph->verts.size(), 0);
     _touchHead.assign(_graph->verts.size(), -1);
     _removedBy.assign(_graph->verts.size(), -1);
@@ -536,7 +578,7 @@ spg_status VertexRemover::planRound() {
         std::vector<std::pair<int, int>> shared;
         for(size_t i = 0; i < toRemove.size(); i++) {
             if(_done[i]) continue;
-            if(!_graph->hasVertex(toRemove[i])) { // merged into an earlier extended blanket (:91)
+            if(_rootIdx[i] < 0 || !_graph->verts[_rootIdx[i]].alive) { // merged into an earlier extended blanket (:91)
                 _done[i] = 1;
                 _remaining--;
                 continue;
@@ -544,8 +586,8 @@ spg_status VertexRemover::planRound() {
             RemovalUnit &u = _unitCache[i];
             bool stale = !_unitBuilt[i];
             if(!stale) {
-                for(int x : u.removed) if(_stamp[_graph->index.at(x)] >= _unitBuilt[i]) { stale = true; break; }
-                if(!stale) for(int x : u.kept) if(_stamp[_graph->index.at(x)] >= _unitBuilt[i]) { stale = true; break; }
+                for(int xi : u.ridx) if(_stamp[xi] >= _unitBuilt[i]) { stale = true; break; }
+                if(!stale) for(int xi : u.kidx) if(_stamp[xi] >= _unitBuilt[i]) { stale = true; break; }
             }
             if(stale) {
                 if(!buildUnit(toRemove[i], (int) i, _toRemoveSet, u)) {
@@ -558,12 +600,10 @@ spg_status VertexRemover::planRound() {
             hit.clear();
             shared.clear();
             auto note = [&](int c) { if(std::find(hit.begin(), hit.end(), c) == hit.end()) hit.push_back(c); };
-            for(int x : u.removed) {
-                const int xi = _graph->index.at(x);
+            for(int xi : u.ridx) {
                 for(int t = _touchHead[xi]; t >= 0; t = _touchNext[t]) note(find(_touchRegion[t]));
             }
-            for(int x : u.kept) {
-                const int xi = _graph->index.at(x);
+            for(int xi : u.kidx) {
                 if(_removedBy[xi] >= 0) note(find(_removedBy[xi]));
                 comps.clear();
                 for(int t = _touchHead[xi]; t >= 0; t = _touchNext[t]) {
@@ -580,16 +620,15 @@ spg_status VertexRemover::planRound() {
             parent.push_back(rid);
             const bool select = hit.empty();
             for(int c : hit) parent[find(c)] = rid;
-            auto reg = [&](int x, bool removed) {
-                const int xi = _graph->index.at(x);
+            auto reg = [&](int xi, bool removed) {
                 if(_touchHead[xi] < 0 && _removedBy[xi] < 0) touched.push_back(xi);
                 _touchNext.push_back(_touchHead[xi]);
                 _touchRegion.push_back(rid);
                 _touchHead[xi] = (int) _touchNext.size() - 1;
                 if(removed) _removedBy[xi] = rid;
             };
-            for(int x : u.removed) reg(x, true);
-            for(int x : u.kept) reg(x, false);
+            for(int xi : u.ridx) reg(xi, true);
+            for(int xi : u.kidx) reg(xi, false);
             if(select) units.push_back(u);
         }
         for(int xi : touched) { _touchHead[xi] = -1; _removedBy[xi] = -1; }
@@ -646,8 +685,8 @@ void VertexRemover::applyRound(const uint64_t *out) {
         const int32_t *oh = reinterpret_cast<const int32_t *>(o);
         const int bstatus = oh[0], nnew = oh[1];
         if(bstatus != SPG_BLANKET_OK) stats.n_failed++;
-        for(int id : u.removed) _stamp[_graph->index.at(id)] = _planNo; // cached blankets containing these are stale
-        for(int id : u.kept) _stamp[_graph->index.at(id)] = _planNo;
+        for(int xi : u.ridx) _stamp[xi] = _planNo; // cached blankets containing these are stale
+        for(int xi : u.kidx) _stamp[xi] = _planNo;
         for(int ei : u.edges) _graph->removeEdge(ei);
         for(int id : u.removed) _graph->removeVertex(id);
         const int nk = (int) u.kept.size();

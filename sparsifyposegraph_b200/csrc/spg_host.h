@@ -126,6 +126,7 @@ struct RemovalUnit {
     std::vector<int> removed;        // ascending id (toRemoveNow)
     std::vector<int> kept;           // ascending id
     std::vector<int> edges;          // blanket edges, canonical order
+    std::vector<int> ridx, kidx;     // Graph::verts indices of removed / kept (scheduler: no id lookups per round)
 };
 
 class VertexRemover {
@@ -175,6 +176,7 @@ private:
     size_t _remaining = 0;
     // scheduler state: cached blankets of the pending vertices (re-extracted when stale) and per-round scratch
     std::vector<RemovalUnit> _unitCache;
+    std::vector<int> _rootIdx;              // Graph::verts index of every list entry (-1: not in the graph)
     std::vector<int> _unitBuilt;            // planning pass that extracted the cached blanket (0: never)
     std::vector<int> _stamp;                // per vertex index: last planning pass whose round touched it
     std::vector<int> _touchHead, _touchNext, _touchRegion, _removedBy;

@@ -195,18 +195,28 @@ def make_grid_graph(rows, cols, dim=6, seed=SEED, sigma_t=0.05, sigma_r=0.02):
     return poses, edges, meas, info
 
 
-def grid_removal_order(rows, cols, sparsity=10, colour_mod=4):
+def grid_removal_order(rows, cols, sparsity=10, colour_mod=4, order=None, seed=SEED):
     """Removal list of BASELINE.json configs[4] (synthetic grid, 90 % removal at sparsity 10): the ids
-    globalDecimate selects (decimation.cpp:36-49: i in [4, V-1] with i % sparsity != 0), ordered by colour class
-    (r % m, c % m) and then by id. The reference removes in list order; in raster order the wavefront rounds are
-    a handful of blankets wide, in colour order thousands. colour_mod = 0: raster order."""
+    globalDecimate selects (decimation.cpp:36-49: i in [4, V-1] with i % sparsity != 0). The reference removes in
+    list order, so the order is part of the input:
+      "raster"  ascending ids: wavefront rounds a handful of blankets wide (SURVEY.md section 8d, C5);
+      "colour"  by colour class (r % m, c % m), then id: rounds of thousands, but hub blankets of 40-70 vertices
+                at the end of the removal;
+      "random"  seeded permutation: ~45 rounds whatever the grid size, blankets stay below 18 vertices.
+    order=None keeps the historical meaning of colour_mod (0: raster, m: colour)."""
     V = rows * cols
     ids = np.arange(4, V, dtype=np.int32)
     ids = ids[ids % sparsity != 0]
-    if colour_mod:
+    if order is None:
+        order = "colour" if colour_mod else "raster"
+    if order == "colour":
         r, c = np.divmod(ids, cols)
         colour = (r % colour_mod) * colour_mod + (c % colour_mod)
         ids = ids[np.lexsort((ids, colour))]
+    elif order == "random":
+        ids = np.random.default_rng(seed).permutation(ids)
+    elif order != "raster":
+        raise ValueError(order)
     return np.ascontiguousarray(ids, dtype=np.int32)
 
 

@@ -120,16 +120,17 @@ def test_glc_dense_global_decimation(ctx, oracle, name):
     print(f"{name} GLC dense: {st['n_blankets']} blankets, {st['n_rounds']} rounds, max blanket {st['max_blanket_vertices']}, worst {worst:.2e}")
 
 
-@pytest.mark.parametrize("alg,topo", [(R.ALG_NFR, R.TOPO_TREE), (R.ALG_GLC, R.TOPO_TREE)])
-def test_synthetic_grid_90_percent_removal(ctx, oracle, alg, topo):
-    """BASELINE.json configs[4] scaled to 60 x 60 poses: SE3 grid, 90 % of the vertices removed in colour order,
+@pytest.mark.parametrize("alg,topo,order", [(R.ALG_NFR, R.TOPO_TREE, "colour"), (R.ALG_GLC, R.TOPO_TREE, "colour"),
+                                            (R.ALG_NFR, R.TOPO_TREE, "random")])
+def test_synthetic_grid_90_percent_removal(ctx, oracle, alg, topo, order):
+    """BASELINE.json configs[4] scaled to 60 x 60 poses: SE3 grid, 90 % of the vertices removed in colour / random order,
     against the oracle's sequential loop on the same list."""
     from sparsifyposegraph_b200 import capi, synth
     rows, cols = 60, 60
     data = synth.make_grid_graph(rows, cols, dim=6)
     g = synth.fill_graph(capi.Graph(dim=6), *data)
     o = synth.fill_graph(oracle.Graph(dim=6), *data)
-    which = synth.grid_removal_order(rows, cols, 10, 4)
+    which = synth.grid_removal_order(rows, cols, 10, 4, order)
     st = g.marginalize(ctx, which, capi.make_opts(topo, R.LIN_GLOBAL), alg)
     assert o.marginalize(which, oracle.make_opts(topo, R.LIN_GLOBAL), alg) == 0
     assert st["n_failed"] == 0 and st["n_blankets"] == len(which)

@@ -98,18 +98,18 @@ def test_compute_substitute_edge_matches_oracle(oracle, name):
     assert checked >= 5
 
 
-@pytest.mark.parametrize("colour_mod", [0, 4])
-def test_round_scheduler_equals_sequential_removal_on_grid(oracle, colour_mod):
+@pytest.mark.parametrize("order", ["raster", "colour", "random"])
+def test_round_scheduler_equals_sequential_removal_on_grid(oracle, order):
     """BASELINE.json configs[4] at small scale: the wavefront rounds (product scheduler; blankets computed by the
     oracle here, no GPU) must leave exactly the graph of the one-at-a-time loop of VertexRemover::remove
-    (vertex_remover.cpp:83-140), in raster order (narrow rounds) and in colour order (wide rounds)."""
+    (vertex_remover.cpp:83-140), in raster order (narrow rounds), in colour order and in random order (wide rounds)."""
     from sparsifyposegraph_b200 import capi, synth, records as R
     from test_gpu_graph import compare_graphs
     rows, cols = 24, 28
     data = synth.make_grid_graph(rows, cols, dim=6)
     g = synth.fill_graph(capi.Graph(dim=6), *data)
     o = synth.fill_graph(oracle.Graph(dim=6), *data)
-    which = synth.grid_removal_order(rows, cols, 10, colour_mod)
+    which = synth.grid_removal_order(rows, cols, 10, 4, order)
     opts = capi.make_opts(R.TOPO_TREE, R.LIN_GLOBAL)
     capi.rounds_begin(g, which, opts, R.ALG_NFR)
     widths = []
@@ -124,5 +124,5 @@ def test_round_scheduler_equals_sequential_removal_on_grid(oracle, colour_mod):
     assert sum(widths) == len(which)
     assert o.marginalize(which, oracle.make_opts(R.TOPO_TREE, R.LIN_GLOBAL), R.ALG_NFR) == 0
     compare_graphs(g, o, tol=1e-9)
-    if colour_mod:
+    if order != "raster":
         assert max(widths) >= 25 and len(widths) < len(which) / 8
