@@ -6,6 +6,8 @@
 #include "spg_host.h"
 
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <chrono>
 #include <cmath>
 #include <cstring>
@@ -576,6 +578,49 @@ spg_status VertexRemover::planRound() {
         auto find = [&](int x) { while(parent[x] != x) { parent[x] = parent[parent[x]]; x = parent[x]; } return x; };
         std::vector<int> hit, comps;
         std::vector<std::pair<int, int>> shared;
+        // pass 1: re-extract the stale cached blankets. Extraction only reads the graph, so it is spread over the
+        // host threads (it is ~70 % of the planning time on large graphs); the selection below stays sequential.
+        {
+            std::vector<int> todo;
+            for(size_t i = 0; i < toRemove.size(); i++) {
+                if(_done[i] || _rootIdx[i] < 0 || !_graph->verts[_rootIdx[i]].alive) continue;
+                const RemovalUnit &u = _unitCache[i];
+                bool stale = !_unitBuilt[i];
+                if(!stale) {
+                    for(int xi : u.ridx) if(_stamp[xi] >= _unitBuilt[i]) { stale = true; break; }
+                    if(!stale) for(int xi : u.kidx) if(_stamp[xi] >= _unitBuilt[i]) { stale = true; break; }
+                }
+                if(stale) todo.push_back((int) i);
+            }
+            std::atomic<int> bad(-1);
+            auto work = [&](size_t b0, size_t b1) {
+                for(size_t q = b0; q < b1; q++) {
+                    const int i = todo[q];
+                    if(!buildUnit(toRemove[i], i, _toRemoveSet, _unitCache[i])) {
+                        int expect = -1;
+                        bad.compare_exchange_strong(expect, i);
+                    }
+                    _unitBuilt[i] = _planNo;
+                }
+            };
+            unsigned nthr = std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
+            if(todo.size() < 4096) nthr = 1;
+            if(nthr <= 1) work(0, todo.size());
+            else {
+                std::vector<std::thread> pool;
+                const size_t chunk = (todo.size() + nthr - 1) / nthr;
+                for(unsigned t = 0; t < nthr; t++) {
+                    const size_t b0 = std::min(todo.size(), t * chunk), b1 = std::min(todo.size(), b0 + chunk);
+                    if(b0 < b1) pool.emplace_back(work, b0, b1);
+                }
+                for(auto &th : pool) th.join();
+            }
+            if(bad.load() >= 0) {
+                // isolated vertex: the reference asserts blanketEdges.size() > 0
+                error = "vertex " + std::to_string(toRemove[bad.load()]) + " has no edges";
+                return SPG_ERR_INVALID;
+            }
+        }
         for(size_t i = 0; i < toRemove.size(); i++) {
             if(_done[i]) continue;
             if(_rootIdx[i] < 0 || !_graph->verts[_rootIdx[i]].alive) { // merged into an earlier extended blanket (:91)
@@ -584,19 +629,6 @@ spg_status VertexRemover::planRound() {
                 continue;
             }
             RemovalUnit &u = _unitCache[i];
-            bool stale = !_unitBuilt[i];
-            if(!stale) {
-                for(int xi : u.ridx) if(_stamp[xi] >= _unitBuilt[i]) { stale = true; break; }
-                if(!stale) for(int xi : u.kidx) if(_stamp[xi] >= _unitBuilt[i]) { stale = true; break; }
-            }
-            if(stale) {
-                if(!buildUnit(toRemove[i], (int) i, _toRemoveSet, u)) {
-                    // isolated vertex: the reference asserts blanketEdges.size() > 0
-                    error = "vertex " + std::to_string(toRemove[i]) + " has no edges";
-                    return SPG_ERR_INVALID;
-                }
-                _unitBuilt[i] = _planNo;
-            }
             hit.clear();
             shared.clear();
             auto note = [&](int c) { if(std::find(hit.begin(), hit.end(), c) == hit.end()) hit.push_back(c); };
