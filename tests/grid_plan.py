@@ -1,7 +1,7 @@
 """CPU-only look at the wavefront rounds of the synthetic grid workload (BASELINE.json configs[4]) under different
 removal orders: number of rounds, round widths, largest blanket, scheduler time. The blankets are computed by the
-ORACLE here (test infrastructure) — this tool is for choosing a removal order, not a benchmark.
-usage: grid_plan.py ROWS COLS ORDER   with ORDER = raster | colourM (M = modulus) | random | level"""
+ORACLE here, which is why this script lives under tests/ — it is for choosing a removal order, not a benchmark.
+usage: python tests/grid_plan.py ROWS COLS ORDER   with ORDER = raster | colourM (M = modulus) | random | level"""
 import sys
 import time
 
