@@ -134,6 +134,9 @@ void spg_destroy(spg_ctx *ctx) {
         b->release();
     if(ctx->ev0) cudaEventDestroy(ctx->ev0);
     if(ctx->ev1) cudaEventDestroy(ctx->ev1);
+    for(cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+    if(ctx->s_in) cudaStreamDestroy(ctx->s_in);
+    if(ctx->s_out) cudaStreamDestroy(ctx->s_out);
     if(ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -250,93 +253,143 @@ spg_status spg_remove_round(spg_ctx *ctx, const spg_round_in *in, spg_round_out 
     const int dim = in->dim;
     const int64_t rec_words = in->rec_off[nb];
     const int64_t out_words = in->out_off[nb];
-
-    // ---- bucket by blanket size -------------------------------------------------------------
-    static const int bounds6[] = {3, 4, 5, 6, 7, 8, 10, 12, 14, 16, 20, 24, 32, 48, 64, 128, 1 << 30};
-    std::vector<Bucket> buckets(sizeof(bounds6) / sizeof(int));
     for(int b = 0; b < nb; b++) {
         const int32_t *h = reinterpret_cast<const int32_t *>(in->records + in->rec_off[b]);
-        const int nv = h[0], ne = h[2];
         const int rw = (int) (in->rec_off[b + 1] - in->rec_off[b]);
-        if(h[3] != dim || h[4] > rw || nv < 1) {
+        if(h[3] != dim || h[4] > rw || h[0] < 1) {
             set_err("malformed blanket record " + std::to_string(b));
             return SPG_ERR_INVALID;
         }
-        int bi = 0;
-        while(nv > bounds6[bi]) bi++;
-        Bucket &B = buckets[bi];
-        B.list.push_back(b);
-        B.max_nv = std::max(B.max_nv, nv);
-        B.max_e = std::max(B.max_e, ne);
-        B.max_rec = std::max(B.max_rec, (int) h[4]);
     }
 
-    // ---- H2D ---------------------------------------------------------------------------------
+    // ---- chunks: contiguous runs of blankets, so that the H2D copy of chunk c+1, the kernels of chunk c and the
+    // D2H copy of chunk c-1 overlap (three streams, events in between). Every chunk owns its own slice of the
+    // device buffers (same offsets as on the host), so nothing is double-buffered. Small rounds: one chunk.
+    const bool dbg = (out->dbg_target && out->dbg_target_off) || (out->dbg_weights && out->dbg_weights_off);
+    const int64_t total_bytes = (rec_words + out_words) * 8;
+    int nchunks = (int) std::min<int64_t>(32, total_bytes / ((int64_t) 48 << 20));
+    if(nchunks < 1 || dbg) nchunks = 1;
+    std::vector<int> cb(nchunks + 1, nb);
+    cb[0] = 0;
+    for(int c = 1, b = 0; c < nchunks; c++) { // split by bytes of records + outputs
+        const int64_t goal = total_bytes / nchunks * c;
+        while(b < nb && (in->rec_off[b] + in->out_off[b]) * 8 < goal) b++;
+        cb[c] = b;
+    }
+    if(!ctx->s_in) {
+        SPG_CUDA(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+        SPG_CUDA(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+    }
+    while((int) ctx->ev_pool.size() < 2 * nchunks) {
+        cudaEvent_t e;
+        SPG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->ev_pool.push_back(e);
+    }
+
     SPG_CUDA(ctx->d_rec.reserve((size_t) rec_words * 8));
     SPG_CUDA(ctx->d_recoff.reserve((size_t) (nb + 1) * 8));
     SPG_CUDA(ctx->d_outoff.reserve((size_t) (nb + 1) * 8));
     SPG_CUDA(ctx->d_out.reserve((size_t) out_words * 8));
     SPG_CUDA(ctx->d_list.reserve((size_t) nb * 4));
-    SPG_CUDA(cudaMemcpyAsync(ctx->d_rec.p, in->records, (size_t) rec_words * 8, cudaMemcpyHostToDevice, ctx->stream));
-    SPG_CUDA(cudaMemcpyAsync(ctx->d_recoff.p, in->rec_off, (size_t) (nb + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-    SPG_CUDA(cudaMemcpyAsync(ctx->d_outoff.p, in->out_off, (size_t) (nb + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-    std::vector<int32_t> flat;
-    flat.reserve(nb);
-    for(auto &B : buckets) flat.insert(flat.end(), B.list.begin(), B.list.end());
-    SPG_CUDA(cudaMemcpyAsync(ctx->d_list.p, flat.data(), (size_t) nb * 4, cudaMemcpyHostToDevice, ctx->stream));
+    SPG_CUDA(cudaMemcpyAsync(ctx->d_recoff.p, in->rec_off, (size_t) (nb + 1) * 8, cudaMemcpyHostToDevice, ctx->s_in));
+    SPG_CUDA(cudaMemcpyAsync(ctx->d_outoff.p, in->out_off, (size_t) (nb + 1) * 8, cudaMemcpyHostToDevice, ctx->s_in));
     int64_t tgt_n = 0, wts_n = 0;
     if(out->dbg_target && out->dbg_target_off) {
         tgt_n = out->dbg_target_off[nb];
         SPG_CUDA(ctx->d_tgt.reserve((size_t) tgt_n * 8 + 8));
         SPG_CUDA(ctx->d_tgtoff.reserve((size_t) (nb + 1) * 8));
-        SPG_CUDA(cudaMemcpyAsync(ctx->d_tgtoff.p, out->dbg_target_off, (size_t) (nb + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-        SPG_CUDA(cudaMemsetAsync(ctx->d_tgt.p, 0, (size_t) tgt_n * 8 + 8, ctx->stream));
+        SPG_CUDA(cudaMemcpyAsync(ctx->d_tgtoff.p, out->dbg_target_off, (size_t) (nb + 1) * 8, cudaMemcpyHostToDevice, ctx->s_in));
+        SPG_CUDA(cudaMemsetAsync(ctx->d_tgt.p, 0, (size_t) tgt_n * 8 + 8, ctx->s_in));
     }
     if(out->dbg_weights && out->dbg_weights_off) {
         wts_n = out->dbg_weights_off[nb];
         SPG_CUDA(ctx->d_wts.reserve((size_t) wts_n * 8 + 8));
         SPG_CUDA(ctx->d_wtsoff.reserve((size_t) (nb + 1) * 8));
-        SPG_CUDA(cudaMemcpyAsync(ctx->d_wtsoff.p, out->dbg_weights_off, (size_t) (nb + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-        SPG_CUDA(cudaMemsetAsync(ctx->d_wts.p, 0, (size_t) wts_n * 8 + 8, ctx->stream));
+        SPG_CUDA(cudaMemcpyAsync(ctx->d_wtsoff.p, out->dbg_weights_off, (size_t) (nb + 1) * 8, cudaMemcpyHostToDevice, ctx->s_in));
+        SPG_CUDA(cudaMemsetAsync(ctx->d_wts.p, 0, (size_t) wts_n * 8 + 8, ctx->s_in));
     }
 
-    // ---- kernels -----------------------------------------------------------------------------
-    SPG_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
-    size_t list_pos = 0;
-    for(auto &B : buckets) {
-        if(B.list.empty()) continue;
-        spg::KernelParams kp{};
-        kp.algorithm = in->algorithm;
-        kp.topology = in->opts.topology;
-        kp.chord_ratio = in->opts.chord_ratio;
-        kp.flags = in->opts.flags;
-        kp.n_list = (int32_t) B.list.size();
-        kp.list = reinterpret_cast<const int32_t *>(ctx->d_list.p) + list_pos;
-        list_pos += B.list.size();
-        kp.rec_off = reinterpret_cast<const int64_t *>(ctx->d_recoff.p);
-        kp.records = reinterpret_cast<const uint64_t *>(ctx->d_rec.p);
-        kp.out_off = reinterpret_cast<const int64_t *>(ctx->d_outoff.p);
-        kp.out = reinterpret_cast<uint64_t *>(ctx->d_out.p);
-        kp.dbg_target = tgt_n ? reinterpret_cast<double *>(ctx->d_tgt.p) : nullptr;
-        kp.dbg_target_off = tgt_n ? reinterpret_cast<const int64_t *>(ctx->d_tgtoff.p) : nullptr;
-        kp.dbg_weights = wts_n ? reinterpret_cast<double *>(ctx->d_wts.p) : nullptr;
-        kp.dbg_weights_off = wts_n ? reinterpret_cast<const int64_t *>(ctx->d_wtsoff.p) : nullptr;
-        kp.max_nv = B.max_nv;
-        kp.max_e = B.max_e;
-        kp.max_rec_words = (B.max_rec + 1) & ~1;
-        spg_status st = (dim == 6) ? launch_dim<6>(ctx, kp) : launch_dim<3>(ctx, kp);
-        if(st != SPG_OK) return st;
+    static const int bounds6[] = {3, 4, 5, 6, 7, 8, 10, 12, 14, 16, 20, 24, 32, 48, 64, 128, 1 << 30};
+    constexpr int NBK = sizeof(bounds6) / sizeof(int);
+    std::vector<int32_t> flat(nb); // bucket-ordered blanket indices of every chunk; must outlive the async copies
+    bool first = true;
+    for(int c = 0; c < nchunks; c++) {
+        const int b0 = cb[c], b1 = cb[c + 1];
+        if(b1 <= b0) continue;
+        // ---- bucket this chunk by blanket size -----------------------------------------------------
+        std::vector<Bucket> buckets(NBK);
+        for(int b = b0; b < b1; b++) {
+            const int32_t *h = reinterpret_cast<const int32_t *>(in->records + in->rec_off[b]);
+            int bi = 0;
+            while(h[0] > bounds6[bi]) bi++;
+            Bucket &B = buckets[bi];
+            B.list.push_back(b);
+            B.max_nv = std::max(B.max_nv, (int) h[0]);
+            B.max_e = std::max(B.max_e, (int) h[2]);
+            B.max_rec = std::max(B.max_rec, (int) h[4]);
+        }
+        size_t pos = (size_t) b0;
+        for(auto &B : buckets) {
+            std::copy(B.list.begin(), B.list.end(), flat.begin() + pos);
+            pos += B.list.size();
+        }
+        // ---- H2D of the chunk -----------------------------------------------------------------------
+        const int64_t r0 = in->rec_off[b0], r1 = in->rec_off[b1];
+        SPG_CUDA(cudaMemcpyAsync(reinterpret_cast<uint64_t *>(ctx->d_rec.p) + r0, in->records + r0, (size_t) (r1 - r0) * 8,
+                                 cudaMemcpyHostToDevice, ctx->s_in));
+        SPG_CUDA(cudaMemcpyAsync(reinterpret_cast<int32_t *>(ctx->d_list.p) + b0, flat.data() + b0, (size_t) (b1 - b0) * 4,
+                                 cudaMemcpyHostToDevice, ctx->s_in));
+        SPG_CUDA(cudaEventRecord(ctx->ev_pool[2 * c], ctx->s_in));
+        SPG_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_pool[2 * c], 0));
+        if(first) {
+            SPG_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+            first = false;
+        }
+        // ---- kernels ----------------------------------------------------------------------------------
+        size_t list_pos = (size_t) b0;
+        for(auto &B : buckets) {
+            if(B.list.empty()) continue;
+            spg::KernelParams kp{};
+            kp.algorithm = in->algorithm;
+            kp.topology = in->opts.topology;
+            kp.chord_ratio = in->opts.chord_ratio;
+            kp.flags = in->opts.flags;
+            kp.n_list = (int32_t) B.list.size();
+            kp.list = reinterpret_cast<const int32_t *>(ctx->d_list.p) + list_pos;
+            list_pos += B.list.size();
+            kp.rec_off = reinterpret_cast<const int64_t *>(ctx->d_recoff.p);
+            kp.records = reinterpret_cast<const uint64_t *>(ctx->d_rec.p);
+            kp.out_off = reinterpret_cast<const int64_t *>(ctx->d_outoff.p);
+            kp.out = reinterpret_cast<uint64_t *>(ctx->d_out.p);
+            kp.dbg_target = tgt_n ? reinterpret_cast<double *>(ctx->d_tgt.p) : nullptr;
+            kp.dbg_target_off = tgt_n ? reinterpret_cast<const int64_t *>(ctx->d_tgtoff.p) : nullptr;
+            kp.dbg_weights = wts_n ? reinterpret_cast<double *>(ctx->d_wts.p) : nullptr;
+            kp.dbg_weights_off = wts_n ? reinterpret_cast<const int64_t *>(ctx->d_wtsoff.p) : nullptr;
+            kp.max_nv = B.max_nv;
+            kp.max_e = B.max_e;
+            kp.max_rec_words = (B.max_rec + 1) & ~1;
+            spg_status st = (dim == 6) ? launch_dim<6>(ctx, kp) : launch_dim<3>(ctx, kp);
+            if(st != SPG_OK) {
+                cudaDeviceSynchronize();
+                return st;
+            }
+        }
+        SPG_CUDA(cudaEventRecord(ctx->ev_pool[2 * c + 1], ctx->stream));
+        // ---- D2H of the chunk -----------------------------------------------------------------------
+        SPG_CUDA(cudaStreamWaitEvent(ctx->s_out, ctx->ev_pool[2 * c + 1], 0));
+        const int64_t o0 = in->out_off[b0], o1 = in->out_off[b1];
+        SPG_CUDA(cudaMemcpyAsync(out->out + o0, reinterpret_cast<uint64_t *>(ctx->d_out.p) + o0, (size_t) (o1 - o0) * 8,
+                                 cudaMemcpyDeviceToHost, ctx->s_out));
     }
     SPG_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
-
-    // ---- D2H ---------------------------------------------------------------------------------
-    SPG_CUDA(cudaMemcpyAsync(out->out, ctx->d_out.p, (size_t) out_words * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    if(tgt_n) SPG_CUDA(cudaMemcpyAsync(out->dbg_target, ctx->d_tgt.p, (size_t) tgt_n * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    if(wts_n) SPG_CUDA(cudaMemcpyAsync(out->dbg_weights, ctx->d_wts.p, (size_t) wts_n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if(tgt_n) SPG_CUDA(cudaMemcpyAsync(out->dbg_target, ctx->d_tgt.p, (size_t) tgt_n * 8, cudaMemcpyDeviceToHost, ctx->s_out));
+    if(wts_n) SPG_CUDA(cudaMemcpyAsync(out->dbg_weights, ctx->d_wts.p, (size_t) wts_n * 8, cudaMemcpyDeviceToHost, ctx->s_out));
+    SPG_CUDA(cudaStreamSynchronize(ctx->s_in));
     SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+    SPG_CUDA(cudaStreamSynchronize(ctx->s_out));
     float ms = 0;
     SPG_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
-    ctx->last_ms = ms;
+    ctx->last_ms = ms; // first kernel to last kernel of the call (waits for the chunked copies included)
     return SPG_OK;
 }
 

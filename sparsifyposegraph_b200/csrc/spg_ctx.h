@@ -44,7 +44,9 @@ struct spg_ctx {
     int device = 0;
     int sm_count = 148;
     size_t smem_optin = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;               // kernels (exposed by spg_stream)
+    cudaStream_t s_in = nullptr, s_out = nullptr; // H2D / D2H of the chunked host-buffer path
+    std::vector<cudaEvent_t> ev_pool;            // two per chunk (copy-in done, kernels done)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int64_t launches = 0;
     double last_ms = 0;
