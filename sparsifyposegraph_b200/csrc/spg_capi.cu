@@ -117,6 +117,7 @@ spg_status spg_create(spg_ctx **out, const spg_config *cfg) {
     ctx->device = dev;
     ctx->sm_count = prop.multiProcessorCount;
     ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    if(const char *e = getenv("SPG_CHUNK_BYTES")) ctx->chunk_bytes = std::max<long long>(4096, atoll(e)); // tests: force many chunks
     SPG_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     SPG_CUDA(cudaEventCreate(&ctx->ev0));
     SPG_CUDA(cudaEventCreate(&ctx->ev1));
@@ -267,7 +268,7 @@ spg_status spg_remove_round(spg_ctx *ctx, const spg_round_in *in, spg_round_out 
     // device buffers (same offsets as on the host), so nothing is double-buffered. Small rounds: one chunk.
     const bool dbg = (out->dbg_target && out->dbg_target_off) || (out->dbg_weights && out->dbg_weights_off);
     const int64_t total_bytes = (rec_words + out_words) * 8;
-    int nchunks = (int) std::min<int64_t>(32, total_bytes / ((int64_t) 48 << 20));
+    int nchunks = (int) std::min<int64_t>(32, total_bytes / std::max<int64_t>(ctx->chunk_bytes, 4096));
     if(nchunks < 1 || dbg) nchunks = 1;
     std::vector<int> cb(nchunks + 1, nb);
     cb[0] = 0;

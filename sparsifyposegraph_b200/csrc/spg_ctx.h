@@ -47,6 +47,7 @@ struct spg_ctx {
     cudaStream_t stream = nullptr;               // kernels (exposed by spg_stream)
     cudaStream_t s_in = nullptr, s_out = nullptr; // H2D / D2H of the chunked host-buffer path
     std::vector<cudaEvent_t> ev_pool;            // two per chunk (copy-in done, kernels done)
+    int64_t chunk_bytes = (int64_t) 48 << 20;    // records + outputs per chunk of spg_remove_round (env SPG_CHUNK_BYTES)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int64_t launches = 0;
     double last_ms = 0;

@@ -176,3 +176,37 @@ def test_pose_only_promise_runs_the_lean_kernel(ctx, oracle, n, topology):
             assert [e["v"] for e in g["edges"]] == [e["v"] for e in r["edges"]]
             for eg, er in zip(g["edges"], r["edges"]):
                 assert rel(eg["info"], er["info"]) <= 1e-9
+
+
+def test_chunked_host_round_equals_single_chunk(oracle, monkeypatch):
+    """spg_remove_round cuts a large round into chunks and overlaps H2D / kernels / D2H on three streams. With the
+    chunk size forced down (SPG_CHUNK_BYTES) a mixed round of a few MB goes through ~30 chunks: the output must be
+    bit-identical to the single-chunk run and match the oracle."""
+    from sparsifyposegraph_b200 import capi
+    parts = [synth.make_blankets(n, 300, dim=6, variant="ring", seed=7 * n) for n in (3, 5, 9, 12, 16, 4, 8)]
+    recs = []
+    for blk in parts:
+        recs += [blk["records"][blk["rec_off"][b]:blk["rec_off"][b + 1]] for b in range(len(blk["rec_off"]) - 1)]
+    rng = np.random.default_rng(0)
+    recs = [recs[i] for i in rng.permutation(len(recs))]     # sizes interleaved: every chunk has several buckets
+    records, rec_off = R.concat_records(recs)
+    nk = R.n_kept_of(records, rec_off)
+    out_off = R.out_offsets(6, R.ALG_NFR, R.TOPO_TREE, 1.0, nk)
+    opts = capi.make_opts(R.TOPO_TREE, 1, flags=2)
+    c1 = capi.Context(0)
+    ref = c1.remove_round(6, R.ALG_NFR, opts, records, rec_off, out_off)[0].copy()
+    c1.close()
+    monkeypatch.setenv("SPG_CHUNK_BYTES", str(256 * 1024))
+    c2 = capi.Context(0)
+    got = c2.remove_round(6, R.ALG_NFR, opts, records, rec_off, out_off)[0].copy()
+    c2.close()
+    assert np.array_equal(ref, got)
+    sample = list(range(0, len(recs), 97))
+    o = oracle.remove_round(6, R.ALG_NFR, oracle.make_opts(R.TOPO_TREE, 1), records, rec_off, out_off, 0)[0]
+    for b in sample:
+        g = R.parse_out(got, out_off, b, 6, R.ALG_NFR, R.TOPO_TREE, nk[b])
+        r = R.parse_out(o, out_off, b, 6, R.ALG_NFR, R.TOPO_TREE, nk[b])
+        assert g["status"] == r["status"] == 0
+        assert [e["v"] for e in g["edges"]] == [e["v"] for e in r["edges"]]
+        for eg, er in zip(g["edges"], r["edges"]):
+            assert rel(eg["info"], er["info"]) <= 1e-9
