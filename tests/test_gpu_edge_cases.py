@@ -210,3 +210,23 @@ def test_chunked_host_round_equals_single_chunk(oracle, monkeypatch):
         assert [e["v"] for e in g["edges"]] == [e["v"] for e in r["edges"]]
         for eg, er in zip(g["edges"], r["edges"]):
             assert rel(eg["info"], er["info"]) <= 1e-9
+
+
+@pytest.mark.parametrize("n", [18, 24, 30, 36])
+@pytest.mark.parametrize("flags", [0, 2])
+def test_se2_mid_sized_blankets_all_variants(ctx, oracle, n, flags):
+    """SE2 blankets of 18-36 vertices (N = 54-108): the 512-thread dual-sweep kernel, the lean two-per-SM kernel
+    (pose-only promise), the 256-thread kernel and (N > 96) the blocked-Cholesky route."""
+    nb = 4
+    blk = synth.make_blankets(n, nb, dim=3, variant="ring", seed=300 + n)
+    nk = R.n_kept_of(blk["records"], blk["rec_off"])
+    recs = [blk["records"][blk["rec_off"][b]:blk["rec_off"][b + 1]] for b in range(nb)]
+    for alg, topo in ((R.ALG_NFR, R.TOPO_TREE), (R.ALG_GLC, R.TOPO_TREE)):
+        if alg == R.ALG_GLC and flags:
+            continue
+        for g, r in both(ctx, oracle, 3, recs, list(nk), alg, topo, flags=flags):
+            assert g["status"] == r["status"] == 0
+            assert [e["v"] for e in g["edges"]] == [e["v"] for e in r["edges"]]
+            if alg == R.ALG_NFR:
+                for eg, er in zip(g["edges"], r["edges"]):
+                    assert rel(eg["info"], er["info"]) <= 1e-9
