@@ -462,7 +462,8 @@ __device__ __forceinline__ void sweep_blocks(double (&a)[TS][TS], double *colbuf
 // BAR > 0: the sweep is run by a group of exactly T*T threads (group-local index `tid`) that synchronises on
 // named barrier BAR, so that two groups of one CTA can sweep two matrices at the same time.
 template <int NT, int T, int TS, int BAR = 0>
-__device__ __forceinline__ bool sweep_spd_inl(double *A, int n, int ld, int nsweep, double *colbuf, int tid) {
+__device__ __forceinline__ bool sweep_spd_inl(const double *S, int lds, double *A, int ld, int n, int nsweep, double *colbuf, int tid,
+                                              double diag_add, bool mirror) {
     static_assert(T * T <= NT, "thread grid larger than the CTA");
     constexpr int NTG = (BAR == 0) ? NT : T * T; // threads taking part
     const bool active = tid < T * T;
@@ -476,7 +477,7 @@ __device__ __forceinline__ bool sweep_spd_inl(double *A, int n, int ld, int nswe
 #pragma unroll
         for(int r = 0; r < TS; r++) {
             const int i = tx + T * r, l = ty + T * c;
-            a[r][c] = (active && i < n && l < n) ? A[i + l * ld] : 0.0;
+            a[r][c] = (active && i < n && l < n) ? S[i + l * lds] + (i == l ? diag_add : 0.0) : 0.0;
         }
     // publish column 0
     if(active && ty == 0) {
@@ -495,15 +496,22 @@ __device__ __forceinline__ bool sweep_spd_inl(double *A, int n, int ld, int nswe
 #pragma unroll
         for(int r = 0; r < TS; r++) {
             const int i = tx + T * r, l = ty + T * c;
-            if(active && i < n && l < n) A[i + l * ld] = sgn * a[r][c];
+            if(active && i < n && l < n) {
+                if(!mirror) A[i + l * ld] = sgn * a[r][c];
+                else if(i <= l) { // upper triangle copied onto the lower one (vertex_remover.cpp:447-449)
+                    A[i + l * ld] = sgn * a[r][c];
+                    A[l + i * ld] = sgn * a[r][c];
+                }
+            }
         }
     group_sync<NT, BAR, T * T>();
     return true;
 }
 
 template <int NT, int T, int TS, int BAR = 0>
-__device__ __noinline__ bool sweep_spd(double *A, int n, int ld, int nsweep, double *colbuf, int tid = threadIdx.x) {
-    return sweep_spd_inl<NT, T, TS, BAR>(A, n, ld, nsweep, colbuf, tid);
+__device__ __noinline__ bool sweep_spd(const double *S, int lds, double *A, int ld, int n, int nsweep, double *colbuf, int tid, double diag_add,
+                                       bool mirror) {
+    return sweep_spd_inl<NT, T, TS, BAR>(S, lds, A, ld, n, nsweep, colbuf, tid, diag_add, mirror);
 }
 
 // Two tile shapes per CTA width: the largest n each covers is T * TS.
@@ -520,12 +528,16 @@ template <> struct SweepGrid<512> { static constexpr int T = 16, TS0 = 4, TS1 = 
 // kernel is issue-latency bound at 8 warps per SM rather than barrier bound. See DESIGN.md §3.)
 // LEAN: the 256-thread CTA built for two residents per SM (128 registers): the tile shapes of the 512-thread grid.
 template <int D, int NT, bool LEAN = false>
-__device__ __forceinline__ int sweep_spd_auto(double *A, int n, int ld, int nsweep, double *scratch) {
+__device__ __forceinline__ int sweep_spd_auto(const double *S, int lds, double *A, int ld, int n, int nsweep, double *scratch,
+                                              double diag_add = 0.0, bool mirror = false) {
     using G = SweepGrid<LEAN ? 512 : NT>;
-    if(n <= G::T * G::TS0) return sweep_spd<NT, G::T, G::TS0>(A, n, ld, nsweep, scratch) ? 1 : 0;
-    if(n <= G::T * G::TS1) return sweep_spd<NT, G::T, G::TS1>(A, n, ld, nsweep, scratch) ? 1 : 0;
+    if(n <= G::T * G::TS0) return sweep_spd<NT, G::T, G::TS0>(S, lds, A, ld, n, nsweep, scratch, threadIdx.x, diag_add, mirror) ? 1 : 0;
+    if(n <= G::T * G::TS1) return sweep_spd<NT, G::T, G::TS1>(S, lds, A, ld, n, nsweep, scratch, threadIdx.x, diag_add, mirror) ? 1 : 0;
     return -1;
 }
+// does an n x n matrix fit the register tiles of this CTA shape?
+template <int NT, bool LEAN = false>
+__device__ __forceinline__ bool sweep_fits(int n) { return n <= SweepGrid<LEAN ? 512 : NT>::T * SweepGrid<LEAN ? 512 : NT>::TS1; }
 
 // CTAs wide enough sweep two matrices at once, one per group of GS threads (group g = threads [g*GS, (g+1)*GS)):
 //   128 threads: two 8 x 8 grids, tiles up to 6 x 6 (n <= 48)
@@ -538,10 +550,11 @@ template <> struct SweepDual<512> { static constexpr bool value = true; static c
 
 // same return convention as sweep_spd_auto
 template <int D, int NT, int BAR>
-__device__ __forceinline__ int sweep_spd_group(double *A, int n, int ld, int nsweep, double *scratch, int gtid) {
+__device__ __forceinline__ int sweep_spd_group(const double *S, int lds, double *A, int ld, int n, int nsweep, double *scratch, int gtid,
+                                               double diag_add) {
     using G = SweepGrid<NT>;
-    if(n <= G::T * G::TS0) return sweep_spd<NT, G::T, G::TS0, BAR>(A, n, ld, nsweep, scratch, gtid) ? 1 : 0;
-    if(n <= G::T * G::TS1) return sweep_spd<NT, G::T, G::TS1, BAR>(A, n, ld, nsweep, scratch, gtid) ? 1 : 0;
+    if(n <= G::T * G::TS0) return sweep_spd<NT, G::T, G::TS0, BAR>(S, lds, A, ld, n, nsweep, scratch, gtid, diag_add, false) ? 1 : 0;
+    if(n <= G::T * G::TS1) return sweep_spd<NT, G::T, G::TS1, BAR>(S, lds, A, ld, n, nsweep, scratch, gtid, diag_add, false) ? 1 : 0;
     return -1;
 }
 

@@ -385,16 +385,10 @@ __global__ void __launch_bounds__(NT, LEAN ? 2 : ((NT >= 256) ? 1 : (NT == 128 ?
         double *T = H + m + (size_t) m * ldH; // Lambda_t in place, leading dimension ldH
         if(status == SPG_BLANKET_OK) {
             // register-tiled partial sweep of the m removed pivots: H_kk <- H_kk - H_km H_mm^-1 H_mk
-            const int sw = sweep_spd_auto<D, NT, LEAN>(H, N, ldH, m, buf1);
+            // (the store mirrors the upper triangle onto the lower one, vertex_remover.cpp:447-449)
+            const int sw = sweep_spd_auto<D, NT, LEAN>(H, ldH, H, ldH, N, m, buf1, 0.0, true);
             if(sw == 0) status = SPG_BLANKET_NOT_PD_MARGINAL;
-            if(sw > 0) {
-                // upper triangle mirrored to the lower (vertex_remover.cpp:447-449)
-                for(int t = tid; t < k * k; t += NT) {
-                    const int i = t % k, j = t / k;
-                    if(i > j) T[i + (size_t) j * ldH] = T[j + (size_t) i * ldH];
-                }
-                gsync<NT>();
-            } else if(sw < 0) { // blanket larger than the register tiles: LLT route
+            if(sw < 0) { // blanket larger than the register tiles: LLT route
                 if(!chol_lower<NT>(H, m, ldH)) status = SPG_BLANKET_NOT_PD_MARGINAL;
                 if(status == SPG_BLANKET_OK && k > 0) {
                     for(int c = m + tid; c < N; c += NT) { // Y = L^-1 H_mk : thread per kept column
@@ -454,47 +448,40 @@ __global__ void __launch_bounds__(NT, LEAN ? 2 : ((NT >= 256) ? 1 : (NT == 128 ?
             } else {
                 n_out = (P.topology == SPG_TOPO_TREE) ? nk - 1 : mch;
                 // C = (Lambda_t + 1 I)^-1  (fillEdges, pseudo_chow_liu.cpp:185-190)
-                double *Lc = buf1, *C = buf1; // the inverse overwrites the factor; buf2 is its scratch
-                for(int t = tid; t < k * k; t += NT) {
-                    const int i = t % k, j = t / k;
-                    Lc[i + j * ldk] = T[i + (size_t) j * ldH] + (i == j ? 1.0 : 0.0);
-                }
+                double *Lc = buf1, *C = buf1; // buf2 is scratch
                 // CTAs twice as wide as the sweep's thread grid invert the anchored block Lambda_rr of the NFR
                 // gauge shortcut (S4) at the same time, on their second group of threads: two independent
-                // pivot chains per SM instead of one.
+                // pivot chains per SM instead of one. The sweeps read Lambda_t (+ I) straight from T.
                 if constexpr(SweepDual<NT>::value && !SPILL) {
-                    const int kk = k - D, ldg = odd_ld(kk > 0 ? kk : 1);
-                    if(P.algorithm == SPG_ALG_NFR && n_out * D == kk && !(P.flags & 1) && k <= SweepDual<NT>::NMAX) {
-                        g_ready = true; // uniform
-                        for(int t = tid; t < kk * kk; t += NT) {
-                            const int i = t % kk, j = t / kk;
-                            buf2[i + j * ldg] = T[i + (size_t) j * ldH];
-                        }
-                    }
+                    const int kk = k - D;
+                    if(P.algorithm == SPG_ALG_NFR && n_out * D == kk && !(P.flags & 1) && k <= SweepDual<NT>::NMAX) g_ready = true; // uniform
                 }
-                gsync<NT>();
                 if(g_ready) {
                     if constexpr(SweepDual<NT>::value && !SPILL) {
                         constexpr int GS = SweepDual<NT>::GS;
                         const int kk = k - D, ldg = odd_ld(kk > 0 ? kk : 1);
                         double *cb = reinterpret_cast<double *>(s_rec_buf); // the record copy is dead after the assembly
                         if(tid < GS) {
-                            const int sw = sweep_spd_group<D, NT, 1>(Lc, k, ldk, k, cb, tid);
+                            const int sw = sweep_spd_group<D, NT, 1>(T, ldH, Lc, ldk, k, k, cb, tid, 1.0);
                             if(tid == 0) s_misc[8] = sw;
                         } else if(tid < 2 * GS) {
-                            const int sw = sweep_spd_group<D, NT, 2>(buf2, kk, ldg, kk, cb + SweepDual<NT>::CB, tid - GS);
+                            const int sw = sweep_spd_group<D, NT, 2>(T, ldH, buf2, ldg, kk, kk, cb + SweepDual<NT>::CB, tid - GS, 0.0);
                             if(tid == GS) s_misc[9] = sw;
                         }
                         gsync<NT>();
                         if(s_misc[8] == 0) status = SPG_BLANKET_NOT_PD_CHOWLIU;
                     }
-                } else {
-                    const int sw = sweep_spd_auto<D, NT, LEAN>(Lc, k, ldk, k, buf2);
+                } else if(sweep_fits<NT, LEAN>(k)) {
+                    const int sw = sweep_spd_auto<D, NT, LEAN>(T, ldH, Lc, ldk, k, k, buf2, 1.0, false);
                     if(sw == 0) status = SPG_BLANKET_NOT_PD_CHOWLIU;
-                    if(sw < 0) {
-                        if(!chol_lower<NT>(Lc, k, ldk)) status = SPG_BLANKET_NOT_PD_CHOWLIU;
-                        else chol_inverse_inplace<NT>(Lc, k, ldk, buf2);
+                } else { // larger than the register tiles: blocked Cholesky + triangular inverse
+                    for(int t = tid; t < k * k; t += NT) {
+                        const int i = t % k, j = t / k;
+                        Lc[i + j * ldk] = T[i + (size_t) j * ldH] + (i == j ? 1.0 : 0.0);
                     }
+                    gsync<NT>();
+                    if(!chol_lower<NT>(Lc, k, ldk)) status = SPG_BLANKET_NOT_PD_CHOWLIU;
+                    else chol_inverse_inplace<NT>(Lc, k, ldk, buf2);
                 }
                 if(status == SPG_BLANKET_OK) {
                     SPG_T(3);
@@ -616,23 +603,21 @@ __global__ void __launch_bounds__(NT, LEAN ? 2 : ((NT >= 256) ? 1 : (NT == 128 ?
             const int kk = k - D, ldg = odd_ld(kk > 0 ? kk : 1);
             double *G = g_ready ? buf2 : buf1; // the inverse overwrites the Cholesky factor; buf2 is its scratch
             if(closed && !(P.flags & 1)) {
-                if(!g_ready)
-                    for(int t = tid; t < kk * kk; t += NT) {
-                        const int i = t % kk, j = t / kk;
-                        buf1[i + j * ldg] = T[i + (size_t) j * ldH];
-                    }
                 // guard (ii): every diagonal entry of Lambda_t below 1e8 (checked by all threads, OR-reduced)
                 int bigdiag = 0;
                 for(int i = tid; i < k; i += NT) bigdiag |= !(fabs(T[i + (size_t) i * ldH]) < 1e8);
                 bigdiag = gsync_or<NT>(bigdiag);
                 int swg;
                 if(g_ready) swg = s_misc[9];
-                else {
-                    swg = sweep_spd_auto<D, NT, LEAN>(buf1, kk, ldg, kk, buf2);
-                    if(swg < 0) {
-                        swg = chol_lower<NT>(buf1, kk, ldg) ? 1 : 0;
-                        if(swg) chol_inverse_inplace<NT>(buf1, kk, ldg, buf2);
+                else if(sweep_fits<NT, LEAN>(kk)) swg = sweep_spd_auto<D, NT, LEAN>(T, ldH, buf1, ldg, kk, kk, buf2, 0.0, false);
+                else { // larger than the register tiles
+                    for(int t = tid; t < kk * kk; t += NT) {
+                        const int i = t % kk, j = t / kk;
+                        buf1[i + j * ldg] = T[i + (size_t) j * ldH];
                     }
+                    gsync<NT>();
+                    swg = chol_lower<NT>(buf1, kk, ldg) ? 1 : 0;
+                    if(swg) chol_inverse_inplace<NT>(buf1, kk, ldg, buf2);
                 }
                 if(swg <= 0) out_flags |= 32; // diagnostic: anchored block not positive definite
                 if(bigdiag) out_flags |= 64;

@@ -981,7 +981,7 @@ __device__ __forceinline__ void v7_blocks(double (&a)[V7::FR][V7::FC][2], double
                 const int i = threadIdx.x & 15, l = threadIdx.x >> 4;
                 Di[i * K::YS + l] = (i < p && l < p) ? Yc[(16 * B + i) * K::YS + l] : 0.0;
                 __syncthreads();
-                if(!sweep_spd<256, 16, 1>(Di, p, K::YS, p, Di + 16 * K::YS + 8)) *flag = 1;
+                if(!sweep_spd<256, 16, 1>(Di, K::YS, Di, K::YS, p, p, Di + 16 * K::YS + 8, threadIdx.x, 0.0, false)) *flag = 1;
                 PROF(1);
             }
             // (2) W = Y D^-1: every warp computes the three fragments it owns of the block's columns
@@ -1111,7 +1111,7 @@ __global__ void __launch_bounds__(NT) __maxnreg__(NT == 288 ? 168 : (NT == 1024 
         __syncthreads();
         const long long t0 = clock64();
         bool ok;
-        if constexpr(VAR == 0) ok = sweep_spd<NT, T, TS>(A, n, ld, nsweep, colbuf);
+        if constexpr(VAR == 0) ok = sweep_spd<NT, T, TS>(A, ld, A, ld, n, nsweep, colbuf, threadIdx.x, 0.0, false);
         else if constexpr(VAR == 60) ok = sweep_v7(A, n, ld, nsweep, colbuf);
         else if constexpr(VAR == 70) ok = rsweep_spd<NT, 32, 16, 3, 6, 1>(A, n, ld, nsweep, colbuf, threadIdx.x);
         else if constexpr(VAR == 71) ok = rsweep_spd<NT, 16, 8, 6, 12, 1>(A, n, ld, nsweep, colbuf, threadIdx.x);
