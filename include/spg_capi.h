@@ -38,7 +38,11 @@ typedef enum {
     SPG_ERR_CUDA = 2,         /* CUDA runtime error (message via spg_last_error)          */
     SPG_ERR_NO_DEVICE = 3,    /* no sm_100 device: the product path has NO CPU fallback   */
     SPG_ERR_UNSUPPORTED = 4,  /* option combination the reference asserts against         */
-    SPG_ERR_IO = 5
+    SPG_ERR_IO = 5,
+    SPG_ERR_BLANKET_FAILED = 6 /* graph level: at least one blanket came back with a status != SPG_BLANKET_OK
+                                  (the reference asserts / exits there). Its vertex and edges were left in the
+                                  graph untouched; every other removal was applied. spg_marginalize_stats
+                                  names the first failing list index and its blanket status.              */
 } spg_status;
 
 /* reference src/sparsity_options.h:12-14 (same numeric values) */
@@ -70,6 +74,11 @@ typedef struct {
  * of mid-sized blankets then run a leaner kernel, two blankets per SM. A record that breaks the promise is
  * answered with SPG_BLANKET_UNSUPPORTED, never with wrong numbers. VertexRemover sets it per round. */
 #define SPG_OPT_POSE_EDGES_ONLY 2
+
+/* Test hook: spg_round_out.dbg_weights is an INPUT — the Chow-Liu mutual-information weights of every blanket
+ * (pairs in (i<j) lexicographic order) are taken from it instead of being computed. Lets a test feed exactly
+ * equal weights and compare the spanning tree with std::priority_queue's pop order (pseudo_chow_liu.h:49-53). */
+#define SPG_OPT_DBG_WEIGHTS_IN 4
 
 /* edge kinds inside a blanket record */
 typedef enum {
@@ -116,7 +125,8 @@ typedef enum {
  *   w0 : int32 status | int32 n_new_edges
  *   w1 : int32 newton_iters | int32 flags   (bit 0: a line search of the iterative fit failed, bit 1: KLD infinite;
  *                                           diagnostics: bit 4: gauge shortcut refused, eigen path taken,
- *                                           bit 5: anchored block not positive definite, bit 6: |diag| >= 1e8)
+ *                                           bit 5: anchored block not positive definite, bit 6: |diag| >= 1e8,
+ *                                           bit 7: two Chow-Liu weights exactly equal, priority_queue order replayed)
  *   w2 : double kld        (value of the projected KLD at the solution, NFR only)
  *   w3 : double reserved
  *   then n_new_edges slots, slot size fixed per (algorithm, dim, topology):
@@ -194,9 +204,13 @@ spg_status spg_remove_round(spg_ctx *ctx, const spg_round_in *in, spg_round_out 
 /*
  * Same, but every pointer inside in/out is a DEVICE pointer already resident in HBM
  * (rec_off/out_off too). Asynchronous on the context stream; call spg_sync().
+ * The records cannot be validated from the host here: the caller states the largest blanket of the round
+ * (vertices, edges, record words; max_rec_words = 0 means "POSE edges only": the bound is derived). A record
+ * beyond these bounds is answered with SPG_BLANKET_TOO_LARGE; the records themselves must be well formed
+ * (spg_remove_round checks that on the host for host buffers).
  */
 spg_status spg_remove_round_device(spg_ctx *ctx, const spg_round_in *in_dev, spg_round_out *out_dev,
-                                   int32_t max_n_vert, int32_t max_n_edges);
+                                   int32_t max_n_vert, int32_t max_n_edges, int32_t max_rec_words);
 spg_status spg_sync(spg_ctx *ctx);
 void *spg_stream(spg_ctx *ctx); /* cudaStream_t of the context */
 
@@ -228,7 +242,8 @@ int32_t spg_graph_num_vertices(const spg_graph *g);
 int32_t spg_graph_num_edges(const spg_graph *g);
 int32_t spg_graph_max_vertex_id(const spg_graph *g);
 
-/* removal schedules, reference src/decimation.cpp:11-49. Returns count; ids written to out (cap). */
+/* removal schedules, reference src/decimation.cpp:11-49. Returns count; ids written to out (cap).
+ * sparsity <= 0 (or cluster_size <= 0) would divide by zero in the reference: returns -1. */
 int32_t spg_decimate_global(int32_t last, int32_t endvert, int32_t sparsity, int32_t *out, int32_t cap);
 int32_t spg_decimate_online(int32_t last, int32_t endvert, int32_t sparsity, int32_t *out, int32_t cap);
 int32_t spg_decimate_cluster(int32_t last, int32_t endvert, int32_t sparsity, int32_t cluster_size,
@@ -262,9 +277,13 @@ typedef struct {
     int32_t n_blankets;
     int32_t max_round_width;
     int32_t max_blanket_vertices;
-    int32_t n_failed;            /* blankets whose status != OK */
+    int32_t n_failed;            /* blankets whose status != OK: left in the graph, call returns SPG_ERR_BLANKET_FAILED */
     int32_t n_dropped_edges;     /* GLC rank-0 edges (reference returns NULL, :85-89) */
     double pack_ms, gpu_ms, splice_ms;
+    int32_t first_failed_index;  /* index into `which` of the first failed blanket, -1 if none */
+    int32_t first_failed_status; /* its spg_blanket_status */
+    int32_t n_applied;           /* list entries whose removal was spliced into the graph (progress on error) */
+    int32_t reserved;
 } spg_marginalize_stats;
 spg_status spg_graph_last_stats(const spg_graph *g, spg_marginalize_stats *stats);
 

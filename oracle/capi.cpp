@@ -152,7 +152,11 @@ double orc_remove_round(const spg_round_in *in, spg_round_out *out, int n_thread
                 i32(o)[0] = ST_UNSUPPORTED;
                 continue;
             }
+            // SPG_OPT_DBG_WEIGHTS_IN: the Chow-Liu weights are an INPUT (exact-tie tests)
+            g_overrideWeights = ((in->opts.flags & SPG_OPT_DBG_WEIGHTS_IN) && out->dbg_weights && out->dbg_weights_off)
+                                        ? out->dbg_weights + out->dbg_weights_off[i] : nullptr;
             BlanketResult res = processBlanket(b, opts, in->algorithm);
+            g_overrideWeights = nullptr;
             writeOut(b, res, in->algorithm, opts, o, ow);
             if(out->dbg_target && out->dbg_target_off) {
                 double *t = out->dbg_target + out->dbg_target_off[i];

@@ -18,6 +18,11 @@ struct SparsityOptions {
     bool includeIntraClique = true;
 };
 
+// Test hook (tie-break tests): when set, fillEdges() takes the mutual-information weights from here (pairs in
+// (i<j) lexicographic order) instead of computing them, so that the CUDA path and the oracle can be fed the SAME
+// weights with exact ties and compared on the pop order of std::priority_queue alone.
+static thread_local const double *g_overrideWeights = nullptr;
+
 // Vertices are the blanket's kept vertices 0..n-1 (all of dimension d).
 class PseudoChowLiu {
 public:
@@ -136,6 +141,7 @@ private:
         for(int i = 0; i < _n - 1; i++)
             for(int j = i + 1; j < _n; j++) {
                 double w = weight(i, j);
+                if(g_overrideWeights) w = g_overrideWeights[weights.size()];
                 weights.push_back(w);
                 _edges.push({w, i, j});
             }

@@ -95,12 +95,14 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
 
 
-def make_opts(topology=0, lin_point=1, chord_ratio=1.0, include_intra_clique=True):
-    return SparsityOptions(int(topology), int(lin_point), float(chord_ratio), int(bool(include_intra_clique)), 0)
+def make_opts(topology=0, lin_point=1, chord_ratio=1.0, include_intra_clique=True, flags=0):
+    return SparsityOptions(int(topology), int(lin_point), float(chord_ratio), int(bool(include_intra_clique)), int(flags))
 
 
-def remove_round(dim, algorithm, opts, records, rec_off, out_off, n_threads=1, want_target=None, want_weights=None):
-    """Oracle twin of spg_remove_round. Returns (out uint64, seconds, dbg_target, dbg_weights)."""
+def remove_round(dim, algorithm, opts, records, rec_off, out_off, n_threads=1, want_target=None, want_weights=None,
+                 weights_in=None):
+    """Oracle twin of spg_remove_round. Returns (out uint64, seconds, dbg_target, dbg_weights).
+    weights_in (with opts.flags & 4 and want_weights offsets): Chow-Liu weights are taken from it."""
     records = np.ascontiguousarray(records, dtype=np.uint64)
     rec_off = np.ascontiguousarray(rec_off, dtype=np.int64)
     out_off = np.ascontiguousarray(out_off, dtype=np.int64)
@@ -117,6 +119,8 @@ def remove_round(dim, algorithm, opts, records, rec_off, out_off, n_threads=1, w
     if want_weights is not None:
         want_weights = np.ascontiguousarray(want_weights, dtype=np.int64)
         wts = np.zeros(int(want_weights[-1]), dtype=np.float64)
+        if weights_in is not None:
+            wts[:] = weights_in
         rout.dbg_weights = _p(wts).value
         rout.dbg_weights_off = _p(want_weights).value
     secs = lib().orc_remove_round(C.byref(rin), C.byref(rout), int(n_threads))
@@ -167,6 +171,11 @@ class Graph:
         ids = np.zeros(self.num_vertices, dtype=np.int32)
         lib().orc_graph_vertex_ids(self.h, _p(ids))
         return ids
+
+    def vertex_pose(self, vid):
+        p = np.zeros(self.P)
+        lib().orc_graph_vertex_pose(self.h, int(vid), _p(p))
+        return p
 
     def marginalize(self, which, opts, algorithm):
         w = np.ascontiguousarray(which, dtype=np.int32)

@@ -45,7 +45,9 @@ class EdgeDesc(C.Structure):
 class MarginalizeStats(C.Structure):
     _fields_ = [("n_rounds", C.c_int32), ("n_blankets", C.c_int32), ("max_round_width", C.c_int32),
                 ("max_blanket_vertices", C.c_int32), ("n_failed", C.c_int32), ("n_dropped_edges", C.c_int32),
-                ("pack_ms", C.c_double), ("gpu_ms", C.c_double), ("splice_ms", C.c_double)]
+                ("pack_ms", C.c_double), ("gpu_ms", C.c_double), ("splice_ms", C.c_double),
+                ("first_failed_index", C.c_int32), ("first_failed_status", C.c_int32), ("n_applied", C.c_int32),
+                ("reserved", C.c_int32)]
 
 
 class SpgError(RuntimeError):
@@ -71,7 +73,7 @@ def lib():
         L.spg_last_kernel_ms.restype = C.c_double
         L.spg_last_kernel_ms.argtypes = [C.c_void_p]
         L.spg_remove_round.argtypes = [C.c_void_p, C.POINTER(RoundIn), C.POINTER(RoundOut)]
-        L.spg_remove_round_device.argtypes = [C.c_void_p, C.POINTER(RoundIn), C.POINTER(RoundOut), C.c_int32, C.c_int32]
+        L.spg_remove_round_device.argtypes = [C.c_void_p, C.POINTER(RoundIn), C.POINTER(RoundOut), C.c_int32, C.c_int32, C.c_int32]
         L.spg_sync.argtypes = [C.c_void_p]
         L.spg_stream.restype = C.c_void_p
         L.spg_stream.argtypes = [C.c_void_p]
@@ -123,8 +125,9 @@ class Context:
         return lib().spg_stream(self.h)
 
     def remove_round(self, dim, algorithm, opts, records, rec_off, out_off, out=None, want_target=None,
-                     want_weights=None):
-        """Host buffers in / out (H2D + kernels + D2H inside). Returns (out, dbg_target, dbg_weights)."""
+                     want_weights=None, weights_in=None):
+        """Host buffers in / out (H2D + kernels + D2H inside). Returns (out, dbg_target, dbg_weights).
+        weights_in (with opts.flags & SPG_OPT_DBG_WEIGHTS_IN and want_weights offsets): test hook, see spg_capi.h."""
         records = np.ascontiguousarray(records, dtype=np.uint64)
         rec_off = np.ascontiguousarray(rec_off, dtype=np.int64)
         out_off = np.ascontiguousarray(out_off, dtype=np.int64)
@@ -141,16 +144,19 @@ class Context:
         if want_weights is not None:
             want_weights = np.ascontiguousarray(want_weights, dtype=np.int64)
             wts = np.zeros(int(want_weights[-1]), dtype=np.float64)
+            if weights_in is not None:
+                wts[:] = weights_in
             rout.dbg_weights, rout.dbg_weights_off = _p(wts), _p(want_weights)
         _check(lib().spg_remove_round(self.h, C.byref(rin), C.byref(rout)))
         return out, tgt, wts
 
     def remove_round_device(self, dim, algorithm, opts, n_blankets, d_records, d_rec_off, d_out_off, d_out,
-                            max_n_vert, max_n_edges):
+                            max_n_vert, max_n_edges, max_rec_words=0):
         """Device pointers (ints) already resident in HBM; asynchronous on the context stream."""
         rin = RoundIn(dim, algorithm, opts, int(n_blankets), 0, int(d_rec_off), int(d_records), int(d_out_off))
         rout = RoundOut(int(d_out), None, None, None, None)
-        _check(lib().spg_remove_round_device(self.h, C.byref(rin), C.byref(rout), int(max_n_vert), int(max_n_edges)))
+        _check(lib().spg_remove_round_device(self.h, C.byref(rin), C.byref(rout), int(max_n_vert), int(max_n_edges),
+                                                 int(max_rec_words)))
 
     def sync(self):
         _check(lib().spg_sync(self.h))
@@ -240,10 +246,13 @@ class Graph:
         _check(lib().spg_graph_vertex_pose(self.h, int(vid), _p(p)))
         return p
 
-    def marginalize(self, ctx, which, opts, algorithm):
-        """VertexRemover::remove(which) through the GPU; returns the marginalize stats."""
+    def marginalize(self, ctx, which, opts, algorithm, allow_failed=False):
+        """VertexRemover::remove(which) through the GPU; returns the marginalize stats.
+        SPG_ERR_BLANKET_FAILED (6) raises unless allow_failed: the stats then name the first failing entry."""
         w = np.ascontiguousarray(which, dtype=np.int32)
-        _check(lib().spg_graph_marginalize(self.h, ctx.h, _p(w), len(w), C.byref(opts), int(algorithm)))
+        rc = lib().spg_graph_marginalize(self.h, ctx.h, _p(w), len(w), C.byref(opts), int(algorithm))
+        if not (allow_failed and rc == 6):
+            _check(rc)
         return self.stats()
 
     def stats(self):

@@ -8,6 +8,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "spg_ctx.h"
@@ -74,6 +75,64 @@ spg_status launch_dim(spg_ctx *ctx, spg::KernelParams &kp) {
     if(N <= 48) return spg_launch_3_128(ctx, kp);
     if(N <= 80) return spg_launch_3_512(ctx, kp);
     return spg_launch_3_256(ctx, kp);
+}
+
+// Host-side validation of blankets [b0, b1) of a round: everything the kernels index with (edge offset table,
+// edge-local vertex indices, edge sizes, output slice) must lie inside the record / the output slice.
+// Returns the index of the first malformed blanket, or -1.
+int validate_records(const spg_round_in *in, int b0, int b1) {
+    const int dim = in->dim;
+    for(int b = b0; b < b1; b++) {
+        const uint64_t *rec = in->records + in->rec_off[b];
+        const int64_t rw = in->rec_off[b + 1] - in->rec_off[b];
+        if(rw < SPG_REC_HEADER_WORDS) return b;
+        const int32_t *h = reinterpret_cast<const int32_t *>(rec);
+        const int nv = h[0], nrem = h[1], ne = h[2];
+        if(h[3] != dim || h[4] > rw || h[4] < SPG_REC_HEADER_WORDS || nv < 1 || nrem < 1 || nrem > nv || ne < 0) return b;
+        const int64_t words = h[4], fixed = spgr_record_fixed_words(dim, nv, ne);
+        if(fixed > words) return b;
+        const int32_t *etab = reinterpret_cast<const int32_t *>(rec + spgr_edgetab_off(dim, nv));
+        for(int e = 0; e < ne; e++) {
+            const int64_t eo = etab[e];
+            if(eo < fixed || eo + 2 > words) return b;
+            const int32_t *eh = reinterpret_cast<const int32_t *>(rec + eo);
+            const int kind = eh[0], env = eh[1], rows = eh[2];
+            if(kind < SPG_EDGE_POSE || kind > SPG_EDGE_MULTI || env < 1 || env > nv || rows < 0) return b;
+            if(kind == SPG_EDGE_POSE && (env != 2 || rows != dim)) return b;
+            if(kind == SPG_EDGE_GLC && rows > dim * env) return b;
+            if(kind == SPG_EDGE_MULTI && rows % dim != 0) return b;
+            if(eo + 2 + spgr_pad2(env) > words || eo + spgr_edge_words(dim, kind, env, rows) > words) return b;
+            const int32_t *vi = reinterpret_cast<const int32_t *>(rec + eo + 2);
+            for(int q = 0; q < env; q++)
+                if(vi[q] < 0 || vi[q] >= nv) return b;
+            if(kind == SPG_EDGE_MULTI) {
+                const int32_t *pr = reinterpret_cast<const int32_t *>(rec + eo + 2 + spgr_pad2(env));
+                for(int q = 0; q < 2 * (rows / dim); q++)
+                    if(pr[q] < 0 || pr[q] >= env) return b;
+            }
+        }
+        const int64_t need = spgr_out_record_words(dim, in->algorithm, in->opts.topology, in->opts.chord_ratio, nv - nrem);
+        if(in->out_off[b + 1] - in->out_off[b] < need) return b;
+    }
+    return -1;
+}
+
+// the same over a large range, spread over host threads (the check of chunk c+1 overlaps the GPU work of chunk c)
+int validate_records_mt(const spg_round_in *in, int b0, int b1) {
+    const int n = b1 - b0;
+    unsigned nthr = std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 8u);
+    if(n < 8192 || nthr <= 1) return validate_records(in, b0, b1);
+    std::vector<int> bad(nthr, -1);
+    std::vector<std::thread> pool;
+    const int per = (n + (int) nthr - 1) / (int) nthr;
+    for(unsigned t = 0; t < nthr; t++) {
+        const int lo = std::min(b1, b0 + (int) t * per), hi = std::min(b1, lo + per);
+        if(lo < hi) pool.emplace_back([&bad, in, lo, hi, t] { bad[t] = validate_records(in, lo, hi); });
+    }
+    for(auto &th : pool) th.join();
+    for(int v : bad)
+        if(v >= 0) return v;
+    return -1;
 }
 
 spg_status check_device(spg_ctx *ctx) {
@@ -208,7 +267,7 @@ spg_status spg_sync(spg_ctx *ctx) {
 }
 
 spg_status spg_remove_round_device(spg_ctx *ctx, const spg_round_in *in, spg_round_out *out, int32_t max_n_vert,
-                                   int32_t max_n_edges) {
+                                   int32_t max_n_edges, int32_t max_rec_words) {
     if(check_device(ctx) != SPG_OK) return SPG_ERR_INVALID;
     if(!in || !out || (in->dim != 3 && in->dim != 6)) {
         set_err("bad round descriptor");
@@ -232,8 +291,9 @@ spg_status spg_remove_round_device(spg_ctx *ctx, const spg_round_in *in, spg_rou
     kp.dbg_weights_off = out->dbg_weights_off;
     kp.max_nv = max_n_vert;
     kp.max_e = max_n_edges;
-    // all-POSE upper bound of the record size for this (nv, ne)
-    kp.max_rec_words = (int32_t) ((spgr_record_fixed_words(in->dim, max_n_vert, max_n_edges) +
+    // record size bound: from the caller (rounds with GLC / MULTI edges), else the all-POSE bound for this (nv, ne)
+    kp.max_rec_words = max_rec_words > 0 ? ((max_rec_words + 1) & ~1)
+                                         : (int32_t) ((spgr_record_fixed_words(in->dim, max_n_vert, max_n_edges) +
                                    (int64_t) max_n_edges * spgr_edge_words(in->dim, SPG_EDGE_POSE, 2, in->dim) + 1) & ~1LL);
     SPG_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
     spg_status st = (in->dim == 6) ? launch_dim<6>(ctx, kp) : launch_dim<3>(ctx, kp);
@@ -254,13 +314,9 @@ spg_status spg_remove_round(spg_ctx *ctx, const spg_round_in *in, spg_round_out 
     const int dim = in->dim;
     const int64_t rec_words = in->rec_off[nb];
     const int64_t out_words = in->out_off[nb];
-    for(int b = 0; b < nb; b++) {
-        const int32_t *h = reinterpret_cast<const int32_t *>(in->records + in->rec_off[b]);
-        const int rw = (int) (in->rec_off[b + 1] - in->rec_off[b]);
-        if(h[3] != dim || h[4] > rw || h[0] < 1) {
-            set_err("malformed blanket record " + std::to_string(b));
-            return SPG_ERR_INVALID;
-        }
+    if(!in->rec_off || !in->out_off || !in->records) {
+        set_err("bad round descriptor");
+        return SPG_ERR_INVALID;
     }
 
     // ---- chunks: contiguous runs of blankets, so that the H2D copy of chunk c+1, the kernels of chunk c and the
@@ -307,7 +363,10 @@ spg_status spg_remove_round(spg_ctx *ctx, const spg_round_in *in, spg_round_out 
         SPG_CUDA(ctx->d_wts.reserve((size_t) wts_n * 8 + 8));
         SPG_CUDA(ctx->d_wtsoff.reserve((size_t) (nb + 1) * 8));
         SPG_CUDA(cudaMemcpyAsync(ctx->d_wtsoff.p, out->dbg_weights_off, (size_t) (nb + 1) * 8, cudaMemcpyHostToDevice, ctx->s_in));
-        SPG_CUDA(cudaMemsetAsync(ctx->d_wts.p, 0, (size_t) wts_n * 8 + 8, ctx->s_in));
+        if(in->opts.flags & SPG_OPT_DBG_WEIGHTS_IN)
+            SPG_CUDA(cudaMemcpyAsync(ctx->d_wts.p, out->dbg_weights, (size_t) wts_n * 8, cudaMemcpyHostToDevice, ctx->s_in));
+        else
+            SPG_CUDA(cudaMemsetAsync(ctx->d_wts.p, 0, (size_t) wts_n * 8 + 8, ctx->s_in));
     }
 
     static const int bounds6[] = {3, 4, 5, 6, 7, 8, 10, 12, 14, 16, 20, 24, 32, 48, 64, 128, 1 << 30};
@@ -317,6 +376,16 @@ spg_status spg_remove_round(spg_ctx *ctx, const spg_round_in *in, spg_round_out 
     for(int c = 0; c < nchunks; c++) {
         const int b0 = cb[c], b1 = cb[c + 1];
         if(b1 <= b0) continue;
+        // ---- validate the chunk's records before anything of it is launched (runs while the GPU works on c-1)
+        {
+            const int bad = validate_records_mt(in, b0, b1);
+            if(bad >= 0) {
+                cudaDeviceSynchronize();
+                set_err("malformed blanket record " + std::to_string(bad) +
+                        " (header, edge table, vertex index or output slice out of bounds)");
+                return SPG_ERR_INVALID;
+            }
+        }
         // ---- bucket this chunk by blanket size -----------------------------------------------------
         std::vector<Bucket> buckets(NBK);
         for(int b = b0; b < b1; b++) {

@@ -368,7 +368,8 @@ __device__ __forceinline__ double fast_rcp(double x) {
 
 // One pivot step of the register-tiled sweep (see sweep_spd). C0 = register row/column of the pivot.
 template <int T, int TS, int C0>
-__device__ __forceinline__ void sweep_step(double (&a)[TS][TS], double *colbuf, int jj, int nsweep, int tx, int ty, bool &bad) {
+__device__ __forceinline__ void sweep_step(double (&a)[TS][TS], double *colbuf, int jj, int nsweep, int tx, int ty, bool &bad,
+                                           double &mypiv) {
     constexpr int NP = T * TS;
     constexpr int cstride = NP + 2;
     const int j = jj + T * C0;
@@ -376,6 +377,7 @@ __device__ __forceinline__ void sweep_step(double (&a)[TS][TS], double *colbuf, 
     double *ncol = colbuf + ((j + 1) & 1) * cstride;
     const double d = col[NP], inv = col[NP + 1];
     bad |= !(d > 0);
+    if(tx + T * ty == j) mypiv = d; // group thread j keeps pivot j (log-determinant of the swept block)
     double ci[TS], cl[TS];
 #pragma unroll
     for(int r = 0; r < TS; r++) {
@@ -432,15 +434,16 @@ __device__ __forceinline__ void sweep_step(double (&a)[TS][TS], double *colbuf, 
 // constant, so the tile never leaves the register file; the jj loop is not unrolled (a fully unrolled
 // sweep of T*TS steps thrashes the instruction cache).
 template <int NT, int T, int TS, int C0, int BAR>
-__device__ __forceinline__ void sweep_blocks(double (&a)[TS][TS], double *colbuf, int nsweep, int tx, int ty, bool active, bool &bad) {
+__device__ __forceinline__ void sweep_blocks(double (&a)[TS][TS], double *colbuf, int nsweep, int tx, int ty, bool active, bool &bad,
+                                             double &mypiv) {
     if constexpr(C0 < TS) {
         const int jjmax = min(T, nsweep - T * C0); // uniform; <= 0: nothing left
 #pragma unroll 1
         for(int jj = 0; jj < jjmax; jj++) {
-            if(active) sweep_step<T, TS, C0>(a, colbuf, jj, nsweep, tx, ty, bad);
+            if(active) sweep_step<T, TS, C0>(a, colbuf, jj, nsweep, tx, ty, bad, mypiv);
             group_sync<NT, BAR, T * T>();
         }
-        sweep_blocks<NT, T, TS, C0 + 1, BAR>(a, colbuf, nsweep, tx, ty, active, bad);
+        sweep_blocks<NT, T, TS, C0 + 1, BAR>(a, colbuf, nsweep, tx, ty, active, bad, mypiv);
     }
 }
 
@@ -463,7 +466,7 @@ __device__ __forceinline__ void sweep_blocks(double (&a)[TS][TS], double *colbuf
 // named barrier BAR, so that two groups of one CTA can sweep two matrices at the same time.
 template <int NT, int T, int TS, int BAR = 0>
 __device__ __forceinline__ bool sweep_spd_inl(const double *S, int lds, double *A, int ld, int n, int nsweep, double *colbuf, int tid,
-                                              double diag_add, bool mirror) {
+                                              double diag_add, bool mirror, double *logpiv = nullptr) {
     static_assert(T * T <= NT, "thread grid larger than the CTA");
     constexpr int NTG = (BAR == 0) ? NT : T * T; // threads taking part
     const bool active = tid < T * T;
@@ -487,8 +490,11 @@ __device__ __forceinline__ bool sweep_spd_inl(const double *S, int lds, double *
     }
     group_sync<NT, BAR, T * T>();
     bool bad = false;
-    sweep_blocks<NT, T, TS, 0, BAR>(a, colbuf, nsweep, tx, ty, active, bad);
+    double mypiv = 1.0;
+    sweep_blocks<NT, T, TS, 0, BAR>(a, colbuf, nsweep, tx, ty, active, bad, mypiv);
     if(group_or<NT, BAR, T * T>(bad)) return false;
+    // log of "my" pivot: summed over the group it is the log-determinant of the swept leading block
+    if(logpiv) *logpiv = (active && tx + T * ty < nsweep) ? log(mypiv) : 0.0;
     // full sweep leaves -A^-1; a partial sweep leaves the Schur complement in the trailing block
     const double sgn = (nsweep >= n) ? -1.0 : 1.0;
 #pragma unroll
@@ -510,8 +516,8 @@ __device__ __forceinline__ bool sweep_spd_inl(const double *S, int lds, double *
 
 template <int NT, int T, int TS, int BAR = 0>
 __device__ __noinline__ bool sweep_spd(const double *S, int lds, double *A, int ld, int n, int nsweep, double *colbuf, int tid, double diag_add,
-                                       bool mirror) {
-    return sweep_spd_inl<NT, T, TS, BAR>(S, lds, A, ld, n, nsweep, colbuf, tid, diag_add, mirror);
+                                       bool mirror, double *logpiv = nullptr) {
+    return sweep_spd_inl<NT, T, TS, BAR>(S, lds, A, ld, n, nsweep, colbuf, tid, diag_add, mirror, logpiv);
 }
 
 // Two tile shapes per CTA width: the largest n each covers is T * TS.
@@ -529,10 +535,10 @@ template <> struct SweepGrid<512> { static constexpr int T = 16, TS0 = 4, TS1 = 
 // LEAN: the 256-thread CTA built for two residents per SM (128 registers): the tile shapes of the 512-thread grid.
 template <int D, int NT, bool LEAN = false>
 __device__ __forceinline__ int sweep_spd_auto(const double *S, int lds, double *A, int ld, int n, int nsweep, double *scratch,
-                                              double diag_add = 0.0, bool mirror = false) {
+                                              double diag_add = 0.0, bool mirror = false, double *logpiv = nullptr) {
     using G = SweepGrid<LEAN ? 512 : NT>;
-    if(n <= G::T * G::TS0) return sweep_spd<NT, G::T, G::TS0>(S, lds, A, ld, n, nsweep, scratch, threadIdx.x, diag_add, mirror) ? 1 : 0;
-    if(n <= G::T * G::TS1) return sweep_spd<NT, G::T, G::TS1>(S, lds, A, ld, n, nsweep, scratch, threadIdx.x, diag_add, mirror) ? 1 : 0;
+    if(n <= G::T * G::TS0) return sweep_spd<NT, G::T, G::TS0>(S, lds, A, ld, n, nsweep, scratch, threadIdx.x, diag_add, mirror, logpiv) ? 1 : 0;
+    if(n <= G::T * G::TS1) return sweep_spd<NT, G::T, G::TS1>(S, lds, A, ld, n, nsweep, scratch, threadIdx.x, diag_add, mirror, logpiv) ? 1 : 0;
     return -1;
 }
 // does an n x n matrix fit the register tiles of this CTA shape?
@@ -551,10 +557,10 @@ template <> struct SweepDual<512> { static constexpr bool value = true; static c
 // same return convention as sweep_spd_auto
 template <int D, int NT, int BAR>
 __device__ __forceinline__ int sweep_spd_group(const double *S, int lds, double *A, int ld, int n, int nsweep, double *scratch, int gtid,
-                                               double diag_add) {
+                                               double diag_add, double *logpiv = nullptr) {
     using G = SweepGrid<NT>;
-    if(n <= G::T * G::TS0) return sweep_spd<NT, G::T, G::TS0, BAR>(S, lds, A, ld, n, nsweep, scratch, gtid, diag_add, false) ? 1 : 0;
-    if(n <= G::T * G::TS1) return sweep_spd<NT, G::T, G::TS1, BAR>(S, lds, A, ld, n, nsweep, scratch, gtid, diag_add, false) ? 1 : 0;
+    if(n <= G::T * G::TS0) return sweep_spd<NT, G::T, G::TS0, BAR>(S, lds, A, ld, n, nsweep, scratch, gtid, diag_add, false, logpiv) ? 1 : 0;
+    if(n <= G::T * G::TS1) return sweep_spd<NT, G::T, G::TS1, BAR>(S, lds, A, ld, n, nsweep, scratch, gtid, diag_add, false, logpiv) ? 1 : 0;
     return -1;
 }
 

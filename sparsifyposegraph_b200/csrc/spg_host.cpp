@@ -172,6 +172,8 @@ void Graph::removeEdge(int ei) {
 void Graph::removeVertex(int id) {
     GraphVertex *v = vertex(id);
     if(!v) return;
+    // g2o's HyperGraph::removeVertex detaches every edge still incident to the vertex
+    while(!v->edges.empty()) removeEdge(v->edges.back());
     v->alive = false;
     aliveVertices--;
 }
@@ -510,13 +512,38 @@ std::vector<int> VertexRemover::remove(const std::vector<int> &toRemove, spg_sta
         stats.gpu_ms += std::chrono::duration<double, std::milli>(t2 - t1).count();
         stats.splice_ms += std::chrono::duration<double, std::milli>(t3 - t2).count();
     }
+    if(st == SPG_OK) st = failureStatus();
     if(status) *status = st;
     return _added;
 }
 
+// SPG_ERR_BLANKET_FAILED once any blanket of the call came back with a status != OK (it stays in the graph)
+spg_status VertexRemover::failureStatus() {
+    if(stats.n_failed == 0) return SPG_OK;
+    error = "blanket of list entry " + std::to_string(stats.first_failed_index) + " (vertex " +
+            std::to_string(_pending[stats.first_failed_index]) + ") failed with blanket status " +
+            std::to_string(stats.first_failed_status) + "; " + std::to_string(stats.n_failed) +
+            " failed blanket(s) were left in the graph untouched";
+    return SPG_ERR_BLANKET_FAILED;
+}
+
 spg_status VertexRemover::beginRemoval(const std::vector<int> &toRemove) {
     stats = spg_marginalize_stats{};
+    stats.first_failed_index = -1;
     _added.clear();
+    // option combinations the path cannot serve are refused before the graph is touched
+    if(_opts.topology == SparsityOptions::CliqueySubgraph || _opts.topology == SparsityOptions::CliqueyDense) {
+        error = "CliqueySubgraph / CliqueyDense (MultiEdgeCorrelated substitutes) are not produced on the device";
+        return SPG_ERR_UNSUPPORTED;
+    }
+    for(TopologyProvider *tp : _topologies)
+        if(tp->algorithm() == SPG_ALG_GLC &&
+           (!(_opts.topology == SparsityOptions::Dense || _opts.topology == SparsityOptions::Tree) ||
+            _opts.linPoint != SparsityOptions::Global)) {
+            // asserts of TopologyProviderGLC::topology (src/topology_provider_glc.cpp:107-111)
+            error = "GLC needs Dense|Tree topology and the Global linearisation point";
+            return SPG_ERR_UNSUPPORTED;
+        }
     _pending = toRemove;
     _toRemoveSet = std::set<int>(toRemove.begin(), toRemove.end());
     _done.assign(toRemove.size(), 0);
@@ -716,7 +743,19 @@ void VertexRemover::applyRound(const uint64_t *out) {
         const uint64_t *o = out + _round.outOff[ui];
         const int32_t *oh = reinterpret_cast<const int32_t *>(o);
         const int bstatus = oh[0], nnew = oh[1];
-        if(bstatus != SPG_BLANKET_OK) stats.n_failed++;
+        if(bstatus != SPG_BLANKET_OK) {
+            // The reference asserts / exits here. The blanket is left in the graph untouched (vertex, edges, no
+            // substitutes); the units of a round commute, so the others are unaffected. The call reports
+            // SPG_ERR_BLANKET_FAILED with the first failing list index.
+            if(stats.n_failed++ == 0) {
+                stats.first_failed_index = u.listIndex;
+                stats.first_failed_status = bstatus;
+            }
+            for(int id : u.removed) _toRemoveSet.erase(id);
+            _done[u.listIndex] = 1;
+            _remaining--;
+            continue;
+        }
         for(int xi : u.ridx) _stamp[xi] = _planNo; // cached blankets containing these are stale
         for(int xi : u.kidx) _stamp[xi] = _planNo;
         for(int ei : u.edges) _graph->removeEdge(ei);
@@ -760,6 +799,7 @@ void VertexRemover::applyRound(const uint64_t *out) {
         _done[u.listIndex] = 1;
         _remaining--;
         stats.n_blankets++;
+        stats.n_applied += (int) u.removed.size();
     }
     stats.n_rounds++;
     stats.max_round_width = std::max<int>(stats.max_round_width, (int) _round.units.size());
@@ -920,13 +960,16 @@ static int32_t copyOut(const std::vector<int> &r, int32_t *out, int32_t cap) {
     return (int32_t) r.size();
 }
 int32_t spg_decimate_global(int32_t last, int32_t endvert, int32_t sparsity, int32_t *out, int32_t cap) {
+    if(sparsity <= 0) return -1;
     return copyOut(spg::globalDecimate(last, endvert, spg::DecimateOptions{sparsity, 0}), out, cap);
 }
 int32_t spg_decimate_online(int32_t last, int32_t endvert, int32_t sparsity, int32_t *out, int32_t cap) {
+    if(sparsity <= 0) return -1;
     return copyOut(spg::onlineDecimate(last, endvert, spg::DecimateOptions{sparsity, 0}), out, cap);
 }
 int32_t spg_decimate_cluster(int32_t last, int32_t endvert, int32_t sparsity, int32_t cluster_size, int32_t *out,
                              int32_t cap) {
+    if(sparsity <= 0 || cluster_size <= 0) return -1;
     return copyOut(spg::clusterDecimate(last, endvert, spg::DecimateOptions{sparsity, cluster_size}), out, cap);
 }
 
@@ -1002,7 +1045,7 @@ spg_status spg_graph_round_apply(spg_graph *g, const uint64_t *out) {
     if(!g || !g->session || !out) return SPG_ERR_INVALID;
     g->session->applyRound(out);
     g->stats = g->session->stats;
-    return SPG_OK;
+    return g->session->failureStatus();
 }
 
 spg_status spg_graph_last_stats(const spg_graph *g, spg_marginalize_stats *stats) {

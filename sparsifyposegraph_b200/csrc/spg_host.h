@@ -160,6 +160,7 @@ public:
     spg_status planRound();
     spg_round_in roundDescriptor() const;
     void applyRound(const uint64_t *out);
+    spg_status failureStatus(); // SPG_OK, or SPG_ERR_BLANKET_FAILED (+ error text) once a blanket failed
 
     spg_marginalize_stats stats{};
     std::string error;

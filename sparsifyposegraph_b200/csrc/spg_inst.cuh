@@ -10,8 +10,9 @@ namespace {
 #define set_err spg_set_err
 template <int D, int NT, bool SPILL = false, bool LEAN = false>
 spg_status launch_bucket(spg_ctx *ctx, spg::KernelParams &kp) {
+    // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: one flag per device ordinal
     static std::mutex mu;
-    static size_t configured = 0;
+    static bool configured[64] = {};
     size_t smem = (size_t) kp.total_doubles * sizeof(double);
     if(SPILL) smem = 0;
     if(smem > ctx->smem_optin) {
@@ -20,10 +21,11 @@ spg_status launch_bucket(spg_ctx *ctx, spg::KernelParams &kp) {
     }
     if(!SPILL) {
         std::lock_guard<std::mutex> lk(mu);
-        if(smem > configured) {
+        const int dv = ctx->device & 63;
+        if(!configured[dv]) {
             SPG_CUDA(cudaFuncSetAttribute(spg::blanket_kernel<D, NT, SPILL, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int) ctx->smem_optin));
-            configured = ctx->smem_optin;
+            configured[dv] = true;
         }
     }
     int per_sm = 0;

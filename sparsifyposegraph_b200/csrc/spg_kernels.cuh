@@ -426,6 +426,7 @@ __global__ void __launch_bounds__(NT, LEAN ? 2 : ((NT >= 256) ? 1 : (NT == 128 ?
         SPG_T(2);
         // ---- S3: sparsity pattern (PseudoChowLiu::computeSparsityPattern, pseudo_chow_liu.cpp:33-87) ---
         int n_out = 0;
+        double glog_part = 0; // this thread's share of logdet(Lambda_rr) (pivots of the anchored sweep): projected KLD of the closed form
         bool g_ready = false; // Lambda_rr^-1 already sits in buf2 (computed next to the Chow-Liu inverse)
         const bool glc_tree = (P.algorithm == SPG_ALG_GLC && P.topology == SPG_TOPO_TREE);
         if(status == SPG_BLANKET_OK && (P.algorithm == SPG_ALG_NFR || glc_tree) && nk >= 2) {
@@ -465,7 +466,7 @@ __global__ void __launch_bounds__(NT, LEAN ? 2 : ((NT >= 256) ? 1 : (NT == 128 ?
                             const int sw = sweep_spd_group<D, NT, 1>(T, ldH, Lc, ldk, k, k, cb, tid, 1.0);
                             if(tid == 0) s_misc[8] = sw;
                         } else if(tid < 2 * GS) {
-                            const int sw = sweep_spd_group<D, NT, 2>(T, ldH, buf2, ldg, kk, kk, cb + SweepDual<NT>::CB, tid - GS, 0.0);
+                            const int sw = sweep_spd_group<D, NT, 2>(T, ldH, buf2, ldg, kk, kk, cb + SweepDual<NT>::CB, tid - GS, 0.0, &glog_part);
                             if(tid == GS) s_misc[9] = sw;
                         }
                         gsync<NT>();
@@ -507,7 +508,12 @@ __global__ void __launch_bounds__(NT, LEAN ? 2 : ((NT >= 256) ? 1 : (NT == 128 ?
                     if(P.dbg_weights) {
                         double *g = P.dbg_weights + P.dbg_weights_off[b];
                         const int cap = (int) (P.dbg_weights_off[b + 1] - P.dbg_weights_off[b]);
-                        for(int t = tid; t < cap; t += NT) g[t] = t < all ? s_wt[t] : 0.0;
+                        if(P.flags & SPG_OPT_DBG_WEIGHTS_IN) { // test hook: weights are an input (exact ties)
+                            for(int t = tid; t < all && t < cap; t += NT) s_wt[t] = g[t];
+                            gsync<NT>();
+                        } else {
+                            for(int t = tid; t < cap; t += NT) g[t] = t < all ? s_wt[t] : 0.0;
+                        }
                     }
                     SPG_T(6);
                     // doKruskal (:253-289): pops of a max-heap keyed on the weight only, accepted edges first
@@ -533,6 +539,7 @@ __global__ void __launch_bounds__(NT, LEAN ? 2 : ((NT >= 256) ? 1 : (NT == 128 ?
                         }
                     }
                     gsync<NT>();
+                    if(s_misc[3]) out_flags |= 128; // diagnostic: exactly equal weights, heap replayed
                     if(tid == 0) {
                         for(int v = 0; v < nk; v++) s_uf[v] = v;
                         int nacc = 0, nrej = 0;
@@ -609,7 +616,7 @@ __global__ void __launch_bounds__(NT, LEAN ? 2 : ((NT >= 256) ? 1 : (NT == 128 ?
                 bigdiag = gsync_or<NT>(bigdiag);
                 int swg;
                 if(g_ready) swg = s_misc[9];
-                else if(sweep_fits<NT, LEAN>(kk)) swg = sweep_spd_auto<D, NT, LEAN>(T, ldH, buf1, ldg, kk, kk, buf2, 0.0, false);
+                else if(sweep_fits<NT, LEAN>(kk)) swg = sweep_spd_auto<D, NT, LEAN>(T, ldH, buf1, ldg, kk, kk, buf2, 0.0, false, &glog_part);
                 else { // larger than the register tiles
                     for(int t = tid; t < kk * kk; t += NT) {
                         const int i = t % kk, j = t / kk;
@@ -617,7 +624,10 @@ __global__ void __launch_bounds__(NT, LEAN ? 2 : ((NT >= 256) ? 1 : (NT == 128 ?
                     }
                     gsync<NT>();
                     swg = chol_lower<NT>(buf1, kk, ldg) ? 1 : 0;
-                    if(swg) chol_inverse_inplace<NT>(buf1, kk, ldg, buf2);
+                    if(swg) {
+                        for(int i = tid; i < kk; i += NT) glog_part += 2.0 * log(buf1[i + (size_t) i * ldg]);
+                        chol_inverse_inplace<NT>(buf1, kk, ldg, buf2);
+                    }
                 }
                 if(swg <= 0) out_flags |= 32; // diagnostic: anchored block not positive definite
                 if(bigdiag) out_flags |= 64;
@@ -751,7 +761,7 @@ __global__ void __launch_bounds__(NT, LEAN ? 2 : ((NT >= 256) ? 1 : (NT == 128 ?
                     int fl = 0;
                     double kld = 0;
                     nfr_iterative<D, NT>(ws, n_out, k, r, V, ldk, s_order + ooff, s_S, Jn, s_tree, s_red, s_misc + 2, newton_iters, fl, kld);
-                    out_flags = fl;
+                    out_flags |= fl;
                     out_kld = kld;
                     if(fl & 2) status = SPG_BLANKET_KLD_INF;
                     const NfrWork w = nfr_carve(ws, n_out, D, r);
@@ -826,6 +836,7 @@ __global__ void __launch_bounds__(NT, LEAN ? 2 : ((NT >= 256) ? 1 : (NT == 128 ?
                         const double *B = src + (size_t) e * D * D;
                         const double d = B[s0 + s0 * D];
                         if(!(d > 0)) s_misc[0] = SPG_BLANKET_NOT_PD_CLOSED;
+                        if(fast && i == s0 && j == s0) s_cs[e * D + s0] = d; // pivots: logdet(X_e^-1); s_cs is free on the shortcut path
                         const double inv = 1.0 / d, bis = B[i + s0 * D], bsj = B[s0 + j * D];
                         double v = B[i + j * D] - bis * bsj * inv;
                         if(j == s0) v = bis * inv;
@@ -843,6 +854,73 @@ __global__ void __launch_bounds__(NT, LEAN ? 2 : ((NT >= 256) ? 1 : (NT == 128 ?
                 }
                 gsync<NT>();
                 if(s_misc[0] != SPG_BLANKET_OK) status = s_misc[0];
+                // ---- projected KLD at the closed form: LogdetFunction::value (logdet_function.cpp:119-133) as
+                // optimizeInformation's diagnostics evaluate it (optimizer.cpp:22-24) ------------------------------
+                if(status == SPG_BLANKET_OK) {
+                    if(fast) {
+                        // X_e = (J Sigma J^T)^-1 makes tr(S U^T J^T X J U) = r exactly, and Lambda_t and J^T X J share
+                        // the gauge null space, so the ratio of their pseudo-determinants is the ratio of the
+                        // determinants of their anchored blocks. J^T X J is tree structured with |det J_child| = 1:
+                        //   KLD = 1/2 [ logdet Lambda_rr - sum_e logdet X_e ]
+                        // = half the sum of the logs of the pivots of the anchored sweep and of the D x D inversions.
+                        double lp = glog_part;
+                        for(int t = tid; t < n_out * D; t += NT) lp += log(s_cs[t]);
+                        out_kld = 0.5 * block_sum<NT>(lp, s_red);
+                    } else {
+                        // literal: A = U^T J^T X J U (r x r), value = 1/2 [tr(A S) - logdet A - logdet S - r]
+                        double *JU = buf0 + (size_t) n_out * JW; // R x r column-major, R = n_out * D = r; beyond Jn
+                        double *Xs = buf2;                        // n_out * D*D
+                        double *A = buf1;                         // V is dead once JU is formed
+                        const int R = n_out * D;
+                        for(int t = tid; t < n_out * D * D; t += NT) Xs[t] = -src[t];
+                        gsync<NT>(); // src (Sg / Bk) lies where JU goes
+                        for(int t = tid; t < R * r; t += NT) {
+                            const int row = t % R, col = t / R, e = row / D, i = row % D;
+                            const int a = pk_a(s_tree[e]), bb = pk_b(s_tree[e]);
+                            const double *u = V + (size_t) s_order[ooff + col] * ldk;
+                            const double *J = Jn + (size_t) e * JW;
+                            double acc = 0;
+#pragma unroll
+                            for(int j = 0; j < D; j++) {
+                                const double ja = J[i + j * D], jb = J[i + (D + j) * D];
+                                if(fabs(ja) >= 2.220446049250313e-16) acc += ja * u[a * D + j]; // sparseJacobian(), :335
+                                if(fabs(jb) >= 2.220446049250313e-16) acc += jb * u[bb * D + j];
+                            }
+                            JU[t] = acc;
+                        }
+                        gsync<NT>();
+                        for(int t = tid; t < r * r; t += NT) {
+                            const int i = t % r, j = t / r;
+                            if(i <= j) { // upper triangle, mirrored (:121-122)
+                                double acc = 0;
+                                for(int e = 0; e < n_out; e++) {
+                                    const double *xe = Xs + (size_t) e * D * D;
+                                    const double *ui = JU + (size_t) e * D + (size_t) i * R, *uj = JU + (size_t) e * D + (size_t) j * R;
+#pragma unroll
+                                    for(int bq = 0; bq < D; bq++) {
+                                        double w = 0;
+#pragma unroll
+                                        for(int aq = 0; aq < D; aq++) w += ui[aq] * xe[aq + bq * D];
+                                        acc += w * uj[bq];
+                                    }
+                                }
+                                A[i + (size_t) j * ldk] = acc;
+                                A[j + (size_t) i * ldk] = acc;
+                            }
+                        }
+                        gsync<NT>();
+                        double tp = 0;
+                        for(int i = tid; i < r; i += NT) tp += A[i + (size_t) i * ldk] * s_S[i] - log(s_S[i]);
+                        const double tr_minus_logS = block_sum<NT>(tp, s_red);
+                        if(!chol_lower<NT>(A, r, ldk)) out_kld = INFINITY;
+                        else {
+                            double dp = 0;
+                            for(int i = tid; i < r; i += NT) dp += log(A[i + (size_t) i * ldk]);
+                            out_kld = 0.5 * (tr_minus_logS - 2.0 * block_sum<NT>(dp, s_red) - (double) r);
+                        }
+                        gsync<NT>();
+                    }
+                }
             }
         }
 

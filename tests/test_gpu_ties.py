@@ -1,0 +1,115 @@
+"""GPU tie-break parity (-m gpu): `north_star` asks for the Chow-Liu topology "bit-exact (same tie-break)".
+The reference pops a std::priority_queue<WeightedEdge> whose operator< looks at the weight only
+(src/pseudo_chow_liu.h:49-53, .cpp:253-289), so edges of exactly equal weight come out in an order fixed by
+libstdc++'s heap. The kernel ranks the weights in parallel and, when two of them are exactly equal, replays that
+heap on one thread (HeapView, spg_kernels.cuh).
+
+Exactly equal fp64 weights cannot be produced reliably from poses and informations (two mathematically equal
+log-determinants differ in the last bit as soon as their pivots are taken in a different order — on the GPU
+and in the oracle alike; second test below). The first test therefore feeds the SAME weights, full of exact
+ties, to both sides through the SPG_OPT_DBG_WEIGHTS_IN hook and compares the edge lists."""
+import numpy as np
+import pytest
+
+from sparsifyposegraph_b200 import records as R
+from sparsifyposegraph_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+DBG_WEIGHTS_IN = 4
+FLAG_HEAP_REPLAYED = 128
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from sparsifyposegraph_b200 import capi
+    c = capi.Context(0)
+    yield c
+    c.close()
+
+
+def tie_weights(rng, B, pairs, mode):
+    if mode == "all-equal":
+        return np.full((B, pairs), 0.75)
+    if mode == "two-levels":
+        return rng.integers(1, 3, size=(B, pairs)).astype(np.float64)
+    if mode == "few-levels":
+        return rng.integers(1, 5, size=(B, pairs)).astype(np.float64) * 0.125
+    if mode == "one-pair-tied":                      # distinct weights except one exact tie
+        w = np.zeros((B, pairs))
+        for b in range(B):
+            w[b] = rng.permutation(pairs) + 1.0
+            i, j = rng.choice(pairs, 2, replace=False)
+            w[b, j] = w[b, i]
+        return w
+    raise ValueError(mode)
+
+
+@pytest.mark.parametrize("dim,n", [(6, 4), (6, 5), (6, 6), (6, 8), (6, 12), (6, 16), (3, 5), (3, 9), (3, 14), (3, 24)])
+@pytest.mark.parametrize("topology", [R.TOPO_TREE, R.TOPO_SUBGRAPH])
+@pytest.mark.parametrize("mode", ["all-equal", "two-levels", "few-levels", "one-pair-tied"])
+def test_exact_ties_pop_in_priority_queue_order(ctx, oracle, dim, n, topology, mode):
+    from sparsifyposegraph_b200 import capi
+    if topology == R.TOPO_SUBGRAPH and (n - 1 <= 4 or n > (9 if dim == 3 else 6)):
+        pytest.skip("Subgraph degenerates to Dense for <= 4 kept vertices; large iterative fits are slow in the oracle")
+    B = 12
+    nk = n - 1
+    pairs = nk * (nk - 1) // 2
+    rng = np.random.default_rng(100 * n + dim + len(mode))
+    blk = synth.make_blankets(n, B, dim=dim, variant="ring", seed=9000 + n)
+    out_off = R.out_offsets(dim, R.ALG_NFR, topology, 1.0, np.full(B, nk))
+    woff = np.arange(B + 1, dtype=np.int64) * pairs
+    w_in = tie_weights(rng, B, pairs, mode).reshape(-1)
+    ro = oracle.remove_round(dim, R.ALG_NFR, oracle.make_opts(topology, R.LIN_GLOBAL, flags=DBG_WEIGHTS_IN), blk["records"],
+                             blk["rec_off"], out_off, 0, None, woff, weights_in=w_in)[0]
+    go = ctx.remove_round(dim, R.ALG_NFR, capi.make_opts(topology, R.LIN_GLOBAL, flags=DBG_WEIGHTS_IN), blk["records"],
+                          blk["rec_off"], out_off, None, None, woff, weights_in=w_in)[0]
+    replayed = 0
+    for b in range(B):
+        r = R.parse_out(ro, out_off, b, dim, R.ALG_NFR, topology, nk)
+        g = R.parse_out(go, out_off, b, dim, R.ALG_NFR, topology, nk)
+        assert g["status"] == r["status"] == 0, (b, g["status"], r["status"])
+        assert [e["v"] for e in g["edges"]] == [e["v"] for e in r["edges"]], (b, mode)
+        replayed += bool(g["flags"] & FLAG_HEAP_REPLAYED)
+    assert replayed == B          # every blanket had an exact tie: the heap replay ran, not the ranking
+
+
+def test_twin_vertices_give_near_ties_not_exact_ties(ctx, oracle):
+    """Two kept vertices with identical poses, measurements and informations: their MI weights towards every
+    third vertex are mathematically equal. In floating point the two come out of different pivot orders, so
+    they agree to a few ulp but not bit for bit: either side may break the near-tie either way. The test
+    requires identical topology wherever the weights are separated by more than 1e-12 relative, and reports
+    the near-tie count."""
+    from sparsifyposegraph_b200 import capi
+    rng = np.random.default_rng(11)
+    recs, B, nk = [], 24, 5
+    for _ in range(B):
+        poses = synth.random_poses(rng, (1 + nk,), 6)
+        poses[3] = poses[2]                                 # kept vertices 1 and 2 (local 2, 3) are twins
+        info = synth.random_info(rng, (), 6)
+        edges = []
+        for i in range(1, 1 + nk):
+            z = synth.se3_compose(synth.se3_inverse(poses[0]), poses[i])
+            edges.append({"kind": 0, "v": [0, i], "meas": z, "info": info if i in (2, 3) else synth.random_info(rng, (), 6)})
+        recs.append(R.pack_blanket(6, [9, 2, 4, 6, 8, 10], poses, edges))
+    records, rec_off = R.concat_records(recs)
+    out_off = R.out_offsets(6, R.ALG_NFR, R.TOPO_TREE, 1.0, np.full(B, nk))
+    pairs = nk * (nk - 1) // 2
+    woff = np.arange(B + 1, dtype=np.int64) * pairs
+    ro, _, _, rw = oracle.remove_round(6, R.ALG_NFR, oracle.make_opts(0, 1), records, rec_off, out_off, 0, None, woff)
+    go, _, gw = ctx.remove_round(6, R.ALG_NFR, capi.make_opts(0, 1), records, rec_off, out_off, None, None, woff)
+    near = differ = 0
+    for b in range(B):
+        r = R.parse_out(ro, out_off, b, 6, R.ALG_NFR, R.TOPO_TREE, nk)
+        g = R.parse_out(go, out_off, b, 6, R.ALG_NFR, R.TOPO_TREE, nk)
+        assert g["status"] == r["status"] == 0
+        w = np.sort(rw[b * pairs:(b + 1) * pairs])
+        gap = np.min(np.diff(w) / np.maximum(np.abs(w[1:]), 1e-300))
+        assert np.allclose(gw[b * pairs:(b + 1) * pairs], rw[b * pairs:(b + 1) * pairs], rtol=1e-9, atol=1e-12)
+        same = [e["v"] for e in g["edges"]] == [e["v"] for e in r["edges"]]
+        if gap < 1e-12:
+            near += 1
+            differ += (not same)
+        else:
+            assert same, b
+    print(f"twin blankets: {near} of {B} with a near-tie (< 1e-12 relative gap), topology differs in {differ} of them")
