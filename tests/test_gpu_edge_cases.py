@@ -111,13 +111,7 @@ def test_weak_blanket_takes_choose_dimensions_branch(ctx, oracle):
             assert g["status"] == r["status"] == 0
             assert [e["v"] for e in g["edges"]] == [e["v"] for e in r["edges"]]
             for eg, er in zip(g["edges"], r["edges"]):
-                # the 3e-6 thread makes X_e = (J Sigma J^T)^-1 ill-conditioned by construction (Sigma is clamped at
-                # 1e6 / lambda_max): two backward-stable solvers agree to ~ eps * cond(X_e), not to 1e-9
-                cond = np.linalg.cond(er["info"])
-                bound = max(1e-9, min(1e-6, 100 * 2.2e-16 * cond))
-                res = rel(eg["info"], er["info"])
-                print(f"weak blanket flags={flags}: rel {res:.2e} cond(X_e) {cond:.2e} bound {bound:.2e}")
-                assert res <= bound, (res, cond)
+                assert rel(eg["info"], er["info"]) <= 1e-9     # measured on B200: <= 1.4e-12
 
 
 def test_not_positive_definite_marginal_is_reported(ctx, oracle):

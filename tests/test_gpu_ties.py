@@ -65,13 +65,15 @@ def test_exact_ties_pop_in_priority_queue_order(ctx, oracle, dim, n, topology, m
     go = ctx.remove_round(dim, R.ALG_NFR, capi.make_opts(topology, R.LIN_GLOBAL, flags=DBG_WEIGHTS_IN), blk["records"],
                           blk["rec_off"], out_off, None, None, woff, weights_in=w_in)[0]
     replayed = 0
+    w2 = w_in.reshape(B, pairs)
+    with_tie = sum(len(np.unique(w2[b])) < pairs for b in range(B))
     for b in range(B):
         r = R.parse_out(ro, out_off, b, dim, R.ALG_NFR, topology, nk)
         g = R.parse_out(go, out_off, b, dim, R.ALG_NFR, topology, nk)
         assert g["status"] == r["status"] == 0, (b, g["status"], r["status"])
         assert [e["v"] for e in g["edges"]] == [e["v"] for e in r["edges"]], (b, mode)
         replayed += bool(g["flags"] & FLAG_HEAP_REPLAYED)
-    assert replayed == B          # every blanket had an exact tie: the heap replay ran, not the ranking
+    assert with_tie >= B // 2 and replayed == with_tie   # blankets with an exact tie replayed the heap, not the ranking
 
 
 def test_twin_vertices_give_near_ties_not_exact_ties(ctx, oracle):
