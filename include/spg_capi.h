@@ -180,6 +180,9 @@ void spg_destroy(spg_ctx *ctx);
 int64_t spg_launch_count(const spg_ctx *ctx);
 /* device time (ms, CUDA events on the context stream) of the kernels of the last round */
 double spg_last_kernel_ms(const spg_ctx *ctx);
+/* diagnostics: blankets of the last spg_remove_round* call that the NFR-tree kernel (fast_kernel) handed over to the
+ * general blanket_kernel (GLC / MULTI edges, several removed vertices, refused gauge guard); synchronises */
+int64_t spg_last_retry_count(spg_ctx *ctx);
 
 /* record sizing + packing helpers (pure host code, usable without a GPU) */
 int64_t spg_pose_words(int32_t dim);                       /* 3 or 7 */

@@ -72,6 +72,8 @@ def lib():
         L.spg_launch_count.argtypes = [C.c_void_p]
         L.spg_last_kernel_ms.restype = C.c_double
         L.spg_last_kernel_ms.argtypes = [C.c_void_p]
+        L.spg_last_retry_count.restype = C.c_int64
+        L.spg_last_retry_count.argtypes = [C.c_void_p]
         L.spg_remove_round.argtypes = [C.c_void_p, C.POINTER(RoundIn), C.POINTER(RoundOut)]
         L.spg_remove_round_device.argtypes = [C.c_void_p, C.POINTER(RoundIn), C.POINTER(RoundOut), C.c_int32, C.c_int32, C.c_int32]
         L.spg_sync.argtypes = [C.c_void_p]
@@ -120,6 +122,10 @@ class Context:
     @property
     def last_kernel_ms(self):
         return float(lib().spg_last_kernel_ms(self.h))
+
+    @property
+    def last_retry_count(self):
+        return int(lib().spg_last_retry_count(self.h))
 
     def stream(self):
         return lib().spg_stream(self.h)

@@ -46,7 +46,34 @@ __global__ void __launch_bounds__(256) dfma_probe_kernel(double *sink, int iters
 }
 
 template <int D>
+spg_status launch_general(spg_ctx *ctx, spg::KernelParams &kp);
+
+// NFR tree rounds go through fast_kernel first (spg_fast.cuh); the blankets it refuses (non-POSE edges, several
+// removed vertices, a failed guard or pivot) are collected in a device-side list and re-run by blanket_kernel,
+// launched right behind it with the count read on the device.
+template <int D>
 spg_status launch_dim(spg_ctx *ctx, spg::KernelParams &kp) {
+    const int nk = kp.max_nv - 1, tiles = nk * (nk + 1) / 2;
+    const bool eligible = !ctx->no_fast && kp.algorithm == SPG_ALG_NFR && kp.topology == SPG_TOPO_TREE &&
+                          !(kp.flags & SPG_OPT_FORCE_EIGEN) && kp.max_nv >= 3 && tiles <= 256 && kp.retry_list && kp.retry_count;
+    if(eligible) {
+        spg_status st;
+        if(D == 6) st = tiles <= 32 ? spg_launch_fast_6_1(ctx, kp) : (tiles <= 128 ? spg_launch_fast_6_4(ctx, kp) : spg_launch_fast_6_8(ctx, kp));
+        else st = tiles <= 32 ? spg_launch_fast_3_1(ctx, kp) : spg_launch_fast_3_8(ctx, kp);
+        if(st == SPG_OK) {
+            spg::KernelParams kr = kp;
+            kr.list = kp.retry_list;
+            kr.n_list_dev = kp.retry_count;
+            return launch_general<D>(ctx, kr);
+        }
+        if(st != SPG_ERR_UNSUPPORTED) return st;
+    }
+    kp.n_list_dev = nullptr;
+    return launch_general<D>(ctx, kp);
+}
+
+template <int D>
+spg_status launch_general(spg_ctx *ctx, spg::KernelParams &kp) {
     spg::plan_smem<D>(kp);
     // CTA width by the size of H (N = D * vertices): the register-tiled sweeps cover
     // N <= 12 / 32 / 48 / 96 for 32 / 64 / 128 / 256 threads (SweepGrid in spg_device.cuh)
@@ -176,6 +203,7 @@ spg_status spg_create(spg_ctx **out, const spg_config *cfg) {
     ctx->device = dev;
     ctx->sm_count = prop.multiProcessorCount;
     ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    if(const char *e = getenv("SPG_NO_FAST")) ctx->no_fast = atoi(e) != 0;
     if(const char *e = getenv("SPG_CHUNK_BYTES")) ctx->chunk_bytes = std::max<long long>(4096, atoll(e)); // tests: force many chunks
     SPG_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     SPG_CUDA(cudaEventCreate(&ctx->ev0));
@@ -190,7 +218,7 @@ void spg_destroy(spg_ctx *ctx) {
     if(!ctx) return;
     cudaSetDevice(ctx->device);
     for(DevBuf *b : {&ctx->d_rec, &ctx->d_recoff, &ctx->d_outoff, &ctx->d_out, &ctx->d_list, &ctx->d_tgt,
-                     &ctx->d_tgtoff, &ctx->d_wts, &ctx->d_wtsoff, &ctx->d_ws, &ctx->d_gws, &ctx->d_prof})
+                     &ctx->d_tgtoff, &ctx->d_wts, &ctx->d_wtsoff, &ctx->d_ws, &ctx->d_gws, &ctx->d_prof, &ctx->d_retry, &ctx->d_retry_cnt})
         b->release();
     if(ctx->ev0) cudaEventDestroy(ctx->ev0);
     if(ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -244,17 +272,30 @@ spg_status spg_fp64_peak_probe(spg_ctx *ctx, int32_t repeats, double *tflops) {
     return SPG_OK;
 }
 
-// Developer aid: per-stage cycle accumulators of blanket_kernel (thread 0 of every CTA, clock64).
-// enable != 0 zeroes and enables them; cycles (16 values) may be NULL. Not part of the product path.
+// Developer aid: per-stage cycle accumulators (thread 0 of every CTA, clock64): [0,16) blanket_kernel, [16,32)
+// fast_kernel. enable != 0 zeroes and enables them; cycles (32 values) may be NULL. Not part of the product path.
 spg_status spg_stage_profile(spg_ctx *ctx, int32_t enable, uint64_t *cycles) {
     if(check_device(ctx) != SPG_OK) return SPG_ERR_INVALID;
     SPG_CUDA(cudaSetDevice(ctx->device));
-    SPG_CUDA(ctx->d_prof.reserve(16 * 8));
+    SPG_CUDA(ctx->d_prof.reserve(32 * 8));
     SPG_CUDA(cudaStreamSynchronize(ctx->stream));
-    if(cycles) SPG_CUDA(cudaMemcpy(cycles, ctx->d_prof.p, 16 * 8, cudaMemcpyDeviceToHost));
-    if(enable) SPG_CUDA(cudaMemset(ctx->d_prof.p, 0, 16 * 8));
+    if(cycles) SPG_CUDA(cudaMemcpy(cycles, ctx->d_prof.p, 32 * 8, cudaMemcpyDeviceToHost));
+    if(enable) SPG_CUDA(cudaMemset(ctx->d_prof.p, 0, 32 * 8));
     ctx->profiling = enable != 0;
     return SPG_OK;
+}
+
+// Diagnostics: blankets of the last spg_remove_round* call that fast_kernel handed over to blanket_kernel
+// (synchronises the context's stream).
+int64_t spg_last_retry_count(spg_ctx *ctx) {
+    if(!ctx || ctx->retry_used <= 0 || !ctx->d_retry_cnt.p) return 0;
+    cudaSetDevice(ctx->device);
+    if(cudaStreamSynchronize(ctx->stream) != cudaSuccess) return -1;
+    std::vector<int32_t> h((size_t) ctx->retry_used);
+    if(cudaMemcpy(h.data(), ctx->d_retry_cnt.p, h.size() * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    int64_t t = 0;
+    for(int32_t v : h) t += v;
+    return t;
 }
 
 spg_status spg_sync(spg_ctx *ctx) {
@@ -295,6 +336,12 @@ spg_status spg_remove_round_device(spg_ctx *ctx, const spg_round_in *in, spg_rou
     kp.max_rec_words = max_rec_words > 0 ? ((max_rec_words + 1) & ~1)
                                          : (int32_t) ((spgr_record_fixed_words(in->dim, max_n_vert, max_n_edges) +
                                    (int64_t) max_n_edges * spgr_edge_words(in->dim, SPG_EDGE_POSE, 2, in->dim) + 1) & ~1LL);
+    SPG_CUDA(ctx->d_retry.reserve((size_t) std::max(1, in->n_blankets) * 4));
+    SPG_CUDA(ctx->d_retry_cnt.reserve(64));
+    SPG_CUDA(cudaMemsetAsync(ctx->d_retry_cnt.p, 0, 4, ctx->stream));
+    kp.retry_list = reinterpret_cast<int32_t *>(ctx->d_retry.p);
+    kp.retry_count = reinterpret_cast<int32_t *>(ctx->d_retry_cnt.p);
+    ctx->retry_used = 1;
     SPG_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
     spg_status st = (in->dim == 6) ? launch_dim<6>(ctx, kp) : launch_dim<3>(ctx, kp);
     if(st != SPG_OK) return st;
@@ -348,6 +395,11 @@ spg_status spg_remove_round(spg_ctx *ctx, const spg_round_in *in, spg_round_out 
     SPG_CUDA(ctx->d_outoff.reserve((size_t) (nb + 1) * 8));
     SPG_CUDA(ctx->d_out.reserve((size_t) out_words * 8));
     SPG_CUDA(ctx->d_list.reserve((size_t) nb * 4));
+    SPG_CUDA(ctx->d_retry.reserve((size_t) nb * 4));
+    const int n_counters = nchunks * 32; // one per bucket launch (NBK <= 32)
+    SPG_CUDA(ctx->d_retry_cnt.reserve((size_t) n_counters * 4));
+    SPG_CUDA(cudaMemsetAsync(ctx->d_retry_cnt.p, 0, (size_t) n_counters * 4, ctx->s_in));
+    int counter_next = 0;
     SPG_CUDA(cudaMemcpyAsync(ctx->d_recoff.p, in->rec_off, (size_t) (nb + 1) * 8, cudaMemcpyHostToDevice, ctx->s_in));
     SPG_CUDA(cudaMemcpyAsync(ctx->d_outoff.p, in->out_off, (size_t) (nb + 1) * 8, cudaMemcpyHostToDevice, ctx->s_in));
     int64_t tgt_n = 0, wts_n = 0;
@@ -426,6 +478,8 @@ spg_status spg_remove_round(spg_ctx *ctx, const spg_round_in *in, spg_round_out 
             kp.flags = in->opts.flags;
             kp.n_list = (int32_t) B.list.size();
             kp.list = reinterpret_cast<const int32_t *>(ctx->d_list.p) + list_pos;
+            kp.retry_list = reinterpret_cast<int32_t *>(ctx->d_retry.p) + list_pos;
+            kp.retry_count = reinterpret_cast<int32_t *>(ctx->d_retry_cnt.p) + counter_next++;
             list_pos += B.list.size();
             kp.rec_off = reinterpret_cast<const int64_t *>(ctx->d_recoff.p);
             kp.records = reinterpret_cast<const uint64_t *>(ctx->d_rec.p);
@@ -451,6 +505,7 @@ spg_status spg_remove_round(spg_ctx *ctx, const spg_round_in *in, spg_round_out 
         SPG_CUDA(cudaMemcpyAsync(out->out + o0, reinterpret_cast<uint64_t *>(ctx->d_out.p) + o0, (size_t) (o1 - o0) * 8,
                                  cudaMemcpyDeviceToHost, ctx->s_out));
     }
+    ctx->retry_used = counter_next;
     SPG_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
     if(tgt_n) SPG_CUDA(cudaMemcpyAsync(out->dbg_target, ctx->d_tgt.p, (size_t) tgt_n * 8, cudaMemcpyDeviceToHost, ctx->s_out));
     if(wts_n) SPG_CUDA(cudaMemcpyAsync(out->dbg_weights, ctx->d_wts.p, (size_t) wts_n * 8, cudaMemcpyDeviceToHost, ctx->s_out));

@@ -52,6 +52,10 @@ struct spg_ctx {
     int64_t launches = 0;
     double last_ms = 0;
     DevBuf d_rec, d_recoff, d_outoff, d_out, d_list, d_tgt, d_tgtoff, d_wts, d_wtsoff, d_ws, d_gws, d_prof;
+    DevBuf d_retry, d_retry_cnt;                 // fast_kernel's refused blankets (per launch: a slice and a counter)
+    int retry_used = 0;                          // counters used by the last call
+    int fast_ctas_per_sm = 0;                    // resident CTAs per SM of the last fast_kernel launch (diagnostics)
+    bool no_fast = false;                        // env SPG_NO_FAST=1: blanket_kernel only (A/B measurements, tests)
     bool profiling = false;
 };
 
@@ -71,3 +75,9 @@ spg_status spg_launch_3_256l(spg_ctx *, spg::KernelParams &);  // lean: 256 thre
 spg_status spg_launch_6_256l(spg_ctx *, spg::KernelParams &);
 spg_status spg_launch_3_spill(spg_ctx *, spg::KernelParams &); // 256 threads, buffers in global memory
 spg_status spg_launch_6_spill(spg_ctx *, spg::KernelParams &);
+// fast_kernel<D, MAXW> (spg_fast.cuh): NFR tree rounds; SPG_ERR_UNSUPPORTED when the bucket does not fit
+spg_status spg_launch_fast_6_1(spg_ctx *, spg::KernelParams &);
+spg_status spg_launch_fast_6_4(spg_ctx *, spg::KernelParams &);
+spg_status spg_launch_fast_6_8(spg_ctx *, spg::KernelParams &);
+spg_status spg_launch_fast_3_1(spg_ctx *, spg::KernelParams &);
+spg_status spg_launch_fast_3_8(spg_ctx *, spg::KernelParams &);

@@ -1,20 +1,22 @@
 // spg_fast.cuh — the NFR-tree kernel (sm_100a): the path BASELINE.json's metric is quoted on and the one the
-// shipped datasets take (Chow-Liu tree, closed-form information fit), for blankets of relative-pose edges with one
-// removed vertex. Same stages as blanket_kernel (spg_kernels.cuh) — assembly, Schur complement, Chow-Liu, gauge
-// shortcut, closed form (reference src/vertex_remover.cpp:394-450, src/pseudo_chow_liu.cpp, src/logdet_function.cpp:
-// 236-279) — but built around ONE data structure: the symmetric k x k matrix lives in REGISTERS, as TR x D tiles of
-// its lower triangle, one tile per thread, from the assembly to the last sweep.
-//   * H_kk is accumulated straight into the tiles (no N x N matrix in shared memory), the rank-d Schur update is
-//     applied in registers, and both SPD inverses (C = (Lambda_t + I)^-1 and the anchored G = Lambda_rr^-1) are
-//     symmetric Gauss-Jordan sweeps over the lower-triangular tiles: half the FMAs and half the threads of the
-//     full-matrix sweep, 18 FMAs + 6 shared-memory loads per thread and pivot.
-//   * Lambda_t, C and G are stored PACKED (lower triangle): 33 KB instead of 65 KB per matrix at k = 90, and G
-//     overwrites C. A 16-vertex SE3 blanket needs ~92 KB and <= 128 registers: two CTAs of 256 threads per SM
-//     (16 warps, two independent pivot chains) instead of one at 229.7 KB; a 6-vertex blanket is ONE warp and 15 KB:
-//     ~14 blankets in flight per SM with __syncwarp() as the only barrier.
-//   * The kernel carries nothing but this path (no GLC, no Newton loop, no Jacobi eigen-solver). Whatever it does not
-//     take — GLC / MULTI input edges, several removed vertices, a refused gauge guard, any non-positive pivot — is
-//     appended to a device-side retry list and re-run by blanket_kernel, which reports the blanket's status.
+// shipped datasets take (Chow-Liu tree + closed-form information fit), for blankets of relative-pose edges with
+// one removed vertex. Same stages as blanket_kernel (spg_kernels.cuh) — assembly, Schur complement, Chow-Liu,
+// gauge shortcut, closed form (reference src/vertex_remover.cpp:394-450, src/pseudo_chow_liu.cpp,
+// src/logdet_function.cpp:236-279) — built around ONE data structure: the symmetric k x k matrix of the kept
+// variables lives in REGISTERS from the assembly to the last sweep, as D x D blocks of its lower block triangle,
+// one (row vertex, column vertex) block per thread.
+//   * H_kk is accumulated straight into the blocks (no N x N matrix anywhere), the rank-d Schur update is applied
+//     in registers, and both SPD inverses (C = (Lambda_t + I)^-1 and the anchored G = Lambda_rr^-1) are symmetric
+//     Gauss-Jordan sweeps over the lower block triangle: half the FMAs and half the threads of a full-matrix
+//     sweep. Per pivot only the pivot column crosses shared memory (double buffered, one barrier, look-ahead).
+//   * No k x k matrix is ever stored in shared memory: the Chow-Liu weights are computed by the thread that holds
+//     the block C_ji (diagonal blocks are published, 36 doubles per vertex), the Sigma blocks of the closed form
+//     are scattered from the registers that hold G. A 16-vertex SE3 blanket needs 120 threads and ~53 KB instead
+//     of 256 threads and 229.7 KB: FOUR blankets per SM (four independent pivot chains) instead of one; a
+//     blanket of <= 8 vertices is ONE warp with __syncwarp() as its only barrier, 10-16 blankets per SM.
+//   * The kernel carries nothing but this path (no GLC, no Newton loop, no Jacobi eigen-solver). Whatever it does
+//     not take — GLC / MULTI input edges, several removed vertices, a refused gauge guard, any non-positive
+//     pivot — is appended to a device-side retry list and re-run by blanket_kernel, which reports the status.
 #pragma once
 #include "spg_kernels.cuh"
 
@@ -30,7 +32,7 @@ __device__ __forceinline__ int fsync_or(int pred) {
     if constexpr(ONEWARP) return __any_sync(0xffffffffu, pred);
     else return __syncthreads_or(pred);
 }
-// sum over the CTA in a fixed order; every thread gets the result. red: >= 16 doubles.
+// sum over the CTA in a fixed order; every thread gets the result. red: >= 32 doubles.
 template <bool ONEWARP>
 __device__ __forceinline__ double fsum(double v, double *red) {
 #pragma unroll
@@ -47,137 +49,174 @@ __device__ __forceinline__ double fsum(double v, double *red) {
     }
 }
 
-// packed lower triangle, column-major: element (i, l), i >= l, of a k x k symmetric matrix
-__device__ __forceinline__ int pidx(int k, int i, int l) { return l * k - ((l * (l - 1)) >> 1) + (i - l); }
-__device__ __forceinline__ double psym(const double *A, int k, int i, int l) { return i >= l ? A[pidx(k, i, l)] : A[pidx(k, l, i)]; }
+// ---- block sweep ---------------------------------------------------------------------------------------------
+// The symmetric sweep operator (B_jj = -1/d, B_ij = A_ij / d, B_il = A_il - A_ij A_jl / d; all pivots swept: -A^-1)
+// applied one VERTEX (D pivots) at a time on the D x D register blocks of the lower block triangle. Per vertex J:
+//   (a) the thread of the diagonal block inverts it in registers (D scalar sweep steps, the pivots are the scalar
+//       sweep's pivots: pivot > 0 is LLT's positive-definiteness test) and publishes B = A_JJ^-1;
+//   (c) the threads of block column J (below the diagonal) and block row J (left of it) publish their panel block
+//       P_I = A_IJ and W_I = P_I B, and keep W_I (the swept panel) as their block;
+//   (e) every other block (I, L) -= W_I P_L^T: 6 x 36 independent DFMAs per thread, operands by 16-byte loads from
+//       shared memory; the thread of the next diagonal block goes on with (a) for vertex J + 1.
+// Two barriers per vertex instead of one per pivot, and two thirds of the instructions of a pivot-by-pivot sweep.
+template <int D> struct FastPad { static constexpr int PST = (D * D + 3) & ~1; }; // panel block stride: 38 (SE3), 10 (SE2)
 
-// One pivot step of the symmetric sweep on TR x D register tiles of the lower triangle. Pivot j = D J + C0.
-// `cur` holds column j of the current matrix (all rows, by symmetry), the pivot and its reciprocal; the threads
-// holding column / row j+1 update those elements first and publish them in `nxt` (look-ahead), then everybody
-// updates the rest of the tile: one barrier per pivot.
-template <int D, int TR, int C0>
-__device__ __forceinline__ void fast_step(double (&a)[TR][D], const double *cur, double *nxt, int NP, int J, int rb, int cb, int nsweep,
-                                          bool &bad, double &mypiv) {
-    constexpr int RPB = D / TR;
-    constexpr int R0 = C0 % TR;
-    const int j = D * J + C0;
-    const double d = cur[NP], inv = cur[NP + 1];
-    bad |= !(d > 0);
-    if((int) threadIdx.x == j) mypiv = d;
-    double ci[TR], cl[D];
-#pragma unroll
-    for(int r = 0; r < TR; r++) ci[r] = cur[TR * rb + r];
-#pragma unroll
-    for(int c = 0; c < D; c++) cl[c] = cur[D * cb + c] * inv;
-    const bool colj = (cb == J);
-    const bool rowj = (rb == RPB * J + C0 / TR);
-    constexpr bool wrap = (C0 + 1 == D);
-    constexpr int C1 = wrap ? 0 : C0 + 1;
-    constexpr int R1 = C1 % TR;
-    const int Jn = wrap ? J + 1 : J;
-    const int rbn = RPB * Jn + C1 / TR;
-    const bool more = (j + 1 < nsweep);
-    const bool pubcol = more && (cb == Jn);              // this tile holds rows of column j+1 (at / below its diagonal block)
-    const bool pubrow = more && (rb == rbn) && (cb < Jn); // this tile holds row j+1 left of the diagonal block
-    if(pubcol) {
-#pragma unroll
-        for(int r = 0; r < TR; r++) {
-            double v = a[r][C1] - ci[r] * cl[C1];
-            if(rowj && r == R0) v = cl[C1];
-            a[r][C1] = v;
-            nxt[TR * rb + r] = v;
-        }
-        if(rb == rbn) {
-            nxt[NP] = a[R1][C1];
-            nxt[NP + 1] = fast_rcp(a[R1][C1]);
-        }
-    }
-    if(pubrow) {
-#pragma unroll
-        for(int c = 0; c < D; c++) {
-            double v = a[R1][c] - ci[R1] * cl[c];
-            if(colj && c == C0) v = ci[R1] * inv;
-            a[R1][c] = v;
-            nxt[D * cb + c] = v;
-        }
-    }
-#pragma unroll
-    for(int r = 0; r < TR; r++)
-#pragma unroll
-        for(int c = 0; c < D; c++) {
-            const bool ahead = (pubcol && c == C1) || (pubrow && r == R1);
-            if(!ahead) a[r][c] -= ci[r] * cl[c];
-        }
-    if(rowj) {
-#pragma unroll
-        for(int c = 0; c < D; c++) a[R0][c] = cl[c];
-    }
-    if(colj) {
-#pragma unroll
-        for(int r = 0; r < TR; r++) a[r][C0] = ci[r] * inv;
-        if(rowj) a[R0][C0] = -inv;
-    }
-}
-
-template <int D, int TR, bool ONEWARP, int C0>
-__device__ __forceinline__ void fast_steps(double (&a)[TR][D], double *colbuf, int NP, int J, int rb, int cb, int nsweep, bool active,
-                                           bool &bad, double &mypiv) {
-    if constexpr(C0 < D) {
-        const int j = D * J + C0;
-        const int cs = NP + 2;
-        if(active) fast_step<D, TR, C0>(a, colbuf + (j & 1) * cs, colbuf + ((j + 1) & 1) * cs, NP, J, rb, cb, nsweep, bad, mypiv);
-        fsync<ONEWARP>();
-        fast_steps<D, TR, ONEWARP, C0 + 1>(a, colbuf, NP, J, rb, cb, nsweep, active, bad, mypiv);
-    }
-}
-
-// Sweeps the first nsweep (a multiple of D) pivots of the symmetric matrix held in the tiles: a <- -(A^-1) on the
-// leading nsweep x nsweep block. Returns false (uniformly) on a non-positive pivot. logpiv: log of pivot
-// threadIdx.x (0 beyond nsweep): summed over the CTA it is the log-determinant.
-template <int D, int TR, bool ONEWARP>
-__device__ __forceinline__ bool fast_sweep(double (&a)[TR][D], double *colbuf, int NP, int rb, int cb, int nsweep, bool active, double *logpiv) {
-    if(active && cb == 0) { // publish column 0
-#pragma unroll
-        for(int r = 0; r < TR; r++) colbuf[TR * rb + r] = a[r][0];
-        if(rb == 0) {
-            colbuf[NP] = a[0][0];
-            colbuf[NP + 1] = fast_rcp(a[0][0]);
-        }
-    }
-    fsync<ONEWARP>();
-    bool bad = false;
-    double mypiv = 1.0;
-    const int nJ = nsweep / D;
-#pragma unroll 1
-    for(int J = 0; J < nJ; J++) fast_steps<D, TR, ONEWARP, 0>(a, colbuf, NP, J, rb, cb, nsweep, active, bad, mypiv);
-    if(fsync_or<ONEWARP>(bad)) return false;
-    if(logpiv) *logpiv = ((int) threadIdx.x < nsweep) ? log(mypiv) : 0.0;
-    return true;
-}
-
-// D x D Cholesky of the diagonal block v of the packed matrix -> Lout (column-major), returns logdet
 template <int D>
-__device__ __forceinline__ double chol_block_packed(const double *Cp, int k, int v, double *Lout, bool &ok) {
-    double A[D * D];
+__device__ __forceinline__ void invert_tile(double (&a)[D][D], double *Bout, double *piv, bool &bad) {
+#pragma unroll
+    for(int s = 0; s < D; s++) {
+        const double d = a[s][s];
+        bad |= !(d > 0);
+        piv[s] = d;
+        const double inv = fast_rcp(d);
+        double cs[D];
+#pragma unroll
+        for(int i = 0; i < D; i++) cs[i] = a[i][s] * inv;
+#pragma unroll
+        for(int i = 0; i < D; i++)
+#pragma unroll
+            for(int j = 0; j < D; j++)
+                if(i != s && j != s) a[i][j] -= cs[i] * a[s][j];
+#pragma unroll
+        for(int j = 0; j < D; j++)
+            if(j != s) {
+                a[s][j] *= inv;
+                a[j][s] = cs[j];
+            }
+        a[s][s] = -inv;
+    }
+#pragma unroll
+    for(int p = 0; p < D; p++)
+#pragma unroll
+        for(int q = 0; q < D; q++) Bout[p * D + q] = -a[p][q];
+}
+
+// panel block of vertex v: X(x, p) = TRANSPOSED ? a[p][x] : a[x][p]. Publishes P[p][x] = X(x, p) and
+// W[q][x] = sum_p X(x, p) B[p][q], and replaces the block by the swept panel.
+template <int D, bool TRANSPOSED>
+__device__ __forceinline__ void panel_tile(double (&a)[D][D], const double *B, double *Pb, double *Wb) {
+#pragma unroll
+    for(int p = 0; p < D; p++)
+#pragma unroll
+        for(int x = 0; x < D; x++) Pb[p * D + x] = TRANSPOSED ? a[p][x] : a[x][p];
+#pragma unroll
+    for(int q = 0; q < D; q++) {
+        double bq[D];
+#pragma unroll
+        for(int p = 0; p < D; p++) bq[p] = B[q * D + p]; // B is symmetric
+#pragma unroll
+        for(int x = 0; x < D; x++) {
+            double w = 0;
+#pragma unroll
+            for(int p = 0; p < D; p++) w += (TRANSPOSED ? a[p][x] : a[x][p]) * bq[p];
+            Wb[q * D + x] = w;
+        }
+    }
+    // block (I, J) <- W_I ; block (J, L) <- B A_JL = W_L^T  (same thread wrote Wb: no barrier needed)
+#pragma unroll
+    for(int q = 0; q < D; q++)
+#pragma unroll
+        for(int x = 0; x < D; x++) {
+            if(TRANSPOSED) a[q][x] = Wb[q * D + x];
+            else a[x][q] = Wb[q * D + x];
+        }
+}
+
+// Sweeps the first nsv vertices of the symmetric matrix held in the blocks (active: vr < nsv): a <- -(A^-1) on the
+// leading block. Pivot j is left in s_piv[j]. Returns false (uniformly) on a non-positive pivot.
+template <int D, bool ONEWARP>
+__device__ __forceinline__ bool block_sweep(double (&a)[D][D], double *s_B, double *s_P, double *s_W, double *s_piv, int vr, int vc,
+                                            int nsv, bool active) {
+    constexpr int DD = D * D, PST = FastPad<D>::PST;
+    bool bad = false;
+    if(active && vr == 0 && vc == 0) invert_tile<D>(a, s_B, s_piv, bad);
+    fsync<ONEWARP>();
+#pragma unroll 1
+    for(int J = 0; J < nsv; J++) {
+        const double *B = s_B + (J & 1) * DD;
+        if(active) {
+            if(vc == J && vr != J) panel_tile<D, false>(a, B, s_P + vr * PST, s_W + vr * PST);
+            else if(vr == J && vc != J) panel_tile<D, true>(a, B, s_P + vc * PST, s_W + vc * PST);
+        }
+        fsync<ONEWARP>();
+        if(active && vr != J && vc != J) {
+            const double *Wb = s_W + vr * PST, *Pb = s_P + vc * PST;
+#pragma unroll
+            for(int p = 0; p < D; p++) {
+                double w[D], q[D];
+                if constexpr(D % 2 == 0) { // 16-byte loads (all offsets are even numbers of doubles)
+#pragma unroll
+                    for(int r = 0; r < D; r += 2) {
+                        const double2 t = *reinterpret_cast<const double2 *>(Wb + p * D + r);
+                        w[r] = t.x; w[r + 1] = t.y;
+                        const double2 u = *reinterpret_cast<const double2 *>(Pb + p * D + r);
+                        q[r] = u.x; q[r + 1] = u.y;
+                    }
+                } else {
+#pragma unroll
+                    for(int r = 0; r < D; r++) w[r] = Wb[p * D + r];
+#pragma unroll
+                    for(int c = 0; c < D; c++) q[c] = Pb[p * D + c];
+                }
+#pragma unroll
+                for(int r = 0; r < D; r++)
+#pragma unroll
+                    for(int c = 0; c < D; c++) a[r][c] -= w[r] * q[c];
+            }
+            if(vr == J + 1 && vc == J + 1 && J + 1 < nsv) invert_tile<D>(a, s_B + ((J + 1) & 1) * DD, s_piv + D * (J + 1), bad);
+        }
+        fsync<ONEWARP>();
+    }
+    return fsync_or<ONEWARP>(bad) == 0;
+}
+
+// Cholesky of the diagonal block C_vv = -a held in registers. Lout: column-major D x D, strictly-lower entries of
+// L and the RECIPROCALS of its diagonal; Cout: the block itself (column-major). Returns logdet C_vv.
+template <int D>
+__device__ __forceinline__ double chol_tile(const double (&a)[D][D], double *Lout, double *Cout, bool &ok) {
+    double L[D][D];
+    double lds = 0;
+    ok = true;
+#pragma unroll
+    for(int c = 0; c < D; c++) {
+        double d = -a[c][c];
+#pragma unroll
+        for(int p = 0; p < c; p++) d -= L[c][p] * L[c][p];
+        if(!(d > 0)) { ok = false; d = 1.0; }
+        lds += log(d);
+        const double il = rsqrt(d);
+        L[c][c] = il;
+#pragma unroll
+        for(int r = c + 1; r < D; r++) {
+            double s = -a[r][c];
+#pragma unroll
+            for(int p = 0; p < c; p++) s -= L[r][p] * L[c][p];
+            L[r][c] = s * il;
+        }
+    }
 #pragma unroll
     for(int c = 0; c < D; c++)
 #pragma unroll
-        for(int r = 0; r < D; r++) A[r + c * D] = (r >= c) ? Cp[pidx(k, v * D + r, v * D + c)] : 0.0;
-    return chol_small<D>(A, D, Lout, ok);
+        for(int r = 0; r < D; r++) {
+            Lout[r + c * D] = (r >= c) ? L[r][c] : 0.0;
+            Cout[r + c * D] = -a[r][c];
+        }
+    return lds;
 }
 
-// logdet (C_jj - C_ji C_ii^-1 C_ij), i < j, from the packed C and Li = chol(C_ii): schur_logdet of spg_kernels.cuh
+// logdet (C_jj - C_ji C_ii^-1 C_ij), i < j: C_ji = -a (rows: components of j, columns: components of i) in
+// registers, Li = chol_tile(C_ii), Cjj = the published diagonal block (pseudo_chow_liu.cpp:169-183)
 template <int D>
-__device__ __forceinline__ double schur_logdet_packed(const double *Cp, int k, int i, int j, const double *Li) {
-    double Y[D][D];
+__device__ __forceinline__ double schur_logdet_tile(const double (&a)[D][D], const double *Li, const double *Cjj) {
+    double Y[D][D]; // Y = Li^-1 C_ij, D x D: row r (component of i), column c (component of j)
 #pragma unroll
     for(int c = 0; c < D; c++) {
 #pragma unroll
         for(int r = 0; r < D; r++) {
-            double s = Cp[pidx(k, j * D + c, i * D + r)];
+            double s = -a[c][r];
 #pragma unroll
             for(int p = 0; p < r; p++) s -= Li[r + p * D] * Y[p][c];
-            Y[r][c] = s / Li[r + r * D];
+            Y[r][c] = s * Li[r + r * D];
         }
     }
     double S[D][D];
@@ -185,7 +224,7 @@ __device__ __forceinline__ double schur_logdet_packed(const double *Cp, int k, i
     for(int c = 0; c < D; c++)
 #pragma unroll
         for(int r = c; r < D; r++) {
-            double s = Cp[pidx(k, j * D + r, j * D + c)];
+            double s = Cjj[r + c * D];
 #pragma unroll
             for(int p = 0; p < D; p++) s -= Y[p][r] * Y[p][c];
             S[r][c] = s;
@@ -198,7 +237,7 @@ __device__ __forceinline__ double schur_logdet_packed(const double *Cp, int k, i
 #pragma unroll
         for(int p = 0; p < c; p++) d -= S[c][p] * S[c][p] * dinv[p];
         ld_sum += log(d);
-        dinv[c] = 1.0 / d;
+        dinv[c] = fast_rcp(d);
 #pragma unroll
         for(int r = c + 1; r < D; r++) {
             double s = S[r][c];
@@ -210,30 +249,53 @@ __device__ __forceinline__ double schur_logdet_packed(const double *Cp, int k, i
     return ld_sum;
 }
 
-// shared-memory plan of fast_kernel (doubles), host + device
-struct FastPlan {
-    int off_pose, off_T, off_C, off_col, off_h0, off_small, total;
-    int tri, NP, scratch; // packed size of one k x k matrix, padded k, doubles available for the per-edge J / M blocks (T + C)
-};
+// shared-memory plan of fast_kernel (doubles; struct FastPlan in spg_plan.h), computed on the host
 template <int D>
-__host__ __device__ inline FastPlan fast_plan(int max_nv, int max_rec_words) {
+inline FastPlan fast_plan(int max_nv, int max_e, int max_rec_words, size_t smem_budget_bytes) {
     constexpr int PS = PoseStride<D>::value;
+    constexpr int JW = 2 * D * D, SW = 4 * D * D, PST = FastPad<D>::PST;
     FastPlan p;
-    const int nk = max_nv - 1, kmax = D * (nk > 0 ? nk : 1), pairs = nk * (nk - 1) / 2;
+    const int nk = max_nv > 1 ? max_nv - 1 : 1, kmax = D * nk, pairs = nk * (nk - 1) / 2;
     p.NP = kmax;
-    p.tri = (kmax * (kmax + 1) / 2 + 1) & ~1;
-    int o = (max_rec_words + 1) & ~1;
-    p.off_pose = o; o += max_nv * PS;
-    p.off_T = o;    o += p.tri;
-    p.off_C = o;    o += p.tri;
-    p.scratch = 2 * p.tri;
-    p.off_col = o;  o += 2 * (p.NP + 2);
-    p.off_h0 = o;   o += 2 * D * D + 2 * D * kmax; // H00 ping-pong, H_k0 and Y, both [D][kmax]
+    p.ntiles = nk * (nk + 1) / 2;
+    int o = 0;
+    p.off_pose = o;  o += max_nv * PS;
+    p.off_B = o;     o += 2 * D * D;
+    p.off_P = o;     o += nk * PST;
+    p.off_W = o;     o += nk * PST;
     p.off_small = o;
-    // wt[pairs] heapw[pairs] heapab[pairs](int) tree[2 pairs + 2](int) uf[nk](int) Lfac[nk D D] logd[nk] cs[kmax] red[34] ev[max_e -> later] misc[16](int)
-    o += pairs + pairs + (pairs + 1) / 2 + (pairs + 1) + (nk + 2) / 2 + nk * D * D + nk + kmax + 34 + 8;
-    p.total = o;
+    // wt[pairs] heapw[pairs] heapab[pairs](int) tree[2 pairs + 2](int) uf[nk](int) ev[max_e](int) Lfac[nk D D] Cd[nk D D]
+    // logd[nk] cs[kmax] piv[kmax] red[34] misc[16](int)
+    o += 2 * pairs + (pairs + 1) / 2 + (pairs + 1) + (nk + 2) / 2 + (max_e + 2) / 2 + 2 * nk * D * D + nk + 2 * kmax + 34 + 8;
+    o = (o + 1) & ~1;
+    p.off_U = o;
+    // union region. A (assembly, Schur): record | H00 x2 | H_k0 | Y | J, M of a chunk of edges.
+    // B (Schur .. anchored sweep): the Lambda_t blocks, [element][tile]. C (closed form): Jn | Sg | Tm | Bk.
+    const int rec = (max_rec_words + 1) & ~1;
+    const int h0 = 2 * D * D + 2 * D * kmax;
+    const int B = p.ntiles * D * D;
+    const int C = (nk > 1 ? nk - 1 : 1) * (2 * JW + SW + D * D);
+    const int emin = max_e < 1 ? 1 : (max_e < 4 ? max_e : 4);
+    int U = rec + h0 + emin * 2 * JW;
+    if(B > U) U = B;
+    if(C > U) U = C;
+    // all edges in one assembly pass when that still leaves room for the resident CTAs the registers allow
+    const int Ufull = rec + h0 + (max_e < 1 ? 1 : max_e) * 2 * JW;
+    if(Ufull > U && (size_t) (p.off_U + Ufull) * sizeof(double) <= smem_budget_bytes) U = Ufull;
+    p.chunk = (U - rec - h0) / (2 * JW);
+    if(p.chunk > max_e) p.chunk = max_e;
+    if(p.chunk < 1) p.chunk = 1;
+    p.off_h00 = p.off_U + rec;
+    p.off_hk0 = p.off_h00 + 2 * D * D;
+    p.off_y = p.off_hk0 + D * kmax;
+    p.off_jm = p.off_y + D * kmax;
+    p.total = p.off_U + U;
     return p;
+}
+// threads of a CTA: one per block of the lower block triangle, rounded up to warps
+__host__ __device__ inline int fast_threads(int max_nv) {
+    const int nk = max_nv > 1 ? max_nv - 1 : 1;
+    return ((nk * (nk + 1) / 2 + 31) / 32) * 32;
 }
 
 #define SPG_FT(i)                                                                                    \
@@ -245,39 +307,47 @@ __host__ __device__ inline FastPlan fast_plan(int max_nv, int max_rec_words) {
         }                                                                                            \
     } while(0)
 
-// ONEWARP: one warp per blanket (k <= 30 for SE3), __syncwarp() only. Otherwise blockDim.x = 32 * ceil(tiles / 32).
-template <int D, bool ONEWARP>
-__global__ void __launch_bounds__(ONEWARP ? 32 : 512) fast_kernel(const KernelParams P) {
-    extern __shared__ double smem_dyn[];
-    double *smem = smem_dyn;
+// MAXW: warps per CTA at most (1: one warp per blanket, __syncwarp() only). blockDim.x = fast_threads(max_nv).
+template <int D, int MAXW>
+__global__ void __launch_bounds__(32 * MAXW, MAXW == 1 ? (D == 6 ? 12 : 16) : (MAXW <= 4 ? 3 : (D == 6 ? 1 : 2))) fast_kernel(const KernelParams P) {
+    extern __shared__ __align__(16) double fast_smem[];
+    double *smem = fast_smem;
+    constexpr bool ONEWARP = (MAXW == 1);
     constexpr int PS = PoseStride<D>::value;
     constexpr int PW = (D == 6) ? 7 : 3;
     constexpr int JW = D * 2 * D;
-    constexpr int TR = 3;
-    constexpr int RPB = D / TR;
+    constexpr int SW = 4 * D * D;
+    constexpr int DD = D * D;
     const int tid = threadIdx.x, NT = blockDim.x;
 
-    const FastPlan pl = fast_plan<D>(P.max_nv, P.max_rec_words);
-    uint64_t *s_rec = reinterpret_cast<uint64_t *>(smem);
+    const FastPlan &pl = P.fast; // computed on the host (fast_plan): constant-bank loads
+    const int NP = pl.NP;
     double *s_pose = smem + pl.off_pose;
-    double *Tp = smem + pl.off_T;
-    double *Cp = smem + pl.off_C;
-    double *colbuf = smem + pl.off_col;
-    double *s_h00 = smem + pl.off_h0;         // 2 x D*D
-    double *s_hk0 = s_h00 + 2 * D * D;        // [D][NP]: H_k0, p-major
-    double *s_y = s_hk0 + D * pl.NP;          // [D][NP]: H_k0 H_00^-1
-    const int nkmax = P.max_nv - 1, kmaxb = pl.NP, pairs_max = nkmax * (nkmax - 1) / 2;
+    double *s_B = smem + pl.off_B;
+    double *s_P = smem + pl.off_P;
+    double *s_W = smem + pl.off_W;
+    const int nkmax = P.max_nv > 1 ? P.max_nv - 1 : 1, kmaxb = pl.NP, pairs_max = nkmax * (nkmax - 1) / 2;
     double *s_wt = smem + pl.off_small;
     double *s_heapw = s_wt + pairs_max;
     int *s_heapab = reinterpret_cast<int *>(s_heapw + pairs_max);
     int *s_tree = reinterpret_cast<int *>(s_heapw + pairs_max + (pairs_max + 1) / 2);
     int *s_uf = reinterpret_cast<int *>(s_heapw + pairs_max + (pairs_max + 1) / 2 + (pairs_max + 1));
-    double *s_Lfac = s_heapw + pairs_max + (pairs_max + 1) / 2 + (pairs_max + 1) + (nkmax + 2) / 2;
-    double *s_logd = s_Lfac + nkmax * D * D;
+    int *s_ev = reinterpret_cast<int *>(s_heapw + pairs_max + (pairs_max + 1) / 2 + (pairs_max + 1) + (nkmax + 2) / 2);
+    double *s_Lfac = s_heapw + pairs_max + (pairs_max + 1) / 2 + (pairs_max + 1) + (nkmax + 2) / 2 + (P.max_e + 2) / 2;
+    double *s_Cd = s_Lfac + nkmax * DD;
+    double *s_logd = s_Cd + nkmax * DD;
     double *s_cs = s_logd + nkmax;
-    double *s_red = s_cs + kmaxb;
+    double *s_piv = s_cs + kmaxb;
+    double *s_red = s_piv + kmaxb;
     int *s_misc = reinterpret_cast<int *>(s_red + 34);
-    const int NP = pl.NP;
+    double *U = smem + pl.off_U;
+    uint64_t *s_rec = reinterpret_cast<uint64_t *>(U);
+    double *s_h00 = smem + pl.off_h00; // 2 x D*D
+    double *s_hk0 = smem + pl.off_hk0; // [D][NP]: H_k0, p-major
+    double *s_y = smem + pl.off_y;     // [D][NP]: H_k0 H_00^-1
+    double *JM = smem + pl.off_jm;     // per edge of a chunk: J = [Ji Jj], M = Omega J
+    double *Tb = U;                    // Lambda_t blocks, [element][tile]
+    const int tstride = pl.ntiles;
 
     for(int li = blockIdx.x; li < P.n_list; li += gridDim.x) {
         const int b = P.list ? P.list[li] : li;
@@ -289,7 +359,7 @@ __global__ void __launch_bounds__(ONEWARP ? 32 : 512) fast_kernel(const KernelPa
         const int nk = nv - nrem, k = D * nk;
 
         fsync<ONEWARP>(); // the shared buffers of the previous blanket are dead
-        bool refuse = (rdim != D || nv > P.max_nv || ne > P.max_e || rec_words > P.max_rec_words || nrem != 1 || nk < 0 || ne < 1);
+        bool refuse = (rdim != D || nv > P.max_nv || ne > P.max_e || rec_words > P.max_rec_words || nrem != 1 || nk < 2 || ne < 1);
         for(int t = tid; t < out_words; t += NT) gout[t] = 0;
         long long t_last = clock64();
         if(!refuse) {
@@ -306,27 +376,27 @@ __global__ void __launch_bounds__(ONEWARP ? 32 : 512) fast_kernel(const KernelPa
                 const int32_t *eh = reinterpret_cast<const int32_t *>(s_rec + r_etab[e]);
                 const int32_t *vi = reinterpret_cast<const int32_t *>(s_rec + r_etab[e] + 2);
                 badedge |= (eh[0] != SPG_EDGE_POSE) || (eh[1] != 2) || (vi[0] == vi[1]);
+                s_ev[e] = pk(vi[0], vi[1]);
             }
             refuse = fsync_or<ONEWARP>(badedge) != 0;
         }
         int n_out = 0;
         double out_kld = 0;
         int out_flags = 0;
-        if(!refuse && nk >= 2) {
-            // ---- tile of this thread: rows [TR rb, TR rb + TR), columns [D cb, D cb + D) of the kept block ----
-            const int nbr = RPB * nk;
-            const int ntiles = nbr * nk - RPB * (nk * (nk - 1) / 2);
+        if(!refuse) {
+            // ---- block of this thread: rows of kept vertex vr, columns of kept vertex vc <= vr ------------------
+            const int ntiles = nk * (nk + 1) / 2;
             const bool has_tile = tid < ntiles;
-            int cb = 0, rb = 0;
+            int vc = 0, vr = 0;
             if(has_tile) {
                 int rem = tid;
-                while(rem >= nbr - RPB * cb) { rem -= nbr - RPB * cb; cb++; }
-                rb = RPB * cb + rem;
+                while(rem >= nk - vc) { rem -= nk - vc; vc++; }
+                vr = vc + rem;
             }
-            const int vr = rb / RPB, roff = (rb % RPB) * TR; // kept vertex of the rows, first row inside its block
-            double a[TR][D];
+            const bool diag = has_tile && (vr == vc);
+            double a[D][D];
 #pragma unroll
-            for(int r = 0; r < TR; r++)
+            for(int r = 0; r < D; r++)
 #pragma unroll
                 for(int c = 0; c < D; c++) a[r][c] = 0.0;
 
@@ -335,15 +405,13 @@ __global__ void __launch_bounds__(ONEWARP ? 32 : 512) fast_kernel(const KernelPa
                 if constexpr(D == 6) se3_from_flat(r_pose + PW * v, s_pose + PS * v);
                 else se2_from_flat(r_pose + PW * v, s_pose + PS * v);
             }
-            for(int t = tid; t < (D + 2 * NP) * D; t += NT) s_h00[D * D + t] = 0.0; // second H00 buffer, H_k0, Y
+            for(int t = tid; t < DD + 2 * D * NP; t += NT) s_h00[DD + t] = 0.0; // second H00 buffer, H_k0, Y
             fsync<ONEWARP>();
             SPG_FT(0);
-            // ---- S1: assembly. Per chunk of edges: J = [Ji Jj] and M = Omega J in shared memory (over the T / C
-            // area, unused until the Schur step), then every tile gathers the edges of its vertex pair in edge
-            // order (fixed summation order), and D (k + D) threads gather H_00 and H_k0. ---------------------------
-            double *JM = Tp;
-            const int chunk = max(1, pl.scratch / (2 * JW));
-            double h0acc = 0; // entry (i, p) of [H_k0; H_00] gathered by this thread: t = i + (k + D) * p ... first entry only
+            // ---- S1: assembly. Per chunk of edges: J = [Ji Jj] and M = Omega J in shared memory, then every
+            // block gathers the edges of its vertex pair in edge order (fixed summation order), and D (k + D)
+            // threads gather H_00 and H_k0. -----------------------------------------------------------------------
+            const int chunk = pl.chunk;
             for(int e0 = 0; e0 < ne; e0 += chunk) {
                 const int ce = min(chunk, ne - e0);
                 for(int e = tid; e < ce; e += NT) {
@@ -367,24 +435,24 @@ __global__ void __launch_bounds__(ONEWARP ? 32 : 512) fast_kernel(const KernelPa
                 }
                 fsync<ONEWARP>();
                 if(has_tile) {
-                    const int lr = vr + 1, lc = cb + 1; // local vertex indices (the removed vertex is 0)
+                    const int lr = vr + 1, lc = vc + 1; // local vertex indices (the removed vertex is 0)
                     for(int e = 0; e < ce; e++) {
-                        const int32_t *vi = reinterpret_cast<const int32_t *>(s_rec + r_etab[e0 + e] + 2);
-                        const int va = vi[0], vb = vi[1];
+                        const int vab = s_ev[e0 + e];
+                        const int va = pk_a(vab), vb = pk_b(vab);
                         int sr, sc; // side (0: Ji / first vertex, 1: Jj) of the row vertex and of the column vertex
                         if(va == lr) sr = 0; else if(vb == lr) sr = 1; else continue;
                         if(va == lc) sc = 0; else if(vb == lc) sc = 1; else continue;
-                        const double *Jr = JM + (size_t) e * 2 * JW + (sr * D + roff) * D;
-                        const double *Mc = JM + (size_t) e * 2 * JW + JW + sc * D * D;
+                        const double *Jr = JM + (size_t) e * 2 * JW + sr * DD;
+                        const double *Mc = JM + (size_t) e * 2 * JW + JW + sc * DD;
 #pragma unroll
                         for(int p = 0; p < D; p++) {
-                            double jr[TR], mc[D];
+                            double jr[D], mc[D];
 #pragma unroll
-                            for(int r = 0; r < TR; r++) jr[r] = Jr[p + r * D];
+                            for(int r = 0; r < D; r++) jr[r] = Jr[p + r * D];
 #pragma unroll
                             for(int c = 0; c < D; c++) mc[c] = Mc[p + c * D];
 #pragma unroll
-                            for(int r = 0; r < TR; r++)
+                            for(int r = 0; r < D; r++)
 #pragma unroll
                                 for(int c = 0; c < D; c++) a[r][c] += jr[r] * mc[c];
                         }
@@ -396,8 +464,8 @@ __global__ void __launch_bounds__(ONEWARP ? 32 : 512) fast_kernel(const KernelPa
                     const int lv = (i < k) ? i / D + 1 : 0, di = (i < k) ? i % D : i - k;
                     double s = 0;
                     for(int e = 0; e < ce; e++) {
-                        const int32_t *vi = reinterpret_cast<const int32_t *>(s_rec + r_etab[e0 + e] + 2);
-                        const int va = vi[0], vb = vi[1];
+                        const int vab = s_ev[e0 + e];
+                        const int va = pk_a(vab), vb = pk_b(vab);
                         int sv, s0;
                         if(va == lv) sv = 0; else if(vb == lv) sv = 1; else continue;
                         if(va == 0) s0 = 0; else if(vb == 0) s0 = 1; else continue;
@@ -407,19 +475,18 @@ __global__ void __launch_bounds__(ONEWARP ? 32 : 512) fast_kernel(const KernelPa
                         for(int q = 0; q < D; q++) s += Jv[q] * M0[q];
                     }
                     if(i < k) s_hk0[p * NP + i] += s;
-                    else s_h00[D * D + di + p * D] += s;
+                    else s_h00[DD + di + p * D] += s;
                 }
                 fsync<ONEWARP>();
             }
-            (void) h0acc;
             SPG_FT(1);
             // ---- S2: Schur complement Lambda_t = H_kk - H_k0 H_00^-1 H_0k (vertex_remover.cpp:443-449) ---------
-            // H_00^-1 by D symmetric Gauss-Jordan steps on D*D threads (a pivot <= 0 is LLT's failure)
+            // H_00^-1 by D symmetric Gauss-Jordan steps (a pivot <= 0 is LLT's failure)
             {
-                double *src = s_h00 + D * D, *dst = s_h00;
+                double *src = s_h00 + DD, *dst = s_h00;
                 for(int s0 = 0; s0 < D; s0++) {
-                    if(tid < D * D) {
-                        const int i = tid % D, j = tid / D;
+                    for(int t = tid; t < DD; t += NT) {
+                        const int i = t % D, j = t / D;
                         const double d = src[s0 + s0 * D];
                         if(!(d > 0)) s_misc[0] = 1;
                         const double inv = 1.0 / d, bis = src[i + s0 * D], bsj = src[s0 + j * D];
@@ -427,13 +494,12 @@ __global__ void __launch_bounds__(ONEWARP ? 32 : 512) fast_kernel(const KernelPa
                         if(j == s0) v = bis * inv;
                         if(i == s0) v = bsj * inv;
                         if(i == s0 && j == s0) v = -inv;
-                        dst[tid] = v;
+                        dst[t] = v;
                     }
                     fsync<ONEWARP>();
                     double *tmp = src; src = dst; dst = tmp;
                 }
-                // D even: the result (-H_00^-1) is back in s_h00 + D*D; D odd: in s_h00
-                const double *Hinv = src;
+                const double *Hinv = src; // -H_00^-1
                 for(int t = tid; t < k * D; t += NT) { // Y[p][i] = sum_q H_k0[q][i] * H_00^-1[q][p]
                     const int i = t % k, p = t / k;
                     double s = 0;
@@ -444,34 +510,49 @@ __global__ void __launch_bounds__(ONEWARP ? 32 : 512) fast_kernel(const KernelPa
                 fsync<ONEWARP>();
             }
             if(s_misc[0]) refuse = true; // uniform (read after the barrier)
+            int bigdiag = 0;
             if(!refuse) {
                 if(has_tile) {
 #pragma unroll
                     for(int p = 0; p < D; p++) {
-                        double yi[TR], hl[D];
+                        double yi[D], hl[D];
 #pragma unroll
-                        for(int r = 0; r < TR; r++) yi[r] = s_y[p * NP + TR * rb + r];
+                        for(int r = 0; r < D; r++) yi[r] = s_y[p * NP + D * vr + r];
 #pragma unroll
-                        for(int c = 0; c < D; c++) hl[c] = s_hk0[p * NP + D * cb + c];
+                        for(int c = 0; c < D; c++) hl[c] = s_hk0[p * NP + D * vc + c];
 #pragma unroll
-                        for(int r = 0; r < TR; r++)
+                        for(int r = 0; r < D; r++)
 #pragma unroll
                             for(int c = 0; c < D; c++) a[r][c] -= yi[r] * hl[c];
                     }
-                    // Lambda_t, lower triangle, packed (the J / M blocks in this area are dead)
+                    if(diag) { // strict upper mirrored onto the strict lower triangle (:447-449); guard (ii) of S4
 #pragma unroll
-                    for(int r = 0; r < TR; r++)
+                        for(int r = 0; r < D; r++)
 #pragma unroll
-                        for(int c = 0; c < D; c++) {
-                            const int i = TR * rb + r, l = D * cb + c;
-                            if(i >= l) Tp[pidx(k, i, l)] = a[r][c];
-                        }
+                            for(int c = 0; c < D; c++)
+                                if(r > c) a[r][c] = a[c][r];
+#pragma unroll
+                        for(int r = 0; r < D; r++) bigdiag |= !(fabs(a[r][r]) < 1e8);
+                    }
                 }
-                fsync<ONEWARP>();
-                if(P.dbg_target) {
+                if(P.dbg_target && has_tile) {
                     double *g = P.dbg_target + P.dbg_target_off[b];
-                    if(P.dbg_target_off[b + 1] - P.dbg_target_off[b] >= (int64_t) k * k)
-                        for(int t = tid; t < k * k; t += NT) g[t] = psym(Tp, k, t % k, t / k);
+                    if(P.dbg_target_off[b + 1] - P.dbg_target_off[b] >= (int64_t) k * k) {
+#pragma unroll
+                        for(int r = 0; r < D; r++)
+#pragma unroll
+                            for(int c = 0; c < D; c++) {
+                                g[(D * vr + r) + (size_t) (D * vc + c) * k] = a[r][c];
+                                g[(D * vc + c) + (size_t) (D * vr + r) * k] = a[r][c];
+                            }
+                    }
+                }
+                fsync<ONEWARP>(); // Y, H_k0 and the record are dead: the union region now holds the Lambda_t blocks
+                if(has_tile) {
+#pragma unroll
+                    for(int r = 0; r < D; r++)
+#pragma unroll
+                        for(int c = 0; c < D; c++) Tb[(r + c * D) * tstride + tid] = a[r][c];
                 }
             }
             SPG_FT(2);
@@ -483,39 +564,25 @@ __global__ void __launch_bounds__(ONEWARP ? 32 : 512) fast_kernel(const KernelPa
                 } else {
                     n_out = nk - 1;
                     const int all = nk * (nk - 1) / 2;
-                    // C = (Lambda_t + 1 I)^-1 (fillEdges, :185-190): symmetric sweep of the tiles
-                    if(has_tile) {
+                    // C = (Lambda_t + 1 I)^-1 (fillEdges, :185-190): symmetric sweep of the blocks
+                    if(diag) {
 #pragma unroll
-                        for(int r = 0; r < TR; r++)
-#pragma unroll
-                            for(int c = 0; c < D; c++)
-                                if(TR * rb + r == D * cb + c) a[r][c] += 1.0;
+                        for(int r = 0; r < D; r++) a[r][r] += 1.0;
                     }
-                    if(!fast_sweep<D, TR, ONEWARP>(a, colbuf, NP, rb, cb, k, has_tile, nullptr)) refuse = true;
+                    if(!block_sweep<D, ONEWARP>(a, s_B, s_P, s_W, s_piv, vr, vc, nk, has_tile)) refuse = true;
                     if(!refuse) {
-                        if(has_tile) {
-#pragma unroll
-                            for(int r = 0; r < TR; r++)
-#pragma unroll
-                                for(int c = 0; c < D; c++) {
-                                    const int i = TR * rb + r, l = D * cb + c;
-                                    if(i >= l) Cp[pidx(k, i, l)] = -a[r][c];
-                                }
-                        }
-                        fsync<ONEWARP>();
                         SPG_FT(3);
-                        for(int v = tid; v < nk; v += NT) {
+                        if(diag) {
                             bool ok;
-                            s_logd[v] = chol_block_packed<D>(Cp, k, v, s_Lfac + v * D * D, ok);
+                            s_logd[vr] = chol_tile<D>(a, s_Lfac + vr * DD, s_Cd + vr * DD, ok);
                             if(!ok) s_misc[0] = 1;
                         }
                         fsync<ONEWARP>();
                         // weight(i,j) = logdet C_jj - logdet (C_jj - C_ji C_ii^-1 C_ij)   (:169-183)
-                        for(int t = tid; t < all; t += NT) {
-                            int i = 0, rem = t;
-                            while(rem >= nk - 1 - i) { rem -= nk - 1 - i; i++; }
-                            const int j = i + 1 + rem;
-                            s_wt[t] = s_logd[j] - schur_logdet_packed<D>(Cp, k, i, j, s_Lfac + i * D * D);
+                        if(has_tile && !diag) {
+                            const int i = vc, j = vr;
+                            const int t = i * nk - (i * (i + 1)) / 2 + (j - i - 1);
+                            s_wt[t] = s_logd[j] - schur_logdet_tile<D>(a, s_Lfac + i * DD, s_Cd + j * DD);
                         }
                         fsync<ONEWARP>();
                         if(s_misc[0]) refuse = true;
@@ -594,50 +661,42 @@ __global__ void __launch_bounds__(ONEWARP ? 32 : 512) fast_kernel(const KernelPa
             double glog = 0;
             if(!refuse) {
                 // guard (ii): every diagonal entry of Lambda_t below 1e8
-                int bigdiag = 0;
-                for(int i = tid; i < k; i += NT) bigdiag |= !(fabs(Tp[pidx(k, i, i)]) < 1e8);
                 if(fsync_or<ONEWARP>(bigdiag)) refuse = true;
             }
             if(!refuse) {
-                // G = Lambda_rr^-1 (last kept vertex anchored): reload the tiles of the leading block and sweep
+                // G = Lambda_rr^-1 (last kept vertex anchored): reload the blocks and sweep the first nk - 1 vertices
                 const bool act = has_tile && vr < nk - 1;
-                if(act) {
+                if(has_tile) {
 #pragma unroll
-                    for(int r = 0; r < TR; r++)
+                    for(int r = 0; r < D; r++)
 #pragma unroll
-                        for(int c = 0; c < D; c++) a[r][c] = psym(Tp, k, TR * rb + r, D * cb + c);
+                        for(int c = 0; c < D; c++) a[r][c] = act ? Tb[(r + c * D) * tstride + tid] : 0.0;
                 }
-                if(!fast_sweep<D, TR, ONEWARP>(a, colbuf, NP, rb, cb, kk, act, &glog)) refuse = true;
+                if(!block_sweep<D, ONEWARP>(a, s_B, s_P, s_W, s_piv, vr, vc, nk - 1, act)) refuse = true;
                 if(!refuse) {
-                    // guard (i): ||G||_F <= 1e5
+                    // guard (i): ||G||_F <= 1e5; log-determinant of Lambda_rr from the pivots
                     double fp = 0;
                     if(act) {
+                        const double w = diag ? 1.0 : 2.0;
 #pragma unroll
-                        for(int r = 0; r < TR; r++)
+                        for(int r = 0; r < D; r++)
 #pragma unroll
-                            for(int c = 0; c < D; c++) {
-                                const int i = TR * rb + r, l = D * cb + c;
-                                const double w = (i > l) ? 2.0 : (i == l ? 1.0 : 0.0);
-                                fp += w * a[r][c] * a[r][c];
-                                if(i >= l) Cp[pidx(kk, i, l)] = -a[r][c]; // G over C (dead since the weights are out)
-                            }
+                            for(int c = 0; c < D; c++) fp += w * a[r][c] * a[r][c];
                     }
                     const double frob2 = fsum<ONEWARP>(fp, s_red);
                     if(!(frob2 <= 1e10)) refuse = true;
-                    fsync<ONEWARP>();
+                    for(int t = tid; t < kk; t += NT) glog += log(s_piv[t]);
                 }
             }
             SPG_FT(6);
             if(!refuse) {
                 // new-edge Jacobians at zero error (vertex_remover.cpp:466-498), Sigma blocks from G, X_e = (J Sigma J^T)^-1
-                const double *Gp = Cp;
-                constexpr int SW = 4 * D * D;
-                double *Jn = Tp;                          // n_out * JW    (Lambda_t is dead)
+                double *Jn = U;                           // n_out * JW    (the Lambda_t blocks are dead)
                 double *Sg = Jn + (size_t) n_out * JW;    // n_out * SW
                 double *Tm = Sg + (size_t) n_out * SW;    // n_out * JW
                 double *Bk = Tm + (size_t) n_out * JW;    // n_out * D*D
-                double *Bk2 = Bk + (size_t) n_out * D * D;
-                const int slot = 1 + PW + D * D;
+                double *Bk2 = Sg;                         // ping-pong partner of Bk once Sg is consumed
+                const int slot = 1 + PW + DD;
                 for(int e = tid; e < n_out; e += NT) {
                     const int ea = pk_a(s_tree[e]), eb = pk_b(s_tree[e]);
                     const double *Xa = s_pose + PS * (1 + ea), *Xb = s_pose + PS * (1 + eb);
@@ -652,16 +711,29 @@ __global__ void __launch_bounds__(ONEWARP ? 32 : 512) fast_kernel(const KernelPa
                     if constexpr(D == 6) se3_to_flat(Z, sm);
                     else { sm[0] = Z[0]; sm[1] = Z[1]; sm[2] = Z[2]; }
                 }
-                for(int t = tid; t < n_out * SW; t += NT) {
-                    const int e = t / SW, q = t % SW, i = q % (2 * D), j = q / (2 * D);
-                    if(i >= j) {
+                // Sigma_e = [[G_aa G_ab] [G_ba G_bb]] scattered from the registers (G = -a; zero rows / columns for the
+                // anchored vertex: its blocks were loaded as zeros)
+                if(has_tile) {
+                    for(int e = 0; e < n_out; e++) {
                         const int ea = pk_a(s_tree[e]), eb = pk_b(s_tree[e]);
-                        const int ri = (i < D ? ea * D + i : eb * D + i - D);
-                        const int rj = (j < D ? ea * D + j : eb * D + j - D);
-                        double s = 0;
-                        if(ri < kk && rj < kk) s = psym(Gp, kk, ri, rj);
-                        Sg[(size_t) e * SW + i + j * 2 * D] = s;
-                        Sg[(size_t) e * SW + j + i * 2 * D] = s;
+                        double *S2 = Sg + (size_t) e * SW;
+                        if(diag) {
+                            if(vr == ea || vr == eb) {
+                                const int o = (vr == ea) ? 0 : D;
+#pragma unroll
+                                for(int r = 0; r < D; r++)
+#pragma unroll
+                                    for(int c = 0; c < D; c++) S2[(o + r) + (o + c) * 2 * D] = (r >= c) ? -a[r][c] : -a[c][r];
+                            }
+                        } else if(vc == ea && vr == eb) {
+#pragma unroll
+                            for(int r = 0; r < D; r++)
+#pragma unroll
+                                for(int c = 0; c < D; c++) {
+                                    S2[(D + r) + c * 2 * D] = -a[r][c];
+                                    S2[c + (D + r) * 2 * D] = -a[r][c];
+                                }
+                        }
                     }
                 }
                 fsync<ONEWARP>();
@@ -675,8 +747,8 @@ __global__ void __launch_bounds__(ONEWARP ? 32 : 512) fast_kernel(const KernelPa
                     Tm[t] = acc;
                 }
                 fsync<ONEWARP>();
-                for(int t = tid; t < n_out * D * D; t += NT) { // block = Tm J^T, symmetrised (logdet_function.cpp:249-270)
-                    const int e = t / (D * D), q = t % (D * D), rr = q % D, cc = q / D;
+                for(int t = tid; t < n_out * DD; t += NT) { // block = Tm J^T, symmetrised (logdet_function.cpp:249-270)
+                    const int e = t / DD, q = t % DD, rr = q % D, cc = q / D;
                     if(rr >= cc) {
                         const double *J = Jn + (size_t) e * JW;
                         const double *Te = Tm + (size_t) e * JW;
@@ -687,16 +759,16 @@ __global__ void __launch_bounds__(ONEWARP ? 32 : 512) fast_kernel(const KernelPa
                             s2 += Te[cc + j * D] * J[rr + j * D];
                         }
                         const double v = 0.5 * (s1 + s2);
-                        Bk[(size_t) e * D * D + rr + cc * D] = v;
-                        Bk[(size_t) e * D * D + cc + rr * D] = v;
+                        Bk[(size_t) e * DD + rr + cc * D] = v;
+                        Bk[(size_t) e * DD + cc + rr * D] = v;
                     }
                 }
                 fsync<ONEWARP>();
                 double *src = Bk, *dst = Bk2;
                 for(int s0 = 0; s0 < D; s0++) { // X_e = block^-1 (:273-274), all blocks together, D Gauss-Jordan steps
-                    for(int t = tid; t < n_out * D * D; t += NT) {
-                        const int e = t / (D * D), q = t % (D * D), i = q % D, j = q / D;
-                        const double *B = src + (size_t) e * D * D;
+                    for(int t = tid; t < n_out * DD; t += NT) {
+                        const int e = t / DD, q = t % DD, i = q % D, j = q / D;
+                        const double *B = src + (size_t) e * DD;
                         const double d = B[s0 + s0 * D];
                         if(!(d > 0)) s_misc[0] = 1;
                         if(i == s0 && j == s0) s_cs[e * D + s0] = d;
@@ -712,8 +784,8 @@ __global__ void __launch_bounds__(ONEWARP ? 32 : 512) fast_kernel(const KernelPa
                 }
                 if(s_misc[0]) refuse = true;
                 if(!refuse) {
-                    for(int t = tid; t < n_out * D * D; t += NT) {
-                        const int e = t / (D * D), q = t % (D * D);
+                    for(int t = tid; t < n_out * DD; t += NT) {
+                        const int e = t / DD, q = t % DD;
                         double *sx = reinterpret_cast<double *>(gout + SPG_OUT_HEADER_WORDS + (size_t) e * slot + 1 + PW);
                         sx[q] = -src[t];
                     }

@@ -268,7 +268,8 @@ __global__ void __launch_bounds__(NT, LEAN ? 2 : ((NT >= 256) ? 1 : (NT == 128 ?
     double *s_logd = s_Lfac + nkmax * D * D;
     int *s_misc = reinterpret_cast<int *>(s_logd + nkmax);
 
-    for(int li = blockIdx.x; li < P.n_list; li += gridDim.x) {
+    const int n_list = P.n_list_dev ? *P.n_list_dev : P.n_list; // retry launches: the count is on the device
+    for(int li = blockIdx.x; li < n_list; li += gridDim.x) {
         const int b = P.list ? P.list[li] : li;
         const uint64_t *grec = P.records + P.rec_off[b];
         uint64_t *gout = P.out + P.out_off[b];

@@ -8,6 +8,13 @@
 
 namespace spg {
 
+// shared-memory plan of fast_kernel (spg_fast.cuh), in doubles; computed on the host by fast_plan<D>()
+struct FastPlan {
+    int NP, ntiles, chunk;
+    int off_pose, off_B, off_P, off_W, off_small, off_U, total;
+    int off_h00, off_hk0, off_y, off_jm; // phase A inside the union region U (after the record copy)
+};
+
 struct KernelParams {
     int32_t algorithm, topology;
     double chord_ratio;
@@ -33,6 +40,12 @@ struct KernelParams {
     double *gws;                  // spill variant: per-CTA slice holding the whole buffer plan (global memory)
     int64_t gws_stride;           // doubles per CTA
     unsigned long long *prof;     // optional: 16 per-stage cycle accumulators (thread 0 of every CTA)
+    // fast_kernel (spg_fast.cuh) appends the blankets it does not take to retry_list (atomic counter retry_count);
+    // the follow-up blanket_kernel launch reads its blanket count from n_list_dev (= retry_count) instead of n_list
+    int32_t *retry_list;
+    int32_t *retry_count;
+    const int32_t *n_list_dev;
+    FastPlan fast;
 };
 
 constexpr int ASM_CHUNK = 8; // edges linearised per pre-pass

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Per-stage cycle breakdown of blanket_kernel (clock64 accumulators, thread 0 of every CTA).
-usage: stage_profile.py [n ...]   (SE3, NFR tree, ring blankets)"""
+"""Per-stage cycle breakdown of the blanket kernels (clock64 accumulators, thread 0 of every CTA).
+usage: stage_profile.py [n ...]   (SE3, NFR tree, ring blankets). SPG_NO_FAST=1 profiles blanket_kernel."""
 import ctypes as C
 import os
 import sys
@@ -12,21 +12,27 @@ from sparsifyposegraph_b200 import capi, records as R, synth  # noqa: E402
 
 NAMES = ["load", "assembly", "schur", "cl_chol", "cl_inverse", "cl_blockchol", "cl_mi", "kruskal", "g_chol", "g_inverse",
          "new_jac", "sigma", "x_inv", "write", "-", "-"]
+FAST = ["load+poses", "assembly", "schur", "C sweep", "MI weights", "kruskal", "G sweep+guards", "closed form"] + ["-"] * 8
 sizes = [int(x) for x in sys.argv[1:]] or [5, 16]
 ctx = capi.Context(0)
 L = capi.lib()
 L.spg_stage_profile.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
 for n in sizes:
-    B = 4000 if n <= 19 else 8
+    B = int(os.environ.get("SPG_PROF_B", "8000")) if n <= 19 else 8
     blk = synth.make_blankets(n, B, dim=6, variant="ring", seed=n)
     out_off = R.out_offsets(6, 0, 0, 1.0, np.full(B, n - 1))
     ctx.remove_round(6, 0, capi.make_opts(0, 1), blk["records"], blk["rec_off"], out_off)
     L.spg_stage_profile(ctx.h, 1, None)
     ctx.remove_round(6, 0, capi.make_opts(0, 1), blk["records"], blk["rec_off"], out_off)
-    cyc = np.zeros(16, dtype=np.uint64)
+    retried = ctx.last_retry_count
+    cyc = np.zeros(32, dtype=np.uint64)
     L.spg_stage_profile(ctx.h, 0, cyc.ctypes.data_as(C.c_void_p))
-    tot = cyc.sum()
-    print(f"n={n}: {tot / B:.0f} cycles per blanket (thread 0 view), kernel {ctx.last_kernel_ms:.3f} ms for {B}")
-    for nm, c in zip(NAMES, cyc):
-        if c:
-            print(f"   {nm:14s} {c / B:10.0f} cyc  {100.0 * c / tot:5.1f}%")
+    print(f"n={n}: kernel {ctx.last_kernel_ms:.3f} ms for {B} blankets, {retried} handed to blanket_kernel")
+    for label, names, c16 in (("blanket_kernel", NAMES, cyc[:16]), ("fast_kernel", FAST, cyc[16:])):
+        tot = c16.sum()
+        if not tot:
+            continue
+        print(f"  {label}: {tot / B:.0f} cycles per blanket (thread 0 view)")
+        for nm, c in zip(names, c16):
+            if c:
+                print(f"   {nm:14s} {c / B:10.0f} cyc  {100.0 * c / tot:5.1f}%")
