@@ -58,8 +58,14 @@ spg_status launch_dim(spg_ctx *ctx, spg::KernelParams &kp) {
                           !(kp.flags & SPG_OPT_FORCE_EIGEN) && kp.max_nv >= 3 && tiles <= 256 && kp.retry_list && kp.retry_count;
     if(eligible) {
         spg_status st;
-        if(D == 6) st = tiles <= 32 ? spg_launch_fast_6_1(ctx, kp) : (tiles <= 128 ? spg_launch_fast_6_4(ctx, kp) : spg_launch_fast_6_8(ctx, kp));
-        else st = tiles <= 32 ? spg_launch_fast_3_1(ctx, kp) : spg_launch_fast_3_8(ctx, kp);
+        const int gsel = getenv("SPG_FAST_NOGROUPS") ? 32 : (tiles <= 8 ? 8 : (tiles <= 16 ? 16 : 32)); // sub-warp group width
+        if(D == 6) {
+            if(tiles <= 32) st = gsel == 8 ? spg_launch_fast_6_g8(ctx, kp) : (gsel == 16 ? spg_launch_fast_6_g16(ctx, kp) : spg_launch_fast_6_g32(ctx, kp));
+            else st = tiles <= 128 ? spg_launch_fast_6_c4(ctx, kp) : spg_launch_fast_6_c8(ctx, kp);
+        } else {
+            if(tiles <= 32) st = gsel == 8 ? spg_launch_fast_3_g8(ctx, kp) : (gsel == 16 ? spg_launch_fast_3_g16(ctx, kp) : spg_launch_fast_3_g32(ctx, kp));
+            else st = spg_launch_fast_3_c8(ctx, kp);
+        }
         if(st == SPG_OK) {
             spg::KernelParams kr = kp;
             kr.list = kp.retry_list;

@@ -76,8 +76,12 @@ spg_status spg_launch_6_256l(spg_ctx *, spg::KernelParams &);
 spg_status spg_launch_3_spill(spg_ctx *, spg::KernelParams &); // 256 threads, buffers in global memory
 spg_status spg_launch_6_spill(spg_ctx *, spg::KernelParams &);
 // fast_kernel<D, MAXW> (spg_fast.cuh): NFR tree rounds; SPG_ERR_UNSUPPORTED when the bucket does not fit
-spg_status spg_launch_fast_6_1(spg_ctx *, spg::KernelParams &);
-spg_status spg_launch_fast_6_4(spg_ctx *, spg::KernelParams &);
-spg_status spg_launch_fast_6_8(spg_ctx *, spg::KernelParams &);
-spg_status spg_launch_fast_3_1(spg_ctx *, spg::KernelParams &);
-spg_status spg_launch_fast_3_8(spg_ctx *, spg::KernelParams &);
+spg_status spg_launch_fast_6_g8(spg_ctx *, spg::KernelParams &);
+spg_status spg_launch_fast_6_g16(spg_ctx *, spg::KernelParams &);
+spg_status spg_launch_fast_6_g32(spg_ctx *, spg::KernelParams &);
+spg_status spg_launch_fast_6_c4(spg_ctx *, spg::KernelParams &);
+spg_status spg_launch_fast_6_c8(spg_ctx *, spg::KernelParams &);
+spg_status spg_launch_fast_3_g8(spg_ctx *, spg::KernelParams &);
+spg_status spg_launch_fast_3_g16(spg_ctx *, spg::KernelParams &);
+spg_status spg_launch_fast_3_g32(spg_ctx *, spg::KernelParams &);
+spg_status spg_launch_fast_3_c8(spg_ctx *, spg::KernelParams &);

@@ -49,6 +49,48 @@ __device__ __forceinline__ double fsum(double v, double *red) {
     }
 }
 
+// Thread group that owns one blanket. G = 8 / 16 / 32: a sub-warp group of G lanes of a one-warp CTA (32 / G
+// blankets per warp side by side, each group with its own control flow, shared-memory slot and masked warp
+// barriers); G = 0: the whole CTA (blockDim.x threads, __syncthreads).
+template <int G>
+struct Grp {
+    static __device__ __forceinline__ unsigned mask() {
+        if constexpr(G == 32 || G == 0) return 0xffffffffu;
+        else return ((1u << G) - 1u) << (G * ((threadIdx.x & 31) / G));
+    }
+    static __device__ __forceinline__ int tid() { return G ? (int) (threadIdx.x % (G ? G : 1)) : (int) threadIdx.x; }
+    static __device__ __forceinline__ int nt() { return G ? G : (int) blockDim.x; }
+    static __device__ __forceinline__ int slot() { return G ? (int) (threadIdx.x / (G ? G : 1)) : 0; }
+    static __device__ __forceinline__ int slots() { return G ? 32 / (G ? G : 1) : 1; }
+    static __device__ __forceinline__ void sync() {
+        if constexpr(G == 0) __syncthreads();
+        else __syncwarp(mask());
+    }
+    static __device__ __forceinline__ int any(int pred) {
+        if constexpr(G == 0) return __syncthreads_or(pred);
+        else return __any_sync(mask(), pred);
+    }
+    // sum in a fixed order; every thread of the group gets the result. red: >= 32 doubles (G = 0 only)
+    static __device__ __forceinline__ double sum(double v, double *red) {
+        if constexpr(G == 0) {
+#pragma unroll
+            for(int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+            __syncthreads();
+            if(l == 0) red[w] = v;
+            __syncthreads();
+            double s = 0;
+            for(int i = 0; i < nw; i++) s += red[i];
+            return s;
+        } else {
+            const unsigned m = mask();
+#pragma unroll
+            for(int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(m, v, o);
+            return v;
+        }
+    }
+};
+
 // ---- block sweep ---------------------------------------------------------------------------------------------
 // The symmetric sweep operator (B_jj = -1/d, B_ij = A_ij / d, B_il = A_il - A_ij A_jl / d; all pivots swept: -A^-1)
 // applied one VERTEX (D pivots) at a time on the D x D register blocks of the lower block triangle. Per vertex J:
@@ -91,83 +133,133 @@ __device__ __forceinline__ void invert_tile(double (&a)[D][D], double *Bout, dou
         for(int q = 0; q < D; q++) Bout[p * D + q] = -a[p][q];
 }
 
-// panel block of vertex v: X(x, p) = TRANSPOSED ? a[p][x] : a[x][p]. Publishes P[p][x] = X(x, p) and
-// W[q][x] = sum_p X(x, p) B[p][q], and replaces the block by the swept panel.
+// publish the panel block of vertex v for the next step: P[p][x] = X(x, p), X(x, p) = TRANSPOSED ? a[p][x] : a[x][p]
 template <int D, bool TRANSPOSED>
-__device__ __forceinline__ void panel_tile(double (&a)[D][D], const double *B, double *Pb, double *Wb) {
+__device__ __forceinline__ void publish_panel(const double (&a)[D][D], double *Pb) {
 #pragma unroll
     for(int p = 0; p < D; p++)
 #pragma unroll
         for(int x = 0; x < D; x++) Pb[p * D + x] = TRANSPOSED ? a[p][x] : a[x][p];
-#pragma unroll
-    for(int q = 0; q < D; q++) {
-        double bq[D];
-#pragma unroll
-        for(int p = 0; p < D; p++) bq[p] = B[q * D + p]; // B is symmetric
-#pragma unroll
-        for(int x = 0; x < D; x++) {
-            double w = 0;
-#pragma unroll
-            for(int p = 0; p < D; p++) w += (TRANSPOSED ? a[p][x] : a[x][p]) * bq[p];
-            Wb[q * D + x] = w;
-        }
-    }
-    // block (I, J) <- W_I ; block (J, L) <- B A_JL = W_L^T  (same thread wrote Wb: no barrier needed)
-#pragma unroll
-    for(int q = 0; q < D; q++)
-#pragma unroll
-        for(int x = 0; x < D; x++) {
-            if(TRANSPOSED) a[q][x] = Wb[q * D + x];
-            else a[x][q] = Wb[q * D + x];
-        }
 }
 
 // Sweeps the first nsv vertices of the symmetric matrix held in the blocks (active: vr < nsv): a <- -(A^-1) on the
 // leading block. Pivot j is left in s_piv[j]. Returns false (uniformly) on a non-positive pivot.
-template <int D, bool ONEWARP>
+// Per vertex J, two phases with one barrier each:
+//   1. one warp computes the swept panel W_v = P_v B for every other vertex v (P_v = A_vJ and B = A_JJ^-1 were
+//      published during the previous phase 2), two lanes per vertex;
+//   2. every block (I, L) off the pivot row / column: a -= W_I P_L^T (216 independent DFMAs, 16-byte operand
+//      loads); blocks on the pivot row / column take W; the blocks of vertex J + 1 publish the next panel and
+//      the thread of the next diagonal block inverts it in registers.
+template <int D, int G>
 __device__ __forceinline__ bool block_sweep(double (&a)[D][D], double *s_B, double *s_P, double *s_W, double *s_piv, int vr, int vc,
-                                            int nsv, bool active) {
+                                            int nsv, bool active, int nkmax) {
     constexpr int DD = D * D, PST = FastPad<D>::PST;
+    constexpr int HS = (D % 2 == 0) ? 2 : 1; // lanes per vertex in phase 1 (nsv <= 16 vertices: otherwise one lane each)
+    const int pstride = nkmax * PST;
+    const int tid = Grp<G>::tid();
+    constexpr int LW = G ? G : 32; // lanes of phase 1
     bool bad = false;
-    if(active && vr == 0 && vc == 0) invert_tile<D>(a, s_B, s_piv, bad);
-    fsync<ONEWARP>();
+    if(active) {
+        if(vc == 0 && vr > 0) publish_panel<D, false>(a, s_P + vr * PST);
+        if(vr == 0 && vc == 0) invert_tile<D>(a, s_B, s_piv, bad);
+    }
+    Grp<G>::sync();
+    const int hs = (HS * nsv <= LW) ? HS : 1;
 #pragma unroll 1
     for(int J = 0; J < nsv; J++) {
         const double *B = s_B + (J & 1) * DD;
-        if(active) {
-            if(vc == J && vr != J) panel_tile<D, false>(a, B, s_P + vr * PST, s_W + vr * PST);
-            else if(vr == J && vc != J) panel_tile<D, true>(a, B, s_P + vc * PST, s_W + vc * PST);
-        }
-        fsync<ONEWARP>();
-        if(active && vr != J && vc != J) {
-            const double *Wb = s_W + vr * PST, *Pb = s_P + vc * PST;
+        const double *Pc = s_P + (J & 1) * pstride;
+        double *Pn = s_P + ((J + 1) & 1) * pstride;
+        // ---- phase 1: W_v[q][x] = sum_p P_v[p][x] B[q][p] -----------------------------------------------------------
+        if(tid < LW) {
+#pragma unroll 1
+            for(int v0 = 0; v0 < nsv; v0 += LW / hs) {
+                const int v = v0 + tid / hs, h = tid % hs;
+                if(v < nsv && v != J) {
+                    const int q0 = h * (D / hs), q1 = q0 + D / hs;
+                    const double *Pv = Pc + v * PST;
+                    double *Wv = s_W + v * PST;
+                    if(hs == HS) {
+                        double bq[D / HS][D];
 #pragma unroll
-            for(int p = 0; p < D; p++) {
-                double w[D], q[D];
-                if constexpr(D % 2 == 0) { // 16-byte loads (all offsets are even numbers of doubles)
+                        for(int q = 0; q < D / HS; q++)
 #pragma unroll
-                    for(int r = 0; r < D; r += 2) {
-                        const double2 t = *reinterpret_cast<const double2 *>(Wb + p * D + r);
-                        w[r] = t.x; w[r + 1] = t.y;
-                        const double2 u = *reinterpret_cast<const double2 *>(Pb + p * D + r);
-                        q[r] = u.x; q[r + 1] = u.y;
+                            for(int p = 0; p < D; p++) bq[q][p] = B[(q0 + q) * D + p];
+#pragma unroll
+                        for(int x = 0; x < D; x++) {
+                            double px[D];
+#pragma unroll
+                            for(int p = 0; p < D; p++) px[p] = Pv[p * D + x];
+#pragma unroll
+                            for(int q = 0; q < D / HS; q++) {
+                                double w = 0;
+#pragma unroll
+                                for(int p = 0; p < D; p++) w += px[p] * bq[q][p];
+                                Wv[(q0 + q) * D + x] = w;
+                            }
+                        }
+                    } else {
+                        for(int q = q0; q < q1; q++)
+                            for(int x = 0; x < D; x++) {
+                                double w = 0;
+#pragma unroll
+                                for(int p = 0; p < D; p++) w += Pv[p * D + x] * B[q * D + p];
+                                Wv[q * D + x] = w;
+                            }
                     }
-                } else {
-#pragma unroll
-                    for(int r = 0; r < D; r++) w[r] = Wb[p * D + r];
-#pragma unroll
-                    for(int c = 0; c < D; c++) q[c] = Pb[p * D + c];
                 }
-#pragma unroll
-                for(int r = 0; r < D; r++)
-#pragma unroll
-                    for(int c = 0; c < D; c++) a[r][c] -= w[r] * q[c];
             }
-            if(vr == J + 1 && vc == J + 1 && J + 1 < nsv) invert_tile<D>(a, s_B + ((J + 1) & 1) * DD, s_piv + D * (J + 1), bad);
         }
-        fsync<ONEWARP>();
+        Grp<G>::sync();
+        // ---- phase 2 ---------------------------------------------------------------------------------------------
+        if(active && !(vr == J && vc == J)) {
+            if(vc == J) { // block (I, J) <- W_I
+                const double *Wb = s_W + vr * PST;
+#pragma unroll
+                for(int q = 0; q < D; q++)
+#pragma unroll
+                    for(int x = 0; x < D; x++) a[x][q] = Wb[q * D + x];
+            } else if(vr == J) { // block (J, L) <- B A_JL = W_L^T
+                const double *Wb = s_W + vc * PST;
+#pragma unroll
+                for(int q = 0; q < D; q++)
+#pragma unroll
+                    for(int x = 0; x < D; x++) a[q][x] = Wb[q * D + x];
+            } else {
+                const double *Wb = s_W + vr * PST, *Pb = Pc + vc * PST;
+#pragma unroll
+                for(int p = 0; p < D; p++) {
+                    double w[D], q[D];
+                    if constexpr(D % 2 == 0) { // 16-byte loads (all offsets are even numbers of doubles)
+#pragma unroll
+                        for(int r = 0; r < D; r += 2) {
+                            const double2 t = *reinterpret_cast<const double2 *>(Wb + p * D + r);
+                            w[r] = t.x; w[r + 1] = t.y;
+                            const double2 u = *reinterpret_cast<const double2 *>(Pb + p * D + r);
+                            q[r] = u.x; q[r + 1] = u.y;
+                        }
+                    } else {
+#pragma unroll
+                        for(int r = 0; r < D; r++) w[r] = Wb[p * D + r];
+#pragma unroll
+                        for(int c = 0; c < D; c++) q[c] = Pb[p * D + c];
+                    }
+#pragma unroll
+                    for(int r = 0; r < D; r++)
+#pragma unroll
+                        for(int c = 0; c < D; c++) a[r][c] -= w[r] * q[c];
+                }
+            }
+            if(J + 1 < nsv) {
+                if(vc == J + 1) {
+                    if(vr == J + 1) invert_tile<D>(a, s_B + ((J + 1) & 1) * DD, s_piv + D * (J + 1), bad);
+                    else publish_panel<D, false>(a, Pn + vr * PST);
+                } else if(vr == J + 1) publish_panel<D, true>(a, Pn + vc * PST);
+            }
+        }
+        Grp<G>::sync();
     }
-    return fsync_or<ONEWARP>(bad) == 0;
+    return Grp<G>::any(bad) == 0;
 }
 
 // Cholesky of the diagonal block C_vv = -a held in registers. Lout: column-major D x D, strictly-lower entries of
@@ -249,53 +341,57 @@ __device__ __forceinline__ double schur_logdet_tile(const double (&a)[D][D], con
     return ld_sum;
 }
 
-// shared-memory plan of fast_kernel (doubles; struct FastPlan in spg_plan.h), computed on the host
+// shared-memory plan of ONE blanket slot of fast_kernel (doubles; struct FastPlan in spg_plan.h), computed on the host
 template <int D>
 inline FastPlan fast_plan(int max_nv, int max_e, int max_rec_words, size_t smem_budget_bytes) {
     constexpr int PS = PoseStride<D>::value;
     constexpr int JW = 2 * D * D, SW = 4 * D * D, PST = FastPad<D>::PST;
     FastPlan p;
     const int nk = max_nv > 1 ? max_nv - 1 : 1, kmax = D * nk, pairs = nk * (nk - 1) / 2;
+    const int me = max_e < 1 ? 1 : max_e;
     p.NP = kmax;
     p.ntiles = nk * (nk + 1) / 2;
     int o = 0;
     p.off_pose = o;  o += max_nv * PS;
-    p.off_B = o;     o += 2 * D * D;
-    p.off_P = o;     o += nk * PST;
-    p.off_W = o;     o += nk * PST;
     p.off_small = o;
-    // wt[pairs] heapw[pairs] heapab[pairs](int) tree[2 pairs + 2](int) uf[nk](int) ev[max_e](int) Lfac[nk D D] Cd[nk D D]
-    // logd[nk] cs[kmax] piv[kmax] red[34] misc[16](int)
-    o += 2 * pairs + (pairs + 1) / 2 + (pairs + 1) + (nk + 2) / 2 + (max_e + 2) / 2 + 2 * nk * D * D + nk + 2 * kmax + 34 + 8;
+    // wt[pairs] heapw[pairs] heapab[pairs](int) tree[2 pairs + 2](int) uf[nk](int) ev[max_e](int) star[5 nk](int)
+    // Lfac[nk D D] Cd[nk D D] logd[nk] cs[kmax] piv[kmax] red[34] misc[16](int)
+    o += 2 * pairs + (pairs + 1) / 2 + (pairs + 1) + (nk + 2) / 2 + (me + 2) / 2 + (5 * nk + 2) / 2 + 2 * nk * D * D + nk + 2 * kmax + 34 + 8;
     o = (o + 1) & ~1;
     p.off_U = o;
-    // union region. A (assembly, Schur): record | H00 x2 | H_k0 | Y | J, M of a chunk of edges.
-    // B (Schur .. anchored sweep): the Lambda_t blocks, [element][tile]. C (closed form): Jn | Sg | Tm | Bk.
+    // union region.
+    //   A (assembly, Schur): record | H00 x2 | H_k0 | Y | J, M of a chunk of edges
+    //   B (Schur .. anchored sweep): the Lambda_t blocks [element][tile] | B x2 | P x2 | W   (block sweep panels)
+    //   C (closed form): Jn | Sg | Tm | Bk
     const int rec = (max_rec_words + 1) & ~1;
     const int h0 = 2 * D * D + 2 * D * kmax;
-    const int B = p.ntiles * D * D;
+    const int tb = (p.ntiles * D * D + 1) & ~1;
+    const int B = tb + 2 * D * D + 3 * nk * PST;
     const int C = (nk > 1 ? nk - 1 : 1) * (2 * JW + SW + D * D);
-    const int emin = max_e < 1 ? 1 : (max_e < 4 ? max_e : 4);
+    const int emin = me < 4 ? me : 4;
     int U = rec + h0 + emin * 2 * JW;
     if(B > U) U = B;
     if(C > U) U = C;
     // all edges in one assembly pass when that still leaves room for the resident CTAs the registers allow
-    const int Ufull = rec + h0 + (max_e < 1 ? 1 : max_e) * 2 * JW;
+    const int Ufull = rec + h0 + me * 2 * JW;
     if(Ufull > U && (size_t) (p.off_U + Ufull) * sizeof(double) <= smem_budget_bytes) U = Ufull;
     p.chunk = (U - rec - h0) / (2 * JW);
-    if(p.chunk > max_e) p.chunk = max_e;
+    if(p.chunk > me) p.chunk = me;
     if(p.chunk < 1) p.chunk = 1;
     p.off_h00 = p.off_U + rec;
     p.off_hk0 = p.off_h00 + 2 * D * D;
     p.off_y = p.off_hk0 + D * kmax;
     p.off_jm = p.off_y + D * kmax;
-    p.total = p.off_U + U;
+    p.off_B = p.off_U + tb;
+    p.off_P = p.off_B + 2 * D * D;
+    p.off_W = p.off_P + 2 * nk * PST;
+    p.total = (p.off_U + U + 1) & ~1;
     return p;
 }
-// threads of a CTA: one per block of the lower block triangle, rounded up to warps
-__host__ __device__ inline int fast_threads(int max_nv) {
+// threads that work on one blanket: one per block of the lower block triangle
+__host__ __device__ inline int fast_tiles(int max_nv) {
     const int nk = max_nv > 1 ? max_nv - 1 : 1;
-    return ((nk * (nk + 1) / 2 + 31) / 32) * 32;
+    return nk * (nk + 1) / 2;
 }
 
 #define SPG_FT(i)                                                                                    \
@@ -307,33 +403,32 @@ __host__ __device__ inline int fast_threads(int max_nv) {
         }                                                                                            \
     } while(0)
 
-// MAXW: warps per CTA at most (1: one warp per blanket, __syncwarp() only). blockDim.x = fast_threads(max_nv).
-template <int D, int MAXW>
+// G: see Grp. MAXW: warps per CTA at most (G = 0), 1 otherwise.
+template <int D, int G, int MAXW>
 __global__ void __launch_bounds__(32 * MAXW, MAXW == 1 ? (D == 6 ? 12 : 16) : (MAXW <= 4 ? 3 : (D == 6 ? 1 : 2))) fast_kernel(const KernelParams P) {
     extern __shared__ __align__(16) double fast_smem[];
-    double *smem = fast_smem;
-    constexpr bool ONEWARP = (MAXW == 1);
+    using GS = Grp<G>;
     constexpr int PS = PoseStride<D>::value;
     constexpr int PW = (D == 6) ? 7 : 3;
     constexpr int JW = D * 2 * D;
     constexpr int SW = 4 * D * D;
     constexpr int DD = D * D;
-    const int tid = threadIdx.x, NT = blockDim.x;
+    const int tid = GS::tid(), NT = GS::nt();
 
     const FastPlan &pl = P.fast; // computed on the host (fast_plan): constant-bank loads
+    double *smem = fast_smem + (size_t) GS::slot() * pl.total;
     const int NP = pl.NP;
     double *s_pose = smem + pl.off_pose;
-    double *s_B = smem + pl.off_B;
-    double *s_P = smem + pl.off_P;
-    double *s_W = smem + pl.off_W;
     const int nkmax = P.max_nv > 1 ? P.max_nv - 1 : 1, kmaxb = pl.NP, pairs_max = nkmax * (nkmax - 1) / 2;
+    const int me = P.max_e < 1 ? 1 : P.max_e;
     double *s_wt = smem + pl.off_small;
     double *s_heapw = s_wt + pairs_max;
     int *s_heapab = reinterpret_cast<int *>(s_heapw + pairs_max);
     int *s_tree = reinterpret_cast<int *>(s_heapw + pairs_max + (pairs_max + 1) / 2);
     int *s_uf = reinterpret_cast<int *>(s_heapw + pairs_max + (pairs_max + 1) / 2 + (pairs_max + 1));
     int *s_ev = reinterpret_cast<int *>(s_heapw + pairs_max + (pairs_max + 1) / 2 + (pairs_max + 1) + (nkmax + 2) / 2);
-    double *s_Lfac = s_heapw + pairs_max + (pairs_max + 1) / 2 + (pairs_max + 1) + (nkmax + 2) / 2 + (P.max_e + 2) / 2;
+    int *s_star = reinterpret_cast<int *>(s_heapw + pairs_max + (pairs_max + 1) / 2 + (pairs_max + 1) + (nkmax + 2) / 2 + (me + 2) / 2);
+    double *s_Lfac = s_heapw + pairs_max + (pairs_max + 1) / 2 + (pairs_max + 1) + (nkmax + 2) / 2 + (me + 2) / 2 + (5 * nkmax + 2) / 2;
     double *s_Cd = s_Lfac + nkmax * DD;
     double *s_logd = s_Cd + nkmax * DD;
     double *s_cs = s_logd + nkmax;
@@ -347,9 +442,12 @@ __global__ void __launch_bounds__(32 * MAXW, MAXW == 1 ? (D == 6 ? 12 : 16) : (M
     double *s_y = smem + pl.off_y;     // [D][NP]: H_k0 H_00^-1
     double *JM = smem + pl.off_jm;     // per edge of a chunk: J = [Ji Jj], M = Omega J
     double *Tb = U;                    // Lambda_t blocks, [element][tile]
+    double *s_B = smem + pl.off_B;
+    double *s_P = smem + pl.off_P;
+    double *s_W = smem + pl.off_W;
     const int tstride = pl.ntiles;
 
-    for(int li = blockIdx.x; li < P.n_list; li += gridDim.x) {
+    for(int li = blockIdx.x * GS::slots() + GS::slot(); li < P.n_list; li += gridDim.x * GS::slots()) {
         const int b = P.list ? P.list[li] : li;
         const uint64_t *grec = P.records + P.rec_off[b];
         uint64_t *gout = P.out + P.out_off[b];
@@ -358,7 +456,7 @@ __global__ void __launch_bounds__(32 * MAXW, MAXW == 1 ? (D == 6 ? 12 : 16) : (M
         const int nv = gh[0], nrem = gh[1], ne = gh[2], rdim = gh[3], rec_words = gh[4];
         const int nk = nv - nrem, k = D * nk;
 
-        fsync<ONEWARP>(); // the shared buffers of the previous blanket are dead
+        GS::sync(); // the shared buffers of the previous blanket are dead
         bool refuse = (rdim != D || nv > P.max_nv || ne > P.max_e || rec_words > P.max_rec_words || nrem != 1 || nk < 2 || ne < 1);
         for(int t = tid; t < out_words; t += NT) gout[t] = 0;
         long long t_last = clock64();
@@ -366,7 +464,7 @@ __global__ void __launch_bounds__(32 * MAXW, MAXW == 1 ? (D == 6 ? 12 : 16) : (M
             for(int t = tid; t < rec_words; t += NT) s_rec[t] = grec[t];
             if(tid == 0) { s_misc[0] = 0; s_misc[3] = 0; }
         }
-        fsync<ONEWARP>();
+        GS::sync();
         const double *r_pose = reinterpret_cast<const double *>(s_rec + spgr_poses_off(nv));
         const int32_t *r_etab = reinterpret_cast<const int32_t *>(s_rec + spgr_edgetab_off(D, nv));
         if(!refuse) {
@@ -378,7 +476,7 @@ __global__ void __launch_bounds__(32 * MAXW, MAXW == 1 ? (D == 6 ? 12 : 16) : (M
                 badedge |= (eh[0] != SPG_EDGE_POSE) || (eh[1] != 2) || (vi[0] == vi[1]);
                 s_ev[e] = pk(vi[0], vi[1]);
             }
-            refuse = fsync_or<ONEWARP>(badedge) != 0;
+            refuse = GS::any(badedge) != 0;
         }
         int n_out = 0;
         double out_kld = 0;
@@ -400,40 +498,64 @@ __global__ void __launch_bounds__(32 * MAXW, MAXW == 1 ? (D == 6 ? 12 : 16) : (M
 #pragma unroll
                 for(int c = 0; c < D; c++) a[r][c] = 0.0;
 
-            // ---- S0: poses ---------------------------------------------------------------------------------
+            // ---- S0: poses; per kept vertex the edges to the removed vertex, in edge order (at most 4 parallel
+            // edges, else blanket_kernel) ----------------------------------------------------------------------------
             for(int v = tid; v < nv; v += NT) {
                 if constexpr(D == 6) se3_from_flat(r_pose + PW * v, s_pose + PS * v);
                 else se2_from_flat(r_pose + PW * v, s_pose + PS * v);
             }
+            int manystar = 0;
+            for(int v = tid; v < nk; v += NT) {
+                int cnt = 0;
+                for(int e = 0; e < ne; e++) {
+                    const int vab = s_ev[e], va = pk_a(vab), vb = pk_b(vab);
+                    if((va == 0 && vb == v + 1) || (vb == 0 && va == v + 1)) {
+                        if(cnt < 4) s_star[5 * v + 1 + cnt] = e;
+                        cnt++;
+                    }
+                }
+                s_star[5 * v] = cnt;
+                manystar |= (cnt > 4);
+            }
             for(int t = tid; t < DD + 2 * D * NP; t += NT) s_h00[DD + t] = 0.0; // second H00 buffer, H_k0, Y
-            fsync<ONEWARP>();
+            if(GS::any(manystar)) refuse = true;
             SPG_FT(0);
-            // ---- S1: assembly. Per chunk of edges: J = [Ji Jj] and M = Omega J in shared memory, then every
-            // block gathers the edges of its vertex pair in edge order (fixed summation order), and D (k + D)
-            // threads gather H_00 and H_k0. -----------------------------------------------------------------------
+            // ---- S1: assembly. Per chunk of edges (normally all of them): one thread per edge writes J = [Ji Jj] and
+            // M = Omega J to shared memory, then every block gathers the edges of its vertex pair in edge order
+            // (fixed summation order), and D (k + D) threads gather H_00 and H_k0 from the edges to the removed vertex.
             const int chunk = pl.chunk;
-            for(int e0 = 0; e0 < ne; e0 += chunk) {
+            for(int e0 = 0; e0 < ne && !refuse; e0 += chunk) {
                 const int ce = min(chunk, ne - e0);
                 for(int e = tid; e < ce; e += NT) {
                     const uint64_t *ew = s_rec + r_etab[e0 + e];
                     const int32_t *vi = reinterpret_cast<const int32_t *>(ew + 2);
                     const double *pm = reinterpret_cast<const double *>(ew + 3);
+                    const double *Om = pm + PW;
+                    double *J = JM + (size_t) e * 2 * JW;
                     double Z[PS];
                     if constexpr(D == 6) se3_from_flat(pm, Z);
                     else se2_from_flat(pm, Z);
-                    edge_jacobians<D>(Z, s_pose + PS * vi[0], s_pose + PS * vi[1], JM + (size_t) e * 2 * JW);
-                }
-                fsync<ONEWARP>();
-                for(int t = tid; t < ce * JW; t += NT) { // M = Omega J
-                    const int e = t / JW, q = t % JW, r = q % D, c = q / D;
-                    const double *Om = reinterpret_cast<const double *>(s_rec + r_etab[e0 + e] + 3) + PW;
-                    const double *J = JM + (size_t) e * 2 * JW;
-                    double s = 0;
+                    edge_jacobians<D>(Z, s_pose + PS * vi[0], s_pose + PS * vi[1], J);
+                    double om[D][D]; // Omega (symmetric), in registers for the 2 D columns of M = Omega J
 #pragma unroll
-                    for(int p = 0; p < D; p++) s += Om[r + p * D] * J[p + c * D];
-                    JM[(size_t) e * 2 * JW + JW + q] = s;
+                    for(int r = 0; r < D; r++)
+#pragma unroll
+                        for(int p2 = 0; p2 < D; p2++) om[r][p2] = Om[r + p2 * D];
+#pragma unroll 1
+                    for(int c = 0; c < 2 * D; c++) {
+                        double jc[D];
+#pragma unroll
+                        for(int p2 = 0; p2 < D; p2++) jc[p2] = J[p2 + c * D];
+#pragma unroll
+                        for(int r = 0; r < D; r++) {
+                            double sm = 0;
+#pragma unroll
+                            for(int p2 = 0; p2 < D; p2++) sm += om[r][p2] * jc[p2];
+                            J[JW + r + c * D] = sm;
+                        }
+                    }
                 }
-                fsync<ONEWARP>();
+                GS::sync();
                 if(has_tile) {
                     const int lr = vr + 1, lc = vc + 1; // local vertex indices (the removed vertex is 0)
                     for(int e = 0; e < ce; e++) {
@@ -458,45 +580,57 @@ __global__ void __launch_bounds__(32 * MAXW, MAXW == 1 ? (D == 6 ? 12 : 16) : (M
                         }
                     }
                 }
-                // [H_k0; H_00]: entry (i, p), i in [0, k + D) (kept dims, then the removed vertex's), p in [0, D)
-                for(int t = tid; t < (k + D) * D; t += NT) {
-                    const int i = t % (k + D), p = t / (k + D);
-                    const int lv = (i < k) ? i / D + 1 : 0, di = (i < k) ? i % D : i - k;
+                // H_k0: entry (i, p), i in [0, k): the edges between the removed vertex and kept vertex i / D
+                for(int t = tid; t < k * D; t += NT) {
+                    const int i = t % k, p = t / k, v = i / D, di = i % D;
+                    const int cnt = s_star[5 * v];
+                    double s = 0;
+                    for(int q = 0; q < cnt; q++) {
+                        const int e = s_star[5 * v + 1 + q] - e0;
+                        if(e < 0 || e >= ce) continue;
+                        const int sv = (pk_a(s_ev[e0 + e]) == 0) ? 1 : 0; // side of the kept vertex
+                        const double *Jv = JM + (size_t) e * 2 * JW + (sv * D + di) * D;
+                        const double *M0 = JM + (size_t) e * 2 * JW + JW + ((1 - sv) * D + p) * D;
+#pragma unroll
+                        for(int q2 = 0; q2 < D; q2++) s += Jv[q2] * M0[q2];
+                    }
+                    s_hk0[p * NP + i] += s;
+                }
+                // H_00: every edge of the removed vertex
+                for(int t = tid; t < DD; t += NT) {
+                    const int di = t % D, p = t / D;
                     double s = 0;
                     for(int e = 0; e < ce; e++) {
                         const int vab = s_ev[e0 + e];
-                        const int va = pk_a(vab), vb = pk_b(vab);
-                        int sv, s0;
-                        if(va == lv) sv = 0; else if(vb == lv) sv = 1; else continue;
-                        if(va == 0) s0 = 0; else if(vb == 0) s0 = 1; else continue;
-                        const double *Jv = JM + (size_t) e * 2 * JW + (sv * D + di) * D;
+                        int s0;
+                        if(pk_a(vab) == 0) s0 = 0; else if(pk_b(vab) == 0) s0 = 1; else continue;
+                        const double *J0 = JM + (size_t) e * 2 * JW + (s0 * D + di) * D;
                         const double *M0 = JM + (size_t) e * 2 * JW + JW + (s0 * D + p) * D;
 #pragma unroll
-                        for(int q = 0; q < D; q++) s += Jv[q] * M0[q];
+                        for(int q2 = 0; q2 < D; q2++) s += J0[q2] * M0[q2];
                     }
-                    if(i < k) s_hk0[p * NP + i] += s;
-                    else s_h00[DD + di + p * D] += s;
+                    s_h00[DD + di + p * D] += s;
                 }
-                fsync<ONEWARP>();
+                GS::sync();
             }
             SPG_FT(1);
             // ---- S2: Schur complement Lambda_t = H_kk - H_k0 H_00^-1 H_0k (vertex_remover.cpp:443-449) ---------
             // H_00^-1 by D symmetric Gauss-Jordan steps (a pivot <= 0 is LLT's failure)
-            {
+            if(!refuse) {
                 double *src = s_h00 + DD, *dst = s_h00;
                 for(int s0 = 0; s0 < D; s0++) {
                     for(int t = tid; t < DD; t += NT) {
                         const int i = t % D, j = t / D;
                         const double d = src[s0 + s0 * D];
                         if(!(d > 0)) s_misc[0] = 1;
-                        const double inv = 1.0 / d, bis = src[i + s0 * D], bsj = src[s0 + j * D];
+                        const double inv = fast_rcp(d), bis = src[i + s0 * D], bsj = src[s0 + j * D];
                         double v = src[i + j * D] - bis * bsj * inv;
                         if(j == s0) v = bis * inv;
                         if(i == s0) v = bsj * inv;
                         if(i == s0 && j == s0) v = -inv;
                         dst[t] = v;
                     }
-                    fsync<ONEWARP>();
+                    GS::sync();
                     double *tmp = src; src = dst; dst = tmp;
                 }
                 const double *Hinv = src; // -H_00^-1
@@ -507,9 +641,9 @@ __global__ void __launch_bounds__(32 * MAXW, MAXW == 1 ? (D == 6 ? 12 : 16) : (M
                     for(int q = 0; q < D; q++) s -= s_hk0[q * NP + i] * Hinv[q + p * D];
                     s_y[p * NP + i] = s;
                 }
-                fsync<ONEWARP>();
+                GS::sync();
+                if(s_misc[0]) refuse = true; // uniform (read after the barrier)
             }
-            if(s_misc[0]) refuse = true; // uniform (read after the barrier)
             int bigdiag = 0;
             if(!refuse) {
                 if(has_tile) {
@@ -547,7 +681,7 @@ __global__ void __launch_bounds__(32 * MAXW, MAXW == 1 ? (D == 6 ? 12 : 16) : (M
                             }
                     }
                 }
-                fsync<ONEWARP>(); // Y, H_k0 and the record are dead: the union region now holds the Lambda_t blocks
+                GS::sync(); // Y, H_k0 and the record are dead: the union region now holds the Lambda_t blocks and the panels
                 if(has_tile) {
 #pragma unroll
                     for(int r = 0; r < D; r++)
@@ -569,7 +703,7 @@ __global__ void __launch_bounds__(32 * MAXW, MAXW == 1 ? (D == 6 ? 12 : 16) : (M
 #pragma unroll
                         for(int r = 0; r < D; r++) a[r][r] += 1.0;
                     }
-                    if(!block_sweep<D, ONEWARP>(a, s_B, s_P, s_W, s_piv, vr, vc, nk, has_tile)) refuse = true;
+                    if(!block_sweep<D, G>(a, s_B, s_P, s_W, s_piv, vr, vc, nk, has_tile, nkmax)) refuse = true;
                     if(!refuse) {
                         SPG_FT(3);
                         if(diag) {
@@ -577,14 +711,14 @@ __global__ void __launch_bounds__(32 * MAXW, MAXW == 1 ? (D == 6 ? 12 : 16) : (M
                             s_logd[vr] = chol_tile<D>(a, s_Lfac + vr * DD, s_Cd + vr * DD, ok);
                             if(!ok) s_misc[0] = 1;
                         }
-                        fsync<ONEWARP>();
+                        GS::sync();
                         // weight(i,j) = logdet C_jj - logdet (C_jj - C_ji C_ii^-1 C_ij)   (:169-183)
                         if(has_tile && !diag) {
                             const int i = vc, j = vr;
                             const int t = i * nk - (i * (i + 1)) / 2 + (j - i - 1);
                             s_wt[t] = s_logd[j] - schur_logdet_tile<D>(a, s_Lfac + i * DD, s_Cd + j * DD);
                         }
-                        fsync<ONEWARP>();
+                        GS::sync();
                         if(s_misc[0]) refuse = true;
                     }
                     if(!refuse) {
@@ -593,7 +727,7 @@ __global__ void __launch_bounds__(32 * MAXW, MAXW == 1 ? (D == 6 ? 12 : 16) : (M
                             const int cap = (int) (P.dbg_weights_off[b + 1] - P.dbg_weights_off[b]);
                             if(P.flags & SPG_OPT_DBG_WEIGHTS_IN) {
                                 for(int t = tid; t < all && t < cap; t += NT) s_wt[t] = g[t];
-                                fsync<ONEWARP>();
+                                GS::sync();
                             } else {
                                 for(int t = tid; t < cap; t += NT) g[t] = t < all ? s_wt[t] : 0.0;
                             }
@@ -617,7 +751,7 @@ __global__ void __launch_bounds__(32 * MAXW, MAXW == 1 ? (D == 6 ? 12 : 16) : (M
                                 s_sorted[rank] = pk(i, i + 1 + rem);
                             }
                         }
-                        fsync<ONEWARP>();
+                        GS::sync();
                         if(s_misc[3]) out_flags |= 128;
                         if(tid == 0) {
                             for(int v = 0; v < nk; v++) s_uf[v] = v;
@@ -651,7 +785,7 @@ __global__ void __launch_bounds__(32 * MAXW, MAXW == 1 ? (D == 6 ? 12 : 16) : (M
                                 }
                             }
                         }
-                        fsync<ONEWARP>();
+                        GS::sync();
                     }
                 }
             }
@@ -661,7 +795,7 @@ __global__ void __launch_bounds__(32 * MAXW, MAXW == 1 ? (D == 6 ? 12 : 16) : (M
             double glog = 0;
             if(!refuse) {
                 // guard (ii): every diagonal entry of Lambda_t below 1e8
-                if(fsync_or<ONEWARP>(bigdiag)) refuse = true;
+                if(GS::any(bigdiag)) refuse = true;
             }
             if(!refuse) {
                 // G = Lambda_rr^-1 (last kept vertex anchored): reload the blocks and sweep the first nk - 1 vertices
@@ -672,7 +806,7 @@ __global__ void __launch_bounds__(32 * MAXW, MAXW == 1 ? (D == 6 ? 12 : 16) : (M
 #pragma unroll
                         for(int c = 0; c < D; c++) a[r][c] = act ? Tb[(r + c * D) * tstride + tid] : 0.0;
                 }
-                if(!block_sweep<D, ONEWARP>(a, s_B, s_P, s_W, s_piv, vr, vc, nk - 1, act)) refuse = true;
+                if(!block_sweep<D, G>(a, s_B, s_P, s_W, s_piv, vr, vc, nk - 1, act, nkmax)) refuse = true;
                 if(!refuse) {
                     // guard (i): ||G||_F <= 1e5; log-determinant of Lambda_rr from the pivots
                     double fp = 0;
@@ -683,7 +817,7 @@ __global__ void __launch_bounds__(32 * MAXW, MAXW == 1 ? (D == 6 ? 12 : 16) : (M
 #pragma unroll
                             for(int c = 0; c < D; c++) fp += w * a[r][c] * a[r][c];
                     }
-                    const double frob2 = fsum<ONEWARP>(fp, s_red);
+                    const double frob2 = GS::sum(fp, s_red);
                     if(!(frob2 <= 1e10)) refuse = true;
                     for(int t = tid; t < kk; t += NT) glog += log(s_piv[t]);
                 }
@@ -691,7 +825,8 @@ __global__ void __launch_bounds__(32 * MAXW, MAXW == 1 ? (D == 6 ? 12 : 16) : (M
             SPG_FT(6);
             if(!refuse) {
                 // new-edge Jacobians at zero error (vertex_remover.cpp:466-498), Sigma blocks from G, X_e = (J Sigma J^T)^-1
-                double *Jn = U;                           // n_out * JW    (the Lambda_t blocks are dead)
+                GS::sync();                               // the Lambda_t blocks and the panels are dead
+                double *Jn = U;                           // n_out * JW
                 double *Sg = Jn + (size_t) n_out * JW;    // n_out * SW
                 double *Tm = Sg + (size_t) n_out * SW;    // n_out * JW
                 double *Bk = Tm + (size_t) n_out * JW;    // n_out * D*D
@@ -736,7 +871,7 @@ __global__ void __launch_bounds__(32 * MAXW, MAXW == 1 ? (D == 6 ? 12 : 16) : (M
                         }
                     }
                 }
-                fsync<ONEWARP>();
+                GS::sync();
                 for(int t = tid; t < n_out * JW; t += NT) { // Tm = J Sigma_e
                     const int e = t / JW, q = t % JW, rr = q % D, j = q / D;
                     const double *J = Jn + (size_t) e * JW;
@@ -746,7 +881,7 @@ __global__ void __launch_bounds__(32 * MAXW, MAXW == 1 ? (D == 6 ? 12 : 16) : (M
                     for(int i = 0; i < 2 * D; i++) acc += J[rr + i * D] * S2[i + j * 2 * D];
                     Tm[t] = acc;
                 }
-                fsync<ONEWARP>();
+                GS::sync();
                 for(int t = tid; t < n_out * DD; t += NT) { // block = Tm J^T, symmetrised (logdet_function.cpp:249-270)
                     const int e = t / DD, q = t % DD, rr = q % D, cc = q / D;
                     if(rr >= cc) {
@@ -763,7 +898,7 @@ __global__ void __launch_bounds__(32 * MAXW, MAXW == 1 ? (D == 6 ? 12 : 16) : (M
                         Bk[(size_t) e * DD + cc + rr * D] = v;
                     }
                 }
-                fsync<ONEWARP>();
+                GS::sync();
                 double *src = Bk, *dst = Bk2;
                 for(int s0 = 0; s0 < D; s0++) { // X_e = block^-1 (:273-274), all blocks together, D Gauss-Jordan steps
                     for(int t = tid; t < n_out * DD; t += NT) {
@@ -772,14 +907,14 @@ __global__ void __launch_bounds__(32 * MAXW, MAXW == 1 ? (D == 6 ? 12 : 16) : (M
                         const double d = B[s0 + s0 * D];
                         if(!(d > 0)) s_misc[0] = 1;
                         if(i == s0 && j == s0) s_cs[e * D + s0] = d;
-                        const double inv = 1.0 / d, bis = B[i + s0 * D], bsj = B[s0 + j * D];
+                        const double inv = fast_rcp(d), bis = B[i + s0 * D], bsj = B[s0 + j * D];
                         double v = B[i + j * D] - bis * bsj * inv;
                         if(j == s0) v = bis * inv;
                         if(i == s0) v = bsj * inv;
                         if(i == s0 && j == s0) v = -inv;
                         dst[t] = v;
                     }
-                    fsync<ONEWARP>();
+                    GS::sync();
                     double *tmp = src; src = dst; dst = tmp;
                 }
                 if(s_misc[0]) refuse = true;
@@ -792,12 +927,12 @@ __global__ void __launch_bounds__(32 * MAXW, MAXW == 1 ? (D == 6 ? 12 : 16) : (M
                     // projected KLD at the closed form = 1/2 [logdet Lambda_rr - sum_e logdet X_e] (see blanket_kernel)
                     double lp = glog;
                     for(int t = tid; t < n_out * D; t += NT) lp += log(s_cs[t]);
-                    out_kld = 0.5 * fsum<ONEWARP>(lp, s_red);
+                    out_kld = 0.5 * GS::sum(lp, s_red);
                 }
             }
             SPG_FT(7);
         }
-        fsync<ONEWARP>();
+        GS::sync();
         if(tid == 0) {
             int32_t *oh = reinterpret_cast<int32_t *>(gout);
             if(refuse) {
