@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libspg_b200.so")
+LIB_PATH = os.environ.get("SPG_LIB") or os.path.join(_HERE, "libspg_b200.so")
 
 
 class SparsityOptions(C.Structure):
