@@ -6,13 +6,17 @@ the batched Markov-blanket sweep — synthetic SE3 blankets with n in {2,3,4,5,6
 (H 12x12 ... 96x96 fp64), `--blankets` (default 1e5) blankets per size, star+ring edge pattern,
 NFR with Chow-Liu Tree topology. One "step" = one pass of the node-removal hot path (assembly,
 Schur complement, Chow-Liu MI + spanning tree, NFR closed-form information fit) over the whole
-sweep. Every rank of a multi-GPU run owns its own sweep (weak scaling, no data-path collective).
+sweep. A multi-GPU run partitions the ONE sweep over the ranks (strong scaling: per size, rank r runs the r-th
+contiguous slice) and gathers the substitute-edge records of every slice over NCCL/NVLink into every rank's
+output buffer inside every timed step (spg_remove_round_sharded_device; the gather of one size overlaps the
+kernels of the next).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--blankets B] [--impl reference]
 
 `value`  : device-resident inputs, CUDA events on the library's stream, max over ranks.
-`e2e`    : the same sweep through the host-buffer C-ABI call spg_remove_round (pinned host
-           records in, H2D + kernels + D2H inside the timed region).
+`e2e`    : the same sweep through the host-buffer C-ABI call spg_remove_round (N = 1) /
+           spg_remove_round_sharded (N > 1, outputs gathered to rank 0, which holds the graph):
+           pinned host records in, H2D + kernels (+ gather) + D2H inside the timed region.
 `--impl reference` times the CPU restatement of the reference path (oracle/) on all host threads
 over a bounded sample of the same sweep (the reference itself cannot be built offline).
 """
@@ -44,13 +48,15 @@ def workload_config(blankets, n_gpus):
                         f"star+ring edges, NFR Chow-Liu tree (closed-form fit)",
             "blankets_per_size": blankets, "sizes": list(SIZES), "topology": "tree", "algorithm": "nfr",
             "lin_point": "global", "l2": "inputs larger than L2 (126 MB) at the default size; each blanket is read once",
-            "parallelism": f"blankets sharded over {n_gpus} GPU(s), no data-path collective"}
+            "parallelism": (f"one sweep partitioned over {n_gpus} GPU(s) (strong scaling); per step every rank's substitute-edge "
+                            f"records are gathered over NCCL/NVLink into every rank's output buffer, inside the timed region"
+                            if n_gpus > 1 else "1 GPU")}
 
 
 def make_sweep(blankets, rank):
     sweep = []
     for n in SIZES:
-        blk = synth.make_blankets(n, blankets, dim=6, variant=VARIANT, seed=synth.SEED + n + 1000 * rank)
+        blk = synth.make_blankets(n, blankets, dim=6, variant=VARIANT, seed=synth.SEED + n)  # the same sweep on every rank
         nk = np.full(blankets, n - 1, dtype=np.int64)
         blk["out_off"] = R.out_offsets(6, R.ALG_NFR, R.TOPO_TREE, 1.0, nk)
         sweep.append(blk)
@@ -133,7 +139,7 @@ def run_reference(args, rank, world):
     val = total / dt
     sample = f"first {S} blankets of each of the {len(SIZES)} sizes per step (same generator and mix as the GPU arm)"
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args.blankets, args.gpus),
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                              "note": "CPU restatement of the reference path (oracle/); the reference itself needs "
@@ -193,10 +199,13 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the node-removal path has no CPU fallback")
     torch.cuda.set_device(local_rank)
-    os.environ["NCCL_DEBUG"] = os.environ.get("SPG_NCCL_DEBUG", "WARN")
+    os.environ["NCCL_DEBUG"] = os.environ.get("SPG_NCCL_DEBUG", "INFO" if world > 1 else "WARN")  # INFO: the driver counts ranks
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = capi.Context(local_rank)
+    if world > 1:
+        from sparsifyposegraph_b200 import distributed
+        distributed.init_comm(ctx, rank, world)  # the library's own NCCL communicator (spg_comm_init)
     stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local_rank))
     opts = capi.make_opts(R.TOPO_TREE, R.LIN_GLOBAL, 1.0, flags=2)  # SPG_OPT_POSE_EDGES_ONLY: the sweep has POSE edges only
 
@@ -237,10 +246,24 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # per size: rank r runs blankets [B r / N, B (r+1) / N) and every rank receives all slices (uniform blankets: equal
+    # counts are cost-balanced). Largest blankets first, so the gather left exposed at the end of a step is the smallest.
+    for d, blk in zip(dev, sweep):
+        d["bounds"] = np.array([d["B"] * r // world for r in range(world + 1)], dtype=np.int32)
+        d["wbounds"] = blk["out_off"][d["bounds"]].astype(np.int64)
+    order = sorted(dev, key=lambda d: -d["n"])
+
     def device_step():
-        for d in dev:
-            ctx.remove_round_device(6, R.ALG_NFR, opts, d["B"], d["rec"].data_ptr(), d["rec_off"].data_ptr(),
-                                    d["out_off"].data_ptr(), d["out"].data_ptr(), d["n"], d["E"])
+        for d in order:
+            if world == 1:
+                ctx.remove_round_device(6, R.ALG_NFR, opts, d["B"], d["rec"].data_ptr(), d["rec_off"].data_ptr(),
+                                        d["out_off"].data_ptr(), d["out"].data_ptr(), d["n"], d["E"])
+            else:
+                ctx.remove_round_sharded_device(6, R.ALG_NFR, opts, d["B"], d["rec"].data_ptr(), d["rec_off"].data_ptr(),
+                                                d["out_off"].data_ptr(), d["out"].data_ptr(), d["bounds"], d["wbounds"],
+                                                d["n"], d["E"], root=-1)
+        if world > 1:
+            ctx.comm_join()  # the compute stream waits for the step's gathers: the output buffers are complete (and reusable)
 
     # ---- FP64 peak (roofline denominator; MEASURED_PEAKS.json has no FP64 figure) --------------------
     fp64_peak = ctx.fp64_peak_tflops(5)
@@ -262,59 +285,84 @@ def main():
         for _ in range(args.steps):
             device_step()
         ev1.record()
-    ctx.sync()
+    ctx.sync()  # compute stream and the gather stream
     barrier()
-    dev_ms = ev0.elapsed_time(ev1)
+    dev_ms = ev0.elapsed_time(ev1)  # every step ends with comm_join: ev1 is behind the last gather too
     launches = ctx.launches - launches0
+    # every blanket of the whole sweep must be present and OK in THIS rank's output buffers (own slice from the
+    # kernels, the other slices through the gather): status == 0 and n_new_edges == n - 2
+    n_dev_ok = 0
+    for d, blk in zip(dev, sweep):
+        hdr = d["out"][torch.from_numpy(blk["out_off"][:-1]).cuda()].cpu().numpy().view(np.int32).reshape(-1, 2)
+        n_dev_ok += int(((hdr[:, 0] == 0) & (hdr[:, 1] == d["n"] - 2)).sum())
 
     # per-size kernel time (dominant kernel + roofline), one extra pass, events on the same stream
     per_size = []
     for d in dev:
+        nb_mine = int(d["bounds"][rank + 1] - d["bounds"][rank])
+        b0 = int(d["bounds"][rank])
         with torch.cuda.stream(stream):
             a, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            ctx.remove_round_device(6, R.ALG_NFR, opts, d["B"], d["rec"].data_ptr(), d["rec_off"].data_ptr(),
-                                    d["out_off"].data_ptr(), d["out"].data_ptr(), d["n"], d["E"])
+            ctx.remove_round_device(6, R.ALG_NFR, opts, nb_mine, d["rec"].data_ptr(), d["rec_off"].data_ptr() + 8 * b0,
+                                    d["out_off"].data_ptr() + 8 * b0, d["out"].data_ptr(), d["n"], d["E"])
             b2.record()
         ctx.sync()
         ms = a.elapsed_time(b2)
         alg = synth.algorithmic_bytes_flops(d["n"], d["E"], 6, "nfr")
-        per_size.append({"n": d["n"], "E": d["E"], "ms": ms, "vertices_per_s": d["B"] / (ms * 1e-3),
-                         "gflops": alg["flops"] * d["B"] / (ms * 1e-3) / 1e9,
-                         "gbs": alg["bytes"] * d["B"] / (ms * 1e-3) / 1e9})
+        per_size.append({"n": d["n"], "E": d["E"], "ms": ms, "blankets": nb_mine, "vertices_per_s": nb_mine / (ms * 1e-3),
+                         "gflops": alg["flops"] * nb_mine / (ms * 1e-3) / 1e9,
+                         "gbs": alg["bytes"] * nb_mine / (ms * 1e-3) / 1e9})
     clocks = sampler.stop()
 
     # ---- timed: end to end through the host-buffer C ABI ----------------------------------------------
     e2e_steps = max(1, min(args.steps, 3))
-    ctx.remove_round(6, R.ALG_NFR, opts, h_rec_np, rec_off_all, out_off_all, out=h_out_np)  # warm-up (allocations)
+    shard_info = None
+
+    def e2e_call():
+        nonlocal shard_info
+        if world == 1:
+            ctx.remove_round(6, R.ALG_NFR, opts, h_rec_np, rec_off_all, out_off_all, out=h_out_np)
+        else:  # collective: shards by the library's cost model, outputs gathered to rank 0 (the graph holder)
+            _, shard_info = ctx.remove_round_sharded(6, R.ALG_NFR, opts, h_rec_np, rec_off_all, out_off_all, out=h_out_np, root=0)
+    h_out_np[:] = 0
+    e2e_call()  # warm-up (allocations)
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        ctx.remove_round(6, R.ALG_NFR, opts, h_rec_np, rec_off_all, out_off_all, out=h_out_np)
+        e2e_call()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    n_ok = int((h_out_np[out_off_all[:-1]].view(np.int32)[0::2] == 0).sum())
+    n_ok = 0
+    if rank == 0:
+        hdr = h_out_np[out_off_all[:-1]].view(np.int32).reshape(-1, 2)
+        nk_all = np.concatenate([np.full(b["B"], b["n"] - 2) for b in sweep])
+        n_ok = int(((hdr[:, 0] == 0) & (hdr[:, 1] == nk_all)).sum())
+    if world > 1:
+        sl = slice(shard_info["first_blanket"], shard_info["end_blanket"])
+        h2d_bytes = int(rec_off_all[sl.stop] - rec_off_all[sl.start]) * 8 + 2 * (total_blankets + 1) * 8 + (sl.stop - sl.start) * 4
+        d2h_bytes = out_words * 8 if rank == 0 else int(out_off_all[sl.stop] - out_off_all[sl.start]) * 8
 
     # ---- reduce over ranks ----------------------------------------------------------------------------
+    gather = None
     if world > 1:
         t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dev_ms, e2e_s = float(t[0]), float(t[1])
-        # the only collective of the multi-GPU path: gather the substitute-edge records (NCCL over
-        # NVLink); timed separately, outside the throughput region
-        small = dev[3]["out"][: min(len(dev[3]["out"]), 1 << 22)]
-        gathered = torch.empty(world * small.numel(), dtype=small.dtype, device="cuda")
-        torch.cuda.synchronize()
-        g0 = time.perf_counter()
-        dist.all_gather_into_tensor(gathered, small)
-        torch.cuda.synchronize()
-        gather_ms = 1e3 * (time.perf_counter() - g0)
-    else:
-        gather_ms = None
+        t = torch.tensor([n_dev_ok, h2d_bytes, d2h_bytes], dtype=torch.int64, device="cuda")
+        tmin = t.clone()
+        dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        n_dev_ok = int(tmin[0])          # the worst rank's count of complete, OK blankets in its gathered buffers
+        h2d_bytes, d2h_bytes = int(t[1]), int(t[2])  # whole job
+        gather = {"all_gather_bytes_per_step_per_rank": int(sum(int(b["out_off"][-1]) for b in sweep) * 8 * (world - 1) // world),
+                  "e2e_gather_to_root_bytes_per_step": int(out_words * 8 * (world - 1) // world),
+                  "e2e_gather_window_ms_rank0": shard_info["gather_window_ms"] if shard_info else None,
+                  "e2e_pipeline_steps": shard_info["steps"] if shard_info else None}
 
     if rank == 0:
-        value = world * total_blankets * args.steps / (dev_ms * 1e-3)
-        e2e_value = world * total_blankets * e2e_steps / e2e_s
+        value = total_blankets * args.steps / (dev_ms * 1e-3)   # the one sweep, whatever the number of ranks
+        e2e_value = total_blankets * e2e_steps / e2e_s
         dom = max(per_size, key=lambda p: p["ms"])
         alg = synth.algorithmic_bytes_flops(dom["n"], dom["E"], 6, "nfr")
         peaks = {}
@@ -340,12 +388,14 @@ def main():
         except Exception:
             pass
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-                "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": workload_config(args.blankets, world),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                         "steps": e2e_steps, "blankets_ok": n_ok, "blankets": total_blankets},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "per_size": per_size,
-                "fp64_peak_tflops_measured": fp64_peak, "gather_ms": gather_ms}
+                "fp64_peak_tflops_measured": fp64_peak, "gather": gather,
+                "blankets_ok_device": n_dev_ok, "blankets_total": total_blankets}
+        assert n_dev_ok == total_blankets, f"device-resident outputs: only {n_dev_ok} of {total_blankets} blankets complete and OK"
         if not args.no_cpu_baseline:
             from oracle import pyoracle
             pyoracle.build()

@@ -39,10 +39,11 @@ typedef enum {
     SPG_ERR_NO_DEVICE = 3,    /* no sm_100 device: the product path has NO CPU fallback   */
     SPG_ERR_UNSUPPORTED = 4,  /* option combination the reference asserts against         */
     SPG_ERR_IO = 5,
-    SPG_ERR_BLANKET_FAILED = 6 /* graph level: at least one blanket came back with a status != SPG_BLANKET_OK
+    SPG_ERR_BLANKET_FAILED = 6, /* graph level: at least one blanket came back with a status != SPG_BLANKET_OK
                                   (the reference asserts / exits there). Its vertex and edges were left in the
                                   graph untouched; every other removal was applied. spg_marginalize_stats
-                                  names the first failing list index and its blanket status.              */
+                                  names the first failing list index and its blanket status.             */
+    SPG_ERR_COMM = 7           /* NCCL missing or a collective failed (message via spg_last_error)        */
 } spg_status;
 
 /* reference src/sparsity_options.h:12-14 (same numeric values) */
@@ -217,6 +218,63 @@ spg_status spg_remove_round_device(spg_ctx *ctx, const spg_round_in *in_dev, spg
 spg_status spg_sync(spg_ctx *ctx);
 void *spg_stream(spg_ctx *ctx); /* cudaStream_t of the context */
 
+/* ------------------------------------------------------------------------------------------ */
+/* Sharded rounds: one process per GPU, the blankets of a round split over the ranks          */
+/* ------------------------------------------------------------------------------------------ */
+/*
+ * The reference is single-threaded (src/evaluate.cpp:342-411 runs one job per process); SURVEY §8(e) shards the
+ * independent blankets of a wavefront round over the GPUs of a box. Every rank holds the same round description
+ * (the graph is replicated or lives on the root), runs a contiguous cost-balanced shard on its GPU, and the
+ * substitute-edge records are gathered with NCCL over NVLink directly between the device output buffers
+ * (ragged all-gather, or send/recv to `root`). NCCL is bound with dlopen at spg_comm_init: the library has no
+ * link-time dependency on it.
+ *   rank 0: spg_comm_unique_id(id); ...ship id to the other ranks (MPI, torch.distributed, a file)...
+ *   all   : spg_comm_init(ctx, nranks, rank, id);   (nranks == 1 is valid and needs no NCCL)
+ */
+#define SPG_COMM_ID_BYTES 128
+spg_status spg_comm_unique_id(uint8_t *id /* SPG_COMM_ID_BYTES */);
+spg_status spg_comm_init(spg_ctx *ctx, int32_t nranks, int32_t rank, const uint8_t *id);
+spg_status spg_comm_destroy(spg_ctx *ctx);
+int32_t spg_comm_nranks(const spg_ctx *ctx);
+int32_t spg_comm_rank(const spg_ctx *ctx);
+int32_t spg_comm_nccl_version(void); /* 0: NCCL not loadable */
+
+/* contiguous shards of a round balanced by a per-blanket cost model (cubic in the blanket size):
+ * bounds[r] .. bounds[r+1] is rank r's part. Pure host code. */
+spg_status spg_shard_bounds(const spg_round_in *in, int32_t nranks, int32_t *bounds /* nranks+1 */);
+
+typedef struct {
+    int32_t nranks, rank;
+    int32_t first_blanket, end_blanket; /* this rank's shard                                        */
+    int32_t steps, reserved;            /* pipeline steps (H2D | kernels | gather | D2H overlap)    */
+    double kernel_ms;                   /* first to last kernel of this rank                        */
+    double gather_window_ms;            /* first to last gather on the gather stream (overlaps)     */
+    int64_t gather_bytes;               /* bytes this rank sent or received over NVLink             */
+} spg_shard_info;
+
+/*
+ * spg_remove_round over all ranks of the communicator. Collective: every rank calls it with the SAME round (host
+ * buffers; a rank only reads the records of its own shard, and the headers of the others for the balance).
+ * root < 0: every rank gets the complete output (replicated graphs, all-gather); root >= 0: only that rank does
+ * (the others get their own shard's records). info may be NULL.
+ */
+spg_status spg_remove_round_sharded(spg_ctx *ctx, const spg_round_in *in, spg_round_out *out, int32_t root,
+                                    spg_shard_info *info);
+/*
+ * Device-resident variant (asynchronous; spg_sync() also drains the gather stream): in_dev / out_dev describe the
+ * whole round in HBM at identical offsets on every rank; the caller gives the shard bounds (blankets) and the
+ * matching word offsets into out (both nranks+1 host arrays). The gather of this call overlaps the kernels of
+ * the next one.
+ */
+spg_status spg_remove_round_sharded_device(spg_ctx *ctx, const spg_round_in *in_dev, spg_round_out *out_dev,
+                                           const int32_t *bounds, const int64_t *out_word_bounds,
+                                           int32_t max_n_vert, int32_t max_n_edges, int32_t max_rec_words,
+                                           int32_t root);
+
+/* the context stream waits (on the device, asynchronously) for every gather issued so far: call it before the output
+ * buffers of a spg_remove_round_sharded_device call are read by later work on spg_stream() or written again */
+spg_status spg_comm_join(spg_ctx *ctx);
+
 /*
  * Roofline denominator: register-resident DFMA loop on every SM (no memory traffic), timed with
  * CUDA events. MEASURED_PEAKS.json carries no FP64 figure, so bench.py measures it with this.
@@ -257,6 +315,8 @@ int32_t spg_decimate_cluster(int32_t last, int32_t endvert, int32_t sparsity, in
  * removes the vertices `which` (in this order) and splices the substitute edges in. The result is
  * identical to the reference's one-at-a-time loop; internally removals are grouped into
  * wavefront rounds of non-interfering blankets, each round is one spg_remove_round().
+ * With a communicator on ctx (spg_comm_init, nranks > 1) the call is collective: every rank passes an identical
+ * graph and list, each round is one spg_remove_round_sharded(root = -1), and the graphs stay identical.
  */
 spg_status spg_graph_marginalize(spg_graph *g, spg_ctx *ctx, const int32_t *which, int32_t n_which,
                                  const spg_sparsity_options *opts, int32_t algorithm);

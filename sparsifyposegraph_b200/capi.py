@@ -50,6 +50,15 @@ class MarginalizeStats(C.Structure):
                 ("reserved", C.c_int32)]
 
 
+class ShardInfo(C.Structure):
+    _fields_ = [("nranks", C.c_int32), ("rank", C.c_int32), ("first_blanket", C.c_int32), ("end_blanket", C.c_int32),
+                ("steps", C.c_int32), ("reserved", C.c_int32), ("kernel_ms", C.c_double), ("gather_window_ms", C.c_double),
+                ("gather_bytes", C.c_int64)]
+
+
+COMM_ID_BYTES = 128
+
+
 class SpgError(RuntimeError):
     pass
 
@@ -82,6 +91,16 @@ def lib():
         L.spg_out_record_words.restype = C.c_int64
         L.spg_out_record_words.argtypes = [C.c_int32, C.c_int32, C.POINTER(SparsityOptions), C.c_int32]
         L.spg_fp64_peak_probe.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_double)]
+        L.spg_comm_unique_id.argtypes = [C.c_void_p]
+        L.spg_comm_init.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+        L.spg_comm_destroy.argtypes = [C.c_void_p]
+        L.spg_comm_join.argtypes = [C.c_void_p]
+        L.spg_comm_nranks.argtypes = [C.c_void_p]
+        L.spg_comm_rank.argtypes = [C.c_void_p]
+        L.spg_shard_bounds.argtypes = [C.POINTER(RoundIn), C.c_int32, C.c_void_p]
+        L.spg_remove_round_sharded.argtypes = [C.c_void_p, C.POINTER(RoundIn), C.POINTER(RoundOut), C.c_int32, C.POINTER(ShardInfo)]
+        L.spg_remove_round_sharded_device.argtypes = [C.c_void_p, C.POINTER(RoundIn), C.POINTER(RoundOut), C.c_void_p, C.c_void_p,
+                                                      C.c_int32, C.c_int32, C.c_int32, C.c_int32]
         _lib = L
     return _lib
 
@@ -167,11 +186,78 @@ class Context:
     def sync(self):
         _check(lib().spg_sync(self.h))
 
+    # ---- sharded rounds (spg_comm.cu): one process per GPU, NCCL gather of the substitute-edge records -------------
+    def comm_init(self, nranks, rank, unique_id=None):
+        """unique_id: the SPG_COMM_ID_BYTES bytes rank 0 got from comm_unique_id() (any transport); None for nranks == 1."""
+        buf = None
+        if unique_id is not None:
+            buf = np.frombuffer(bytes(unique_id), dtype=np.uint8).copy()
+            assert len(buf) == COMM_ID_BYTES
+        _check(lib().spg_comm_init(self.h, int(nranks), int(rank), _p(buf)))
+
+    def comm_join(self):
+        """The context stream waits for the gathers issued so far (asynchronous)."""
+        _check(lib().spg_comm_join(self.h))
+
+    def comm_destroy(self):
+        _check(lib().spg_comm_destroy(self.h))
+
+    @property
+    def nranks(self):
+        return int(lib().spg_comm_nranks(self.h))
+
+    @property
+    def rank(self):
+        return int(lib().spg_comm_rank(self.h))
+
+    def remove_round_sharded(self, dim, algorithm, opts, records, rec_off, out_off, out=None, root=-1):
+        """Collective: the same round on every rank, each runs its shard, outputs gathered over NCCL.
+        Returns (out, info dict). root < 0: every rank gets the whole output."""
+        records = np.ascontiguousarray(records, dtype=np.uint64)
+        rec_off = np.ascontiguousarray(rec_off, dtype=np.int64)
+        out_off = np.ascontiguousarray(out_off, dtype=np.int64)
+        nb = len(rec_off) - 1
+        if out is None:
+            out = np.zeros(int(out_off[-1]), dtype=np.uint64)
+        rin = RoundIn(dim, algorithm, opts, nb, 0, _p(rec_off), _p(records), _p(out_off))
+        rout = RoundOut(_p(out), None, None, None, None)
+        info = ShardInfo()
+        _check(lib().spg_remove_round_sharded(self.h, C.byref(rin), C.byref(rout), int(root), C.byref(info)))
+        return out, {f: getattr(info, f) for f, _ in ShardInfo._fields_}
+
+    def remove_round_sharded_device(self, dim, algorithm, opts, n_blankets, d_records, d_rec_off, d_out_off, d_out, bounds,
+                                    out_word_bounds, max_n_vert, max_n_edges, max_rec_words=0, root=-1):
+        """Device-resident collective round; bounds / out_word_bounds: nranks+1 host arrays (blankets / output words)."""
+        b = np.ascontiguousarray(bounds, dtype=np.int32)
+        w = np.ascontiguousarray(out_word_bounds, dtype=np.int64)
+        rin = RoundIn(dim, algorithm, opts, int(n_blankets), 0, int(d_rec_off), int(d_records), int(d_out_off))
+        rout = RoundOut(int(d_out), None, None, None, None)
+        _check(lib().spg_remove_round_sharded_device(self.h, C.byref(rin), C.byref(rout), _p(b), _p(w), int(max_n_vert),
+                                                     int(max_n_edges), int(max_rec_words), int(root)))
+
     def fp64_peak_tflops(self, repeats=5):
         """Measured DFMA peak of this device (roofline denominator for the FP64-bound kernels)."""
         v = C.c_double()
         _check(lib().spg_fp64_peak_probe(self.h, int(repeats), C.byref(v)))
         return float(v.value)
+
+
+def comm_unique_id():
+    """ncclGetUniqueId through the library (rank 0); ship the bytes to the other ranks."""
+    buf = np.zeros(COMM_ID_BYTES, dtype=np.uint8)
+    _check(lib().spg_comm_unique_id(_p(buf)))
+    return buf.tobytes()
+
+
+def shard_bounds(dim, algorithm, opts, records, rec_off, out_off, nranks):
+    """spg_shard_bounds: contiguous cost-balanced shards of a round (pure host code)."""
+    records = np.ascontiguousarray(records, dtype=np.uint64)
+    rec_off = np.ascontiguousarray(rec_off, dtype=np.int64)
+    out_off = np.ascontiguousarray(out_off, dtype=np.int64)
+    rin = RoundIn(dim, algorithm, opts, len(rec_off) - 1, 0, _p(rec_off), _p(records), _p(out_off))
+    b = np.zeros(nranks + 1, dtype=np.int32)
+    _check(lib().spg_shard_bounds(C.byref(rin), int(nranks), _p(b)))
+    return b
 
 
 def _graph_protos(L):

@@ -178,6 +178,166 @@ spg_status check_device(spg_ctx *ctx) {
 
 } // namespace
 
+// ---- pieces of the host-buffer round shared by spg_remove_round and spg_remove_round_sharded (spg_comm.cu) ----------
+
+// contiguous split of blankets [b0, b1) into `parts` runs of about equal bytes (records + outputs): parts+1 bounds
+void spg_split_by_bytes(const spg_round_in *in, int b0, int b1, int parts, std::vector<int> &cb) {
+    cb.assign(parts + 1, b1);
+    cb[0] = b0;
+    const int64_t base = in->rec_off[b0] + in->out_off[b0];
+    const int64_t total = (in->rec_off[b1] + in->out_off[b1] - base) * 8;
+    for(int c = 1, b = b0; c < parts; c++) {
+        const int64_t goal = total / parts * c;
+        while(b < b1 && (in->rec_off[b] + in->out_off[b] - base) * 8 < goal) b++;
+        cb[c] = b;
+    }
+}
+
+// device buffers at the host offsets, offset tables and debug buffers up, retry counters zeroed (stream s_in)
+spg_status spg_round_prepare(spg_ctx *ctx, const spg_round_in *in, spg_round_out *out, int nchunks, spg::RoundRun &run) {
+    const int nb = in->n_blankets;
+    const int64_t rec_words = in->rec_off[nb], out_words = in->out_off[nb];
+    if(!ctx->s_in) {
+        SPG_CUDA(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+        SPG_CUDA(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+    }
+    while((int) ctx->ev_pool.size() < 2 * nchunks) {
+        cudaEvent_t e;
+        SPG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->ev_pool.push_back(e);
+    }
+    SPG_CUDA(ctx->d_rec.reserve((size_t) rec_words * 8));
+    SPG_CUDA(ctx->d_recoff.reserve((size_t) (nb + 1) * 8));
+    SPG_CUDA(ctx->d_outoff.reserve((size_t) (nb + 1) * 8));
+    SPG_CUDA(ctx->d_out.reserve((size_t) out_words * 8));
+    SPG_CUDA(ctx->d_list.reserve((size_t) nb * 4));
+    SPG_CUDA(ctx->d_retry.reserve((size_t) nb * 4));
+    const int n_counters = nchunks * 32; // one per bucket launch (NBK <= 32)
+    SPG_CUDA(ctx->d_retry_cnt.reserve((size_t) n_counters * 4));
+    SPG_CUDA(cudaMemsetAsync(ctx->d_retry_cnt.p, 0, (size_t) n_counters * 4, ctx->s_in));
+    run.counter_next = 0;
+    run.first = true;
+    run.flat.resize(nb);
+    SPG_CUDA(cudaMemcpyAsync(ctx->d_recoff.p, in->rec_off, (size_t) (nb + 1) * 8, cudaMemcpyHostToDevice, ctx->s_in));
+    SPG_CUDA(cudaMemcpyAsync(ctx->d_outoff.p, in->out_off, (size_t) (nb + 1) * 8, cudaMemcpyHostToDevice, ctx->s_in));
+    run.tgt_n = run.wts_n = 0;
+    if(out->dbg_target && out->dbg_target_off) {
+        run.tgt_n = out->dbg_target_off[nb];
+        SPG_CUDA(ctx->d_tgt.reserve((size_t) run.tgt_n * 8 + 8));
+        SPG_CUDA(ctx->d_tgtoff.reserve((size_t) (nb + 1) * 8));
+        SPG_CUDA(cudaMemcpyAsync(ctx->d_tgtoff.p, out->dbg_target_off, (size_t) (nb + 1) * 8, cudaMemcpyHostToDevice, ctx->s_in));
+        SPG_CUDA(cudaMemsetAsync(ctx->d_tgt.p, 0, (size_t) run.tgt_n * 8 + 8, ctx->s_in));
+    }
+    if(out->dbg_weights && out->dbg_weights_off) {
+        run.wts_n = out->dbg_weights_off[nb];
+        SPG_CUDA(ctx->d_wts.reserve((size_t) run.wts_n * 8 + 8));
+        SPG_CUDA(ctx->d_wtsoff.reserve((size_t) (nb + 1) * 8));
+        SPG_CUDA(cudaMemcpyAsync(ctx->d_wtsoff.p, out->dbg_weights_off, (size_t) (nb + 1) * 8, cudaMemcpyHostToDevice, ctx->s_in));
+        if(in->opts.flags & SPG_OPT_DBG_WEIGHTS_IN)
+            SPG_CUDA(cudaMemcpyAsync(ctx->d_wts.p, out->dbg_weights, (size_t) run.wts_n * 8, cudaMemcpyHostToDevice, ctx->s_in));
+        else
+            SPG_CUDA(cudaMemsetAsync(ctx->d_wts.p, 0, (size_t) run.wts_n * 8 + 8, ctx->s_in));
+    }
+    return SPG_OK;
+}
+
+// blankets [b0, b1) of the round: validate, bucket by size, H2D on s_in (event 2c), one fused kernel per bucket on
+// the context stream (event 2c+1 behind the last one)
+spg_status spg_round_enqueue_chunk(spg_ctx *ctx, const spg_round_in *in, spg::RoundRun &run, int b0, int b1, int c) {
+    static const int bounds6[] = {3, 4, 5, 6, 7, 8, 10, 12, 14, 16, 20, 24, 32, 48, 64, 128, 1 << 30};
+    constexpr int NBK = sizeof(bounds6) / sizeof(int);
+    const int dim = in->dim;
+    // ---- validate the chunk's records before anything of it is launched (runs while the GPU works on c-1)
+    {
+        const int bad = validate_records_mt(in, b0, b1);
+        if(bad >= 0) {
+            cudaDeviceSynchronize();
+            set_err("malformed blanket record " + std::to_string(bad) +
+                    " (header, edge table, vertex index or output slice out of bounds)");
+            return SPG_ERR_INVALID;
+        }
+    }
+    // ---- bucket this chunk by blanket size -----------------------------------------------------
+    std::vector<Bucket> buckets(NBK);
+    for(int b = b0; b < b1; b++) {
+        const int32_t *h = reinterpret_cast<const int32_t *>(in->records + in->rec_off[b]);
+        int bi = 0;
+        while(h[0] > bounds6[bi]) bi++;
+        Bucket &B = buckets[bi];
+        B.list.push_back(b);
+        B.max_nv = std::max(B.max_nv, (int) h[0]);
+        B.max_e = std::max(B.max_e, (int) h[2]);
+        B.max_rec = std::max(B.max_rec, (int) h[4]);
+    }
+    size_t pos = (size_t) b0;
+    for(auto &B : buckets) {
+        std::copy(B.list.begin(), B.list.end(), run.flat.begin() + pos);
+        pos += B.list.size();
+    }
+    // ---- H2D of the chunk -----------------------------------------------------------------------
+    const int64_t r0 = in->rec_off[b0], r1 = in->rec_off[b1];
+    SPG_CUDA(cudaMemcpyAsync(reinterpret_cast<uint64_t *>(ctx->d_rec.p) + r0, in->records + r0, (size_t) (r1 - r0) * 8,
+                             cudaMemcpyHostToDevice, ctx->s_in));
+    SPG_CUDA(cudaMemcpyAsync(reinterpret_cast<int32_t *>(ctx->d_list.p) + b0, run.flat.data() + b0, (size_t) (b1 - b0) * 4,
+                             cudaMemcpyHostToDevice, ctx->s_in));
+    SPG_CUDA(cudaEventRecord(ctx->ev_pool[2 * c], ctx->s_in));
+    SPG_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_pool[2 * c], 0));
+    if(run.first) {
+        SPG_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+        run.first = false;
+    }
+    // ---- kernels ----------------------------------------------------------------------------------
+    size_t list_pos = (size_t) b0;
+    for(auto &B : buckets) {
+        if(B.list.empty()) continue;
+        spg::KernelParams kp{};
+        kp.algorithm = in->algorithm;
+        kp.topology = in->opts.topology;
+        kp.chord_ratio = in->opts.chord_ratio;
+        kp.flags = in->opts.flags;
+        kp.n_list = (int32_t) B.list.size();
+        kp.list = reinterpret_cast<const int32_t *>(ctx->d_list.p) + list_pos;
+        kp.retry_list = reinterpret_cast<int32_t *>(ctx->d_retry.p) + list_pos;
+        kp.retry_count = reinterpret_cast<int32_t *>(ctx->d_retry_cnt.p) + run.counter_next++;
+        list_pos += B.list.size();
+        kp.rec_off = reinterpret_cast<const int64_t *>(ctx->d_recoff.p);
+        kp.records = reinterpret_cast<const uint64_t *>(ctx->d_rec.p);
+        kp.out_off = reinterpret_cast<const int64_t *>(ctx->d_outoff.p);
+        kp.out = reinterpret_cast<uint64_t *>(ctx->d_out.p);
+        kp.dbg_target = run.tgt_n ? reinterpret_cast<double *>(ctx->d_tgt.p) : nullptr;
+        kp.dbg_target_off = run.tgt_n ? reinterpret_cast<const int64_t *>(ctx->d_tgtoff.p) : nullptr;
+        kp.dbg_weights = run.wts_n ? reinterpret_cast<double *>(ctx->d_wts.p) : nullptr;
+        kp.dbg_weights_off = run.wts_n ? reinterpret_cast<const int64_t *>(ctx->d_wtsoff.p) : nullptr;
+        kp.max_nv = B.max_nv;
+        kp.max_e = B.max_e;
+        kp.max_rec_words = (B.max_rec + 1) & ~1;
+        spg_status st = (dim == 6) ? launch_dim<6>(ctx, kp) : launch_dim<3>(ctx, kp);
+        if(st != SPG_OK) {
+            cudaDeviceSynchronize();
+            return st;
+        }
+    }
+    SPG_CUDA(cudaEventRecord(ctx->ev_pool[2 * c + 1], ctx->stream));
+    return SPG_OK;
+}
+
+// debug buffers back, all three streams drained, kernel time of the call recorded
+spg_status spg_round_finish(spg_ctx *ctx, spg_round_out *out, spg::RoundRun &run) {
+    ctx->retry_used = run.counter_next;
+    SPG_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+    if(run.tgt_n) SPG_CUDA(cudaMemcpyAsync(out->dbg_target, ctx->d_tgt.p, (size_t) run.tgt_n * 8, cudaMemcpyDeviceToHost, ctx->s_out));
+    if(run.wts_n) SPG_CUDA(cudaMemcpyAsync(out->dbg_weights, ctx->d_wts.p, (size_t) run.wts_n * 8, cudaMemcpyDeviceToHost, ctx->s_out));
+    SPG_CUDA(cudaStreamSynchronize(ctx->s_in));
+    SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+    SPG_CUDA(cudaStreamSynchronize(ctx->s_out));
+    float ms = 0;
+    if(!run.first) {
+        SPG_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        ctx->last_ms = ms; // first kernel to last kernel of the call (waits for the chunked copies included)
+    }
+    return SPG_OK;
+}
+
 extern "C" {
 
 const char *spg_version(void) { return "sparsifyposegraph_b200 0.1 (sm_100a)"; }
@@ -223,6 +383,7 @@ spg_status spg_create(spg_ctx **out, const spg_config *cfg) {
 void spg_destroy(spg_ctx *ctx) {
     if(!ctx) return;
     cudaSetDevice(ctx->device);
+    spg_comm_release(ctx);
     for(DevBuf *b : {&ctx->d_rec, &ctx->d_recoff, &ctx->d_outoff, &ctx->d_out, &ctx->d_list, &ctx->d_tgt,
                      &ctx->d_tgtoff, &ctx->d_wts, &ctx->d_wtsoff, &ctx->d_ws, &ctx->d_gws, &ctx->d_prof, &ctx->d_retry, &ctx->d_retry_cnt})
         b->release();
@@ -307,6 +468,7 @@ int64_t spg_last_retry_count(spg_ctx *ctx) {
 spg_status spg_sync(spg_ctx *ctx) {
     if(check_device(ctx) != SPG_OK) return SPG_ERR_INVALID;
     SPG_CUDA(cudaStreamSynchronize(ctx->stream));
+    if(ctx->s_comm) SPG_CUDA(cudaStreamSynchronize(ctx->s_comm));
     float ms = 0;
     if(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) == cudaSuccess) ctx->last_ms = ms;
     else (void) cudaGetLastError();
@@ -363,14 +525,13 @@ spg_status spg_remove_round(spg_ctx *ctx, const spg_round_in *in, spg_round_out 
     }
     const int nb = in->n_blankets;
     if(nb == 0) return SPG_OK;
-    SPG_CUDA(cudaSetDevice(ctx->device));
-    const int dim = in->dim;
-    const int64_t rec_words = in->rec_off[nb];
-    const int64_t out_words = in->out_off[nb];
     if(!in->rec_off || !in->out_off || !in->records) {
         set_err("bad round descriptor");
         return SPG_ERR_INVALID;
     }
+    SPG_CUDA(cudaSetDevice(ctx->device));
+    const int64_t rec_words = in->rec_off[nb];
+    const int64_t out_words = in->out_off[nb];
 
     // ---- chunks: contiguous runs of blankets, so that the H2D copy of chunk c+1, the kernels of chunk c and the
     // D2H copy of chunk c-1 overlap (three streams, events in between). Every chunk owns its own slice of the
@@ -379,149 +540,24 @@ spg_status spg_remove_round(spg_ctx *ctx, const spg_round_in *in, spg_round_out 
     const int64_t total_bytes = (rec_words + out_words) * 8;
     int nchunks = (int) std::min<int64_t>(32, total_bytes / std::max<int64_t>(ctx->chunk_bytes, 4096));
     if(nchunks < 1 || dbg) nchunks = 1;
-    std::vector<int> cb(nchunks + 1, nb);
-    cb[0] = 0;
-    for(int c = 1, b = 0; c < nchunks; c++) { // split by bytes of records + outputs
-        const int64_t goal = total_bytes / nchunks * c;
-        while(b < nb && (in->rec_off[b] + in->out_off[b]) * 8 < goal) b++;
-        cb[c] = b;
-    }
-    if(!ctx->s_in) {
-        SPG_CUDA(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
-        SPG_CUDA(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
-    }
-    while((int) ctx->ev_pool.size() < 2 * nchunks) {
-        cudaEvent_t e;
-        SPG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        ctx->ev_pool.push_back(e);
-    }
+    std::vector<int> cb;
+    spg_split_by_bytes(in, 0, nb, nchunks, cb);
 
-    SPG_CUDA(ctx->d_rec.reserve((size_t) rec_words * 8));
-    SPG_CUDA(ctx->d_recoff.reserve((size_t) (nb + 1) * 8));
-    SPG_CUDA(ctx->d_outoff.reserve((size_t) (nb + 1) * 8));
-    SPG_CUDA(ctx->d_out.reserve((size_t) out_words * 8));
-    SPG_CUDA(ctx->d_list.reserve((size_t) nb * 4));
-    SPG_CUDA(ctx->d_retry.reserve((size_t) nb * 4));
-    const int n_counters = nchunks * 32; // one per bucket launch (NBK <= 32)
-    SPG_CUDA(ctx->d_retry_cnt.reserve((size_t) n_counters * 4));
-    SPG_CUDA(cudaMemsetAsync(ctx->d_retry_cnt.p, 0, (size_t) n_counters * 4, ctx->s_in));
-    int counter_next = 0;
-    SPG_CUDA(cudaMemcpyAsync(ctx->d_recoff.p, in->rec_off, (size_t) (nb + 1) * 8, cudaMemcpyHostToDevice, ctx->s_in));
-    SPG_CUDA(cudaMemcpyAsync(ctx->d_outoff.p, in->out_off, (size_t) (nb + 1) * 8, cudaMemcpyHostToDevice, ctx->s_in));
-    int64_t tgt_n = 0, wts_n = 0;
-    if(out->dbg_target && out->dbg_target_off) {
-        tgt_n = out->dbg_target_off[nb];
-        SPG_CUDA(ctx->d_tgt.reserve((size_t) tgt_n * 8 + 8));
-        SPG_CUDA(ctx->d_tgtoff.reserve((size_t) (nb + 1) * 8));
-        SPG_CUDA(cudaMemcpyAsync(ctx->d_tgtoff.p, out->dbg_target_off, (size_t) (nb + 1) * 8, cudaMemcpyHostToDevice, ctx->s_in));
-        SPG_CUDA(cudaMemsetAsync(ctx->d_tgt.p, 0, (size_t) tgt_n * 8 + 8, ctx->s_in));
-    }
-    if(out->dbg_weights && out->dbg_weights_off) {
-        wts_n = out->dbg_weights_off[nb];
-        SPG_CUDA(ctx->d_wts.reserve((size_t) wts_n * 8 + 8));
-        SPG_CUDA(ctx->d_wtsoff.reserve((size_t) (nb + 1) * 8));
-        SPG_CUDA(cudaMemcpyAsync(ctx->d_wtsoff.p, out->dbg_weights_off, (size_t) (nb + 1) * 8, cudaMemcpyHostToDevice, ctx->s_in));
-        if(in->opts.flags & SPG_OPT_DBG_WEIGHTS_IN)
-            SPG_CUDA(cudaMemcpyAsync(ctx->d_wts.p, out->dbg_weights, (size_t) wts_n * 8, cudaMemcpyHostToDevice, ctx->s_in));
-        else
-            SPG_CUDA(cudaMemsetAsync(ctx->d_wts.p, 0, (size_t) wts_n * 8 + 8, ctx->s_in));
-    }
-
-    static const int bounds6[] = {3, 4, 5, 6, 7, 8, 10, 12, 14, 16, 20, 24, 32, 48, 64, 128, 1 << 30};
-    constexpr int NBK = sizeof(bounds6) / sizeof(int);
-    std::vector<int32_t> flat(nb); // bucket-ordered blanket indices of every chunk; must outlive the async copies
-    bool first = true;
+    spg::RoundRun run;
+    spg_status st = spg_round_prepare(ctx, in, out, nchunks, run);
+    if(st != SPG_OK) return st;
     for(int c = 0; c < nchunks; c++) {
         const int b0 = cb[c], b1 = cb[c + 1];
         if(b1 <= b0) continue;
-        // ---- validate the chunk's records before anything of it is launched (runs while the GPU works on c-1)
-        {
-            const int bad = validate_records_mt(in, b0, b1);
-            if(bad >= 0) {
-                cudaDeviceSynchronize();
-                set_err("malformed blanket record " + std::to_string(bad) +
-                        " (header, edge table, vertex index or output slice out of bounds)");
-                return SPG_ERR_INVALID;
-            }
-        }
-        // ---- bucket this chunk by blanket size -----------------------------------------------------
-        std::vector<Bucket> buckets(NBK);
-        for(int b = b0; b < b1; b++) {
-            const int32_t *h = reinterpret_cast<const int32_t *>(in->records + in->rec_off[b]);
-            int bi = 0;
-            while(h[0] > bounds6[bi]) bi++;
-            Bucket &B = buckets[bi];
-            B.list.push_back(b);
-            B.max_nv = std::max(B.max_nv, (int) h[0]);
-            B.max_e = std::max(B.max_e, (int) h[2]);
-            B.max_rec = std::max(B.max_rec, (int) h[4]);
-        }
-        size_t pos = (size_t) b0;
-        for(auto &B : buckets) {
-            std::copy(B.list.begin(), B.list.end(), flat.begin() + pos);
-            pos += B.list.size();
-        }
-        // ---- H2D of the chunk -----------------------------------------------------------------------
-        const int64_t r0 = in->rec_off[b0], r1 = in->rec_off[b1];
-        SPG_CUDA(cudaMemcpyAsync(reinterpret_cast<uint64_t *>(ctx->d_rec.p) + r0, in->records + r0, (size_t) (r1 - r0) * 8,
-                                 cudaMemcpyHostToDevice, ctx->s_in));
-        SPG_CUDA(cudaMemcpyAsync(reinterpret_cast<int32_t *>(ctx->d_list.p) + b0, flat.data() + b0, (size_t) (b1 - b0) * 4,
-                                 cudaMemcpyHostToDevice, ctx->s_in));
-        SPG_CUDA(cudaEventRecord(ctx->ev_pool[2 * c], ctx->s_in));
-        SPG_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_pool[2 * c], 0));
-        if(first) {
-            SPG_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
-            first = false;
-        }
-        // ---- kernels ----------------------------------------------------------------------------------
-        size_t list_pos = (size_t) b0;
-        for(auto &B : buckets) {
-            if(B.list.empty()) continue;
-            spg::KernelParams kp{};
-            kp.algorithm = in->algorithm;
-            kp.topology = in->opts.topology;
-            kp.chord_ratio = in->opts.chord_ratio;
-            kp.flags = in->opts.flags;
-            kp.n_list = (int32_t) B.list.size();
-            kp.list = reinterpret_cast<const int32_t *>(ctx->d_list.p) + list_pos;
-            kp.retry_list = reinterpret_cast<int32_t *>(ctx->d_retry.p) + list_pos;
-            kp.retry_count = reinterpret_cast<int32_t *>(ctx->d_retry_cnt.p) + counter_next++;
-            list_pos += B.list.size();
-            kp.rec_off = reinterpret_cast<const int64_t *>(ctx->d_recoff.p);
-            kp.records = reinterpret_cast<const uint64_t *>(ctx->d_rec.p);
-            kp.out_off = reinterpret_cast<const int64_t *>(ctx->d_outoff.p);
-            kp.out = reinterpret_cast<uint64_t *>(ctx->d_out.p);
-            kp.dbg_target = tgt_n ? reinterpret_cast<double *>(ctx->d_tgt.p) : nullptr;
-            kp.dbg_target_off = tgt_n ? reinterpret_cast<const int64_t *>(ctx->d_tgtoff.p) : nullptr;
-            kp.dbg_weights = wts_n ? reinterpret_cast<double *>(ctx->d_wts.p) : nullptr;
-            kp.dbg_weights_off = wts_n ? reinterpret_cast<const int64_t *>(ctx->d_wtsoff.p) : nullptr;
-            kp.max_nv = B.max_nv;
-            kp.max_e = B.max_e;
-            kp.max_rec_words = (B.max_rec + 1) & ~1;
-            spg_status st = (dim == 6) ? launch_dim<6>(ctx, kp) : launch_dim<3>(ctx, kp);
-            if(st != SPG_OK) {
-                cudaDeviceSynchronize();
-                return st;
-            }
-        }
-        SPG_CUDA(cudaEventRecord(ctx->ev_pool[2 * c + 1], ctx->stream));
+        st = spg_round_enqueue_chunk(ctx, in, run, b0, b1, c);
+        if(st != SPG_OK) return st;
         // ---- D2H of the chunk -----------------------------------------------------------------------
         SPG_CUDA(cudaStreamWaitEvent(ctx->s_out, ctx->ev_pool[2 * c + 1], 0));
         const int64_t o0 = in->out_off[b0], o1 = in->out_off[b1];
         SPG_CUDA(cudaMemcpyAsync(out->out + o0, reinterpret_cast<uint64_t *>(ctx->d_out.p) + o0, (size_t) (o1 - o0) * 8,
                                  cudaMemcpyDeviceToHost, ctx->s_out));
     }
-    ctx->retry_used = counter_next;
-    SPG_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
-    if(tgt_n) SPG_CUDA(cudaMemcpyAsync(out->dbg_target, ctx->d_tgt.p, (size_t) tgt_n * 8, cudaMemcpyDeviceToHost, ctx->s_out));
-    if(wts_n) SPG_CUDA(cudaMemcpyAsync(out->dbg_weights, ctx->d_wts.p, (size_t) wts_n * 8, cudaMemcpyDeviceToHost, ctx->s_out));
-    SPG_CUDA(cudaStreamSynchronize(ctx->s_in));
-    SPG_CUDA(cudaStreamSynchronize(ctx->stream));
-    SPG_CUDA(cudaStreamSynchronize(ctx->s_out));
-    float ms = 0;
-    SPG_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
-    ctx->last_ms = ms; // first kernel to last kernel of the call (waits for the chunked copies included)
-    return SPG_OK;
+    return spg_round_finish(ctx, out, run);
 }
 
 } // extern "C"

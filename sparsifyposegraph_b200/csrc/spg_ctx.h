@@ -57,7 +57,30 @@ struct spg_ctx {
     int fast_ctas_per_sm = 0;                    // resident CTAs per SM of the last fast_kernel launch (diagnostics)
     bool no_fast = false;                        // env SPG_NO_FAST=1: blanket_kernel only (A/B measurements, tests)
     bool profiling = false;
+    // multi-GPU (spg_comm.cu): NCCL communicator of this context, its own stream, events compute -> gather -> D2H
+    void *comm = nullptr; // ncclComm_t
+    int nranks = 1, rank = 0;
+    cudaStream_t s_comm = nullptr;
+    std::vector<cudaEvent_t> ev_comm;
+    cudaEvent_t ev_g0 = nullptr, ev_g1 = nullptr; // timing of the gathers of the last call
+    double last_gather_ms = 0;
+    int64_t last_gather_bytes = 0;
 };
+
+// host-buffer round, shared between spg_remove_round (spg_capi.cu) and spg_remove_round_sharded (spg_comm.cu)
+namespace spg {
+struct RoundRun {
+    std::vector<int32_t> flat; // bucket-ordered blanket indices of every chunk; must outlive the async copies
+    int counter_next = 0;
+    bool first = true;
+    int64_t tgt_n = 0, wts_n = 0;
+};
+} // namespace spg
+void spg_split_by_bytes(const spg_round_in *in, int b0, int b1, int parts, std::vector<int> &cb);
+spg_status spg_round_prepare(spg_ctx *ctx, const spg_round_in *in, spg_round_out *out, int nchunks, spg::RoundRun &run);
+spg_status spg_round_enqueue_chunk(spg_ctx *ctx, const spg_round_in *in, spg::RoundRun &run, int b0, int b1, int c);
+spg_status spg_round_finish(spg_ctx *ctx, spg_round_out *out, spg::RoundRun &run);
+void spg_comm_release(spg_ctx *ctx);
 
 namespace spg { struct KernelParams; }
 // one per kernel instantiation (spg_inst_<D>_<NT>.cu)

@@ -500,7 +500,9 @@ std::vector<int> VertexRemover::remove(const std::vector<int> &toRemove, spg_sta
         spg_round_in rin = roundDescriptor();
         spg_round_out rout{};
         rout.out = out.data();
-        st = spg_remove_round(_ctx, &rin, &rout);
+        // a context with a communicator (spg_comm_init) shards every round over its ranks; all ranks hold the same
+        // graph, get the complete output (all-gather) and splice the same edges
+        st = spg_comm_nranks(_ctx) > 1 ? spg_remove_round_sharded(_ctx, &rin, &rout, -1, nullptr) : spg_remove_round(_ctx, &rin, &rout);
         if(st != SPG_OK) {
             error = spg_last_error();
             break;

@@ -1,8 +1,11 @@
 """Multi-GPU node removal: the blankets of a wavefront round are independent, so every rank takes a
 contiguous shard of the round, runs it on its own GPU, and the substitute-edge records are gathered
-back (the only exchange of the path: torch.distributed all_gather — NCCL over NVLink on GPUs, gloo in
-the CPU tests). Every rank holds the same host-side graph and applies the same gathered round, so the
-graphs stay identical without any other communication.
+back. The product path is C++ behind the C ABI (csrc/spg_comm.cu: spg_comm_init, spg_remove_round_sharded, NCCL
+directly on the device output buffers); this module only (1) hands the NCCL unique id around with
+torch.distributed and (2) keeps a Python restatement of the round loop with a pluggable per-shard engine and a gloo
+gather, so that the sharding / gather / splice logic is tested on CPU (tests/test_distributed.py).
+Every rank holds the same host-side graph and applies the same gathered round, so the graphs stay identical
+without any other communication.
 """
 from __future__ import annotations
 
@@ -11,28 +14,32 @@ import numpy as np
 from . import capi
 
 
-def shard_bounds(rec_off, world):
-    """Contiguous split of a round's blankets into `world` shards balanced by record size cubed (a proxy
-    for the per-blanket cost, which is cubic in the blanket dimension). Returns world+1 boundaries."""
-    n = len(rec_off) - 1
-    if n == 0:
+def init_comm(ctx, rank, world, group=None):
+    """Give `ctx` its NCCL communicator (spg_comm_init): rank 0 draws the unique id through the library and it is
+    shipped over the already-initialised torch.distributed group (any transport would do: it is 128 bytes)."""
+    import torch.distributed as dist
+    box = [capi.comm_unique_id() if rank == 0 else None] if world > 1 else [None]
+    if world > 1:
+        dist.broadcast_object_list(box, src=0, group=group)
+    ctx.comm_init(world, rank, box[0])
+
+
+def shard_bounds(rd, world):
+    """spg_shard_bounds of a round dict (capi.round_next): contiguous shards balanced by the per-blanket cost
+    model of the library. Returns world+1 boundaries."""
+    if rd["n"] == 0:
         return [0] * (world + 1)
-    w = np.diff(np.asarray(rec_off, dtype=np.float64)) ** 1.5
-    c = np.concatenate([[0.0], np.cumsum(w)])
-    bounds = [0]
-    for r in range(1, world):
-        bounds.append(int(np.searchsorted(c, c[-1] * r / world)))
-    bounds.append(n)
-    for i in range(1, len(bounds)):
-        bounds[i] = max(bounds[i], bounds[i - 1])
-    return bounds
+    return [int(x) for x in capi.shard_bounds(rd["dim"], rd["algorithm"], rd["opts"], rd["records"], rd["rec_off"],
+                                              rd["out_off"], world)]
 
 
 def marginalize_sharded(graph, which, opts, algorithm, compute, rank=0, world=1, group=None, device=None):
     """VertexRemover::remove(which) with every round sharded over `world` ranks.
 
     compute(dim, algorithm, opts, records, rec_off, out_off) -> uint64 output buffer of a sub-round
-    (in production `lambda *a: ctx.remove_round(*a)[0]` on this rank's GPU).
+    (this Python loop exists for the CPU tests, where the oracle stands in for the GPU; on GPUs the whole loop is
+    C++: `distributed.init_comm(ctx, rank, world)` once, then `graph.marginalize(ctx, ...)` is collective and every
+    round is one spg_remove_round_sharded with the NCCL gather on the device buffers).
     Returns the number of rounds."""
     capi.rounds_begin(graph, which, opts, algorithm)
     rounds = 0
@@ -40,7 +47,7 @@ def marginalize_sharded(graph, which, opts, algorithm, compute, rank=0, world=1,
         rd = capi.round_next(graph)
         if rd is None:
             break
-        bounds = shard_bounds(rd["rec_off"], world)
+        bounds = shard_bounds(rd, world)
         b0, b1 = bounds[rank], bounds[rank + 1]
         ro, oo = rd["rec_off"], rd["out_off"]
         if b1 > b0:

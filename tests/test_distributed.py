@@ -46,14 +46,27 @@ def _worker(rank, world, port, path, which, q):
 
 
 def test_shard_bounds_cover_and_balance():
-    from sparsifyposegraph_b200 import distributed
-    rec_off = np.concatenate([[0], np.cumsum(np.random.default_rng(0).integers(100, 2000, 1000))])
+    """spg_shard_bounds (C++, pure host): contiguous, covering, balanced by the cost model."""
+    from sparsifyposegraph_b200 import capi, records as R, synth
+    blks = [synth.make_blankets(n, 200, dim=6, variant="ring", seed=n) for n in (3, 5, 9, 16)]
+    rec = np.concatenate([b["records"] for b in blks])
+    rec_off = np.zeros(1, dtype=np.int64)
+    for b in blks:
+        rec_off = np.concatenate([rec_off, b["rec_off"][1:] + rec_off[-1]])
+    nk = R.n_kept_of(rec, rec_off)
+    out_off = R.out_offsets(6, R.ALG_NFR, R.TOPO_TREE, 1.0, nk)
+    opts = capi.make_opts(R.TOPO_TREE, R.LIN_GLOBAL)
+    nb = len(rec_off) - 1
+    nvs = [int(rec[o:o + 1].view(np.int32)[0]) for o in rec_off[:-1]]
+    cost = np.array([1.0 if n <= 2 else (1.6 if n == 3 else 3.4 * (n - 2.6)) for n in nvs])   # NFR tree model, spg_comm.cu
     for world in (1, 2, 4, 8):
-        b = distributed.shard_bounds(rec_off, world)
-        assert b[0] == 0 and b[-1] == 1000 and all(x <= y for x, y in zip(b, b[1:]))
-    assert distributed.shard_bounds(np.array([0]), 4) == [0, 0, 0, 0, 0]
-    b = distributed.shard_bounds(np.array([0, 10, 20]), 8)   # fewer blankets than ranks: empty shards allowed
-    assert b[0] == 0 and b[-1] == 2
+        b = capi.shard_bounds(6, R.ALG_NFR, opts, rec, rec_off, out_off, world)
+        assert b[0] == 0 and b[-1] == nb and all(x <= y for x, y in zip(b, b[1:]))
+        loads = np.array([cost[b[r]:b[r + 1]].sum() for r in range(world)])
+        assert loads.max() <= loads.mean() * 1.02 + cost.max()
+    # fewer blankets than ranks: empty shards allowed
+    b = capi.shard_bounds(6, R.ALG_NFR, opts, rec[:rec_off[2]], rec_off[:3], out_off[:3], 8)
+    assert b[0] == 0 and b[-1] == 2 and all(x <= y for x, y in zip(b, b[1:]))
 
 
 def test_two_rank_sharded_removal_matches_sequential_oracle(oracle):
