@@ -339,9 +339,7 @@ def main():
         nk_all = np.concatenate([np.full(b["B"], b["n"] - 2) for b in sweep])
         n_ok = int(((hdr[:, 0] == 0) & (hdr[:, 1] == nk_all)).sum())
     if world > 1:
-        sl = slice(shard_info["first_blanket"], shard_info["end_blanket"])
-        h2d_bytes = int(rec_off_all[sl.stop] - rec_off_all[sl.start]) * 8 + 2 * (total_blankets + 1) * 8 + (sl.stop - sl.start) * 4
-        d2h_bytes = out_words * 8 if rank == 0 else int(out_off_all[sl.stop] - out_off_all[sl.start]) * 8
+        h2d_bytes, d2h_bytes = shard_info["h2d_bytes"], shard_info["d2h_bytes"]  # this rank's; summed over ranks below
 
     # ---- reduce over ranks ----------------------------------------------------------------------------
     gather = None

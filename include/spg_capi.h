@@ -245,18 +245,21 @@ spg_status spg_shard_bounds(const spg_round_in *in, int32_t nranks, int32_t *bou
 
 typedef struct {
     int32_t nranks, rank;
-    int32_t first_blanket, end_blanket; /* this rank's shard                                        */
+    int32_t n_blankets_mine, reserved0; /* blankets this rank ran                                   */
     int32_t steps, reserved;            /* pipeline steps (H2D | kernels | gather | D2H overlap)    */
     double kernel_ms;                   /* first to last kernel of this rank                        */
     double gather_window_ms;            /* first to last gather on the gather stream (overlaps)     */
     int64_t gather_bytes;               /* bytes this rank sent or received over NVLink             */
+    int64_t h2d_bytes, d2h_bytes;       /* bytes this rank copied host -> device / device -> host   */
 } spg_shard_info;
 
 /*
  * spg_remove_round over all ranks of the communicator. Collective: every rank calls it with the SAME round (host
- * buffers; a rank only reads the records of its own shard, and the headers of the others for the balance).
+ * buffers; a rank only reads the records of its own blankets, and the headers of the others for the balance).
+ * The round is cut into pipeline steps of about equal bytes and every step is split over the ranks by modelled
+ * cost, so each rank moves 1/nranks of the bytes and does 1/nranks of the work of every step.
  * root < 0: every rank gets the complete output (replicated graphs, all-gather); root >= 0: only that rank does
- * (the others get their own shard's records). info may be NULL.
+ * (the others get the records of their own blankets). info may be NULL.
  */
 spg_status spg_remove_round_sharded(spg_ctx *ctx, const spg_round_in *in, spg_round_out *out, int32_t root,
                                     spg_shard_info *info);

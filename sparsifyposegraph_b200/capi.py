@@ -51,9 +51,9 @@ class MarginalizeStats(C.Structure):
 
 
 class ShardInfo(C.Structure):
-    _fields_ = [("nranks", C.c_int32), ("rank", C.c_int32), ("first_blanket", C.c_int32), ("end_blanket", C.c_int32),
+    _fields_ = [("nranks", C.c_int32), ("rank", C.c_int32), ("n_blankets_mine", C.c_int32), ("reserved0", C.c_int32),
                 ("steps", C.c_int32), ("reserved", C.c_int32), ("kernel_ms", C.c_double), ("gather_window_ms", C.c_double),
-                ("gather_bytes", C.c_int64)]
+                ("gather_bytes", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
 
 
 COMM_ID_BYTES = 128

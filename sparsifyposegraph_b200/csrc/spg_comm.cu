@@ -87,6 +87,24 @@ inline double blanket_cost(int algorithm, int topology, int nv, int ne) {
     return 40.0 + 12.0 * ne + (double) nv * nv * (nv + 6.0);
 }
 
+// contiguous split of blankets [b0, b1) into R parts of about equal modelled cost: bounds[0..R]
+void cost_bounds(const spg_round_in *in, int b0, int b1, int R, int32_t *bounds) {
+    const int nb = b1 - b0;
+    std::vector<double> cum((size_t) nb + 1, 0.0);
+    for(int b = 0; b < nb; b++) {
+        const int32_t *h = reinterpret_cast<const int32_t *>(in->records + in->rec_off[b0 + b]);
+        cum[b + 1] = cum[b] + blanket_cost(in->algorithm, in->opts.topology, h[0], h[2]);
+    }
+    bounds[0] = b0;
+    for(int r = 1; r < R; r++) {
+        const double goal = cum[nb] * r / R;
+        int b = (int) (std::lower_bound(cum.begin(), cum.end(), goal) - cum.begin());
+        if(b > 0 && goal - cum[b - 1] < cum[b] - goal) b--; // nearer boundary
+        bounds[r] = std::max(bounds[r - 1], b0 + std::min(b, nb));
+    }
+    bounds[R] = b1;
+}
+
 spg_status ensure_comm_stream(spg_ctx *ctx, int n_events) {
     if(!ctx->s_comm) SPG_CUDA(cudaStreamCreateWithFlags(&ctx->s_comm, cudaStreamNonBlocking));
     if(!ctx->ev_g0) {
@@ -204,20 +222,7 @@ int32_t spg_comm_nccl_version(void) {
 // pure host code (CPU tests cover it): contiguous shards of the round, balanced by the per-blanket cost model
 spg_status spg_shard_bounds(const spg_round_in *in, int32_t nranks, int32_t *bounds) {
     if(!in || !bounds || nranks < 1 || in->n_blankets < 0) return SPG_ERR_INVALID;
-    const int nb = in->n_blankets;
-    std::vector<double> cum((size_t) nb + 1, 0.0);
-    for(int b = 0; b < nb; b++) {
-        const int32_t *h = reinterpret_cast<const int32_t *>(in->records + in->rec_off[b]);
-        cum[b + 1] = cum[b] + blanket_cost(in->algorithm, in->opts.topology, h[0], h[2]);
-    }
-    bounds[0] = 0;
-    for(int r = 1; r < nranks; r++) {
-        const double goal = cum[nb] * r / nranks;
-        int b = (int) (std::lower_bound(cum.begin(), cum.end(), goal) - cum.begin());
-        if(b > 0 && goal - cum[b - 1] < cum[b] - goal) b--; // nearer boundary
-        bounds[r] = std::max(bounds[r - 1], std::min(b, nb));
-    }
-    bounds[nranks] = nb;
+    cost_bounds(in, 0, in->n_blankets, nranks, bounds);
     return SPG_OK;
 }
 
@@ -281,13 +286,22 @@ spg_status spg_remove_round_sharded(spg_ctx *ctx, const spg_round_in *in, spg_ro
     SPG_CUDA(cudaSetDevice(ctx->device));
 
     // ---- every rank derives the same plan from the (replicated) round description --------------------------------
-    std::vector<int32_t> bounds((size_t) R + 1);
-    spg_status st = spg_shard_bounds(in, R, bounds.data());
-    if(st != SPG_OK) return st;
+    // Step-major: the round is cut into `steps` contiguous chunks of about equal bytes, and every chunk is split over
+    // the ranks by modelled cost. Every rank then moves 1/R of the bytes and does 1/R of the work of every chunk,
+    // whatever the order of blanket sizes inside the round, and step s of all ranks is one gather.
     const int64_t total_bytes = (in->rec_off[nb] + in->out_off[nb]) * 8;
-    const int steps = (int) std::max<int64_t>(1, std::min<int64_t>(16, total_bytes / R / std::max<int64_t>(ctx->chunk_bytes, 4096)));
-    std::vector<std::vector<int>> cb((size_t) R); // cb[r][s]: rank r's blankets of step s
-    for(int r = 0; r < R; r++) spg_split_by_bytes(in, bounds[r], bounds[r + 1], steps, cb[r]);
+    const int steps = (int) std::max<int64_t>(1, std::min<int64_t>(32, total_bytes / std::max<int64_t>(ctx->chunk_bytes, 4096)));
+    std::vector<int> gcb;
+    spg_split_by_bytes(in, 0, nb, steps, gcb);
+    std::vector<int32_t> sb((size_t) R + 1);
+    std::vector<std::vector<int32_t>> lo((size_t) steps, std::vector<int32_t>((size_t) R + 1)); // lo[s][r] .. lo[s][r+1]: rank r's blankets of step s
+    int mine = 0;
+    for(int s2 = 0; s2 < steps; s2++) {
+        cost_bounds(in, gcb[s2], gcb[s2 + 1], R, sb.data());
+        lo[s2] = sb;
+        mine += sb[me + 1] - sb[me];
+    }
+    spg_status st = SPG_OK;
     st = ensure_comm_stream(ctx, steps);
     if(st != SPG_OK) return st;
 
@@ -296,11 +310,11 @@ spg_status spg_remove_round_sharded(spg_ctx *ctx, const spg_round_in *in, spg_ro
     if(st != SPG_OK) return st;
     const bool receiver = root < 0 || root == me;
     uint64_t *d_out = reinterpret_cast<uint64_t *>(ctx->d_out.p);
-    int64_t moved = 0;
+    int64_t moved = 0, h2d = 2 * (int64_t) (nb + 1) * 8, d2h = 0;
     std::vector<int64_t> w0((size_t) R), cnt((size_t) R);
     SPG_CUDA(cudaEventRecord(ctx->ev_g0, ctx->s_comm));
     for(int s = 0; s < steps; s++) {
-        const int b0 = cb[me][s], b1 = cb[me][s + 1];
+        const int b0 = lo[s][me], b1 = lo[s][me + 1];
         bool launched = false;
         if(b1 > b0) {
             st = spg_round_enqueue_chunk(ctx, in, run, b0, b1, s);
@@ -311,8 +325,8 @@ spg_status spg_remove_round_sharded(spg_ctx *ctx, const spg_round_in *in, spg_ro
             // the slices of step s of all ranks are disjoint word ranges of the one output buffer
             if(launched) SPG_CUDA(cudaStreamWaitEvent(ctx->s_comm, ctx->ev_pool[2 * s + 1], 0));
             for(int r = 0; r < R; r++) {
-                w0[r] = in->out_off[cb[r][s]];
-                cnt[r] = in->out_off[cb[r][s + 1]] - w0[r];
+                w0[r] = in->out_off[lo[s][r]];
+                cnt[r] = in->out_off[lo[s][r + 1]] - w0[r];
             }
             st = gather_outputs(ctx, d_out, w0.data(), cnt.data(), root, &moved);
             if(st != SPG_OK) return st;
@@ -321,14 +335,17 @@ spg_status spg_remove_round_sharded(spg_ctx *ctx, const spg_round_in *in, spg_ro
         } else if(launched) {
             SPG_CUDA(cudaStreamWaitEvent(ctx->s_out, ctx->ev_pool[2 * s + 1], 0));
         }
-        // ---- D2H: a receiver reads step s of every rank, the others only their own (they keep a copy of what they
-        // produced; the graph-holding root gets everything)
-        for(int r = 0; r < R; r++) {
-            if(!receiver && r != me) continue;
-            const int64_t o0 = in->out_off[cb[r][s]], oc = in->out_off[cb[r][s + 1]] - o0;
-            if(oc <= 0) continue;
-            if(!receiver) SPG_CUDA(cudaStreamWaitEvent(ctx->s_out, ctx->ev_pool[2 * s + 1], 0));
-            SPG_CUDA(cudaMemcpyAsync(out->out + o0, d_out + o0, (size_t) oc * 8, cudaMemcpyDeviceToHost, ctx->s_out));
+        // ---- D2H: a receiver reads the whole step (the slices of the ranks are adjacent), the others only their own
+        // slice (they keep a copy of what they produced; the graph-holding root gets everything)
+        {
+            const int r0 = receiver ? 0 : me, r1 = receiver ? R : me + 1;
+            const int64_t o0 = in->out_off[lo[s][r0]], oc = in->out_off[lo[s][r1]] - o0;
+            if(oc > 0) {
+                if(!receiver) SPG_CUDA(cudaStreamWaitEvent(ctx->s_out, ctx->ev_pool[2 * s + 1], 0));
+                SPG_CUDA(cudaMemcpyAsync(out->out + o0, d_out + o0, (size_t) oc * 8, cudaMemcpyDeviceToHost, ctx->s_out));
+                d2h += oc * 8;
+            }
+            h2d += (in->rec_off[b1] - in->rec_off[b0]) * 8 + (int64_t) (b1 - b0) * 4;
         }
     }
     SPG_CUDA(cudaEventRecord(ctx->ev_g1, ctx->s_comm));
@@ -342,12 +359,14 @@ spg_status spg_remove_round_sharded(spg_ctx *ctx, const spg_round_in *in, spg_ro
     if(info) {
         info->nranks = R;
         info->rank = me;
-        info->first_blanket = bounds[me];
-        info->end_blanket = bounds[me + 1];
+        info->n_blankets_mine = mine;
+        info->reserved0 = 0;
         info->steps = steps;
         info->kernel_ms = ctx->last_ms;
         info->gather_window_ms = gms;
         info->gather_bytes = moved;
+        info->h2d_bytes = h2d;
+        info->d2h_bytes = d2h;
     }
     return SPG_OK;
 }

@@ -10,6 +10,8 @@
 #include <thread>
 #include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <fstream>
@@ -581,10 +583,22 @@ spg_round_in VertexRemover::roundDescriptor() const {
     return rin;
 }
 
+namespace {
+struct HostProf {
+    double stale = 0, extract = 0, select = 0, pack = 0, apply = 0;
+    bool on = getenv("SPG_HOST_PROF") != nullptr;
+    ~HostProf() {
+        if(on) fprintf(stderr, "[spg host] stale-check %.3f s, extract %.3f s, select %.3f s, pack %.3f s, splice %.3f s\n", stale, extract, select, pack, apply);
+    }
+} g_prof;
+inline double nowS() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+} // namespace
+
 // Select and pack the next wavefront round (empty round: nothing left).
 spg_status VertexRemover::planRound() {
     _round = Round();
     if(_remaining == 0) return SPG_OK;
+    double tp0 = nowS();
     const int dim = _graph->dim;
     const std::vector<int> &toRemove = _pending;
     {
@@ -621,6 +635,7 @@ spg_status VertexRemover::planRound() {
                 }
                 if(stale) todo.push_back((int) i);
             }
+            g_prof.stale += nowS() - tp0; tp0 = nowS();
             std::atomic<int> bad(-1);
             auto work = [&](size_t b0, size_t b1) {
                 for(size_t q = b0; q < b1; q++) {
@@ -649,6 +664,7 @@ spg_status VertexRemover::planRound() {
                 error = "vertex " + std::to_string(toRemove[bad.load()]) + " has no edges";
                 return SPG_ERR_INVALID;
             }
+            g_prof.extract += nowS() - tp0; tp0 = nowS();
         }
         for(size_t i = 0; i < toRemove.size(); i++) {
             if(_done[i]) continue;
@@ -693,6 +709,7 @@ spg_status VertexRemover::planRound() {
             if(select) units.push_back(u);
         }
         for(int xi : touched) { _touchHead[xi] = -1; _removedBy[xi] = -1; }
+        g_prof.select += nowS() - tp0; tp0 = nowS();
         if(units.empty()) return SPG_OK;
     }
     // ---- pack ----------------------------------------------------------------------------
@@ -723,6 +740,7 @@ spg_status VertexRemover::planRound() {
                                                                              (int) u.kept.size()));
         stats.max_blanket_vertices = std::max<int>(stats.max_blanket_vertices, (int) (u.removed.size() + u.kept.size()));
     }
+    g_prof.pack += nowS() - tp0;
     _round.algorithm = tp->algorithm();
     _round.poseOnly = poseOnly;
     if(_round.algorithm == SPG_ALG_GLC) {
@@ -740,6 +758,7 @@ spg_status VertexRemover::planRound() {
 // src/vertex_remover.cpp:500-546).
 void VertexRemover::applyRound(const uint64_t *out) {
     const int dim = _graph->dim, P = _graph->poseWords(), algorithm = _round.algorithm;
+    const double ta0 = nowS();
     for(size_t ui = 0; ui < _round.units.size(); ui++) {
         const RemovalUnit &u = _round.units[ui];
         const uint64_t *o = out + _round.outOff[ui];
@@ -806,6 +825,7 @@ void VertexRemover::applyRound(const uint64_t *out) {
     stats.n_rounds++;
     stats.max_round_width = std::max<int>(stats.max_round_width, (int) _round.units.size());
     _round.units.clear();
+    g_prof.apply += nowS() - ta0;
 }
 
 // ---- computeSubstituteEdge (src/compute_substitute_edge.cpp:13-96) ---------------------------------

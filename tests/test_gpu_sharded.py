@@ -31,7 +31,8 @@ def test_sharded_round_single_rank_equals_plain_round(monkeypatch):
     for root in (-1, 0):
         got, info = ctx.remove_round_sharded(6, R.ALG_NFR, opts, rec, rec_off, out_off, root=root)
         assert np.array_equal(got, ref)
-        assert (info["first_blanket"], info["end_blanket"]) == (0, len(rec_off) - 1) and info["steps"] >= 2
+        assert info["n_blankets_mine"] == len(rec_off) - 1 and info["steps"] >= 2
+        assert info["d2h_bytes"] == int(out_off[-1]) * 8
         assert info["gather_bytes"] == 0
     ctx.close()
 
