@@ -16,7 +16,10 @@
 #include <deque>
 #include <fstream>
 #include <limits>
+#include <mutex>
 #include <sstream>
+
+#include <cuda_runtime.h>
 
 #include "../../include/spg_record.h"
 
@@ -112,18 +115,16 @@ std::vector<int> globalDecimate(int last, int endvert, const DecimateOptions &op
 
 // ---- Graph -------------------------------------------------------------------------------------------
 bool Graph::hasVertex(int id) const {
-    auto it = index.find(id);
-    return it != index.end() && verts[it->second].alive;
+    const int i = indexOf(id);
+    return i >= 0 && verts[i].alive;
 }
 GraphVertex *Graph::vertex(int id) {
-    auto it = index.find(id);
-    if(it == index.end() || !verts[it->second].alive) return nullptr;
-    return &verts[it->second];
+    const int i = indexOf(id);
+    return (i < 0 || !verts[i].alive) ? nullptr : &verts[i];
 }
 const GraphVertex *Graph::vertex(int id) const {
-    auto it = index.find(id);
-    if(it == index.end() || !verts[it->second].alive) return nullptr;
-    return &verts[it->second];
+    const int i = indexOf(id);
+    return (i < 0 || !verts[i].alive) ? nullptr : &verts[i];
 }
 bool Graph::addVertex(int id, const double *pose) {
     if(hasVertex(id)) return false;
@@ -132,17 +133,33 @@ bool Graph::addVertex(int id, const double *pose) {
     std::memcpy(v.pose, pose, sizeof(double) * poseWords());
     if(dim == 3) v.pose[2] = normalizeTheta(v.pose[2]);
     else qnorm(v.pose + 3);
-    index[id] = (int) verts.size();
+    if((unsigned) id < (1u << 26)) {
+        if((size_t) id >= dense.size()) dense.resize(std::max<size_t>((size_t) id + 1, dense.size() * 2), -1);
+        dense[id] = (int) verts.size();
+    } else {
+        sparse[id] = (int) verts.size();
+    }
     verts.push_back(v);
     aliveVertices++;
     return true;
 }
-int Graph::addEdge(const GraphEdge &e) {
-    int ei = (int) edges.size();
-    edges.push_back(e);
-    edges.back().alive = true;
-    for(int id : e.v) verts[index[id]].edges.push_back(ei);
+int Graph::addEdge(GraphEdge &&e) {
+    const int ei = (int) edges.size();
+    const int n = (int) e.v.size();
+    e.alive = true;
+    e.vx0 = n > 0 ? indexOf(e.v[0]) : -1;
+    e.vx1 = n > 1 ? indexOf(e.v[1]) : -1;
+    e.vxn.clear();
+    if(n > 2)
+        for(int id : e.v) e.vxn.push_back(indexOf(id));
+    for(int q = 0; q < n; q++) {
+        GraphVertex &gv = verts[e.vx(q)];
+        gv.edges.push_back(ei);
+        gv.peer.push_back(n == 2 ? ((e.vx(1 - q) << 1) | (q == 0)) : -1);
+    }
+    edges.push_back(std::move(e));
     aliveEdges++;
+    version++;
     return ei;
 }
 int Graph::addPoseEdge(int from, int to, const double *meas, const double *info) {
@@ -151,25 +168,31 @@ int Graph::addPoseEdge(int from, int to, const double *meas, const double *info)
     e.kind = SPG_EDGE_POSE;
     e.v = {from, to};
     e.rows = dim;
-    e.meas.assign(meas, meas + poseWords());
-    if(dim == 3) e.meas[2] = normalizeTheta(e.meas[2]);
-    else qnorm(e.meas.data() + 3);
-    e.info.assign(info, info + dim * dim);
+    e.setPayload(meas, poseWords(), info, dim * dim);
+    if(dim == 3) e.meas()[2] = normalizeTheta(e.meas()[2]);
+    else qnorm(e.meas() + 3);
     e.uidMajor = -1;
     e.uidMinor = fileEdges++;
-    return addEdge(e);
+    return addEdge(std::move(e));
 }
 void Graph::removeEdge(int ei) {
     GraphEdge &e = edges[ei];
     if(!e.alive) return;
     e.alive = false;
-    for(int id : e.v) {
-        std::vector<int> &ve = verts[index[id]].edges;
+    for(int q = 0, n = e.nv(); q < n; q++) {
+        GraphVertex &gv = verts[e.vx(q)];
+        std::vector<int> &ve = gv.edges;
         auto it = std::find(ve.begin(), ve.end(), ei);
-        if(it != ve.end()) { *it = ve.back(); ve.pop_back(); }
+        if(it != ve.end()) {
+            gv.peer[it - ve.begin()] = gv.peer.back();
+            gv.peer.pop_back();
+            *it = ve.back();
+            ve.pop_back();
+        }
     }
-    std::vector<double>().swap(e.info);
+    std::vector<double>().swap(e.payload);
     aliveEdges--;
+    version++;
 }
 void Graph::removeVertex(int id) {
     GraphVertex *v = vertex(id);
@@ -319,50 +342,80 @@ bool VertexRemover::buildUnit(int root, int listIndex, const std::set<int> &toRe
     if(_opts.topology == SparsityOptions::Dense || _opts.topology == SparsityOptions::CliqueyDense) {
         vmarkov = extendedMarkovBlanketVertices(root, toRemoveSet, u.removed);
     } else {
-        // single removal (Tree / Subgraph / CliqueySubgraph): the same sets as markovBlanketVertices / -Edges with
-        // sorted vectors instead of node-based sets — this runs once per pending vertex and round
-        const GraphVertex *rv = _graph->vertex(root);
-        std::vector<int> &mb = vmarkov;
-        mb.push_back(root);
-        if(rv)
-            for(int ei : rv->edges)
-                for(int id : _graph->edges[ei].v) mb.push_back(id);
-        std::sort(mb.begin(), mb.end());
-        mb.erase(std::unique(mb.begin(), mb.end()), mb.end());
-        u.removed.push_back(root);
-        for(int id : mb)
-            if(id != root) u.kept.push_back(id);
-        std::vector<int> &es = u.edges;
-        for(int id : mb) {
-            const GraphVertex *v = _graph->vertex(id);
-            if(!v) continue;
-            for(int ei : v->edges) {
-                const GraphEdge &e = _graph->edges[ei];
-                bool is_markov = true, found_hub = false;
-                for(int x : e.v) {
-                    if(!std::binary_search(mb.begin(), mb.end(), x)) { is_markov = false; break; }
-                    if(x == root) found_hub = true;
+        // single removal (Tree / Subgraph / CliqueySubgraph): the same sets as markovBlanketVertices / -Edges, walked
+        // by vertex index with a per-thread stamp array for membership — this runs once per pending vertex and round
+        static thread_local std::vector<unsigned> mark;
+        static thread_local unsigned token = 0;
+        static thread_local std::vector<std::pair<int, int>> mb;                    // (id, vertex index) of the blanket
+        static thread_local std::vector<std::pair<unsigned long long, int>> keyed;  // (canonical order key, edge)
+        const std::vector<GraphVertex> &V = _graph->verts;
+        const std::vector<GraphEdge> &E = _graph->edges;
+        if(mark.size() < V.size()) mark.resize(V.size() + V.size() / 4 + 64, 0);
+        if(++token == 0) { std::fill(mark.begin(), mark.end(), 0u); token = 1; }
+        const int ri = _graph->indexOf(root);
+        mb.clear();
+        keyed.clear();
+        if(ri >= 0 && V[ri].alive) {
+            mark[ri] = token;
+            mb.emplace_back(root, ri);
+            const GraphVertex &rv = V[ri];
+            for(size_t k = 0; k < rv.edges.size(); k++) {
+                const int p = rv.peer[k];
+                if(p >= 0) {
+                    const int xi = p >> 1;
+                    if(mark[xi] != token) { mark[xi] = token; mb.emplace_back(V[xi].id, xi); }
+                    continue;
                 }
-                if(is_markov && (_opts.includeIntraClique || found_hub)) es.push_back(ei);
+                const GraphEdge &e = E[rv.edges[k]];
+                for(int q = 0, n = e.nv(); q < n; q++) {
+                    const int xi = e.vx(q);
+                    if(mark[xi] != token) { mark[xi] = token; mb.emplace_back(V[xi].id, xi); }
+                }
+            }
+        } else {
+            mb.emplace_back(root, -1);
+        }
+        std::sort(mb.begin(), mb.end());
+        u.removed.push_back(root);
+        for(const auto &pr : mb)
+            if(pr.first != root) { u.kept.push_back(pr.first); u.kidx.push_back(pr.second); }
+        if(ri >= 0) u.ridx.push_back(ri);
+        for(const auto &pr : mb) {
+            const int xi = pr.second;
+            if(xi < 0 || !V[xi].alive) continue;
+            const GraphVertex &gv = V[xi];
+            for(size_t k = 0; k < gv.edges.size(); k++) {
+                const int ei = gv.edges[k], p = gv.peer[k];
+                if(p >= 0) { // two-vertex edge: decided from the adjacency entry alone
+                    if(!(p & 1)) continue; // met once per endpoint: taken at its first one
+                    const int yi = p >> 1;
+                    if(mark[yi] != token) continue;
+                    if(_opts.includeIntraClique || xi == ri || yi == ri) keyed.emplace_back(E[ei].uidKey(), ei);
+                    continue;
+                }
+                const GraphEdge &e = E[ei];
+                const int n = e.nv();
+                if(e.vx(0) != xi) continue; // every blanket edge is met once per vertex: take it at its first one
+                bool is_markov = true, found_hub = false;
+                for(int q = 0; q < n; q++) {
+                    const int yi = e.vx(q);
+                    if(mark[yi] != token) { is_markov = false; break; }
+                    if(yi == ri) found_hub = true;
+                }
+                if(is_markov && (_opts.includeIntraClique || found_hub)) keyed.emplace_back(e.uidKey(), ei);
             }
         }
-        std::sort(es.begin(), es.end(), [&](int a, int b) {
-            const GraphEdge &x = _graph->edges[a], &y = _graph->edges[b];
-            if(x.uidMajor != y.uidMajor) return x.uidMajor < y.uidMajor;
-            if(x.uidMinor != y.uidMinor) return x.uidMinor < y.uidMinor;
-            return a < b;
-        });
-        es.erase(std::unique(es.begin(), es.end()), es.end());
-        for(int id : u.removed) u.ridx.push_back(_graph->index.at(id));
-        for(int id : u.kept) u.kidx.push_back(_graph->index.at(id));
-        return !es.empty();
+        std::sort(keyed.begin(), keyed.end());
+        keyed.erase(std::unique(keyed.begin(), keyed.end()), keyed.end());
+        for(const auto &ke : keyed) u.edges.push_back(ke.second);
+        return !u.edges.empty();
     }
     std::set<int> rem(u.removed.begin(), u.removed.end());
     for(int id : vmarkov)
         if(!rem.count(id)) u.kept.push_back(id);
     u.edges = markovBlanketEdges(vmarkov, u.removed);
-    for(int id : u.removed) u.ridx.push_back(_graph->index.at(id));
-    for(int id : u.kept) u.kidx.push_back(_graph->index.at(id));
+    for(int id : u.removed) u.ridx.push_back(_graph->indexOf(id));
+    for(int id : u.kept) u.kidx.push_back(_graph->indexOf(id));
     return !u.edges.empty();
 }
 
@@ -375,17 +428,40 @@ TopologyProvider *VertexRemover::chooseTopologyProvider(const RemovalUnit &u) co
     return nullptr;
 }
 
-// buildSubgraph (src/vertex_remover.cpp:285-392) + record packing. Returns false when the blanket
-// needs the Local non-star linearisation point (g2o LM on the subgraph; not part of this path).
-bool VertexRemover::packUnit(const RemovalUnit &u, std::vector<uint64_t> &rec) const {
+// per-thread map vertex index -> local index inside the blanket being packed (entries of other blankets are stale
+// but never read: every endpoint of a blanket edge is a blanket vertex)
+static thread_local std::vector<int> t_local;
+
+// record size of a unit, 0 when the blanket needs the Local non-star linearisation point
+int64_t VertexRemover::unitWords(const RemovalUnit &u) const {
+    const int dim = _graph->dim;
+    const int nv = (int) (u.removed.size() + u.kept.size()), ne = (int) u.edges.size();
+    int64_t words = spgr_record_fixed_words(dim, nv, ne);
+    for(int ei : u.edges) {
+        const GraphEdge &e = _graph->edges[ei];
+        words += spgr_edge_words(dim, e.kind, e.nv(), e.rows);
+    }
+    return (words + 1) & ~(int64_t) 1;
+}
+
+// buildSubgraph (src/vertex_remover.cpp:285-392) + record packing into rec[0, words). Returns false when the
+// blanket needs the Local non-star linearisation point (g2o LM on the subgraph; not part of this path).
+bool VertexRemover::packUnit(const RemovalUnit &u, uint64_t *rec, int64_t words) const {
     const int dim = _graph->dim, P = _graph->poseWords();
     const int nrem = (int) u.removed.size(), nv = nrem + (int) u.kept.size(), ne = (int) u.edges.size();
-    std::unordered_map<int, int> local;
-    std::vector<int> ids;
-    for(int id : u.removed) { local[id] = (int) ids.size(); ids.push_back(id); }
-    for(int id : u.kept) { local[id] = (int) ids.size(); ids.push_back(id); }
-    std::vector<double> poses((size_t) nv * P);
-    for(int i = 0; i < nv; i++) std::memcpy(&poses[(size_t) i * P], _graph->vertex(ids[i])->pose, sizeof(double) * P);
+    const std::vector<GraphVertex> &V = _graph->verts;
+    if(t_local.size() < V.size()) t_local.resize(V.size() + V.size() / 4 + 64, -1);
+    std::memset(rec, 0, (size_t) words * 8);
+    int32_t *h = reinterpret_cast<int32_t *>(rec);
+    h[0] = nv; h[1] = nrem; h[2] = ne; h[3] = dim; h[4] = (int32_t) words; h[5] = 0; h[6] = u.listIndex; h[7] = 0;
+    int32_t *rid = reinterpret_cast<int32_t *>(rec + spgr_ids_off());
+    double *poses = reinterpret_cast<double *>(rec + spgr_poses_off(nv));
+    for(int i = 0; i < nv; i++) {
+        const int xi = i < nrem ? u.ridx[i] : u.kidx[i - nrem];
+        t_local[xi] = i;
+        rid[i] = V[xi].id;
+        std::memcpy(poses + (size_t) i * P, V[xi].pose, sizeof(double) * P);
+    }
 
     if(_opts.linPoint == SparsityOptions::Local) {
         // closed-form estimate only for star-shaped blankets (:304-342)
@@ -393,8 +469,8 @@ bool VertexRemover::packUnit(const RemovalUnit &u, std::vector<uint64_t> &rec) c
         std::vector<int> nconn(nv, 0);
         for(int ei : u.edges) {
             const GraphEdge &e = _graph->edges[ei];
-            for(int id : e.v) {
-                int li = local[id];
+            for(int q = 0, n = e.nv(); q < n; q++) {
+                const int li = t_local[e.vx(q)];
                 if(li != 0) {
                     nconn[li]++;
                     closedForm = closedForm && (e.kind != SPG_EDGE_GLC); // GLCEdge::initialEstimatePossible == -1
@@ -420,57 +496,93 @@ bool VertexRemover::packUnit(const RemovalUnit &u, std::vector<uint64_t> &rec) c
         for(int ei : u.edges) {
             const GraphEdge &e = _graph->edges[ei];
             if(e.kind == SPG_EDGE_POSE) {
-                apply(local[e.v[0]], local[e.v[1]], e.meas.data());
+                apply(t_local[e.vx(0)], t_local[e.vx(1)], e.meas());
             } else if(e.kind == SPG_EDGE_MULTI) {
-                for(size_t vi = 0; vi < e.v.size(); vi++)
+                for(int vi = 0; vi < e.nv(); vi++)
                     for(size_t m = 0; m < e.pairs.size() / 2; m++)
-                        if(e.pairs[2 * m] == (int) vi || e.pairs[2 * m + 1] == (int) vi)
-                            apply(local[e.v[e.pairs[2 * m]]], local[e.v[e.pairs[2 * m + 1]]], &e.meas[m * P]);
+                        if(e.pairs[2 * m] == vi || e.pairs[2 * m + 1] == vi)
+                            apply(t_local[e.vx(e.pairs[2 * m])], t_local[e.vx(e.pairs[2 * m + 1])], e.meas() + m * P);
             }
         }
     }
 
-    int64_t words = spgr_record_fixed_words(dim, nv, ne);
-    std::vector<int64_t> eoff(ne);
+    int32_t *etab = reinterpret_cast<int32_t *>(rec + spgr_edgetab_off(dim, nv));
+    int64_t eoff = spgr_record_fixed_words(dim, nv, ne);
     for(int i = 0; i < ne; i++) {
         const GraphEdge &e = _graph->edges[u.edges[i]];
-        eoff[i] = words;
-        words += spgr_edge_words(dim, e.kind, (int) e.v.size(), e.rows);
-    }
-    words = (words + 1) & ~(int64_t) 1;
-    rec.assign((size_t) words, 0);
-    int32_t *h = reinterpret_cast<int32_t *>(rec.data());
-    h[0] = nv; h[1] = nrem; h[2] = ne; h[3] = dim; h[4] = (int32_t) words; h[5] = 0; h[6] = u.listIndex; h[7] = 0;
-    int32_t *rid = reinterpret_cast<int32_t *>(rec.data() + spgr_ids_off());
-    for(int i = 0; i < nv; i++) rid[i] = ids[i];
-    std::memcpy(rec.data() + spgr_poses_off(nv), poses.data(), sizeof(double) * nv * P);
-    int32_t *etab = reinterpret_cast<int32_t *>(rec.data() + spgr_edgetab_off(dim, nv));
-    for(int i = 0; i < ne; i++) {
-        const GraphEdge &e = _graph->edges[u.edges[i]];
-        etab[i] = (int32_t) eoff[i];
-        uint64_t *ew = rec.data() + eoff[i];
+        etab[i] = (int32_t) eoff;
+        uint64_t *ew = rec + eoff;
         int32_t *eh = reinterpret_cast<int32_t *>(ew);
-        const int nve = (int) e.v.size();
+        const int nve = e.nv();
         eh[0] = e.kind; eh[1] = nve; eh[2] = e.rows; eh[3] = 0;
         int32_t *vi = reinterpret_cast<int32_t *>(ew + 2);
-        for(int q = 0; q < nve; q++) vi[q] = local[e.v[q]];
+        for(int q = 0; q < nve; q++) vi[q] = t_local[e.vx(q)];
         double *pl = reinterpret_cast<double *>(ew + 2 + spgr_pad2(nve));
         if(e.kind == SPG_EDGE_POSE) {
-            std::memcpy(pl, e.meas.data(), sizeof(double) * P);
-            std::memcpy(pl + P, e.info.data(), sizeof(double) * dim * dim);
+            std::memcpy(pl, e.meas(), sizeof(double) * P);
+            std::memcpy(pl + P, e.info(), sizeof(double) * dim * dim);
         } else if(e.kind == SPG_EDGE_GLC) {
-            std::memcpy(pl, e.meas.data(), sizeof(double) * dim * nve);
-            std::memcpy(pl + dim * nve, e.info.data(), sizeof(double) * e.rows * dim * nve);
+            std::memcpy(pl, e.meas(), sizeof(double) * dim * nve);
+            std::memcpy(pl + dim * nve, e.info(), sizeof(double) * e.rows * dim * nve);
         } else {
             const int nm = e.rows / dim;
             int32_t *pr = reinterpret_cast<int32_t *>(ew + 2 + spgr_pad2(nve));
             for(int q = 0; q < 2 * nm; q++) pr[q] = e.pairs[q];
             double *pm = reinterpret_cast<double *>(ew + 2 + spgr_pad2(nve) + spgr_pad2(2 * nm));
-            std::memcpy(pm, e.meas.data(), sizeof(double) * nm * P);
-            std::memcpy(pm + (size_t) nm * P, e.info.data(), sizeof(double) * e.rows * e.rows);
+            std::memcpy(pm, e.meas(), sizeof(double) * nm * P);
+            std::memcpy(pm + (size_t) nm * P, e.info(), sizeof(double) * e.rows * e.rows);
         }
+        eoff += spgr_edge_words(dim, e.kind, nve, e.rows);
     }
     return true;
+}
+
+// ---- host buffers of a round: page-locked when a CUDA device is there (the copies of spg_remove_round then overlap
+// the kernels), plain memory otherwise (CPU tests drive the planner without a GPU) -------------------------------------
+uint64_t *HostBuf::reserve(size_t words) {
+    if(words <= cap) return p;
+    release();
+    const size_t want = words + words / 4 + 1024;
+    void *q = nullptr;
+    static const bool have_gpu = [] { int n = 0; return cudaGetDeviceCount(&n) == cudaSuccess && n > 0; }();
+    if(have_gpu && cudaHostAlloc(&q, want * 8, cudaHostAllocDefault) == cudaSuccess) pinned = true;
+    else {
+        (void) cudaGetLastError();
+        q = std::malloc(want * 8);
+        pinned = false;
+    }
+    p = static_cast<uint64_t *>(q);
+    cap = p ? want : 0;
+    return p;
+}
+void HostBuf::release() {
+    if(p) {
+        if(pinned) cudaFreeHost(p);
+        else std::free(p);
+    }
+    p = nullptr;
+    cap = 0;
+}
+
+// run fn(begin, end) over [0, n) on up to 16 host threads (one call on this thread when n is small)
+template <class F>
+static void parallelFor(size_t n, size_t min_per_thread, F fn) {
+    static const unsigned max_thr = [] {
+        const char *e = getenv("SPG_HOST_THREADS");
+        return e ? (unsigned) std::max(1, atoi(e)) : std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
+    }();
+    const unsigned nthr = (unsigned) std::min<size_t>(max_thr, std::max<size_t>(1, n / std::max<size_t>(1, min_per_thread)));
+    if(nthr <= 1) {
+        fn((size_t) 0, n);
+        return;
+    }
+    std::vector<std::thread> pool;
+    const size_t chunk = (n + nthr - 1) / nthr;
+    for(unsigned t = 0; t < nthr; t++) {
+        const size_t b0 = std::min(n, t * chunk), b1 = std::min(n, b0 + chunk);
+        if(b0 < b1) pool.emplace_back(fn, b0, b1);
+    }
+    for(auto &th : pool) th.join();
 }
 
 std::vector<int> VertexRemover::remove(int toRemove, spg_status *status) {
@@ -496,12 +608,17 @@ std::vector<int> VertexRemover::remove(const std::vector<int> &toRemove, spg_sta
     while(st == SPG_OK) {
         auto t0 = clk::now();
         st = planRound();
-        if(st != SPG_OK || _round.units.empty()) break;
+        if(st != SPG_OK || _round.sel.empty()) break;
         auto t1 = clk::now();
-        std::vector<uint64_t> out((size_t) _round.outOff.back(), 0);
+        uint64_t *out = _outBuf.reserve((size_t) _round.outOff.back()); // every word is written by the kernels
+        if(!out) {
+            error = "out of host memory";
+            st = SPG_ERR_INVALID;
+            break;
+        }
         spg_round_in rin = roundDescriptor();
         spg_round_out rout{};
-        rout.out = out.data();
+        rout.out = out;
         // a context with a communicator (spg_comm_init) shards every round over its ranks; all ranks hold the same
         // graph, get the complete output (all-gather) and splice the same edges
         st = spg_comm_nranks(_ctx) > 1 ? spg_remove_round_sharded(_ctx, &rin, &rout, -1, nullptr) : spg_remove_round(_ctx, &rin, &rout);
@@ -510,7 +627,7 @@ std::vector<int> VertexRemover::remove(const std::vector<int> &toRemove, spg_sta
             break;
         }
         auto t2 = clk::now();
-        applyRound(out.data());
+        applyRound(out);
         auto t3 = clk::now();
         stats.pack_ms += std::chrono::duration<double, std::milli>(t1 - t0).count();
         stats.gpu_ms += std::chrono::duration<double, std::milli>(t2 - t1).count();
@@ -549,16 +666,23 @@ spg_status VertexRemover::beginRemoval(const std::vector<int> &toRemove) {
             return SPG_ERR_UNSUPPORTED;
         }
     _pending = toRemove;
-    _toRemoveSet = std::set<int>(toRemove.begin(), toRemove.end());
+    _toRemoveSet.clear(); // only the extended (Dense) blankets consult it
+    if(_opts.topology == SparsityOptions::Dense || _opts.topology == SparsityOptions::CliqueyDense)
+        _toRemoveSet = std::set<int>(toRemove.begin(), toRemove.end());
+    _cursor = 0;
+    _leftover.clear();
+    _window = 0;
+    if(const char *e = getenv("SPG_PLAN_WINDOW")) _window = (size_t) std::max(1LL, atoll(e));
     _done.assign(toRemove.size(), 0);
     _remaining = toRemove.size();
-    _round = Round();
+    _round.sel.clear();
+    _round.recOff.assign(1, 0);
+    _round.outOff.assign(1, 0);
     _unitCache.assign(toRemove.size(), RemovalUnit());
     _unitBuilt.assign(toRemove.size(), 0);
     _rootIdx.assign(toRemove.size(), -1);
     for(size_t i = 0; i < toRemove.size(); i++) {
-        auto it = _graph->index.find(toRemove[i]);
-        if(it != _graph->index.end()) _rootIdx[i] = it->second;
+        _rootIdx[i] = _graph->indexOf(toRemove[i]);
     }
     _stamp.assign(_graph->verts.size(), 0);
     _touchHead.assign(_graph->verts.size(), -1);
@@ -576,9 +700,9 @@ spg_round_in VertexRemover::roundDescriptor() const {
     rin.opts.chord_ratio = _opts.chordRatio;
     rin.opts.include_intra_clique = _opts.includeIntraClique;
     rin.opts.flags = _opts.flags | (_round.poseOnly ? SPG_OPT_POSE_EDGES_ONLY : 0);
-    rin.n_blankets = (int32_t) _round.units.size();
+    rin.n_blankets = (int32_t) _round.sel.size();
     rin.rec_off = _round.recOff.data();
-    rin.records = _round.records.data();
+    rin.records = _round.records.p;
     rin.out_off = _round.outOff.data();
     return rin;
 }
@@ -586,94 +710,105 @@ spg_round_in VertexRemover::roundDescriptor() const {
 namespace {
 struct HostProf {
     double stale = 0, extract = 0, select = 0, pack = 0, apply = 0;
+    long long n_extract = 0, n_visit = 0, n_sel = 0;
+    double a1 = 0, a2 = 0, a3 = 0;
     bool on = getenv("SPG_HOST_PROF") != nullptr;
     ~HostProf() {
-        if(on) fprintf(stderr, "[spg host] stale-check %.3f s, extract %.3f s, select %.3f s, pack %.3f s, splice %.3f s\n", stale, extract, select, pack, apply);
+        if(on) fprintf(stderr, "[spg host] stale-check %.3f s, extract %.3f s, select %.3f s, pack %.3f s, splice %.3f s; %lld extractions, %lld window visits, %lld selected; splice passes %.3f %.3f %.3f\n", stale, extract, select, pack, apply, n_extract, n_visit, n_sel, a1, a2, a3);
     }
 } g_prof;
 inline double nowS() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 } // namespace
 
 // Select and pack the next wavefront round (empty round: nothing left).
+//
+// A unit U may run in this round iff it commutes with every earlier pending unit V (selected or deferred):
+// removed(U) misses V's blanket, kept(U) misses removed(V) and U shares at most one kept vertex with V. A deferred
+// unit waits for the units it hit; its blanket after they ran lies inside the union of their blankets and its own, so
+// the two are merged into one component (union-find over region ids) and later units are tested against whole
+// components. Only earlier list entries matter for a unit, so the scan may stop anywhere: a round is drawn from a
+// WINDOW — the units deferred so far plus the next entries of the list — which keeps the per-round work (staleness
+// test, blanket re-extraction, selection) proportional to the window instead of to everything still pending. Any such
+// schedule ends in the same graph (the units of a round commute with each other and with everything before them).
 spg_status VertexRemover::planRound() {
-    _round = Round();
+    _round.sel.clear();
+    _round.recOff.assign(1, 0);
+    _round.outOff.assign(1, 0);
     if(_remaining == 0) return SPG_OK;
     double tp0 = nowS();
     const int dim = _graph->dim;
     const std::vector<int> &toRemove = _pending;
+    const int Vn = (int) _graph->verts.size();
+    _planNo++;
+    if((int) _stamp.size() < Vn) _stamp.resize(Vn, 0);
+    if((int) _touchHead.size() < Vn) { _touchHead.resize(Vn, -1); _removedBy.resize(Vn, -1); }
+
+    // ---- window: the deferred units (list order) and then fresh list entries ---------------------------------------
+    const size_t W = _window ? _window : std::max<size_t>(32768, _remaining / 12);
+    std::vector<int> win;
+    win.reserve(_leftover.size() + W);
+    auto admit = [&](int i) {
+        if(_done[i]) return;
+        if(_rootIdx[i] < 0 || !_graph->verts[_rootIdx[i]].alive) { // merged into an earlier extended blanket (:91)
+            _done[i] = 1;
+            _remaining--;
+            return;
+        }
+        win.push_back(i);
+    };
+    for(int i : _leftover) admit(i);
+    const size_t fresh_goal = std::max(W / 4, W > win.size() ? W - win.size() : 0);
+    for(size_t fresh0 = win.size(); _cursor < toRemove.size() && win.size() - fresh0 < fresh_goal; _cursor++) admit((int) _cursor);
+    if(win.empty()) return SPG_OK;
+
+    // ---- re-extract the stale cached blankets of the window (reads the graph only: spread over the host threads) ---
     {
-        // ---- select a round -------------------------------------------------------------------
-        // A unit U may run in this round iff it commutes with every earlier pending unit V (selected or
-        // deferred): removed(U) misses V's blanket, kept(U) misses removed(V) and U shares at most one kept
-        // vertex with V. A deferred unit waits for the units it hit; its blanket after they ran lies inside
-        // the union of their blankets and its own, so the two are merged into one component (union-find over
-        // region ids) and later units are tested against whole components. Linear in the blanket sizes;
-        // blankets are re-extracted only when a vertex of theirs was touched by an applied round.
-        std::vector<RemovalUnit> &units = _round.units;
-        const int Vn = (int) _graph->verts.size();
-        _planNo++;
-        if((int) _stamp.size() < Vn) _stamp.resize(Vn, 0);
-        if((int) _touchHead.size() < Vn) { _touchHead.resize(Vn, -1); _removedBy.resize(Vn, -1); }
+        std::vector<int> todo;
+        for(int i : win) {
+            const RemovalUnit &u = _unitCache[i];
+            bool stale = !_unitBuilt[i];
+            if(!stale) {
+                for(int xi : u.ridx) if(_stamp[xi] >= _unitBuilt[i]) { stale = true; break; }
+                if(!stale) for(int xi : u.kidx) if(_stamp[xi] >= _unitBuilt[i]) { stale = true; break; }
+            }
+            if(stale) todo.push_back(i);
+        }
+        g_prof.stale += nowS() - tp0; tp0 = nowS();
+        g_prof.n_extract += (long long) todo.size();
+        g_prof.n_visit += (long long) win.size();
+        std::atomic<int> bad(-1);
+        parallelFor(todo.size(), 512, [&](size_t b0, size_t b1) {
+            for(size_t q = b0; q < b1; q++) {
+                const int i = todo[q];
+                if(!buildUnit(toRemove[i], i, _toRemoveSet, _unitCache[i])) {
+                    int expect = -1;
+                    bad.compare_exchange_strong(expect, i);
+                }
+                _unitBuilt[i] = _planNo;
+            }
+        });
+        if(bad.load() >= 0) {
+            // isolated vertex: the reference asserts blanketEdges.size() > 0
+            error = "vertex " + std::to_string(toRemove[bad.load()]) + " has no edges";
+            return SPG_ERR_INVALID;
+        }
+        g_prof.extract += nowS() - tp0; tp0 = nowS();
+    }
+
+    // ---- select (sequential: the decision for a unit depends on every earlier unit of the window) -----------------
+    {
+        std::vector<int> &sel = _round.sel;
         _touchNext.clear();
         _touchRegion.clear();
         std::vector<int> touched;   // vertex indices whose per-round lists must be reset
         std::vector<int> parent;    // union-find over region ids
+        parent.reserve(win.size());
         auto find = [&](int x) { while(parent[x] != x) { parent[x] = parent[parent[x]]; x = parent[x]; } return x; };
         std::vector<int> hit, comps;
         std::vector<std::pair<int, int>> shared;
-        // pass 1: re-extract the stale cached blankets. Extraction only reads the graph, so it is spread over the
-        // host threads (it is ~70 % of the planning time on large graphs); the selection below stays sequential.
-        {
-            std::vector<int> todo;
-            for(size_t i = 0; i < toRemove.size(); i++) {
-                if(_done[i] || _rootIdx[i] < 0 || !_graph->verts[_rootIdx[i]].alive) continue;
-                const RemovalUnit &u = _unitCache[i];
-                bool stale = !_unitBuilt[i];
-                if(!stale) {
-                    for(int xi : u.ridx) if(_stamp[xi] >= _unitBuilt[i]) { stale = true; break; }
-                    if(!stale) for(int xi : u.kidx) if(_stamp[xi] >= _unitBuilt[i]) { stale = true; break; }
-                }
-                if(stale) todo.push_back((int) i);
-            }
-            g_prof.stale += nowS() - tp0; tp0 = nowS();
-            std::atomic<int> bad(-1);
-            auto work = [&](size_t b0, size_t b1) {
-                for(size_t q = b0; q < b1; q++) {
-                    const int i = todo[q];
-                    if(!buildUnit(toRemove[i], i, _toRemoveSet, _unitCache[i])) {
-                        int expect = -1;
-                        bad.compare_exchange_strong(expect, i);
-                    }
-                    _unitBuilt[i] = _planNo;
-                }
-            };
-            unsigned nthr = std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
-            if(todo.size() < 4096) nthr = 1;
-            if(nthr <= 1) work(0, todo.size());
-            else {
-                std::vector<std::thread> pool;
-                const size_t chunk = (todo.size() + nthr - 1) / nthr;
-                for(unsigned t = 0; t < nthr; t++) {
-                    const size_t b0 = std::min(todo.size(), t * chunk), b1 = std::min(todo.size(), b0 + chunk);
-                    if(b0 < b1) pool.emplace_back(work, b0, b1);
-                }
-                for(auto &th : pool) th.join();
-            }
-            if(bad.load() >= 0) {
-                // isolated vertex: the reference asserts blanketEdges.size() > 0
-                error = "vertex " + std::to_string(toRemove[bad.load()]) + " has no edges";
-                return SPG_ERR_INVALID;
-            }
-            g_prof.extract += nowS() - tp0; tp0 = nowS();
-        }
-        for(size_t i = 0; i < toRemove.size(); i++) {
-            if(_done[i]) continue;
-            if(_rootIdx[i] < 0 || !_graph->verts[_rootIdx[i]].alive) { // merged into an earlier extended blanket (:91)
-                _done[i] = 1;
-                _remaining--;
-                continue;
-            }
-            RemovalUnit &u = _unitCache[i];
+        _leftover.clear();
+        for(int i : win) {
+            const RemovalUnit &u = _unitCache[i];
             hit.clear();
             shared.clear();
             auto note = [&](int c) { if(std::find(hit.begin(), hit.end(), c) == hit.end()) hit.push_back(c); };
@@ -706,20 +841,45 @@ spg_status VertexRemover::planRound() {
             };
             for(int xi : u.ridx) reg(xi, true);
             for(int xi : u.kidx) reg(xi, false);
-            if(select) units.push_back(u);
+            if(select) sel.push_back(i);
+            else _leftover.push_back(i);
         }
         for(int xi : touched) { _touchHead[xi] = -1; _removedBy[xi] = -1; }
         g_prof.select += nowS() - tp0; tp0 = nowS();
-        if(units.empty()) return SPG_OK;
+        if(sel.empty()) return SPG_OK;
     }
-    // ---- pack ----------------------------------------------------------------------------
+
+    // ---- pack: sizes and providers per unit, prefix sums, then every record written in place by the host threads ---
+    const std::vector<int> &sel = _round.sel;
+    const size_t ns = sel.size();
+    TopologyProvider *byMask[8] = {};
+    bool haveMask[8] = {};
+    for(int m = 1; m < 8; m++) {
+        std::set<int> kinds;
+        for(int k = 0; k < 3; k++) if(m & (1 << k)) kinds.insert(k);
+        for(TopologyProvider *tp : _topologies)
+            if(tp->applicable(dim, kinds)) { byMask[m] = tp; break; }
+        haveMask[m] = true;
+    }
+    std::vector<int64_t> &recOff = _round.recOff, &outOff = _round.outOff;
+    recOff.assign(ns + 1, 0);
+    outOff.assign(ns + 1, 0);
+    std::vector<unsigned char> mask(ns, 0);
+    parallelFor(ns, 2048, [&](size_t b0, size_t b1) {
+        for(size_t q = b0; q < b1; q++) {
+            const RemovalUnit &u = _unitCache[sel[q]];
+            unsigned char m = 0;
+            for(int ei : u.edges) m |= (unsigned char) (1u << _graph->edges[ei].kind);
+            mask[q] = m;
+            recOff[q + 1] = unitWords(u);
+        }
+    });
+    unsigned char allMask = 0;
+    int maxv = stats.max_blanket_vertices;
     TopologyProvider *tp = nullptr;
-    _round.recOff.assign(1, 0);
-    _round.outOff.assign(1, 0);
-    std::vector<uint64_t> rec;
-    bool poseOnly = true;
-    for(const RemovalUnit &u : _round.units) {
-        TopologyProvider *t = chooseTopologyProvider(u);
+    for(size_t q = 0; q < ns; q++) {
+        allMask |= mask[q];
+        TopologyProvider *t = byMask[mask[q] & 7];
         if(!t) {
             error = "No valid topology provider for Markov blanket";
             return SPG_ERR_UNSUPPORTED;
@@ -729,20 +889,32 @@ spg_status VertexRemover::planRound() {
             return SPG_ERR_UNSUPPORTED;
         }
         tp = t;
-        for(int ei : u.edges) poseOnly = poseOnly && (_graph->edges[ei].kind == SPG_EDGE_POSE);
-        if(!packUnit(u, rec)) {
-            error = "Local linearisation point on a non-star blanket needs the subgraph optimiser (not on this path)";
-            return SPG_ERR_UNSUPPORTED;
-        }
-        _round.records.insert(_round.records.end(), rec.begin(), rec.end());
-        _round.recOff.push_back((int64_t) _round.records.size());
-        _round.outOff.push_back(_round.outOff.back() + spgr_out_record_words(dim, tp->algorithm(), _opts.topology, _opts.chordRatio,
-                                                                             (int) u.kept.size()));
-        stats.max_blanket_vertices = std::max<int>(stats.max_blanket_vertices, (int) (u.removed.size() + u.kept.size()));
+        const RemovalUnit &u = _unitCache[sel[q]];
+        maxv = std::max<int>(maxv, (int) (u.removed.size() + u.kept.size()));
+        outOff[q + 1] = outOff[q] + spgr_out_record_words(dim, t->algorithm(), _opts.topology, _opts.chordRatio, (int) u.kept.size());
+        recOff[q + 1] += recOff[q];
+    }
+    stats.max_blanket_vertices = maxv;
+    uint64_t *rec = _round.records.reserve((size_t) recOff[ns]);
+    if(!rec) {
+        error = "out of host memory";
+        return SPG_ERR_INVALID;
+    }
+    std::atomic<int> badPack(-1);
+    parallelFor(ns, 1024, [&](size_t b0, size_t b1) {
+        for(size_t q = b0; q < b1; q++)
+            if(!packUnit(_unitCache[sel[q]], rec + recOff[q], recOff[q + 1] - recOff[q])) {
+                int expect = -1;
+                badPack.compare_exchange_strong(expect, (int) q);
+            }
+    });
+    if(badPack.load() >= 0) {
+        error = "Local linearisation point on a non-star blanket needs the subgraph optimiser (not on this path)";
+        return SPG_ERR_UNSUPPORTED;
     }
     g_prof.pack += nowS() - tp0;
     _round.algorithm = tp->algorithm();
-    _round.poseOnly = poseOnly;
+    _round.poseOnly = (allMask == (1u << SPG_EDGE_POSE));
     if(_round.algorithm == SPG_ALG_GLC) {
         // asserts of TopologyProviderGLC::topology (src/topology_provider_glc.cpp:107-111)
         if(!(_opts.topology == SparsityOptions::Dense || _opts.topology == SparsityOptions::Tree) ||
@@ -759,11 +931,23 @@ spg_status VertexRemover::planRound() {
 void VertexRemover::applyRound(const uint64_t *out) {
     const int dim = _graph->dim, P = _graph->poseWords(), algorithm = _round.algorithm;
     const double ta0 = nowS();
-    for(size_t ui = 0; ui < _round.units.size(); ui++) {
-        const RemovalUnit &u = _round.units[ui];
+    const std::vector<int> &sel = _round.sel;
+    const size_t ns = sel.size();
+    std::vector<GraphVertex> &V = _graph->verts;
+    std::vector<GraphEdge> &E = _graph->edges;
+
+    // ---- pass 1 (sequential, headers only): status bookkeeping, staleness stamps, edge indices of the substitutes --
+    std::vector<int> base(ns + 1, 0); // new edges of unit ui go to E[e0 + base[ui] ...); failed units add none
+    std::vector<char> okUnit(ns, 0);
+    int removedEdges = 0, removedVerts = 0;
+    for(size_t ui = 0; ui < ns; ui++) {
+        const RemovalUnit &u = _unitCache[sel[ui]];
         const uint64_t *o = out + _round.outOff[ui];
         const int32_t *oh = reinterpret_cast<const int32_t *>(o);
         const int bstatus = oh[0], nnew = oh[1];
+        base[ui + 1] = base[ui];
+        _done[u.listIndex] = 1;
+        _remaining--;
         if(bstatus != SPG_BLANKET_OK) {
             // The reference asserts / exits here. The blanket is left in the graph untouched (vertex, edges, no
             // substitutes); the units of a round commute, so the others are unaffected. The call reports
@@ -772,59 +956,153 @@ void VertexRemover::applyRound(const uint64_t *out) {
                 stats.first_failed_index = u.listIndex;
                 stats.first_failed_status = bstatus;
             }
-            for(int id : u.removed) _toRemoveSet.erase(id);
-            _done[u.listIndex] = 1;
-            _remaining--;
+            if(!_toRemoveSet.empty())
+                for(int id : u.removed) _toRemoveSet.erase(id);
             continue;
         }
+        okUnit[ui] = 1;
         for(int xi : u.ridx) _stamp[xi] = _planNo; // cached blankets containing these are stale
         for(int xi : u.kidx) _stamp[xi] = _planNo;
-        for(int ei : u.edges) _graph->removeEdge(ei);
-        for(int id : u.removed) _graph->removeVertex(id);
-        const int nk = (int) u.kept.size();
-        const int64_t slot = spgr_out_slot_words(dim, algorithm, _opts.topology, nk);
-        int minor = 0;
-        for(int e = 0; e < nnew; e++) {
-            const uint64_t *sl = o + SPG_OUT_HEADER_WORDS + (int64_t) e * slot;
-            const int32_t *si = reinterpret_cast<const int32_t *>(sl);
-            GraphEdge ge;
-            ge.uidMajor = u.listIndex;
-            if(algorithm == SPG_ALG_NFR) {
-                ge.kind = SPG_EDGE_POSE;
-                ge.v = {u.kept[si[0]], u.kept[si[1]]};
-                ge.rows = dim;
-                const double *pm = reinterpret_cast<const double *>(sl + 1);
-                ge.meas.assign(pm, pm + P);
-                ge.info.assign(pm + P, pm + P + dim * dim);
-            } else {
-                const int nvcap = (_opts.topology == SparsityOptions::Dense || nk == 1) ? nk : 2;
-                const int c = dim * nvcap, nve = si[0], rank = si[1];
-                if(rank == 0) { // getEdge returned NULL (src/topology_provider_glc.cpp:85-89)
-                    stats.n_dropped_edges++;
-                    continue;
-                }
-                ge.kind = SPG_EDGE_GLC;
-                const int32_t *vi = reinterpret_cast<const int32_t *>(sl + 1);
-                for(int q = 0; q < nve; q++) ge.v.push_back(u.kept[vi[q]]);
-                ge.rows = rank;
-                const double *pm = reinterpret_cast<const double *>(sl + 1 + spgr_pad2(nvcap));
-                ge.meas.assign(pm, pm + dim * nve);
-                const double *W = pm + c;
-                ge.info.resize((size_t) rank * dim * nve);
-                for(int r = 0; r < rank; r++)
-                    for(int q = 0; q < dim * nve; q++) ge.info[(size_t) r * dim * nve + q] = W[(size_t) r * c + q];
-            }
-            ge.uidMinor = minor++;
-            _added.push_back(_graph->addEdge(ge));
+        int cnt = nnew;
+        if(algorithm == SPG_ALG_GLC) { // getEdge returned NULL for rank-0 factors (src/topology_provider_glc.cpp:85-89)
+            const int64_t slot = spgr_out_slot_words(dim, algorithm, _opts.topology, (int) u.kept.size());
+            cnt = 0;
+            for(int e = 0; e < nnew; e++)
+                cnt += reinterpret_cast<const int32_t *>(o + SPG_OUT_HEADER_WORDS + (int64_t) e * slot)[1] != 0;
+            stats.n_dropped_edges += nnew - cnt;
         }
-        _done[u.listIndex] = 1;
-        _remaining--;
+        base[ui + 1] += cnt;
         stats.n_blankets++;
         stats.n_applied += (int) u.removed.size();
+        removedVerts += (int) u.removed.size();
     }
+    const int e0 = (int) E.size();
+    E.resize((size_t) e0 + base[ns]);
+    double tq = nowS();
+    g_prof.a1 += tq - ta0;
+
+    // ---- pass 2 (parallel over units; blankets of a round share no edge and no removed vertex): blanket edges and
+    // removed vertices die, the substitute edges are built in place --------------------------------------------------
+    std::atomic<int> removedEdgesA(0);
+    std::mutex garbageMx;
+    std::vector<std::vector<double>> garbage; // payload blocks nobody took over: freed off the critical path
+    parallelFor(ns, 256, [&](size_t q0, size_t q1) {
+        int dead = 0;
+        std::vector<int> spare;
+        std::vector<std::vector<double>> mine;
+        for(size_t ui = q0; ui < q1; ui++) {
+            if(!okUnit[ui]) continue;
+            const RemovalUnit &u = _unitCache[sel[ui]];
+            spare.clear();
+            auto kill = [&](int ei) {
+                GraphEdge &e = E[ei];
+                if(!e.alive) return;
+                e.alive = false;
+                if(e.payload.capacity()) spare.push_back(ei); // its payload block is handed to a substitute edge below
+                dead++;
+            };
+            for(int ei : u.edges) kill(ei);
+            for(int xi : u.ridx) {
+                // g2o's HyperGraph::removeVertex detaches every edge still incident to the vertex; its other ends are
+                // blanket vertices, whose adjacency is cleaned below
+                for(int ei : V[xi].edges) kill(ei);
+                V[xi].alive = false;
+                std::vector<int>().swap(V[xi].edges);
+                std::vector<int>().swap(V[xi].peer);
+            }
+            const uint64_t *o = out + _round.outOff[ui];
+            const int nnew = reinterpret_cast<const int32_t *>(o)[1];
+            const int nk = (int) u.kept.size();
+            const int64_t slot = spgr_out_slot_words(dim, algorithm, _opts.topology, nk);
+            int minor = 0;
+            for(int e = 0; e < nnew; e++) {
+                const uint64_t *sl = o + SPG_OUT_HEADER_WORDS + (int64_t) e * slot;
+                const int32_t *si = reinterpret_cast<const int32_t *>(sl);
+                if(algorithm != SPG_ALG_NFR && si[1] == 0) continue;
+                GraphEdge &ge = E[(size_t) e0 + base[ui] + minor];
+                if(!spare.empty()) {
+                    ge.payload.swap(E[spare.back()].payload);
+                    spare.pop_back();
+                }
+                ge.uidMajor = u.listIndex;
+                ge.uidMinor = minor++;
+                ge.alive = true;
+                if(algorithm == SPG_ALG_NFR) {
+                    ge.kind = SPG_EDGE_POSE;
+                    ge.v = {u.kept[si[0]], u.kept[si[1]]};
+                    ge.vx0 = u.kidx[si[0]];
+                    ge.vx1 = u.kidx[si[1]];
+                    ge.rows = dim;
+                    const double *pm = reinterpret_cast<const double *>(sl + 1);
+                    ge.setPayload(pm, P, pm + P, dim * dim);
+                } else {
+                    const int nvcap = (_opts.topology == SparsityOptions::Dense || nk == 1) ? nk : 2;
+                    const int c = dim * nvcap, nve = si[0], rank = si[1];
+                    ge.kind = SPG_EDGE_GLC;
+                    const int32_t *vi = reinterpret_cast<const int32_t *>(sl + 1);
+                    for(int q = 0; q < nve; q++) ge.v.push_back(u.kept[vi[q]]);
+                    ge.vx0 = nve > 0 ? u.kidx[vi[0]] : -1;
+                    ge.vx1 = nve > 1 ? u.kidx[vi[1]] : -1;
+                    if(nve > 2)
+                        for(int q = 0; q < nve; q++) ge.vxn.push_back(u.kidx[vi[q]]);
+                    ge.rows = rank;
+                    const double *pm = reinterpret_cast<const double *>(sl + 1 + spgr_pad2(nvcap));
+                    const double *W = pm + c;
+                    ge.allocPayload(dim * nve, rank * dim * nve);
+                    std::memcpy(ge.meas(), pm, sizeof(double) * dim * nve);
+                    double *gi = ge.info();
+                    for(int r = 0; r < rank; r++)
+                        for(int q = 0; q < dim * nve; q++) gi[(size_t) r * dim * nve + q] = W[(size_t) r * c + q];
+                }
+            }
+            for(int ei : spare) mine.emplace_back(std::move(E[ei].payload));
+        }
+        removedEdgesA += dead;
+        std::lock_guard<std::mutex> lk(garbageMx);
+        for(auto &g : mine) garbage.emplace_back(std::move(g));
+    });
+    if(garbage.size() > 4096) std::thread([g = std::move(garbage)]() mutable { g.clear(); }).detach();
+    removedEdges = removedEdgesA.load();
+    g_prof.a2 += nowS() - tq; tq = nowS();
+
+    // ---- pass 3 (parallel over units, one byte lock per vertex: two blankets of a round may share one kept vertex):
+    // adjacency of the kept vertices — dead edges out, substitutes in. The order inside an adjacency list carries no
+    // meaning (every consumer sorts by the canonical edge key).
+    if(_vlock.size() < V.size()) _vlock = std::vector<std::atomic<unsigned char>>(V.size() + V.size() / 4 + 64);
+    parallelFor(ns, 256, [&](size_t q0, size_t q1) {
+        for(size_t ui = q0; ui < q1; ui++) {
+            if(!okUnit[ui]) continue;
+            const RemovalUnit &u = _unitCache[sel[ui]];
+            const int nb0 = e0 + base[ui], nb1 = e0 + base[ui + 1];
+            for(int xi : u.kidx) {
+                std::atomic<unsigned char> &lk = _vlock[xi];
+                while(lk.exchange(1, std::memory_order_acquire)) { /* spin: held for a few dozen instructions */ }
+                GraphVertex &gv = V[xi];
+                size_t w = 0;
+                for(size_t k = 0; k < gv.edges.size(); k++)
+                    if(E[gv.edges[k]].alive) { gv.edges[w] = gv.edges[k]; gv.peer[w] = gv.peer[k]; w++; }
+                gv.edges.resize(w);
+                gv.peer.resize(w);
+                for(int ei = nb0; ei < nb1; ei++) {
+                    const GraphEdge &ge = E[ei];
+                    for(int q = 0, n = ge.nv(); q < n; q++)
+                        if(ge.vx(q) == xi) {
+                            gv.edges.push_back(ei);
+                            gv.peer.push_back(n == 2 ? ((ge.vx(1 - q) << 1) | (q == 0)) : -1);
+                        }
+                }
+                lk.store(0, std::memory_order_release);
+            }
+        }
+    });
+    g_prof.a3 += nowS() - tq;
+    for(int k = 0; k < base[ns]; k++) _added.push_back(e0 + k);
+    _graph->version++;
+    _graph->aliveEdges += base[ns] - removedEdges;
+    _graph->aliveVertices -= removedVerts;
     stats.n_rounds++;
-    stats.max_round_width = std::max<int>(stats.max_round_width, (int) _round.units.size());
-    _round.units.clear();
+    stats.max_round_width = std::max<int>(stats.max_round_width, (int) ns);
+    _round.sel.clear();
     g_prof.apply += nowS() - ta0;
 }
 
@@ -914,15 +1192,15 @@ void computeSubstituteEdge(const Graph *gw, const std::set<int> &marginalized, i
             const GraphEdge &e = gw->edges[ei];
             if(e.v.size() != 2 || e.kind != SPG_EDGE_POSE) continue;
             if(lastFrontier.count(e.v[0]) || lastFrontier.count(e.v[1])) {
-                invertSmall(dim, e.info.data(), inv.data());
+                invertSmall(dim, e.info(), inv.data());
                 for(int q = 0; q < dim * dim; q++) covsum[q] += inv[q];
-                poseInverse(dim, e.meas.data(), zi);
+                poseInverse(dim, e.meas(), zi);
                 if(from == toConnect) {
-                    if(e.v[1] == reach) poseCompose(dim, e.meas.data(), meas, tmp);
+                    if(e.v[1] == reach) poseCompose(dim, e.meas(), meas, tmp);
                     else poseCompose(dim, zi, meas, tmp);
                 } else {
                     if(e.v[1] == reach) poseCompose(dim, meas, zi, tmp);
-                    else poseCompose(dim, meas, e.meas.data(), tmp);
+                    else poseCompose(dim, meas, e.meas(), tmp);
                 }
                 std::memcpy(meas, tmp, sizeof(double) * P);
                 reach = e.v[1] == reach ? e.v[0] : e.v[1];
@@ -1079,13 +1357,14 @@ spg_status spg_graph_last_stats(const spg_graph *g, spg_marginalize_stats *stats
 // edge read-back in canonical order (idx is a position in that order; O(E log E) per call batch: the
 // order is cached per query run by callers that iterate 0..E-1)
 static thread_local std::vector<int> t_order;
-static thread_local const spg::Graph *t_order_of = nullptr;
-static thread_local size_t t_order_edges = 0;
+static thread_local unsigned long long t_order_serial = 0, t_order_version = ~0ULL;
 static const spg::GraphEdge *edgeAt(const spg_graph *g, int idx) {
-    if(t_order_of != g->g || t_order_edges != g->g->edges.size() || (int) t_order.size() != g->g->aliveEdges) {
+    // cached canonical order, keyed by the graph's serial number and mutation count (not by its address: a new graph
+    // may be allocated where an old one lived)
+    if(t_order_serial != g->g->serial || t_order_version != g->g->version) {
         t_order = g->g->edgeOrder();
-        t_order_of = g->g;
-        t_order_edges = g->g->edges.size();
+        t_order_serial = g->g->serial;
+        t_order_version = g->g->version;
     }
     if(idx < 0 || idx >= (int) t_order.size()) return nullptr;
     return &g->g->edges[t_order[idx]];
@@ -1106,8 +1385,8 @@ spg_status spg_graph_edge_data(const spg_graph *g, int32_t idx, int32_t *vert_id
     const spg::GraphEdge *e = edgeAt(g, idx);
     if(!e) return SPG_ERR_INVALID;
     if(vert_ids) for(size_t i = 0; i < e->v.size(); i++) vert_ids[i] = e->v[i];
-    if(meas) std::memcpy(meas, e->meas.data(), sizeof(double) * e->meas.size());
-    if(info_or_w) std::memcpy(info_or_w, e->info.data(), sizeof(double) * e->info.size());
+    if(meas) std::memcpy(meas, e->meas(), sizeof(double) * e->nMeas);
+    if(info_or_w) std::memcpy(info_or_w, e->info(), sizeof(double) * e->nInfo());
     return SPG_OK;
 }
 spg_status spg_graph_vertex_ids(const spg_graph *g, int32_t *ids) {

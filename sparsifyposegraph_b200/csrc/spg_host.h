@@ -11,7 +11,10 @@
 //        reference's one-at-a-time loop) and sends each round through spg_remove_round().
 //   computeSubstituteEdge  src/compute_substitute_edge.cpp:13-96
 #pragma once
+#include <atomic>
 #include <cstdint>
+#include <cstring>
+#include <initializer_list>
 #include <list>
 #include <map>
 #include <set>
@@ -43,31 +46,92 @@ std::vector<int> globalDecimate(int lastid, int endvert, const DecimateOptions &
 typedef std::vector<int> (*DecimateFunction)(int last, int endvert, const DecimateOptions &opts);
 
 // ---- pose-graph container ----------------------------------------------------------------------
+// vertex-id list of an edge: two ids inline (POSE edges never touch the heap), more on the heap
+class IdList {
+public:
+    IdList() {}
+    IdList(std::initializer_list<int> il) { for(int x : il) push_back(x); }
+    size_t size() const { return _n; }
+    bool empty() const { return _n == 0; }
+    void clear() { _n = 0; _more.clear(); }
+    void push_back(int x) {
+        if(_n < 2) _in[_n] = x;
+        else {
+            if(_n == 2) { _more.assign(_in, _in + 2); }
+            _more.push_back(x);
+        }
+        _n++;
+    }
+    const int *begin() const { return _n <= 2 ? _in : _more.data(); }
+    const int *end() const { return begin() + _n; }
+    int operator[](size_t i) const { return begin()[i]; }
+private:
+    int _in[2] = {0, 0};
+    unsigned _n = 0;
+    std::vector<int> _more;
+};
+
 struct GraphEdge {
     int kind = SPG_EDGE_POSE;
-    std::vector<int> v;          // vertex ids, in the edge's own order (from, to, ...)
+    IdList v;                    // vertex ids, in the edge's own order (from, to, ...)
     int rows = 0;                // error dimension
-    std::vector<double> meas;    // POSE: P; GLC: d*nv; MULTI: nmeas*P
-    std::vector<double> info;    // POSE/MULTI: rows*rows column-major; GLC: W rows x d*nv row-major
+    // one payload block per edge: the measurement (POSE: P; GLC: d*nv; MULTI: nmeas*P doubles) followed by the
+    // information (POSE/MULTI: rows*rows column-major; GLC: W rows x d*nv row-major). Freed when the edge dies.
+    std::vector<double> payload;
+    int nMeas = 0;
+    double *meas() { return payload.data(); }
+    const double *meas() const { return payload.data(); }
+    double *info() { return payload.data() + nMeas; }
+    const double *info() const { return payload.data() + nMeas; }
+    int nInfo() const { return (int) payload.size() - nMeas; }
+    void allocPayload(int nm, int ni) { nMeas = nm; payload.resize((size_t) nm + ni); }
+    void setPayload(const double *m, int nm, const double *inf, int ni) {
+        nMeas = nm;
+        payload.resize((size_t) nm + ni);
+        std::memcpy(payload.data(), m, sizeof(double) * nm);
+        std::memcpy(payload.data() + nm, inf, sizeof(double) * ni);
+    }
     std::vector<int> pairs;      // MULTI: 2*nmeas indices into v
     int uidMajor = -1, uidMinor = 0; // canonical order: file edges (-1, file index); new edges (list index, k)
     bool alive = true;
+    // Graph::verts indices of the vertices (set by Graph::addEdge): the first two inline, all of them in vxn when the
+    // edge has more than two (the scheduler walks adjacency by index, without id lookups or heap hops for POSE edges)
+    int vx0 = -1, vx1 = -1;
+    std::vector<int> vxn;
+    int nv() const { return (int) v.size(); }
+    int vx(int q) const { return v.size() <= 2 ? (q == 0 ? vx0 : vx1) : vxn[q]; }
+    unsigned long long uidKey() const { return ((unsigned long long) (unsigned) (uidMajor + 1) << 32) | (unsigned) uidMinor; }
 };
 struct GraphVertex {
     int id = 0;
     double pose[7] = {0, 0, 0, 0, 0, 0, 1};
     std::vector<int> edges;      // indices into Graph::edges (alive ones only)
+    // same positions as `edges`: for a two-vertex edge (other endpoint's verts index << 1) | (this vertex is the
+    // edge's first one), -1 for any other edge — blanket extraction then walks binary edges without touching them
+    std::vector<int> peer;
     bool alive = true;
 };
 
 class Graph {
 public:
-    explicit Graph(int dim_) : dim(dim_) {}
+    explicit Graph(int dim_) : dim(dim_) {
+        static std::atomic<unsigned long long> next(1);
+        serial = next++;
+    }
     int dim;
+    unsigned long long serial = 0, version = 0; // identity and mutation count (caches of derived orders key on these)
     int poseWords() const { return dim == 3 ? 3 : 7; }
     std::vector<GraphVertex> verts;
     std::vector<GraphEdge> edges;
-    std::unordered_map<int, int> index; // id -> verts index
+    // id -> verts index: a dense table for ids in [0, 2^26), a hash map for anything else
+    std::vector<int> dense;
+    std::unordered_map<int, int> sparse;
+    int indexOf(int id) const {
+        if((unsigned) id < dense.size()) return dense[(unsigned) id];
+        if((unsigned) id < (1u << 26)) return -1;
+        auto it = sparse.find(id);
+        return it == sparse.end() ? -1 : it->second;
+    }
     int fileEdges = 0;
     int aliveVertices = 0, aliveEdges = 0;
 
@@ -77,7 +141,8 @@ public:
     const GraphVertex *vertex(int id) const;
     bool addVertex(int id, const double *pose);
     int addPoseEdge(int from, int to, const double *meas, const double *info);
-    int addEdge(const GraphEdge &e); // generic (uid must be set)
+    int addEdge(GraphEdge &&e);      // generic (uid must be set)
+    int addEdge(const GraphEdge &e) { return addEdge(GraphEdge(e)); }
     void removeEdge(int ei);
     void removeVertex(int id);
     int maxVertexId() const;
@@ -129,6 +194,19 @@ struct RemovalUnit {
     std::vector<int> ridx, kidx;     // Graph::verts indices of removed / kept (scheduler: no id lookups per round)
 };
 
+// growable host buffer of 8-byte words: page-locked when a CUDA device is present, plain memory otherwise
+struct HostBuf {
+    uint64_t *p = nullptr;
+    size_t cap = 0;
+    bool pinned = false;
+    HostBuf() {}
+    HostBuf(const HostBuf &) = delete;
+    HostBuf &operator=(const HostBuf &) = delete;
+    ~HostBuf() { release(); }
+    uint64_t *reserve(size_t words); // contents are NOT preserved on growth
+    void release();
+};
+
 class VertexRemover {
 public:
     VertexRemover();
@@ -150,8 +228,8 @@ public:
     // round-by-round interface (what remove() loops over): beginRemoval, then planRound /
     // roundDescriptor / applyRound until planRound leaves an empty round
     struct Round {
-        std::vector<RemovalUnit> units;
-        std::vector<uint64_t> records;
+        std::vector<int> sel;        // selected units: indices into the removal list, ascending
+        HostBuf records;
         std::vector<int64_t> recOff, outOff;
         int algorithm = SPG_ALG_NFR;
         bool poseOnly = false;       // every blanket edge of the round is a POSE edge (SPG_OPT_POSE_EDGES_ONLY)
@@ -168,7 +246,8 @@ public:
 private:
     bool buildUnit(int root, int listIndex, const std::set<int> &toRemoveSet, RemovalUnit &u) const;
     TopologyProvider *chooseTopologyProvider(const RemovalUnit &u) const;
-    bool packUnit(const RemovalUnit &u, std::vector<uint64_t> &rec) const;
+    int64_t unitWords(const RemovalUnit &u) const;
+    bool packUnit(const RemovalUnit &u, uint64_t *rec, int64_t words) const;
 
     Round _round;
     std::vector<int> _pending, _added;
@@ -182,6 +261,11 @@ private:
     std::vector<int> _stamp;                // per vertex index: last planning pass whose round touched it
     std::vector<int> _touchHead, _touchNext, _touchRegion, _removedBy;
     int _planNo = 0;
+    // the window a round is drawn from: units deferred by earlier rounds (list order) + fresh entries from _cursor on
+    std::vector<int> _leftover;
+    size_t _cursor = 0, _window = 0;   // _window = 0: adaptive (env SPG_PLAN_WINDOW overrides; tests)
+    HostBuf _outBuf;                   // output records of the round in flight (remove())
+    std::vector<std::atomic<unsigned char>> _vlock; // per-vertex byte locks of the parallel splice
     SparsityOptions _opts;
     Graph *_graph = nullptr;
     spg_ctx *_ctx = nullptr;

@@ -98,12 +98,18 @@ def test_compute_substitute_edge_matches_oracle(oracle, name):
     assert checked >= 5
 
 
-@pytest.mark.parametrize("order", ["raster", "colour", "random"])
-def test_round_scheduler_equals_sequential_removal_on_grid(oracle, order):
+@pytest.mark.parametrize("order,window", [("raster", 0), ("colour", 0), ("random", 0), ("random", 48), ("colour", 7)])
+def test_round_scheduler_equals_sequential_removal_on_grid(oracle, order, window, monkeypatch):
     """BASELINE.json configs[4] at small scale: the wavefront rounds (product scheduler; blankets computed by the
     oracle here, no GPU) must leave exactly the graph of the one-at-a-time loop of VertexRemover::remove
-    (vertex_remover.cpp:83-140), in raster order (narrow rounds), in colour order and in random order (wide rounds)."""
+    (vertex_remover.cpp:83-140), in raster order (narrow rounds), in colour order and in random order (wide rounds).
+    window > 0 forces the planner's scan window (SPG_PLAN_WINDOW) far below the list length: rounds are then drawn from
+    the deferred units plus a few fresh list entries — a different schedule, the same final graph. The multi-threaded
+    pack / splice paths run too (SPG_HOST_THREADS=4 with thresholds far below these round widths is not needed: the
+    parallel passes switch on by round width, see test below)."""
     from sparsifyposegraph_b200 import capi, synth, records as R
+    if window:
+        monkeypatch.setenv("SPG_PLAN_WINDOW", str(window))
     from test_gpu_graph import compare_graphs
     rows, cols = 24, 28
     data = synth.make_grid_graph(rows, cols, dim=6)
@@ -124,5 +130,33 @@ def test_round_scheduler_equals_sequential_removal_on_grid(oracle, order):
     assert sum(widths) == len(which)
     assert o.marginalize(which, oracle.make_opts(R.TOPO_TREE, R.LIN_GLOBAL), R.ALG_NFR) == 0
     compare_graphs(g, o, tol=1e-9)
-    if order != "raster":
+    if order != "raster" and not window:
         assert max(widths) >= 25 and len(widths) < len(which) / 8
+    if window:
+        assert max(widths) <= max(window, 2 * window)   # a round never exceeds leftover + fresh entries
+
+
+def test_round_scheduler_parallel_passes_equal_single_thread(oracle, monkeypatch):
+    """A grid wide enough for the threaded extraction / packing / splicing passes (>= 512 / 1024 / 256 units per
+    thread) against the one-at-a-time oracle loop."""
+    from sparsifyposegraph_b200 import capi, synth, records as R
+    from test_gpu_graph import compare_graphs
+    rows, cols = 150, 150
+    data = synth.make_grid_graph(rows, cols, dim=6)
+    g = synth.fill_graph(capi.Graph(dim=6), *data)
+    o = synth.fill_graph(oracle.Graph(dim=6), *data)
+    which = synth.grid_removal_order(rows, cols, 10, 4, "random")
+    opts = capi.make_opts(R.TOPO_TREE, R.LIN_GLOBAL)
+    capi.rounds_begin(g, which, opts, R.ALG_NFR)
+    widest = 0
+    while True:
+        rd = capi.round_next(g)
+        if rd is None:
+            break
+        widest = max(widest, rd["n"])
+        out = oracle.remove_round(rd["dim"], rd["algorithm"], oracle.make_opts(R.TOPO_TREE, R.LIN_GLOBAL), rd["records"],
+                                  rd["rec_off"], rd["out_off"], 0)[0]
+        capi.round_apply(g, out)
+    assert widest >= 2048
+    assert o.marginalize(which, oracle.make_opts(R.TOPO_TREE, R.LIN_GLOBAL), R.ALG_NFR) == 0
+    compare_graphs(g, o, tol=1e-9)

@@ -5,10 +5,11 @@ which gives ~45 wide rounds and blankets below 18 vertices; --order colour / ras
     python tools/grid_bench.py --rows 300 --cols 300                      # one GPU
     python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/grid_bench.py --rows 300 --cols 300
 
-Every rank holds the whole host graph, plans the same rounds, runs its contiguous shard of each round on its own
-GPU and all-gathers the output records (sparsifyposegraph_b200.distributed). Prints one JSON line: whole-job
-vertices/s including planning, packing, H2D/D2H and splicing, and the share of the time spent in each.
-The host scheduler is single-threaded: beyond a few GPUs this workload is host-bound (printed as host_share)."""
+The whole removal is one C-ABI call (spg_graph_marginalize). Under torchrun every rank holds the whole host graph
+and a communicator on its context (spg_comm_init): the call is then collective, every round is cut into pipeline
+steps that are split over the ranks, and the output records are all-gathered over NCCL between the device buffers
+(spg_remove_round_sharded). Prints one JSON line: whole-job vertices/s including planning, packing, H2D/D2H and
+splicing, and the share of the time spent in each (host_share = planning + packing + splicing)."""
 import argparse
 import json
 import os
@@ -58,66 +59,12 @@ def main():
     warm = synth.fill_graph(capi.Graph(dim=6), *synth.make_grid_graph(40, 40, dim=6))
     warm.marginalize(ctx, synth.grid_removal_order(40, 40, args.sparsity, args.colour_mod, args.order), opts, alg)
 
-    log = []
-    t_plan = t_gpu = t_apply = 0.0
-    rounds = widest = 0
     if world > 1:
+        distributed.init_comm(ctx, rank, world)  # marginalize() is then collective: every round sharded + gathered (NCCL)
         dist.barrier()
     torch.cuda.synchronize()
     t_start = time.time()
-    capi.rounds_begin(g, which, opts, alg)
-    while True:
-        t0 = time.time()
-        rd = capi.round_next(g)
-        t1 = time.time()
-        t_plan += t1 - t0
-        if rd is None:
-            break
-        rounds += 1
-        widest = max(widest, rd["n"])
-        bounds = distributed.shard_bounds(rd["rec_off"], world)
-        b0, b1 = bounds[rank], bounds[rank + 1]
-        ro, oo = rd["rec_off"], rd["out_off"]
-        prof = False
-        if os.environ.get("SPG_GRID_LOG") and b1 > b0:
-            nvs_ = rd["records"][ro[:-1]].view(np.int32).reshape(-1, 2)[:, 0]
-            prof = int(nvs_.max()) >= 30
-            if prof:
-                import ctypes as C
-                L = capi.lib()
-                L.spg_stage_profile.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
-                L.spg_stage_profile(ctx.h, 1, None)
-        if b1 > b0:
-            local = ctx.remove_round(rd["dim"], rd["algorithm"], rd["opts"], rd["records"][ro[b0]:ro[b1]], ro[b0:b1 + 1] - ro[b0],
-                                     oo[b0:b1 + 1] - oo[b0])[0]
-        else:
-            local = np.zeros(0, dtype=np.uint64)
-        if prof:
-            main.profiled = True
-            cyc = np.zeros(16, dtype=np.uint64)
-            L.spg_stage_profile(ctx.h, 0, cyc.ctypes.data_as(C.c_void_p))
-            names = ["load", "assembly", "schur", "cl_chol", "cl_inverse", "cl_blockchol", "cl_mi", "kruskal", "g_chol", "g_inverse",
-                     "new_jac", "sigma", "x_inv", "write", "-", "-"]
-            print("stage cycles of a round with a", int(nvs_.max()), "vertex blanket:", {n: int(c) for n, c in zip(names, cyc) if c}, file=sys.stderr)
-            st = np.asarray(local).view(np.int32)
-            for b in range(b0, b1):
-                hdr = np.asarray(local)[oo[b] - oo[b0]:oo[b] - oo[b0] + 2]
-                i32 = hdr.view(np.int32)
-                if i32[3]:
-                    print(f"   blanket with {int(nvs_[b])} vertices: status {int(i32[0])} flags {int(i32[3])} kld-slot {hdr[1:2].view(np.float64)[0]:.4g}", file=sys.stderr)
-        if world > 1:
-            out = distributed.gather_outputs(np.ascontiguousarray(local, dtype=np.uint64),
-                                             [int(oo[bounds[r + 1]] - oo[bounds[r]]) for r in range(world)], None,
-                                             torch.device("cuda", local_rank))
-        else:
-            out = local
-        t2 = time.time()
-        t_gpu += t2 - t1
-        if os.environ.get("SPG_GRID_LOG"):
-            nvs = rd["records"][ro[:-1]].view(np.int32).reshape(-1, 2)[:, 0]
-            log.append((t2 - t1, rd["n"], int(nvs.max()), int((nvs > 19).sum()), ctx.last_kernel_ms))
-        capi.round_apply(g, out)
-        t_apply += time.time() - t2
+    st = g.marginalize(ctx, which, opts, alg)   # the whole loop is C++: plan, pack, spg_remove_round[_sharded], splice
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -126,19 +73,16 @@ def main():
         tt = torch.tensor([total], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         total = float(tt.item())
-    if rank == 0 and log:
-        log.sort(reverse=True)
-        for sec, n, mx, big, kms in log[:12]:
-            print(f"round: {sec * 1e3:8.1f} ms wall, {kms:8.1f} ms kernels, {n:6d} blankets, largest {mx:3d} vertices, {big:4d} beyond shared memory", file=sys.stderr)
-        hist = np.bincount([l[2] for l in log])
-        print("rounds by largest blanket:", {int(i): int(c) for i, c in enumerate(hist) if c}, file=sys.stderr)
+    rounds, widest = st["n_rounds"], st["max_round_width"]
+    t_plan, t_gpu, t_apply = st["pack_ms"] * 1e-3, st["gpu_ms"] * 1e-3, st["splice_ms"] * 1e-3
     if rank == 0:
         json_out.write(json.dumps({
             "metric": "vertices marginalized/sec, graph level (plan + pack + H2D + kernels + D2H + gather + splice)",
             "value": len(which) / total, "unit": "vertices/s", "n_gpus": world, "higher_is_better": True,
             "config": {"workload": f"C5 synthetic SE3 grid {args.rows}x{args.cols} = {args.rows * args.cols} poses, {len(which)} removed "
                                    f"(sparsity {args.sparsity}, {args.order} order), {args.algorithm.upper()} Tree, Global lin. point"},
-            "seconds": total, "rounds": rounds, "max_round_width": widest, "remaining_vertices": len(g.vertex_ids()),
+            "seconds": total, "rounds": rounds, "max_round_width": widest, "max_blanket_vertices": st["max_blanket_vertices"],
+            "host_threads": os.cpu_count(), "remaining_vertices": len(g.vertex_ids()),
             "remaining_edges": g.num_edges if hasattr(g, "num_edges") else None,
             "split_s": {"plan_pack": t_plan, "gpu_incl_copies_gather": t_gpu, "splice": t_apply},
             "host_share": (t_plan + t_apply) / max(total, 1e-9), "graph_build_s": t_build, "data": "synthetic",
