@@ -338,6 +338,24 @@ spg_status spg_round_finish(spg_ctx *ctx, spg_round_out *out, spg::RoundRun &run
     return SPG_OK;
 }
 
+uint64_t *spg_ctx_pinned(spg_ctx *ctx, int slot, size_t words) {
+    if(!ctx || slot < 0 || slot > 1) return nullptr;
+    if(words <= ctx->h_pinned_words[slot]) return static_cast<uint64_t *>(ctx->h_pinned[slot]);
+    cudaSetDevice(ctx->device);
+    if(ctx->h_pinned[slot]) cudaFreeHost(ctx->h_pinned[slot]);
+    ctx->h_pinned[slot] = nullptr;
+    ctx->h_pinned_words[slot] = 0;
+    const size_t want = words + words / 2 + 4096;
+    void *q = nullptr;
+    if(cudaHostAlloc(&q, want * 8, cudaHostAllocDefault) != cudaSuccess) {
+        (void) cudaGetLastError();
+        return nullptr;
+    }
+    ctx->h_pinned[slot] = q;
+    ctx->h_pinned_words[slot] = want;
+    return static_cast<uint64_t *>(q);
+}
+
 extern "C" {
 
 const char *spg_version(void) { return "sparsifyposegraph_b200 0.1 (sm_100a)"; }
@@ -387,6 +405,10 @@ void spg_destroy(spg_ctx *ctx) {
     for(DevBuf *b : {&ctx->d_rec, &ctx->d_recoff, &ctx->d_outoff, &ctx->d_out, &ctx->d_list, &ctx->d_tgt,
                      &ctx->d_tgtoff, &ctx->d_wts, &ctx->d_wtsoff, &ctx->d_ws, &ctx->d_gws, &ctx->d_prof, &ctx->d_retry, &ctx->d_retry_cnt})
         b->release();
+    for(void *&hp : ctx->h_pinned) {
+        if(hp) cudaFreeHost(hp);
+        hp = nullptr;
+    }
     if(ctx->ev0) cudaEventDestroy(ctx->ev0);
     if(ctx->ev1) cudaEventDestroy(ctx->ev1);
     for(cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);

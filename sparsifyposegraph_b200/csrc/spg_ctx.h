@@ -65,7 +65,13 @@ struct spg_ctx {
     cudaEvent_t ev_g0 = nullptr, ev_g1 = nullptr; // timing of the gathers of the last call
     double last_gather_ms = 0;
     int64_t last_gather_bytes = 0;
+    // page-locked staging of the graph level (round records, round outputs): kept for the life of the context, since
+    // cudaHostAlloc / cudaFreeHost of hundreds of MB per spg_graph_marginalize call cost more than a small graph does
+    void *h_pinned[2] = {nullptr, nullptr};
+    size_t h_pinned_words[2] = {0, 0};
 };
+// grow-only page-locked buffer `slot` (0: records, 1: outputs) of at least `words` 8-byte words; NULL on failure
+uint64_t *spg_ctx_pinned(spg_ctx *ctx, int slot, size_t words);
 
 // host-buffer round, shared between spg_remove_round (spg_capi.cu) and spg_remove_round_sharded (spg_comm.cu)
 namespace spg {

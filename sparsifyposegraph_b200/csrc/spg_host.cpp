@@ -22,6 +22,7 @@
 #include <cuda_runtime.h>
 
 #include "../../include/spg_record.h"
+#include "spg_ctx.h"
 
 namespace spg {
 
@@ -349,7 +350,7 @@ bool VertexRemover::buildUnit(int root, int listIndex, const std::set<int> &toRe
         static thread_local std::vector<std::pair<int, int>> mb;                    // (id, vertex index) of the blanket
         static thread_local std::vector<std::pair<unsigned long long, int>> keyed;  // (canonical order key, edge)
         const std::vector<GraphVertex> &V = _graph->verts;
-        const std::vector<GraphEdge> &E = _graph->edges;
+        const ChunkedVector<GraphEdge> &E = _graph->edges;
         if(mark.size() < V.size()) mark.resize(V.size() + V.size() / 4 + 64, 0);
         if(++token == 0) { std::fill(mark.begin(), mark.end(), 0u); token = 1; }
         const int ri = _graph->indexOf(root);
@@ -610,7 +611,8 @@ std::vector<int> VertexRemover::remove(const std::vector<int> &toRemove, spg_sta
         st = planRound();
         if(st != SPG_OK || _round.sel.empty()) break;
         auto t1 = clk::now();
-        uint64_t *out = _outBuf.reserve((size_t) _round.outOff.back()); // every word is written by the kernels
+        uint64_t *out = spg_ctx_pinned(_ctx, 1, (size_t) _round.outOff.back()); // every word is written by the kernels
+        if(!out) out = _outBuf.reserve((size_t) _round.outOff.back());
         if(!out) {
             error = "out of host memory";
             st = SPG_ERR_INVALID;
@@ -702,7 +704,7 @@ spg_round_in VertexRemover::roundDescriptor() const {
     rin.opts.flags = _opts.flags | (_round.poseOnly ? SPG_OPT_POSE_EDGES_ONLY : 0);
     rin.n_blankets = (int32_t) _round.sel.size();
     rin.rec_off = _round.recOff.data();
-    rin.records = _round.records.p;
+    rin.records = _round.rec;
     rin.out_off = _round.outOff.data();
     return rin;
 }
@@ -764,15 +766,21 @@ spg_status VertexRemover::planRound() {
     // ---- re-extract the stale cached blankets of the window (reads the graph only: spread over the host threads) ---
     {
         std::vector<int> todo;
-        for(int i : win) {
-            const RemovalUnit &u = _unitCache[i];
-            bool stale = !_unitBuilt[i];
-            if(!stale) {
-                for(int xi : u.ridx) if(_stamp[xi] >= _unitBuilt[i]) { stale = true; break; }
-                if(!stale) for(int xi : u.kidx) if(_stamp[xi] >= _unitBuilt[i]) { stale = true; break; }
+        std::vector<char> staleFlag(win.size(), 0);
+        parallelFor(win.size(), 4096, [&](size_t b0, size_t b1) {
+            for(size_t q = b0; q < b1; q++) {
+                const int i = win[q];
+                const RemovalUnit &u = _unitCache[i];
+                bool stale = !_unitBuilt[i];
+                if(!stale) {
+                    for(int xi : u.ridx) if(_stamp[xi] >= _unitBuilt[i]) { stale = true; break; }
+                    if(!stale) for(int xi : u.kidx) if(_stamp[xi] >= _unitBuilt[i]) { stale = true; break; }
+                }
+                staleFlag[q] = stale;
             }
-            if(stale) todo.push_back(i);
-        }
+        });
+        for(size_t q = 0; q < win.size(); q++)
+            if(staleFlag[q]) todo.push_back(win[q]);
         g_prof.stale += nowS() - tp0; tp0 = nowS();
         g_prof.n_extract += (long long) todo.size();
         g_prof.n_visit += (long long) win.size();
@@ -895,7 +903,9 @@ spg_status VertexRemover::planRound() {
         recOff[q + 1] += recOff[q];
     }
     stats.max_blanket_vertices = maxv;
-    uint64_t *rec = _round.records.reserve((size_t) recOff[ns]);
+    uint64_t *rec = _ctx ? spg_ctx_pinned(_ctx, 0, (size_t) recOff[ns]) : nullptr; // the context keeps its staging buffers
+    if(!rec) rec = _round.records.reserve((size_t) recOff[ns]);
+    _round.rec = rec;
     if(!rec) {
         error = "out of host memory";
         return SPG_ERR_INVALID;
@@ -934,7 +944,7 @@ void VertexRemover::applyRound(const uint64_t *out) {
     const std::vector<int> &sel = _round.sel;
     const size_t ns = sel.size();
     std::vector<GraphVertex> &V = _graph->verts;
-    std::vector<GraphEdge> &E = _graph->edges;
+    ChunkedVector<GraphEdge> &E = _graph->edges;
 
     // ---- pass 1 (sequential, headers only): status bookkeeping, staleness stamps, edge indices of the substitutes --
     std::vector<int> base(ns + 1, 0); // new edges of unit ui go to E[e0 + base[ui] ...); failed units add none

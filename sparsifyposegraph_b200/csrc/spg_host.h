@@ -102,6 +102,33 @@ struct GraphEdge {
     int vx(int q) const { return v.size() <= 2 ? (q == 0 ? vx0 : vx1) : vxn[q]; }
     unsigned long long uidKey() const { return ((unsigned long long) (unsigned) (uidMajor + 1) << 32) | (unsigned) uidMinor; }
 };
+// edge store: fixed-size blocks, so growing never moves an edge (a std::vector of ~150-byte edges re-touches gigabytes on
+// every doubling of a million-pose graph) and references stay valid while other threads append
+template <class T, int LOG2 = 14>
+class ChunkedVector {
+public:
+    ChunkedVector() {}
+    ChunkedVector(const ChunkedVector &) = delete;
+    ChunkedVector &operator=(const ChunkedVector &) = delete;
+    ~ChunkedVector() { for(T *b : _blocks) delete[] b; }
+    size_t size() const { return _n; }
+    T &operator[](size_t i) { return _blocks[i >> LOG2][i & MASK]; }
+    const T &operator[](size_t i) const { return _blocks[i >> LOG2][i & MASK]; }
+    T &back() { return (*this)[_n - 1]; }
+    void resize(size_t n) { // grow only (default-constructed elements)
+        while(_blocks.size() << LOG2 < n) _blocks.push_back(new T[(size_t) 1 << LOG2]);
+        if(n > _n) _n = n;
+    }
+    void push_back(T &&x) {
+        resize(_n + 1);
+        (*this)[_n - 1] = std::move(x);
+    }
+private:
+    static constexpr size_t MASK = ((size_t) 1 << LOG2) - 1;
+    std::vector<T *> _blocks;
+    size_t _n = 0;
+};
+
 struct GraphVertex {
     int id = 0;
     double pose[7] = {0, 0, 0, 0, 0, 0, 1};
@@ -122,7 +149,7 @@ public:
     unsigned long long serial = 0, version = 0; // identity and mutation count (caches of derived orders key on these)
     int poseWords() const { return dim == 3 ? 3 : 7; }
     std::vector<GraphVertex> verts;
-    std::vector<GraphEdge> edges;
+    ChunkedVector<GraphEdge> edges;
     // id -> verts index: a dense table for ids in [0, 2^26), a hash map for anything else
     std::vector<int> dense;
     std::unordered_map<int, int> sparse;
@@ -229,7 +256,8 @@ public:
     // roundDescriptor / applyRound until planRound leaves an empty round
     struct Round {
         std::vector<int> sel;        // selected units: indices into the removal list, ascending
-        HostBuf records;
+        HostBuf records;             // used when the remover has no context (rounds planned for a caller-run engine)
+        uint64_t *rec = nullptr;     // the packed records of this round (context staging buffer, or `records`)
         std::vector<int64_t> recOff, outOff;
         int algorithm = SPG_ALG_NFR;
         bool poseOnly = false;       // every blanket edge of the round is a POSE edge (SPG_OPT_POSE_EDGES_ONLY)
