@@ -206,6 +206,17 @@ int64_t spg_out_slot_words(int32_t dim, int32_t algorithm, const spg_sparsity_op
 spg_status spg_remove_round(spg_ctx *ctx, const spg_round_in *in, spg_round_out *out);
 
 /*
+ * The same call with the records produced on demand: `in->rec_off` / `in->out_off` are complete, `in->records` points at
+ * a buffer of rec_off[n_blankets] words that `fill(user, b0, b1)` fills for blankets [b0, b1) (return 0; anything else
+ * aborts with SPG_ERR_INVALID). fill is called once per pipeline chunk, in order, on the calling thread, right before
+ * the chunk is validated and copied — so packing chunk c+1 overlaps the GPU work on chunk c. A VertexRemover adapter
+ * packs straight from its graph structures this way (spg_graph_marginalize does). Page-locked buffers make the copies
+ * asynchronous.
+ */
+typedef int32_t (*spg_fill_fn)(void *user, int32_t first_blanket, int32_t end_blanket);
+spg_status spg_remove_round_streamed(spg_ctx *ctx, const spg_round_in *in, spg_round_out *out, spg_fill_fn fill, void *user);
+
+/*
  * Same, but every pointer inside in/out is a DEVICE pointer already resident in HBM
  * (rec_off/out_off too). Asynchronous on the context stream; call spg_sync().
  * The records cannot be validated from the host here: the caller states the largest blanket of the round

@@ -345,7 +345,8 @@ uint64_t *spg_ctx_pinned(spg_ctx *ctx, int slot, size_t words) {
     if(ctx->h_pinned[slot]) cudaFreeHost(ctx->h_pinned[slot]);
     ctx->h_pinned[slot] = nullptr;
     ctx->h_pinned_words[slot] = 0;
-    const size_t want = words + words / 2 + 4096;
+    // page-locking costs ~0.3 ms per MB: grow by doubling from 8 MB so that a removal re-pins at most a couple of times
+    const size_t want = std::max<size_t>(2 * words, (size_t) 1 << 20);
     void *q = nullptr;
     if(cudaHostAlloc(&q, want * 8, cudaHostAllocDefault) != cudaSuccess) {
         (void) cudaGetLastError();
@@ -540,6 +541,10 @@ spg_status spg_remove_round_device(spg_ctx *ctx, const spg_round_in *in, spg_rou
 }
 
 spg_status spg_remove_round(spg_ctx *ctx, const spg_round_in *in, spg_round_out *out) {
+    return spg_remove_round_streamed(ctx, in, out, nullptr, nullptr);
+}
+
+spg_status spg_remove_round_streamed(spg_ctx *ctx, const spg_round_in *in, spg_round_out *out, spg_fill_fn fill, void *user) {
     if(check_device(ctx) != SPG_OK) return SPG_ERR_INVALID;
     if(!in || !out || !out->out || (in->dim != 3 && in->dim != 6) || in->n_blankets < 0) {
         set_err("bad round descriptor");
@@ -571,6 +576,13 @@ spg_status spg_remove_round(spg_ctx *ctx, const spg_round_in *in, spg_round_out 
     for(int c = 0; c < nchunks; c++) {
         const int b0 = cb[c], b1 = cb[c + 1];
         if(b1 <= b0) continue;
+        // streamed rounds: the caller writes the records of this chunk now, while the GPU works on the previous ones
+        if(fill && fill(user, b0, b1) != 0) {
+            cudaDeviceSynchronize();
+            set_err("the record producer of spg_remove_round_streamed failed on blankets [" + std::to_string(b0) + ", " +
+                    std::to_string(b1) + ")");
+            return SPG_ERR_INVALID;
+        }
         st = spg_round_enqueue_chunk(ctx, in, run, b0, b1, c);
         if(st != SPG_OK) return st;
         // ---- D2H of the chunk -----------------------------------------------------------------------

@@ -586,6 +586,19 @@ static void parallelFor(size_t n, size_t min_per_thread, F fn) {
     for(auto &th : pool) th.join();
 }
 
+namespace {
+struct HostProf {
+    double stale = 0, extract = 0, select = 0, pack = 0, apply = 0;
+    long long n_extract = 0, n_visit = 0, n_sel = 0;
+    double a1 = 0, a2 = 0, a3 = 0;
+    bool on = getenv("SPG_HOST_PROF") != nullptr;
+    ~HostProf() {
+        if(on) fprintf(stderr, "[spg host] stale-check %.3f s, extract %.3f s, select %.3f s, pack %.3f s, splice %.3f s; %lld extractions, %lld window visits, %lld selected; splice passes %.3f %.3f %.3f\n", stale, extract, select, pack, apply, n_extract, n_visit, n_sel, a1, a2, a3);
+    }
+} g_prof;
+inline double nowS() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+} // namespace
+
 std::vector<int> VertexRemover::remove(int toRemove, spg_status *status) {
     return remove(std::vector<int>(1, toRemove), status);
 }
@@ -608,7 +621,8 @@ std::vector<int> VertexRemover::remove(const std::vector<int> &toRemove, spg_sta
     spg_status st = beginRemoval(toRemove);
     while(st == SPG_OK) {
         auto t0 = clk::now();
-        st = planRound();
+        const bool sharded = spg_comm_nranks(_ctx) > 1;
+        st = planRound(sharded); // one GPU: the records are packed chunk by chunk inside the streamed call below
         if(st != SPG_OK || _round.sel.empty()) break;
         auto t1 = clk::now();
         uint64_t *out = spg_ctx_pinned(_ctx, 1, (size_t) _round.outOff.back()); // every word is written by the kernels
@@ -621,9 +635,29 @@ std::vector<int> VertexRemover::remove(const std::vector<int> &toRemove, spg_sta
         spg_round_in rin = roundDescriptor();
         spg_round_out rout{};
         rout.out = out;
-        // a context with a communicator (spg_comm_init) shards every round over its ranks; all ranks hold the same
-        // graph, get the complete output (all-gather) and splice the same edges
-        st = spg_comm_nranks(_ctx) > 1 ? spg_remove_round_sharded(_ctx, &rin, &rout, -1, nullptr) : spg_remove_round(_ctx, &rin, &rout);
+        if(sharded) {
+            // a context with a communicator (spg_comm_init) shards every round over its ranks; all ranks hold the same
+            // graph, get the complete output (all-gather) and splice the same edges
+            st = spg_remove_round_sharded(_ctx, &rin, &rout, -1, nullptr);
+        } else {
+            struct Fill {
+                VertexRemover *self;
+                static int32_t fn(void *u, int32_t b0, int32_t b1) {
+                    VertexRemover *vr = static_cast<Fill *>(u)->self;
+                    const double t = nowS();
+                    const bool ok = vr->packRange((size_t) b0, (size_t) b1);
+                    g_prof.pack += nowS() - t;
+                    if(!ok) vr->_packFailed = true;
+                    return ok ? 0 : 1;
+                }
+            } fill{this};
+            _packFailed = false;
+            st = spg_remove_round_streamed(_ctx, &rin, &rout, &Fill::fn, &fill);
+            if(_packFailed) { // `error` names the reason (packRange); nothing of this round was applied
+                st = SPG_ERR_UNSUPPORTED;
+                break;
+            }
+        }
         if(st != SPG_OK) {
             error = spg_last_error();
             break;
@@ -709,18 +743,6 @@ spg_round_in VertexRemover::roundDescriptor() const {
     return rin;
 }
 
-namespace {
-struct HostProf {
-    double stale = 0, extract = 0, select = 0, pack = 0, apply = 0;
-    long long n_extract = 0, n_visit = 0, n_sel = 0;
-    double a1 = 0, a2 = 0, a3 = 0;
-    bool on = getenv("SPG_HOST_PROF") != nullptr;
-    ~HostProf() {
-        if(on) fprintf(stderr, "[spg host] stale-check %.3f s, extract %.3f s, select %.3f s, pack %.3f s, splice %.3f s; %lld extractions, %lld window visits, %lld selected; splice passes %.3f %.3f %.3f\n", stale, extract, select, pack, apply, n_extract, n_visit, n_sel, a1, a2, a3);
-    }
-} g_prof;
-inline double nowS() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
-} // namespace
 
 // Select and pack the next wavefront round (empty round: nothing left).
 //
@@ -732,7 +754,7 @@ inline double nowS() { return std::chrono::duration<double>(std::chrono::steady_
 // WINDOW — the units deferred so far plus the next entries of the list — which keeps the per-round work (staleness
 // test, blanket re-extraction, selection) proportional to the window instead of to everything still pending. Any such
 // schedule ends in the same graph (the units of a round commute with each other and with everything before them).
-spg_status VertexRemover::planRound() {
+spg_status VertexRemover::planRound(bool packNow) {
     _round.sel.clear();
     _round.recOff.assign(1, 0);
     _round.outOff.assign(1, 0);
@@ -910,18 +932,7 @@ spg_status VertexRemover::planRound() {
         error = "out of host memory";
         return SPG_ERR_INVALID;
     }
-    std::atomic<int> badPack(-1);
-    parallelFor(ns, 1024, [&](size_t b0, size_t b1) {
-        for(size_t q = b0; q < b1; q++)
-            if(!packUnit(_unitCache[sel[q]], rec + recOff[q], recOff[q + 1] - recOff[q])) {
-                int expect = -1;
-                badPack.compare_exchange_strong(expect, (int) q);
-            }
-    });
-    if(badPack.load() >= 0) {
-        error = "Local linearisation point on a non-star blanket needs the subgraph optimiser (not on this path)";
-        return SPG_ERR_UNSUPPORTED;
-    }
+    if(packNow && !packRange(0, ns)) return SPG_ERR_UNSUPPORTED;
     g_prof.pack += nowS() - tp0;
     _round.algorithm = tp->algorithm();
     _round.poseOnly = (allMask == (1u << SPG_EDGE_POSE));
@@ -934,6 +945,26 @@ spg_status VertexRemover::planRound() {
         }
     }
     return SPG_OK;
+}
+
+// records of the selected units [q0, q1) of the planned round, written in place by the host threads
+bool VertexRemover::packRange(size_t q0, size_t q1) {
+    const std::vector<int> &sel = _round.sel;
+    const std::vector<int64_t> &recOff = _round.recOff;
+    uint64_t *rec = _round.rec;
+    std::atomic<int> badPack(-1);
+    parallelFor(q1 - q0, 1024, [&](size_t b0, size_t b1) {
+        for(size_t q = q0 + b0; q < q0 + b1; q++)
+            if(!packUnit(_unitCache[sel[q]], rec + recOff[q], recOff[q + 1] - recOff[q])) {
+                int expect = -1;
+                badPack.compare_exchange_strong(expect, (int) q);
+            }
+    });
+    if(badPack.load() >= 0) {
+        error = "Local linearisation point on a non-star blanket needs the subgraph optimiser (not on this path)";
+        return false;
+    }
+    return true;
 }
 
 // Splice the output records of the planned round, in list order (updateInputGraph,

@@ -212,13 +212,39 @@ typedef TopologyProviderBinary<6> TopologyProviderSE3ISAM; // (graph_wrapper_g2o
 typedef TopologyProviderBinary<3> TopologyProviderSE2;
 typedef TopologyProviderBinary<6> TopologyProviderSE3;
 
+// small int list with N entries inline: the scheduler's per-unit vertex lists are read every round for every unit of the
+// window, and a heap hop per list is a cache miss per unit
+template <int N>
+class InlineInts {
+public:
+    size_t size() const { return _n; }
+    bool empty() const { return _n == 0; }
+    void clear() { _n = 0; _more.clear(); }
+    void push_back(int x) {
+        if(_n < (unsigned) N) _in[_n] = x;
+        else {
+            if(_n == (unsigned) N) _more.assign(_in, _in + N);
+            _more.push_back(x);
+        }
+        _n++;
+    }
+    const int *begin() const { return _n <= (unsigned) N ? _in : _more.data(); }
+    const int *end() const { return begin() + _n; }
+    int operator[](size_t i) const { return begin()[i]; }
+private:
+    int _in[N];
+    unsigned _n = 0;
+    std::vector<int> _more;
+};
+
 // ---- VertexRemover ---------------------------------------------------------------------------------
 struct RemovalUnit {
     int listIndex = 0;               // index of the root in the removal list
     std::vector<int> removed;        // ascending id (toRemoveNow)
     std::vector<int> kept;           // ascending id
     std::vector<int> edges;          // blanket edges, canonical order
-    std::vector<int> ridx, kidx;     // Graph::verts indices of removed / kept (scheduler: no id lookups per round)
+    InlineInts<2> ridx;              // Graph::verts indices of removed / kept (scheduler: no id lookups per round)
+    InlineInts<20> kidx;
 };
 
 // growable host buffer of 8-byte words: page-locked when a CUDA device is present, plain memory otherwise
@@ -263,7 +289,9 @@ public:
         bool poseOnly = false;       // every blanket edge of the round is a POSE edge (SPG_OPT_POSE_EDGES_ONLY)
     };
     spg_status beginRemoval(const std::vector<int> &toRemove);
-    spg_status planRound();
+    spg_status planRound(bool packNow = true);
+    bool _packFailed = false;
+    bool packRange(size_t q0, size_t q1); // pack the selected units [q0, q1) of the planned round (planRound(false))
     spg_round_in roundDescriptor() const;
     void applyRound(const uint64_t *out);
     spg_status failureStatus(); // SPG_OK, or SPG_ERR_BLANKET_FAILED (+ error text) once a blanket failed
