@@ -307,8 +307,21 @@ typedef struct spg_graph spg_graph;
 
 spg_status spg_graph_create(spg_graph **g, int32_t dim);
 void spg_graph_destroy(spg_graph *g);
-/* reads VERTEX_SE2/EDGE_SE2/VERTEX_SE3:QUAT/EDGE_SE3:QUAT (src/graph_wrapper_g2o.cpp:107-147) */
+/* reads VERTEX_SE2/EDGE_SE2/VERTEX_SE3:QUAT/EDGE_SE3:QUAT (src/graph_wrapper_g2o.cpp:107-147) and the factor types of
+ * a saved sparsified graph: EDGE_SE2_ISAM, GLC_EDGE with GLC_REPARAM_{SE2_ISAM,SE2,SE3} (src/glc_edge.cpp:64-118),
+ * MULTI_EDGE_{SE2,SE2_ISAM,SE3,SE3_ISAM} (src/multi_edge_correlated.hpp:183-267; tags src/edge_types.cpp:68-76) */
 spg_status spg_graph_load_g2o(spg_graph **g, const char *path);
+/* GraphWrapperG2O::write (src/graph_wrapper_g2o.cpp:467-470): the same text format, 17 significant digits. A multi-edge
+ * is preceded by a comment line "#SPG_MULTI_PAIRS .." with the vertex pair of every measurement (the reference's
+ * format drops them; stock g2o skips comment lines). */
+spg_status spg_graph_save_g2o(const spg_graph *g, const char *path);
+/* generic factor (an adapter copying GLCEdge / MultiEdgeCorrelated objects out of g2o): kind = spg_edge_kind;
+ * POSE: nv 2, rows d, meas P, info d*d column-major; GLC: meas d*nv, W rows x d*nv row-major; MULTI: rows = d*nmeas,
+ * meas nmeas*P, info rows*rows column-major, pairs = 2*nmeas indices into vert_ids (NULL otherwise) */
+spg_status spg_graph_add_factor(spg_graph *g, int32_t kind, int32_t nv, const int32_t *vert_ids, int32_t rows,
+                                const double *meas, const double *info_or_w, const int32_t *pairs);
+/* MULTI edges: the 2*nmeas vertex-list indices of the measurements (see spg_graph_edge_desc for sizes) */
+spg_status spg_graph_edge_pairs(const spg_graph *g, int32_t idx, int32_t *pairs);
 spg_status spg_graph_add_vertex(spg_graph *g, int32_t id, const double *pose);
 spg_status spg_graph_add_edge(spg_graph *g, int32_t from, int32_t to, const double *meas,
                               const double *info /* d*d column-major */);

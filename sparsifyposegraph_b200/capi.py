@@ -266,6 +266,9 @@ def _graph_protos(L):
     L.spg_graph_create.argtypes = [C.POINTER(C.c_void_p), C.c_int32]
     L.spg_graph_destroy.argtypes = [C.c_void_p]
     L.spg_graph_load_g2o.argtypes = [C.POINTER(C.c_void_p), C.c_char_p]
+    L.spg_graph_save_g2o.argtypes = [C.c_void_p, C.c_char_p]
+    L.spg_graph_add_factor.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.spg_graph_edge_pairs.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
     L.spg_graph_add_vertex.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
     L.spg_graph_add_edge.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
     for f in ("spg_graph_dim", "spg_graph_num_vertices", "spg_graph_num_edges", "spg_graph_max_vertex_id"):
@@ -315,6 +318,19 @@ class Graph:
         m = np.ascontiguousarray(meas, dtype=np.float64)
         i = np.ascontiguousarray(np.asarray(info, dtype=np.float64).T)
         _check(lib().spg_graph_add_edge(self.h, int(a), int(b), _p(m), _p(i)))
+
+    def add_factor(self, kind, verts, rows, meas, info, pairs=None):
+        """Generic factor (spg_graph_add_factor). info: POSE / MULTI symmetric matrix, GLC the W matrix (rows x d*nv)."""
+        v = np.ascontiguousarray(verts, dtype=np.int32)
+        m = np.ascontiguousarray(meas, dtype=np.float64).reshape(-1)
+        i = np.asarray(info, dtype=np.float64)
+        i = np.ascontiguousarray(i.T if kind != 1 else i).reshape(-1)   # column-major for POSE / MULTI, row-major W
+        pr = np.ascontiguousarray(pairs, dtype=np.int32) if pairs is not None else None
+        _check(lib().spg_graph_add_factor(self.h, int(kind), len(v), _p(v), int(rows), _p(m), _p(i), _p(pr)))
+
+    def save(self, path):
+        """GraphWrapperG2O::write: g2o text with GLC_EDGE / MULTI_EDGE_* factors."""
+        _check(lib().spg_graph_save_g2o(self.h, os.fsencode(path)))
 
     @property
     def num_vertices(self):
@@ -372,8 +388,12 @@ class Graph:
                 info = info.reshape(d.rows, self.dim * d.nv)
             else:
                 info = info.reshape(d.rows, d.rows).T
-            res.append({"kind": d.kind, "v": ids, "rows": d.rows, "uid": (d.uid_major, d.uid_minor), "meas": meas,
-                        "info": info})
+            rec = {"kind": d.kind, "v": ids, "rows": d.rows, "uid": (d.uid_major, d.uid_minor), "meas": meas, "info": info}
+            if d.kind == 2:
+                pr = np.zeros(2 * (d.rows // self.dim), dtype=np.int32)
+                _check(L.spg_graph_edge_pairs(self.h, i, _p(pr)))
+                rec["pairs"] = pr
+            res.append(rec)
         return res
 
     def compute_substitute_edge(self, marginalized, maxid, frm, to):

@@ -126,6 +126,29 @@ __device__ bool glc_marginal(const double *T, int k, int ldT, int va, int vb, in
         gsync<NT>();
         return true;
     }
+    // Register-tiled partial sweep (spg_device.cuh): T permuted to [rest, keep], the nr rest pivots swept, and the
+    // trailing block is S — the same Schur complement as the LLT route below at a fraction of its barriers (the LLT
+    // route factors T_rr cooperatively but solves with one thread per right-hand side: c of NT threads busy).
+    if(sweep_fits<NT>(k)) {
+        const int ldp = odd_ld(k);
+        auto permIdx = [&](int i) { return i < nr ? restIdx(i) : keepIdx(i - nr); };
+        for(int t = tid; t < k * k; t += NT) {
+            const int i = t % k, j = t / k;
+            work[i + j * ldp] = T[permIdx(i) + (size_t) permIdx(j) * ldT];
+        }
+        gsync<NT>();
+        const int r = sweep_spd_auto<D, NT>(work, ldp, work, ldp, k, nr, xs);
+        if(r == 0) return false;
+        if(r == 1) {
+            for(int t = tid; t < c * c; t += NT) {
+                const int i = t % c, j = t / c;
+                const int a = i <= j ? i : j, b = i <= j ? j : i; // upper triangle mirrored
+                S[i + j * c] = work[(nr + a) + (size_t) (nr + b) * ldp];
+            }
+            gsync<NT>();
+            return true;
+        }
+    }
     for(int t = tid; t < nr * nr; t += NT) {
         const int i = t % nr, j = t / nr;
         work[i + j * ldw] = T[restIdx(i) + (size_t) restIdx(j) * ldT];

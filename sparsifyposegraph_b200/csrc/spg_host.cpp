@@ -227,7 +227,28 @@ std::vector<int> Graph::edgeOrder() const {
     return o;
 }
 
-// g2o text reader for the four tags the reference's datasets use (graph_wrapper_g2o.cpp:107-147).
+// g2o text I/O. Reader: the four tags of the reference's datasets (graph_wrapper_g2o.cpp:107-147) plus the factor types a
+// sparsified graph carries when the reference saves it (GraphWrapperG2O::write -> g2o save, tags registered in
+// src/edge_types.cpp:68-76):
+//   EDGE_SE2_ISAM a b  x y th  <upper info>                                  (EdgeSE2ISAM, se2_compatibility.h)
+//   GLC_EDGE v0 v1 .. || GLC_REPARAM_{SE2_ISAM,SE2,SE3} rows cols  meas[cols]  W[rows x cols, row-major]  <upper I_rows>
+//                                                                            (GLCEdge::write, src/glc_edge.cpp:94-118)
+//   MULTI_EDGE_{SE2,SE2_ISAM,SE3,SE3_ISAM} v0 v1 .. || nmeas nrelevant  (meas tokens) x nmeas  <upper info, d*nmeas>
+//                                                                            (MultiEdgeCorrelated::write, multi_edge_correlated.hpp:226-267)
+// The reference's multi-edge writer does not store which vertices each measurement connects (_mappings), so its own
+// reader cannot restore them either; the writer here puts them on a comment line in front of the edge
+// ("#SPG_MULTI_PAIRS a0 b0 a1 b1 ..", indices into the edge's vertex list), which stock g2o skips and this reader uses.
+static bool readUpper(std::istream &is, int n, double *full) {
+    for(int i = 0; i < n; i++)
+        for(int j = i; j < n; j++) {
+            double v;
+            if(!(is >> v)) return false;
+            full[i + j * n] = v;
+            full[j + i * n] = v;
+        }
+    return true;
+}
+
 Graph *Graph::loadG2o(const std::string &path, std::string *err) {
     std::ifstream f(path);
     if(!f) {
@@ -235,42 +256,171 @@ Graph *Graph::loadG2o(const std::string &path, std::string *err) {
         return nullptr;
     }
     Graph *g = nullptr;
-    struct Pend { int a, b; double z[7]; double info[36]; };
-    std::vector<Pend> pend;
+    std::vector<GraphEdge> pend; // edges may precede their vertices in a file
+    std::vector<int> pendingPairs;
     std::string line;
+    int lineNo = 0;
+    auto fail = [&](const std::string &what) -> Graph * {
+        if(err) *err = path + ":" + std::to_string(lineNo) + ": " + what;
+        delete g;
+        return nullptr;
+    };
     while(std::getline(f, line)) {
+        lineNo++;
         std::istringstream is(line);
         std::string tag;
         if(!(is >> tag)) continue;
+        if(tag == "#SPG_MULTI_PAIRS") {
+            pendingPairs.clear();
+            int x;
+            while(is >> x) pendingPairs.push_back(x);
+            continue;
+        }
+        if(tag[0] == '#') continue;
         if(tag == "VERTEX_SE2" || tag == "VERTEX_SE3:QUAT") {
             int d = tag == "VERTEX_SE2" ? 3 : 6;
             if(!g) g = new Graph(d);
+            if(g->dim != d) return fail("vertex dimension differs from the graph's");
             int id;
             double p[7] = {0, 0, 0, 0, 0, 0, 1};
             is >> id;
             for(int i = 0; i < g->poseWords(); i++) is >> p[i];
+            if(!is) return fail("short vertex line");
             g->addVertex(id, p);
-        } else if(tag == "EDGE_SE2" || tag == "EDGE_SE3:QUAT") {
-            int d = tag == "EDGE_SE2" ? 3 : 6, P = d == 3 ? 3 : 7;
-            Pend pe;
-            is >> pe.a >> pe.b;
-            for(int i = 0; i < P; i++) is >> pe.z[i];
-            for(int i = 0; i < d; i++)
-                for(int j = i; j < d; j++) {
-                    double v;
-                    is >> v;
-                    pe.info[i + j * d] = v;
-                    pe.info[j + i * d] = v;
-                }
-            pend.push_back(pe);
+        } else if(tag == "EDGE_SE2" || tag == "EDGE_SE2_ISAM" || tag == "EDGE_SE3:QUAT") {
+            int d = tag == "EDGE_SE3:QUAT" ? 6 : 3, P = d == 3 ? 3 : 7;
+            GraphEdge e;
+            int a, b;
+            double z[7], info[36];
+            is >> a >> b;
+            for(int i = 0; i < P; i++) is >> z[i];
+            if(!is || !readUpper(is, d, info)) return fail("short edge line");
+            e.kind = SPG_EDGE_POSE;
+            e.v = {a, b};
+            e.rows = d;
+            e.setPayload(z, P, info, d * d);
+            pend.push_back(std::move(e));
+        } else if(tag == "GLC_EDGE" || tag.rfind("MULTI_EDGE_", 0) == 0) {
+            GraphEdge e;
+            std::string tok;
+            while(is >> tok && tok != "||") e.v.push_back(atoi(tok.c_str()));
+            if(tok != "||" || e.v.empty()) return fail("multi-vertex edge without the '||' separator");
+            if(tag == "GLC_EDGE") {
+                std::string reparam;
+                int rows = 0, cols = 0;
+                is >> reparam >> rows >> cols;
+                const int d = reparam == "GLC_REPARAM_SE3" ? 6 : 3;
+                if(!is || reparam.rfind("GLC_REPARAM_", 0) != 0 || rows < 0 || cols != d * (int) e.v.size())
+                    return fail("bad GLC_EDGE header");
+                e.kind = SPG_EDGE_GLC;
+                e.rows = rows;
+                e.allocPayload(cols, rows * cols);
+                for(int i = 0; i < cols; i++) is >> e.meas()[i];
+                for(int i = 0; i < rows * cols; i++) is >> e.info()[i];
+                std::vector<double> I((size_t) rows * rows);
+                if(!is || !readUpper(is, rows, I.data())) return fail("short GLC_EDGE line");
+                e.pairs.assign(1, d); // remembers the dimension until the graph exists
+            } else {
+                const int d = tag.find("SE3") != std::string::npos ? 6 : 3, P = d == 3 ? 3 : 7;
+                int nmeas = 0, nrel = 0;
+                is >> nmeas >> nrel;
+                if(!is || nmeas < 1 || nrel != P) return fail("bad MULTI_EDGE header");
+                if((int) pendingPairs.size() != 2 * nmeas)
+                    return fail("MULTI_EDGE without its #SPG_MULTI_PAIRS line: the reference's format does not store which "
+                                "vertices a measurement connects");
+                e.kind = SPG_EDGE_MULTI;
+                e.rows = d * nmeas;
+                e.allocPayload(nmeas * P, e.rows * e.rows);
+                for(int i = 0; i < nmeas * P; i++) is >> e.meas()[i];
+                if(!is || !readUpper(is, e.rows, e.info())) return fail("short MULTI_EDGE line");
+                e.pairs = pendingPairs;
+                for(int x : e.pairs)
+                    if(x < 0 || x >= (int) e.v.size()) return fail("#SPG_MULTI_PAIRS index out of range");
+                e.pairs.push_back(-d); // dimension marker, removed below
+                pendingPairs.clear();
+            }
+            pend.push_back(std::move(e));
         }
+        // FIX, PARAMS_* and unknown tags are skipped like g2o's loader skips unregistered ones
     }
     if(!g) {
         if(err) *err = "no vertices in " + path;
         return nullptr;
     }
-    for(const Pend &pe : pend) g->addPoseEdge(pe.a, pe.b, pe.z, pe.info);
+    lineNo = 0;
+    for(GraphEdge &e : pend) {
+        int d = g->dim;
+        if(e.kind == SPG_EDGE_POSE) d = e.rows;
+        else if(e.kind == SPG_EDGE_GLC) { d = e.pairs[0]; e.pairs.clear(); }
+        else { d = -e.pairs.back(); e.pairs.pop_back(); }
+        if(d != g->dim) return fail("edge dimension differs from the graph's");
+        for(int id : e.v)
+            if(!g->hasVertex(id)) return fail("edge refers to unknown vertex " + std::to_string(id));
+        if(e.kind == SPG_EDGE_POSE) {
+            if(g->dim == 3) e.meas()[2] = normalizeTheta(e.meas()[2]);
+            else qnorm(e.meas() + 3);
+        }
+        e.uidMajor = -1;
+        e.uidMinor = g->fileEdges++;
+        g->addEdge(std::move(e));
+    }
     return g;
+}
+
+// Writer: what GraphWrapperG2O::write (-> g2o's OptimizableGraph::save) emits for a graph of this wrapper — vertices in
+// ascending id, then edges in the canonical order, numbers with 17 significant digits (g2o's default stream precision
+// of 6 would not survive a round trip at the 1e-9 parity bar).
+bool Graph::saveG2o(const std::string &path, std::string *err) const {
+    std::ofstream f(path);
+    if(!f) {
+        if(err) *err = "cannot open " + path + " for writing";
+        return false;
+    }
+    f.precision(17);
+    const int P = poseWords();
+    for(int id : vertexIds()) {
+        const GraphVertex *v = vertex(id);
+        f << (dim == 3 ? "VERTEX_SE2 " : "VERTEX_SE3:QUAT ") << id;
+        for(int i = 0; i < P; i++) f << ' ' << v->pose[i];
+        f << '\n';
+    }
+    auto upper = [&](const double *M, int n) {
+        for(int i = 0; i < n; i++)
+            for(int j = i; j < n; j++) f << ' ' << M[i + j * n];
+    };
+    for(int ei : edgeOrder()) {
+        const GraphEdge &e = edges[ei];
+        if(e.kind == SPG_EDGE_POSE) {
+            f << (dim == 3 ? "EDGE_SE2_ISAM " : "EDGE_SE3:QUAT ") << e.v[0] << ' ' << e.v[1];
+            for(int i = 0; i < P; i++) f << ' ' << e.meas()[i];
+            upper(e.info(), dim);
+        } else if(e.kind == SPG_EDGE_GLC) {
+            f << "GLC_EDGE";
+            for(int id : e.v) f << ' ' << id;
+            const int cols = dim * e.nv();
+            f << " || " << (dim == 3 ? "GLC_REPARAM_SE2_ISAM " : "GLC_REPARAM_SE3 ") << e.rows << ' ' << cols;
+            for(int i = 0; i < cols; i++) f << ' ' << e.meas()[i];
+            for(int i = 0; i < e.rows * cols; i++) f << ' ' << e.info()[i];
+            for(int i = 0; i < e.rows; i++)
+                for(int j = i; j < e.rows; j++) f << ' ' << (i == j ? 1 : 0);
+        } else {
+            const int nmeas = e.rows / dim;
+            f << "#SPG_MULTI_PAIRS";
+            for(int x : e.pairs) f << ' ' << x;
+            f << '\n' << (dim == 3 ? "MULTI_EDGE_SE2_ISAM" : "MULTI_EDGE_SE3_ISAM");
+            for(int id : e.v) f << ' ' << id;
+            f << " || " << nmeas << ' ' << P;
+            for(int i = 0; i < nmeas * P; i++) f << ' ' << e.meas()[i];
+            upper(e.info(), e.rows);
+        }
+        f << '\n';
+    }
+    f.flush();
+    if(!f) {
+        if(err) *err = "write error on " + path;
+        return false;
+    }
+    return true;
 }
 
 // ---- VertexRemover --------------------------------------------------------------------------------
@@ -717,8 +867,17 @@ spg_status VertexRemover::beginRemoval(const std::vector<int> &toRemove) {
     _unitCache.assign(toRemove.size(), RemovalUnit());
     _unitBuilt.assign(toRemove.size(), 0);
     _rootIdx.assign(toRemove.size(), -1);
-    for(size_t i = 0; i < toRemove.size(); i++) {
-        _rootIdx[i] = _graph->indexOf(toRemove[i]);
+    _extended = _opts.topology == SparsityOptions::Dense || _opts.topology == SparsityOptions::CliqueyDense;
+    _dupInList.assign(toRemove.size(), 0);
+    {
+        std::vector<unsigned char> seen(_graph->verts.size(), 0);
+        for(size_t i = 0; i < toRemove.size(); i++) {
+            _rootIdx[i] = _graph->indexOf(toRemove[i]);
+            if(_rootIdx[i] >= 0) {
+                if(seen[_rootIdx[i]]) _dupInList[i] = 1;
+                seen[_rootIdx[i]] = 1;
+            }
+        }
     }
     _stamp.assign(_graph->verts.size(), 0);
     _touchHead.assign(_graph->verts.size(), -1);
@@ -773,7 +932,10 @@ spg_status VertexRemover::planRound(bool packNow) {
     win.reserve(_leftover.size() + W);
     auto admit = [&](int i) {
         if(_done[i]) return;
-        if(_rootIdx[i] < 0 || !_graph->verts[_rootIdx[i]].alive) { // merged into an earlier extended blanket (:91)
+        // gone already: merged into an earlier extended blanket (:91), or listed twice. (Single-removal topologies can
+        // only lose a listed vertex through its own entry, i.e. a duplicate: those are flagged once in beginRemoval,
+        // which spares this sequential loop a cache miss per unit on the vertex table.)
+        if(_rootIdx[i] < 0 || ((_extended || _dupInList[i]) && !_graph->verts[_rootIdx[i]].alive)) {
             _done[i] = 1;
             _remaining--;
             return;
@@ -1283,6 +1445,47 @@ spg_status spg_graph_load_g2o(spg_graph **g, const char *path) {
     (*g)->g = gr;
     return SPG_OK;
 }
+spg_status spg_graph_save_g2o(const spg_graph *g, const char *path) {
+    if(!g || !path) return SPG_ERR_INVALID;
+    std::string err;
+    if(!g->g->saveG2o(path, &err)) {
+        spg_set_err(err);
+        return SPG_ERR_IO;
+    }
+    return SPG_OK;
+}
+spg_status spg_graph_add_factor(spg_graph *g, int32_t kind, int32_t nv, const int32_t *vert_ids, int32_t rows, const double *meas,
+                                const double *info_or_w, const int32_t *pairs) {
+    if(!g || !vert_ids || !meas || !info_or_w || nv < 1 || rows < 0) return SPG_ERR_INVALID;
+    const int dim = g->g->dim, P = g->g->poseWords();
+    for(int i = 0; i < nv; i++)
+        if(!g->g->hasVertex(vert_ids[i])) return SPG_ERR_INVALID;
+    spg::GraphEdge e;
+    e.kind = kind;
+    for(int i = 0; i < nv; i++) e.v.push_back(vert_ids[i]);
+    e.rows = rows;
+    if(kind == SPG_EDGE_POSE) {
+        if(nv != 2 || rows != dim) return SPG_ERR_INVALID;
+        return g->g->addPoseEdge(vert_ids[0], vert_ids[1], meas, info_or_w) >= 0 ? SPG_OK : SPG_ERR_INVALID;
+    } else if(kind == SPG_EDGE_GLC) {
+        if(rows > dim * nv) return SPG_ERR_INVALID;
+        e.setPayload(meas, dim * nv, info_or_w, rows * dim * nv);
+    } else if(kind == SPG_EDGE_MULTI) {
+        if(rows % dim != 0 || rows == 0 || !pairs) return SPG_ERR_INVALID;
+        const int nm = rows / dim;
+        for(int q = 0; q < 2 * nm; q++) {
+            if(pairs[q] < 0 || pairs[q] >= nv) return SPG_ERR_INVALID;
+            e.pairs.push_back(pairs[q]);
+        }
+        e.setPayload(meas, nm * P, info_or_w, rows * rows);
+    } else {
+        return SPG_ERR_INVALID;
+    }
+    e.uidMajor = -1;
+    e.uidMinor = g->g->fileEdges++;
+    g->g->addEdge(std::move(e));
+    return SPG_OK;
+}
 spg_status spg_graph_add_vertex(spg_graph *g, int32_t id, const double *pose) {
     if(!g || !pose) return SPG_ERR_INVALID;
     return g->g->addVertex(id, pose) ? SPG_OK : SPG_ERR_INVALID;
@@ -1428,6 +1631,13 @@ spg_status spg_graph_edge_data(const spg_graph *g, int32_t idx, int32_t *vert_id
     if(vert_ids) for(size_t i = 0; i < e->v.size(); i++) vert_ids[i] = e->v[i];
     if(meas) std::memcpy(meas, e->meas(), sizeof(double) * e->nMeas);
     if(info_or_w) std::memcpy(info_or_w, e->info(), sizeof(double) * e->nInfo());
+    return SPG_OK;
+}
+spg_status spg_graph_edge_pairs(const spg_graph *g, int32_t idx, int32_t *pairs) {
+    if(!g || !pairs) return SPG_ERR_INVALID;
+    const spg::GraphEdge *e = edgeAt(g, idx);
+    if(!e) return SPG_ERR_INVALID;
+    for(size_t i = 0; i < e->pairs.size(); i++) pairs[i] = e->pairs[i];
     return SPG_OK;
 }
 spg_status spg_graph_vertex_ids(const spg_graph *g, int32_t *ids) {

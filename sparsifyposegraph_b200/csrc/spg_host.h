@@ -163,6 +163,7 @@ public:
     int aliveVertices = 0, aliveEdges = 0;
 
     static Graph *loadG2o(const std::string &path, std::string *err);
+    bool saveG2o(const std::string &path, std::string *err) const;
     bool hasVertex(int id) const;
     GraphVertex *vertex(int id);
     const GraphVertex *vertex(int id) const;
@@ -291,6 +292,8 @@ public:
     spg_status beginRemoval(const std::vector<int> &toRemove);
     spg_status planRound(bool packNow = true);
     bool _packFailed = false;
+    bool _extended = false;                 // Dense / CliqueyDense: a unit may remove other list entries
+    std::vector<unsigned char> _dupInList;  // list entry repeats an earlier one
     bool packRange(size_t q0, size_t q1); // pack the selected units [q0, q1) of the planned round (planRound(false))
     spg_round_in roundDescriptor() const;
     void applyRound(const uint64_t *out);
