@@ -369,7 +369,10 @@ def main():
         except Exception:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        roofline = {"bound": "fp64", "kernel": f"blanket_kernel<6,256> (n={dom['n']} bucket)",
+        tiles = (dom["n"] - 1) * dom["n"] // 2   # launch_dim<6> in csrc/spg_capi.cu picks the instantiation by the blanket's tile count
+        kname = ("blanket_kernel<6,32>" if dom["n"] < 3 else "fast_kernel<6,8,1>" if tiles <= 8 else "fast_kernel<6,16,1>" if tiles <= 16 else
+                 "fast_kernel<6,32,1>" if tiles <= 32 else "fast_kernel<6,0,4>" if tiles <= 128 else "fast_kernel<6,0,8>")
+        roofline = {"bound": "fp64", "kernel": f"{kname} (n={dom['n']} bucket)",
                     "achieved": dom["gflops"] / 1e3, "peak": fp64_peak, "unit": "TFLOP/s",
                     "frac": dom["gflops"] / 1e3 / fp64_peak if fp64_peak else None,
                     "peak_source": "measured here: register-resident DFMA loop on all SMs (spg_fp64_peak_probe); "
@@ -379,10 +382,13 @@ def main():
                             "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"},
                     "traffic": None, "share_of_step": dom["ms"] / sum(p["ms"] for p in per_size)}
         try:  # DRAM bytes per blanket of this kernel from the committed ncu --set full capture
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))
             if tr.get("n") == dom["n"]:
-                roofline["traffic"] = tr["dram_bytes_per_blanket"] * args.blankets
+                roofline["traffic"] = tr["dram_bytes_per_blanket"] * dom["blankets"]
                 roofline["traffic_source"] = tr["source"]
+                # the contract's `frac` counts the reference algorithm's flops; what the FP64 pipe really executed:
+                roofline["fp64_pipe_active_pct_ncu"] = tr.get("fp64_pipe_active_pct")
+                roofline["fp64_pipe_source"] = tr.get("fp64_pipe_source")
         except Exception:
             pass
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),

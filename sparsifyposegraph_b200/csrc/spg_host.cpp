@@ -15,6 +15,8 @@
 #include <cstring>
 #include <deque>
 #include <fstream>
+#include <condition_variable>
+#include <functional>
 #include <limits>
 #include <mutex>
 #include <sstream>
@@ -715,6 +717,75 @@ void HostBuf::release() {
     cap = 0;
 }
 
+// Persistent worker pool of the host scheduler: the parallel passes of a removal (staleness test, blanket extraction,
+// packing, splicing) run dozens of times per round, so threads are created once — thread creation and the first
+// touch of the per-thread scratch arrays would otherwise cost more than the passes themselves.
+namespace {
+class WorkerPool {
+public:
+    explicit WorkerPool(unsigned n) {
+        for(unsigned t = 0; t < n; t++) _threads.emplace_back([this] { loop(); });
+    }
+    ~WorkerPool() {
+        {
+            std::lock_guard<std::mutex> lk(_mx);
+            _stop = true;
+        }
+        _cv.notify_all();
+        for(auto &th : _threads) th.join();
+    }
+    unsigned size() const { return (unsigned) _threads.size(); }
+    // runs job(k) for k in [0, parts) on the workers and the calling thread; returns when all are done
+    void run(unsigned parts, const std::function<void(unsigned)> &job) {
+        std::unique_lock<std::mutex> lk(_mx);
+        _job = &job;
+        _next = 0;
+        _parts = parts;
+        _pending = parts;
+        _gen++;
+        lk.unlock();
+        _cv.notify_all();
+        for(;;) { // the caller works too
+            lk.lock();
+            if(_next >= _parts) break;
+            const unsigned k = _next++;
+            lk.unlock();
+            job(k);
+            lk.lock();
+            _pending--;
+            lk.unlock();
+        }
+        _done.wait(lk, [this] { return _pending == 0; });
+        _job = nullptr;
+    }
+private:
+    void loop() {
+        std::unique_lock<std::mutex> lk(_mx);
+        unsigned long long seen = 0;
+        for(;;) {
+            _cv.wait(lk, [&] { return _stop || (_gen != seen && _job && _next < _parts); });
+            if(_stop) return;
+            seen = _gen;
+            while(_job && _next < _parts) {
+                const unsigned k = _next++;
+                const std::function<void(unsigned)> *job = _job;
+                lk.unlock();
+                (*job)(k);
+                lk.lock();
+                if(--_pending == 0) _done.notify_all();
+            }
+        }
+    }
+    std::vector<std::thread> _threads;
+    std::mutex _mx;
+    std::condition_variable _cv, _done;
+    const std::function<void(unsigned)> *_job = nullptr;
+    unsigned _next = 0, _parts = 0, _pending = 0;
+    unsigned long long _gen = 0;
+    bool _stop = false;
+};
+} // namespace
+
 // run fn(begin, end) over [0, n) on up to 16 host threads (one call on this thread when n is small)
 template <class F>
 static void parallelFor(size_t n, size_t min_per_thread, F fn) {
@@ -727,13 +798,14 @@ static void parallelFor(size_t n, size_t min_per_thread, F fn) {
         fn((size_t) 0, n);
         return;
     }
-    std::vector<std::thread> pool;
+    static WorkerPool pool(max_thr - 1); // + the calling thread
+    static std::mutex one_at_a_time;     // removals on different graphs may run from several caller threads
+    std::lock_guard<std::mutex> guard(one_at_a_time);
     const size_t chunk = (n + nthr - 1) / nthr;
-    for(unsigned t = 0; t < nthr; t++) {
-        const size_t b0 = std::min(n, t * chunk), b1 = std::min(n, b0 + chunk);
-        if(b0 < b1) pool.emplace_back(fn, b0, b1);
-    }
-    for(auto &th : pool) th.join();
+    pool.run(nthr, [&](unsigned t) {
+        const size_t b0 = std::min(n, (size_t) t * chunk), b1 = std::min(n, b0 + chunk);
+        if(b0 < b1) fn(b0, b1);
+    });
 }
 
 namespace {
