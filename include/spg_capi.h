@@ -393,6 +393,49 @@ spg_status spg_graph_edge_data(const spg_graph *g, int32_t idx, int32_t *vert_id
 spg_status spg_graph_vertex_ids(const spg_graph *g, int32_t *ids /* num_vertices */);
 spg_status spg_graph_vertex_pose(const spg_graph *g, int32_t id, double *pose);
 
+/* ------------------------------------------------------------------------------------------ */
+/* Whole-graph evaluator and optimiser on the GPU (the steps either side of the removal path) */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct {
+    double innerprod;      /* tr(Lambda_y^-1 Lambda_x)                                        */
+    double mahalanobis;    /* d^T Lambda_x d, d = estimateDifference                          */
+    double logdet_x;       /* sparsified graph                                                */
+    double logdet_y;       /* true marginal of the full graph                                 */
+    int32_t n_keep;        /* dimensions both informations have                               */
+    int32_t n_marginalized;
+    double device_ms;      /* assembly + factorisations, CUDA events                          */
+    double flops;          /* dense flops of the factorisations / solves (n^3/3 conventions)  */
+} spg_kld_terms;
+/*
+ * GraphWrapperG2O::kullbackLeibler(other) (src/graph_wrapper_g2o.cpp:531-548, src/utils.cpp:70-97, mode
+ * InformationInformation): `full` is the unsparsified graph, `sparse` the sparsified one (its vertices are a subset).
+ * Both informations are H = sum J^T Omega J at the graphs' current estimates with vertex `fixed_id` (0 in the
+ * reference) held fixed; the full graph's is marginalised onto the kept variables by a partial blocked Cholesky.
+ * POSE and GLC factors. terms may be NULL.
+ */
+spg_status spg_graph_kld(spg_ctx *ctx, const spg_graph *full, const spg_graph *sparse, int32_t fixed_id, double *kld,
+                         spg_kld_terms *terms);
+
+typedef struct {
+    int32_t iterations;    /* outer Levenberg-Marquardt iterations run                        */
+    int32_t trials;        /* linear solves (an iteration retries with a larger lambda)       */
+    int32_t dimensions;
+    int32_t terminated;    /* 1: g2o's Terminate (no acceptable step), 0: iteration limit     */
+    double chi2_initial, chi2_final, lambda_final;
+} spg_optimize_stats;
+/*
+ * GraphWrapperG2O::optimize (src/graph_wrapper_g2o.cpp:250-269): g2o's OptimizationAlgorithmLevenberg with its
+ * default parameters (tau 1e-5, step scales 1/3 .. 2/3, 10 trials after a failure), max_iterations = 50 in the
+ * reference, the listed vertices fixed (the reference fixes vertex 0). The linear system is assembled dense in HBM and
+ * solved by a blocked Cholesky; the estimates of the graph are updated in place. stats may be NULL.
+ */
+spg_status spg_graph_optimize(spg_ctx *ctx, spg_graph *g, const int32_t *fixed_ids, int32_t n_fixed, int32_t max_iterations,
+                              spg_optimize_stats *stats);
+/* OptimizableGraph::chi2 at the current estimates: sum e^T Omega e over all factors */
+spg_status spg_graph_chi2(spg_ctx *ctx, const spg_graph *g, double *chi2);
+/* overwrite the estimate of a vertex (GraphWrapper::setEstimate) */
+spg_status spg_graph_set_vertex_pose(spg_graph *g, int32_t id, const double *pose);
+
 /*
  * computeSubstituteEdge (src/compute_substitute_edge.cpp:13-96) on this container.
  * marginalized: sorted ids. from/to are in-out. meas: P doubles, info: d*d column-major.

@@ -59,6 +59,16 @@ class ShardInfo(C.Structure):
 COMM_ID_BYTES = 128
 
 
+class KldTerms(C.Structure):
+    _fields_ = [("innerprod", C.c_double), ("mahalanobis", C.c_double), ("logdet_x", C.c_double), ("logdet_y", C.c_double),
+                ("n_keep", C.c_int32), ("n_marginalized", C.c_int32), ("device_ms", C.c_double), ("flops", C.c_double)]
+
+
+class OptimizeStats(C.Structure):
+    _fields_ = [("iterations", C.c_int32), ("trials", C.c_int32), ("dimensions", C.c_int32), ("terminated", C.c_int32),
+                ("chi2_initial", C.c_double), ("chi2_final", C.c_double), ("lambda_final", C.c_double)]
+
+
 class SpgError(RuntimeError):
     pass
 
@@ -269,6 +279,10 @@ def _graph_protos(L):
     L.spg_graph_save_g2o.argtypes = [C.c_void_p, C.c_char_p]
     L.spg_graph_add_factor.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
     L.spg_graph_edge_pairs.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+    L.spg_graph_kld.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_double), C.POINTER(KldTerms)]
+    L.spg_graph_optimize.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(OptimizeStats)]
+    L.spg_graph_chi2.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
+    L.spg_graph_set_vertex_pose.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
     L.spg_graph_add_vertex.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
     L.spg_graph_add_edge.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
     for f in ("spg_graph_dim", "spg_graph_num_vertices", "spg_graph_num_edges", "spg_graph_max_vertex_id"):
@@ -327,6 +341,28 @@ class Graph:
         i = np.ascontiguousarray(i.T if kind != 1 else i).reshape(-1)   # column-major for POSE / MULTI, row-major W
         pr = np.ascontiguousarray(pairs, dtype=np.int32) if pairs is not None else None
         _check(lib().spg_graph_add_factor(self.h, int(kind), len(v), _p(v), int(rows), _p(m), _p(i), _p(pr)))
+
+    def set_vertex_pose(self, vid, pose):
+        p = np.ascontiguousarray(pose, dtype=np.float64)
+        _check(lib().spg_graph_set_vertex_pose(self.h, int(vid), _p(p)))
+
+    def kld(self, ctx, sparse, fixed_id=0):
+        """GraphWrapperG2O::kullbackLeibler(other): self = full graph, sparse = sparsified graph -> (kld, terms dict)."""
+        v, t = C.c_double(), KldTerms()
+        _check(lib().spg_graph_kld(ctx.h, self.h, sparse.h, int(fixed_id), C.byref(v), C.byref(t)))
+        return float(v.value), {f: getattr(t, f) for f, _ in KldTerms._fields_}
+
+    def optimize(self, ctx, fixed=(0,), max_iterations=50):
+        """GraphWrapperG2O::optimize (g2o Levenberg-Marquardt over a dense Cholesky on the GPU) -> stats dict."""
+        f = np.ascontiguousarray(list(fixed), dtype=np.int32)
+        st = OptimizeStats()
+        _check(lib().spg_graph_optimize(ctx.h, self.h, _p(f), len(f), int(max_iterations), C.byref(st)))
+        return {k: getattr(st, k) for k, _ in OptimizeStats._fields_}
+
+    def chi2(self, ctx):
+        v = C.c_double()
+        _check(lib().spg_graph_chi2(ctx.h, self.h, C.byref(v)))
+        return float(v.value)
 
     def save(self, path):
         """GraphWrapperG2O::write: g2o text with GLC_EDGE / MULTI_EDGE_* factors."""

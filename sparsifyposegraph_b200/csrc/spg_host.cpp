@@ -1725,6 +1725,14 @@ spg_status spg_graph_vertex_pose(const spg_graph *g, int32_t id, double *pose) {
     std::memcpy(pose, v->pose, sizeof(double) * g->g->poseWords());
     return SPG_OK;
 }
+spg_status spg_graph_set_vertex_pose(spg_graph *g, int32_t id, const double *pose) {
+    if(!g || !pose) return SPG_ERR_INVALID;
+    spg::GraphVertex *v = g->g->vertex(id);
+    if(!v) return SPG_ERR_INVALID;
+    std::memcpy(v->pose, pose, sizeof(double) * g->g->poseWords());
+    g->g->version++;
+    return SPG_OK;
+}
 spg_status spg_compute_substitute_edge(const spg_graph *g, const int32_t *marginalized, int32_t n_marginalized,
                                        int32_t maxid, int32_t *from, int32_t *to, double *meas, double *info) {
     if(!g || !from || !to || !meas || !info) return SPG_ERR_INVALID;
