@@ -436,6 +436,47 @@ spg_status spg_graph_chi2(spg_ctx *ctx, const spg_graph *g, double *chi2);
 /* overwrite the estimate of a vertex (GraphWrapper::setEstimate) */
 spg_status spg_graph_set_vertex_pose(spg_graph *g, int32_t id, const double *pose);
 
+/* ------------------------------------------------------------------------------------------ */
+/* evaluate(): the replay loop of the reference's `sparsifier` binary                         */
+/* ------------------------------------------------------------------------------------------ */
+#define SPG_EVAL_NONE (-1)    /* EvaluateInfo::None: no sparsification, baseline only */
+typedef enum { SPG_PROFILE_ONLINE = 0, SPG_PROFILE_CLUSTER = 1, SPG_PROFILE_GLOBAL = 2 } spg_profile; /* decimation.cpp */
+/* EvaluateInfo (src/evaluate.h:16-31) */
+typedef struct {
+    int32_t algorithm;          /* SPG_ALG_NFR | SPG_ALG_GLC | SPG_EVAL_NONE                          */
+    int32_t profile;            /* spg_profile: which decimate function                              */
+    spg_sparsity_options opts;
+    int32_t sparsity, cluster_size;
+    int32_t kld_period;
+    int32_t use_chi2;           /* delta chi2 instead of the KLD                                      */
+    const char *g2oname;        /* names the result files (may be NULL)                               */
+    const char *destdir;        /* NULL: no result files; else <destdir>/<profile>/<sparsity>/<dataset>/<alg>_<type>_<l|g>.{kld,txt} */
+} spg_evaluate_info;
+typedef struct {
+    int32_t n_samples;          /* KLD / chi2 samples taken (may exceed the caller's capacity)        */
+    int32_t last_vertex;
+    double last_value;
+    int32_t baseline_nodes, baseline_edges, marginal_nodes, marginal_edges; /* printStats (:606-612) */
+    double baseline_fillin, marginal_fillin;
+    double seconds_marginalize, seconds_optimize, seconds_kld;
+    int32_t n_marginalize_calls, n_marginalized;
+} spg_evaluate_result;
+/* parseLine (src/main.cpp:9-103): one job line "<nfr|glc|none> <file.g2o> <online|cluster|global>
+ * <tree|subgr|clsubgr|dense|cldense> <local|global> <sparsity> [kldPeriod [chi2|kld [clusterSize]]]";
+ * the file name is copied to g2oname (cap bytes) and info->g2oname points at it */
+spg_status spg_evaluate_parse_job(const char *line, spg_evaluate_info *info, char *g2oname, int32_t cap);
+/*
+ * evaluate(gw, info) (src/evaluate.cpp:32-221): grows an incremental and a baseline graph from `gw` vertex by vertex
+ * (ids 0..last must exist), links to already-marginalised vertices through computeSubstituteEdge, optimises both,
+ * marginalises the incremental one on the decimation schedule (spg_graph_marginalize + optimise) and samples
+ * KLD(baseline || incremental) — or the delta chi2 — every kld_period vertices and at the end. Samples go to
+ * sample_vertex / sample_value (cap entries; may be NULL) and, with destdir, to the reference's result files.
+ * incremental_out / baseline_out (may be NULL) receive the final graphs (spg_graph_destroy them).
+ */
+spg_status spg_evaluate(spg_ctx *ctx, const spg_graph *gw, const spg_evaluate_info *info, int32_t *sample_vertex,
+                        double *sample_value, int32_t cap, spg_evaluate_result *res, spg_graph **incremental_out,
+                        spg_graph **baseline_out);
+
 /*
  * computeSubstituteEdge (src/compute_substitute_edge.cpp:13-96) on this container.
  * marginalized: sorted ids. from/to are in-out. meas: P doubles, info: d*d column-major.

@@ -69,6 +69,21 @@ class OptimizeStats(C.Structure):
                 ("chi2_initial", C.c_double), ("chi2_final", C.c_double), ("lambda_final", C.c_double)]
 
 
+class EvaluateInfo(C.Structure):
+    """EvaluateInfo, reference src/evaluate.h:16-31"""
+    _fields_ = [("algorithm", C.c_int32), ("profile", C.c_int32), ("opts", SparsityOptions), ("sparsity", C.c_int32),
+                ("cluster_size", C.c_int32), ("kld_period", C.c_int32), ("use_chi2", C.c_int32), ("g2oname", C.c_char_p),
+                ("destdir", C.c_char_p)]
+
+
+class EvaluateResult(C.Structure):
+    _fields_ = [("n_samples", C.c_int32), ("last_vertex", C.c_int32), ("last_value", C.c_double), ("baseline_nodes", C.c_int32),
+                ("baseline_edges", C.c_int32), ("marginal_nodes", C.c_int32), ("marginal_edges", C.c_int32),
+                ("baseline_fillin", C.c_double), ("marginal_fillin", C.c_double), ("seconds_marginalize", C.c_double),
+                ("seconds_optimize", C.c_double), ("seconds_kld", C.c_double), ("n_marginalize_calls", C.c_int32),
+                ("n_marginalized", C.c_int32)]
+
+
 class SpgError(RuntimeError):
     pass
 
@@ -439,6 +454,45 @@ class Graph:
         meas, info = np.zeros(self.P), np.zeros(self.dim * self.dim)
         _check(lib().spg_compute_substitute_edge(self.h, _p(m), len(m), int(maxid), C.byref(f), C.byref(t), _p(meas), _p(info)))
         return f.value, t.value, meas, info.reshape(self.dim, self.dim).T
+
+
+def parse_job(line):
+    """parseLine (reference src/main.cpp:9-103) -> EvaluateInfo (its g2oname buffer is kept alive on the object)."""
+    L = lib()
+    L.spg_evaluate_parse_job.argtypes = [C.c_char_p, C.POINTER(EvaluateInfo), C.c_void_p, C.c_int32]
+    info = EvaluateInfo()
+    buf = C.create_string_buffer(1024)
+    _check(L.spg_evaluate_parse_job(line.encode(), C.byref(info), buf, 1024))
+    info._buf = buf
+    return info
+
+
+def evaluate(ctx, graph, info, destdir=None, want_graphs=False, cap=100000):
+    """evaluate(gw, info) (reference src/evaluate.cpp:32-221) -> dict(samples=[(vertex, value)], result fields...,
+    incremental=Graph, baseline=Graph when want_graphs)."""
+    L = lib()
+    _graph_protos(L)
+    L.spg_evaluate.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(EvaluateInfo), C.c_void_p, C.c_void_p, C.c_int32,
+                               C.POINTER(EvaluateResult), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+    if destdir is not None:
+        info.destdir = os.fsencode(destdir)
+    sv, sk = np.zeros(cap, dtype=np.int32), np.zeros(cap, dtype=np.float64)
+    res = EvaluateResult()
+    inc, base = C.c_void_p(), C.c_void_p()
+    rc = L.spg_evaluate(ctx.h, graph.h, C.byref(info), _p(sv), _p(sk), cap, C.byref(res),
+                        C.byref(inc) if want_graphs else None, C.byref(base) if want_graphs else None)
+    _check(rc)
+    out = {f: getattr(res, f) for f, _ in EvaluateResult._fields_}
+    n = min(res.n_samples, cap)
+    out["samples"] = list(zip(sv[:n].tolist(), sk[:n].tolist()))
+    if want_graphs:
+        for key, h in (("incremental", inc), ("baseline", base)):
+            g = Graph.__new__(Graph)
+            g.h = h
+            g.dim = L.spg_graph_dim(h)
+            g.P = 3 if g.dim == 3 else 7
+            out[key] = g
+    return out
 
 
 def decimate_global(last, endvert, sparsity):
