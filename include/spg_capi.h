@@ -373,7 +373,7 @@ typedef struct {
     int32_t first_failed_index;  /* index into `which` of the first failed blanket, -1 if none */
     int32_t first_failed_status; /* its spg_blanket_status */
     int32_t n_applied;           /* list entries whose removal was spliced into the graph (progress on error) */
-    int32_t reserved;
+    int32_t n_local_optimised;   /* Local lin. point: non-star blankets whose subgraph was optimised (:382-391) */
 } spg_marginalize_stats;
 spg_status spg_graph_last_stats(const spg_graph *g, spg_marginalize_stats *stats);
 

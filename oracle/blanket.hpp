@@ -142,6 +142,106 @@ static inline Mat assembleH(const Blanket &b) {
     return H;
 }
 
+// Edge error vector at the given poses (rows of the edge): g2o computeError of the three factor kinds.
+static inline std::vector<double> edgeErrorVector(int dim, const BEdge &e, const std::vector<Pose> &poses) {
+    std::vector<double> err;
+    if(e.kind == EDGE_POSE) {
+        err.resize(dim);
+        edgeError(e.meas, poses[e.v[0]], poses[e.v[1]], err.data());
+    } else if(e.kind == EDGE_GLC) { // GLCEdge::computeError, glc_edge.cpp:28-32
+        std::vector<Pose> vs;
+        for(int vi : e.v) vs.push_back(poses[vi]);
+        std::vector<double> r = glcReparametrize(dim, vs, e.gmeas);
+        err.assign(e.W.rows(), 0.0);
+        for(int i = 0; i < e.W.rows(); i++)
+            for(int j = 0; j < e.W.cols(); j++) err[i] += e.W(i, j) * r[j];
+    } else { // MultiEdgeCorrelated::computeError, multi_edge_correlated.hpp:64-77
+        err.resize(e.rows());
+        for(size_t m = 0; m < e.pairs.size(); m++)
+            edgeError(e.mmeas[m], poses[e.v[e.pairs[m][0]]], poses[e.v[e.pairs[m][1]]], &err[dim * m]);
+    }
+    return err;
+}
+
+// Local linearisation point without a closed form (vertex_remover.cpp:382-391): the blanket subgraph optimised for
+// 10 iterations with the first removed vertex fixed. g2o's OptimizationAlgorithmLevenberg is third party (absent here);
+// restated from its published algorithm with the default parameters: lambda_0 = 1e-5 * max diag(H), a step is accepted
+// when rho = (chi - chi') / (sum x (lambda x + b) + 1e-3) > 0, lambda *= max(1/3, min(1 - (2 rho - 1)^3, 2/3)) on
+// success, lambda *= nu, nu *= 2 on failure (at most 10 trials), Terminate when no trial succeeded or rho == 0.
+static inline void localOptimize(Blanket &b, int iterations = 10) {
+    const int d = b.dim, nv = (int) b.ids.size(), n = d * (nv - 1);
+    if(n <= 0) return;
+    auto chi2 = [&](const std::vector<Pose> &poses) {
+        double c = 0;
+        for(const BEdge &e : b.edges) {
+            std::vector<double> err = edgeErrorVector(d, e, poses);
+            Mat Om = edgeInformation(e);
+            for(int i = 0; i < Om.rows(); i++)
+                for(int j = 0; j < Om.cols(); j++) c += err[i] * Om(i, j) * err[j];
+        }
+        return c;
+    };
+    double lambda = 0, ni = 2, chi = chi2(b.poses);
+    for(int it = 0; it < iterations; it++) {
+        Mat H(n, n), g(n, 1);
+        for(const BEdge &e : b.edges) {
+            std::vector<Mat> J = edgeJacobianBlocks(d, e, b.poses);
+            std::vector<double> err = edgeErrorVector(d, e, b.poses);
+            Mat Om = edgeInformation(e), ev((int) err.size(), 1);
+            for(size_t i = 0; i < err.size(); i++) ev((int) i, 0) = err[i];
+            for(size_t i = 0; i < e.v.size(); i++) {
+                if(e.v[i] == 0) continue; // the fixed vertex
+                Mat JtO = J[i].transpose() * Om, gi = JtO * ev;
+                for(int q = 0; q < d; q++) g(d * (e.v[i] - 1) + q, 0) += gi(q, 0);
+                for(size_t j = 0; j < e.v.size(); j++)
+                    if(e.v[j] != 0) H.addBlock(d * (e.v[i] - 1), d * (e.v[j] - 1), JtO * J[j]);
+            }
+        }
+        if(it == 0) {
+            double md = 0;
+            for(int i = 0; i < n; i++) md = std::max(md, H(i, i));
+            lambda = 1e-5 * md;
+            ni = 2;
+        }
+        double rho = 0;
+        int qmax = 0;
+        do {
+            Mat A = H;
+            for(int i = 0; i < n; i++) A(i, i) += lambda;
+            LLT llt(A);
+            Mat rhs(n, 1);
+            for(int i = 0; i < n; i++) rhs(i, 0) = -g(i, 0);
+            Mat x = llt.solve(rhs);
+            std::vector<Pose> trial = b.poses;
+            if(llt.ok)
+                for(int v = 1; v < nv; v++) {
+                    double dx[6];
+                    for(int q = 0; q < d; q++) dx[q] = x(d * (v - 1) + q, 0);
+                    trial[v] = oplus(b.poses[v], dx);
+                }
+            double tempChi = llt.ok ? chi2(trial) : std::numeric_limits<double>::max();
+            rho = chi - tempChi;
+            double scale = 0;
+            for(int i = 0; i < n; i++) scale += x(i, 0) * (lambda * x(i, 0) - g(i, 0));
+            rho /= scale + 1e-3;
+            if(rho > 0 && std::isfinite(tempChi)) {
+                double alpha = 1.0 - std::pow(2 * rho - 1, 3);
+                alpha = std::min(alpha, 2.0 / 3.0);
+                lambda *= std::max(1.0 / 3.0, alpha);
+                ni = 2;
+                chi = tempChi;
+                b.poses = trial;
+            } else {
+                lambda *= ni;
+                ni *= 2;
+                if(!std::isfinite(lambda)) break;
+            }
+            qmax++;
+        } while(rho < 0 && qmax < 10);
+        if(qmax == 10 || rho == 0 || !std::isfinite(lambda)) break;
+    }
+}
+
 // Schur complement, vertex_remover.cpp:443-449
 static inline Mat schurTarget(const Mat &H, int m, bool *ok) {
     int N = H.rows(), k = N - m;

@@ -266,8 +266,7 @@ public:
     }
 
 private:
-    // :285-392. Returns false for the Local non-star case (g2o LM on the subgraph: third party,
-    // not restated).
+    // :285-392. The Local non-star case runs the restated Levenberg-Marquardt of blanket.hpp (g2o is third party).
     bool buildSubgraph(const VertexSet &toRemove, const VertexSet &blanketVertices, const EdgeSet &blanketEdges, Blanket &b) {
         b.dim = graph->dim;
         b.nRemoved = (int) toRemove.size();
@@ -323,7 +322,8 @@ private:
             }
             return true;
         } else if(opts.linPoint != SparsityOptions::Global) {
-            return false;
+            // :382-391 — Local without a closed form: 10 LM iterations on the subgraph, removed vertex fixed
+            localOptimize(b, 10);
         }
         return true;
     }

@@ -47,7 +47,7 @@ class MarginalizeStats(C.Structure):
                 ("max_blanket_vertices", C.c_int32), ("n_failed", C.c_int32), ("n_dropped_edges", C.c_int32),
                 ("pack_ms", C.c_double), ("gpu_ms", C.c_double), ("splice_ms", C.c_double),
                 ("first_failed_index", C.c_int32), ("first_failed_status", C.c_int32), ("n_applied", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("n_local_optimised", C.c_int32)]
 
 
 class ShardInfo(C.Structure):

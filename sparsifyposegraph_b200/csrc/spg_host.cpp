@@ -585,6 +585,53 @@ TopologyProvider *VertexRemover::chooseTopologyProvider(const RemovalUnit &u) co
 // but never read: every endpoint of a blanket edge is a blanket vertex)
 static thread_local std::vector<int> t_local;
 
+// Local linearisation point: does the blanket lack the closed-form estimate (:304-342)? True when a kept vertex
+// appears in more than one blanket edge or a GLC factor is involved (GLCEdge::initialEstimatePossible == -1).
+bool VertexRemover::needsSubgraphOptimisation(const RemovalUnit &u) const {
+    if(_opts.linPoint != SparsityOptions::Local) return false;
+    const int root = u.ridx.empty() ? -1 : u.ridx[0];
+    std::vector<std::pair<int, int>> nconn; // (vertex index, count): blankets are small
+    for(int ei : u.edges) {
+        const GraphEdge &e = _graph->edges[ei];
+        for(int q = 0, n = e.nv(); q < n; q++) {
+            const int xi = e.vx(q);
+            if(xi == root) continue;
+            if(e.kind == SPG_EDGE_GLC) return true;
+            auto it = std::find_if(nconn.begin(), nconn.end(), [&](const std::pair<int, int> &pr) { return pr.first == xi; });
+            if(it == nconn.end()) nconn.emplace_back(xi, 1);
+            else if(++it->second > 1) return true;
+        }
+    }
+    return false;
+}
+
+// vertex_remover.cpp:382-391: the blanket subgraph optimised for 10 Levenberg-Marquardt iterations with the (first)
+// removed vertex fixed — spg_graph_optimize on a copy of the blanket, i.e. on the GPU like every other numerical step.
+// poses: nv x P in record order (removed first, kept ascending).
+spg_status VertexRemover::localLinearise(const RemovalUnit &u, std::vector<double> &poses) const {
+    const int P = _graph->poseWords();
+    spg_graph sub;
+    sub.g = new Graph(_graph->dim);
+    std::vector<int> order;
+    for(size_t i = 0; i < u.ridx.size(); i++) order.push_back(u.ridx[i]);
+    for(size_t i = 0; i < u.kidx.size(); i++) order.push_back(u.kidx[i]);
+    for(int xi : order) sub.g->addVertex(_graph->verts[xi].id, _graph->verts[xi].pose);
+    for(int ei : u.edges) {
+        GraphEdge e = _graph->edges[ei]; // copy (ids, payload, pairs, canonical key)
+        sub.g->addEdge(std::move(e));
+    }
+    const int32_t fixed = u.removed[0];
+    spg_status st = spg_graph_optimize(_ctx, &sub, &fixed, 1, 10, nullptr);
+    if(st == SPG_OK) {
+        poses.resize(order.size() * (size_t) P);
+        for(size_t i = 0; i < order.size(); i++)
+            std::memcpy(&poses[i * P], sub.g->vertex(_graph->verts[order[i]].id)->pose, sizeof(double) * P);
+    }
+    delete sub.g;
+    sub.g = nullptr;
+    return st;
+}
+
 // record size of a unit, 0 when the blanket needs the Local non-star linearisation point
 int64_t VertexRemover::unitWords(const RemovalUnit &u) const {
     const int dim = _graph->dim;
@@ -599,7 +646,7 @@ int64_t VertexRemover::unitWords(const RemovalUnit &u) const {
 
 // buildSubgraph (src/vertex_remover.cpp:285-392) + record packing into rec[0, words). Returns false when the
 // blanket needs the Local non-star linearisation point (g2o LM on the subgraph; not part of this path).
-bool VertexRemover::packUnit(const RemovalUnit &u, uint64_t *rec, int64_t words) const {
+bool VertexRemover::packUnit(const RemovalUnit &u, uint64_t *rec, int64_t words, const double *linPoses) const {
     const int dim = _graph->dim, P = _graph->poseWords();
     const int nrem = (int) u.removed.size(), nv = nrem + (int) u.kept.size(), ne = (int) u.edges.size();
     const std::vector<GraphVertex> &V = _graph->verts;
@@ -616,7 +663,10 @@ bool VertexRemover::packUnit(const RemovalUnit &u, uint64_t *rec, int64_t words)
         std::memcpy(poses + (size_t) i * P, V[xi].pose, sizeof(double) * P);
     }
 
-    if(_opts.linPoint == SparsityOptions::Local) {
+    if(linPoses) {
+        // Local linearisation point of a non-star blanket: the subgraph was optimised in planRound (:382-391)
+        std::memcpy(poses, linPoses, sizeof(double) * nv * P);
+    } else if(_opts.linPoint == SparsityOptions::Local) {
         // closed-form estimate only for star-shaped blankets (:304-342)
         bool closedForm = true;
         std::vector<int> nconn(nv, 0);
@@ -1113,9 +1163,28 @@ spg_status VertexRemover::planRound(bool packNow) {
         if(sel.empty()) return SPG_OK;
     }
 
-    // ---- pack: sizes and providers per unit, prefix sums, then every record written in place by the host threads ---
+    // ---- Local linearisation point of non-star blankets: optimise the blanket subgraph (GPU), one blanket at a time ---
     const std::vector<int> &sel = _round.sel;
     const size_t ns = sel.size();
+    _round.linPoses.clear();
+    if(_opts.linPoint == SparsityOptions::Local) {
+        _round.linPoses.resize(ns);
+        for(size_t q = 0; q < ns; q++) {
+            const RemovalUnit &u = _unitCache[sel[q]];
+            if(!needsSubgraphOptimisation(u)) continue;
+            if(!_ctx) {
+                error = "Local linearisation point on a non-star blanket needs the subgraph optimiser: give the remover a context";
+                return SPG_ERR_UNSUPPORTED;
+            }
+            const spg_status ls = localLinearise(u, _round.linPoses[q]);
+            if(ls != SPG_OK) {
+                error = std::string("subgraph optimisation of the blanket of vertex ") + std::to_string(u.removed[0]) + " failed: " + spg_last_error();
+                return ls;
+            }
+            stats.n_local_optimised++;
+        }
+    }
+    // ---- pack: sizes and providers per unit, prefix sums, then every record written in place by the host threads ---
     TopologyProvider *byMask[8] = {};
     bool haveMask[8] = {};
     for(int m = 1; m < 8; m++) {
@@ -1189,7 +1258,8 @@ bool VertexRemover::packRange(size_t q0, size_t q1) {
     std::atomic<int> badPack(-1);
     parallelFor(q1 - q0, 1024, [&](size_t b0, size_t b1) {
         for(size_t q = q0 + b0; q < q0 + b1; q++)
-            if(!packUnit(_unitCache[sel[q]], rec + recOff[q], recOff[q + 1] - recOff[q])) {
+            if(!packUnit(_unitCache[sel[q]], rec + recOff[q], recOff[q + 1] - recOff[q],
+                         (q < _round.linPoses.size() && !_round.linPoses[q].empty()) ? _round.linPoses[q].data() : nullptr)) {
                 int expect = -1;
                 badPack.compare_exchange_strong(expect, (int) q);
             }

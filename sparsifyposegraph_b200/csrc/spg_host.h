@@ -285,6 +285,7 @@ public:
         std::vector<int> sel;        // selected units: indices into the removal list, ascending
         HostBuf records;             // used when the remover has no context (rounds planned for a caller-run engine)
         uint64_t *rec = nullptr;     // the packed records of this round (context staging buffer, or `records`)
+        std::vector<std::vector<double>> linPoses; // Local lin. point: optimised subgraph poses of non-star blankets
         std::vector<int64_t> recOff, outOff;
         int algorithm = SPG_ALG_NFR;
         bool poseOnly = false;       // every blanket edge of the round is a POSE edge (SPG_OPT_POSE_EDGES_ONLY)
@@ -306,7 +307,9 @@ private:
     bool buildUnit(int root, int listIndex, const std::set<int> &toRemoveSet, RemovalUnit &u) const;
     TopologyProvider *chooseTopologyProvider(const RemovalUnit &u) const;
     int64_t unitWords(const RemovalUnit &u) const;
-    bool packUnit(const RemovalUnit &u, uint64_t *rec, int64_t words) const;
+    bool packUnit(const RemovalUnit &u, uint64_t *rec, int64_t words, const double *linPoses) const;
+    bool needsSubgraphOptimisation(const RemovalUnit &u) const;
+    spg_status localLinearise(const RemovalUnit &u, std::vector<double> &poses) const;
 
     Round _round;
     std::vector<int> _pending, _added;
