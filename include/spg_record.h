@@ -66,7 +66,7 @@ SPGR_FN int32_t spgr_out_edge_count(int32_t algorithm, int32_t topology, double 
     case SPG_TOPO_SUBGRAPH: return m >= all ? all : m;
     case SPG_TOPO_DENSE: return all;
     case SPG_TOPO_CLIQUEY_DENSE: return 1;
-    default: return n - 1; /* CliqueySubgraph: at most n-1 correlated groups */
+    default: return n - 1; /* CliqueySubgraph: at most n-1 correlated groups (entries) */
     }
 }
 
@@ -78,17 +78,30 @@ SPGR_FN int64_t spgr_out_slot_words(int32_t dim, int32_t algorithm, int32_t topo
         int64_t c = (int64_t) dim * nvcap;
         return 1 + spgr_pad2(nvcap) + c + c * c;
     }
-    if(topology == SPG_TOPO_CLIQUEY_DENSE || topology == SPG_TOPO_CLIQUEY_SUBGRAPH) {
-        /* MULTI slot: int32 nmeas | int32 rows ; int32 pairs[2*(n-1)] ; meas[(n-1)][P] ; info[((n-1)d)^2]
-         * (capacity of the largest possible group; see DESIGN.md, not produced on device yet) */
-        int64_t nm = n_kept > 1 ? n_kept - 1 : 0;
-        return 1 + spgr_pad2(2 * nm) + nm * P + (nm * dim) * (nm * dim);
-    }
+    if(topology == SPG_TOPO_CLIQUEY_DENSE || topology == SPG_TOPO_CLIQUEY_SUBGRAPH)
+        return 0; /* correlated topologies: variable-size entries, see spgr_out_record_words */
     return 1 + P + (int64_t) dim * dim;
+}
+
+/* Correlated (cliquey) NFR topologies emit a SEQUENCE of variable-size entries behind the header, one per correlated
+ * skeleton tree of the pattern (pseudo_chow_liu.cpp:198-251), in pattern order:
+ *     w0 : int32 nmeas | int32 rows                   rows = dim * nmeas
+ *     int32 ab[2*nmeas] (padded)                      kept-list indices (a, b) of every measurement, pattern order
+ *     double meas[nmeas][P]                           Z = Xa^-1 Xb (setMeasurementFromState)
+ *     double info[rows*rows]                          column-major (X of the closed form)
+ * nmeas == 1 is a plain pose edge, nmeas > 1 a MultiEdgeCorrelated. The spanning tree has n_kept - 1 measurements in
+ * total, so one entry with all of them bounds the information words and (5 + P) words per measurement bound the rest. */
+SPGR_FN int64_t spgr_out_entry_words(int32_t dim, int32_t nmeas) {
+    return 1 + spgr_pad2(2 * (int64_t) nmeas) + (int64_t) nmeas * spgr_pose_words(dim) + ((int64_t) dim * nmeas) * ((int64_t) dim * nmeas);
 }
 
 SPGR_FN int64_t spgr_out_record_words(int32_t dim, int32_t algorithm, int32_t topology,
                                             double chord_ratio, int32_t n_kept) {
+    if(algorithm == SPG_ALG_NFR && (topology == SPG_TOPO_CLIQUEY_DENSE || topology == SPG_TOPO_CLIQUEY_SUBGRAPH)) {
+        int64_t nm = n_kept > 1 ? n_kept - 1 : 0;
+        int64_t wc = SPG_OUT_HEADER_WORDS + nm * (5 + spgr_pose_words(dim)) + (nm * dim) * (nm * dim);
+        return (wc + 1) & ~(int64_t) 1;
+    }
     int64_t w = SPG_OUT_HEADER_WORDS +
                 (int64_t) spgr_out_edge_count(algorithm, topology, chord_ratio, n_kept) *
                         spgr_out_slot_words(dim, algorithm, topology, n_kept);

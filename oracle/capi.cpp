@@ -113,9 +113,43 @@ void writeOut(const Blanket &b, const BlanketResult &res, int algorithm, const S
             for(int r = 0; r < e.W.rows(); r++)
                 for(int j = 0; j < dim * nv; j++) W[(size_t) r * c + j] = e.W(r, j);
         } else {
-            h[0] = ST_UNSUPPORTED; // correlated (MULTI) output slots: graph-level API only
+            h[0] = ST_UNSUPPORTED;
             return;
         }
+    }
+}
+
+// correlated topologies: the sequence of variable-size entries of spg_record.h (spgr_out_entry_words)
+void writeOutCliquey(const Blanket &b, const BlanketResult &res, uint64_t *out, int64_t outWords) {
+    std::memset(out, 0, sizeof(uint64_t) * outWords);
+    int dim = b.dim, P = (int) spgr_pose_words(dim);
+    int32_t *h = i32(out);
+    h[0] = res.status;
+    h[1] = (int32_t) res.edges.size();
+    h[2] = res.nfr.newtonIters;
+    h[3] = (res.nfr.lineSearchFailed ? 1 : 0);
+    f64(out)[2] = res.nfr.kld;
+    uint64_t *w = out + SPG_OUT_HEADER_WORDS;
+    for(const BEdge &e : res.edges) {
+        const int nm = e.kind == EDGE_POSE ? 1 : (int) e.pairs.size(), rows = dim * nm;
+        if((w - out) + spgr_out_entry_words(dim, nm) > outWords) { h[0] = ST_UNSUPPORTED; return; }
+        i32(w)[0] = nm;
+        i32(w)[1] = rows;
+        int32_t *ab = i32(w + 1);
+        double *m = f64(w + 1 + spgr_pad2(2 * nm));
+        if(e.kind == EDGE_POSE) {
+            ab[0] = e.v[0];
+            ab[1] = e.v[1];
+            poseToFlat(e.meas, m);
+        } else {
+            for(int q = 0; q < nm; q++) {
+                ab[2 * q] = e.v[e.pairs[q][0]];
+                ab[2 * q + 1] = e.v[e.pairs[q][1]];
+                poseToFlat(e.mmeas[q], m + (size_t) q * P);
+            }
+        }
+        std::memcpy(m + (size_t) nm * P, e.info.a.data(), sizeof(double) * rows * rows);
+        w += spgr_out_entry_words(dim, nm);
     }
 }
 
@@ -157,7 +191,10 @@ double orc_remove_round(const spg_round_in *in, spg_round_out *out, int n_thread
                                         ? out->dbg_weights + out->dbg_weights_off[i] : nullptr;
             BlanketResult res = processBlanket(b, opts, in->algorithm);
             g_overrideWeights = nullptr;
-            writeOut(b, res, in->algorithm, opts, o, ow);
+            if(in->algorithm == ALG_NFR && (opts.topology == SparsityOptions::CliqueyDense || opts.topology == SparsityOptions::CliqueySubgraph))
+                writeOutCliquey(b, res, o, ow);
+            else
+                writeOut(b, res, in->algorithm, opts, o, ow);
             if(out->dbg_target && out->dbg_target_off) {
                 double *t = out->dbg_target + out->dbg_target_off[i];
                 int64_t cap = out->dbg_target_off[i + 1] - out->dbg_target_off[i];

@@ -85,7 +85,8 @@ spg_status launch_general(spg_ctx *ctx, spg::KernelParams &kp) {
     // N <= 12 / 32 / 48 / 96 for 32 / 64 / 128 / 256 threads (SweepGrid in spg_device.cuh)
     const int N = D * kp.max_nv;
     // NFR rounds of POSE edges, 48 < N <= 80: lean variant, two CTAs per SM (falls through when it does not fit twice)
-    if(kp.algorithm == SPG_ALG_NFR && (kp.flags & SPG_OPT_POSE_EDGES_ONLY) && N > 48 && N <= 80) {
+    const bool cliquey = kp.topology == SPG_TOPO_CLIQUEY_SUBGRAPH || kp.topology == SPG_TOPO_CLIQUEY_DENSE; // needs the full third buffer
+    if(kp.algorithm == SPG_ALG_NFR && (kp.flags & SPG_OPT_POSE_EDGES_ONLY) && N > 48 && N <= 80 && !cliquey) {
         kp.lean = 1;
         spg::plan_smem<D>(kp);
         const spg_status st = (D == 6) ? spg_launch_6_256l(ctx, kp) : spg_launch_3_256l(ctx, kp);

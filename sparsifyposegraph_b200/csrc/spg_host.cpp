@@ -961,10 +961,6 @@ spg_status VertexRemover::beginRemoval(const std::vector<int> &toRemove) {
     stats.first_failed_index = -1;
     _added.clear();
     // option combinations the path cannot serve are refused before the graph is touched
-    if(_opts.topology == SparsityOptions::CliqueySubgraph || _opts.topology == SparsityOptions::CliqueyDense) {
-        error = "CliqueySubgraph / CliqueyDense (MultiEdgeCorrelated substitutes) are not produced on the device";
-        return SPG_ERR_UNSUPPORTED;
-    }
     for(TopologyProvider *tp : _topologies)
         if(tp->algorithm() == SPG_ALG_GLC &&
            (!(_opts.topology == SparsityOptions::Dense || _opts.topology == SparsityOptions::Tree) ||
@@ -1275,6 +1271,7 @@ bool VertexRemover::packRange(size_t q0, size_t q1) {
 // src/vertex_remover.cpp:500-546).
 void VertexRemover::applyRound(const uint64_t *out) {
     const int dim = _graph->dim, P = _graph->poseWords(), algorithm = _round.algorithm;
+    const bool cliquey = _opts.topology == SparsityOptions::CliqueySubgraph || _opts.topology == SparsityOptions::CliqueyDense;
     const double ta0 = nowS();
     const std::vector<int> &sel = _round.sel;
     const size_t ns = sel.size();
@@ -1360,6 +1357,7 @@ void VertexRemover::applyRound(const uint64_t *out) {
             const int nk = (int) u.kept.size();
             const int64_t slot = spgr_out_slot_words(dim, algorithm, _opts.topology, nk);
             int minor = 0;
+            int64_t centry = SPG_OUT_HEADER_WORDS; // correlated topologies: word offset of the next entry
             for(int e = 0; e < nnew; e++) {
                 const uint64_t *sl = o + SPG_OUT_HEADER_WORDS + (int64_t) e * slot;
                 const int32_t *si = reinterpret_cast<const int32_t *>(sl);
@@ -1372,7 +1370,41 @@ void VertexRemover::applyRound(const uint64_t *out) {
                 ge.uidMajor = u.listIndex;
                 ge.uidMinor = minor++;
                 ge.alive = true;
-                if(algorithm == SPG_ALG_NFR) {
+                if(algorithm == SPG_ALG_NFR && cliquey) {
+                    // correlated topologies: variable-size entries (spg_record.h); nmeas == 1 is a plain pose edge, more a
+                    // MultiEdgeCorrelated whose vertex list grows in order of appearance (addMeasurement,
+                    // multi_edge_correlated.hpp:29-62)
+                    sl = o + centry;
+                    si = reinterpret_cast<const int32_t *>(sl);
+                    const int nm = si[0], rows = si[1];
+                    const int32_t *ab = si + 2;
+                    const double *pm = reinterpret_cast<const double *>(sl + 1 + spgr_pad2(2 * nm));
+                    centry += spgr_out_entry_words(dim, nm);
+                    if(nm == 1) {
+                        ge.kind = SPG_EDGE_POSE;
+                        ge.v = {u.kept[ab[0]], u.kept[ab[1]]};
+                        ge.vx0 = u.kidx[ab[0]];
+                        ge.vx1 = u.kidx[ab[1]];
+                        ge.rows = dim;
+                        ge.setPayload(pm, P, pm + P, dim * dim);
+                    } else {
+                        ge.kind = SPG_EDGE_MULTI;
+                        ge.rows = rows;
+                        std::vector<int> order; // kept-list indices in order of appearance
+                        for(int q = 0; q < 2 * nm; q++) {
+                            int pos = (int) (std::find(order.begin(), order.end(), ab[q]) - order.begin());
+                            if(pos == (int) order.size()) order.push_back(ab[q]);
+                            ge.pairs.push_back(pos);
+                        }
+                        for(int ki : order) ge.v.push_back(u.kept[ki]);
+                        const int nve = (int) order.size();
+                        ge.vx0 = nve > 0 ? u.kidx[order[0]] : -1;
+                        ge.vx1 = nve > 1 ? u.kidx[order[1]] : -1;
+                        if(nve > 2)
+                            for(int ki : order) ge.vxn.push_back(u.kidx[ki]);
+                        ge.setPayload(pm, nm * P, pm + (size_t) nm * P, rows * rows);
+                    }
+                } else if(algorithm == SPG_ALG_NFR) {
                     ge.kind = SPG_EDGE_POSE;
                     ge.v = {u.kept[si[0]], u.kept[si[1]]};
                     ge.vx0 = u.kidx[si[0]];

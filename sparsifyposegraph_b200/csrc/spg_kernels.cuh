@@ -220,6 +220,53 @@ __device__ bool assemble_glc_edge(const uint64_t *ew, const double *s_pose, doub
     return true;
 }
 
+// H += J^T Omega J for one MultiEdgeCorrelated (multi_edge_correlated.hpp:96-140): nmeas pose measurements over the
+// nv vertices of the edge, J stacked (rows = D * nmeas), Omega rows x rows. Returns false (uniformly) when the scratch
+// (J and Omega J, rows x D nv each) does not fit.
+template <int D, int NT>
+__device__ bool assemble_multi_edge(const uint64_t *ew, const double *s_pose, double *H, int ldH, double *scratch, int cap) {
+    constexpr int PS = PoseStride<D>::value, PW = (D == 6) ? 7 : 3;
+    const int tid = threadIdx.x;
+    const int32_t *eh = reinterpret_cast<const int32_t *>(ew);
+    const int nv = eh[1], rows = eh[2], nm = rows / D, c = D * nv;
+    const int32_t *vi = reinterpret_cast<const int32_t *>(ew + 2);
+    const int32_t *pr = reinterpret_cast<const int32_t *>(ew + 2 + spgr_pad2(nv));
+    const double *meas = reinterpret_cast<const double *>(ew + 2 + spgr_pad2(nv) + spgr_pad2(2 * nm));
+    const double *Om = meas + (size_t) nm * PW; // rows x rows, column-major
+    double *Jf = scratch, *M = scratch + (size_t) rows * c;
+    if(2 * (int64_t) rows * c > cap) return false;
+    for(int t = tid; t < rows * c; t += NT) Jf[t] = 0.0;
+    gsync<NT>();
+    for(int p = tid; p < nm; p += NT) {
+        double Z[PS], J[2 * D * D];
+        if constexpr(D == 6) se3_from_flat(meas + (size_t) p * PW, Z);
+        else se2_from_flat(meas + (size_t) p * PW, Z);
+        const int a = pr[2 * p], b = pr[2 * p + 1];
+        edge_jacobians<D>(Z, s_pose + PS * vi[a], s_pose + PS * vi[b], J);
+        for(int q = 0; q < D; q++)
+            for(int r = 0; r < D; r++) {
+                Jf[(p * D + r) + (size_t) (a * D + q) * rows] = J[r + q * D];
+                Jf[(p * D + r) + (size_t) (b * D + q) * rows] = J[D * D + r + q * D];
+            }
+    }
+    gsync<NT>();
+    for(int t = tid; t < rows * c; t += NT) {
+        const int row = t % rows, col = t / rows;
+        double s = 0;
+        for(int q = 0; q < rows; q++) s += Om[row + (size_t) q * rows] * Jf[q + (size_t) col * rows];
+        M[t] = s;
+    }
+    gsync<NT>();
+    for(int t = tid; t < c * c; t += NT) {
+        const int a = t % c, b = t / c;
+        double s = 0;
+        for(int row = 0; row < rows; row++) s += Jf[row + (size_t) a * rows] * M[row + (size_t) b * rows];
+        H[(vi[a / D] * D + a % D) + (size_t) (vi[b / D] * D + b % D) * ldH] += s;
+    }
+    gsync<NT>();
+    return true;
+}
+
 #define SPG_T(i)                                                                                     \
     do {                                                                                             \
         if(P.prof && tid == 0) {                                                                     \
@@ -325,6 +372,8 @@ __global__ void __launch_bounds__(NT, LEAN ? 2 : ((NT >= 256) ? 1 : (NT == 128 ?
                 bool okg = false;
                 if(kind0 == SPG_EDGE_GLC)
                     okg = assemble_glc_edge<D, NT>(s_rec + r_etab[e0], s_pose, H, ldH, buf1, P.buf1_doubles + P.buf2_doubles);
+                else if(kind0 == SPG_EDGE_MULTI)
+                    okg = assemble_multi_edge<D, NT>(s_rec + r_etab[e0], s_pose, H, ldH, buf1, P.buf1_doubles + P.buf2_doubles);
                 if(!okg) status = SPG_BLANKET_UNSUPPORTED; // uniform
                 e0++;
                 continue;
@@ -437,9 +486,7 @@ __global__ void __launch_bounds__(NT, LEAN ? 2 : ((NT >= 256) ? 1 : (NT == 128 ?
             const bool cliquey = (P.topology == SPG_TOPO_CLIQUEY_DENSE || P.topology == SPG_TOPO_CLIQUEY_SUBGRAPH);
             if(nk == 2) {
                 n_out = 1;
-                if(tid == 0) s_tree[0] = pk(0, 1);
-            } else if(cliquey) {
-                status = SPG_BLANKET_UNSUPPORTED; // correlated (MultiEdgeCorrelated) outputs: host path, see DESIGN.md
+                if(tid == 0) { s_tree[0] = pk(0, 1); s_heapab[0] = 0; s_misc[14] = 1; }
             } else if(P.topology == SPG_TOPO_DENSE || (P.topology == SPG_TOPO_SUBGRAPH && full)) {
                 n_out = all;
                 for(int t = tid; t < all; t += NT) {
@@ -448,7 +495,7 @@ __global__ void __launch_bounds__(NT, LEAN ? 2 : ((NT >= 256) ? 1 : (NT == 128 ?
                     s_tree[t] = pk(i, i + 1 + rem);
                 }
             } else {
-                n_out = (P.topology == SPG_TOPO_TREE) ? nk - 1 : mch;
+                n_out = (P.topology == SPG_TOPO_TREE || cliquey) ? nk - 1 : mch; // correlated topologies group the spanning tree
                 // C = (Lambda_t + 1 I)^-1  (fillEdges, pseudo_chow_liu.cpp:185-190)
                 double *Lc = buf1, *C = buf1; // buf2 is scratch
                 // CTAs twice as wide as the sweep's thread grid invert the anchored block Lambda_rr of the NFR
@@ -585,6 +632,60 @@ __global__ void __launch_bounds__(NT, LEAN ? 2 : ((NT >= 256) ? 1 : (NT == 128 ?
                         }
                     }
                     gsync<NT>();
+                    if(cliquey) {
+                        // Correlated skeleton trees (pseudo_chow_liu.cpp:60-68, fillCliques :198-251): the n-1 tree edges, in
+                        // acceptance order, are grouped into cliques; s_heapab[e] = clique of tree edge e, s_misc[14] =
+                        // number of cliques (-1: not representable here). Integer logic, one thread.
+                        if(tid == 0) {
+                            int *clq = s_heapab;
+                            const int ne_t = nk - 1;
+                            if(P.topology == SPG_TOPO_CLIQUEY_DENSE || full) {
+                                for(int e = 0; e < ne_t; e++) clq[e] = 0;
+                                s_misc[14] = 1;
+                            } else if(nk > 64) {
+                                s_misc[14] = -1;
+                            } else {
+                                unsigned long long cm[64];
+                                int ncl = ne_t;
+                                for(int e = 0; e < ne_t; e++) cm[e] = (1ull << pk_a(s_tree[e])) | (1ull << pk_b(s_tree[e]));
+                                bool joined = true;
+                                for(int nedges = nk - 1, maxfill = 1; nedges < mch && joined; maxfill++) {
+                                    joined = false;
+                                    int minfill = 0x7fffffff;
+                                    for(int i = 0; i < ncl; i++)
+                                        for(int j = i + 1; j < ncl; j++)
+                                            if(cm[i] & cm[j]) {
+                                                const int thisfill = (__popcll(cm[i]) - 1) * (__popcll(cm[j]) - 1);
+                                                minfill = min(thisfill, minfill);
+                                                if(thisfill <= maxfill && nedges + thisfill <= mch) {
+                                                    cm[i] |= cm[j];
+                                                    nedges += thisfill;
+                                                    for(int q = j; q + 1 < ncl; q++) cm[q] = cm[q + 1];
+                                                    ncl--;
+                                                    joined = true;
+                                                    j--;
+                                                }
+                                            }
+                                    if(!joined && minfill > maxfill) {
+                                        joined = true;
+                                        maxfill = minfill - 1;
+                                    }
+                                }
+                                int ok = 1;
+                                for(int e = 0; e < ne_t; e++) {
+                                    const unsigned long long both = (1ull << pk_a(s_tree[e])) | (1ull << pk_b(s_tree[e]));
+                                    int owner = -1, cnt = 0;
+                                    for(int j = 0; j < ncl; j++)
+                                        if((cm[j] & both) == both) { if(owner < 0) owner = j; cnt++; }
+                                    clq[e] = owner;
+                                    if(cnt != 1) ok = 0; // an edge inside two cliques: more rows than the closed form has (iterative fit)
+                                }
+                                s_misc[14] = ok ? ncl : -1;
+                            }
+                        }
+                        gsync<NT>();
+                        if(s_misc[14] < 0) status = SPG_BLANKET_UNSUPPORTED;
+                    }
                 }
             }
         }
@@ -676,6 +777,7 @@ __global__ void __launch_bounds__(NT, LEAN ? 2 : ((NT >= 256) ? 1 : (NT == 128 ?
             double *Sg = buf0 + (size_t) n_out * JW; // n_out * SW
             double *Bk = Sg + (size_t) n_out * SW;   // n_out * D*D
             const int slot = 1 + PW + D * D;
+            const bool cliquey4 = (P.topology == SPG_TOPO_CLIQUEY_DENSE || P.topology == SPG_TOPO_CLIQUEY_SUBGRAPH);
             for(int e = tid; e < n_out; e += NT) {
                 const int a = pk_a(s_tree[e]), bb = pk_b(s_tree[e]);
                 const double *Xa = s_pose + PS * (nrem + a), *Xb = s_pose + PS * (nrem + bb);
@@ -683,6 +785,7 @@ __global__ void __launch_bounds__(NT, LEAN ? 2 : ((NT >= 256) ? 1 : (NT == 128 ?
                 if constexpr(D == 6) { se3_inverse(Xa, Ti); se3_compose(Ti, Xb, Z); }
                 else { se2_inverse(Xa, Ti); se2_compose(Ti, Xb, Z); }
                 edge_jacobians_zero_error<D>(Z, Xa, Xb, Jn + (size_t) e * JW);
+                if(cliquey4) continue; // correlated topologies write their entries after the fit
                 uint64_t *sl = gout + SPG_OUT_HEADER_WORDS + (size_t) e * slot;
                 int32_t *si = reinterpret_cast<int32_t *>(sl);
                 si[0] = a; si[1] = bb;
@@ -773,6 +876,130 @@ __global__ void __launch_bounds__(NT, LEAN ? 2 : ((NT >= 256) ? 1 : (NT == 128 ?
                         sx[qq] = (i >= j) ? xe[i + j * D] : xe[j + i * D];
                     }
                     gsync<NT>();
+                }
+            } else if(status == SPG_BLANKET_OK && cliquey4) {
+                // ---- correlated topologies (CliqueySubgraph / CliqueyDense): one information block per clique of tree
+                // edges, X_c = (J_c Sigma J_c^T)^-1 with J_c the stacked Jacobians of the clique's measurements
+                // (closedFormSolution, logdet_function.cpp:236-279; single clique: the sparse-Jacobian branch :243-247).
+                // The measurements of a spanning tree always add up to k - d rows, so the closed form always exists.
+                gsync<NT>(); // Jn, S, order complete
+                const int *clq = s_heapab;
+                const int nc = s_misc[14];
+                int *map = s_uf; // tree edges of the current clique
+                double *Blk = buf0 + (size_t) n_out * JW;          // R x R
+                double *Tm = fast ? ((G == buf2) ? buf1 : buf2) : buf2; // fast: J G~ (R x kk); eigen path: J U (R x r); then scratch
+                int64_t woff = SPG_OUT_HEADER_WORDS;
+                int emitted = 0;
+                double lp = fast ? glog_part : 0.0;
+                for(int c = 0; c < nc && status == SPG_BLANKET_OK; c++) {
+                    if(tid == 0) {
+                        int m0 = 0;
+                        for(int e = 0; e < n_out; e++)
+                            if(clq[e] == c) map[m0++] = e;
+                        s_misc[15] = m0;
+                    }
+                    gsync<NT>();
+                    const int m = s_misc[15], R = D * m, ldR = odd_ld(R);
+                    if(fast) {
+                        for(int t = tid; t < R * kk; t += NT) { // Tm = J_c G~, G~ = [[Lambda_rr^-1, 0], [0, 0]] (lower triangle of G)
+                            const int row = t % R, col = t / R, e = map[row / D], i = row % D;
+                            const int a = pk_a(s_tree[e]), bb = pk_b(s_tree[e]);
+                            const double *J = Jn + (size_t) e * JW;
+                            double acc = 0;
+#pragma unroll
+                            for(int j = 0; j < D; j++) {
+                                const int ra = a * D + j, rb = bb * D + j;
+                                if(ra < kk) acc += J[i + j * D] * (ra >= col ? G[ra + (size_t) col * ldg] : G[col + (size_t) ra * ldg]);
+                                if(rb < kk) acc += J[i + (D + j) * D] * (rb >= col ? G[rb + (size_t) col * ldg] : G[col + (size_t) rb * ldg]);
+                            }
+                            Tm[row + (size_t) col * R] = acc;
+                        }
+                        gsync<NT>();
+                        for(int t = tid; t < R * R; t += NT) { // B = Tm J_c^T
+                            const int row = t % R, col = t / R, e = map[col / D], j = col % D;
+                            const int a = pk_a(s_tree[e]), bb = pk_b(s_tree[e]);
+                            const double *J = Jn + (size_t) e * JW;
+                            double acc = 0;
+#pragma unroll
+                            for(int l = 0; l < D; l++) {
+                                const int ca = a * D + l, cb2 = bb * D + l;
+                                if(ca < kk) acc += Tm[row + (size_t) ca * R] * J[j + l * D];
+                                if(cb2 < kk) acc += Tm[row + (size_t) cb2 * R] * J[j + (D + l) * D];
+                            }
+                            Blk[row + (size_t) col * ldR] = acc;
+                        }
+                    } else {
+                        for(int t = tid; t < R * r; t += NT) { // JU = J_c U (kept eigen-directions)
+                            const int row = t % R, l = t / R, e = map[row / D], i = row % D;
+                            const int a = pk_a(s_tree[e]), bb = pk_b(s_tree[e]);
+                            const double *J = Jn + (size_t) e * JW;
+                            const double *u = V + (size_t) s_order[ooff + l] * ldk;
+                            double acc = 0;
+#pragma unroll
+                            for(int j = 0; j < D; j++) acc += J[i + j * D] * u[a * D + j] + J[i + (D + j) * D] * u[bb * D + j];
+                            Tm[row + (size_t) l * R] = acc;
+                        }
+                        gsync<NT>();
+                        for(int t = tid; t < R * R; t += NT) { // B = JU S JU^T
+                            const int row = t % R, col = t / R;
+                            double acc = 0;
+                            for(int l = 0; l < r; l++) acc += Tm[row + (size_t) l * R] * s_S[l] * Tm[col + (size_t) l * R];
+                            Blk[row + (size_t) col * ldR] = acc;
+                        }
+                    }
+                    gsync<NT>();
+                    for(int t = tid; t < R * R; t += NT) { // symmetrise (:249-270)
+                        const int i = t % R, j = t / R;
+                        if(i > j) {
+                            const double v = 0.5 * (Blk[i + (size_t) j * ldR] + Blk[j + (size_t) i * ldR]);
+                            Blk[i + (size_t) j * ldR] = v;
+                            Blk[j + (size_t) i * ldR] = v;
+                        }
+                    }
+                    gsync<NT>();
+                    // X_c = B^-1: register-tiled sweep (pivot <= 0 is LLT's failure), blocked Cholesky beyond the tiles
+                    double mylog = 0;
+                    int sw = -1;
+                    if(sweep_fits<NT, LEAN>(R)) sw = sweep_spd_auto<D, NT, LEAN>(Blk, ldR, Blk, ldR, R, R, Tm, 0.0, false, &mylog);
+                    if(sw < 0) {
+                        sw = chol_lower<NT>(Blk, R, ldR) ? 1 : 0;
+                        if(sw) {
+                            for(int i = tid; i < R; i += NT) mylog += 2.0 * log(Blk[i + (size_t) i * ldR]);
+                            chol_inverse_inplace<NT>(Blk, R, ldR, Tm);
+                        }
+                    }
+                    if(sw == 0) { status = SPG_BLANKET_NOT_PD_CLOSED; break; } // uniform
+                    lp += mylog;
+                    uint64_t *w = gout + woff;
+                    if(tid == 0) {
+                        int32_t *wi = reinterpret_cast<int32_t *>(w);
+                        wi[0] = m; wi[1] = R;
+                        for(int p = 0; p < m; p++) { wi[2 + 2 * p] = pk_a(s_tree[map[p]]); wi[3 + 2 * p] = pk_b(s_tree[map[p]]); }
+                    }
+                    double *wm = reinterpret_cast<double *>(w + 1 + spgr_pad2(2 * m));
+                    for(int p = tid; p < m; p += NT) {
+                        const int e = map[p];
+                        const double *Xa = s_pose + PS * (nrem + pk_a(s_tree[e])), *Xb = s_pose + PS * (nrem + pk_b(s_tree[e]));
+                        double Z[PS], Ti[PS];
+                        if constexpr(D == 6) { se3_inverse(Xa, Ti); se3_compose(Ti, Xb, Z); se3_to_flat(Z, wm + (size_t) p * PW); }
+                        else { se2_inverse(Xa, Ti); se2_compose(Ti, Xb, Z); wm[p * PW] = Z[0]; wm[p * PW + 1] = Z[1]; wm[p * PW + 2] = Z[2]; }
+                    }
+                    double *wx = wm + (size_t) m * PW;
+                    for(int t = tid; t < R * R; t += NT) {
+                        const int i = t % R, j = t / R;
+                        wx[t] = (i >= j) ? Blk[i + (size_t) j * ldR] : Blk[j + (size_t) i * ldR]; // selfadjointView<Lower>
+                    }
+                    woff += spgr_out_entry_words(D, m);
+                    emitted++;
+                    gsync<NT>();
+                }
+                n_out = emitted;
+                if(status == SPG_BLANKET_OK) {
+                    // projected KLD (logdet_function.cpp:119-133): the trace term is exactly r, J^T X J = J_all^T blockdiag(X_c)
+                    // J_all with the square, unit-determinant tree Jacobian in anchored coordinates, so
+                    // KLD = 1/2 [logdet Lambda_rr + sum_c logdet B_c]. Evaluated on the shortcut path only.
+                    if(fast) out_kld = 0.5 * block_sum<NT>(lp, s_red);
+                    else out_flags |= 8; // diagnostic: KLD not evaluated (eigen path of a correlated topology)
                 }
             } else if(status == SPG_BLANKET_OK) {
                 SPG_T(10);

@@ -75,12 +75,15 @@ def out_slot_words(dim, algorithm, topology, n_kept):
         c = dim * nvcap
         return 1 + pad2(nvcap) + c + c * c
     if topology in (TOPO_CLIQUEY_DENSE, TOPO_CLIQUEY_SUBGRAPH):
-        nm = max(n_kept - 1, 0)
-        return 1 + pad2(2 * nm) + nm * P + (nm * dim) ** 2
+        return 0   # variable-size entries (spg_record.h: spgr_out_entry_words)
     return 1 + P + dim * dim
 
 
 def out_record_words(dim, algorithm, topology, chord_ratio, n_kept):
+    if algorithm == ALG_NFR and topology in (TOPO_CLIQUEY_DENSE, TOPO_CLIQUEY_SUBGRAPH):
+        nm = max(int(n_kept) - 1, 0)
+        w = OUT_HEADER_WORDS + nm * (5 + pose_words(dim)) + (nm * dim) ** 2
+        return (w + 1) & ~1
     w = OUT_HEADER_WORDS + out_edge_count(algorithm, topology, chord_ratio, n_kept) * out_slot_words(
         dim, algorithm, topology, n_kept)
     return (w + 1) & ~1
@@ -241,6 +244,18 @@ def parse_out(out, out_off, b, dim, algorithm, topology, n_kept):
     P, d = pose_words(dim), dim
     slot = out_slot_words(dim, algorithm, topology, n_kept)
     o = OUT_HEADER_WORDS
+    if algorithm == ALG_NFR and topology in (TOPO_CLIQUEY_DENSE, TOPO_CLIQUEY_SUBGRAPH):
+        # correlated topologies: a sequence of variable-size entries (nmeas == 1: pose edge, > 1: multi-edge)
+        for _ in range(res["n_edges"]):
+            nm, rows = int(i32[2 * o]), int(i32[2 * o + 1])
+            ab = [int(x) for x in i32[2 * (o + 1):2 * (o + 1) + 2 * nm]]
+            m0 = o + 1 + pad2(2 * nm)
+            meas = f64[m0:m0 + nm * P].reshape(nm, P).copy()
+            info = f64[m0 + nm * P:m0 + nm * P + rows * rows].reshape(rows, rows).T.copy()
+            res["edges"].append({"v": ab, "pairs": [(ab[2 * q], ab[2 * q + 1]) for q in range(nm)], "nmeas": nm, "meas": meas,
+                                 "info": info})
+            o = m0 + nm * P + rows * rows
+        return res
     for _ in range(res["n_edges"]):
         if algorithm == ALG_NFR:
             a, bb = int(i32[2 * o]), int(i32[2 * o + 1])
