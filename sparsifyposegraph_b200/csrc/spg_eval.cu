@@ -38,9 +38,8 @@ struct DeviceGraph {
     std::vector<double> poses;   // nV x P (flat poses)
     std::vector<int> verts;      // per edge: local vertex indices
     std::vector<double> data;
-    std::vector<EdgeRef> pose_edges, glc_edges;
+    std::vector<EdgeRef> pose_edges, glc_edges, multi_edges;
     int64_t scratch_doubles = 0;
-    bool has_multi = false;
 };
 
 void flatten(const Graph &g, DeviceGraph &dg) {
@@ -57,10 +56,6 @@ void flatten(const Graph &g, DeviceGraph &dg) {
     }
     for(int ei : g.edgeOrder()) {
         const GraphEdge &e = g.edges[ei];
-        if(e.kind == SPG_EDGE_MULTI) {
-            dg.has_multi = true;
-            continue;
-        }
         EdgeRef r{};
         r.kind = e.kind;
         r.nv = e.nv();
@@ -68,12 +63,19 @@ void flatten(const Graph &g, DeviceGraph &dg) {
         r.vert = (int64_t) dg.verts.size();
         r.data = (int64_t) dg.data.size();
         for(int q = 0; q < e.nv(); q++) dg.verts.push_back(local[e.vx(q)]);
+        if(e.kind == SPG_EDGE_MULTI) // the measurement -> vertex pairs follow the vertex indices
+            for(int x : e.pairs) dg.verts.push_back(x);
         dg.data.insert(dg.data.end(), e.payload.begin(), e.payload.end());
         if(e.kind == SPG_EDGE_GLC) {
             const int c = g.dim * e.nv();
             r.scratch = dg.scratch_doubles;
             dg.scratch_doubles += 2 * (int64_t) e.nv() * g.dim * g.dim + (int64_t) e.rows * c + c + e.rows;
             dg.glc_edges.push_back(r);
+        } else if(e.kind == SPG_EDGE_MULTI) {
+            const int c = g.dim * e.nv();
+            r.scratch = dg.scratch_doubles;
+            dg.scratch_doubles += 2 * (int64_t) e.rows * c + 2 * (int64_t) e.rows;
+            dg.multi_edges.push_back(r);
         } else {
             dg.pose_edges.push_back(r);
         }
@@ -262,6 +264,76 @@ __global__ void __launch_bounds__(64) assemble_glc_edges_kernel(const AsmParams 
     }
 }
 
+// one CTA per MultiEdgeCorrelated (multi_edge_correlated.hpp:64-140): stacked pose errors and Jacobians, full Omega
+template <int D>
+__global__ void __launch_bounds__(64) assemble_multi_edges_kernel(const AsmParams p) {
+    constexpr int PS = spg::PoseStride<D>::value, PW = (D == 6) ? 7 : 3, NT = 64;
+    const int tid = threadIdx.x;
+    for(int ei = blockIdx.x; ei < p.n_edges; ei += gridDim.x) {
+        const EdgeRef er = p.edges[ei];
+        const int nv = er.nv, rows = er.rows, nm = rows / D, c = D * nv;
+        const int32_t *vi = p.verts + er.vert, *pr = vi + nv;
+        const double *meas = p.data + er.data;
+        const double *Om = meas + (size_t) nm * PW; // rows x rows column-major
+        double *Jf = p.scratch + er.scratch, *M = Jf + (size_t) rows * c, *err = M + (size_t) rows * c, *Oe = err + rows;
+        __syncthreads();
+        for(int t = tid; t < rows * c; t += NT) Jf[t] = 0.0;
+        __syncthreads();
+        for(int q = tid; q < nm; q += NT) {
+            double Z[PS], Xa[PS], Xb[PS], J[2 * D * D], e[D];
+            const int a = pr[2 * q], b = pr[2 * q + 1];
+            pose_from_flat<D>(meas + (size_t) q * PW, Z);
+            pose_from_flat<D>(p.poses + (size_t) vi[a] * PW, Xa);
+            pose_from_flat<D>(p.poses + (size_t) vi[b] * PW, Xb);
+            edge_error<D>(Z, Xa, Xb, e);
+            spg::edge_jacobians<D>(Z, Xa, Xb, J);
+            for(int r = 0; r < D; r++) {
+                err[q * D + r] = e[r];
+                for(int l = 0; l < D; l++) {
+                    Jf[(q * D + r) + (size_t) (a * D + l) * rows] = J[r + l * D];
+                    Jf[(q * D + r) + (size_t) (b * D + l) * rows] = J[D * D + r + l * D];
+                }
+            }
+        }
+        __syncthreads();
+        for(int row = tid; row < rows; row += NT) {
+            double s = 0;
+            for(int q = 0; q < rows; q++) s += Om[row + (size_t) q * rows] * err[q];
+            Oe[row] = s;
+        }
+        if(p.H)
+            for(int t = tid; t < rows * c; t += NT) {
+                const int row = t % rows, col = t / rows;
+                double s = 0;
+                for(int q = 0; q < rows; q++) s += Om[row + (size_t) q * rows] * Jf[q + (size_t) col * rows];
+                M[t] = s;
+            }
+        __syncthreads();
+        if(p.chi2 && tid == 0) {
+            double s = 0;
+            for(int row = 0; row < rows; row++) s += err[row] * Oe[row];
+            atomicAdd(p.chi2, s);
+        }
+        if(p.g)
+            for(int a = tid; a < c; a += NT) {
+                const int pv = p.pos[vi[a / D]];
+                if(pv < 0) continue;
+                double s = 0;
+                for(int row = 0; row < rows; row++) s += Jf[row + (size_t) a * rows] * Oe[row];
+                atomicAdd(&p.g[pv + a % D], s);
+            }
+        if(p.H)
+            for(int t = tid; t < c * c; t += NT) {
+                const int a = t % c, b = t / c;
+                const int pa = p.pos[vi[a / D]], pb = p.pos[vi[b / D]];
+                if(pa < 0 || pb < 0) continue;
+                double s = 0;
+                for(int row = 0; row < rows; row++) s += Jf[row + (size_t) a * rows] * M[row + (size_t) b * rows];
+                atomicAdd(&p.H[(pa + a % D) + (int64_t) (pb + b % D) * p.ldh], s);
+            }
+    }
+}
+
 __global__ void add_diag_kernel(double *A, int64_t lda, int n, double lambda) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if(i < n) A[i + (int64_t) i * lda] += lambda;
@@ -358,7 +430,7 @@ void backward_solve_vec(spg_ctx *ctx, const double *L, int64_t ldl, int n, doubl
 }
 
 struct DevArrays {
-    DevBuf poses, pos, verts, data, pedges, gedges, scratch;
+    DevBuf poses, pos, verts, data, pedges, gedges, medges, scratch;
 };
 
 spg_status upload(spg_ctx *ctx, const DeviceGraph &dg, const std::vector<int32_t> &pos, DevArrays &d) {
@@ -369,6 +441,7 @@ spg_status upload(spg_ctx *ctx, const DeviceGraph &dg, const std::vector<int32_t
     SPG_CUDA(d.data.reserve(dg.data.size() * 8 + 8));
     SPG_CUDA(d.pedges.reserve(dg.pose_edges.size() * sizeof(EdgeRef) + 8));
     SPG_CUDA(d.gedges.reserve(dg.glc_edges.size() * sizeof(EdgeRef) + 8));
+    SPG_CUDA(d.medges.reserve(dg.multi_edges.size() * sizeof(EdgeRef) + 8));
     SPG_CUDA(d.scratch.reserve((size_t) dg.scratch_doubles * 8 + 8));
     SPG_CUDA(cudaMemcpyAsync(d.poses.p, dg.poses.data(), dg.poses.size() * 8, cudaMemcpyHostToDevice, st));
     SPG_CUDA(cudaMemcpyAsync(d.pos.p, pos.data(), pos.size() * 4, cudaMemcpyHostToDevice, st));
@@ -378,10 +451,12 @@ spg_status upload(spg_ctx *ctx, const DeviceGraph &dg, const std::vector<int32_t
         SPG_CUDA(cudaMemcpyAsync(d.pedges.p, dg.pose_edges.data(), dg.pose_edges.size() * sizeof(EdgeRef), cudaMemcpyHostToDevice, st));
     if(!dg.glc_edges.empty())
         SPG_CUDA(cudaMemcpyAsync(d.gedges.p, dg.glc_edges.data(), dg.glc_edges.size() * sizeof(EdgeRef), cudaMemcpyHostToDevice, st));
+    if(!dg.multi_edges.empty())
+        SPG_CUDA(cudaMemcpyAsync(d.medges.p, dg.multi_edges.data(), dg.multi_edges.size() * sizeof(EdgeRef), cudaMemcpyHostToDevice, st));
     return SPG_OK;
 }
 void release(DevArrays &d) {
-    for(DevBuf *b : {&d.poses, &d.pos, &d.verts, &d.data, &d.pedges, &d.gedges, &d.scratch}) b->release();
+    for(DevBuf *b : {&d.poses, &d.pos, &d.verts, &d.data, &d.pedges, &d.gedges, &d.medges, &d.scratch}) b->release();
 }
 
 // H (n x n, zeroed here when given), g (n, zeroed), chi2 (1, zeroed) of the graph at the uploaded poses
@@ -414,6 +489,14 @@ spg_status assemble(spg_ctx *ctx, const DeviceGraph &dg, DevArrays &d, int n, do
         const int blocks = std::min<int>(p.n_edges, ctx->sm_count * 16);
         if(dg.dim == 6) assemble_glc_edges_kernel<6><<<blocks, 64, 0, st>>>(p);
         else assemble_glc_edges_kernel<3><<<blocks, 64, 0, st>>>(p);
+        ctx->launches++;
+    }
+    if(!dg.multi_edges.empty()) {
+        p.edges = static_cast<const EdgeRef *>(d.medges.p);
+        p.n_edges = (int) dg.multi_edges.size();
+        const int blocks = std::min<int>(p.n_edges, ctx->sm_count * 16);
+        if(dg.dim == 6) assemble_multi_edges_kernel<6><<<blocks, 64, 0, st>>>(p);
+        else assemble_multi_edges_kernel<3><<<blocks, 64, 0, st>>>(p);
         ctx->launches++;
     }
     SPG_CUDA(cudaGetLastError());
@@ -470,10 +553,6 @@ spg_status spg_graph_kld(spg_ctx *ctx, const spg_graph *full, const spg_graph *s
     DeviceGraph F, S;
     flatten(*full->g, F);
     flatten(*sparse->g, S);
-    if(F.has_multi || S.has_multi) {
-        spg_set_err("spg_graph_kld: MULTI (correlated) edges are not assembled on this path");
-        return SPG_ERR_UNSUPPORTED;
-    }
     const int dim = F.dim;
     // computeIndices (:472-499): the variables of the sparsified graph are kept, the rest of the full graph is marginalised
     std::vector<char> fixedF(F.nV, 0), keepF(F.nV, 0), fixedS(S.nV, 0);
@@ -633,10 +712,6 @@ spg_status spg_graph_optimize(spg_ctx *ctx, spg_graph *gr, const int32_t *fixed_
     Graph &G = *gr->g;
     DeviceGraph dg;
     flatten(G, dg);
-    if(dg.has_multi) {
-        spg_set_err("spg_graph_optimize: MULTI (correlated) edges are not assembled on this path");
-        return SPG_ERR_UNSUPPORTED;
-    }
     std::vector<char> fixed(dg.nV, 0);
     for(int i = 0; i < n_fixed; i++) {
         auto it = std::lower_bound(dg.ids.begin(), dg.ids.end(), fixed_ids[i]);
@@ -789,10 +864,6 @@ spg_status spg_graph_chi2(spg_ctx *ctx, const spg_graph *gr, double *chi2) {
     SPG_CUDA(cudaSetDevice(ctx->device));
     DeviceGraph dg;
     flatten(*gr->g, dg);
-    if(dg.has_multi) {
-        spg_set_err("spg_graph_chi2: MULTI (correlated) edges are not assembled on this path");
-        return SPG_ERR_UNSUPPORTED;
-    }
     std::vector<int32_t> pos((size_t) dg.nV, -1);
     DevArrays arr;
     DevBuf dsc;

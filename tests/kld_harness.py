@@ -31,7 +31,18 @@ def _edge_blocks(oracle, dim, e, poses):
         _, Jr = oracle.glc_reparam(dim, np.stack([poses[i] for i in v]), e["meas"])
         J = np.asarray(e["info"]) @ Jr                      # W (rank x d nv) * J_reparam
         return [(vi, J[:, dim * q:dim * (q + 1)]) for q, vi in enumerate(v)], np.eye(J.shape[0])
-    raise NotImplementedError("MULTI edges")
+    # MultiEdgeCorrelated (multi_edge_correlated.hpp:96-140): stacked pose Jacobians, full information
+    P = 3 if dim == 3 else 7
+    nm = e["rows"] // dim
+    meas = np.asarray(e["meas"]).reshape(nm, P)
+    pairs = np.asarray(e["pairs"]).reshape(nm, 2)
+    blocks = {vi: np.zeros((e["rows"], dim)) for vi in v}
+    for m in range(nm):
+        a, b = v[pairs[m, 0]], v[pairs[m, 1]]
+        Ji, Jj = oracle.edge_jacobians(dim, meas[m], poses[a], poses[b])
+        blocks[a][dim * m:dim * (m + 1)] += Ji
+        blocks[b][dim * m:dim * (m + 1)] += Jj
+    return [(vi, blocks[vi]) for vi in v], np.asarray(e["info"])
 
 
 def graph_information(oracle, dim, poses, edges, fixed=0):

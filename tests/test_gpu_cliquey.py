@@ -100,3 +100,36 @@ def test_multi_edges_round_trip_through_g2o_text(ctx, tmp_path):
         assert x["kind"] == y["kind"] and list(x["v"]) == list(y["v"]) and np.array_equal(x["info"], y["info"])
         if x["kind"] == 2:
             assert np.array_equal(x["pairs"], y["pairs"])
+
+
+def test_kld_and_optimiser_handle_multi_edges(ctx, oracle):
+    """The evaluator / optimiser assemble MultiEdgeCorrelated factors: KLD of a CliqueySubgraph-sparsified intel against the
+    CPU harness, a lower KLD than the plain tree (the cliques carry the correlations the tree drops), and the replay loop on
+    a `clsubgr` job line."""
+    import kld_harness as K
+    from sparsifyposegraph_b200 import capi
+    full = capi.Graph(datasets.path("intel"))
+    klds = {}
+    for topo in (R.TOPO_TREE, R.TOPO_CLIQUEY_SUBGRAPH):
+        g = capi.Graph(datasets.path("intel"))
+        which = capi.decimate_global(g.max_vertex_id, g.max_vertex_id, 2)
+        g.marginalize(ctx, which, capi.make_opts(topo, R.LIN_GLOBAL), R.ALG_NFR)
+        klds[topo], _ = full.kld(ctx, g)
+        if topo == R.TOPO_CLIQUEY_SUBGRAPH:
+            assert any(e["kind"] == 2 for e in g.edges())
+            ref, _ = K.full_graph_kld(oracle, 3, K.poses_of(full), full.edges(), K.poses_of(g), g.edges())
+            assert abs(klds[topo] - ref) <= 1e-6 * abs(ref)
+            chi0 = g.chi2(ctx)
+            st = g.optimize(ctx)
+            assert st["chi2_final"] <= chi0 * (1 + 1e-12)
+    print("intel KLD tree", klds[R.TOPO_TREE], "cliquey subgraph", klds[R.TOPO_CLIQUEY_SUBGRAPH])
+    assert 0 < klds[R.TOPO_CLIQUEY_SUBGRAPH] < klds[R.TOPO_TREE]
+    # evaluate() on a correlated topology
+    small = capi.Graph(dim=3)
+    for vid in range(200):
+        small.add_vertex(vid, full.vertex_pose(vid))
+    for e in full.edges():
+        if max(e["v"]) < 200:
+            small.add_edge(int(e["v"][0]), int(e["v"][1]), e["meas"], e["info"])
+    res = capi.evaluate(ctx, small, capi.parse_job("sen datasets/intel.g2o global clsubgr global 2"))
+    assert res["n_samples"] == 1 and np.isfinite(res["last_value"]) and res["last_value"] > 0
