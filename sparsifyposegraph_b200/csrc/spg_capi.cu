@@ -94,6 +94,11 @@ spg_status launch_general(spg_ctx *ctx, spg::KernelParams &kp) {
         kp.lean = 0;
         spg::plan_smem<D>(kp);
     }
+    // GLC tree: fewer factor-finishing warps (less scratch) before giving up on shared memory
+    while(kp.algorithm == SPG_ALG_GLC && kp.glc_warps > 1 && (size_t) kp.total_doubles * sizeof(double) > ctx->smem_optin) {
+        kp.glc_warps--;
+        spg::plan_smem<D>(kp);
+    }
     // working set beyond shared memory (SE3 > 19, SE2 > 39 vertices): same kernel over a global workspace
     if((size_t) kp.total_doubles * sizeof(double) > ctx->smem_optin)
         return D == 6 ? spg_launch_6_spill(ctx, kp) : spg_launch_3_spill(ctx, kp);

@@ -606,7 +606,9 @@ template <int NT>
 __device__ int jacobi_eig(double *A, int n, int ld, double *V, int ldv, double *cs, double *red) {
     constexpr int TX = (NT >= 128) ? 16 : 8;
     constexpr int TY = NT / TX;
-    const int tid = threadIdx.x;
+    // NT <= 32: a single warp, which may be any warp of a wider CTA (the GLC factors of a blanket are finished by
+    // several warps side by side)
+    const int tid = (NT <= 32) ? (int) (threadIdx.x & 31) : (int) threadIdx.x;
     const int tx = tid % TX, ty = tid / TX;
     for(int j = ty; j < n; j += TY)
         for(int i = tx; i < n; i += TX) V[i + j * ldv] = (i == j) ? 1.0 : 0.0;

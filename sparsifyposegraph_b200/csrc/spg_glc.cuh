@@ -194,7 +194,7 @@ template <int D, int NT>
 __device__ int glc_get_edge_small(const double *target, int nv, const int *kv, const double *s_pose_kept, double *sc,
                                   uint64_t *slot, int cslot, int nvcap) {
     constexpr int PS = PoseStride<D>::value;
-    const int tid = threadIdx.x;
+    const int tid = (NT <= 32) ? (int) (threadIdx.x & 31) : (int) threadIdx.x; // NT = 32: any one warp of the CTA
     const int c = D * nv, ldm = odd_ld(c);
     double *meas = sc;               // c
     double *AB = meas + c;           // 2 * nv * D*D
@@ -302,7 +302,7 @@ __device__ int glc_get_edge_small(const double *target, int nv, const int *kv, c
 // eps * D * max|lambda|, V diag(1/lambda | 0) V^T -> out (D x D, ld D). sc: 2*D*odd(D) + 2D + 16 doubles.
 template <int D, int NT>
 __device__ void glc_posdef_pinv(const double *A, int lda, double *out, double *sc) {
-    const int tid = threadIdx.x;
+    const int tid = (NT <= 32) ? (int) (threadIdx.x & 31) : (int) threadIdx.x; // NT = 32: any one warp of the CTA
     constexpr int LD = D | 1;
     double *M = sc, *V = sc + D * LD, *cs = V + D * LD, *red = cs + 2 * D + 4;
     for(int t = tid; t < D * D; t += NT) {

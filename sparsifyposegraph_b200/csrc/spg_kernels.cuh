@@ -1167,47 +1167,95 @@ __global__ void __launch_bounds__(NT, LEAN ? 2 : ((NT >= 256) ? 1 : (NT == 128 ?
                 if(rank < 0) status = SPG_BLANKET_EIG_NOCONV;
                 else if(rank > 0) emitted = 1;
             } else {
-                double *Sj = gsc, *tgt = Sj + 4 * D * D, *pin = tgt + 4 * D * D, *psc = pin + D * D;
-                double *esc = psc + (2 * D * (D | 1) + 2 * D + 16);
-                int *kv = s_misc + 12;
-                // root unary factor from the marginal of the root vertex (:134-140)
-                const int root = pk_a(s_tree[0]);
-                if(!glc_marginal<D, NT>(T, k, ldH, root, 0, 1, Sj, buf1, buf2)) status = SPG_BLANKET_NOT_PD_JOINT;
-                if(status == SPG_BLANKET_OK) {
-                    if(tid == 0) kv[0] = root;
-                    gsync<NT>();
-                    const int rank = glc_get_edge_small<D, NT>(Sj, 1, kv, kept_pose, esc, gout + SPG_OUT_HEADER_WORDS + emitted * slotw, cslot, nvcap);
-                    if(rank < 0) status = SPG_BLANKET_EIG_NOCONV;
-                    else if(rank > 0) emitted++;
+                // Tree: the root's unary factor and one binary factor per tree edge (:134-176). Phase A (whole CTA): the
+                // marginal of every factor's vertices, parked in the information area of the factor's own output slot
+                // (global memory, L2-resident; the slot is rewritten in phase B). Phase B: the factors are independent, so
+                // warp w finishes factors w, w + W, ... on its own scratch with warp-level barriers only (pseudo-inverse,
+                // conditional target, J^-1, 12 x 12 eigen-decomposition, W) — up to W factors side by side instead of
+                // one factor at a time behind CTA-wide barriers.
+                const int nf = 1 + n_out; // factor 0: root; factor f: tree edge f - 1
+                const int c2 = 2 * D;
+                int *s_rank = s_heapab; // rank of every factor (the Chow-Liu scratch is dead)
+                for(int f = 0; f < nf && status == SPG_BLANKET_OK; f++) {
+                    double *park = reinterpret_cast<double *>(gout + SPG_OUT_HEADER_WORDS + (int64_t) f * slotw + 1 + spgr_pad2(nvcap) + cslot);
+                    const int a = f ? pk_a(s_tree[f - 1]) : pk_a(s_tree[0]), bb = f ? pk_b(s_tree[f - 1]) : 0;
+                    if(!glc_marginal<D, NT>(T, k, ldH, a, bb, f ? 2 : 1, park, buf1, buf2)) status = SPG_BLANKET_NOT_PD_JOINT;
                 }
-                for(int e = 0; e < n_out && status == SPG_BLANKET_OK; e++) {
-                    const int a = pk_a(s_tree[e]), bb = pk_b(s_tree[e]);
-                    if(!glc_marginal<D, NT>(T, k, ldH, a, bb, 2, Sj, buf1, buf2)) { status = SPG_BLANKET_NOT_PD_JOINT; break; }
-                    // target = [Jaa Jab; Jba Jba pinv(Jaa) Jab], then selfadjointView<Upper> (:146-176)
-                    glc_posdef_pinv<D, NT>(Sj, 2 * D, pin, psc);
-                    for(int t = tid; t < 4 * D * D; t += NT) {
-                        const int i = t % (2 * D), j = t / (2 * D);
-                        if(i <= j) {
-                            double v;
-                            if(i >= D) { // lower-right block: Jba * pinv * Jab
-                                v = 0;
-                                for(int p = 0; p < D; p++) {
-                                    double u = 0;
-                                    for(int q = 0; q < D; q++) u += Sj[i + q * 2 * D] * pin[q + p * D];
-                                    v += u * Sj[p + j * 2 * D];
+                SPG_T(14);
+                __threadfence_block();
+                gsync<NT>();
+                if(status == SPG_BLANKET_OK) {
+                    const int W = min(P.glc_warps > 0 ? P.glc_warps : 1, (NT + 31) / 32);
+                    const int warp = tid >> 5, lane = tid & 31;
+                    if(warp < W) {
+                        double *ws = gsc + (size_t) warp * P.glc_warp_doubles;
+                        double *Sj = ws, *tgt = Sj + 4 * D * D, *pin = tgt + 4 * D * D, *psc = pin + D * D;
+                        double *esc = psc + (2 * D * (D | 1) + 2 * D + 16);
+                        int *kv = reinterpret_cast<int *>(esc + (8 * c2 * c2 + 8 * c2 + 64));
+                        for(int f = warp; f < nf; f += W) {
+                            uint64_t *slotp = gout + SPG_OUT_HEADER_WORDS + (int64_t) f * slotw;
+                            const double *park = reinterpret_cast<const double *>(slotp + 1 + spgr_pad2(nvcap) + cslot);
+                            const int cf = f ? c2 : D;
+                            for(int t = lane; t < cf * cf; t += 32) Sj[t] = park[t];
+                            __syncwarp();
+                            const double *target = Sj;
+                            if(f) {
+                                // target = [Jaa Jab; Jba Jba pinv(Jaa) Jab], then selfadjointView<Upper> (:146-176)
+                                glc_posdef_pinv<D, 32>(Sj, 2 * D, pin, psc);
+                                for(int t = lane; t < 4 * D * D; t += 32) {
+                                    const int i = t % (2 * D), j = t / (2 * D);
+                                    if(i <= j) {
+                                        double v;
+                                        if(i >= D) { // lower-right block: Jba * pinv * Jab
+                                            v = 0;
+                                            for(int p = 0; p < D; p++) {
+                                                double u = 0;
+                                                for(int q = 0; q < D; q++) u += Sj[i + q * 2 * D] * pin[q + p * D];
+                                                v += u * Sj[p + j * 2 * D];
+                                            }
+                                        } else {
+                                            v = Sj[i + j * 2 * D];
+                                        }
+                                        tgt[i + j * 2 * D] = v;
+                                        tgt[j + i * 2 * D] = v;
+                                    }
                                 }
-                            } else {
-                                v = Sj[i + j * 2 * D];
+                                target = tgt;
                             }
-                            tgt[i + j * 2 * D] = v;
-                            tgt[j + i * 2 * D] = v;
+                            if(lane == 0) {
+                                kv[0] = f ? pk_a(s_tree[f - 1]) : pk_a(s_tree[0]);
+                                kv[1] = f ? pk_b(s_tree[f - 1]) : 0;
+                            }
+                            __syncwarp();
+                            // the parked marginal is consumed: clear the slot before the factor is written into it
+                            for(int t = lane; t < (int) slotw; t += 32) slotp[t] = 0;
+                            __syncwarp();
+                            const int rank = glc_get_edge_small<D, 32>(target, f ? 2 : 1, kv, kept_pose, esc, slotp, cslot, nvcap);
+                            if(lane == 0) s_rank[f] = rank;
+                            __syncwarp();
                         }
                     }
-                    if(tid == 0) { kv[0] = a; kv[1] = bb; }
+                    __threadfence_block();
                     gsync<NT>();
-                    const int rank = glc_get_edge_small<D, NT>(tgt, 2, kv, kept_pose, esc, gout + SPG_OUT_HEADER_WORDS + emitted * slotw, cslot, nvcap);
-                    if(rank < 0) status = SPG_BLANKET_EIG_NOCONV;
-                    else if(rank > 0) emitted++;
+                    SPG_T(15);
+                    // compaction: factors of rank 0 are dropped (getEdge returned NULL, :85-89), the others keep their order
+                    for(int f = 0; f < nf; f++) {
+                        const int rank = s_rank[f];
+                        if(rank < 0) status = SPG_BLANKET_EIG_NOCONV;
+                        else if(rank > 0) {
+                            if(emitted != f) {
+                                uint64_t *dst = gout + SPG_OUT_HEADER_WORDS + (int64_t) emitted * slotw;
+                                const uint64_t *src = gout + SPG_OUT_HEADER_WORDS + (int64_t) f * slotw;
+                                for(int t = tid; t < (int) slotw; t += NT) dst[t] = src[t];
+                                gsync<NT>();
+                            }
+                            emitted++;
+                        }
+                    }
+                    for(int f = emitted; f < nf; f++) { // slots behind the last emitted factor read as empty
+                        uint64_t *dst = gout + SPG_OUT_HEADER_WORDS + (int64_t) f * slotw;
+                        for(int t = tid; t < (int) slotw; t += NT) dst[t] = 0;
+                    }
                 }
             }
             n_out = emitted;

@@ -35,6 +35,8 @@ struct KernelParams {
     int32_t off_pose, off_buf0, off_buf1, off_buf2, off_small, total_doubles;
     int32_t buf0_doubles, buf1_doubles, buf2_doubles;
     int32_t off_glc, glc_doubles; // GLC scratch (only for algorithm == SPG_ALG_GLC launches)
+    int32_t glc_warps;            // GLC tree: warps that finish factors side by side (0: plan_smem picks by CTA width)
+    int32_t glc_warp_doubles;     // scratch of one such warp
     double *nfr_ws;               // per-CTA workspace of the iterative NFR fit (global memory)
     int64_t nfr_ws_stride;        // doubles per CTA
     double *gws;                  // spill variant: per-CTA slice holding the whole buffer plan (global memory)
@@ -89,7 +91,14 @@ inline void plan_smem(KernelParams &p) {
         // tree: joint (4D^2) + target (4D^2) + pinv out (D^2) + pinv scratch + getEdge scratch (c = 2D);
         // dense: meas k + blocks 2 nk D^2 + Jacobi scratch + order
         const int c = 2 * D;
-        const int tree = 4 * D * D + 4 * D * D + D * D + (2 * D * (D | 1) + 2 * D + 16) + (8 * c * c + 8 * c + 64);
+        // per warp: joint (4D^2) + target (4D^2) + pinv out (D^2) + pinv scratch + getEdge scratch (c = 2D) + vertex pair
+        p.glc_warp_doubles = 4 * D * D + 4 * D * D + D * D + (2 * D * (D | 1) + 2 * D + 16) + (8 * c * c + 8 * c + 64) + 2;
+        if(p.glc_warps <= 0) { // warps of the CTA width launch_general picks for this N, at most 4
+            const int NN = D * p.max_nv;
+            p.glc_warps = NN <= 12 ? 1 : (NN <= 32 ? 2 : 4);
+        }
+        const int tree = p.glc_warps * p.glc_warp_doubles;
+        // dense: meas k + blocks 2 nk D^2 + Jacobi scratch + order
         const int dense = kmax + 2 * nk * D * D + (kmax + kmax / 2 + 8) + 8 + kmax / 2 + 2;
         p.glc_doubles = (tree > dense ? tree : dense) + 8;
         o += p.glc_doubles;

@@ -132,4 +132,5 @@ def test_kld_and_optimiser_handle_multi_edges(ctx, oracle):
         if max(e["v"]) < 200:
             small.add_edge(int(e["v"][0]), int(e["v"][1]), e["meas"], e["info"])
     res = capi.evaluate(ctx, small, capi.parse_job("sen datasets/intel.g2o global clsubgr global 2"))
-    assert res["n_samples"] == 1 and np.isfinite(res["last_value"]) and res["last_value"] > 0
+    # the first 200 poses of intel are almost a chain: the cliques keep every correlation and the KLD is 0 up to rounding
+    assert res["n_samples"] == 1 and np.isfinite(res["last_value"]) and -1e-9 < res["last_value"] < 1.0 and res["n_marginalized"] == 98
