@@ -318,46 +318,85 @@ def main():
     # ---- timed: end to end through the host-buffer C ABI ----------------------------------------------
     e2e_steps = max(1, min(args.steps, 3))
     shard_info = None
+    e2e_modes = {}
+    shm = None
+    if world > 1:
+        # host-resident graph on one node: ONE output buffer in POSIX shared memory, mapped and page-locked by every rank;
+        # each rank copies the records of its own blankets into it over its own PCIe link (SPG_ROOT_SHARED_HOST)
+        from multiprocessing import shared_memory
+        name = [f"spg_bench_out_{os.getpid()}" if rank == 0 else None]
+        if rank == 0:
+            shm = shared_memory.SharedMemory(name=name[0], create=True, size=out_words * 8)
+        dist.broadcast_object_list(name, src=0)
+        if rank != 0:
+            shm = shared_memory.SharedMemory(name=name[0])
+        sh_out_np = np.ndarray((out_words,), dtype=np.uint64, buffer=shm.buf)
+        rc = torch.cuda.cudart().cudaHostRegister(sh_out_np.ctypes.data, out_words * 8, 0)
+        assert int(rc) == 0, f"cudaHostRegister failed: {rc}"
 
-    def e2e_call():
+    def e2e_call(mode):
         nonlocal shard_info
         if world == 1:
             ctx.remove_round(6, R.ALG_NFR, opts, h_rec_np, rec_off_all, out_off_all, out=h_out_np)
-        else:  # collective: shards by the library's cost model, outputs gathered to rank 0 (the graph holder)
+        elif mode == "shared_host":   # collective; every rank writes its slices of the one host buffer, then the ranks meet
+            _, shard_info = ctx.remove_round_sharded(6, R.ALG_NFR, opts, h_rec_np, rec_off_all, out_off_all, out=sh_out_np, root=-2)
+            dist.barrier()
+        else:                         # NCCL gather of the records to rank 0 over NVLink, rank 0 copies everything to its host buffer
             _, shard_info = ctx.remove_round_sharded(6, R.ALG_NFR, opts, h_rec_np, rec_off_all, out_off_all, out=h_out_np, root=0)
-    h_out_np[:] = 0
-    e2e_call()  # warm-up (allocations)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_call()
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    n_ok = 0
-    if rank == 0:
-        hdr = h_out_np[out_off_all[:-1]].view(np.int32).reshape(-1, 2)
-        nk_all = np.concatenate([np.full(b["B"], b["n"] - 2) for b in sweep])
-        n_ok = int(((hdr[:, 0] == 0) & (hdr[:, 1] == nk_all)).sum())
-    if world > 1:
-        h2d_bytes, d2h_bytes = shard_info["h2d_bytes"], shard_info["d2h_bytes"]  # this rank's; summed over ranks below
 
+    def count_ok(buf):
+        hdr = buf[out_off_all[:-1]].view(np.int32).reshape(-1, 2)
+        nk_all = np.concatenate([np.full(b["B"], b["n"] - 2) for b in sweep])
+        return int(((hdr[:, 0] == 0) & (hdr[:, 1] == nk_all)).sum())
+
+    n_ok = 0
+    for mode in (["host"] if world == 1 else ["nccl_root0", "shared_host"]):
+        buf = h_out_np if mode != "shared_host" else sh_out_np
+        if rank == 0:
+            buf[:] = 0
+        barrier()
+        e2e_call(mode)  # warm-up (allocations)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_call(mode)
+        torch.cuda.synchronize()
+        secs = time.perf_counter() - t0
+        barrier()
+        ok = count_ok(buf) if rank == 0 else 0
+        e2e_modes[mode] = {"seconds": secs, "blankets_ok": ok,
+                           "h2d": shard_info["h2d_bytes"] if shard_info else h2d_bytes,
+                           "d2h": shard_info["d2h_bytes"] if shard_info else d2h_bytes,
+                           "gather_window_ms": shard_info["gather_window_ms"] if shard_info else None}
+    headline = "host" if world == 1 else "shared_host"
+    e2e_s, n_ok = e2e_modes[headline]["seconds"], e2e_modes[headline]["blankets_ok"]
+    h2d_bytes, d2h_bytes = e2e_modes[headline]["h2d"], e2e_modes[headline]["d2h"]
     # ---- reduce over ranks ----------------------------------------------------------------------------
     gather = None
     if world > 1:
-        t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device="cuda")
+        t = torch.tensor([dev_ms, e2e_s, e2e_modes["nccl_root0"]["seconds"]], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, e2e_s = float(t[0]), float(t[1])
-        t = torch.tensor([n_dev_ok, h2d_bytes, d2h_bytes], dtype=torch.int64, device="cuda")
+        dev_ms, e2e_s, nccl_s = float(t[0]), float(t[1]), float(t[2])
+        t = torch.tensor([n_dev_ok, h2d_bytes, d2h_bytes, e2e_modes["nccl_root0"]["h2d"], e2e_modes["nccl_root0"]["d2h"]], dtype=torch.int64, device="cuda")
         tmin = t.clone()
         dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         n_dev_ok = int(tmin[0])          # the worst rank's count of complete, OK blankets in its gathered buffers
         h2d_bytes, d2h_bytes = int(t[1]), int(t[2])  # whole job
         gather = {"all_gather_bytes_per_step_per_rank": int(sum(int(b["out_off"][-1]) for b in sweep) * 8 * (world - 1) // world),
-                  "e2e_gather_to_root_bytes_per_step": int(out_words * 8 * (world - 1) // world),
-                  "e2e_gather_window_ms_rank0": shard_info["gather_window_ms"] if shard_info else None,
+                  "e2e_mode": "SPG_ROOT_SHARED_HOST: every rank copies its own records into one shared, page-locked host buffer",
+                  "e2e_nccl_gather_to_rank0": {"value": total_blankets * e2e_steps / nccl_s, "unit": UNIT,
+                                               "blankets_ok": e2e_modes["nccl_root0"]["blankets_ok"],
+                                               "h2d_bytes_per_step": int(t[3]), "d2h_bytes_per_step": int(t[4]),
+                                               "gather_window_ms_rank0": e2e_modes["nccl_root0"]["gather_window_ms"],
+                                               "note": "rank 0 reads ALL records back over its own PCIe link: bound by that copy"},
                   "e2e_pipeline_steps": shard_info["steps"] if shard_info else None}
-
+    if shm is not None:
+        torch.cuda.cudart().cudaHostUnregister(sh_out_np.ctypes.data)
+        del sh_out_np
+        shm.close()
+        if rank == 0:
+            shm.unlink()
     if rank == 0:
         value = total_blankets * args.steps / (dev_ms * 1e-3)   # the one sweep, whatever the number of ranks
         e2e_value = total_blankets * e2e_steps / e2e_s

@@ -269,9 +269,15 @@ typedef struct {
  * buffers; a rank only reads the records of its own blankets, and the headers of the others for the balance).
  * The round is cut into pipeline steps of about equal bytes and every step is split over the ranks by modelled
  * cost, so each rank moves 1/nranks of the bytes and does 1/nranks of the work of every step.
- * root < 0: every rank gets the complete output (replicated graphs, all-gather); root >= 0: only that rank does
- * (the others get the records of their own blankets). info may be NULL.
+ * root == -1: every rank gets the complete output (replicated graphs, all-gather); root >= 0: only that rank does
+ * (the others get the records of their own blankets). root == SPG_ROOT_SHARED_HOST: no device gather at all — `out->out`
+ * is ONE host buffer mapped by every rank of the box (POSIX shared memory, page-locked in each process) and every rank
+ * copies the records of its own blankets straight into it over its own PCIe link; the caller synchronises the ranks
+ * before the graph-holding process reads the buffer. That is the fastest way to a host-resident graph on one node (the
+ * root of a gather is bound by ITS device -> host copy of everything); the NCCL modes serve device-resident consumers
+ * and replicated graphs. info may be NULL.
  */
+#define SPG_ROOT_SHARED_HOST (-2)
 spg_status spg_remove_round_sharded(spg_ctx *ctx, const spg_round_in *in, spg_round_out *out, int32_t root,
                                     spg_shard_info *info);
 /*

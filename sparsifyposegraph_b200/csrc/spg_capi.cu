@@ -119,14 +119,19 @@ spg_status launch_general(spg_ctx *ctx, spg::KernelParams &kp) {
 // Host-side validation of blankets [b0, b1) of a round: everything the kernels index with (edge offset table,
 // edge-local vertex indices, edge sizes, output slice) must lie inside the record / the output slice.
 // Returns the index of the first malformed blanket, or -1.
-int validate_records(const spg_round_in *in, int b0, int b1) {
+int validate_records(const spg_round_in *in, int b0, int b1, int32_t *hdr3, int hdr_base) {
     const int dim = in->dim;
     for(int b = b0; b < b1; b++) {
         const uint64_t *rec = in->records + in->rec_off[b];
+        if(b + 1 < b1) __builtin_prefetch(in->records + in->rec_off[b + 1]);
         const int64_t rw = in->rec_off[b + 1] - in->rec_off[b];
         if(rw < SPG_REC_HEADER_WORDS) return b;
         const int32_t *h = reinterpret_cast<const int32_t *>(rec);
         const int nv = h[0], nrem = h[1], ne = h[2];
+        if(hdr3) { // what the bucketing needs, captured while the header is in cache
+            int32_t *o = hdr3 + 3 * (size_t) (b - hdr_base);
+            o[0] = nv; o[1] = ne; o[2] = h[4];
+        }
         if(h[3] != dim || h[4] > rw || h[4] < SPG_REC_HEADER_WORDS || nv < 1 || nrem < 1 || nrem > nv || ne < 0) return b;
         const int64_t words = h[4], fixed = spgr_record_fixed_words(dim, nv, ne);
         if(fixed > words) return b;
@@ -157,16 +162,17 @@ int validate_records(const spg_round_in *in, int b0, int b1) {
 }
 
 // the same over a large range, spread over host threads (the check of chunk c+1 overlaps the GPU work of chunk c)
-int validate_records_mt(const spg_round_in *in, int b0, int b1) {
+int validate_records_mt(const spg_round_in *in, int b0, int b1, int32_t *hdr3, int nranks) {
     const int n = b1 - b0;
-    unsigned nthr = std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 8u);
-    if(n < 8192 || nthr <= 1) return validate_records(in, b0, b1);
+    // the ranks of a sharded round share the host: split its cores between them
+    unsigned nthr = std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency() / (unsigned) std::max(1, nranks)), 8u);
+    if(n < 4096 || nthr <= 1) return validate_records(in, b0, b1, hdr3, b0);
     std::vector<int> bad(nthr, -1);
     std::vector<std::thread> pool;
     const int per = (n + (int) nthr - 1) / (int) nthr;
     for(unsigned t = 0; t < nthr; t++) {
         const int lo = std::min(b1, b0 + (int) t * per), hi = std::min(b1, lo + per);
-        if(lo < hi) pool.emplace_back([&bad, in, lo, hi, t] { bad[t] = validate_records(in, lo, hi); });
+        if(lo < hi) pool.emplace_back([&bad, in, lo, hi, t, hdr3, b0] { bad[t] = validate_records(in, lo, hi, hdr3, b0); });
     }
     for(auto &th : pool) th.join();
     for(int v : bad)
@@ -253,9 +259,11 @@ spg_status spg_round_enqueue_chunk(spg_ctx *ctx, const spg_round_in *in, spg::Ro
     static const int bounds6[] = {3, 4, 5, 6, 7, 8, 10, 12, 14, 16, 20, 24, 32, 48, 64, 128, 1 << 30};
     constexpr int NBK = sizeof(bounds6) / sizeof(int);
     const int dim = in->dim;
+    std::vector<int32_t> hdr3; // (n_vert, n_edges, rec_words) of every blanket of the chunk
     // ---- validate the chunk's records before anything of it is launched (runs while the GPU works on c-1)
     {
-        const int bad = validate_records_mt(in, b0, b1);
+        hdr3.resize(3 * (size_t) (b1 - b0));
+        const int bad = validate_records_mt(in, b0, b1, hdr3.data(), ctx->nranks);
         if(bad >= 0) {
             cudaDeviceSynchronize();
             set_err("malformed blanket record " + std::to_string(bad) +
@@ -266,14 +274,14 @@ spg_status spg_round_enqueue_chunk(spg_ctx *ctx, const spg_round_in *in, spg::Ro
     // ---- bucket this chunk by blanket size -----------------------------------------------------
     std::vector<Bucket> buckets(NBK);
     for(int b = b0; b < b1; b++) {
-        const int32_t *h = reinterpret_cast<const int32_t *>(in->records + in->rec_off[b]);
+        const int32_t *h = hdr3.data() + 3 * (size_t) (b - b0);
         int bi = 0;
         while(h[0] > bounds6[bi]) bi++;
         Bucket &B = buckets[bi];
         B.list.push_back(b);
         B.max_nv = std::max(B.max_nv, (int) h[0]);
-        B.max_e = std::max(B.max_e, (int) h[2]);
-        B.max_rec = std::max(B.max_rec, (int) h[4]);
+        B.max_e = std::max(B.max_e, (int) h[1]);
+        B.max_rec = std::max(B.max_rec, (int) h[2]);
     }
     size_t pos = (size_t) b0;
     for(auto &B : buckets) {

@@ -13,8 +13,12 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "spg_ctx.h"
@@ -87,20 +91,40 @@ inline double blanket_cost(int algorithm, int topology, int nv, int ne) {
     return 40.0 + 12.0 * ne + (double) nv * nv * (nv + 6.0);
 }
 
-// contiguous split of blankets [b0, b1) into R parts of about equal modelled cost: bounds[0..R]
-void cost_bounds(const spg_round_in *in, int b0, int b1, int R, int32_t *bounds) {
-    const int nb = b1 - b0;
-    std::vector<double> cum((size_t) nb + 1, 0.0);
-    for(int b = 0; b < nb; b++) {
-        const int32_t *h = reinterpret_cast<const int32_t *>(in->records + in->rec_off[b0 + b]);
-        cum[b + 1] = cum[b] + blanket_cost(in->algorithm, in->opts.topology, h[0], h[2]);
+// cum[b] = modelled cost of blankets [0, b): the headers are read by several host threads (one cache miss per blanket
+// in a multi-GB record buffer), the prefix sum is sequential
+void cost_prefix(const spg_round_in *in, std::vector<double> &cum) {
+    const int nb = in->n_blankets;
+    cum.assign((size_t) nb + 1, 0.0);
+    auto fill = [&](int lo, int hi) {
+        for(int b = lo; b < hi; b++) {
+            const int32_t *h = reinterpret_cast<const int32_t *>(in->records + in->rec_off[b]);
+            cum[(size_t) b + 1] = blanket_cost(in->algorithm, in->opts.topology, h[0], h[2]);
+        }
+    };
+    const unsigned nthr = nb < 16384 ? 1u : std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 8u);
+    if(nthr <= 1) fill(0, nb);
+    else {
+        std::vector<std::thread> pool;
+        const int per = (nb + (int) nthr - 1) / (int) nthr;
+        for(unsigned t = 0; t < nthr; t++) {
+            const int lo = std::min(nb, (int) t * per), hi = std::min(nb, lo + per);
+            if(lo < hi) pool.emplace_back(fill, lo, hi);
+        }
+        for(auto &th : pool) th.join();
     }
+    for(int b = 0; b < nb; b++) cum[(size_t) b + 1] += cum[b];
+}
+
+// contiguous split of blankets [b0, b1) into R parts of about equal modelled cost: bounds[0..R]
+void cost_bounds(const std::vector<double> &cum, int b0, int b1, int R, int32_t *bounds) {
     bounds[0] = b0;
+    const double base = cum[b0], total = cum[b1] - base;
     for(int r = 1; r < R; r++) {
-        const double goal = cum[nb] * r / R;
-        int b = (int) (std::lower_bound(cum.begin(), cum.end(), goal) - cum.begin());
-        if(b > 0 && goal - cum[b - 1] < cum[b] - goal) b--; // nearer boundary
-        bounds[r] = std::max(bounds[r - 1], b0 + std::min(b, nb));
+        const double goal = base + total * r / R;
+        int b = (int) (std::lower_bound(cum.begin() + b0, cum.begin() + b1 + 1, goal) - cum.begin());
+        if(b > b0 && goal - cum[b - 1] < cum[b] - goal) b--; // nearer boundary
+        bounds[r] = std::max(bounds[r - 1], std::min(b, b1));
     }
     bounds[R] = b1;
 }
@@ -222,7 +246,9 @@ int32_t spg_comm_nccl_version(void) {
 // pure host code (CPU tests cover it): contiguous shards of the round, balanced by the per-blanket cost model
 spg_status spg_shard_bounds(const spg_round_in *in, int32_t nranks, int32_t *bounds) {
     if(!in || !bounds || nranks < 1 || in->n_blankets < 0) return SPG_ERR_INVALID;
-    cost_bounds(in, 0, in->n_blankets, nranks, bounds);
+    std::vector<double> cum;
+    cost_prefix(in, cum);
+    cost_bounds(cum, 0, in->n_blankets, nranks, bounds);
     return SPG_OK;
 }
 
@@ -268,7 +294,8 @@ spg_status spg_remove_round_sharded_device(spg_ctx *ctx, const spg_round_in *in,
 
 spg_status spg_remove_round_sharded(spg_ctx *ctx, const spg_round_in *in, spg_round_out *out, int32_t root,
                                     spg_shard_info *info) {
-    if(!ctx || !in || !out || !out->out || (in->dim != 3 && in->dim != 6) || in->n_blankets < 0 || root >= ctx->nranks) {
+    if(!ctx || !in || !out || !out->out || (in->dim != 3 && in->dim != 6) || in->n_blankets < 0 || root >= ctx->nranks ||
+       root < SPG_ROOT_SHARED_HOST) {
         spg_set_err("spg_remove_round_sharded: bad arguments");
         return SPG_ERR_INVALID;
     }
@@ -285,6 +312,9 @@ spg_status spg_remove_round_sharded(spg_ctx *ctx, const spg_round_in *in, spg_ro
     }
     SPG_CUDA(cudaSetDevice(ctx->device));
 
+    const bool prof = getenv("SPG_SHARD_PROF") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double tp0 = now();
     // ---- every rank derives the same plan from the (replicated) round description --------------------------------
     // Step-major: the round is cut into `steps` contiguous chunks of about equal bytes, and every chunk is split over
     // the ranks by modelled cost. Every rank then moves 1/R of the bytes and does 1/R of the work of every chunk,
@@ -296,8 +326,10 @@ spg_status spg_remove_round_sharded(spg_ctx *ctx, const spg_round_in *in, spg_ro
     std::vector<int32_t> sb((size_t) R + 1);
     std::vector<std::vector<int32_t>> lo((size_t) steps, std::vector<int32_t>((size_t) R + 1)); // lo[s][r] .. lo[s][r+1]: rank r's blankets of step s
     int mine = 0;
+    std::vector<double> cum;
+    cost_prefix(in, cum);
     for(int s2 = 0; s2 < steps; s2++) {
-        cost_bounds(in, gcb[s2], gcb[s2 + 1], R, sb.data());
+        cost_bounds(cum, gcb[s2], gcb[s2 + 1], R, sb.data());
         lo[s2] = sb;
         mine += sb[me + 1] - sb[me];
     }
@@ -305,10 +337,13 @@ spg_status spg_remove_round_sharded(spg_ctx *ctx, const spg_round_in *in, spg_ro
     st = ensure_comm_stream(ctx, steps);
     if(st != SPG_OK) return st;
 
+    const double tp1 = now();
     spg::RoundRun run;
     st = spg_round_prepare(ctx, in, out, steps, run);
     if(st != SPG_OK) return st;
-    const bool receiver = root < 0 || root == me;
+    const double tp2 = now();
+    const bool shared_host = root == SPG_ROOT_SHARED_HOST; // every rank writes its own records into one shared host buffer
+    const bool receiver = !shared_host && (root < 0 || root == me);
     uint64_t *d_out = reinterpret_cast<uint64_t *>(ctx->d_out.p);
     int64_t moved = 0, h2d = 2 * (int64_t) (nb + 1) * 8, d2h = 0;
     std::vector<int64_t> w0((size_t) R), cnt((size_t) R);
@@ -321,7 +356,7 @@ spg_status spg_remove_round_sharded(spg_ctx *ctx, const spg_round_in *in, spg_ro
             if(st != SPG_OK) return st;
             launched = true;
         }
-        if(R > 1) {
+        if(R > 1 && !shared_host) {
             // the slices of step s of all ranks are disjoint word ranges of the one output buffer
             if(launched) SPG_CUDA(cudaStreamWaitEvent(ctx->s_comm, ctx->ev_pool[2 * s + 1], 0));
             for(int r = 0; r < R; r++) {
@@ -332,7 +367,7 @@ spg_status spg_remove_round_sharded(spg_ctx *ctx, const spg_round_in *in, spg_ro
             if(st != SPG_OK) return st;
             SPG_CUDA(cudaEventRecord(ctx->ev_comm[s], ctx->s_comm));
             if(receiver) SPG_CUDA(cudaStreamWaitEvent(ctx->s_out, ctx->ev_comm[s], 0));
-        } else if(launched) {
+        } else if(launched && !shared_host) {
             SPG_CUDA(cudaStreamWaitEvent(ctx->s_out, ctx->ev_pool[2 * s + 1], 0));
         }
         // ---- D2H: a receiver reads the whole step (the slices of the ranks are adjacent), the others only their own
@@ -349,8 +384,12 @@ spg_status spg_remove_round_sharded(spg_ctx *ctx, const spg_round_in *in, spg_ro
         }
     }
     SPG_CUDA(cudaEventRecord(ctx->ev_g1, ctx->s_comm));
+    const double tp3 = now();
     st = spg_round_finish(ctx, out, run);
     if(st != SPG_OK) return st;
+    if(prof)
+        fprintf(stderr, "[spg shard r%d] plan %.1f ms, prepare %.1f ms, enqueue loop (validate + bucket + launches) %.1f ms, drain %.1f ms\n", me,
+                tp1 - tp0, tp2 - tp1, tp3 - tp2, now() - tp3);
     SPG_CUDA(cudaStreamSynchronize(ctx->s_comm));
     float gms = 0;
     SPG_CUDA(cudaEventElapsedTime(&gms, ctx->ev_g0, ctx->ev_g1));
