@@ -177,6 +177,9 @@ const char *spg_version(void);
 const char *spg_last_error(void);
 spg_status spg_create(spg_ctx **ctx, const spg_config *cfg);
 void spg_destroy(spg_ctx *ctx);
+/* grow the context's page-locked staging buffers (round records / round outputs of the graph level) ahead of time:
+ * page-locking hundreds of MB costs tenths of a second, better spent outside a latency-sensitive removal */
+spg_status spg_reserve_staging(spg_ctx *ctx, int64_t record_words, int64_t out_words);
 /* number of kernels launched by this context so far (bench.py's gpu_launches) */
 int64_t spg_launch_count(const spg_ctx *ctx);
 /* device time (ms, CUDA events on the context stream) of the kernels of the last round */
@@ -267,8 +270,9 @@ typedef struct {
 /*
  * spg_remove_round over all ranks of the communicator. Collective: every rank calls it with the SAME round (host
  * buffers; a rank only reads the records of its own blankets, and the headers of the others for the balance).
- * The round is cut into pipeline steps of about equal bytes and every step is split over the ranks by modelled
- * cost, so each rank moves 1/nranks of the bytes and does 1/nranks of the work of every step.
+ * The round is cut into pipeline steps of about equal bytes and every step is split over the ranks by bytes again
+ * (offset tables only: the plan is derived by every rank on every call and must not touch the records), so each rank
+ * moves 1/nranks of the bytes of every step and — cost per byte being flat within a step — does 1/nranks of its work.
  * root == -1: every rank gets the complete output (replicated graphs, all-gather); root >= 0: only that rank does
  * (the others get the records of their own blankets). root == SPG_ROOT_SHARED_HOST: no device gather at all — `out->out`
  * is ONE host buffer mapped by every rank of the box (POSIX shared memory, page-locked in each process) and every rank

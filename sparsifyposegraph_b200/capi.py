@@ -211,6 +211,12 @@ class Context:
     def sync(self):
         _check(lib().spg_sync(self.h))
 
+    def reserve_staging(self, record_words, out_words):
+        """Page-lock the graph-level staging buffers ahead of time (spg_reserve_staging)."""
+        L = lib()
+        L.spg_reserve_staging.argtypes = [C.c_void_p, C.c_int64, C.c_int64]
+        _check(L.spg_reserve_staging(self.h, int(record_words), int(out_words)))
+
     # ---- sharded rounds (spg_comm.cu): one process per GPU, NCCL gather of the substitute-edge records -------------
     def comm_init(self, nranks, rank, unique_id=None):
         """unique_id: the SPG_COMM_ID_BYTES bytes rank 0 got from comm_unique_id() (any transport); None for nranks == 1."""

@@ -137,6 +137,9 @@ int validate_records(const spg_round_in *in, int b0, int b1, int32_t *hdr3, int 
         if(fixed > words) return b;
         const int32_t *etab = reinterpret_cast<const int32_t *>(rec + spgr_edgetab_off(dim, nv));
         for(int e = 0; e < ne; e++) {
+            // the edge headers of a record are a cache line or more apart: fetch a few edges ahead (offsets are checked
+            // before use; a wild prefetch address is harmless)
+            if(e + 6 < ne) __builtin_prefetch(rec + (etab[e + 6] & 0xffffff));
             const int64_t eo = etab[e];
             if(eo < fixed || eo + 2 > words) return b;
             const int32_t *eh = reinterpret_cast<const int32_t *>(rec + eo);
@@ -433,6 +436,18 @@ void spg_destroy(spg_ctx *ctx) {
     delete ctx;
 }
 
+spg_status spg_reserve_staging(spg_ctx *ctx, int64_t record_words, int64_t out_words) {
+    if(check_device(ctx) != SPG_OK || record_words < 0 || out_words < 0) return SPG_ERR_INVALID;
+    if(record_words > 0 && !spg_ctx_pinned(ctx, 0, (size_t) record_words)) {
+        set_err("cannot page-lock the record staging buffer");
+        return SPG_ERR_CUDA;
+    }
+    if(out_words > 0 && !spg_ctx_pinned(ctx, 1, (size_t) out_words)) {
+        set_err("cannot page-lock the output staging buffer");
+        return SPG_ERR_CUDA;
+    }
+    return SPG_OK;
+}
 int64_t spg_launch_count(const spg_ctx *ctx) { return ctx ? ctx->launches : 0; }
 double spg_last_kernel_ms(const spg_ctx *ctx) { return ctx ? ctx->last_ms : 0.0; }
 void *spg_stream(spg_ctx *ctx) { return ctx ? (void *) ctx->stream : nullptr; }

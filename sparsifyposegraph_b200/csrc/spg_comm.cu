@@ -326,10 +326,15 @@ spg_status spg_remove_round_sharded(spg_ctx *ctx, const spg_round_in *in, spg_ro
     std::vector<int32_t> sb((size_t) R + 1);
     std::vector<std::vector<int32_t>> lo((size_t) steps, std::vector<int32_t>((size_t) R + 1)); // lo[s][r] .. lo[s][r+1]: rank r's blankets of step s
     int mine = 0;
-    std::vector<double> cum;
-    cost_prefix(in, cum);
+    // Inside a step the split is by BYTES (records + outputs), read off the offset tables alone: every rank derives the
+    // plan of the whole round on every call, so the plan must not touch the records (a header read per blanket is a cache
+    // miss per blanket, times the number of ranks). A pipeline step is a short contiguous run of the round, and for the
+    // NFR-tree path cost per byte is flat (both grow linearly with the blanket size), so bytes balance the work too;
+    // spg_shard_bounds offers the cost-model split for callers that shard by themselves.
+    std::vector<int> sbi;
     for(int s2 = 0; s2 < steps; s2++) {
-        cost_bounds(cum, gcb[s2], gcb[s2 + 1], R, sb.data());
+        spg_split_by_bytes(in, gcb[s2], gcb[s2 + 1], R, sbi);
+        for(int r = 0; r <= R; r++) sb[r] = sbi[r];
         lo[s2] = sb;
         mine += sb[me + 1] - sb[me];
     }

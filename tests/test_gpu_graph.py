@@ -171,8 +171,8 @@ def test_unsupported_options_are_refused_before_the_graph_is_touched(ctx):
     from sparsifyposegraph_b200 import capi
     g = capi.Graph(datasets.path("intel"))
     ne = g.num_edges
-    for topo, lin, alg in ((R.TOPO_CLIQUEY_DENSE, R.LIN_GLOBAL, R.ALG_NFR), (R.TOPO_SUBGRAPH, R.LIN_GLOBAL, R.ALG_GLC),
-                           (R.TOPO_TREE, R.LIN_LOCAL, R.ALG_GLC)):
+    for topo, lin, alg in ((R.TOPO_CLIQUEY_DENSE, R.LIN_GLOBAL, R.ALG_GLC), (R.TOPO_SUBGRAPH, R.LIN_GLOBAL, R.ALG_GLC),
+                           (R.TOPO_TREE, R.LIN_LOCAL, R.ALG_GLC)):   # asserts of TopologyProviderGLC::topology (:107-111)
         with pytest.raises(capi.SpgError):
             g.marginalize(ctx, [5, 7, 9], capi.make_opts(topo, lin), alg)
         assert g.num_edges == ne and g.num_vertices == 943

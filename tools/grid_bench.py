@@ -59,6 +59,10 @@ def main():
     warm = synth.fill_graph(capi.Graph(dim=6), *synth.make_grid_graph(40, 40, dim=6))
     warm.marginalize(ctx, synth.grid_removal_order(40, 40, args.sparsity, args.colour_mod, args.order), opts, alg)
 
+    # page-lock the round staging buffers up front (a round of this workload is ~6 % of the removals, ~0.9 K words of
+    # records and ~0.6 K words of outputs per blanket): cudaHostAlloc of 0.5 GB inside the timed removal costs 0.3-1 s
+    widest_guess = max(4096, len(which) // 12)
+    ctx.reserve_staging(widest_guess * 1000, widest_guess * 700)
     if world > 1:
         distributed.init_comm(ctx, rank, world)  # marginalize() is then collective: every round sharded + gathered (NCCL)
         dist.barrier()
