@@ -169,7 +169,7 @@ int validate_records_mt(const spg_round_in *in, int b0, int b1, int32_t *hdr3, i
     const int n = b1 - b0;
     // the ranks of a sharded round share the host: split its cores between them
     unsigned nthr = std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency() / (unsigned) std::max(1, nranks)), 8u);
-    if(n < 4096 || nthr <= 1) return validate_records(in, b0, b1, hdr3, b0);
+    if(n < 1024 || nthr <= 1) return validate_records(in, b0, b1, hdr3, b0); // (a sharded rank's pipeline step is a few thousand blankets)
     std::vector<int> bad(nthr, -1);
     std::vector<std::thread> pool;
     const int per = (n + (int) nthr - 1) / (int) nthr;

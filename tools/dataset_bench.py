@@ -37,6 +37,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--repeat", type=int, default=5)
     ap.add_argument("--no-oracle", action="store_true")
+    ap.add_argument("--only", default="", help="comma-separated dataset:algorithm:topology filters, e.g. intel:glc:tree")
     args = ap.parse_args()
     import datasets
     from test_gpu_graph import compare_graphs
@@ -46,7 +47,10 @@ def main():
     ctx = capi.Context(0)
     ALG = {"glc": R.ALG_GLC, "nfr": R.ALG_NFR}
     TOPO = {"tree": R.TOPO_TREE, "dense": R.TOPO_DENSE, "subgraph": R.TOPO_SUBGRAPH}
+    only = [f for f in args.only.split(",") if f]
     for cfg, name, alg, topo, sparsity in JOBS:
+        if only and f"{name}:{alg}:{topo}" not in only:
+            continue
         path = datasets.path(name)
         opts = capi.make_opts(TOPO[topo], R.LIN_GLOBAL)
         times, st, g = [], None, None
