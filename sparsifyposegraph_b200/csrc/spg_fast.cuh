@@ -49,9 +49,10 @@ __device__ __forceinline__ double fsum(double v, double *red) {
     }
 }
 
-// Thread group that owns one blanket. G = 8 / 16 / 32: a sub-warp group of G lanes of a one-warp CTA (32 / G
-// blankets per warp side by side, each group with its own control flow, shared-memory slot and masked warp
-// barriers); G = 0: the whole CTA (blockDim.x threads, __syncthreads).
+// Thread group that owns one blanket. G = 8 / 16 / 32: a sub-warp group of G lanes (32 / G blankets per warp side
+// by side, each group with its own control flow, shared-memory slot and masked warp barriers; a CTA is one or
+// several such warps, see the phase barriers of fast_kernel); G = 0: the whole CTA (blockDim.x threads,
+// __syncthreads).
 template <int G>
 struct Grp {
     static __device__ __forceinline__ unsigned mask() {
@@ -61,7 +62,7 @@ struct Grp {
     static __device__ __forceinline__ int tid() { return G ? (int) (threadIdx.x % (G ? G : 1)) : (int) threadIdx.x; }
     static __device__ __forceinline__ int nt() { return G ? G : (int) blockDim.x; }
     static __device__ __forceinline__ int slot() { return G ? (int) (threadIdx.x / (G ? G : 1)) : 0; }
-    static __device__ __forceinline__ int slots() { return G ? 32 / (G ? G : 1) : 1; }
+    static __device__ __forceinline__ int slots() { return G ? (int) blockDim.x / (G ? G : 1) : 1; }
     static __device__ __forceinline__ void sync() {
         if constexpr(G == 0) __syncthreads();
         else __syncwarp(mask());
@@ -403,9 +404,34 @@ __host__ __device__ inline int fast_tiles(int max_nv) {
         }                                                                                            \
     } while(0)
 
-// G: see Grp. MAXW: warps per CTA at most (G = 0), 1 otherwise.
+// Phase barrier of the sub-warp-group kernels (G > 0). The warps of such a CTA work on different blankets and never
+// exchange data, but the kernel is ~13 k instructions of mostly straight-line code against a 32 KB instruction cache:
+// warps that drift apart each stream the whole kernel through the cache on their own (ncu, n = 8: 4.1 of 9.8 stall
+// cycles per issue are `no_instruction`, 40 % of the instruction-cache requests miss). A CTA-wide barrier at every
+// stage boundary keeps the warps of an SM inside the same few KB of code, so that a line is fetched once for all of
+// them. barrier.sync (not .aligned): the groups of a warp may arrive from different places; every thread executes
+// exactly FAST_PHASES barriers per blanket (stages it skips are made up for at the end of the iteration).
+#define SPG_PHASE()                                                                                  \
+    do {                                                                                             \
+        if constexpr(G != 0) {                                                                       \
+            if(phased) {                                                                             \
+                asm volatile("barrier.sync 1;");                                                     \
+                nb++;                                                                                \
+            }                                                                                        \
+        }                                                                                            \
+    } while(0)
+constexpr int FAST_PHASES = 9;
+#define SPG_PHASE_CATCH_UP()                                                                         \
+    do {                                                                                             \
+        if constexpr(G != 0) {                                                                       \
+            if(phased)                                                                               \
+                for(; nb < FAST_PHASES; nb++) asm volatile("barrier.sync 1;");                       \
+        }                                                                                            \
+    } while(0)
+
+// G: see Grp. MAXW: warps per CTA at most (G = 0: one blanket per CTA; G > 0: one blanket per group of G lanes).
 template <int D, int G, int MAXW>
-__global__ void __launch_bounds__(32 * MAXW, MAXW == 1 ? (D == 6 ? 12 : 16) : (MAXW <= 4 ? 3 : (D == 6 ? 1 : 2))) fast_kernel(const KernelParams P) {
+__global__ void __launch_bounds__(32 * MAXW, G ? 1 : (MAXW <= 4 ? 3 : (D == 6 ? 1 : 2))) fast_kernel(const KernelParams P) {
     extern __shared__ __align__(16) double fast_smem[];
     using GS = Grp<G>;
     constexpr int PS = PoseStride<D>::value;
@@ -447,7 +473,14 @@ __global__ void __launch_bounds__(32 * MAXW, MAXW == 1 ? (D == 6 ? 12 : 16) : (M
     double *s_W = smem + pl.off_W;
     const int tstride = pl.ntiles;
 
-    for(int li = blockIdx.x * GS::slots() + GS::slot(); li < P.n_list; li += gridDim.x * GS::slots()) {
+    const bool phased = G != 0 && blockDim.x > 32;
+    for(int base = blockIdx.x * GS::slots(); base < P.n_list; base += gridDim.x * GS::slots()) {
+        int nb = 0; // phase barriers executed in this iteration
+        const int li = base + GS::slot();
+        if(li >= P.n_list) { // no blanket for this group in the last iteration: it only keeps the barrier count
+            SPG_PHASE_CATCH_UP();
+            continue;
+        }
         const int b = P.list ? P.list[li] : li;
         const uint64_t *grec = P.records + P.rec_off[b];
         uint64_t *gout = P.out + P.out_off[b];
@@ -457,6 +490,7 @@ __global__ void __launch_bounds__(32 * MAXW, MAXW == 1 ? (D == 6 ? 12 : 16) : (M
         const int nk = nv - nrem, k = D * nk;
 
         GS::sync(); // the shared buffers of the previous blanket are dead
+        SPG_PHASE(); // 1
         bool refuse = (rdim != D || nv > P.max_nv || ne > P.max_e || rec_words > P.max_rec_words || nrem != 1 || nk < 2 || ne < 1);
         for(int t = tid; t < out_words; t += NT) gout[t] = 0;
         long long t_last = clock64();
@@ -520,6 +554,7 @@ __global__ void __launch_bounds__(32 * MAXW, MAXW == 1 ? (D == 6 ? 12 : 16) : (M
             for(int t = tid; t < DD + 2 * D * NP; t += NT) s_h00[DD + t] = 0.0; // second H00 buffer, H_k0, Y
             if(GS::any(manystar)) refuse = true;
             SPG_FT(0);
+            SPG_PHASE(); // 2
             // ---- S1: assembly. Per chunk of edges (normally all of them): one thread per edge writes J = [Ji Jj] and
             // M = Omega J to shared memory, then every block gathers the edges of its vertex pair in edge order
             // (fixed summation order), and D (k + D) threads gather H_00 and H_k0 from the edges to the removed vertex.
@@ -536,6 +571,7 @@ __global__ void __launch_bounds__(32 * MAXW, MAXW == 1 ? (D == 6 ? 12 : 16) : (M
                     if constexpr(D == 6) se3_from_flat(pm, Z);
                     else se2_from_flat(pm, Z);
                     edge_jacobians<D>(Z, s_pose + PS * vi[0], s_pose + PS * vi[1], J);
+                    if(e == 0) SPG_FT(8);
                     double om[D][D]; // Omega (symmetric), in registers for the 2 D columns of M = Omega J
 #pragma unroll
                     for(int r = 0; r < D; r++)
@@ -555,7 +591,10 @@ __global__ void __launch_bounds__(32 * MAXW, MAXW == 1 ? (D == 6 ? 12 : 16) : (M
                         }
                     }
                 }
+                SPG_FT(9);
                 GS::sync();
+                SPG_FT(10);
+                if(e0 == 0) SPG_PHASE(); // 3
                 if(has_tile) {
                     const int lr = vr + 1, lc = vc + 1; // local vertex indices (the removed vertex is 0)
                     for(int e = 0; e < ce; e++) {
@@ -580,6 +619,7 @@ __global__ void __launch_bounds__(32 * MAXW, MAXW == 1 ? (D == 6 ? 12 : 16) : (M
                         }
                     }
                 }
+                SPG_FT(11);
                 // H_k0: entry (i, p), i in [0, k): the edges between the removed vertex and kept vertex i / D
                 for(int t = tid; t < k * D; t += NT) {
                     const int i = t % k, p = t / k, v = i / D, di = i % D;
@@ -614,6 +654,7 @@ __global__ void __launch_bounds__(32 * MAXW, MAXW == 1 ? (D == 6 ? 12 : 16) : (M
                 GS::sync();
             }
             SPG_FT(1);
+            SPG_PHASE(); // 4
             // ---- S2: Schur complement Lambda_t = H_kk - H_k0 H_00^-1 H_0k (vertex_remover.cpp:443-449) ---------
             // H_00^-1 by D symmetric Gauss-Jordan steps (a pivot <= 0 is LLT's failure)
             if(!refuse) {
@@ -690,6 +731,7 @@ __global__ void __launch_bounds__(32 * MAXW, MAXW == 1 ? (D == 6 ? 12 : 16) : (M
                 }
             }
             SPG_FT(2);
+            SPG_PHASE(); // 5
             // ---- S3: Chow-Liu tree (pseudo_chow_liu.cpp:33-87) --------------------------------------------------
             if(!refuse) {
                 if(nk == 2) {
@@ -706,6 +748,7 @@ __global__ void __launch_bounds__(32 * MAXW, MAXW == 1 ? (D == 6 ? 12 : 16) : (M
                     if(!block_sweep<D, G>(a, s_B, s_P, s_W, s_piv, vr, vc, nk, has_tile, nkmax)) refuse = true;
                     if(!refuse) {
                         SPG_FT(3);
+                        SPG_PHASE(); // 6
                         if(diag) {
                             bool ok;
                             s_logd[vr] = chol_tile<D>(a, s_Lfac + vr * DD, s_Cd + vr * DD, ok);
@@ -733,6 +776,7 @@ __global__ void __launch_bounds__(32 * MAXW, MAXW == 1 ? (D == 6 ? 12 : 16) : (M
                             }
                         }
                         SPG_FT(4);
+                        SPG_PHASE(); // 7
                         // doKruskal (:253-289): same scheme as blanket_kernel — parallel ranking, or the replay of
                         // libstdc++'s heap when two weights are exactly equal
                         int *s_sorted = s_tree + all;
@@ -790,6 +834,7 @@ __global__ void __launch_bounds__(32 * MAXW, MAXW == 1 ? (D == 6 ? 12 : 16) : (M
                 }
             }
             SPG_FT(5);
+            SPG_PHASE(); // 8
             // ---- S4: gauge shortcut + closed form (see blanket_kernel for the argument) --------------------------
             const int kk = k - D;
             double glog = 0;
@@ -823,6 +868,7 @@ __global__ void __launch_bounds__(32 * MAXW, MAXW == 1 ? (D == 6 ? 12 : 16) : (M
                 }
             }
             SPG_FT(6);
+            SPG_PHASE(); // 9
             if(!refuse) {
                 // new-edge Jacobians at zero error (vertex_remover.cpp:466-498), Sigma blocks from G, X_e = (J Sigma J^T)^-1
                 GS::sync();                               // the Lambda_t blocks and the panels are dead
@@ -933,6 +979,7 @@ __global__ void __launch_bounds__(32 * MAXW, MAXW == 1 ? (D == 6 ? 12 : 16) : (M
             SPG_FT(7);
         }
         GS::sync();
+        SPG_PHASE_CATCH_UP(); // stages this blanket skipped
         if(tid == 0) {
             int32_t *oh = reinterpret_cast<int32_t *>(gout);
             if(refuse) {

@@ -1,3 +1,3 @@
 // one translation unit per kernel instantiation (parallel build)
 #include "spg_fast_inst.cuh"
-spg_status spg_launch_fast_3_g16(spg_ctx *ctx, spg::KernelParams &kp) { return launch_fast<3, 16, 1>(ctx, kp); }
+spg_status spg_launch_fast_3_g16(spg_ctx *ctx, spg::KernelParams &kp) { return launch_fast<3, 16, 16>(ctx, kp); }
