@@ -1,3 +1,3 @@
 // one translation unit per kernel instantiation (parallel build)
 #include "spg_fast_inst.cuh"
-spg_status spg_launch_fast_6_g32(spg_ctx *ctx, spg::KernelParams &kp) { return launch_fast<6, 32, 12>(ctx, kp); }
+spg_status spg_launch_fast_6_g32(spg_ctx *ctx, spg::KernelParams &kp) { return launch_fast<6, 32, 8>(ctx, kp); }
