@@ -46,7 +46,11 @@ __device__ __forceinline__ void quat_to_R(const double q[4], double R[9]) {
     R[6] = txz - twy;       R[7] = tyz + twx;       R[8] = 1 - (txx + tyy);
 }
 
-// Eigen::Quaterniond(Matrix3d) followed by g2o normalize (unit, w >= 0)
+// Eigen::Quaterniond(Matrix3d) followed by g2o normalize (unit, w >= 0).
+// STATIC_IDX: the rare branch (trace <= 0) written out per case, so that R and q are only ever indexed with constants
+// and the caller's matrices stay in registers; without it the dynamic indices put them in local memory, which the
+// register-starved multi-warp kernels prefer (fewer spills inside their sweeps). Same arithmetic either way.
+template <bool STATIC_IDX = false>
 __device__ __forceinline__ void R_to_quat(const double R[9], double q[4]) {
     double t = R[0] + R[4] + R[8];
     if(t > 0) {
@@ -56,6 +60,34 @@ __device__ __forceinline__ void R_to_quat(const double R[9], double q[4]) {
         q[0] = (R[7] - R[5]) * t;
         q[1] = (R[2] - R[6]) * t;
         q[2] = (R[3] - R[1]) * t;
+    } else if constexpr(STATIC_IDX) {
+        // largest diagonal entry i, then j = i + 1, k = i + 2 (mod 3); the three cases are written out so that R and q
+        // are only ever indexed with constants (a dynamic index would put the caller's matrices in local memory)
+        int i = 0;
+        if(R[4] > R[0]) i = 1;
+        if(R[8] > (i ? R[4] : R[0])) i = 2;
+        if(i == 0) {
+            t = sqrt(R[0] - R[4] - R[8] + 1.0);
+            q[0] = 0.5 * t;
+            t = 0.5 / t;
+            q[3] = (R[7] - R[5]) * t;
+            q[1] = (R[3] + R[1]) * t;
+            q[2] = (R[6] + R[2]) * t;
+        } else if(i == 1) {
+            t = sqrt(R[4] - R[8] - R[0] + 1.0);
+            q[1] = 0.5 * t;
+            t = 0.5 / t;
+            q[3] = (R[2] - R[6]) * t;
+            q[2] = (R[7] + R[5]) * t;
+            q[0] = (R[1] + R[3]) * t;
+        } else {
+            t = sqrt(R[8] - R[0] - R[4] + 1.0);
+            q[2] = 0.5 * t;
+            t = 0.5 / t;
+            q[3] = (R[3] - R[1]) * t;
+            q[0] = (R[2] + R[6]) * t;
+            q[1] = (R[5] + R[7]) * t;
+        }
     } else {
         int i = 0;
         if(R[4] > R[0]) i = 1;
@@ -84,9 +116,10 @@ __device__ __forceinline__ void se3_from_flat(const double *v, double *p) {
     quat_to_R(q, p);
     p[9] = v[0]; p[10] = v[1]; p[11] = v[2];
 }
+template <bool STATIC_IDX = false>
 __device__ __forceinline__ void se3_to_flat(const double *p, double *v) {
     double q[4];
-    R_to_quat(p, q);
+    R_to_quat<STATIC_IDX>(p, q);
     v[0] = p[9]; v[1] = p[10]; v[2] = p[11];
     v[3] = q[0]; v[4] = q[1]; v[5] = q[2]; v[6] = q[3];
 }
@@ -149,7 +182,7 @@ __device__ __forceinline__ void se2_inverse(const double *a, double *r) {
 //   SE3: analytic derivative of toVectorMQT(Z^-1 (Xi (+) di)^-1 (Xj (+) dj)) — the quantity
 //        g2o::internal::computeEdgeSE3Gradient evaluates (call site src/se3_compatibility.h:25-29);
 //        closed form derived in DESIGN.md §Jacobians.
-template <int D>
+template <int D, bool STATIC_IDX = false>
 __device__ __noinline__ void edge_jacobians(const double *Z, const double *Xi, const double *Xj, double *J) {
     if constexpr(D == 3) {
         const double dtx = Xj[0] - Xi[0], dty = Xj[1] - Xi[1];
@@ -169,8 +202,8 @@ __device__ __noinline__ void edge_jacobians(const double *Z, const double *Xi, c
         se3_compose(T, Xj, B);
         se3_compose(A, B, E);
         double qA[4], qB[4];
-        R_to_quat(A, qA);
-        R_to_quat(B, qB);
+        R_to_quat<STATIC_IDX>(A, qA);
+        R_to_quat<STATIC_IDX>(B, qB);
         const double wA = qA[3], wB = qB[3];
         double wE = wA * wB - (qA[0] * qB[0] + qA[1] * qB[1] + qA[2] * qB[2]);
         double vE[3] = {wA * qB[0] + wB * qA[0] + (qA[1] * qB[2] - qA[2] * qB[1]),

@@ -570,7 +570,7 @@ __global__ void __launch_bounds__(32 * MAXW, G ? 1 : (MAXW <= 4 ? 3 : (D == 6 ? 
                     double Z[PS];
                     if constexpr(D == 6) se3_from_flat(pm, Z);
                     else se2_from_flat(pm, Z);
-                    edge_jacobians<D>(Z, s_pose + PS * vi[0], s_pose + PS * vi[1], J);
+                    edge_jacobians<D, G != 0>(Z, s_pose + PS * vi[0], s_pose + PS * vi[1], J);
                     if(e == 0) SPG_FT(8);
                     double om[D][D]; // Omega (symmetric), in registers for the 2 D columns of M = Omega J
 #pragma unroll
@@ -889,7 +889,7 @@ __global__ void __launch_bounds__(32 * MAXW, G ? 1 : (MAXW <= 4 ? 3 : (D == 6 ? 
                     int32_t *si = reinterpret_cast<int32_t *>(sl);
                     si[0] = ea; si[1] = eb;
                     double *sm = reinterpret_cast<double *>(sl + 1);
-                    if constexpr(D == 6) se3_to_flat(Z, sm);
+                    if constexpr(D == 6) se3_to_flat<G != 0>(Z, sm);
                     else { sm[0] = Z[0]; sm[1] = Z[1]; sm[2] = Z[2]; }
                 }
                 // Sigma_e = [[G_aa G_ab] [G_ba G_bb]] scattered from the registers (G = -a; zero rows / columns for the
