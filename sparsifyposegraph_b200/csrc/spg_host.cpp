@@ -528,6 +528,12 @@ bool VertexRemover::buildUnit(int root, int listIndex, const std::set<int> &toRe
         } else {
             mb.emplace_back(root, -1);
         }
+        // the second walk reads the adjacency arrays of every blanket vertex (heap blocks): start fetching them now
+        for(const auto &pr : mb)
+            if(pr.second >= 0) {
+                __builtin_prefetch(V[pr.second].edges.data());
+                __builtin_prefetch(V[pr.second].peer.data());
+            }
         std::sort(mb.begin(), mb.end());
         u.removed.push_back(root);
         for(const auto &pr : mb)
@@ -543,7 +549,10 @@ bool VertexRemover::buildUnit(int root, int listIndex, const std::set<int> &toRe
                     if(!(p & 1)) continue; // met once per endpoint: taken at its first one
                     const int yi = p >> 1;
                     if(mark[yi] != token) continue;
-                    if(_opts.includeIntraClique || xi == ri || yi == ri) keyed.emplace_back(E[ei].uidKey(), ei);
+                    if(_opts.includeIntraClique || xi == ri || yi == ri) {
+                        __builtin_prefetch(&E[ei]);
+                        keyed.emplace_back(~0ULL, ei); // key filled in below, once the edge has arrived
+                    }
                     continue;
                 }
                 const GraphEdge &e = E[ei];
@@ -558,6 +567,8 @@ bool VertexRemover::buildUnit(int root, int listIndex, const std::set<int> &toRe
                 if(is_markov && (_opts.includeIntraClique || found_hub)) keyed.emplace_back(e.uidKey(), ei);
             }
         }
+        for(auto &ke : keyed)
+            if(ke.first == ~0ULL) ke.first = E[ke.second].uidKey();
         std::sort(keyed.begin(), keyed.end());
         keyed.erase(std::unique(keyed.begin(), keyed.end()), keyed.end());
         for(const auto &ke : keyed) u.edges.push_back(ke.second);
@@ -711,7 +722,19 @@ bool VertexRemover::packUnit(const RemovalUnit &u, uint64_t *rec, int64_t words,
 
     int32_t *etab = reinterpret_cast<int32_t *>(rec + spgr_edgetab_off(dim, nv));
     int64_t eoff = spgr_record_fixed_words(dim, nv, ne);
+    // an edge costs two dependent cache misses (the edge, then its payload block on the heap): fetch the edges four
+    // ahead and the payloads two ahead of the copy
+    for(int i = 0; i < ne && i < 4; i++) __builtin_prefetch(&_graph->edges[u.edges[i]]);
+    for(int i = 0; i < ne && i < 2; i++) {
+        const char *pp = reinterpret_cast<const char *>(_graph->edges[u.edges[i]].meas());
+        for(int l = 0; l < 6; l++) __builtin_prefetch(pp + 64 * l);
+    }
     for(int i = 0; i < ne; i++) {
+        if(i + 4 < ne) __builtin_prefetch(&_graph->edges[u.edges[i + 4]]);
+        if(i + 2 < ne) {
+            const char *pp = reinterpret_cast<const char *>(_graph->edges[u.edges[i + 2]].meas());
+            for(int l = 0; l < 6; l++) __builtin_prefetch(pp + 64 * l);
+        }
         const GraphEdge &e = _graph->edges[u.edges[i]];
         etab[i] = (int32_t) eoff;
         uint64_t *ew = rec + eoff;
@@ -1090,6 +1113,12 @@ spg_status VertexRemover::planRound(bool packNow) {
         parallelFor(todo.size(), 512, [&](size_t b0, size_t b1) {
             for(size_t q = b0; q < b1; q++) {
                 const int i = todo[q];
+                if(q + 2 < b1 && _rootIdx[todo[q + 2]] >= 0) __builtin_prefetch(&_graph->verts[_rootIdx[todo[q + 2]]]);
+                if(q + 1 < b1 && _rootIdx[todo[q + 1]] >= 0) {
+                    const GraphVertex &nr = _graph->verts[_rootIdx[todo[q + 1]]];
+                    __builtin_prefetch(nr.edges.data());
+                    __builtin_prefetch(nr.peer.data());
+                }
                 if(!buildUnit(toRemove[i], i, _toRemoveSet, _unitCache[i])) {
                     int expect = -1;
                     bad.compare_exchange_strong(expect, i);
@@ -1117,7 +1146,19 @@ spg_status VertexRemover::planRound(bool packNow) {
         std::vector<int> hit, comps;
         std::vector<std::pair<int, int>> shared;
         _leftover.clear();
-        for(int i : win) {
+        for(size_t wq = 0; wq < win.size(); wq++) {
+            const int i = win[wq];
+            // the loop is a chain of dependent cache misses (unit -> per-vertex touch heads): fetch the unit three entries
+            // ahead and the touch heads of the next one
+            if(wq + 3 < win.size()) { // (the index lists are stored inside the unit: four cache lines)
+                const char *pu = reinterpret_cast<const char *>(&_unitCache[win[wq + 3]]);
+                for(size_t l = 0; l < sizeof(RemovalUnit); l += 64) __builtin_prefetch(pu + l);
+            }
+            if(wq + 1 < win.size()) {
+                const RemovalUnit &n1 = _unitCache[win[wq + 1]];
+                for(int xi : n1.ridx) { __builtin_prefetch(&_touchHead[xi]); __builtin_prefetch(&_removedBy[xi]); }
+                for(int xi : n1.kidx) { __builtin_prefetch(&_touchHead[xi]); __builtin_prefetch(&_removedBy[xi]); }
+            }
             const RemovalUnit &u = _unitCache[i];
             hit.clear();
             shared.clear();
@@ -1253,12 +1294,19 @@ bool VertexRemover::packRange(size_t q0, size_t q1) {
     uint64_t *rec = _round.rec;
     std::atomic<int> badPack(-1);
     parallelFor(q1 - q0, 1024, [&](size_t b0, size_t b1) {
-        for(size_t q = q0 + b0; q < q0 + b1; q++)
+        for(size_t q = q0 + b0; q < q0 + b1; q++) {
+            if(q + 1 < q0 + b1) { // the next unit's vertices and first edges, while this one is copied
+                const RemovalUnit &nx = _unitCache[sel[q + 1]];
+                for(int xi : nx.ridx) __builtin_prefetch(&_graph->verts[xi]);
+                for(int xi : nx.kidx) __builtin_prefetch(&_graph->verts[xi]);
+                for(size_t i = 0; i < nx.edges.size() && i < 4; i++) __builtin_prefetch(&_graph->edges[nx.edges[i]]);
+            }
             if(!packUnit(_unitCache[sel[q]], rec + recOff[q], recOff[q + 1] - recOff[q],
                          (q < _round.linPoses.size() && !_round.linPoses[q].empty()) ? _round.linPoses[q].data() : nullptr)) {
                 int expect = -1;
                 badPack.compare_exchange_strong(expect, (int) q);
             }
+        }
     });
     if(badPack.load() >= 0) {
         error = "Local linearisation point on a non-star blanket needs the subgraph optimiser (not on this path)";
@@ -1278,45 +1326,64 @@ void VertexRemover::applyRound(const uint64_t *out) {
     std::vector<GraphVertex> &V = _graph->verts;
     ChunkedVector<GraphEdge> &E = _graph->edges;
 
-    // ---- pass 1 (sequential, headers only): status bookkeeping, staleness stamps, edge indices of the substitutes --
+    // ---- pass 1 (headers only): staleness stamps and the number of substitutes per unit by the host threads, then
+    // the sequential part — status bookkeeping in list order and the edge indices of the substitutes (a prefix sum) ----
     std::vector<int> base(ns + 1, 0); // new edges of unit ui go to E[e0 + base[ui] ...); failed units add none
     std::vector<char> okUnit(ns, 0);
     int removedEdges = 0, removedVerts = 0;
+    std::atomic<int> droppedA(0);
+    parallelFor(ns, 2048, [&](size_t q0, size_t q1) {
+        int dropped = 0;
+        for(size_t ui = q0; ui < q1; ui++) {
+            if(ui + 2 < q1) {
+                __builtin_prefetch(out + _round.outOff[ui + 2]);
+                __builtin_prefetch(&_unitCache[sel[ui + 2]]);
+            }
+            const RemovalUnit &u = _unitCache[sel[ui]];
+            const uint64_t *o = out + _round.outOff[ui];
+            const int32_t *oh = reinterpret_cast<const int32_t *>(o);
+            const int bstatus = oh[0], nnew = oh[1];
+            _done[u.listIndex] = 1; // (one byte per list entry, every entry belongs to one unit)
+            if(bstatus != SPG_BLANKET_OK) continue;
+            okUnit[ui] = 1;
+            // cached blankets containing these vertices are stale; two units of a round may share a kept vertex and then
+            // store the same value
+            for(int xi : u.ridx) __atomic_store_n(&_stamp[xi], _planNo, __ATOMIC_RELAXED);
+            for(int xi : u.kidx) __atomic_store_n(&_stamp[xi], _planNo, __ATOMIC_RELAXED);
+            int cnt = nnew;
+            if(algorithm == SPG_ALG_GLC) { // getEdge returned NULL for rank-0 factors (src/topology_provider_glc.cpp:85-89)
+                const int64_t slot = spgr_out_slot_words(dim, algorithm, _opts.topology, (int) u.kept.size());
+                cnt = 0;
+                for(int e = 0; e < nnew; e++)
+                    cnt += reinterpret_cast<const int32_t *>(o + SPG_OUT_HEADER_WORDS + (int64_t) e * slot)[1] != 0;
+                dropped += nnew - cnt;
+            }
+            base[ui + 1] = cnt;
+        }
+        droppedA += dropped;
+    });
+    stats.n_dropped_edges += droppedA.load();
+    _remaining -= (int) ns;
     for(size_t ui = 0; ui < ns; ui++) {
-        const RemovalUnit &u = _unitCache[sel[ui]];
-        const uint64_t *o = out + _round.outOff[ui];
-        const int32_t *oh = reinterpret_cast<const int32_t *>(o);
-        const int bstatus = oh[0], nnew = oh[1];
-        base[ui + 1] = base[ui];
-        _done[u.listIndex] = 1;
-        _remaining--;
-        if(bstatus != SPG_BLANKET_OK) {
+        if(!okUnit[ui]) {
             // The reference asserts / exits here. The blanket is left in the graph untouched (vertex, edges, no
             // substitutes); the units of a round commute, so the others are unaffected. The call reports
             // SPG_ERR_BLANKET_FAILED with the first failing list index.
+            const RemovalUnit &u = _unitCache[sel[ui]];
             if(stats.n_failed++ == 0) {
                 stats.first_failed_index = u.listIndex;
-                stats.first_failed_status = bstatus;
+                stats.first_failed_status = reinterpret_cast<const int32_t *>(out + _round.outOff[ui])[0];
             }
             if(!_toRemoveSet.empty())
                 for(int id : u.removed) _toRemoveSet.erase(id);
+            base[ui + 1] = base[ui];
             continue;
         }
-        okUnit[ui] = 1;
-        for(int xi : u.ridx) _stamp[xi] = _planNo; // cached blankets containing these are stale
-        for(int xi : u.kidx) _stamp[xi] = _planNo;
-        int cnt = nnew;
-        if(algorithm == SPG_ALG_GLC) { // getEdge returned NULL for rank-0 factors (src/topology_provider_glc.cpp:85-89)
-            const int64_t slot = spgr_out_slot_words(dim, algorithm, _opts.topology, (int) u.kept.size());
-            cnt = 0;
-            for(int e = 0; e < nnew; e++)
-                cnt += reinterpret_cast<const int32_t *>(o + SPG_OUT_HEADER_WORDS + (int64_t) e * slot)[1] != 0;
-            stats.n_dropped_edges += nnew - cnt;
-        }
-        base[ui + 1] += cnt;
+        base[ui + 1] += base[ui];
         stats.n_blankets++;
-        stats.n_applied += (int) u.removed.size();
-        removedVerts += (int) u.removed.size();
+        const int nr = !_extended ? 1 : (int) _unitCache[sel[ui]].removed.size(); // (single-removal topologies: no cache miss here)
+        stats.n_applied += nr;
+        removedVerts += nr;
     }
     const int e0 = (int) E.size();
     E.resize((size_t) e0 + base[ns]);
@@ -1333,6 +1400,18 @@ void VertexRemover::applyRound(const uint64_t *out) {
         std::vector<int> spare;
         std::vector<std::vector<double>> mine;
         for(size_t ui = q0; ui < q1; ui++) {
+            // dependent cache misses again (unit -> edge list -> edges -> payload blocks): three, two and one units ahead
+            if(ui + 3 < q1) {
+                const char *pu = reinterpret_cast<const char *>(&_unitCache[sel[ui + 3]]);
+                for(size_t l = 0; l < sizeof(RemovalUnit); l += 64) __builtin_prefetch(pu + l);
+            }
+            if(ui + 2 < q1) __builtin_prefetch(_unitCache[sel[ui + 2]].edges.data());
+            if(ui + 1 < q1) {
+                const RemovalUnit &nx = _unitCache[sel[ui + 1]];
+                for(int ei : nx.edges) __builtin_prefetch(&E[ei]);
+                for(int xi : nx.ridx) __builtin_prefetch(&V[xi]);
+                __builtin_prefetch(out + _round.outOff[ui + 1]);
+            }
             if(!okUnit[ui]) continue;
             const RemovalUnit &u = _unitCache[sel[ui]];
             spare.clear();
@@ -1448,6 +1527,17 @@ void VertexRemover::applyRound(const uint64_t *out) {
     if(_vlock.size() < V.size()) _vlock = std::vector<std::atomic<unsigned char>>(V.size() + V.size() / 4 + 64);
     parallelFor(ns, 256, [&](size_t q0, size_t q1) {
         for(size_t ui = q0; ui < q1; ui++) {
+            if(ui + 3 < q1) {
+                const char *pu = reinterpret_cast<const char *>(&_unitCache[sel[ui + 3]]);
+                for(size_t l = 0; l < sizeof(RemovalUnit); l += 64) __builtin_prefetch(pu + l);
+            }
+            if(ui + 2 < q1)
+                for(int xi : _unitCache[sel[ui + 2]].kidx) __builtin_prefetch(&V[xi]);
+            if(ui + 1 < q1)
+                for(int xi : _unitCache[sel[ui + 1]].kidx) { // (a racing writer may be resizing these: only a hint)
+                    __builtin_prefetch(V[xi].edges.data());
+                    __builtin_prefetch(V[xi].peer.data());
+                }
             if(!okUnit[ui]) continue;
             const RemovalUnit &u = _unitCache[sel[ui]];
             const int nb0 = e0 + base[ui], nb1 = e0 + base[ui + 1];
@@ -1455,6 +1545,8 @@ void VertexRemover::applyRound(const uint64_t *out) {
                 std::atomic<unsigned char> &lk = _vlock[xi];
                 while(lk.exchange(1, std::memory_order_acquire)) { /* spin: held for a few dozen instructions */ }
                 GraphVertex &gv = V[xi];
+                // the liveness flags read below are one edge (cache miss) per adjacency entry: all of them in flight first
+                for(int ei : gv.edges) __builtin_prefetch(&E[ei].alive);
                 size_t w = 0;
                 for(size_t k = 0; k < gv.edges.size(); k++)
                     if(E[gv.edges[k]].alive) { gv.edges[w] = gv.edges[k]; gv.peer[w] = gv.peer[k]; w++; }
