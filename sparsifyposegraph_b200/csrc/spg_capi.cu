@@ -8,6 +8,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <chrono>
 #include <thread>
 #include <vector>
 
@@ -216,6 +217,11 @@ spg_status spg_round_prepare(spg_ctx *ctx, const spg_round_in *in, spg_round_out
         SPG_CUDA(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
         SPG_CUDA(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
     }
+    for(int k = 0; k < spg_ctx::N_SIDE; k++)
+        if(!ctx->s_side[k]) {
+            SPG_CUDA(cudaStreamCreateWithFlags(&ctx->s_side[k], cudaStreamNonBlocking));
+            SPG_CUDA(cudaEventCreateWithFlags(&ctx->ev_side[k], cudaEventDisableTiming));
+        }
     while((int) ctx->ev_pool.size() < 2 * nchunks) {
         cudaEvent_t e;
         SPG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -256,6 +262,21 @@ spg_status spg_round_prepare(spg_ctx *ctx, const spg_round_in *in, spg_round_out
     return SPG_OK;
 }
 
+namespace {
+// SPG_HOST_PROF=1: where the host time of the round calls goes (printed at exit)
+struct CapiProf {
+    double prepare = 0, fill = 0, validate = 0, bucket = 0, enqueue = 0, finish = 0;
+    long long rounds = 0, chunks = 0;
+    bool on = getenv("SPG_HOST_PROF") != nullptr;
+    ~CapiProf() {
+        if(on && rounds)
+            fprintf(stderr, "[spg capi] %lld round calls, %lld chunks: prepare %.3f s, fill callback %.3f s, validate %.3f s, bucket %.3f s, "
+                            "copies + launches enqueued %.3f s, final wait %.3f s\n", rounds, chunks, prepare, fill, validate, bucket, enqueue, finish);
+    }
+} g_cprof;
+inline double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+} // namespace
+
 // blankets [b0, b1) of the round: validate, bucket by size, H2D on s_in (event 2c), one fused kernel per bucket on
 // the context stream (event 2c+1 behind the last one)
 spg_status spg_round_enqueue_chunk(spg_ctx *ctx, const spg_round_in *in, spg::RoundRun &run, int b0, int b1, int c) {
@@ -263,6 +284,8 @@ spg_status spg_round_enqueue_chunk(spg_ctx *ctx, const spg_round_in *in, spg::Ro
     constexpr int NBK = sizeof(bounds6) / sizeof(int);
     const int dim = in->dim;
     std::vector<int32_t> hdr3; // (n_vert, n_edges, rec_words) of every blanket of the chunk
+    double tp = now_s();
+    g_cprof.chunks++;
     // ---- validate the chunk's records before anything of it is launched (runs while the GPU works on c-1)
     {
         hdr3.resize(3 * (size_t) (b1 - b0));
@@ -274,6 +297,7 @@ spg_status spg_round_enqueue_chunk(spg_ctx *ctx, const spg_round_in *in, spg::Ro
             return SPG_ERR_INVALID;
         }
     }
+    g_cprof.validate += now_s() - tp; tp = now_s();
     // ---- bucket this chunk by blanket size -----------------------------------------------------
     std::vector<Bucket> buckets(NBK);
     for(int b = b0; b < b1; b++) {
@@ -291,6 +315,7 @@ spg_status spg_round_enqueue_chunk(spg_ctx *ctx, const spg_round_in *in, spg::Ro
         std::copy(B.list.begin(), B.list.end(), run.flat.begin() + pos);
         pos += B.list.size();
     }
+    g_cprof.bucket += now_s() - tp; tp = now_s();
     // ---- H2D of the chunk -----------------------------------------------------------------------
     const int64_t r0 = in->rec_off[b0], r1 = in->rec_off[b1];
     SPG_CUDA(cudaMemcpyAsync(reinterpret_cast<uint64_t *>(ctx->d_rec.p) + r0, in->records + r0, (size_t) (r1 - r0) * 8,
@@ -304,9 +329,32 @@ spg_status spg_round_enqueue_chunk(spg_ctx *ctx, const spg_round_in *in, spg::Ro
         run.first = false;
     }
     // ---- kernels ----------------------------------------------------------------------------------
+    // NFR tree rounds of on-chip blankets use no per-context workspace: their buckets go round-robin to the side
+    // streams and run side by side (a graph-level round holds blankets of many sizes, and a bucket of a few hundred
+    // blankets fills a fraction of the SMs); everything else runs bucket after bucket on the context stream
+    int n_buckets = 0;
+    for(auto &B : buckets) n_buckets += !B.list.empty();
+    static const bool no_side = getenv("SPG_NO_SIDE_STREAMS") != nullptr;
+    const bool side = !no_side && n_buckets > 1 && in->algorithm == SPG_ALG_NFR && in->opts.topology == SPG_TOPO_TREE &&
+                      !ctx->profiling && ctx->s_side[0];
+    cudaStream_t const main_stream = ctx->stream;
+    bool used_side[spg_ctx::N_SIDE] = {};
+    int next_side = 0;
     size_t list_pos = (size_t) b0;
     for(auto &B : buckets) {
         if(B.list.empty()) continue;
+        const bool on_side = side && B.max_nv <= 16; // (far below the spill limit: no global workspace)
+        if(on_side) {
+            const int k = next_side++ % spg_ctx::N_SIDE;
+            if(!used_side[k]) {
+                // behind the copy-in of this chunk and behind everything already queued on the context stream
+                SPG_CUDA(cudaStreamWaitEvent(ctx->s_side[k], ctx->ev_pool[2 * c], 0));
+                SPG_CUDA(cudaEventRecord(ctx->ev_side[k], main_stream));
+                SPG_CUDA(cudaStreamWaitEvent(ctx->s_side[k], ctx->ev_side[k], 0));
+                used_side[k] = true;
+            }
+            ctx->stream = ctx->s_side[k];
+        }
         spg::KernelParams kp{};
         kp.algorithm = in->algorithm;
         kp.topology = in->opts.topology;
@@ -329,12 +377,19 @@ spg_status spg_round_enqueue_chunk(spg_ctx *ctx, const spg_round_in *in, spg::Ro
         kp.max_e = B.max_e;
         kp.max_rec_words = (B.max_rec + 1) & ~1;
         spg_status st = (dim == 6) ? launch_dim<6>(ctx, kp) : launch_dim<3>(ctx, kp);
+        ctx->stream = main_stream;
         if(st != SPG_OK) {
             cudaDeviceSynchronize();
             return st;
         }
     }
+    for(int k = 0; k < spg_ctx::N_SIDE; k++) // join: the chunk is done when every side stream is
+        if(used_side[k]) {
+            SPG_CUDA(cudaEventRecord(ctx->ev_side[k], ctx->s_side[k]));
+            SPG_CUDA(cudaStreamWaitEvent(main_stream, ctx->ev_side[k], 0));
+        }
     SPG_CUDA(cudaEventRecord(ctx->ev_pool[2 * c + 1], ctx->stream));
+    g_cprof.enqueue += now_s() - tp;
     return SPG_OK;
 }
 
@@ -430,6 +485,10 @@ void spg_destroy(spg_ctx *ctx) {
     if(ctx->ev0) cudaEventDestroy(ctx->ev0);
     if(ctx->ev1) cudaEventDestroy(ctx->ev1);
     for(cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+    for(int k = 0; k < spg_ctx::N_SIDE; k++) {
+        if(ctx->s_side[k]) cudaStreamDestroy(ctx->s_side[k]);
+        if(ctx->ev_side[k]) cudaEventDestroy(ctx->ev_side[k]);
+    }
     if(ctx->s_in) cudaStreamDestroy(ctx->s_in);
     if(ctx->s_out) cudaStreamDestroy(ctx->s_out);
     if(ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -600,13 +659,19 @@ spg_status spg_remove_round_streamed(spg_ctx *ctx, const spg_round_in *in, spg_r
     spg_split_by_bytes(in, 0, nb, nchunks, cb);
 
     spg::RoundRun run;
+    double tp = now_s();
+    g_cprof.rounds++;
     spg_status st = spg_round_prepare(ctx, in, out, nchunks, run);
     if(st != SPG_OK) return st;
+    g_cprof.prepare += now_s() - tp;
     for(int c = 0; c < nchunks; c++) {
         const int b0 = cb[c], b1 = cb[c + 1];
         if(b1 <= b0) continue;
         // streamed rounds: the caller writes the records of this chunk now, while the GPU works on the previous ones
-        if(fill && fill(user, b0, b1) != 0) {
+        tp = now_s();
+        const int frc = fill ? fill(user, b0, b1) : 0;
+        g_cprof.fill += now_s() - tp;
+        if(frc != 0) {
             cudaDeviceSynchronize();
             set_err("the record producer of spg_remove_round_streamed failed on blankets [" + std::to_string(b0) + ", " +
                     std::to_string(b1) + ")");
@@ -620,7 +685,10 @@ spg_status spg_remove_round_streamed(spg_ctx *ctx, const spg_round_in *in, spg_r
         SPG_CUDA(cudaMemcpyAsync(out->out + o0, reinterpret_cast<uint64_t *>(ctx->d_out.p) + o0, (size_t) (o1 - o0) * 8,
                                  cudaMemcpyDeviceToHost, ctx->s_out));
     }
-    return spg_round_finish(ctx, out, run);
+    tp = now_s();
+    st = spg_round_finish(ctx, out, run);
+    g_cprof.finish += now_s() - tp;
+    return st;
 }
 
 } // extern "C"

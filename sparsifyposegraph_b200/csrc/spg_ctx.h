@@ -47,6 +47,10 @@ struct spg_ctx {
     cudaStream_t stream = nullptr;               // kernels (exposed by spg_stream)
     cudaStream_t s_in = nullptr, s_out = nullptr; // H2D / D2H of the chunked host-buffer path
     std::vector<cudaEvent_t> ev_pool;            // two per chunk (copy-in done, kernels done)
+    // size buckets of one chunk run side by side (a bucket of a few hundred blankets fills a fraction of the SMs)
+    static constexpr int N_SIDE = 4;
+    cudaStream_t s_side[N_SIDE] = {};
+    cudaEvent_t ev_side[N_SIDE] = {};
     int64_t chunk_bytes = (int64_t) 48 << 20;    // records + outputs per chunk of spg_remove_round (env SPG_CHUNK_BYTES)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int64_t launches = 0;

@@ -947,7 +947,11 @@ std::vector<int> VertexRemover::remove(const std::vector<int> &toRemove, spg_sta
                 }
             } fill{this};
             _packFailed = false;
+            // the substitute edges of the round need fresh blocks of the edge store (page faults, constructors): a helper
+            // thread prepares them while the GPU works
+            std::thread grow([this] { _graph->edges.reserve(_graph->edges.size() + (size_t) _round.maxNewEdges); });
             st = spg_remove_round_streamed(_ctx, &rin, &rout, &Fill::fn, &fill);
+            grow.join();
             if(_packFailed) { // `error` names the reason (packRange); nothing of this round was applied
                 st = SPG_ERR_UNSUPPORTED;
                 break;
@@ -1245,6 +1249,7 @@ spg_status VertexRemover::planRound(bool packNow) {
         }
     });
     unsigned char allMask = 0;
+    int64_t maxNew = 0; // substitute edges of the round at most
     int maxv = stats.max_blanket_vertices;
     TopologyProvider *tp = nullptr;
     for(size_t q = 0; q < ns; q++) {
@@ -1262,9 +1267,11 @@ spg_status VertexRemover::planRound(bool packNow) {
         const RemovalUnit &u = _unitCache[sel[q]];
         maxv = std::max<int>(maxv, (int) (u.removed.size() + u.kept.size()));
         outOff[q + 1] = outOff[q] + spgr_out_record_words(dim, t->algorithm(), _opts.topology, _opts.chordRatio, (int) u.kept.size());
+        maxNew += spgr_out_edge_count(t->algorithm(), _opts.topology, _opts.chordRatio, (int) u.kept.size());
         recOff[q + 1] += recOff[q];
     }
     stats.max_blanket_vertices = maxv;
+    _round.maxNewEdges = maxNew;
     uint64_t *rec = _ctx ? spg_ctx_pinned(_ctx, 0, (size_t) recOff[ns]) : nullptr; // the context keeps its staging buffers
     if(!rec) rec = _round.records.reserve((size_t) recOff[ns]);
     _round.rec = rec;

@@ -20,6 +20,7 @@
 #include <set>
 #include <string>
 #include <unordered_map>
+#include <memory>
 #include <vector>
 
 #include "../../include/spg_capi.h"
@@ -103,20 +104,28 @@ struct GraphEdge {
     unsigned long long uidKey() const { return ((unsigned long long) (unsigned) (uidMajor + 1) << 32) | (unsigned) uidMinor; }
 };
 // edge store: fixed-size blocks, so growing never moves an edge (a std::vector of ~150-byte edges re-touches gigabytes on
-// every doubling of a million-pose graph) and references stay valid while other threads append
+// every doubling of a million-pose graph) and references stay valid while other threads append. The table of block
+// pointers has a fixed capacity too, so reserve() may run on a helper thread (the remover grows the store for the
+// substitute edges of a round while the GPU works on it) next to threads that read existing edges.
 template <class T, int LOG2 = 14>
 class ChunkedVector {
 public:
-    ChunkedVector() {}
+    ChunkedVector() : _blocks(new T *[MAXB]()) {}
     ChunkedVector(const ChunkedVector &) = delete;
     ChunkedVector &operator=(const ChunkedVector &) = delete;
-    ~ChunkedVector() { for(T *b : _blocks) delete[] b; }
+    ~ChunkedVector() { for(size_t b = 0; b < _nb; b++) delete[] _blocks[b]; }
     size_t size() const { return _n; }
     T &operator[](size_t i) { return _blocks[i >> LOG2][i & MASK]; }
     const T &operator[](size_t i) const { return _blocks[i >> LOG2][i & MASK]; }
     T &back() { return (*this)[_n - 1]; }
-    void resize(size_t n) { // grow only (default-constructed elements)
-        while(_blocks.size() << LOG2 < n) _blocks.push_back(new T[(size_t) 1 << LOG2]);
+    void reserve(size_t n) { // blocks (default-constructed elements) for n elements; size() unchanged
+        while((_nb << LOG2) < n && _nb < MAXB) {
+            _blocks[_nb] = new T[(size_t) 1 << LOG2];
+            _nb++;
+        }
+    }
+    void resize(size_t n) { // grow only
+        reserve(n);
         if(n > _n) _n = n;
     }
     void push_back(T &&x) {
@@ -125,8 +134,9 @@ public:
     }
 private:
     static constexpr size_t MASK = ((size_t) 1 << LOG2) - 1;
-    std::vector<T *> _blocks;
-    size_t _n = 0;
+    static constexpr size_t MAXB = (size_t) 1 << 17; // 2^31 edges: the edge indices are ints
+    std::unique_ptr<T *[]> _blocks;
+    size_t _nb = 0, _n = 0;
 };
 
 struct GraphVertex {
@@ -289,6 +299,7 @@ public:
         std::vector<int64_t> recOff, outOff;
         int algorithm = SPG_ALG_NFR;
         bool poseOnly = false;       // every blanket edge of the round is a POSE edge (SPG_OPT_POSE_EDGES_ONLY)
+        int64_t maxNewEdges = 0;     // substitute edges the round can add at most (the edge store is grown ahead)
     };
     spg_status beginRemoval(const std::vector<int> &toRemove);
     spg_status planRound(bool packNow = true);
