@@ -230,3 +230,58 @@ def test_se2_mid_sized_blankets_all_variants(ctx, oracle, n, flags):
             if alg == R.ALG_NFR:
                 for eg, er in zip(g["edges"], r["edges"]):
                     assert rel(eg["info"], er["info"]) <= 1e-9
+
+
+def test_wide_round_with_refusals_through_the_phase_barriers(ctx, oracle, monkeypatch):
+    """fast_kernel's sub-warp-group variants run a wide round as CTAs of several warps with a CTA-wide barrier at every
+    stage boundary (spg_fast.cuh, SPG_PHASE); every thread must execute the same number of barriers per blanket
+    whatever the blanket does. A 2999-blanket round (ragged tail: not a multiple of the blankets per CTA) mixes regular
+    5-vertex blankets with the three ways of leaving the kernel early — refused at the door (two removed vertices),
+    refused in S0 (five parallel edges to one neighbour) and refused after both sweeps (weak blanket: the gauge
+    shortcut's guard) — which blanket_kernel then re-runs. The result must equal the oracle and, bit for bit, the
+    one-warp-per-CTA launch of the same binary (SPG_FAST_WPC=1: no barriers)."""
+    from sparsifyposegraph_b200 import capi
+    rng = np.random.default_rng(77)
+    recs, nks = [], []
+    for b in range(2999):
+        if b % 11 == 5:     # two removed vertices, three kept
+            poses = synth.random_poses(rng, (5,), 6)
+            edges = [se3_edge(rng, poses, 0, 1)] + [se3_edge(rng, poses, j % 2, 2 + j) for j in range(3)]
+            edges += [se3_edge(rng, poses, 2, 3), se3_edge(rng, poses, 3, 4)]
+            recs.append(R.pack_blanket(6, list(range(100, 105)), poses, edges, n_removed=2))
+            nks.append(3)
+            continue
+        poses = synth.random_poses(rng, (5,), 6)
+        if b % 13 == 7:     # five parallel edges between the removed vertex and one neighbour
+            edges = [se3_edge(rng, poses, 0, 1) for _ in range(5)] + [se3_edge(rng, poses, 0, i) for i in range(2, 5)]
+            edges += [se3_edge(rng, poses, 1, 2), se3_edge(rng, poses, 3, 4)]
+        elif b % 7 == 3:    # weak blanket (see test_weak_blanket_takes_choose_dimensions_branch)
+            edges = [se3_edge(rng, poses, 0, i) for i in range(1, 4)]
+            edges.append(se3_edge(rng, poses, 0, 4, info=3e-6 * np.eye(6)))
+            edges.append(se3_edge(rng, poses, 1, 2))
+        else:               # star + ring
+            edges = [se3_edge(rng, poses, 0, i) for i in range(1, 5)]
+            edges += [se3_edge(rng, poses, i, i % 4 + 1) for i in range(1, 5)]
+        recs.append(R.pack_blanket(6, [9, 2, 4, 6, 8], poses, edges))
+        nks.append(4)
+    records, rec_off = R.concat_records(recs)
+    out_off = R.out_offsets(6, R.ALG_NFR, R.TOPO_TREE, 1.0, nks)
+    opts = capi.make_opts(R.TOPO_TREE, 1)
+    phased = ctx.remove_round(6, R.ALG_NFR, opts, records, rec_off, out_off)[0].copy()
+    retried = ctx.last_retry_count
+    assert retried >= 2999 // 11 + 2999 // 13      # the refused blankets went through the device-side retry list
+    monkeypatch.setenv("SPG_FAST_WPC", "1")
+    onewarp = ctx.remove_round(6, R.ALG_NFR, opts, records, rec_off, out_off)[0].copy()
+    monkeypatch.delenv("SPG_FAST_WPC")
+    assert ctx.last_retry_count == retried
+    assert np.array_equal(phased, onewarp)
+    ro = oracle.remove_round(6, R.ALG_NFR, oracle.make_opts(R.TOPO_TREE, 1), records, rec_off, out_off, 0)[0]
+    worst = 0.0
+    for b, nk in enumerate(nks):
+        g = R.parse_out(phased, out_off, b, 6, R.ALG_NFR, R.TOPO_TREE, nk)
+        r = R.parse_out(ro, out_off, b, 6, R.ALG_NFR, R.TOPO_TREE, nk)
+        assert g["status"] == r["status"] == 0, (b, g["status"], r["status"])
+        assert [e["v"] for e in g["edges"]] == [e["v"] for e in r["edges"]], b
+        for eg, er in zip(g["edges"], r["edges"]):
+            worst = max(worst, rel(eg["info"], er["info"]))
+    assert worst <= 1e-9, worst
