@@ -220,6 +220,19 @@ typedef int32_t (*spg_fill_fn)(void *user, int32_t first_blanket, int32_t end_bl
 spg_status spg_remove_round_streamed(spg_ctx *ctx, const spg_round_in *in, spg_round_out *out, spg_fill_fn fill, void *user);
 
 /*
+ * Both ends on demand: as above (fill may be NULL: the records are there already), and `drain(user, b0, b1)` is called on
+ * the calling thread once the output records of blankets [b0, b1) are complete in out->out — per pipeline chunk, in
+ * order, each chunk exactly once: between two fills when a chunk happens to be back, and one by one after the last
+ * fill. A VertexRemover adapter splices chunk c into its graph (updateInputGraph, src/vertex_remover.cpp:500-546)
+ * while the GPU works on the chunks behind it, instead of waiting for the whole round (spg_graph_marginalize does; the
+ * blankets of a round commute, so splicing some while others are still being packed is safe as long as packing reads
+ * nothing but its own blanket). A nonzero return aborts with SPG_ERR_INVALID.
+ */
+typedef int32_t (*spg_drain_fn)(void *user, int32_t first_blanket, int32_t end_blanket);
+spg_status spg_remove_round_pipelined(spg_ctx *ctx, const spg_round_in *in, spg_round_out *out, spg_fill_fn fill, spg_drain_fn drain,
+                                      void *user);
+
+/*
  * Same, but every pointer inside in/out is a DEVICE pointer already resident in HBM
  * (rec_off/out_off too). Asynchronous on the context stream; call spg_sync().
  * The records cannot be validated from the host here: the caller states the largest blanket of the round

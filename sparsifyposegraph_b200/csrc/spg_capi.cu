@@ -265,13 +265,14 @@ spg_status spg_round_prepare(spg_ctx *ctx, const spg_round_in *in, spg_round_out
 namespace {
 // SPG_HOST_PROF=1: where the host time of the round calls goes (printed at exit)
 struct CapiProf {
-    double prepare = 0, fill = 0, validate = 0, bucket = 0, enqueue = 0, finish = 0;
+    double prepare = 0, fill = 0, validate = 0, bucket = 0, enqueue = 0, finish = 0, drain = 0;
     long long rounds = 0, chunks = 0;
     bool on = getenv("SPG_HOST_PROF") != nullptr;
     ~CapiProf() {
         if(on && rounds)
             fprintf(stderr, "[spg capi] %lld round calls, %lld chunks: prepare %.3f s, fill callback %.3f s, validate %.3f s, bucket %.3f s, "
-                            "copies + launches enqueued %.3f s, final wait %.3f s\n", rounds, chunks, prepare, fill, validate, bucket, enqueue, finish);
+                            "copies + launches enqueued %.3f s, drain callback incl. its waits %.3f s, final wait %.3f s\n", rounds, chunks, prepare, fill, validate, bucket, enqueue,
+                    drain, finish);
     }
 } g_cprof;
 inline double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
@@ -633,6 +634,11 @@ spg_status spg_remove_round(spg_ctx *ctx, const spg_round_in *in, spg_round_out 
 }
 
 spg_status spg_remove_round_streamed(spg_ctx *ctx, const spg_round_in *in, spg_round_out *out, spg_fill_fn fill, void *user) {
+    return spg_remove_round_pipelined(ctx, in, out, fill, nullptr, user);
+}
+
+spg_status spg_remove_round_pipelined(spg_ctx *ctx, const spg_round_in *in, spg_round_out *out, spg_fill_fn fill, spg_drain_fn drain,
+                                      void *user) {
     if(check_device(ctx) != SPG_OK) return SPG_ERR_INVALID;
     if(!in || !out || !out->out || (in->dim != 3 && in->dim != 6) || in->n_blankets < 0) {
         set_err("bad round descriptor");
@@ -663,7 +669,43 @@ spg_status spg_remove_round_streamed(spg_ctx *ctx, const spg_round_in *in, spg_r
     g_cprof.rounds++;
     spg_status st = spg_round_prepare(ctx, in, out, nchunks, run);
     if(st != SPG_OK) return st;
+    if(drain) // one more event per chunk: its output records have arrived on the host
+        while((int) ctx->ev_pool.size() < 3 * nchunks) {
+            cudaEvent_t e;
+            SPG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            ctx->ev_pool.push_back(e);
+        }
     g_cprof.prepare += now_s() - tp;
+    // chunks whose records are on their way back, in order; drained as their copies complete: between two fills when a
+    // copy happens to be done, after the last fill one by one (the host would only wait for the device otherwise)
+    std::vector<int> inflight;
+    size_t drained = 0;
+    auto drain_ready = [&](bool wait) -> spg_status {
+        while(drain && drained < inflight.size()) {
+            const int c = inflight[drained];
+            cudaEvent_t ev = ctx->ev_pool[2 * nchunks + c];
+            if(wait) SPG_CUDA(cudaEventSynchronize(ev));
+            else {
+                const cudaError_t q = cudaEventQuery(ev);
+                if(q == cudaErrorNotReady) {
+                    (void) cudaGetLastError(); // "not ready" is recorded as the thread's last error: clear it
+                    return SPG_OK;
+                }
+                SPG_CUDA(q);
+            }
+            const double td = now_s();
+            const int rc = drain(user, cb[c], cb[c + 1]);
+            g_cprof.drain += now_s() - td;
+            if(rc != 0) {
+                cudaDeviceSynchronize();
+                set_err("the record consumer of spg_remove_round_pipelined failed on blankets [" + std::to_string(cb[c]) + ", " +
+                        std::to_string(cb[c + 1]) + ")");
+                return SPG_ERR_INVALID;
+            }
+            drained++;
+        }
+        return SPG_OK;
+    };
     for(int c = 0; c < nchunks; c++) {
         const int b0 = cb[c], b1 = cb[c + 1];
         if(b1 <= b0) continue;
@@ -684,10 +726,19 @@ spg_status spg_remove_round_streamed(spg_ctx *ctx, const spg_round_in *in, spg_r
         const int64_t o0 = in->out_off[b0], o1 = in->out_off[b1];
         SPG_CUDA(cudaMemcpyAsync(out->out + o0, reinterpret_cast<uint64_t *>(ctx->d_out.p) + o0, (size_t) (o1 - o0) * 8,
                                  cudaMemcpyDeviceToHost, ctx->s_out));
+        if(drain) {
+            SPG_CUDA(cudaEventRecord(ctx->ev_pool[2 * nchunks + c], ctx->s_out));
+            inflight.push_back(c);
+            st = drain_ready(false);
+            if(st != SPG_OK) return st;
+        }
     }
     tp = now_s();
+    st = drain_ready(true);
+    if(st != SPG_OK) return st;
+    const double tdr = now_s() - tp;
     st = spg_round_finish(ctx, out, run);
-    g_cprof.finish += now_s() - tp;
+    g_cprof.finish += now_s() - tp - tdr;
     return st;
 }
 

@@ -881,6 +881,34 @@ static void parallelFor(size_t n, size_t min_per_thread, F fn) {
     });
 }
 
+// plain threads, not the worker pool: a remover may be destroyed when the pool is gone already (process exit)
+void UnitCache::reset(size_t n) {
+    auto spread = [](size_t count, auto fn) {
+        const unsigned nthr = count < 65536 ? 1u : std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+        if(nthr == 1) { fn((size_t) 0, count); return; }
+        std::vector<std::thread> th;
+        const size_t per = (count + nthr - 1) / nthr;
+        for(unsigned t = 0; t < nthr; t++) {
+            const size_t b0 = std::min(count, (size_t) t * per), b1 = std::min(count, b0 + per);
+            if(b0 < b1) th.emplace_back(fn, b0, b1);
+        }
+        for(auto &x : th) x.join();
+    };
+    if(_p) {
+        RemovalUnit *p = _p;
+        spread(_n, [p](size_t b0, size_t b1) { for(size_t i = b0; i < b1; i++) p[i].~RemovalUnit(); });
+        ::operator delete(static_cast<void *>(_p));
+        _p = nullptr;
+        _n = 0;
+    }
+    if(n) {
+        RemovalUnit *p = static_cast<RemovalUnit *>(::operator new(n * sizeof(RemovalUnit)));
+        spread(n, [p](size_t b0, size_t b1) { for(size_t i = b0; i < b1; i++) new(p + i) RemovalUnit(); });
+        _p = p;
+        _n = n;
+    }
+}
+
 namespace {
 struct HostProf {
     double stale = 0, extract = 0, select = 0, pack = 0, apply = 0;
@@ -935,27 +963,57 @@ std::vector<int> VertexRemover::remove(const std::vector<int> &toRemove, spg_sta
             // graph, get the complete output (all-gather) and splice the same edges
             st = spg_remove_round_sharded(_ctx, &rin, &rout, -1, nullptr);
         } else {
-            struct Fill {
+            // the substitute edges of the round need fresh blocks of the edge store (page faults, constructors): a helper
+            // thread prepares them while the GPU works; the records of every pipeline chunk are spliced as they arrive
+            // (the host is idle otherwise, waiting for the device at the end of the round)
+            struct Pipe {
                 VertexRemover *self;
-                static int32_t fn(void *u, int32_t b0, int32_t b1) {
-                    VertexRemover *vr = static_cast<Fill *>(u)->self;
+                const uint64_t *out;
+                std::thread grow;
+                double spliceS = 0;
+                static int32_t fill(void *u, int32_t b0, int32_t b1) {
+                    VertexRemover *vr = static_cast<Pipe *>(u)->self;
                     const double t = nowS();
                     const bool ok = vr->packRange((size_t) b0, (size_t) b1);
                     g_prof.pack += nowS() - t;
                     if(!ok) vr->_packFailed = true;
                     return ok ? 0 : 1;
                 }
-            } fill{this};
+                static int32_t drain(void *u, int32_t b0, int32_t b1) {
+                    Pipe *p = static_cast<Pipe *>(u);
+                    const double t = nowS();
+                    if(p->grow.joinable()) p->grow.join();
+                    p->self->applyRange(p->out, (size_t) b0, (size_t) b1);
+                    p->spliceS += nowS() - t;
+                    return 0;
+                }
+            } pipe{this, out, {}, 0};
             _packFailed = false;
-            // the substitute edges of the round need fresh blocks of the edge store (page faults, constructors): a helper
-            // thread prepares them while the GPU works
-            std::thread grow([this] { _graph->edges.reserve(_graph->edges.size() + (size_t) _round.maxNewEdges); });
-            st = spg_remove_round_streamed(_ctx, &rin, &rout, &Fill::fn, &fill);
-            grow.join();
-            if(_packFailed) { // `error` names the reason (packRange); nothing of this round was applied
+            applyBegin();
+            static const bool no_drain = getenv("SPG_NO_CHUNKED_SPLICE") != nullptr;
+            pipe.grow = std::thread([this] {
+                _graph->edges.reserve((size_t) _apply.e0 + (size_t) _apply.base.back(), [](GraphEdge &e) { e.alive = false; });
+            });
+            st = spg_remove_round_pipelined(_ctx, &rin, &rout, &Pipe::fill, no_drain ? nullptr : &Pipe::drain, &pipe);
+            if(pipe.grow.joinable()) pipe.grow.join();
+            if(_packFailed) { // `error` names the reason (packRange); chunks spliced before it stay spliced
+                if(_apply.spliced) applyEnd();
                 st = SPG_ERR_UNSUPPORTED;
                 break;
             }
+            if(st != SPG_OK) {
+                error = spg_last_error();
+                if(_apply.spliced) applyEnd();
+                break;
+            }
+            auto t2 = clk::now();
+            if(_apply.spliced < _round.sel.size()) applyRange(out, _apply.spliced, _round.sel.size());
+            applyEnd();
+            auto t3 = clk::now();
+            stats.pack_ms += std::chrono::duration<double, std::milli>(t1 - t0).count();
+            stats.gpu_ms += std::chrono::duration<double, std::milli>(t2 - t1).count() - 1e3 * pipe.spliceS;
+            stats.splice_ms += std::chrono::duration<double, std::milli>(t3 - t2).count() + 1e3 * pipe.spliceS;
+            continue;
         }
         if(st != SPG_OK) {
             error = spg_last_error();
@@ -1009,7 +1067,7 @@ spg_status VertexRemover::beginRemoval(const std::vector<int> &toRemove) {
     _round.sel.clear();
     _round.recOff.assign(1, 0);
     _round.outOff.assign(1, 0);
-    _unitCache.assign(toRemove.size(), RemovalUnit());
+    _unitCache.reset(toRemove.size());
     _unitBuilt.assign(toRemove.size(), 0);
     _rootIdx.assign(toRemove.size(), -1);
     _extended = _opts.topology == SparsityOptions::Dense || _opts.topology == SparsityOptions::CliqueyDense;
@@ -1025,8 +1083,7 @@ spg_status VertexRemover::beginRemoval(const std::vector<int> &toRemove) {
         }
     }
     _stamp.assign(_graph->verts.size(), 0);
-    _touchHead.assign(_graph->verts.size(), -1);
-    _removedBy.assign(_graph->verts.size(), -1);
+    _vtouch.assign(_graph->verts.size(), VTouch());
     _planNo = 0;
     return SPG_OK;
 }
@@ -1069,7 +1126,7 @@ spg_status VertexRemover::planRound(bool packNow) {
     const int Vn = (int) _graph->verts.size();
     _planNo++;
     if((int) _stamp.size() < Vn) _stamp.resize(Vn, 0);
-    if((int) _touchHead.size() < Vn) { _touchHead.resize(Vn, -1); _removedBy.resize(Vn, -1); }
+    if((int) _vtouch.size() < Vn) _vtouch.resize(Vn);
 
     // ---- window: the deferred units (list order) and then fresh list entries ---------------------------------------
     const size_t W = _window ? _window : std::max<size_t>(32768, _remaining / 12);
@@ -1141,8 +1198,7 @@ spg_status VertexRemover::planRound(bool packNow) {
     // ---- select (sequential: the decision for a unit depends on every earlier unit of the window) -----------------
     {
         std::vector<int> &sel = _round.sel;
-        _touchNext.clear();
-        _touchRegion.clear();
+        _touchNodes.clear();
         std::vector<int> touched;   // vertex indices whose per-round lists must be reset
         std::vector<int> parent;    // union-find over region ids
         parent.reserve(win.size());
@@ -1152,29 +1208,29 @@ spg_status VertexRemover::planRound(bool packNow) {
         _leftover.clear();
         for(size_t wq = 0; wq < win.size(); wq++) {
             const int i = win[wq];
-            // the loop is a chain of dependent cache misses (unit -> per-vertex touch heads): fetch the unit three entries
-            // ahead and the touch heads of the next one
-            if(wq + 3 < win.size()) { // (the index lists are stored inside the unit: four cache lines)
-                const char *pu = reinterpret_cast<const char *>(&_unitCache[win[wq + 3]]);
+            // the loop is a chain of dependent cache misses (unit -> per-vertex touch heads): fetch the unit eight entries
+            // ahead and the touch heads three ahead
+            if(wq + 8 < win.size()) { // (the index lists are stored inside the unit: four cache lines)
+                const char *pu = reinterpret_cast<const char *>(&_unitCache[win[wq + 8]]);
                 for(size_t l = 0; l < sizeof(RemovalUnit); l += 64) __builtin_prefetch(pu + l);
             }
-            if(wq + 1 < win.size()) {
-                const RemovalUnit &n1 = _unitCache[win[wq + 1]];
-                for(int xi : n1.ridx) { __builtin_prefetch(&_touchHead[xi]); __builtin_prefetch(&_removedBy[xi]); }
-                for(int xi : n1.kidx) { __builtin_prefetch(&_touchHead[xi]); __builtin_prefetch(&_removedBy[xi]); }
+            if(wq + 3 < win.size()) {
+                const RemovalUnit &n1 = _unitCache[win[wq + 3]];
+                for(int xi : n1.ridx) __builtin_prefetch(&_vtouch[xi]);
+                for(int xi : n1.kidx) __builtin_prefetch(&_vtouch[xi]);
             }
             const RemovalUnit &u = _unitCache[i];
             hit.clear();
             shared.clear();
             auto note = [&](int c) { if(std::find(hit.begin(), hit.end(), c) == hit.end()) hit.push_back(c); };
             for(int xi : u.ridx) {
-                for(int t = _touchHead[xi]; t >= 0; t = _touchNext[t]) note(find(_touchRegion[t]));
+                for(int t = _vtouch[xi].head; t >= 0; t = _touchNodes[t].next) note(find(_touchNodes[t].region));
             }
             for(int xi : u.kidx) {
-                if(_removedBy[xi] >= 0) note(find(_removedBy[xi]));
+                if(_vtouch[xi].removedBy >= 0) note(find(_vtouch[xi].removedBy));
                 comps.clear();
-                for(int t = _touchHead[xi]; t >= 0; t = _touchNext[t]) {
-                    const int c = find(_touchRegion[t]);
+                for(int t = _vtouch[xi].head; t >= 0; t = _touchNodes[t].next) {
+                    const int c = find(_touchNodes[t].region);
                     if(std::find(comps.begin(), comps.end(), c) == comps.end()) comps.push_back(c);
                 }
                 for(int c : comps) {
@@ -1188,18 +1244,18 @@ spg_status VertexRemover::planRound(bool packNow) {
             const bool select = hit.empty();
             for(int c : hit) parent[find(c)] = rid;
             auto reg = [&](int xi, bool removed) {
-                if(_touchHead[xi] < 0 && _removedBy[xi] < 0) touched.push_back(xi);
-                _touchNext.push_back(_touchHead[xi]);
-                _touchRegion.push_back(rid);
-                _touchHead[xi] = (int) _touchNext.size() - 1;
-                if(removed) _removedBy[xi] = rid;
+                VTouch &vt = _vtouch[xi];
+                if(vt.head < 0 && vt.removedBy < 0) touched.push_back(xi);
+                _touchNodes.push_back(TouchNode{vt.head, rid});
+                vt.head = (int) _touchNodes.size() - 1;
+                if(removed) vt.removedBy = rid;
             };
             for(int xi : u.ridx) reg(xi, true);
             for(int xi : u.kidx) reg(xi, false);
             if(select) sel.push_back(i);
             else _leftover.push_back(i);
         }
-        for(int xi : touched) { _touchHead[xi] = -1; _removedBy[xi] = -1; }
+        for(int xi : touched) _vtouch[xi] = VTouch();
         g_prof.select += nowS() - tp0; tp0 = nowS();
         if(sel.empty()) return SPG_OK;
     }
@@ -1323,97 +1379,133 @@ bool VertexRemover::packRange(size_t q0, size_t q1) {
 }
 
 // Splice the output records of the planned round, in list order (updateInputGraph,
-// src/vertex_remover.cpp:500-546).
+// src/vertex_remover.cpp:500-546). Three steps, so that the units of a round can be spliced range by range while the
+// GPU still works on the rest of the round (remove() drains every pipeline chunk as its records arrive):
+//   applyBegin  — edge-store slots of every unit's substitutes from the providers' upper bounds (prefix sum);
+//   applyRange  — units [q0, q1): status and staleness bookkeeping, blanket edges and removed vertices die, substitutes
+//                 are built in their slots, adjacency of the kept vertices;
+//   applyEnd    — counters, the list of added edges.
+// Slots a unit does not use (failed blanket, GLC factors of rank 0) stay dead edges.
 void VertexRemover::applyRound(const uint64_t *out) {
+    applyBegin();
+    const size_t ns = _round.sel.size();
+    // test hook: SPG_SPLICE_RANGES=k splices the round in k ranges, like the pipelined path does per chunk
+    size_t parts = 1;
+    if(const char *e = getenv("SPG_SPLICE_RANGES")) parts = (size_t) std::max(1, atoi(e));
+    for(size_t pi = 0; pi < parts; pi++) applyRange(out, ns * pi / parts, ns * (pi + 1) / parts);
+    applyEnd();
+}
+
+void VertexRemover::applyBegin() {
+    const double ta0 = nowS();
+    const std::vector<int> &sel = _round.sel;
+    const size_t ns = sel.size();
+    ApplyState &A = _apply;
+    A.base.assign(ns + 1, 0);
+    A.used.assign(ns, 0);
+    A.okUnit.assign(ns, 0);
+    A.removedEdges = 0;
+    A.removedVerts = 0;
+    A.sized = false;
+    A.spliced = 0;
+    parallelFor(ns, 4096, [&](size_t q0, size_t q1) {
+        for(size_t ui = q0; ui < q1; ui++)
+            A.base[ui + 1] = spgr_out_edge_count(_round.algorithm, _opts.topology, _opts.chordRatio, (int) _unitCache[sel[ui]].kept.size());
+    });
+    for(size_t ui = 0; ui < ns; ui++) A.base[ui + 1] += A.base[ui];
+    A.e0 = (int) _graph->edges.size();
+    g_prof.a1 += nowS() - ta0;
+    g_prof.apply += nowS() - ta0;
+}
+
+// the slots of the round's substitutes: blocks prepared ahead (remove(): helper thread) or here; every slot starts dead
+void VertexRemover::applySizeEdgeStore() {
+    ApplyState &A = _apply;
+    if(A.sized) return;
+    ChunkedVector<GraphEdge> &E = _graph->edges;
+    const size_t end = (size_t) A.e0 + (size_t) A.base.back();
+    E.reserve(end, [](GraphEdge &e) { e.alive = false; });
+    E.resize(end);
+    // slots in the block that was in use already were constructed alive
+    for(size_t i = (size_t) A.e0; i < end && i < E.blockEnd((size_t) A.e0); i++) E[i].alive = false;
+    A.sized = true;
+}
+
+void VertexRemover::applyRange(const uint64_t *out, size_t r0, size_t r1) {
+    if(r1 <= r0) return;
     const int dim = _graph->dim, P = _graph->poseWords(), algorithm = _round.algorithm;
     const bool cliquey = _opts.topology == SparsityOptions::CliqueySubgraph || _opts.topology == SparsityOptions::CliqueyDense;
     const double ta0 = nowS();
     const std::vector<int> &sel = _round.sel;
-    const size_t ns = sel.size();
     std::vector<GraphVertex> &V = _graph->verts;
     ChunkedVector<GraphEdge> &E = _graph->edges;
+    ApplyState &A = _apply;
+    applySizeEdgeStore();
+    const std::vector<int> &base = A.base;
+    std::vector<char> &okUnit = A.okUnit;
+    const int e0 = A.e0;
+    const size_t nr = r1 - r0;
 
-    // ---- pass 1 (headers only): staleness stamps and the number of substitutes per unit by the host threads, then
-    // the sequential part — status bookkeeping in list order and the edge indices of the substitutes (a prefix sum) ----
-    std::vector<int> base(ns + 1, 0); // new edges of unit ui go to E[e0 + base[ui] ...); failed units add none
-    std::vector<char> okUnit(ns, 0);
-    int removedEdges = 0, removedVerts = 0;
-    std::atomic<int> droppedA(0);
-    parallelFor(ns, 2048, [&](size_t q0, size_t q1) {
-        int dropped = 0;
-        for(size_t ui = q0; ui < q1; ui++) {
-            if(ui + 2 < q1) {
+    // ---- pass 1 (headers only, host threads): status, staleness stamps ---------------------------------------------
+    std::atomic<int> failedA(0), firstBad(-1);
+    parallelFor(nr, 2048, [&](size_t q0, size_t q1) {
+        for(size_t ui = r0 + q0; ui < r0 + q1; ui++) {
+            if(ui + 2 < r0 + q1) {
                 __builtin_prefetch(out + _round.outOff[ui + 2]);
                 __builtin_prefetch(&_unitCache[sel[ui + 2]]);
             }
             const RemovalUnit &u = _unitCache[sel[ui]];
-            const uint64_t *o = out + _round.outOff[ui];
-            const int32_t *oh = reinterpret_cast<const int32_t *>(o);
-            const int bstatus = oh[0], nnew = oh[1];
+            const int32_t *oh = reinterpret_cast<const int32_t *>(out + _round.outOff[ui]);
             _done[u.listIndex] = 1; // (one byte per list entry, every entry belongs to one unit)
-            if(bstatus != SPG_BLANKET_OK) continue;
+            if(oh[0] != SPG_BLANKET_OK) {
+                failedA++;
+                int cur = firstBad.load();
+                while((cur < 0 || (int) ui < cur) && !firstBad.compare_exchange_weak(cur, (int) ui)) {}
+                continue;
+            }
             okUnit[ui] = 1;
             // cached blankets containing these vertices are stale; two units of a round may share a kept vertex and then
             // store the same value
             for(int xi : u.ridx) __atomic_store_n(&_stamp[xi], _planNo, __ATOMIC_RELAXED);
             for(int xi : u.kidx) __atomic_store_n(&_stamp[xi], _planNo, __ATOMIC_RELAXED);
-            int cnt = nnew;
-            if(algorithm == SPG_ALG_GLC) { // getEdge returned NULL for rank-0 factors (src/topology_provider_glc.cpp:85-89)
-                const int64_t slot = spgr_out_slot_words(dim, algorithm, _opts.topology, (int) u.kept.size());
-                cnt = 0;
-                for(int e = 0; e < nnew; e++)
-                    cnt += reinterpret_cast<const int32_t *>(o + SPG_OUT_HEADER_WORDS + (int64_t) e * slot)[1] != 0;
-                dropped += nnew - cnt;
-            }
-            base[ui + 1] = cnt;
         }
-        droppedA += dropped;
     });
-    stats.n_dropped_edges += droppedA.load();
-    _remaining -= (int) ns;
-    for(size_t ui = 0; ui < ns; ui++) {
-        if(!okUnit[ui]) {
-            // The reference asserts / exits here. The blanket is left in the graph untouched (vertex, edges, no
-            // substitutes); the units of a round commute, so the others are unaffected. The call reports
-            // SPG_ERR_BLANKET_FAILED with the first failing list index.
-            const RemovalUnit &u = _unitCache[sel[ui]];
-            if(stats.n_failed++ == 0) {
-                stats.first_failed_index = u.listIndex;
-                stats.first_failed_status = reinterpret_cast<const int32_t *>(out + _round.outOff[ui])[0];
-            }
-            if(!_toRemoveSet.empty())
-                for(int id : u.removed) _toRemoveSet.erase(id);
-            base[ui + 1] = base[ui];
-            continue;
+    _remaining -= nr;
+    if(failedA.load()) {
+        // The reference asserts / exits here. A failed blanket is left in the graph untouched (vertex, edges, no
+        // substitutes); the units of a round commute, so the others are unaffected. The call reports
+        // SPG_ERR_BLANKET_FAILED with the first failing list index.
+        const int fb = firstBad.load();
+        if(stats.n_failed == 0) { // (ranges are spliced in list order: the first one seen is the first of the call)
+            stats.first_failed_index = _unitCache[sel[fb]].listIndex;
+            stats.first_failed_status = reinterpret_cast<const int32_t *>(out + _round.outOff[fb])[0];
         }
-        base[ui + 1] += base[ui];
-        stats.n_blankets++;
-        const int nr = !_extended ? 1 : (int) _unitCache[sel[ui]].removed.size(); // (single-removal topologies: no cache miss here)
-        stats.n_applied += nr;
-        removedVerts += nr;
+        stats.n_failed += failedA.load();
+        if(!_toRemoveSet.empty())
+            for(size_t ui = r0; ui < r1; ui++)
+                if(!okUnit[ui])
+                    for(int id : _unitCache[sel[ui]].removed) _toRemoveSet.erase(id);
     }
-    const int e0 = (int) E.size();
-    E.resize((size_t) e0 + base[ns]);
     double tq = nowS();
     g_prof.a1 += tq - ta0;
 
     // ---- pass 2 (parallel over units; blankets of a round share no edge and no removed vertex): blanket edges and
     // removed vertices die, the substitute edges are built in place --------------------------------------------------
-    std::atomic<int> removedEdgesA(0);
+    std::atomic<int> removedEdgesA(0), removedVertsA(0), droppedA(0), blanketsA(0);
     std::mutex garbageMx;
     std::vector<std::vector<double>> garbage; // payload blocks nobody took over: freed off the critical path
-    parallelFor(ns, 256, [&](size_t q0, size_t q1) {
-        int dead = 0;
+    parallelFor(nr, 256, [&](size_t q0, size_t q1) {
+        int dead = 0, deadV = 0, dropped = 0, nblk = 0;
         std::vector<int> spare;
         std::vector<std::vector<double>> mine;
-        for(size_t ui = q0; ui < q1; ui++) {
+        for(size_t ui = r0 + q0; ui < r0 + q1; ui++) {
             // dependent cache misses again (unit -> edge list -> edges -> payload blocks): three, two and one units ahead
-            if(ui + 3 < q1) {
+            if(ui + 3 < r0 + q1) {
                 const char *pu = reinterpret_cast<const char *>(&_unitCache[sel[ui + 3]]);
                 for(size_t l = 0; l < sizeof(RemovalUnit); l += 64) __builtin_prefetch(pu + l);
             }
-            if(ui + 2 < q1) __builtin_prefetch(_unitCache[sel[ui + 2]].edges.data());
-            if(ui + 1 < q1) {
+            if(ui + 2 < r0 + q1) __builtin_prefetch(_unitCache[sel[ui + 2]].edges.data());
+            if(ui + 1 < r0 + q1) {
                 const RemovalUnit &nx = _unitCache[sel[ui + 1]];
                 for(int ei : nx.edges) __builtin_prefetch(&E[ei]);
                 for(int xi : nx.ridx) __builtin_prefetch(&V[xi]);
@@ -1421,6 +1513,8 @@ void VertexRemover::applyRound(const uint64_t *out) {
             }
             if(!okUnit[ui]) continue;
             const RemovalUnit &u = _unitCache[sel[ui]];
+            nblk++;
+            deadV += (int) u.removed.size();
             spare.clear();
             auto kill = [&](int ei) {
                 GraphEdge &e = E[ei];
@@ -1518,36 +1612,45 @@ void VertexRemover::applyRound(const uint64_t *out) {
                         for(int q = 0; q < dim * nve; q++) gi[(size_t) r * dim * nve + q] = W[(size_t) r * c + q];
                 }
             }
+            A.used[ui] = minor;
+            dropped += nnew - minor; // GLC: getEdge returned NULL for rank-0 factors (src/topology_provider_glc.cpp:85-89)
             for(int ei : spare) mine.emplace_back(std::move(E[ei].payload));
         }
         removedEdgesA += dead;
+        removedVertsA += deadV;
+        droppedA += dropped;
+        blanketsA += nblk;
         std::lock_guard<std::mutex> lk(garbageMx);
         for(auto &g : mine) garbage.emplace_back(std::move(g));
     });
     if(garbage.size() > 4096) std::thread([g = std::move(garbage)]() mutable { g.clear(); }).detach();
-    removedEdges = removedEdgesA.load();
+    A.removedEdges += removedEdgesA.load();
+    A.removedVerts += removedVertsA.load();
+    stats.n_dropped_edges += droppedA.load();
+    stats.n_blankets += blanketsA.load();
+    stats.n_applied += removedVertsA.load();
     g_prof.a2 += nowS() - tq; tq = nowS();
 
     // ---- pass 3 (parallel over units, one byte lock per vertex: two blankets of a round may share one kept vertex):
     // adjacency of the kept vertices — dead edges out, substitutes in. The order inside an adjacency list carries no
     // meaning (every consumer sorts by the canonical edge key).
     if(_vlock.size() < V.size()) _vlock = std::vector<std::atomic<unsigned char>>(V.size() + V.size() / 4 + 64);
-    parallelFor(ns, 256, [&](size_t q0, size_t q1) {
-        for(size_t ui = q0; ui < q1; ui++) {
-            if(ui + 3 < q1) {
+    parallelFor(nr, 256, [&](size_t q0, size_t q1) {
+        for(size_t ui = r0 + q0; ui < r0 + q1; ui++) {
+            if(ui + 3 < r0 + q1) {
                 const char *pu = reinterpret_cast<const char *>(&_unitCache[sel[ui + 3]]);
                 for(size_t l = 0; l < sizeof(RemovalUnit); l += 64) __builtin_prefetch(pu + l);
             }
-            if(ui + 2 < q1)
+            if(ui + 2 < r0 + q1)
                 for(int xi : _unitCache[sel[ui + 2]].kidx) __builtin_prefetch(&V[xi]);
-            if(ui + 1 < q1)
+            if(ui + 1 < r0 + q1)
                 for(int xi : _unitCache[sel[ui + 1]].kidx) { // (a racing writer may be resizing these: only a hint)
                     __builtin_prefetch(V[xi].edges.data());
                     __builtin_prefetch(V[xi].peer.data());
                 }
             if(!okUnit[ui]) continue;
             const RemovalUnit &u = _unitCache[sel[ui]];
-            const int nb0 = e0 + base[ui], nb1 = e0 + base[ui + 1];
+            const int nb0 = e0 + base[ui], nb1 = nb0 + A.used[ui];
             for(int xi : u.kidx) {
                 std::atomic<unsigned char> &lk = _vlock[xi];
                 while(lk.exchange(1, std::memory_order_acquire)) { /* spin: held for a few dozen instructions */ }
@@ -1572,10 +1675,22 @@ void VertexRemover::applyRound(const uint64_t *out) {
         }
     });
     g_prof.a3 += nowS() - tq;
-    for(int k = 0; k < base[ns]; k++) _added.push_back(e0 + k);
+    A.spliced += nr;
+    g_prof.apply += nowS() - ta0;
+}
+
+void VertexRemover::applyEnd() {
+    const double ta0 = nowS();
+    ApplyState &A = _apply;
+    const size_t ns = _round.sel.size();
+    int added = 0;
+    for(size_t ui = 0; ui < ns; ui++) {
+        for(int k = 0; k < A.used[ui]; k++) _added.push_back(A.e0 + A.base[ui] + k);
+        added += A.used[ui];
+    }
     _graph->version++;
-    _graph->aliveEdges += base[ns] - removedEdges;
-    _graph->aliveVertices -= removedVerts;
+    _graph->aliveEdges += added - A.removedEdges;
+    _graph->aliveVertices -= A.removedVerts;
     stats.n_rounds++;
     stats.max_round_width = std::max<int>(stats.max_round_width, (int) ns);
     _round.sel.clear();

@@ -118,12 +118,18 @@ public:
     T &operator[](size_t i) { return _blocks[i >> LOG2][i & MASK]; }
     const T &operator[](size_t i) const { return _blocks[i >> LOG2][i & MASK]; }
     T &back() { return (*this)[_n - 1]; }
-    void reserve(size_t n) { // blocks (default-constructed elements) for n elements; size() unchanged
+    void reserve(size_t n) { reserve(n, [](T &) {}); }
+    // blocks for n elements (size() unchanged); every element of a NEW block is default-constructed, then init(element)
+    template <class F>
+    void reserve(size_t n, F init) {
         while((_nb << LOG2) < n && _nb < MAXB) {
-            _blocks[_nb] = new T[(size_t) 1 << LOG2];
+            T *b = new T[(size_t) 1 << LOG2];
+            for(size_t i = 0; i < ((size_t) 1 << LOG2); i++) init(b[i]);
+            _blocks[_nb] = b;
             _nb++;
         }
     }
+    size_t blockEnd(size_t i) const { return ((i >> LOG2) + 1) << LOG2; } // first index behind the block of element i
     void resize(size_t n) { // grow only
         reserve(n);
         if(n > _n) _n = n;
@@ -258,6 +264,23 @@ struct RemovalUnit {
     InlineInts<20> kidx;
 };
 
+// the cached blankets of a removal list: a million units with three heap vectors each are constructed (first touch of
+// ~0.2 GB) and destroyed (millions of frees) by a few threads instead of one
+class UnitCache {
+public:
+    UnitCache() {}
+    UnitCache(const UnitCache &) = delete;
+    UnitCache &operator=(const UnitCache &) = delete;
+    ~UnitCache() { reset(0); }
+    void reset(size_t n); // destroys the old units, default-constructs n new ones
+    RemovalUnit &operator[](size_t i) { return _p[i]; }
+    const RemovalUnit &operator[](size_t i) const { return _p[i]; }
+    size_t size() const { return _n; }
+private:
+    RemovalUnit *_p = nullptr;
+    size_t _n = 0;
+};
+
 // growable host buffer of 8-byte words: page-locked when a CUDA device is present, plain memory otherwise
 struct HostBuf {
     uint64_t *p = nullptr;
@@ -309,6 +332,10 @@ public:
     bool packRange(size_t q0, size_t q1); // pack the selected units [q0, q1) of the planned round (planRound(false))
     spg_round_in roundDescriptor() const;
     void applyRound(const uint64_t *out);
+    // the same in steps (remove() splices every pipeline chunk as its records arrive, see spg_host.cpp)
+    void applyBegin();
+    void applyRange(const uint64_t *out, size_t q0, size_t q1);
+    void applyEnd();
     spg_status failureStatus(); // SPG_OK, or SPG_ERR_BLANKET_FAILED (+ error text) once a blanket failed
 
     spg_marginalize_stats stats{};
@@ -323,16 +350,30 @@ private:
     spg_status localLinearise(const RemovalUnit &u, std::vector<double> &poses) const;
 
     Round _round;
+    struct ApplyState {              // splice of the round in flight (applyBegin .. applyEnd)
+        std::vector<int> base;       // substitutes of unit ui go to edges[e0 + base[ui] ...): slots by the provider's upper bound
+        std::vector<int> used;       // how many of its slots the unit filled
+        std::vector<char> okUnit;
+        int e0 = 0, removedEdges = 0, removedVerts = 0;
+        size_t spliced = 0;
+        bool sized = false;          // the edge store holds the round's slots
+    } _apply;
+    void applySizeEdgeStore();
     std::vector<int> _pending, _added;
     std::set<int> _toRemoveSet;
     std::vector<char> _done;
     size_t _remaining = 0;
     // scheduler state: cached blankets of the pending vertices (re-extracted when stale) and per-round scratch
-    std::vector<RemovalUnit> _unitCache;
+    UnitCache _unitCache;
     std::vector<int> _rootIdx;              // Graph::verts index of every list entry (-1: not in the graph)
     std::vector<int> _unitBuilt;            // planning pass that extracted the cached blanket (0: never)
     std::vector<int> _stamp;                // per vertex index: last planning pass whose round touched it
-    std::vector<int> _touchHead, _touchNext, _touchRegion, _removedBy;
+    // selection scratch. Per vertex (one cache line for both): head of its list of touching regions of this round, and
+    // the region that removes it; the list nodes (next, region) side by side as well
+    struct VTouch { int head = -1, removedBy = -1; };
+    struct TouchNode { int next, region; };
+    std::vector<VTouch> _vtouch;
+    std::vector<TouchNode> _touchNodes;
     int _planNo = 0;
     // the window a round is drawn from: units deferred by earlier rounds (list order) + fresh entries from _cursor on
     std::vector<int> _leftover;

@@ -160,3 +160,66 @@ def test_round_scheduler_parallel_passes_equal_single_thread(oracle, monkeypatch
     assert widest >= 2048
     assert o.marginalize(which, oracle.make_opts(R.TOPO_TREE, R.LIN_GLOBAL), R.ALG_NFR) == 0
     compare_graphs(g, o, tol=1e-9)
+
+
+@pytest.mark.parametrize("ranges", [3, 64])
+def test_round_spliced_in_ranges_equals_sequential_removal(oracle, ranges, monkeypatch):
+    """remove() splices every pipeline chunk of a round as its records arrive (applyBegin / applyRange / applyEnd,
+    spg_remove_round_pipelined). SPG_SPLICE_RANGES cuts the splice of a CPU-driven round the same way: the final graph
+    must still be the one of the one-at-a-time loop."""
+    from sparsifyposegraph_b200 import capi, synth, records as R
+    from test_gpu_graph import compare_graphs
+    monkeypatch.setenv("SPG_SPLICE_RANGES", str(ranges))
+    rows, cols = 40, 44
+    data = synth.make_grid_graph(rows, cols, dim=6)
+    g = synth.fill_graph(capi.Graph(dim=6), *data)
+    o = synth.fill_graph(oracle.Graph(dim=6), *data)
+    which = synth.grid_removal_order(rows, cols, 10, 4, "random")
+    opts = capi.make_opts(R.TOPO_TREE, R.LIN_GLOBAL)
+    capi.rounds_begin(g, which, opts, R.ALG_NFR)
+    widest = 0
+    while True:
+        rd = capi.round_next(g)
+        if rd is None:
+            break
+        widest = max(widest, rd["n"])
+        out = oracle.remove_round(rd["dim"], rd["algorithm"], oracle.make_opts(R.TOPO_TREE, R.LIN_GLOBAL), rd["records"],
+                                  rd["rec_off"], rd["out_off"], 0)[0]
+        capi.round_apply(g, out)
+    assert widest > ranges
+    assert o.marginalize(which, oracle.make_opts(R.TOPO_TREE, R.LIN_GLOBAL), R.ALG_NFR) == 0
+    compare_graphs(g, o, tol=1e-9)
+    assert g.num_edges == o.num_edges and g.num_vertices == o.num_vertices
+
+
+def test_failed_blanket_in_a_ranged_splice_keeps_its_slots_dead(oracle, monkeypatch):
+    """The substitutes of a round get their edge-store slots from the providers' upper bounds before any record is read:
+    a blanket that comes back failed must leave its vertex and edges in place and its slots dead (not counted, not
+    listed), whatever range it falls into."""
+    from sparsifyposegraph_b200 import capi, synth, records as R
+    monkeypatch.setenv("SPG_SPLICE_RANGES", "4")
+    rows, cols = 12, 12
+    data = synth.make_grid_graph(rows, cols, dim=6)
+    g = synth.fill_graph(capi.Graph(dim=6), *data)
+    which = synth.grid_removal_order(rows, cols, 10, 4, "random")
+    opts = capi.make_opts(R.TOPO_TREE, R.LIN_GLOBAL)
+    capi.rounds_begin(g, which, opts, R.ALG_NFR)
+    rd = capi.round_next(g)
+    assert rd["n"] >= 8
+    out = oracle.remove_round(rd["dim"], rd["algorithm"], oracle.make_opts(R.TOPO_TREE, R.LIN_GLOBAL), rd["records"],
+                              rd["rec_off"], rd["out_off"], 0)[0]
+    victim = 5
+    nv0, ne0 = g.num_vertices, g.num_edges
+    i32 = out.view(np.int32)
+    new_edges = sum(int(i32[2 * int(rd["out_off"][b]) + 1]) for b in range(rd["n"]) if b != victim)
+    rec = rd["records"][int(rd["rec_off"][victim]):int(rd["rec_off"][victim + 1])]
+    victim_id = int(rec.view(np.int32)[2 * 4])          # first id of the record: the removed vertex
+    i32[2 * int(rd["out_off"][victim])] = 1               # NOT_PD_MARGINAL
+    with pytest.raises(capi.SpgError):                    # SPG_ERR_BLANKET_FAILED: reported, the other units are applied
+        capi.round_apply(g, out)
+    assert victim_id in list(g.vertex_ids())
+    assert g.num_vertices == nv0 - (rd["n"] - 1)
+    edges = g.edges()
+    assert len(edges) == g.num_edges
+    assert sum(1 for e in edges if e["uid"][0] >= 0) == new_edges
+    assert sum(1 for e in edges if victim_id in e["v"]) >= 2      # its blanket edges are still there

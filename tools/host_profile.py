@@ -35,7 +35,9 @@ def main():
     oopts = pyoracle.make_opts(R.TOPO_TREE, R.LIN_GLOBAL)
     L = capi.lib()
     capi._round_protos(L)
+    t0 = time.perf_counter()
     capi.rounds_begin(g, which, opts, R.ALG_NFR)
+    t_begin = time.perf_counter() - t0
     t_next = t_apply = t_dev = 0.0
     rounds = widest = 0
     while True:
@@ -58,7 +60,7 @@ def main():
         capi._check(L.spg_graph_round_apply(g.h, capi._p(out)))
         t_apply += time.perf_counter() - t0
     print(json.dumps({"grid": [args.rows, args.cols], "removed": int(len(which)), "rounds": rounds, "widest": widest,
-                      "plan_pack_s": t_next, "splice_s": t_apply, "host_s": t_next + t_apply,
+                      "begin_s": t_begin, "plan_pack_s": t_next, "splice_s": t_apply, "host_s": t_next + t_apply,
                       "host_vertices_per_s": len(which) / (t_next + t_apply), "oracle_standin_s": t_dev,
                       "host_threads": os.environ.get("SPG_HOST_THREADS", "default"), "cores": os.cpu_count()}))
 
