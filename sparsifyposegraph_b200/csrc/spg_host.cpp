@@ -662,10 +662,15 @@ bool VertexRemover::packUnit(const RemovalUnit &u, uint64_t *rec, int64_t words,
     const int nrem = (int) u.removed.size(), nv = nrem + (int) u.kept.size(), ne = (int) u.edges.size();
     const std::vector<GraphVertex> &V = _graph->verts;
     if(t_local.size() < V.size()) t_local.resize(V.size() + V.size() / 4 + 64, -1);
-    std::memset(rec, 0, (size_t) words * 8);
+    // every word of the record is written exactly once below (no memset of the whole record first: the records of a
+    // round are gigabytes); the padding slots of the int32 tables and the tail are zeroed explicitly
+    // (tests: SPG_POISON_RECORDS=1 fills the record with 0xFF first — the result must not change)
+    static const bool poison = getenv("SPG_POISON_RECORDS") != nullptr;
+    if(poison) std::memset(rec, 0xFF, (size_t) words * 8);
     int32_t *h = reinterpret_cast<int32_t *>(rec);
     h[0] = nv; h[1] = nrem; h[2] = ne; h[3] = dim; h[4] = (int32_t) words; h[5] = 0; h[6] = u.listIndex; h[7] = 0;
     int32_t *rid = reinterpret_cast<int32_t *>(rec + spgr_ids_off());
+    if(nv & 1) rid[nv] = 0;
     double *poses = reinterpret_cast<double *>(rec + spgr_poses_off(nv));
     for(int i = 0; i < nv; i++) {
         const int xi = i < nrem ? u.ridx[i] : u.kidx[i - nrem];
@@ -721,6 +726,7 @@ bool VertexRemover::packUnit(const RemovalUnit &u, uint64_t *rec, int64_t words,
     }
 
     int32_t *etab = reinterpret_cast<int32_t *>(rec + spgr_edgetab_off(dim, nv));
+    if(ne & 1) etab[ne] = 0;
     int64_t eoff = spgr_record_fixed_words(dim, nv, ne);
     // an edge costs two dependent cache misses (the edge, then its payload block on the heap): fetch the edges four
     // ahead and the payloads two ahead of the copy
@@ -743,6 +749,7 @@ bool VertexRemover::packUnit(const RemovalUnit &u, uint64_t *rec, int64_t words,
         eh[0] = e.kind; eh[1] = nve; eh[2] = e.rows; eh[3] = 0;
         int32_t *vi = reinterpret_cast<int32_t *>(ew + 2);
         for(int q = 0; q < nve; q++) vi[q] = t_local[e.vx(q)];
+        if(nve & 1) vi[nve] = 0;
         double *pl = reinterpret_cast<double *>(ew + 2 + spgr_pad2(nve));
         if(e.kind == SPG_EDGE_POSE) {
             std::memcpy(pl, e.meas(), sizeof(double) * P);
@@ -760,6 +767,7 @@ bool VertexRemover::packUnit(const RemovalUnit &u, uint64_t *rec, int64_t words,
         }
         eoff += spgr_edge_words(dim, e.kind, nve, e.rows);
     }
+    for(int64_t w = eoff; w < words; w++) rec[w] = 0; // (the record is rounded up to an even number of words)
     return true;
 }
 

@@ -223,3 +223,46 @@ def test_failed_blanket_in_a_ranged_splice_keeps_its_slots_dead(oracle, monkeypa
     assert len(edges) == g.num_edges
     assert sum(1 for e in edges if e["uid"][0] >= 0) == new_edges
     assert sum(1 for e in edges if victim_id in e["v"]) >= 2      # its blanket edges are still there
+
+
+def test_packed_records_have_no_unwritten_words(oracle):
+    """packUnit writes every word of a record exactly once (no memset of the whole round first). With
+    SPG_POISON_RECORDS=1 the staging memory is filled with 0xFF before each record is packed: the records of every round
+    — pose edges, GLC factors with one (odd: padded index table) and two vertices, odd vertex and edge counts — must be
+    bit-identical to the unpoisoned ones. Run in a child process: the switch is read once per process."""
+    import subprocess
+    import sys
+    code = r'''
+import hashlib, sys
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import numpy as np
+import datasets
+from oracle import pyoracle
+from sparsifyposegraph_b200 import capi, records as R
+h = hashlib.sha256()
+for alg, topo in ((R.ALG_GLC, R.TOPO_TREE), (R.ALG_NFR, R.TOPO_TREE)):
+    g = capi.Graph(datasets.path("intel"))
+    for sparsity in (3, 2):          # the second pass meets the factors the first one created
+        which = capi.decimate_global(g.max_vertex_id, g.max_vertex_id, sparsity)
+        which = [v for v in which if v in set(g.vertex_ids().tolist())]
+        capi.rounds_begin(g, which, capi.make_opts(topo, R.LIN_GLOBAL), alg)
+        while True:
+            rd = capi.round_next(g)
+            if rd is None:
+                break
+            h.update(rd["records"].tobytes())
+            out = pyoracle.remove_round(rd["dim"], rd["algorithm"], pyoracle.make_opts(topo, R.LIN_GLOBAL), rd["records"],
+                                        rd["rec_off"], rd["out_off"], 0)[0]
+            capi.round_apply(g, out)
+print(h.hexdigest())
+''' % (ROOT, os.path.join(ROOT, "tests"))
+    digests = []
+    for poison in (False, True):
+        env = dict(os.environ)
+        env.pop("SPG_POISON_RECORDS", None)
+        if poison:
+            env["SPG_POISON_RECORDS"] = "1"
+        res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+        assert res.returncode == 0, res.stderr[-2000:]
+        digests.append(res.stdout.strip().splitlines()[-1])
+    assert digests[0] == digests[1] and len(digests[0]) == 64
